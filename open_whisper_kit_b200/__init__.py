@@ -1,0 +1,43 @@
+"""open_whisper_kit_b200 -- B200-native (sm_100a) batched-transcription hot path behind the whisper.h C ABI.
+
+The product is the shared library lib/libwhisper.so (C++ host + hand-written CUDA).  This package only
+locates / builds it and binds the C ABI with ctypes.  There is no CPU fallback: if the library is missing or
+no CUDA device is visible, loading or the first compute call fails loudly.
+"""
+import ctypes as _C
+import os as _os
+
+from . import capi
+
+_HERE = _os.path.dirname(_os.path.abspath(__file__))
+LIB_PATH = _os.path.join(_HERE, "lib", "libwhisper.so")
+
+_FP = _C.POINTER(_C.c_float)
+_U16P = _C.POINTER(_C.c_uint16)
+_IP = _C.POINTER(_C.c_int)
+
+# extension entry points of include/whisper_b200.h
+EXT_PROTOTYPES = {
+    "whisper_b200_device_count": (_C.c_int, []),
+    "whisper_b200_kernel_log_mel": (_C.c_int, [_FP, _C.c_int, _FP, _C.c_int, _FP, _C.c_int, _IP, _IP]),
+    "whisper_b200_kernel_log_mel_bench": (_C.c_double, [_C.c_int, _C.c_int, _FP, _C.c_int, _C.c_int, _C.c_int]),
+    "whisper_b200_kernel_gemm": (_C.c_int, [_C.c_int, _C.c_int, _C.c_int, _C.c_int, _U16P, _U16P, _FP, _C.c_float,
+                                            _C.c_int, _C.c_int, _FP, _C.c_int, _FP, _U16P, _FP]),
+    "whisper_b200_kernel_gemm_bench": (_C.c_double, [_C.c_int, _C.c_int, _C.c_int, _C.c_int, _C.c_int, _C.c_int]),
+}
+
+_lib = None
+
+
+def load(strict_api=True):
+    """Load lib/libwhisper.so and bind whisper.h + whisper_b200.h.  Raises OSError if it was not built."""
+    global _lib
+    if _lib is None:
+        if not _os.path.exists(LIB_PATH):
+            raise OSError(f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(the CUDA extension is required; there is no CPU fallback)")
+        lib = _C.CDLL(LIB_PATH, mode=_C.RTLD_LOCAL)
+        capi.bind(lib, EXT_PROTOTYPES, strict=True)
+        capi.bind(lib, capi.PROTOTYPES, strict=strict_api)
+        _lib = lib
+    return _lib

@@ -1,0 +1,115 @@
+"""Thin object wrapper over the whisper.h C ABI (works on any library that exports it).
+
+Mirrors how the reference's own callers drive the API (examples/cli/cli.cpp:1039-1276,
+examples/bench/bench.cpp:63-165): init -> [pcm_to_mel -> encode -> decode] or full -> read segments.
+"""
+import ctypes as C
+import wave
+
+import numpy as np
+
+from . import capi
+
+
+def read_wav_f32(path):
+    """16-bit PCM mono/stereo 16 kHz WAV -> float32 mono in [-1, 1) (what examples/common-whisper.cpp:42-134 yields)."""
+    with wave.open(path, "rb") as w:
+        assert w.getsampwidth() == 2 and w.getframerate() == 16000
+        raw = np.frombuffer(w.readframes(w.getnframes()), dtype=np.int16)
+        if w.getnchannels() == 2:
+            raw = raw.reshape(-1, 2).astype(np.int32).sum(axis=1) // 2
+        return (raw.astype(np.float32) / 32768.0).astype(np.float32)
+
+
+class Segment:
+    def __init__(self, t0, t1, text, tokens, token_data, no_speech_prob):
+        self.t0, self.t1, self.text = t0, t1, text
+        self.tokens, self.token_data, self.no_speech_prob = tokens, token_data, no_speech_prob
+
+    def __repr__(self):
+        return f"Segment({self.t0},{self.t1},{self.text!r},{self.tokens})"
+
+
+class Whisper:
+    def __init__(self, lib, model_path, use_gpu=True, flash_attn=True, gpu_device=0):
+        self.lib = lib
+        cp = lib.whisper_context_default_params()
+        cp.use_gpu = use_gpu
+        cp.flash_attn = flash_attn
+        cp.gpu_device = gpu_device
+        self.ctx = lib.whisper_init_from_file_with_params(model_path.encode(), cp)
+        if not self.ctx:
+            raise RuntimeError(f"whisper_init_from_file_with_params failed for {model_path}")
+
+    def close(self):
+        if self.ctx:
+            self.lib.whisper_free(self.ctx)
+            self.ctx = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- low-level trio -------------------------------------------------------------------
+    def pcm_to_mel(self, pcm, n_threads=1):
+        pcm = np.ascontiguousarray(pcm, dtype=np.float32)
+        return self.lib.whisper_pcm_to_mel(self.ctx, capi.as_float_ptr(pcm), len(pcm), n_threads)
+
+    def set_mel(self, mel):
+        """mel: [n_mel][n_len] float32."""
+        mel = np.ascontiguousarray(mel, dtype=np.float32)
+        return self.lib.whisper_set_mel(self.ctx, capi.as_float_ptr(mel), mel.shape[1], mel.shape[0])
+
+    def encode(self, offset=0, n_threads=1):
+        return self.lib.whisper_encode(self.ctx, offset, n_threads)
+
+    def decode(self, tokens, n_past, n_threads=1):
+        arr = (C.c_int32 * len(tokens))(*tokens)
+        rc = self.lib.whisper_decode(self.ctx, arr, len(tokens), n_past, n_threads)
+        if rc != 0:
+            return rc, None
+        n_vocab = self.lib.whisper_n_vocab(self.ctx)
+        p = self.lib.whisper_get_logits(self.ctx)
+        # the reference exposes [n_tokens][n_vocab] with only the last row valid (src/whisper.cpp:2949-2955)
+        full = np.ctypeslib.as_array(p, shape=(len(tokens) * n_vocab,))
+        return rc, full[(len(tokens) - 1) * n_vocab:].copy()
+
+    # ---- whisper_full ---------------------------------------------------------------------
+    def default_params(self, strategy=capi.GREEDY):
+        return self.lib.whisper_full_default_params(strategy)
+
+    def greedy_params(self, no_timestamps=False, n_threads=1, language=b"en"):
+        """whisper-cli -bs 1 -bo 1 -nf: greedy, one decoder, no temperature fallback."""
+        p = self.default_params(capi.GREEDY)
+        p.greedy.best_of = 1
+        p.temperature_inc = 0.0
+        p.n_threads = n_threads
+        p.no_timestamps = no_timestamps
+        p.print_progress = False
+        p.language = language
+        return p
+
+    def full(self, params, pcm, n_processors=1):
+        pcm = np.ascontiguousarray(pcm, dtype=np.float32)
+        if n_processors == 1:
+            rc = self.lib.whisper_full(self.ctx, params, capi.as_float_ptr(pcm), len(pcm))
+        else:
+            rc = self.lib.whisper_full_parallel(self.ctx, params, capi.as_float_ptr(pcm), len(pcm), n_processors)
+        return rc, self.segments() if rc == 0 else []
+
+    def segments(self):
+        lib, ctx = self.lib, self.ctx
+        out = []
+        for i in range(lib.whisper_full_n_segments(ctx)):
+            n_tok = lib.whisper_full_n_tokens(ctx, i)
+            tds = [lib.whisper_full_get_token_data(ctx, i, j) for j in range(n_tok)]
+            out.append(Segment(lib.whisper_full_get_segment_t0(ctx, i), lib.whisper_full_get_segment_t1(ctx, i),
+                               lib.whisper_full_get_segment_text(ctx, i),
+                               [t.id for t in tds], tds,
+                               lib.whisper_full_get_segment_no_speech_prob(ctx, i)))
+        return out
+
+    def all_tokens(self):
+        return [t for s in self.segments() for t in s.tokens]

@@ -1,0 +1,64 @@
+// Shared device/host helpers for the sm_100a kernels of the batched transcription path.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace wb {
+
+// ---- error handling -------------------------------------------------------------------------------
+// No exception crosses the C ABI (reference contract, include/whisper.h: errors are return codes), so
+// CUDA failures are recorded, logged once and surfaced by the caller as the API's failure value.
+void cuda_fail(cudaError_t e, const char * expr, const char * file, int line);
+bool cuda_failed();            // sticky flag, per process
+void cuda_clear_failure();
+
+#define WB_CUDA(expr)                                                        \
+    do {                                                                     \
+        cudaError_t e__ = (expr);                                            \
+        if (e__ != cudaSuccess) ::wb::cuda_fail(e__, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+template <typename T> static inline T ceil_div(T a, T b) { return (a + b - 1) / b; }
+template <typename T> static inline T round_up(T a, T b) { return ceil_div(a, b) * b; }
+
+// ---- 16-bit operand type of the tensor path (f16 matches the reference's F16 weight files bit for
+// bit; bf16 is the alternative named by the spec).  Selected per context at load time. -----------------
+enum class DType : int { F16 = 0, BF16 = 1 };
+
+#ifdef __CUDACC__
+template <typename T> struct Half16;
+template <> struct Half16<__half> {
+    static __device__ __forceinline__ float to_f(__half v) { return __half2float(v); }
+    static __device__ __forceinline__ __half from_f(float v) { return __float2half_rn(v); }
+    static constexpr int kind = 0;
+};
+template <> struct Half16<__nv_bfloat16> {
+    static __device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+    static __device__ __forceinline__ __nv_bfloat16 from_f(float v) { return __float2bfloat16_rn(v); }
+    static constexpr int kind = 1;
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// GELU, tanh form, as ggml computes it (reference ggml/src/ggml-cpu/vec.h:  0.5*x*(1+tanh(sqrt(2/pi)*x*(1+0.044715*x*x))))
+__device__ __forceinline__ float gelu_tanh(float x) {
+    const float c = 0.79788456080286535587989211986876f;
+    const float a = 0.044715f;
+    return 0.5f * x * (1.0f + tanhf(c * x * (1.0f + a * x * x)));
+}
+#endif
+
+}  // namespace wb

@@ -1,0 +1,182 @@
+// C-ABI entry points that expose single kernels of the path (declared in include/whisper_b200.h).
+// They take HOST buffers, run the CUDA kernel and copy the result back, so the parity tests can compare
+// each kernel with the oracle on identical inputs; the *_bench variants time the kernel with CUDA events
+// on device-resident data.
+#include <vector>
+
+#include "common.cuh"
+#include "mel.h"
+#include "tc_gemm.h"
+#include "whisper_b200.h"
+
+using namespace wb;
+
+namespace {
+
+struct DevBuf {
+    void * p = nullptr;
+    explicit DevBuf(size_t n) {
+        if (n == 0) n = 16;
+        WB_CUDA(cudaMalloc(&p, n));
+    }
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+    template <typename T> T * as() { return reinterpret_cast<T *>(p); }
+};
+
+}  // namespace
+
+extern "C" {
+
+WB200_API int whisper_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+WB200_API int whisper_b200_kernel_log_mel(const float * pcm, int n_samples, const float * filters, int n_mel,
+                                          float * mel_out, int mel_cap, int * n_len, int * n_len_org) {
+    if (!pcm || n_samples <= 0 || !filters || !n_len || !n_len_org) return -1;
+    cuda_clear_failure();
+    MelPlan plan;
+    if (!mel_plan_init(plan, filters, n_mel, 201)) return -2;
+    const MelGeometry g = mel_geometry(n_samples);
+    *n_len = g.n_len;
+    *n_len_org = g.n_len_org;
+    if (!mel_out) return 0;
+    if ((long long) mel_cap < (long long) g.n_len * n_mel) return -3;
+    DevBuf d_pcm((size_t) n_samples * 4), d_raw((size_t) n_mel * g.stride * 4), d_max(4), d_st(sizeof(MelStream)),
+        d_fin((size_t) n_mel * g.n_len * 4);
+    WB_CUDA(cudaMemcpy(d_pcm.p, pcm, (size_t) n_samples * 4, cudaMemcpyHostToDevice));
+    WB_CUDA(cudaMemset(d_max.p, 0, 4));
+    MelStream st;
+    st.pcm = d_pcm.as<float>();
+    st.n_samples = n_samples;
+    st.n_frames_fft = g.n_frames_fft;
+    st.out = d_raw.as<float>();
+    st.out_stride = g.stride;
+    st.max_enc = d_max.as<unsigned>();
+    WB_CUDA(cudaMemcpy(d_st.p, &st, sizeof(st), cudaMemcpyHostToDevice));
+    mel_launch(plan, d_st.as<MelStream>(), 1, g.n_frames_fft, 0);
+    mel_finalize_launch(d_raw.as<float>(), g.stride, g.n_frames_fft, d_max.as<unsigned>(), d_fin.as<float>(), g.n_len,
+                        n_mel, 0);
+    WB_CUDA(cudaMemcpy(mel_out, d_fin.p, (size_t) n_mel * g.n_len * 4, cudaMemcpyDeviceToHost));
+    return cuda_failed() ? -4 : 0;
+}
+
+// n_streams independent streams of n_samples each (synthetic, device resident); returns average ms per launch.
+WB200_API double whisper_b200_kernel_log_mel_bench(int n_streams, int n_samples, const float * filters, int n_mel,
+                                                   int iters, int flush_l2) {
+    cuda_clear_failure();
+    MelPlan plan;
+    if (!mel_plan_init(plan, filters, n_mel, 201)) return -1.0;
+    const MelGeometry g = mel_geometry(n_samples);
+    std::vector<float> h((size_t) n_samples);
+    unsigned s = 12345u;
+    for (auto & v : h) {
+        s = s * 1664525u + 1013904223u;
+        v = ((int) (s >> 8) % 20001 - 10000) / 30000.0f;
+    }
+    DevBuf d_pcm((size_t) n_streams * n_samples * 4), d_raw((size_t) n_streams * n_mel * g.stride * 4),
+        d_max((size_t) n_streams * 4), d_st(sizeof(MelStream) * n_streams), d_flush(flush_l2 ? (256u << 20) : 16);
+    std::vector<MelStream> sts(n_streams);
+    for (int i = 0; i < n_streams; ++i) {
+        WB_CUDA(cudaMemcpy(d_pcm.as<float>() + (size_t) i * n_samples, h.data(), (size_t) n_samples * 4,
+                           cudaMemcpyHostToDevice));
+        sts[i] = {d_pcm.as<float>() + (size_t) i * n_samples, n_samples, g.n_frames_fft,
+                  d_raw.as<float>() + (size_t) i * n_mel * g.stride, g.stride, d_max.as<unsigned>() + i};
+    }
+    WB_CUDA(cudaMemcpy(d_st.p, sts.data(), sizeof(MelStream) * n_streams, cudaMemcpyHostToDevice));
+    WB_CUDA(cudaMemset(d_max.p, 0, (size_t) n_streams * 4));
+    cudaEvent_t e0, e1;
+    WB_CUDA(cudaEventCreate(&e0));
+    WB_CUDA(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; ++i) mel_launch(plan, d_st.as<MelStream>(), n_streams, g.n_frames_fft, 0);
+    double total = 0.0;
+    for (int i = 0; i < iters; ++i) {
+        if (flush_l2) WB_CUDA(cudaMemsetAsync(d_flush.p, i, 256u << 20, 0));
+        WB_CUDA(cudaEventRecord(e0, 0));
+        mel_launch(plan, d_st.as<MelStream>(), n_streams, g.n_frames_fft, 0);
+        WB_CUDA(cudaEventRecord(e1, 0));
+        WB_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        WB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        total += ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return cuda_failed() ? -1.0 : total / iters;
+}
+
+WB200_API int whisper_b200_kernel_gemm(int dtype, int M, int N, int K, const uint16_t * a, const uint16_t * w,
+                                       const float * bias, float scale, int scale_cols, int gelu, const float * pos,
+                                       int pos_rows, const float * resid, uint16_t * out16, float * out32) {
+    cuda_clear_failure();
+    const int ldo = round_up(N, 8);
+    DevBuf d_a((size_t) M * K * 2), d_w((size_t) N * K * 2), d_bias((size_t) N * 4), d_pos((size_t) pos_rows * N * 4),
+        d_res((size_t) M * ldo * 4), d_o16((size_t) M * ldo * 2), d_o32((size_t) M * ldo * 4);
+    WB_CUDA(cudaMemcpy(d_a.p, a, (size_t) M * K * 2, cudaMemcpyHostToDevice));
+    WB_CUDA(cudaMemcpy(d_w.p, w, (size_t) N * K * 2, cudaMemcpyHostToDevice));
+    if (bias) WB_CUDA(cudaMemcpy(d_bias.p, bias, (size_t) N * 4, cudaMemcpyHostToDevice));
+    if (pos) WB_CUDA(cudaMemcpy(d_pos.p, pos, (size_t) pos_rows * N * 4, cudaMemcpyHostToDevice));
+    if (resid)
+        WB_CUDA(cudaMemcpy2D(d_res.p, (size_t) ldo * 4, resid, (size_t) N * 4, (size_t) N * 4, M, cudaMemcpyHostToDevice));
+    WB_CUDA(cudaMemset(d_o16.p, 0xff, (size_t) M * ldo * 2));
+    WB_CUDA(cudaMemset(d_o32.p, 0xff, (size_t) M * ldo * 4));
+    GemmArgs g;
+    g.dtype = dtype == 1 ? DType::BF16 : DType::F16;
+    g.M = M; g.N = N; g.K = K;
+    g.a = d_a.p; g.lda = K;
+    g.w = d_w.p; g.ldw = K;
+    g.bias = bias ? d_bias.as<float>() : nullptr;
+    g.scale = scale; g.scale_cols = scale_cols;
+    g.gelu = gelu != 0;
+    g.pos = pos ? d_pos.as<float>() : nullptr; g.pos_rows = pos_rows;
+    g.resid = resid ? d_res.as<float>() : nullptr; g.ldr = ldo;
+    g.out16 = out16 ? d_o16.p : nullptr; g.ldo16 = ldo;
+    g.out32 = out32 ? d_o32.as<float>() : nullptr; g.ldo32 = ldo;
+    if (!tc_gemm(g, 0)) return -2;
+    WB_CUDA(cudaDeviceSynchronize());
+    if (out16)
+        WB_CUDA(cudaMemcpy2D(out16, (size_t) N * 2, d_o16.p, (size_t) ldo * 2, (size_t) N * 2, M, cudaMemcpyDeviceToHost));
+    if (out32)
+        WB_CUDA(cudaMemcpy2D(out32, (size_t) N * 4, d_o32.p, (size_t) ldo * 4, (size_t) N * 4, M, cudaMemcpyDeviceToHost));
+    return cuda_failed() ? -3 : 0;
+}
+
+// Device-resident GEMM timing (random-ish operands); returns average ms.
+WB200_API double whisper_b200_kernel_gemm_bench(int dtype, int M, int N, int K, int gelu, int iters) {
+    cuda_clear_failure();
+    DevBuf d_a((size_t) M * K * 2), d_w((size_t) N * K * 2), d_bias((size_t) N * 4), d_o16((size_t) M * N * 2);
+    WB_CUDA(cudaMemset(d_a.p, 0x11, (size_t) M * K * 2));
+    WB_CUDA(cudaMemset(d_w.p, 0x12, (size_t) N * K * 2));
+    WB_CUDA(cudaMemset(d_bias.p, 0, (size_t) N * 4));
+    GemmArgs g;
+    g.dtype = dtype == 1 ? DType::BF16 : DType::F16;
+    g.M = M; g.N = N; g.K = K;
+    g.a = d_a.p; g.lda = K;
+    g.w = d_w.p; g.ldw = K;
+    g.bias = d_bias.as<float>();
+    g.gelu = gelu != 0;
+    g.out16 = d_o16.p; g.ldo16 = N;
+    cudaEvent_t e0, e1;
+    WB_CUDA(cudaEventCreate(&e0));
+    WB_CUDA(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; ++i)
+        if (!tc_gemm(g, 0)) return -1.0;
+    WB_CUDA(cudaEventRecord(e0, 0));
+    for (int i = 0; i < iters; ++i) tc_gemm(g, 0);
+    WB_CUDA(cudaEventRecord(e1, 0));
+    WB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    WB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return cuda_failed() ? -1.0 : ms / iters;
+}
+
+}  // extern "C"

@@ -1,0 +1,390 @@
+// C[M,N] = epilogue( A[M,K] * W[N,K]^T )  on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM),
+// operands staged by TMA into 128B-swizzled shared memory through an mbarrier ring.  Both operands are K-major
+// ("TN"): activations are [tokens][features] and every Whisper weight is stored [out][in]
+// (reference src/whisper.cpp:1775-1793), so no transposes exist anywhere on the path.
+//
+// This kernel replaces, for every GEMM of the encoder / cross-K/V / prompt pass, the reference's
+// ggml_mul_mat + separate bias add / scale / GELU / residual add / cast launches
+// (src/whisper.cpp:2006-2014, 2112-2237, 2300-2339; on CUDA: cublasGemmEx + convert + k_bin_bcast + unary kernels,
+// ggml/src/ggml-cuda/ggml-cuda.cu:1228-1382).
+//
+// Structure (one CTA per SM, persistent over output tiles, 256 threads):
+//   warp 0      : TMA producer   (one elected lane)       global -> smem ring, kStages deep
+//   warp 1      : MMA issuer     (one elected lane)       tcgen05.mma 128 x BN x 16, accumulates over K in TMEM
+//   warp 2      : TMEM allocator (2 accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1)
+//   warps 4..7  : epilogue       tcgen05.ld -> registers -> bias / scale / GELU / positional add / residual -> global
+#include "tc_gemm.h"
+
+#include <cuda.h>
+#include <mutex>
+
+#include "ptx.cuh"
+
+namespace wb {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;           // 64 x 16-bit = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kThreads = 256;
+constexpr int kEpiWarp0 = 4;
+
+template <int BN> struct Cfg {
+    static constexpr int kStages = BN == 256 ? 4 : 6;
+    static constexpr int kABytes = BM * BK * 2;
+    static constexpr int kBBytes = BN * BK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kTmemCols = 2 * BN;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct EpiParams {
+    int M, N;
+    const float * bias;
+    float scale;
+    int scale_cols;
+    int gelu;          // 0 none, 1 tanh-GELU
+    int ref_f16_gelu;  // round GELU input/output through f16 like ggml's lookup table
+    const float * pos;
+    int pos_rows;
+    const float * resid;
+    int ldr;
+    void * out16;
+    int ldo16;
+    float * out32;
+    int ldo32;
+};
+
+template <typename T16> __device__ __forceinline__ float gelu_epi(float v, int ref_f16) {
+    if (ref_f16) {
+        // ggml_vec_gelu_f32 with GGML_GELU_FP16 (reference ggml/src/ggml-cpu/vec.h:996-1009): table lookup on the
+        // f16-rounded input, f16 result; identity / zero outside (-10, 10).
+        if (v <= -10.0f) return 0.0f;
+        if (v >= 10.0f) return v;
+        const float x = __half2float(__float2half_rn(v));
+        return __half2float(__float2half_rn(gelu_tanh(x)));
+    }
+    return gelu_tanh(v);
+}
+
+template <int BN, typename T16>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int K,
+               const EpiParams ep) {
+    using C = Cfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    // 128B swizzle needs 1024-byte aligned tiles
+    uint8_t * smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t * smem_a = smem;
+    uint8_t * smem_b = smem + C::kStages * C::kABytes;
+    uint64_t * bars = reinterpret_cast<uint64_t *>(smem + C::kStages * C::kStageBytes);
+    uint64_t * full_bar = bars;                       // [kStages]   TMA -> MMA
+    uint64_t * empty_bar = bars + C::kStages;         // [kStages]   MMA -> TMA
+    uint64_t * tfull_bar = bars + 2 * C::kStages;     // [2]         MMA -> epilogue
+    uint64_t * tempty_bar = tfull_bar + 2;            // [2]         epilogue -> MMA
+    uint32_t * tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    const int tiles_m = (ep.M + BM - 1) / BM;
+    const int tiles_n = (ep.N + BN - 1) / BN;
+    const int n_tiles = tiles_m * tiles_n;
+    const int k_blocks = (K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tmap_a);
+        ptx::prefetch_tensormap(&tmap_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < C::kStages; ++i) {
+            ptx::mbar_init(&full_bar[i], 1);
+            ptx::mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&tfull_bar[i], 1);
+            ptx::mbar_init(&tempty_bar[i], 4);     // one arrive per epilogue warp
+        }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 2) {
+        ptx::tmem_alloc(tmem_slot, C::kTmemCols);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int m0 = (tile / tiles_n) * BM;
+                const int n0 = (tile % tiles_n) * BN;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    ptx::mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
+                    ptx::tma_load_2d(smem_a + stage * C::kABytes, &tmap_a, &full_bar[stage], kb * BK, m0);
+                    ptx::tma_load_2d(smem_b + stage * C::kBBytes, &tmap_b, &full_bar[stage], kb * BK, n0);
+                    if (++stage == C::kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_f16(Half16<T16>::kind, BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);       // epilogue drained this accumulator
+                ptx::tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t) (acc * BN);
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint64_t da = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem_a + stage * C::kABytes));
+                    const uint64_t db = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem_b + stage * C::kBBytes));
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        // advance 32 bytes (16 elements) along K inside the swizzle atom: +2 in 16-byte units
+                        ptx::umma_f16(tmem_d, da + (uint64_t) (2 * k), db + (uint64_t) (2 * k), idesc,
+                                      (uint32_t) ((kb | k) != 0));
+                    }
+                    ptx::umma_commit(&empty_bar[stage]);                // smem slot free once these MMAs retire
+                    if (++stage == C::kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                ptx::umma_commit(&tfull_bar[acc]);                       // accumulator complete
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+            }
+        }
+    } else if (warp >= kEpiWarp0) {
+        // ===== epilogue =====
+        const int ew = warp - kEpiWarp0;               // == warp % 4: TMEM lane quarter this warp may read
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        T16 * out16 = reinterpret_cast<T16 *>(ep.out16);
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int m0 = (tile / tiles_n) * BM;
+            const int n0 = (tile % tiles_n) * BN;
+            ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+            ptx::tc_fence_after();
+            const int row = m0 + ew * 32 + lane;
+            const bool row_ok = row < ep.M;
+            const float * pos_row = ep.pos ? ep.pos + (size_t) (row % ep.pos_rows) * ep.N : nullptr;
+            const float * res_row = ep.resid ? ep.resid + (size_t) row * ep.ldr : nullptr;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                const int col0 = n0 + c * 32;
+                if (col0 >= ep.N) break;               // warp-uniform
+                uint32_t r[32];
+                ptx::tmem_ld_32x32(tmem_base + ((uint32_t) (ew * 32) << 16) + (uint32_t) (acc * BN + c * 32), r);
+                ptx::tmem_ld_wait();
+                if (!row_ok) continue;
+                const bool full = col0 + 32 <= ep.N;
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                if (ep.bias) {
+                    if (full) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b = __ldg(reinterpret_cast<const float4 *>(ep.bias + col0 + j));
+                            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < ep.N) v[j] += __ldg(ep.bias + col0 + j);
+                    }
+                }
+                if (col0 < ep.scale_cols) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (col0 + j < ep.scale_cols) v[j] *= ep.scale;
+                }
+                if (ep.gelu) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = gelu_epi<T16>(v[j], ep.ref_f16_gelu);
+                }
+                if (pos_row) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (col0 + j < ep.N) v[j] += __ldg(pos_row + col0 + j);
+                }
+                if (res_row) {
+                    if (full) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b = *reinterpret_cast<const float4 *>(res_row + col0 + j);
+                            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < ep.N) v[j] += res_row[col0 + j];
+                    }
+                }
+                if (ep.out32) {
+                    float * o = ep.out32 + (size_t) row * ep.ldo32 + col0;
+                    if (full) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4 *>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < ep.N) o[j] = v[j];
+                    }
+                }
+                if (out16) {
+                    T16 * o = out16 + (size_t) row * ep.ldo16 + col0;
+                    if (full) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            union {
+                                uint4 u;
+                                T16 h[8];
+                            } pk;
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) pk.h[q] = Half16<T16>::from_f(v[j + q]);
+                            *reinterpret_cast<uint4 *>(o + j) = pk.u;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < ep.N) o[j] = Half16<T16>::from_f(v[j]);
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, C::kTmemCols);
+    }
+}
+
+// ---- host: tensor maps ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void * p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess) {
+            fn = (EncodeTiledFn) p;
+        }
+    });
+    return fn;
+}
+
+bool make_tmap(CUtensorMap * tm, const void * base, int rows, int cols, int ld_elems, int box_rows, DType dt) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {(cuuint64_t) cols, (cuuint64_t) rows};
+    cuuint64_t strides[1] = {(cuuint64_t) ld_elems * 2};
+    cuuint32_t box[2] = {(cuuint32_t) BK, (cuuint32_t) box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(tm, dt == DType::F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                    const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+template <int BN, typename T16> void launch(const GemmArgs & g, const EpiParams & ep, int n_sm, cudaStream_t stream,
+                                            bool & ok) {
+    using C = Cfg<BN>;
+    CUtensorMap ta, tb;
+    if (!make_tmap(&ta, g.a, g.M, g.K, g.lda, BM, g.dtype) || !make_tmap(&tb, g.w, g.N, g.K, g.ldw, BN, g.dtype)) {
+        ok = false;
+        return;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        WB_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, T16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     C::kSmemBytes));
+        attr_set = true;
+    }
+    const int tiles = ceil_div(g.M, BM) * ceil_div(g.N, BN);
+    const int grid = tiles < n_sm ? tiles : n_sm;
+    tc_gemm_kernel<BN, T16><<<grid, kThreads, C::kSmemBytes, stream>>>(ta, tb, g.K, ep);
+    WB_CUDA(cudaGetLastError());
+}
+
+}  // namespace
+
+bool tc_gemm(const GemmArgs & g, cudaStream_t stream) {
+    if (g.M <= 0 || g.N <= 0 || g.K <= 0) return true;
+    // TMA needs 16-byte aligned bases and row pitches; the epilogue's vector stores need aligned leading dims.
+    if ((g.lda % 8) || (g.ldw % 8) || (reinterpret_cast<uintptr_t>(g.a) & 15) || (reinterpret_cast<uintptr_t>(g.w) & 15))
+        return false;
+    if (g.out16 && (g.ldo16 % 8)) return false;
+    if (g.out32 && (g.ldo32 % 4)) return false;
+    if (g.resid && (g.ldr % 4)) return false;
+    EpiParams ep;
+    ep.M = g.M;
+    ep.N = g.N;
+    ep.bias = g.bias;
+    ep.scale = g.scale;
+    ep.scale_cols = g.scale_cols;
+    ep.gelu = g.gelu ? 1 : 0;
+    ep.ref_f16_gelu = (g.dtype == DType::F16) ? 1 : 0;
+    ep.pos = g.pos;
+    ep.pos_rows = g.pos_rows > 0 ? g.pos_rows : 1;
+    ep.resid = g.resid;
+    ep.ldr = g.ldr;
+    ep.out16 = g.out16;
+    ep.ldo16 = g.ldo16;
+    ep.out32 = g.out32;
+    ep.ldo32 = g.ldo32;
+    static int n_sm = 0;
+    if (n_sm == 0) {
+        int dev = 0;
+        WB_CUDA(cudaGetDevice(&dev));
+        WB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        if (n_sm <= 0) n_sm = 148;
+    }
+    bool ok = true;
+    const bool wide = (g.N % 256 == 0) || g.N > 1024;
+    if (g.dtype == DType::F16) {
+        if (wide) launch<256, __half>(g, ep, n_sm, stream, ok);
+        else launch<128, __half>(g, ep, n_sm, stream, ok);
+    } else {
+        if (wide) launch<256, __nv_bfloat16>(g, ep, n_sm, stream, ok);
+        else launch<128, __nv_bfloat16>(g, ep, n_sm, stream, ok);
+    }
+    return ok && !cuda_failed();
+}
+
+}  // namespace wb

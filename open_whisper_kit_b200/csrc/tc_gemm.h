@@ -1,0 +1,29 @@
+// Host interface of the tcgen05/TMEM/TMA GEMM (tc_gemm.cu).
+#pragma once
+
+#include "common.cuh"
+
+namespace wb {
+
+// out = epilogue(A[M,K] * W[N,K]^T), A and W row-major 16-bit (f16 or bf16), f32 accumulation.
+// epilogue order (mirrors the op order of the reference graphs, src/whisper.cpp:2006-2014, 2112-2237, 2300-2339):
+//   v = acc + bias[n];  if (n < scale_cols) v *= scale;  if (gelu) v = gelu(v);
+//   v += pos[(m % pos_rows)*N + n];  v += resid[m*ldr + n];  out32[m*ldo32+n] = v;  out16[m*ldo16+n] = (16-bit) v
+struct GemmArgs {
+    DType dtype = DType::F16;
+    int M = 0, N = 0, K = 0;
+    const void * a = nullptr;   int lda = 0;    // [M][lda]
+    const void * w = nullptr;   int ldw = 0;    // [N][ldw]
+    const float * bias = nullptr;               // [N] or null
+    float scale = 1.0f;         int scale_cols = 0;
+    bool gelu = false;
+    const float * pos = nullptr; int pos_rows = 0;
+    const float * resid = nullptr; int ldr = 0; // may alias out32
+    void * out16 = nullptr;     int ldo16 = 0;
+    float * out32 = nullptr;    int ldo32 = 0;
+};
+
+// Returns false when the arguments violate the kernel's alignment contract or the launch failed.
+bool tc_gemm(const GemmArgs & g, cudaStream_t stream);
+
+}  // namespace wb

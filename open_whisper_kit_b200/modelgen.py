@@ -1,0 +1,228 @@
+"""Random-init GGML model files of a named Whisper architecture + synthetic PCM (test / bench tooling).
+
+There is no network for real checkpoints, so parity and throughput are measured on seeded
+random-init weights written in the reference's legacy GGML container
+(reference: src/whisper.cpp:1485-1956 reader, models/convert-pt-to-ggml.py:268-337 writer;
+tensor names src/whisper-arch.h:42-109).  The same file is fed to the reference CPU build and to
+our library.
+
+Initialisation is variance preserving: sigma = 1/sqrt(fan_in) for GEMM/conv
+weights, 0.5x on residual-branch output projections, LayerNorm gamma = 1 + N(0, 0.02), biases
+N(0, 0.02), sinusoidal encoder positions (as real checkpoints have), so the residual stream stays
+O(1) and attention is not uniform.
+"""
+import struct
+
+import numpy as np
+
+GGML_MAGIC = 0x67676D6C
+N_FFT_BINS = 201
+SAMPLE_RATE = 16000
+WINDOW_SAMPLES = 30 * SAMPLE_RATE
+
+# name -> (n_vocab, n_audio_ctx, d, n_head, n_audio_layer, n_text_ctx, n_text_layer, n_mels)
+ARCHS = {
+    "tiny.en": (51864, 1500, 384, 6, 4, 448, 4, 80),
+    "tiny": (51865, 1500, 384, 6, 4, 448, 4, 80),
+    "base.en": (51864, 1500, 512, 8, 6, 448, 6, 80),
+    "base": (51865, 1500, 512, 8, 6, 448, 6, 80),
+    "small.en": (51864, 1500, 768, 12, 12, 448, 12, 80),
+    "medium.en": (51864, 1500, 1024, 16, 24, 448, 24, 80),
+    "large-v2": (51865, 1500, 1280, 20, 32, 448, 32, 80),
+    "large-v3": (51866, 1500, 1280, 20, 32, 448, 32, 128),
+    "large-v3-turbo": (51866, 1500, 1280, 20, 32, 448, 4, 128),
+    # a 2-layer toy with the tiny geometry for fast CPU tests of the full pipeline
+    "micro.en": (51864, 1500, 128, 2, 2, 448, 2, 80),
+}
+
+
+def _hz_to_mel(f):
+    f = np.asarray(f, dtype=np.float64)
+    f_sp = 200.0 / 3
+    mels = f / f_sp
+    min_log_hz = 1000.0
+    min_log_mel = min_log_hz / f_sp
+    logstep = np.log(6.4) / 27.0
+    return np.where(f >= min_log_hz, min_log_mel + np.log(np.maximum(f, 1e-10) / min_log_hz) / logstep, mels)
+
+
+def _mel_to_hz(m):
+    m = np.asarray(m, dtype=np.float64)
+    f_sp = 200.0 / 3
+    min_log_hz = 1000.0
+    min_log_mel = min_log_hz / f_sp
+    logstep = np.log(6.4) / 27.0
+    return np.where(m >= min_log_mel, min_log_hz * np.exp(logstep * (m - min_log_mel)), f_sp * m)
+
+
+def mel_filters(n_mels, sr=SAMPLE_RATE, n_fft=400):
+    """Slaney-scale, area-normalised triangular filterbank [n_mels][201] (what the model files carry,
+    reference src/whisper.cpp:1576-1586; reproduces the 80-bin fixture to ~2e-9)."""
+    fftfreqs = np.linspace(0, sr / 2, 1 + n_fft // 2)
+    mel_f = _mel_to_hz(np.linspace(_hz_to_mel(0.0), _hz_to_mel(sr / 2.0), n_mels + 2))
+    fdiff = np.diff(mel_f)
+    ramps = mel_f[:, None] - fftfreqs[None, :]
+    w = np.zeros((n_mels, 1 + n_fft // 2))
+    for i in range(n_mels):
+        lower = -ramps[i] / fdiff[i]
+        upper = ramps[i + 2] / fdiff[i + 1]
+        w[i] = np.maximum(0, np.minimum(lower, upper))
+    enorm = 2.0 / (mel_f[2:n_mels + 2] - mel_f[:n_mels])
+    w *= enorm[:, None]
+    return w.astype(np.float32)
+
+
+def _gpt2_byte_order():
+    bs = list(range(ord("!"), ord("~") + 1)) + list(range(0xA1, 0xAC + 1)) + list(range(0xAE, 0xFF + 1))
+    rest = [b for b in range(256) if b not in bs]
+    return bs + rest
+
+
+NON_SPEECH = ["\"", "#", "(", ")", "*", "+", "/", ":", ";", "<", "=", ">", "@", "[", "\\", "]", "^", "_", "`",
+              "{", "|", "}", "~", "<<", ">>", "<<<", ">>>", "--", "---", "-(", "-[", "('", "(\"", "((", "))",
+              "(((", ")))", "[[", "]]", "{{", "}}"]
+
+
+def synth_vocab(multilingual, seed=99):
+    """50257 byte strings shaped like the GPT-2 BPE table: ids 0..255 are the single bytes in GPT-2 order
+    (so " " is id 220, which the suppress_blank rule looks up, reference src/whisper.cpp:6219), followed by
+    the multi-character non-speech strings the suppress_nst rule searches for and seeded pseudo-words."""
+    toks = [bytes([b]) for b in _gpt2_byte_order()]
+    seen = set(toks)
+    for t in NON_SPEECH + ["-", "'"]:
+        for cand in (t.encode(), b" " + t.encode()):
+            if cand not in seen:
+                seen.add(cand)
+                toks.append(cand)
+    rng = np.random.default_rng(seed)
+    letters = np.frombuffer(b"etaoinshrdlucmfwypvbgkqjxz", dtype=np.uint8)
+    while len(toks) < 50256:
+        n = int(rng.integers(2, 8))
+        w = bytes(rng.choice(letters, size=n).tolist())
+        if rng.random() < 0.5:
+            w = b" " + w
+        if w not in seen:
+            seen.add(w)
+            toks.append(w)
+    toks.append(b"" if multilingual else b"<|endoftext|>")
+    return toks
+
+
+def sinusoids(length, channels, max_timescale=10000.0):
+    inc = np.log(max_timescale) / (channels // 2 - 1)
+    inv = np.exp(-inc * np.arange(channels // 2))
+    t = np.arange(length)[:, None] * inv[None, :]
+    return np.concatenate([np.sin(t), np.cos(t)], axis=1).astype(np.float32)
+
+
+def tensor_specs(arch):
+    """Yield (name, torch-order shape, kind) for every tensor in file order (Appendix A of SURVEY.md)."""
+    n_vocab, n_actx, d, n_head, n_al, n_tctx, n_tl, n_mels = ARCHS[arch]
+    out = []
+    out.append(("encoder.positional_embedding", (n_actx, d), "enc_pos"))
+    out.append(("encoder.conv1.weight", (d, n_mels, 3), "conv"))
+    out.append(("encoder.conv1.bias", (d, 1), "bias2d"))
+    out.append(("encoder.conv2.weight", (d, d, 3), "conv"))
+    out.append(("encoder.conv2.bias", (d, 1), "bias2d"))
+
+    def block(prefix, cross):
+        b = []
+        b.append((prefix + ".attn_ln.weight", (d,), "ln_w"))
+        b.append((prefix + ".attn_ln.bias", (d,), "bias"))
+        b.append((prefix + ".attn.query.weight", (d, d), "w"))
+        b.append((prefix + ".attn.query.bias", (d,), "bias"))
+        b.append((prefix + ".attn.key.weight", (d, d), "w"))
+        b.append((prefix + ".attn.value.weight", (d, d), "w"))
+        b.append((prefix + ".attn.value.bias", (d,), "bias"))
+        b.append((prefix + ".attn.out.weight", (d, d), "w_out"))
+        b.append((prefix + ".attn.out.bias", (d,), "bias"))
+        if cross:
+            b.append((prefix + ".cross_attn_ln.weight", (d,), "ln_w"))
+            b.append((prefix + ".cross_attn_ln.bias", (d,), "bias"))
+            b.append((prefix + ".cross_attn.query.weight", (d, d), "w"))
+            b.append((prefix + ".cross_attn.query.bias", (d,), "bias"))
+            b.append((prefix + ".cross_attn.key.weight", (d, d), "w"))
+            b.append((prefix + ".cross_attn.value.weight", (d, d), "w"))
+            b.append((prefix + ".cross_attn.value.bias", (d,), "bias"))
+            b.append((prefix + ".cross_attn.out.weight", (d, d), "w_out"))
+            b.append((prefix + ".cross_attn.out.bias", (d,), "bias"))
+        b.append((prefix + ".mlp_ln.weight", (d,), "ln_w"))
+        b.append((prefix + ".mlp_ln.bias", (d,), "bias"))
+        b.append((prefix + ".mlp.0.weight", (4 * d, d), "w"))
+        b.append((prefix + ".mlp.0.bias", (4 * d,), "bias"))
+        b.append((prefix + ".mlp.2.weight", (d, 4 * d), "w_out"))
+        b.append((prefix + ".mlp.2.bias", (d,), "bias"))
+        return b
+
+    for i in range(n_al):
+        out += block(f"encoder.blocks.{i}", False)
+    out.append(("encoder.ln_post.weight", (d,), "ln_w"))
+    out.append(("encoder.ln_post.bias", (d,), "bias"))
+    out.append(("decoder.positional_embedding", (n_tctx, d), "dec_pos"))
+    out.append(("decoder.token_embedding.weight", (n_vocab, d), "tok_emb"))
+    for i in range(n_tl):
+        out += block(f"decoder.blocks.{i}", True)
+    out.append(("decoder.ln.weight", (d,), "ln_w"))
+    out.append(("decoder.ln.bias", (d,), "bias"))
+    return out
+
+
+def _init(kind, shape, rng, tok_emb_gain):
+    if kind == "enc_pos":
+        return sinusoids(shape[0], shape[1])
+    if kind == "dec_pos":
+        return (0.1 * rng.standard_normal(shape, dtype=np.float32))
+    if kind == "ln_w":
+        return (1.0 + 0.02 * rng.standard_normal(shape, dtype=np.float32)).astype(np.float32)
+    if kind in ("bias", "bias2d"):
+        return (0.02 * rng.standard_normal(shape, dtype=np.float32))
+    if kind == "conv":
+        fan_in = shape[1] * shape[2]
+        return (1.4 / np.sqrt(fan_in)) * rng.standard_normal(shape, dtype=np.float32)
+    if kind == "w":
+        return (1.0 / np.sqrt(shape[1])) * rng.standard_normal(shape, dtype=np.float32)
+    if kind == "w_out":
+        return (0.5 / np.sqrt(shape[1])) * rng.standard_normal(shape, dtype=np.float32)
+    if kind == "tok_emb":
+        return (tok_emb_gain / np.sqrt(shape[1])) * rng.standard_normal(shape, dtype=np.float32)
+    raise ValueError(kind)
+
+
+def write_model(path, arch, seed=1234, ftype=1, tok_emb_gain=4.0, with_tensors=True):
+    """Write a GGML whisper model file.  ftype=1: 2-D+ weights as F16 (conv biases / positional
+    embeddings / 1-D tensors stay F32, as the reference converter does); ftype=0: everything F32."""
+    n_vocab, n_actx, d, n_head, n_al, n_tctx, n_tl, n_mels = ARCHS[arch]
+    multilingual = n_vocab >= 51865
+    rng = np.random.default_rng(seed)
+    with open(path, "wb") as f:
+        f.write(struct.pack("<I", GGML_MAGIC))
+        f.write(struct.pack("<11i", n_vocab, n_actx, d, n_head, n_al, n_tctx, d, n_head, n_tl, n_mels, ftype))
+        filt = mel_filters(n_mels)
+        f.write(struct.pack("<2i", n_mels, N_FFT_BINS))
+        f.write(filt.tobytes())
+        toks = synth_vocab(multilingual)
+        f.write(struct.pack("<i", len(toks)))
+        for t in toks:
+            f.write(struct.pack("<I", len(t)))
+            f.write(t)
+        if not with_tensors:
+            return
+        for name, shape, kind in tensor_specs(arch):
+            data = _init(kind, shape, rng, tok_emb_gain)
+            use_f16 = ftype == 1 and len(shape) >= 2 and kind not in ("enc_pos", "dec_pos", "bias2d")
+            ttype = 1 if use_f16 else 0
+            nb = name.encode()
+            f.write(struct.pack("<3i", len(shape), len(nb), ttype))
+            for dim in reversed(shape):  # ggml ne[] order: fastest dimension first
+                f.write(struct.pack("<i", dim))
+            f.write(nb)
+            f.write(data.astype(np.float16 if use_f16 else np.float32).tobytes())
+
+
+def synth_pcm(n_samples, seed=7, stream=0):
+    """0.1*N(0,1) + 0.3*sin(2*pi*440 t)*sin(2*pi*0.5 t), clipped to [-1,1]."""
+    rng = np.random.default_rng([seed, stream])
+    t = np.arange(n_samples, dtype=np.float64) / SAMPLE_RATE
+    x = 0.1 * rng.standard_normal(n_samples) + 0.3 * np.sin(2 * np.pi * (440.0 + 37.0 * stream) * t) * np.sin(
+        2 * np.pi * 0.5 * t + 0.1 * stream)
+    return np.clip(x, -1.0, 1.0).astype(np.float32)

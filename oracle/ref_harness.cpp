@@ -1,0 +1,127 @@
+// TEST INFRASTRUCTURE ONLY -- never linked into, imported or called by the product path.
+//
+// Harness translation unit for building the UNMODIFIED reference CPU implementation
+// (whisper.cpp + ggml-cpu, from the sources where they lie under /root/reference) into
+// oracle/_ref/libwhisper_ref_<arch>.so.  It textually includes the reference's
+// src/whisper.cpp (it is NOT copied into this repo) so the file-static internals the
+// public C API does not expose -- the mel buffer, the encoder output, the cross K/V cache --
+// can be read back for parity checks.  Everything in include/whisper.h of the reference is
+// exported by the resulting library as well, so the ctypes bindings used against our own
+// libwhisper.so can be pointed at the reference unchanged.
+//
+// Build: oracle/build_ref.sh  (g++ on the reference's own sources; the reference's cmake
+// build system is not run).
+
+#include REF_WHISPER_CPP   // -DREF_WHISPER_CPP='"/root/reference/src/whisper.cpp"'
+
+#include <cstring>
+
+extern "C" {
+
+// mel of the default state after whisper_pcm_to_mel: [n_mel][n_len] f32
+// (reference: whisper_state::mel, src/whisper.cpp:414-420, filled at 3170-3260)
+__attribute__((visibility("default")))
+int ref_mel_dims(struct whisper_context * ctx, int * n_len, int * n_len_org, int * n_mel) {
+    if (!ctx || !ctx->state) return -1;
+    *n_len     = ctx->state->mel.n_len;
+    *n_len_org = ctx->state->mel.n_len_org;
+    *n_mel     = ctx->state->mel.n_mel;
+    return 0;
+}
+
+__attribute__((visibility("default")))
+int ref_mel_copy(struct whisper_context * ctx, float * out) {
+    if (!ctx || !ctx->state) return -1;
+    const auto & m = ctx->state->mel;
+    memcpy(out, m.data.data(), m.data.size()*sizeof(float));
+    return 0;
+}
+
+// direct entry to log_mel_spectrogram with explicit filters (for 128-bin sweeps on 80-bin models)
+__attribute__((visibility("default")))
+int ref_log_mel(const float * samples, int n_samples, int n_mel, const float * filters_data, int n_threads,
+                float * out, int out_cap, int * n_len, int * n_len_org) {
+    whisper_state st;
+    whisper_filters f;
+    f.n_mel = n_mel;
+    f.n_fft = 1 + WHISPER_N_FFT/2;
+    f.data.assign(filters_data, filters_data + (size_t) n_mel*f.n_fft);
+    whisper_mel mel;
+    if (!log_mel_spectrogram(st, samples, n_samples, WHISPER_SAMPLE_RATE, WHISPER_N_FFT, WHISPER_HOP_LENGTH,
+                             n_mel, n_threads, f, false, mel)) {
+        return -1;
+    }
+    *n_len = mel.n_len;
+    *n_len_org = mel.n_len_org;
+    if ((size_t) out_cap < mel.data.size()) return -2;
+    memcpy(out, mel.data.data(), mel.data.size()*sizeof(float));
+    return 0;
+}
+
+// encoder output after whisper_encode: [n_audio_ctx][n_audio_state] f32
+// (reference: whisper_state::embd_enc, src/whisper.cpp:2241-2251)
+__attribute__((visibility("default")))
+int ref_embd_enc_copy(struct whisper_context * ctx, float * out, int n_floats) {
+    if (!ctx || !ctx->state || !ctx->state->embd_enc) return -1;
+    ggml_tensor * t = ctx->state->embd_enc;
+    if ((int64_t) n_floats != ggml_nelements(t)) return -2;
+    ggml_backend_tensor_get(t, out, 0, ggml_nbytes(t));
+    return 0;
+}
+
+// cross K/V cache (F16 in the reference) converted to f32.  Layout of the reference buffer:
+// flash_attn: K,V = [n_text_layer][n_ctx_pad][n_state]; otherwise K = [layer][n_ctx][n_state],
+// V = [layer][n_state][n_ctx] (transposed) (src/whisper.cpp:2300-2339).  Raw copy; caller interprets.
+__attribute__((visibility("default")))
+int64_t ref_kv_cross_copy(struct whisper_context * ctx, int which /*0=k 1=v*/, float * out, int64_t cap) {
+    if (!ctx || !ctx->state) return -1;
+    ggml_tensor * t = which == 0 ? ctx->state->kv_cross.k : ctx->state->kv_cross.v;
+    const int64_t n = ggml_nelements(t);
+    if (!out) return n;
+    if (cap < n) return -2;
+    if (t->type == GGML_TYPE_F16) {
+        std::vector<ggml_fp16_t> tmp(n);
+        ggml_backend_tensor_get(t, tmp.data(), 0, ggml_nbytes(t));
+        ggml_fp16_to_fp32_row(tmp.data(), out, n);
+    } else {
+        ggml_backend_tensor_get(t, out, 0, ggml_nbytes(t));
+    }
+    return n;
+}
+
+// Run the reference's own logit rules + greedy sampler on an externally supplied logits row.
+// Used to pin the oracle restatement of whisper_process_logits / whisper_sample_token
+// (src/whisper.cpp:6177-6445, 6460-6517).  `hist` are the tokens sampled so far.
+__attribute__((visibility("default")))
+int ref_process_logits(struct whisper_context * ctx, struct whisper_full_params params, float temperature,
+                       const float * logits_row, const whisper_token * hist, int n_hist,
+                       int has_ts, int seek_delta,
+                       float * logits_out, float * logprobs_out, float * probs_out, whisper_token_data * tok_out) {
+    if (!ctx || !ctx->state) return -1;
+    auto & state = *ctx->state;
+    const int n_vocab = ctx->vocab.n_vocab;
+    state.logits.assign(logits_row, logits_row + n_vocab);
+    whisper_decoder & dec = state.decoders[0];
+    dec.i_batch = 0;
+    dec.has_ts = has_ts != 0;
+    dec.seek_delta = seek_delta;
+    dec.sequence.tokens.clear();
+    for (int i = 0; i < n_hist; ++i) {
+        whisper_token_data td = {};
+        td.id = hist[i];
+        dec.sequence.tokens.push_back(td);
+    }
+    whisper_process_logits(*ctx, state, dec, params, temperature);
+    if (logits_out)   memcpy(logits_out,   dec.logits.data(),   n_vocab*sizeof(float));
+    if (logprobs_out) memcpy(logprobs_out, dec.logprobs.data(), n_vocab*sizeof(float));
+    if (probs_out)    memcpy(probs_out,    dec.probs.data(),    n_vocab*sizeof(float));
+    if (tok_out)      *tok_out = whisper_sample_token(*ctx, dec, true);
+    return 0;
+}
+
+__attribute__((visibility("default")))
+float ref_no_speech_prob(struct whisper_context * ctx) {
+    return ctx && ctx->state ? ctx->state->no_speech_prob : -1.0f;
+}
+
+} // extern "C"
