@@ -2,6 +2,7 @@
 // They take HOST buffers, run the CUDA kernel and copy the result back, so the parity tests can compare
 // each kernel with the oracle on identical inputs; the *_bench variants time the kernel with CUDA events
 // on device-resident data.
+#include <string.h>
 #include <vector>
 
 #include "common.cuh"
@@ -152,8 +153,32 @@ WB200_API int whisper_b200_kernel_gemm(int dtype, int M, int N, int K, const uin
 WB200_API double whisper_b200_kernel_gemm_bench(int dtype, int M, int N, int K, int gelu, int iters) {
     cuda_clear_failure();
     DevBuf d_a((size_t) M * K * 2), d_w((size_t) N * K * 2), d_bias((size_t) N * 4), d_o16((size_t) M * N * 2);
-    WB_CUDA(cudaMemset(d_a.p, 0x11, (size_t) M * K * 2));
-    WB_CUDA(cudaMemset(d_w.p, 0x12, (size_t) N * K * 2));
+    {
+        // pseudo-random operands in [-1, 1): constant data would under-state power draw and over-state clocks
+        const size_t blk = 8u << 20;
+        std::vector<uint16_t> h(blk);
+        unsigned s = 777u;
+        for (auto & v : h) {
+            s = s * 1664525u + 1013904223u;
+            const float f = ((int) (s >> 9) % 4096 - 2048) / 2048.0f;
+            if (dtype == 1) {
+                unsigned u;
+                memcpy(&u, &f, 4);
+                v = (uint16_t) (u >> 16);
+            } else {
+                __half hh = __float2half(f);
+                memcpy(&v, &hh, 2);
+            }
+        }
+        auto fill = [&](void * dst, size_t n_elems) {
+            for (size_t off = 0; off < n_elems; off += blk) {
+                const size_t n = n_elems - off < blk ? n_elems - off : blk;
+                WB_CUDA(cudaMemcpy((uint16_t *) dst + off, h.data(), n * 2, cudaMemcpyHostToDevice));
+            }
+        };
+        fill(d_a.p, (size_t) M * K);
+        fill(d_w.p, (size_t) N * K);
+    }
     WB_CUDA(cudaMemset(d_bias.p, 0, (size_t) N * 4));
     GemmArgs g;
     g.dtype = dtype == 1 ? DType::BF16 : DType::F16;

@@ -8,11 +8,13 @@
 // (src/whisper.cpp:2006-2014, 2112-2237, 2300-2339; on CUDA: cublasGemmEx + convert + k_bin_bcast + unary kernels,
 // ggml/src/ggml-cuda/ggml-cuda.cu:1228-1382).
 //
-// Structure (one CTA per SM, persistent over output tiles, 256 threads):
+// Structure (one CTA per SM, persistent over output tiles, 384 threads):
 //   warp 0      : TMA producer   (one elected lane)       global -> smem ring, kStages deep
 //   warp 1      : MMA issuer     (one elected lane)       tcgen05.mma 128 x BN x 16, accumulates over K in TMEM
 //   warp 2      : TMEM allocator (2 accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1)
-//   warps 4..7  : epilogue       tcgen05.ld -> registers -> bias / scale / GELU / positional add / residual -> global
+//   warps 4..11 : epilogue       tcgen05.ld -> registers -> bias / scale / GELU / positional add / residual -> global
+//                 (warp % 4 selects the TMEM lane quarter, (warp-4)/4 the column half; two warps per SM sub-partition
+//                  so MUFU/convert latency of the GELU epilogue hides behind the other warp)
 #include "tc_gemm.h"
 
 #include <cuda.h>
@@ -27,8 +29,9 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;           // 64 x 16-bit = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int kThreads = 256;
 constexpr int kEpiWarp0 = 4;
+constexpr int kEpiWarps = 8;        // two per SM sub-partition: lane quarter = warp % 4, column half = (warp-4)/4
+constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;
 
 template <int BN> struct Cfg {
     static constexpr int kStages = BN == 256 ? 4 : 6;
@@ -59,11 +62,10 @@ struct EpiParams {
 template <typename T16> __device__ __forceinline__ float gelu_epi(float v, int ref_f16) {
     if (ref_f16) {
         // ggml_vec_gelu_f32 with GGML_GELU_FP16 (reference ggml/src/ggml-cpu/vec.h:996-1009): table lookup on the
-        // f16-rounded input, f16 result; identity / zero outside (-10, 10).
-        if (v <= -10.0f) return 0.0f;
-        if (v >= 10.0f) return v;
+        // f16-rounded input, f16 result; identity / zero outside (-10, 10).  Branch-free.
         const float x = __half2float(__float2half_rn(v));
-        return __half2float(__float2half_rn(gelu_tanh(x)));
+        const float y = __half2float(__float2half_rn(gelu_tanh(x)));
+        return v <= -10.0f ? 0.0f : (v >= 10.0f ? v : y);
     }
     return gelu_tanh(v);
 }
@@ -104,7 +106,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tfull_bar[i], 1);
-            ptx::mbar_init(&tempty_bar[i], 4);     // one arrive per epilogue warp
+            ptx::mbar_init(&tempty_bar[i], kEpiWarps);   // one arrive per epilogue warp
         }
         ptx::fence_mbar_init();
     }
@@ -175,7 +177,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
     } else if (warp >= kEpiWarp0) {
         // ===== epilogue =====
-        const int ew = warp - kEpiWarp0;               // == warp % 4: TMEM lane quarter this warp may read
+        const int ew = warp & 3;                       // TMEM lane quarter this warp may read (warp % 4)
+        const int chalf = (warp - kEpiWarp0) >> 2;     // which half of the tile's columns
         int acc = 0;
         uint32_t acc_phase = 0;
         T16 * out16 = reinterpret_cast<T16 *>(ep.out16);
@@ -189,7 +192,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const float * pos_row = ep.pos ? ep.pos + (size_t) (row % ep.pos_rows) * ep.N : nullptr;
             const float * res_row = ep.resid ? ep.resid + (size_t) row * ep.ldr : nullptr;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = chalf * (BN / 64); c < (chalf + 1) * (BN / 64); ++c) {
                 const int col0 = n0 + c * 32;
                 if (col0 >= ep.N) break;               // warp-uniform
                 uint32_t r[32];

@@ -24,7 +24,7 @@ def _has_gpu():
 def lib():
     """The product library.  GPU tests must never silently pass without it."""
     import open_whisper_kit_b200 as pkg
-    lib = pkg.load()
+    lib = pkg.load(strict_api=False)
     if lib.whisper_b200_device_count() <= 0:
         pytest.fail("no CUDA device visible: GPU parity tests cannot run (there is no CPU fallback)")
     return lib
