@@ -13,6 +13,8 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include "whisper.h"
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -23,11 +25,38 @@ extern "C" {
 #define WB200_API
 #endif
 
-struct whisper_context;
-struct whisper_state;
-
 /* Number of CUDA devices visible to the library (0 when there is none: every compute entry point then fails). */
 WB200_API int whisper_b200_device_count(void);
+
+/* ---- (1) device-resident / batched path and read-back of intermediates ------------------------------------ */
+
+/* whisper_full_parallel for PCM that already lives in device memory (d_samples is a CUDA device pointer on the
+ * context's GPU): the audio is split in n_processors equal chunks (one 30 s window each when
+ * n_samples == n_processors * 480000) which are decoded as ONE device batch.  Results are read with the usual
+ * whisper_full_get_* accessors.  Same return codes as whisper_full (reference include/whisper.h:603-620). */
+WB200_API int whisper_b200_full_device(struct whisper_context * ctx, struct whisper_full_params params,
+                                       const float * d_samples, int n_samples, int n_processors);
+
+/* The reference's mel container [n_mel][n_len] (f32, clamped + normalised) of a state (NULL = default state),
+ * which the reference API never exposes (whisper_state::mel, reference src/whisper.cpp:414-420).  out == NULL
+ * returns only the geometry. */
+WB200_API int whisper_b200_get_mel(struct whisper_context * ctx, struct whisper_state * state, float * out, int cap,
+                                   int * n_len, int * n_mel);
+
+/* Encoder output [1500][n_audio_state] f32 of the last whisper_encode on this context
+ * (whisper_state::embd_enc, reference src/whisper.cpp:2241-2251). */
+WB200_API int whisper_b200_get_encoder_output(struct whisper_context * ctx, float * out, int n_floats);
+
+/* Cross-attention K|V of one text layer after whisper_encode: [1500][2*n_text_state] 16-bit patterns
+ * (kv_cross, reference src/whisper.cpp:2300-2339; K carries the dh^-0.25 scale). */
+WB200_API int whisper_b200_get_cross_kv(struct whisper_context * ctx, int layer, uint16_t * out, int n_elems);
+
+/* 16-bit operand type of the tensor path: 0 = f16 (default; bit-exact weights of F16 model files), 1 = bf16
+ * (environment WHISPER_B200_DTYPE=bf16 at context creation). */
+WB200_API int whisper_b200_dtype(struct whisper_context * ctx);
+
+/* Number of kernels of this library launched on the context so far. */
+WB200_API long long whisper_b200_kernel_launches(struct whisper_context * ctx);
 
 /* ---- (2) kernel hooks ------------------------------------------------------------------------------------- */
 

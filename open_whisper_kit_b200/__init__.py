@@ -24,6 +24,12 @@ EXT_PROTOTYPES = {
     "whisper_b200_kernel_gemm": (_C.c_int, [_C.c_int, _C.c_int, _C.c_int, _C.c_int, _U16P, _U16P, _FP, _C.c_float,
                                             _C.c_int, _C.c_int, _FP, _C.c_int, _FP, _U16P, _FP]),
     "whisper_b200_kernel_gemm_bench": (_C.c_double, [_C.c_int, _C.c_int, _C.c_int, _C.c_int, _C.c_int, _C.c_int]),
+    "whisper_b200_full_device": (_C.c_int, [_C.c_void_p, capi.whisper_full_params, _C.c_void_p, _C.c_int, _C.c_int]),
+    "whisper_b200_get_mel": (_C.c_int, [_C.c_void_p, _C.c_void_p, _FP, _C.c_int, _IP, _IP]),
+    "whisper_b200_get_encoder_output": (_C.c_int, [_C.c_void_p, _FP, _C.c_int]),
+    "whisper_b200_get_cross_kv": (_C.c_int, [_C.c_void_p, _C.c_int, _U16P, _C.c_int]),
+    "whisper_b200_dtype": (_C.c_int, [_C.c_void_p]),
+    "whisper_b200_kernel_launches": (_C.c_longlong, [_C.c_void_p]),
 }
 
 _lib = None

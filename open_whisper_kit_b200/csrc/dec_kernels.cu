@@ -1,0 +1,444 @@
+// Decoder-step kernels: token+position embedding, KV append, masked self-attention over the device-resident
+// KV cache, cross-attention over the per-window cross K/V, and the on-device logit rules + greedy selection.
+//
+// Reference operators replaced (src/whisper.cpp):
+//   embed        ggml_get_rows(d_te) + ggml_get_rows(d_pe) + add                      2515-2519
+//   kv_append    ggml_cpy(Kcur/Vcur -> kv_self views)                                  2559-2590
+//   self_attn    KQ = K*Q, soft_max_ext(KQ, mask), KQV  (mask built on the host 2908-2940)   2594-2632
+//   cross_attn   KQ = Kcross*Q, soft_max_ext(scale), KQV                               2680-2742
+//   sample       whisper_process_logits + whisper_sample_token(best) on the host      6177-6445, 6460-6517
+#include "dec_kernels.h"
+
+namespace wb {
+
+namespace {
+
+template <typename T16>
+__global__ void embed_kernel(const T16 * __restrict__ te, const float * __restrict__ pe, const DecRow * __restrict__ rows,
+                             int d, float * __restrict__ x) {
+    const int r = blockIdx.x;
+    const DecRow row = rows[r];
+    const T16 * t = te + (size_t) row.token * d;
+    const float * p = pe + (size_t) row.pos * d;
+    for (int c = threadIdx.x; c < d; c += blockDim.x) x[(size_t) r * d + c] = Half16<T16>::to_f(t[c]) + p[c];
+}
+
+// qkv [R][3d] -> self_kv[layer][pos][0..2d) = (K | V)
+__global__ void kv_append_kernel(const uint4 * __restrict__ qkv, const DecRow * __restrict__ rows, int d8,
+                                 size_t layer_off8) {
+    const int r = blockIdx.x;
+    const DecRow row = rows[r];
+    uint4 * dst = reinterpret_cast<uint4 *>(row.self_kv) + layer_off8 + (size_t) row.pos * (2 * d8);
+    const uint4 * src = qkv + (size_t) r * (3 * d8) + d8;
+    for (int c = threadIdx.x; c < 2 * d8; c += blockDim.x) dst[c] = src[c];
+}
+
+// One warp per (row, head).  Scores over positions 0..pos of the row's slot (causal), softmax in f32, probabilities
+// rounded to the 16-bit operand type before the PV product (as the reference's KQV mul_mat does), f32 accumulation.
+template <typename T16>
+__global__ void self_attn_kernel(const T16 * __restrict__ qkv, const DecRow * __restrict__ rows, int d, int n_head,
+                                 size_t layer_off, int n_ctx, T16 * __restrict__ out) {
+    extern __shared__ float s_scores[];      // [warps][n_ctx]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int idx = blockIdx.x * (blockDim.x >> 5) + warp;
+    const int r = idx / n_head, h = idx % n_head;
+    float * sc = s_scores + (size_t) warp * n_ctx;
+    const DecRow row = rows[r];
+    const int n_kv = row.pos + 1;
+    const T16 * kbase = reinterpret_cast<const T16 *>(row.self_kv) + layer_off + h * 64;
+    const int ld = 2 * d;
+
+    // q (64 values) in registers of every lane
+    float q[64];
+    {
+        const uint4 * qp = reinterpret_cast<const uint4 *>(qkv + (size_t) r * 3 * d + h * 64);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint4 u = qp[i];
+            const T16 * e = reinterpret_cast<const T16 *>(&u);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) q[i * 8 + j] = Half16<T16>::to_f(e[j]);
+        }
+    }
+    float mx = -INFINITY;
+    for (int p = lane; p < n_kv; p += 32) {
+        const uint4 * kp = reinterpret_cast<const uint4 *>(kbase + (size_t) p * ld);
+        float acc = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint4 u = kp[i];
+            const T16 * e = reinterpret_cast<const T16 *>(&u);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc = fmaf(q[i * 8 + j], Half16<T16>::to_f(e[j]), acc);
+        }
+        sc[p] = acc;
+        mx = fmaxf(mx, acc);
+    }
+    mx = warp_max(mx);
+    float sum = 0.0f;
+    for (int p = lane; p < n_kv; p += 32) {
+        const float e = expf(sc[p] - mx);
+        sc[p] = e;
+        sum += e;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    __syncwarp();
+    // PV: lane owns dims 2*lane, 2*lane+1
+    const T16 * vbase = kbase + d;
+    float o0 = 0.0f, o1 = 0.0f;
+    for (int p = 0; p < n_kv; ++p) {
+        const float pr = Half16<T16>::to_f(Half16<T16>::from_f(sc[p] * inv));
+        const T16 * vp = vbase + (size_t) p * ld + 2 * lane;
+        o0 = fmaf(pr, Half16<T16>::to_f(vp[0]), o0);
+        o1 = fmaf(pr, Half16<T16>::to_f(vp[1]), o1);
+    }
+    T16 * op = out + (size_t) r * d + h * 64 + 2 * lane;
+    op[0] = Half16<T16>::from_f(o0);
+    op[1] = Half16<T16>::from_f(o1);
+}
+
+// One CTA (128 threads) per (row, head) streaming the window's cross K/V: 8 lanes x 16 bytes cover one 64-value key
+// row, so every warp-wide load instruction reads four whole 128-byte rows.  kv: [xslot][layer][T][2d] (K | V), K already
+// carries dh^-0.25 (cross graph, src/whisper.cpp:2300-2305); score = (q.k) * dh^-0.25 (src/whisper.cpp:2695, 2719).
+template <typename T16>
+__global__ void __launch_bounds__(128)
+cross_attn_kernel(const T16 * __restrict__ q, const DecRow * __restrict__ rows, int d, size_t layer_off, int T,
+                  float kq_scale, int n_phantom, T16 * __restrict__ out) {
+    extern __shared__ float s_sc[];          // [T]
+    __shared__ float s_red[8];
+    __shared__ float s_o[4][64];
+    const int r = blockIdx.x, h = blockIdx.y;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int sub = lane & 7, grp = lane >> 3;     // 8 lanes per key row, 4 key rows per warp instruction
+    const DecRow row = rows[r];
+    const T16 * kbase = reinterpret_cast<const T16 *>(row.cross_kv) + layer_off + h * 64;
+    const int ld = 2 * d;
+
+    float qv[8];
+    {
+        const uint4 u = *reinterpret_cast<const uint4 *>(q + (size_t) r * d + h * 64 + sub * 8);
+        const T16 * e = reinterpret_cast<const T16 *>(&u);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) qv[j] = Half16<T16>::to_f(e[j]);
+    }
+    float mx = -INFINITY;
+    for (int t0 = warp * 4; t0 < T; t0 += 16) {
+        const int t = t0 + grp;
+        float acc = 0.0f;
+        if (t < T) {
+            const uint4 u = __ldg(reinterpret_cast<const uint4 *>(kbase + (size_t) t * ld + sub * 8));
+            const T16 * e = reinterpret_cast<const T16 *>(&u);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc = fmaf(qv[j], Half16<T16>::to_f(e[j]), acc);
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        acc *= kq_scale;
+        if (t < T) {
+            if (sub == 0) s_sc[t] = acc;
+            mx = fmaxf(mx, acc);
+        }
+    }
+    mx = warp_max(mx);
+    if (lane == 0) s_red[warp] = mx;
+    __syncthreads();
+    mx = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
+    if (n_phantom > 0) mx = fmaxf(mx, 0.0f);
+    float sum = 0.0f;
+    for (int t = tid; t < T; t += 128) {
+        const float e = expf(s_sc[t] - mx);
+        s_sc[t] = e;
+        sum += e;
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) s_red[4 + warp] = sum;
+    __syncthreads();
+    sum = s_red[4] + s_red[5] + s_red[6] + s_red[7];
+    if (n_phantom > 0) sum += (float) n_phantom * expf(-mx);
+    const float inv = 1.0f / sum;
+
+    const T16 * vbase = kbase + d;
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = 0.0f;
+    for (int t0 = warp * 4; t0 < T; t0 += 16) {
+        const int t = t0 + grp;
+        if (t < T) {
+            const float pr = Half16<T16>::to_f(Half16<T16>::from_f(s_sc[t] * inv));
+            const uint4 u = __ldg(reinterpret_cast<const uint4 *>(vbase + (size_t) t * ld + sub * 8));
+            const T16 * e = reinterpret_cast<const T16 *>(&u);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = fmaf(pr, Half16<T16>::to_f(e[j]), o[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        o[j] += __shfl_xor_sync(0xffffffffu, o[j], 8);
+        o[j] += __shfl_xor_sync(0xffffffffu, o[j], 16);
+    }
+    if (grp == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s_o[warp][sub * 8 + j] = o[j];
+    }
+    __syncthreads();
+    if (tid < 64) {
+        const float v = s_o[0][tid] + s_o[1][tid] + s_o[2][tid] + s_o[3][tid];
+        out[(size_t) r * d + h * 64 + tid] = Half16<T16>::from_f(v);
+    }
+}
+
+// ---- logit rules + greedy selection ------------------------------------------------------------------------
+struct ArgMax {
+    float v;
+    int i;
+};
+__device__ __forceinline__ ArgMax amax(ArgMax a, ArgMax b) {        // larger value, then lower index
+    return (b.v > a.v || (b.v == a.v && b.i < a.i)) ? b : a;
+}
+__device__ __forceinline__ ArgMax warp_amax(ArgMax a) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ArgMax b;
+        b.v = __shfl_xor_sync(0xffffffffu, a.v, o);
+        b.i = __shfl_xor_sync(0xffffffffu, a.i, o);
+        a = amax(a, b);
+    }
+    return a;
+}
+
+template <int NT> __device__ float block_max(float v, float * sh) {
+    v = warp_max(v);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = sh[0];
+    for (int i = 1; i < NT / 32; ++i) r = fmaxf(r, sh[i]);
+    __syncthreads();
+    return r;
+}
+template <int NT> __device__ float block_sum(float v, float * sh) {
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = 0.0f;
+    for (int i = 0; i < NT / 32; ++i) r += sh[i];
+    __syncthreads();
+    return r;
+}
+template <int NT> __device__ double block_sum_d(double v, double * sh) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = 0.0;
+    for (int i = 0; i < NT / 32; ++i) r += sh[i];
+    __syncthreads();
+    return r;
+}
+template <int NT> __device__ ArgMax block_amax(ArgMax a, ArgMax * sh) {
+    a = warp_amax(a);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = a;
+    __syncthreads();
+    ArgMax r = sh[0];
+    for (int i = 1; i < NT / 32; ++i) r = amax(r, sh[i]);
+    __syncthreads();
+    return r;
+}
+
+constexpr int SAMPLE_THREADS = 1024;
+
+// One CTA per decoder row.  Rule order follows whisper_process_logits line by line; the masked logits are written
+// back in place so the later passes (max, sum-exp, timestamp mass, arg-max) read them from L2.
+__global__ void __launch_bounds__(SAMPLE_THREADS)
+sample_greedy_kernel(float * __restrict__ logits, int ld, const SampleRow * __restrict__ srows,
+                     const uint32_t * __restrict__ static_mask, SampleParams prm, SampleOut * __restrict__ outs) {
+    __shared__ float sh_f[SAMPLE_THREADS / 32];
+    __shared__ double sh_d[SAMPLE_THREADS / 32];
+    __shared__ ArgMax sh_a[SAMPLE_THREADS / 32];
+    const int r = blockIdx.x;
+    const SampleRow sr = srows[r];
+    float * l = logits + (size_t) sr.logits_row * ld;
+    const int V = prm.n_vocab, beg = prm.token_beg, eot = prm.token_eot;
+    const int tid = threadIdx.x;
+
+    const bool is_initial = sr.n_tokens == 0;
+    const bool last_ts = sr.n_tokens > 0 && sr.last >= beg;
+    const bool pen_ts = sr.n_tokens < 2 || sr.penult >= beg;
+    const int init_lim = (is_initial && prm.max_initial_ts > 0.0f) ? beg + prm.tid0 + 1 : V;
+    const int mono_lim = sr.has_ts ? beg + sr.seek_delta / 2 : beg;
+    const float inv_temp = prm.temperature > 0.0f ? prm.temperature : 1.0f;
+
+    // pass 1: rules -> masked logits; track max over all, over timestamps, over text
+    float m_all = -INFINITY;
+    for (int i = tid; i < V; i += SAMPLE_THREADS) {
+        float v = l[i];
+        if (prm.temperature > 0.0f) v = v / inv_temp;
+        bool kill = (static_mask[i >> 5] >> (i & 31)) & 1u;
+        if (is_initial && prm.suppress_blank && (i == eot || i == prm.token_space)) kill = true;
+        if (prm.no_timestamps && i >= beg) kill = true;
+        if (last_ts) {
+            if (pen_ts) {
+                if (i >= beg) kill = true;
+            } else {
+                if (i < eot) kill = true;
+            }
+        }
+        if (i >= init_lim) kill = true;
+        if (i >= beg && i < mono_lim) kill = true;
+        if (kill) v = -INFINITY;
+        l[i] = v;
+        m_all = fmaxf(m_all, v);
+    }
+    m_all = block_max<SAMPLE_THREADS>(m_all, sh_f);
+    __syncthreads();
+
+    // pass 2: log-sum-exp  (whisper_compute_logprobs, src/whisper.cpp:6137-6158)
+    float se = 0.0f;
+    for (int i = tid; i < V; i += SAMPLE_THREADS) {
+        const float v = l[i];
+        if (v > -INFINITY) se += expf(v - m_all);
+    }
+    se = block_sum<SAMPLE_THREADS>(se, sh_f);
+    const float logZ = logf(se) + m_all;
+
+    // pass 3: timestamp mass vs best text token  (src/whisper.cpp:6336-6361)
+    float lp_ts_max = -INFINITY, lp_text_max = -INFINITY;
+    for (int i = tid; i < V; i += SAMPLE_THREADS) {
+        const float v = l[i];
+        const float lp = v > -INFINITY ? v - logZ : -INFINITY;
+        if (i >= beg) lp_ts_max = fmaxf(lp_ts_max, lp);
+        else lp_text_max = fmaxf(lp_text_max, lp);
+    }
+    lp_ts_max = block_max<SAMPLE_THREADS>(lp_ts_max, sh_f);
+    lp_text_max = block_max<SAMPLE_THREADS>(lp_text_max, sh_f);
+    float ts_se = 0.0f;
+    for (int i = beg + tid; i < V; i += SAMPLE_THREADS) {
+        const float v = l[i];
+        if (v > -INFINITY) ts_se += expf((v - logZ) - lp_ts_max);
+    }
+    ts_se = block_sum<SAMPLE_THREADS>(ts_se, sh_f);
+    float ts_lp = -INFINITY;
+    if (ts_se > 0.0f) ts_lp = logf(ts_se) + lp_ts_max;
+    const bool mask_text = ts_lp > lp_text_max;
+
+    // pass 4: probs, greedy arg-max (first maximal index), timestamp statistics  (src/whisper.cpp:6460-6517)
+    ArgMax best = {0.0f, 0x7fffffff}, best_ts = {0.0f, 0x7fffffff};
+    double sum_ts = 0.0;
+    for (int i = tid; i < V; i += SAMPLE_THREADS) {
+        const float v = l[i];
+        float p = 0.0f;
+        if (v > -INFINITY && !(mask_text && i < beg)) p = expf(v - logZ);
+        if (p > 0.0f) {
+            best = amax(best, ArgMax{p, i});
+            if (i >= beg) {
+                best_ts = amax(best_ts, ArgMax{p, i});
+            }
+        }
+        if (i >= beg) sum_ts += (double) p;
+    }
+    best = block_amax<SAMPLE_THREADS>(best, sh_a);
+    best_ts = block_amax<SAMPLE_THREADS>(best_ts, sh_a);
+    sum_ts = block_sum_d<SAMPLE_THREADS>(sum_ts, sh_d);
+    if (tid == 0) {
+        SampleOut o;
+        o.id = best.i == 0x7fffffff ? 0 : best.i;
+        o.p = best.i == 0x7fffffff ? 0.0f : best.v;
+        o.plog = best.i == 0x7fffffff ? 0.0f : (l[o.id] - logZ);
+        o.tid = best_ts.i == 0x7fffffff ? 0 : best_ts.i;
+        o.pt = (float) ((double) (best_ts.i == 0x7fffffff ? 0.0f : best_ts.v) / (sum_ts + 1e-10));
+        o.ptsum = (float) sum_ts;
+        if (o.id >= beg) {
+            o.tid = o.id;
+            o.pt = o.p;
+        }
+        outs[r] = o;
+    }
+}
+
+// softmax probability of one token on the RAW logits row (no_speech_prob, src/whisper.cpp:7188-7196)
+__global__ void __launch_bounds__(SAMPLE_THREADS)
+token_prob_kernel(const float * __restrict__ logits, int ld, const SampleRow * __restrict__ srows, int V, int token,
+                  float * __restrict__ out) {
+    __shared__ float sh_f[SAMPLE_THREADS / 32];
+    const float * l = logits + (size_t) srows[blockIdx.x].logits_row * ld;
+    float m = -INFINITY;
+    for (int i = threadIdx.x; i < V; i += SAMPLE_THREADS) m = fmaxf(m, l[i]);
+    m = block_max<SAMPLE_THREADS>(m, sh_f);
+    float se = 0.0f;
+    for (int i = threadIdx.x; i < V; i += SAMPLE_THREADS) {
+        const float v = l[i];
+        if (v > -INFINITY) se += expf(v - m);
+    }
+    se = block_sum<SAMPLE_THREADS>(se, sh_f);
+    if (threadIdx.x == 0) out[blockIdx.x] = expf(l[token] - (logf(se) + m));
+}
+
+}  // namespace
+
+void dec_embed(DType dt, const void * te, const float * pe, const DecRow * d_rows, int R, int d, float * x,
+               cudaStream_t st) {
+    if (R <= 0) return;
+    if (dt == DType::F16)
+        embed_kernel<__half><<<R, 256, 0, st>>>(reinterpret_cast<const __half *>(te), pe, d_rows, d, x);
+    else
+        embed_kernel<__nv_bfloat16><<<R, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16 *>(te), pe, d_rows, d, x);
+    WB_CUDA(cudaGetLastError());
+}
+
+void dec_kv_append(const void * qkv, const DecRow * d_rows, int R, int d, size_t layer_off_elems, cudaStream_t st) {
+    if (R <= 0) return;
+    kv_append_kernel<<<R, 128, 0, st>>>(reinterpret_cast<const uint4 *>(qkv), d_rows, d / 8, layer_off_elems / 8);
+    WB_CUDA(cudaGetLastError());
+}
+
+template <typename T16>
+static void self_attn_launch(const void * qkv, const DecRow * d_rows, int R, int d, int n_head, size_t layer_off, int n_ctx,
+                             void * out, cudaStream_t st) {
+    const int total = R * n_head;
+    // the kernel maps idx = block*warps + warp -> (row, head); launch exact multiples only
+    const int warps = (total % 4 == 0) ? 4 : ((total % 2 == 0) ? 2 : 1);
+    const size_t smem = (size_t) warps * n_ctx * sizeof(float);
+    self_attn_kernel<T16><<<total / warps, warps * 32, smem, st>>>(reinterpret_cast<const T16 *>(qkv), d_rows, d, n_head,
+                                                                    layer_off, n_ctx, reinterpret_cast<T16 *>(out));
+}
+
+void dec_self_attn(DType dt, const void * qkv, const DecRow * d_rows, int R, int d, int n_head, size_t layer_off_elems,
+                   int n_ctx, void * out, cudaStream_t st) {
+    if (R <= 0) return;
+    if (dt == DType::F16) self_attn_launch<__half>(qkv, d_rows, R, d, n_head, layer_off_elems, n_ctx, out, st);
+    else self_attn_launch<__nv_bfloat16>(qkv, d_rows, R, d, n_head, layer_off_elems, n_ctx, out, st);
+    WB_CUDA(cudaGetLastError());
+}
+
+void dec_cross_attn(DType dt, const void * q, const DecRow * d_rows, int R, int d, int n_head, size_t layer_off_elems,
+                    int T, int n_phantom, void * out, cudaStream_t st) {
+    if (R <= 0) return;
+    dim3 grid(R, n_head);
+    const float kq_scale = powf(64.0f, -0.25f);
+    const size_t smem = (size_t) T * sizeof(float);
+    if (dt == DType::F16)
+        cross_attn_kernel<__half><<<grid, 128, smem, st>>>(reinterpret_cast<const __half *>(q), d_rows, d, layer_off_elems,
+                                                           T, kq_scale, n_phantom, reinterpret_cast<__half *>(out));
+    else
+        cross_attn_kernel<__nv_bfloat16><<<grid, 128, smem, st>>>(reinterpret_cast<const __nv_bfloat16 *>(q), d_rows, d,
+                                                                  layer_off_elems, T, kq_scale, n_phantom,
+                                                                  reinterpret_cast<__nv_bfloat16 *>(out));
+    WB_CUDA(cudaGetLastError());
+}
+
+void dec_sample_greedy(float * logits, int ld, const SampleRow * d_srows, int R, const uint32_t * d_static_mask,
+                       const SampleParams & prm, SampleOut * d_out, cudaStream_t st) {
+    if (R <= 0) return;
+    sample_greedy_kernel<<<R, SAMPLE_THREADS, 0, st>>>(logits, ld, d_srows, d_static_mask, prm, d_out);
+    WB_CUDA(cudaGetLastError());
+}
+
+void dec_token_prob(const float * logits, int ld, const SampleRow * d_srows, int R, int n_vocab, int token, float * d_out,
+                    cudaStream_t st) {
+    if (R <= 0) return;
+    token_prob_kernel<<<R, SAMPLE_THREADS, 0, st>>>(logits, ld, d_srows, n_vocab, token, d_out);
+    WB_CUDA(cudaGetLastError());
+}
+
+}  // namespace wb

@@ -1,0 +1,53 @@
+// Decoder-step kernels (dec_kernels.cu).
+#pragma once
+
+#include "common.cuh"
+
+namespace wb {
+
+// One token row of a decoder batch (device memory).  Replaces whisper_batch + the host-built KQ mask
+// (reference src/whisper.cpp:472-523, 2908-2940): causality is "positions 0..pos of the row's own slot".
+struct DecRow {
+    int          token;
+    int          pos;       // position in the text context (n_past + i)
+    void *       self_kv;   // this sequence's self-attention cache   [n_text_layer][n_text_ctx][2d]  (K | V)
+    const void * cross_kv;  // this window's cross K/V, layer 0       [1500][2d] (K | V); layers are layer_stride apart
+};
+
+// Per-row decoder state the logit rules depend on (reference whisper_decoder, src/whisper.cpp:797-820).
+struct SampleRow {
+    int logits_row;   // row of the logits buffer
+    int n_tokens;     // tokens sampled so far in this window (0 -> "initial")
+    int last;         // last / penultimate sampled token ids (valid if n_tokens >= 1 / 2)
+    int penult;
+    int has_ts;
+    int seek_delta;
+};
+
+struct SampleParams {
+    int n_vocab;
+    int token_eot, token_beg, token_space;
+    int suppress_blank, no_timestamps;
+    float max_initial_ts;
+    int tid0;            // round(max_initial_ts / 0.02)
+    float temperature;
+};
+
+struct SampleOut {       // the float fields of whisper_token_data (include/whisper.h)
+    int id, tid;
+    float p, plog, pt, ptsum;
+};
+
+void dec_embed(DType dt, const void * te, const float * pe, const DecRow * d_rows, int R, int d, float * x,
+               cudaStream_t st);
+void dec_kv_append(const void * qkv, const DecRow * d_rows, int R, int d, size_t layer_off_elems, cudaStream_t st);
+void dec_self_attn(DType dt, const void * qkv, const DecRow * d_rows, int R, int d, int n_head, size_t layer_off_elems,
+                   int n_ctx, void * out, cudaStream_t st);
+void dec_cross_attn(DType dt, const void * q, const DecRow * d_rows, int R, int d, int n_head, size_t layer_off_elems,
+                    int T, int n_phantom, void * out, cudaStream_t st);
+void dec_sample_greedy(float * logits, int ld, const SampleRow * d_srows, int R, const uint32_t * d_static_mask,
+                       const SampleParams & prm, SampleOut * d_out, cudaStream_t st);
+void dec_token_prob(const float * logits, int ld, const SampleRow * d_srows, int R, int n_vocab, int token, float * d_out,
+                    cudaStream_t st);
+
+}  // namespace wb

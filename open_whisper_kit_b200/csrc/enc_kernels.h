@@ -1,0 +1,31 @@
+// Encoder-side kernels around the GEMMs (enc_kernels.cu).
+#pragma once
+
+#include "common.cuh"
+
+namespace wb {
+
+// One 30 s encoder window of a batched launch (device memory).
+struct EncWindow {
+    const float *    mel;           // stream's mel, [n_mel][stride]: raw log10 (finalized == 0) or final values
+    int              stride;
+    int              n_len;         // frames the reference container holds; beyond it the window is zero
+    int              n_frames_fft;  // frames stored in the raw buffer; [n_frames_fft, n_len) is the constant -10
+    int              seek;          // first mel frame of the window (mel_offset, src/whisper.cpp:2381-2403)
+    const unsigned * max_enc;       // ordered-uint max of the raw mel (mel.cu); unused when finalized
+    int              finalized;
+};
+
+void im2col1(DType dt, const EncWindow * d_wins, int n_windows, int n_mel, int k_pad, void * out /*[W*3000][k_pad]*/,
+             cudaStream_t st);
+void im2col2(const void * act1 /*[W*3000][d]*/, int n_windows, int d, void * out /*[W*1500][3d]*/, cudaStream_t st);
+
+// y = LayerNorm(x[row_map ? row_map[m] : m]) for m < M; 16-bit and/or f32 outputs.
+void layernorm(DType dt, const float * x, int ldx, const float * gamma, const float * beta, float eps, int M, int d,
+               void * y16, int ldy16, float * y32, int ldy32, const int * row_map, cudaStream_t st);
+
+// Non-causal self-attention over T positions per window, dh = 64.  qkv [W*T][3d] -> out [W*T][d].
+void enc_attention(DType dt, const void * qkv, void * out, int n_windows, int T, int d, int n_head, int n_phantom,
+                   cudaStream_t st);
+
+}  // namespace wb

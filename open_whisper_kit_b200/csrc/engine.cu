@@ -1,0 +1,430 @@
+// Batched device engine (see engine.h).  Launch sequences for the three stages of the path:
+//   run_mel   <- log_mel_spectrogram                                   reference src/whisper.cpp:3170-3260
+//   encode    <- whisper_encode_internal (conv + encoder + cross)      reference src/whisper.cpp:2358-2456
+//   decode    <- whisper_decode_internal / whisper_build_graph_decoder reference src/whisper.cpp:2458-2978
+// Every GEMM is tc_gemm (tcgen05) with its bias / scale / GELU / residual fused; nothing is computed on the host.
+#include "engine.h"
+
+#include <string.h>
+
+#include "tc_gemm.h"
+
+namespace wb {
+
+bool DeviceBlock::reserve(size_t bytes, bool keep) {
+    if (bytes <= cap) return true;
+    const size_t ncap = round_up<size_t>(bytes + bytes / 8, 1 << 20);
+    void * np = nullptr;
+    WB_CUDA(cudaMalloc(&np, ncap));
+    if (!np) return false;
+    if (p) {
+        if (keep && cap) WB_CUDA(cudaMemcpy(np, p, cap, cudaMemcpyDeviceToDevice));
+        WB_CUDA(cudaFree(p));
+    }
+    p = np;
+    cap = ncap;
+    return true;
+}
+DeviceBlock::~DeviceBlock() {
+    if (p) cudaFree(p);
+}
+
+namespace {
+__global__ void kv_copy_prefix_kernel(const uint4 * __restrict__ src, uint4 * __restrict__ dst, size_t layer_stride8,
+                                      size_t n8) {
+    const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n8) dst[blockIdx.y * layer_stride8 + i] = src[blockIdx.y * layer_stride8 + i];
+}
+}  // namespace
+
+bool Engine::init(int dev, bool fa) {
+    device = dev;
+    flash_attn = fa;
+    cuda_clear_failure();
+    WB_CUDA(cudaSetDevice(device));
+    WB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    if (cuda_failed()) return false;
+    if (!mel_plan_init(mel_plan, model.filters.data(), model.filt_n_mel, model.filt_n_fft)) {
+        wlog(GGML_LOG_LEVEL_ERROR, "%s: mel filterbank of the model is not usable (n_mel=%d, n_fft=%d)\n", __func__,
+             model.filt_n_mel, model.filt_n_fft);
+        return false;
+    }
+    ld_logits = round_up(model.hp.n_vocab, 8);
+    return true;
+}
+
+Engine::~Engine() {
+    for (int i = 0; i < 2; ++i)
+        if (h_pinned[i]) cudaFreeHost(h_pinned[i]);
+    if (stream) cudaStreamDestroy(stream);
+}
+
+void * Engine::pinned(int which, size_t bytes) {
+    if (bytes > h_pinned_cap[which]) {
+        WB_CUDA(cudaStreamSynchronize(stream));     // nothing may still be reading the old block
+        if (h_pinned[which]) cudaFreeHost(h_pinned[which]);
+        h_pinned_cap[which] = round_up<size_t>(bytes, 1 << 16);
+        WB_CUDA(cudaMallocHost(&h_pinned[which], h_pinned_cap[which]));
+    }
+    return h_pinned[which];
+}
+
+// ---- mel ------------------------------------------------------------------------------------------------
+bool Engine::run_mel(const std::vector<MelJob> & jobs) {
+    if (jobs.empty()) return true;
+    WB_CUDA(cudaSetDevice(device));
+    const int n_mel = model.filt_n_mel;
+    size_t stage_floats = 0;
+    for (const auto & j : jobs)
+        if (j.pcm_host) stage_floats += round_up<size_t>(j.n_samples, 4);
+    if (!pcm_stage.reserve(stage_floats * 4)) return false;
+    if (!meta.reserve(jobs.size() * sizeof(MelStream))) return false;
+    std::vector<MelStream> sts(jobs.size());
+    size_t off = 0;
+    int max_frames = 0;
+    for (size_t i = 0; i < jobs.size(); ++i) {
+        const MelJob & j = jobs[i];
+        MelBuf & mb = *j.out;
+        const MelGeometry g = mel_geometry(j.n_samples);
+        mb.n_mel = n_mel;
+        mb.n_len = g.n_len;
+        mb.n_len_org = g.n_len_org;
+        mb.n_frames_fft = g.n_frames_fft;
+        mb.stride = g.stride;
+        mb.finalized = false;
+        mb.valid = true;
+        if (!mb.data.reserve((size_t) n_mel * g.stride * 4) || !mb.max_enc.reserve(4)) return false;
+        WB_CUDA(cudaMemsetAsync(mb.max_enc.p, 0, 4, stream));
+        const float * src = j.pcm_dev;
+        if (j.pcm_host) {
+            float * dst = (float *) pcm_stage.p + off;
+            WB_CUDA(cudaMemcpyAsync(dst, j.pcm_host, (size_t) j.n_samples * 4, cudaMemcpyHostToDevice, stream));
+            src = dst;
+            off += round_up<size_t>(j.n_samples, 4);
+        }
+        sts[i] = {src, j.n_samples, g.n_frames_fft, (float *) mb.data.p, g.stride, (unsigned *) mb.max_enc.p};
+        max_frames = std::max(max_frames, g.n_frames_fft);
+    }
+    WB_CUDA(cudaMemcpyAsync(meta.p, sts.data(), sts.size() * sizeof(MelStream), cudaMemcpyHostToDevice, stream));
+    mel_launch(mel_plan, (const MelStream *) meta.p, (int) jobs.size(), max_frames, stream);
+    n_kernel_launches += 1;
+    WB_CUDA(cudaStreamSynchronize(stream));   // sts / host PCM go out of scope
+    return !cuda_failed();
+}
+
+bool Engine::set_mel(MelBuf & out, const float * data, int n_len, int n_mel) {
+    WB_CUDA(cudaSetDevice(device));
+    out.n_mel = n_mel;
+    out.n_len = n_len;
+    out.n_len_org = n_len;
+    out.n_frames_fft = n_len;
+    out.stride = n_len > 0 ? n_len : 1;
+    out.finalized = true;
+    out.valid = true;
+    if (!out.data.reserve((size_t) std::max(1, n_len) * n_mel * 4) || !out.max_enc.reserve(4)) return false;
+    if (n_len > 0) WB_CUDA(cudaMemcpy(out.data.p, data, (size_t) n_len * n_mel * 4, cudaMemcpyHostToDevice));
+    return !cuda_failed();
+}
+
+bool Engine::get_mel(const MelBuf & mel, float * out) {
+    if (!mel.valid) return false;
+    WB_CUDA(cudaSetDevice(device));
+    const size_t n = (size_t) mel.n_mel * mel.n_len;
+    if (mel.finalized) {
+        WB_CUDA(cudaMemcpy(out, mel.data.p, n * 4, cudaMemcpyDeviceToHost));
+    } else {
+        DeviceBlock tmp;
+        if (!tmp.reserve(n * 4)) return false;
+        mel_finalize_launch((const float *) mel.data.p, mel.stride, mel.n_frames_fft, (const unsigned *) mel.max_enc.p,
+                            (float *) tmp.p, mel.n_len, mel.n_mel, stream);
+        WB_CUDA(cudaMemcpyAsync(out, tmp.p, n * 4, cudaMemcpyDeviceToHost, stream));
+        WB_CUDA(cudaStreamSynchronize(stream));
+    }
+    return !cuda_failed();
+}
+
+// ---- encoder ----------------------------------------------------------------------------------------------
+bool Engine::size_cross(CrossKV & kv, int n_windows) {
+    const int d = model.hp.n_audio_state;
+    kv.n_windows = n_windows;
+    kv.layer_stride = (size_t) n_windows * 1500 * 2 * d;
+    return kv.data.reserve(kv.layer_stride * model.hp.n_text_layer * 2);
+}
+
+bool Engine::encode(const std::vector<EncJob> & jobs, CrossKV & kv, int win0, bool keep_embd32) {
+    const int W = (int) jobs.size();
+    if (W == 0) return true;
+    WB_CUDA(cudaSetDevice(device));
+    const auto & hp = model.hp;
+    const int d = hp.n_audio_state, H = hp.n_audio_head, T = 1500;
+    const DType dt = model.dtype;
+    const int n_mel = hp.n_mels;
+    const int k1 = model.conv1_kpad;
+    const size_t M1 = (size_t) W * 3000, M = (size_t) W * T;
+
+    size_t need = 0;
+    auto sz = [&](size_t b) { need += round_up<size_t>(b, 256); return b; };
+    sz(M1 * k1 * 2); sz(M1 * d * 2); sz(M * 3 * d * 2); sz(M * d * 4); sz(M * d * 2); sz(M * 3 * d * 2); sz(M * d * 2);
+    sz(M * 4 * d * 2); sz(M * d * 2); sz(W * sizeof(EncWindow));
+    if (!ws.begin(need)) return false;
+    void * A1 = ws.take(M1 * k1 * 2);
+    void * act1 = ws.take(M1 * d * 2);
+    void * A2 = ws.take(M * 3 * d * 2);
+    float * x = (float *) ws.take(M * d * 4);
+    void * h16 = ws.take(M * d * 2);
+    void * qkv = ws.take(M * 3 * d * 2);
+    void * att = ws.take(M * d * 2);
+    void * mlp = ws.take(M * 4 * d * 2);
+    void * enc16 = ws.take(M * d * 2);
+    EncWindow * d_wins = (EncWindow *) ws.take(W * sizeof(EncWindow));
+
+    std::vector<EncWindow> wins(W);
+    for (int i = 0; i < W; ++i) {
+        const MelBuf & mb = *jobs[i].mel;
+        if (!mb.valid || mb.n_mel != n_mel) {
+            wlog(GGML_LOG_LEVEL_ERROR, "%s: no mel for window %d (call whisper_pcm_to_mel / whisper_set_mel first)\n", __func__, i);
+            return false;
+        }
+        wins[i] = {(const float *) mb.data.p, mb.stride, mb.n_len, mb.n_frames_fft, jobs[i].seek,
+                   (const unsigned *) mb.max_enc.p, mb.finalized ? 1 : 0};
+    }
+    WB_CUDA(cudaMemcpyAsync(d_wins, wins.data(), W * sizeof(EncWindow), cudaMemcpyHostToDevice, stream));
+
+    bool ok = true;
+    auto gemm = [&](const GemmArgs & g) {
+        ok = ok && tc_gemm(g, stream);
+        n_kernel_launches += 1;
+    };
+
+    // conv stem: two GEMMs over im2col'd time-major activations, GELU fused; positional add fused into the second
+    im2col1(dt, d_wins, W, n_mel, k1, A1, stream);
+    {
+        GemmArgs g;
+        g.dtype = dt; g.M = (int) M1; g.N = d; g.K = k1; g.a = A1; g.lda = k1; g.w = model.conv1_w; g.ldw = k1;
+        g.bias = model.conv1_b; g.gelu = true; g.out16 = act1; g.ldo16 = d;
+        gemm(g);
+    }
+    im2col2(act1, W, d, A2, stream);
+    {
+        GemmArgs g;
+        g.dtype = dt; g.M = (int) M; g.N = d; g.K = 3 * d; g.a = A2; g.lda = 3 * d; g.w = model.conv2_w; g.ldw = 3 * d;
+        g.bias = model.conv2_b; g.gelu = true; g.pos = model.e_pe; g.pos_rows = T; g.out32 = x; g.ldo32 = d;
+        gemm(g);
+    }
+    n_kernel_launches += 2;
+
+    for (int il = 0; il < hp.n_audio_layer; ++il) {
+        const EncLayer & L = model.enc[il];
+        layernorm(dt, x, d, L.ln1_w, L.ln1_b, hp.eps, (int) M, d, h16, d, nullptr, 0, nullptr, stream);
+        {
+            GemmArgs g;
+            g.dtype = dt; g.M = (int) M; g.N = 3 * d; g.K = d; g.a = h16; g.lda = d; g.w = L.wqkv; g.ldw = d;
+            g.bias = L.bqkv; g.out16 = qkv; g.ldo16 = 3 * d;
+            gemm(g);
+        }
+        enc_attention(dt, qkv, att, W, T, d, H, n_phantom(), stream);
+        {
+            GemmArgs g;
+            g.dtype = dt; g.M = (int) M; g.N = d; g.K = d; g.a = att; g.lda = d; g.w = L.wo; g.ldw = d;
+            g.bias = L.bo; g.resid = x; g.ldr = d; g.out32 = x; g.ldo32 = d;
+            gemm(g);
+        }
+        layernorm(dt, x, d, L.ln2_w, L.ln2_b, hp.eps, (int) M, d, h16, d, nullptr, 0, nullptr, stream);
+        {
+            GemmArgs g;
+            g.dtype = dt; g.M = (int) M; g.N = 4 * d; g.K = d; g.a = h16; g.lda = d; g.w = L.w1; g.ldw = d;
+            g.bias = L.b1; g.gelu = true; g.out16 = mlp; g.ldo16 = 4 * d;
+            gemm(g);
+        }
+        {
+            GemmArgs g;
+            g.dtype = dt; g.M = (int) M; g.N = d; g.K = 4 * d; g.a = mlp; g.lda = 4 * d; g.w = L.w2; g.ldw = 4 * d;
+            g.bias = L.b2; g.resid = x; g.ldr = d; g.out32 = x; g.ldo32 = d;
+            gemm(g);
+        }
+        n_kernel_launches += 3;
+    }
+    float * e32 = nullptr;
+    if (keep_embd32) {
+        if (!embd_enc32.reserve(M * d * 4)) return false;
+        e32 = (float *) embd_enc32.p;
+    }
+    layernorm(dt, x, d, model.e_ln_w, model.e_ln_b, hp.eps, (int) M, d, enc16, d, e32, d, nullptr, stream);
+    n_kernel_launches += 1;
+
+    // cross K/V for every text layer straight into the pool: K scaled by dh^-0.25 (no bias), V + bias
+    const float kscale = powf(64.0f, -0.25f);
+    for (int il = 0; il < hp.n_text_layer; ++il) {
+        const DecLayer & L = model.dec[il];
+        GemmArgs g;
+        g.dtype = dt; g.M = (int) M; g.N = 2 * d; g.K = d; g.a = enc16; g.lda = d; g.w = L.wxkv; g.ldw = d;
+        g.bias = L.bxkv; g.scale = kscale; g.scale_cols = d;
+        g.out16 = (char *) kv.data.p + (il * kv.layer_stride + (size_t) win0 * T * 2 * d) * 2;
+        g.ldo16 = 2 * d;
+        gemm(g);
+    }
+    WB_CUDA(cudaStreamSynchronize(stream));
+    if (!ok) wlog(GGML_LOG_LEVEL_ERROR, "%s: GEMM launch rejected its arguments\n", __func__);
+    return ok && !cuda_failed();
+}
+
+// ---- decoder ----------------------------------------------------------------------------------------------
+bool Engine::decode(const std::vector<DecRow> & rows, const std::vector<int> & logit_rows, size_t cross_layer_stride) {
+    const int R = (int) rows.size(), RL = (int) logit_rows.size();
+    if (R == 0) return true;
+    WB_CUDA(cudaSetDevice(device));
+    const auto & hp = model.hp;
+    const int d = hp.n_text_state, H = hp.n_text_head, n_ctx = hp.n_text_ctx, V = hp.n_vocab;
+    const DType dt = model.dtype;
+
+    size_t need = 0;
+    auto sz = [&](size_t b) { need += round_up<size_t>(b, 256); };
+    sz((size_t) R * d * 4); sz((size_t) R * d * 2); sz((size_t) R * 3 * d * 2); sz((size_t) R * d * 2); sz((size_t) R * d * 2);
+    sz((size_t) R * 4 * d * 2); sz((size_t) std::max(1, RL) * d * 2); sz(R * sizeof(DecRow)); sz(std::max(1, RL) * sizeof(int));
+    if (!ws.begin(need)) return false;
+    float * x = (float *) ws.take((size_t) R * d * 4);
+    void * h16 = ws.take((size_t) R * d * 2);
+    void * qkv = ws.take((size_t) R * 3 * d * 2);
+    void * att = ws.take((size_t) R * d * 2);
+    void * q16 = ws.take((size_t) R * d * 2);
+    void * mlp = ws.take((size_t) R * 4 * d * 2);
+    void * hl16 = ws.take((size_t) std::max(1, RL) * d * 2);
+    DecRow * d_rows = (DecRow *) ws.take(R * sizeof(DecRow));
+    int * d_lrows = (int *) ws.take(std::max(1, RL) * sizeof(int));
+    if (!logits.reserve((size_t) std::max(1, RL) * ld_logits * 4)) return false;
+
+    // stage the row descriptors through pinned memory so the copy is asynchronous
+    char * hp_buf = (char *) pinned(0, R * sizeof(DecRow) + RL * sizeof(int));
+    memcpy(hp_buf, rows.data(), R * sizeof(DecRow));
+    if (RL) memcpy(hp_buf + R * sizeof(DecRow), logit_rows.data(), RL * sizeof(int));
+    WB_CUDA(cudaMemcpyAsync(d_rows, hp_buf, R * sizeof(DecRow), cudaMemcpyHostToDevice, stream));
+    if (RL) WB_CUDA(cudaMemcpyAsync(d_lrows, hp_buf + R * sizeof(DecRow), RL * sizeof(int), cudaMemcpyHostToDevice, stream));
+
+    bool ok = true;
+    auto gemm = [&](const GemmArgs & g) {
+        ok = ok && tc_gemm(g, stream);
+        n_kernel_launches += 1;
+    };
+    const float qk_scale = powf(64.0f, -0.25f);
+    const size_t self_layer = (size_t) n_ctx * 2 * d;
+
+    dec_embed(dt, model.d_te, model.d_pe, d_rows, R, d, x, stream);
+    n_kernel_launches += 1;
+    for (int il = 0; il < hp.n_text_layer; ++il) {
+        const DecLayer & L = model.dec[il];
+        layernorm(dt, x, d, L.ln1_w, L.ln1_b, hp.eps, R, d, h16, d, nullptr, 0, nullptr, stream);
+        {
+            GemmArgs g;   // Q and K carry dh^-0.25 each (src/whisper.cpp:2506, 2550, 2557); V is biased only
+            g.dtype = dt; g.M = R; g.N = 3 * d; g.K = d; g.a = h16; g.lda = d; g.w = L.wqkv; g.ldw = d;
+            g.bias = L.bqkv; g.scale = qk_scale; g.scale_cols = 2 * d; g.out16 = qkv; g.ldo16 = 3 * d;
+            gemm(g);
+        }
+        dec_kv_append(qkv, d_rows, R, d, il * self_layer, stream);
+        dec_self_attn(dt, qkv, d_rows, R, d, H, il * self_layer, n_ctx, att, stream);
+        {
+            GemmArgs g;
+            g.dtype = dt; g.M = R; g.N = d; g.K = d; g.a = att; g.lda = d; g.w = L.wo; g.ldw = d;
+            g.bias = L.bo; g.resid = x; g.ldr = d; g.out32 = x; g.ldo32 = d;
+            gemm(g);
+        }
+        layernorm(dt, x, d, L.lnx_w, L.lnx_b, hp.eps, R, d, h16, d, nullptr, 0, nullptr, stream);
+        {
+            GemmArgs g;
+            g.dtype = dt; g.M = R; g.N = d; g.K = d; g.a = h16; g.lda = d; g.w = L.wxq; g.ldw = d;
+            g.bias = L.bxq; g.out16 = q16; g.ldo16 = d;
+            gemm(g);
+        }
+        dec_cross_attn(dt, q16, d_rows, R, d, H, il * cross_layer_stride, 1500, n_phantom(), att, stream);
+        {
+            GemmArgs g;
+            g.dtype = dt; g.M = R; g.N = d; g.K = d; g.a = att; g.lda = d; g.w = L.wxo; g.ldw = d;
+            g.bias = L.bxo; g.resid = x; g.ldr = d; g.out32 = x; g.ldo32 = d;
+            gemm(g);
+        }
+        layernorm(dt, x, d, L.ln2_w, L.ln2_b, hp.eps, R, d, h16, d, nullptr, 0, nullptr, stream);
+        {
+            GemmArgs g;
+            g.dtype = dt; g.M = R; g.N = 4 * d; g.K = d; g.a = h16; g.lda = d; g.w = L.w1; g.ldw = d;
+            g.bias = L.b1; g.gelu = true; g.out16 = mlp; g.ldo16 = 4 * d;
+            gemm(g);
+        }
+        {
+            GemmArgs g;
+            g.dtype = dt; g.M = R; g.N = d; g.K = 4 * d; g.a = mlp; g.lda = 4 * d; g.w = L.w2; g.ldw = 4 * d;
+            g.bias = L.b2; g.resid = x; g.ldr = d; g.out32 = x; g.ldo32 = d;
+            gemm(g);
+        }
+        n_kernel_launches += 6;
+    }
+    if (RL > 0) {
+        // final LayerNorm only on the rows whose logits are wanted, then the tied-embedding logits GEMM
+        layernorm(dt, x, d, model.d_ln_w, model.d_ln_b, hp.eps, RL, d, hl16, d, nullptr, 0, d_lrows, stream);
+        GemmArgs g;
+        g.dtype = dt; g.M = RL; g.N = V; g.K = d; g.a = hl16; g.lda = d; g.w = model.d_te; g.ldw = d;
+        g.out32 = (float *) logits.p; g.ldo32 = ld_logits;
+        gemm(g);
+        n_kernel_launches += 1;
+    }
+    if (!ok) wlog(GGML_LOG_LEVEL_ERROR, "%s: GEMM launch rejected its arguments\n", __func__);
+    return ok && !cuda_failed();
+}
+
+bool Engine::fetch_logits(int row, float * out) {
+    WB_CUDA(cudaMemcpyAsync(out, (const float *) logits.p + (size_t) row * ld_logits, (size_t) model.hp.n_vocab * 4,
+                            cudaMemcpyDeviceToHost, stream));
+    WB_CUDA(cudaStreamSynchronize(stream));
+    return !cuda_failed();
+}
+
+bool Engine::sample_greedy(const std::vector<SampleRow> & srows, const uint32_t * d_mask, const SampleParams & prm,
+                           std::vector<SampleOut> & out) {
+    const int R = (int) srows.size();
+    out.resize(R);
+    if (R == 0) return true;
+    const size_t in_b = R * sizeof(SampleRow), out_b = R * sizeof(SampleOut);
+    if (!meta.reserve(round_up<size_t>(in_b, 256) + out_b)) return false;
+    SampleRow * d_in = (SampleRow *) meta.p;
+    SampleOut * d_out = (SampleOut *) ((char *) meta.p + round_up<size_t>(in_b, 256));
+    char * hb = (char *) pinned(1, in_b + out_b);
+    memcpy(hb, srows.data(), in_b);
+    WB_CUDA(cudaMemcpyAsync(d_in, hb, in_b, cudaMemcpyHostToDevice, stream));
+    dec_sample_greedy((float *) logits.p, ld_logits, d_in, R, d_mask, prm, d_out, stream);
+    n_kernel_launches += 1;
+    WB_CUDA(cudaMemcpyAsync(hb + in_b, d_out, out_b, cudaMemcpyDeviceToHost, stream));
+    WB_CUDA(cudaStreamSynchronize(stream));
+    memcpy(out.data(), hb + in_b, out_b);
+    return !cuda_failed();
+}
+
+bool Engine::token_prob(const std::vector<SampleRow> & srows, int token, std::vector<float> & out) {
+    const int R = (int) srows.size();
+    out.resize(R);
+    if (R == 0) return true;
+    const size_t in_b = R * sizeof(SampleRow), out_b = R * sizeof(float);
+    if (!meta.reserve(round_up<size_t>(in_b, 256) + out_b)) return false;
+    SampleRow * d_in = (SampleRow *) meta.p;
+    float * d_out = (float *) ((char *) meta.p + round_up<size_t>(in_b, 256));
+    char * hb = (char *) pinned(1, in_b + out_b);
+    memcpy(hb, srows.data(), in_b);
+    WB_CUDA(cudaMemcpyAsync(d_in, hb, in_b, cudaMemcpyHostToDevice, stream));
+    dec_token_prob((const float *) logits.p, ld_logits, d_in, R, model.hp.n_vocab, token, d_out, stream);
+    n_kernel_launches += 1;
+    WB_CUDA(cudaMemcpyAsync(hb + in_b, d_out, out_b, cudaMemcpyDeviceToHost, stream));
+    WB_CUDA(cudaStreamSynchronize(stream));
+    memcpy(out.data(), hb + in_b, out_b);
+    return !cuda_failed();
+}
+
+bool Engine::kv_copy_prefix(const void * src, void * dst, int n_pos) {
+    if (n_pos <= 0 || src == dst) return true;
+    const int d = model.hp.n_text_state;
+    const size_t layer8 = (size_t) model.hp.n_text_ctx * 2 * d / 8;
+    const size_t n8 = (size_t) n_pos * 2 * d / 8;
+    dim3 grid((unsigned) ceil_div<size_t>(n8, 256), model.hp.n_text_layer);
+    kv_copy_prefix_kernel<<<grid, 256, 0, stream>>>((const uint4 *) src, (uint4 *) dst, layer8, n8);
+    n_kernel_launches += 1;
+    WB_CUDA(cudaGetLastError());
+    return !cuda_failed();
+}
+
+}  // namespace wb

@@ -1,0 +1,113 @@
+// Batched device engine: mel -> encoder (+ cross K/V) -> decoder rows -> logits / on-device selection.
+// One Engine per whisper_context (one model replica on one GPU); calls are serialised by a mutex.
+#pragma once
+
+#include <mutex>
+#include <vector>
+
+#include "dec_kernels.h"
+#include "enc_kernels.h"
+#include "mel.h"
+#include "model.h"
+
+namespace wb {
+
+struct DeviceBlock {           // growable device allocation (contents are transient unless stated otherwise)
+    void * p = nullptr;
+    size_t cap = 0;
+    bool reserve(size_t bytes, bool keep = false);
+    ~DeviceBlock();
+    DeviceBlock() = default;
+    DeviceBlock(const DeviceBlock &) = delete;
+    DeviceBlock & operator=(const DeviceBlock &) = delete;
+};
+
+struct Arena {                 // bump allocator over a DeviceBlock, reset per engine call
+    DeviceBlock blk;
+    size_t off = 0;
+    bool begin(size_t total) { off = 0; return blk.reserve(total); }
+    void * take(size_t bytes) {
+        void * r = (char *) blk.p + off;
+        off += round_up<size_t>(bytes, 256);
+        return r;
+    }
+};
+
+// Mel of one audio stream, device resident (reference: whisper_mel, src/whisper.cpp:414-420).
+struct MelBuf {
+    DeviceBlock data;          // raw log10 [n_mel][stride] (finalized == false) or final values [n_mel][n_len]
+    DeviceBlock max_enc;       // 1 x unsigned
+    int n_mel = 0, n_len = 0, n_len_org = 0, n_frames_fft = 0, stride = 0;
+    bool finalized = false;
+    bool valid = false;
+};
+
+// Cross-attention K/V of a set of windows: [n_text_layer][n_windows*1500][2d] (K | V), 16-bit.
+struct CrossKV {
+    DeviceBlock data;
+    int n_windows = 0;
+    size_t layer_stride = 0;   // elements
+    const void * window_base(int w, int d) const { return (const char *) data.p + (size_t) w * 1500 * 2 * d * 2; }
+};
+
+struct MelJob {
+    const float * pcm_host = nullptr;   // exactly one of pcm_host / pcm_dev
+    const float * pcm_dev = nullptr;
+    int n_samples = 0;
+    MelBuf * out = nullptr;
+};
+
+struct EncJob {
+    const MelBuf * mel = nullptr;
+    int seek = 0;
+};
+
+struct Engine {
+    Model model;
+    bool flash_attn = true;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    MelPlan mel_plan;
+    std::mutex mu;
+
+    Arena ws;                  // activations
+    DeviceBlock meta;          // small per-call device arrays
+    DeviceBlock pcm_stage;     // H2D staging for PCM
+    DeviceBlock logits;        // f32 [rows][ld_logits], valid until the next decode
+    DeviceBlock embd_enc32;    // f32 [windows*1500][d] of the last encode when requested
+    int ld_logits = 0;
+    void * h_pinned[2] = {nullptr, nullptr};   // pinned host staging: [0] decoder rows (H2D), [1] sampler I/O
+    size_t h_pinned_cap[2] = {0, 0};
+    long long n_kernel_launches = 0;   // launches of our own kernels (bench.py reports them)
+
+    int n_phantom() const { return flash_attn ? 36 : 0; }
+
+    bool init(int device, bool flash_attn);
+    ~Engine();
+
+    void * pinned(int which, size_t bytes);
+
+    bool run_mel(const std::vector<MelJob> & jobs);
+    bool set_mel(MelBuf & out, const float * data, int n_len, int n_mel);
+    // copies the reference's final [n_mel][n_len] container to the host (parity hook)
+    bool get_mel(const MelBuf & mel, float * out);
+
+    // Encodes jobs.size() windows; K/V rows for job i land at window index win0 + i of kv (kv must be sized already).
+    bool encode(const std::vector<EncJob> & jobs, CrossKV & kv, int win0, bool keep_embd32);
+    bool size_cross(CrossKV & kv, int n_windows);
+
+    // Runs the decoder over `rows`; logits are produced for rows[logit_rows[i]] into logits row i.
+    // cross_layer_stride: element distance between text layers in the cross-K/V pool the rows point into.
+    bool decode(const std::vector<DecRow> & rows, const std::vector<int> & logit_rows, size_t cross_layer_stride);
+    bool fetch_logits(int row, float * out);                         // D2H one row (n_vocab floats)
+    bool sample_greedy(const std::vector<SampleRow> & srows, const uint32_t * d_mask, const SampleParams & prm,
+                       std::vector<SampleOut> & out);
+    bool token_prob(const std::vector<SampleRow> & srows, int token, std::vector<float> & out);
+    bool kv_copy_prefix(const void * src, void * dst, int n_pos);    // self-KV: positions [0, n_pos) of every layer
+
+    size_t self_kv_bytes() const {
+        return (size_t) model.hp.n_text_layer * model.hp.n_text_ctx * 2 * model.hp.n_text_state * 2;
+    }
+};
+
+}  // namespace wb

@@ -1,0 +1,1130 @@
+// whisper_full semantics on the batched engine.
+//
+// The reference runs ONE audio stream per call and walks it window by window (whisper_full_with_state,
+// src/whisper.cpp:6827-7776); whisper_full_parallel spawns one thread + state per chunk (7801-7929).  Here a set of
+// streams (one per chunk) advances in lock-step: every round encodes the current 30 s window of every live stream as
+// one device batch and decodes all their sequences as rows of one decoder batch.  Per stream the control flow --
+// seek loop, temperature ladder, prompt construction, per-token state machine, fallback decision, segment emission --
+// is the reference's, so each stream produces exactly what a stand-alone whisper_full call would.
+//
+// Two selection paths per stream and temperature round:
+//   device path : greedy at temperature 0 without a logits callback -> rules + log-softmax + arg-max run in
+//                 dec_kernels.cu right after the decode step; 24 bytes per sequence come back to the host.
+//   host path   : temperature > 0 (mt19937 + discrete_distribution draws), "beam search" (which in the reference is k
+//                 draws per beam, src/whisper.cpp:6519-6592) or a user logits callback -> the logits row is copied to
+//                 the host and the restated reference rules/samplers below run there.
+#include "full.h"
+
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <chrono>
+#include <map>
+#include <regex>
+
+namespace wb {
+
+int64_t time_us() {
+    return std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+static const char * const kNonSpeech[] = {
+    "\"", "#", "(", ")", "*", "+", "/", ":", ";", "<", "=", ">", "@", "[", "\\", "]", "^", "_", "`", "{", "|", "}", "~",
+    "「", "」", "『", "』", "<<", ">>", "<<<", ">>>", "--", "---", "-(", "-[", "('", "(\"", "((", "))", "(((",
+    ")))", "[[", "]]", "{{", "}}", "♪♪", "♪♪♪", "♩", "♪", "♫", "♬", "♭",
+    "♮", "♯"};
+
+std::string to_timestamp(int64_t t, bool comma) {
+    int64_t msec = t * 10;
+    const int64_t hr = msec / (1000 * 60 * 60);
+    msec -= hr * (1000 * 60 * 60);
+    const int64_t mn = msec / (1000 * 60);
+    msec -= mn * (1000 * 60);
+    const int64_t sec = msec / 1000;
+    msec -= sec * 1000;
+    char buf[32];
+    snprintf(buf, sizeof(buf), "%02d:%02d:%02d%s%03d", (int) hr, (int) mn, (int) sec, comma ? "," : ".", (int) msec);
+    return buf;
+}
+
+// ---- token ids that are suppressed at every step (everything in whisper_process_logits that does not depend on the
+// decoder state: src/whisper.cpp:6224-6292) ------------------------------------------------------------------------
+static void build_static_suppress(const whisper_context & ctx, const whisper_full_params & p, std::vector<uint32_t> & bits) {
+    const Vocab & v = ctx.eng.model.vocab;
+    const int V = v.n_vocab;
+    bits.assign((V + 31) / 32, 0u);
+    auto kill = [&](int id) {
+        if (id >= 0 && id < V) bits[id >> 5] |= 1u << (id & 31);
+    };
+    kill(v.token_not);
+    kill(v.token_sot);
+    kill(v.token_nosp);
+    if (!p.tdrz_enable) kill(v.token_solm);
+    kill(v.token_translate);
+    kill(v.token_transcribe);
+    kill(v.token_prev);
+    for (int i = 0; i <= lang_max_id(); ++i) kill(v.token_sot + 1 + i);
+    if (p.suppress_regex) {
+        try {
+            std::regex re(p.suppress_regex);
+            for (const auto & kv : v.token_to_id)
+                if (std::regex_match(kv.first, re)) kill(kv.second);
+        } catch (const std::regex_error &) {
+            wlog(GGML_LOG_LEVEL_ERROR, "%s: invalid suppress_regex ignored\n", __func__);
+        }
+    }
+    if (p.suppress_nst) {
+        for (const char * t : kNonSpeech) {
+            const std::string a = t, b = std::string(" ") + t;
+            auto ia = v.token_to_id.find(a);
+            if (ia != v.token_to_id.end()) kill(ia->second);
+            auto ib = v.token_to_id.find(b);
+            if (ib != v.token_to_id.end()) kill(ib->second);
+        }
+        auto i1 = v.token_to_id.find(" -");
+        if (i1 != v.token_to_id.end()) kill(i1->second);
+        auto i2 = v.token_to_id.find(" '");
+        if (i2 != v.token_to_id.end()) kill(i2->second);
+    }
+}
+
+// ---- host restatement of the reference's logit processing (used only by the host path) -------------------------
+// whisper_compute_logprobs / whisper_compute_probs, src/whisper.cpp:6137-6171
+static void compute_logprobs(const float * logits, int n, std::vector<float> & logprobs) {
+    float logit_max = -INFINITY;
+    for (int i = 0; i < n; ++i) logit_max = std::max(logit_max, logits[i]);
+    float logsumexp = 0.0f;
+    for (int i = 0; i < n; ++i)
+        if (logits[i] > -INFINITY) logsumexp += expf(logits[i] - logit_max);
+    logsumexp = logf(logsumexp) + logit_max;
+    logprobs.resize(n);
+    for (int i = 0; i < n; ++i) logprobs[i] = logits[i] > -INFINITY ? logits[i] - logsumexp : -INFINITY;
+}
+
+// whisper_process_logits, src/whisper.cpp:6177-6445 (grammar branch omitted: out of scope)
+static void process_logits_host(whisper_context & ctx, whisper_state & state, whisper_decoder & dec,
+                                const whisper_full_params & params, const std::vector<uint32_t> & static_bits,
+                                const float * logits_row, float temperature) {
+    const Vocab & vocab = ctx.eng.model.vocab;
+    const int n = vocab.n_vocab;
+    const auto & toks = dec.sequence.tokens;
+    const bool is_initial = toks.empty();
+    auto & logits = dec.logits;
+    auto & logprobs = dec.logprobs;
+    auto & probs = dec.probs;
+    logits.assign(logits_row, logits_row + n);
+    if (temperature > 0.0f)
+        for (int i = 0; i < n; ++i) logits[i] /= temperature;
+    probs.resize(n);
+
+    if (params.suppress_blank && is_initial) {
+        logits[vocab.token_eot] = -INFINITY;
+        auto it = vocab.token_to_id.find(" ");
+        if (it != vocab.token_to_id.end()) logits[it->second] = -INFINITY;
+    }
+    // state-independent suppressions before the user callback: <|notimestamps|>, sot, nosp, solm, task, prev, languages
+    logits[vocab.token_not] = -INFINITY;
+    if (params.no_timestamps)
+        for (int i = vocab.token_beg; i < n; ++i) logits[i] = -INFINITY;
+    logits[vocab.token_sot] = -INFINITY;
+    logits[vocab.token_nosp] = -INFINITY;
+    if (!params.tdrz_enable) logits[vocab.token_solm] = -INFINITY;
+    logits[vocab.token_translate] = -INFINITY;
+    logits[vocab.token_transcribe] = -INFINITY;
+    logits[vocab.token_prev] = -INFINITY;
+    for (int i = 0; i <= lang_max_id(); ++i) {
+        const int id = vocab.token_sot + 1 + i;
+        if (id < n) logits[id] = -INFINITY;
+    }
+    if (params.logits_filter_callback) {
+        params.logits_filter_callback(&ctx, &state, toks.data(), (int) toks.size(), logits.data(),
+                                      params.logits_filter_callback_user_data);
+    }
+    // regex / non-speech suppressions (after the callback, as in the reference)
+    for (int i = 0; i < n; ++i)
+        if ((static_bits[i >> 5] >> (i & 31)) & 1u) logits[i] = -INFINITY;
+
+    {
+        const bool last_ts = !toks.empty() && toks.back().id >= vocab.token_beg;
+        const bool pen_ts = toks.size() < 2 || toks[toks.size() - 2].id >= vocab.token_beg;
+        if (last_ts) {
+            if (pen_ts) {
+                for (int i = vocab.token_beg; i < n; ++i) logits[i] = -INFINITY;
+            } else {
+                for (int i = 0; i < vocab.token_eot; ++i) logits[i] = -INFINITY;
+            }
+        }
+    }
+    if (is_initial && params.max_initial_ts > 0.0f) {
+        const float precision = 30.0f / ctx.eng.model.hp.n_audio_ctx;
+        const int tid0 = (int) std::round(params.max_initial_ts / precision);
+        for (int i = vocab.token_beg + tid0 + 1; i < n; ++i) logits[i] = -INFINITY;
+    }
+    if (dec.has_ts) {
+        const int tid0 = dec.seek_delta / 2;
+        for (int i = vocab.token_beg; i < vocab.token_beg + tid0 && i < n; ++i) logits[i] = -INFINITY;
+    }
+    compute_logprobs(logits.data(), n, logprobs);
+    {
+        float timestamp_logprob = -INFINITY;
+        {
+            float logsumexp = 0.0f;
+            float logprob_max = -INFINITY;
+            for (int i = vocab.token_beg; i < n; ++i) logprob_max = std::max(logprob_max, logprobs[i]);
+            for (int i = vocab.token_beg; i < n; ++i)
+                if (logprobs[i] > -INFINITY) logsumexp += expf(logprobs[i] - logprob_max);
+            if (logsumexp > 0.0f) timestamp_logprob = logf(logsumexp) + logprob_max;
+        }
+        float max_text = -INFINITY;
+        for (int i = 0; i < vocab.token_beg; ++i) max_text = std::max(max_text, logprobs[i]);
+        if (timestamp_logprob > max_text) {
+            for (int i = 0; i < vocab.token_beg; ++i) {
+                logits[i] = -INFINITY;
+                logprobs[i] = -INFINITY;
+            }
+        }
+    }
+    for (int i = 0; i < n; ++i) probs[i] = logits[i] == -INFINITY ? 0.0f : expf(logprobs[i]);
+}
+
+// whisper_sample_token, src/whisper.cpp:6460-6517
+static whisper_token_data sample_token_host(const Vocab & vocab, whisper_decoder & dec, bool best) {
+    whisper_token_data r = {0, 0, 0.0f, 0.0f, 0.0f, 0.0f, -1, -1, -1, 0.0f};
+    const auto & probs = dec.probs;
+    const auto & logprobs = dec.logprobs;
+    const int n = vocab.n_vocab;
+    {
+        double sum_ts = 0.0, max_ts = 0.0;
+        for (int i = vocab.token_beg; i < n; ++i) {
+            sum_ts += probs[i];
+            if (max_ts < probs[i]) {
+                max_ts = probs[i];
+                r.tid = i;
+            }
+        }
+        r.pt = (float) (max_ts / (sum_ts + 1e-10));
+        r.ptsum = (float) sum_ts;
+    }
+    if (best) {
+        for (int i = 0; i < n; ++i)
+            if (r.p < probs[i]) {
+                r.id = i;
+                r.p = probs[i];
+                r.plog = logprobs[i];
+            }
+    } else {
+        std::discrete_distribution<> dist(probs.begin(), probs.end());
+        r.id = dist(dec.rng);
+        r.p = probs[r.id];
+        r.plog = logprobs[r.id];
+    }
+    if (r.id >= vocab.token_beg) {
+        r.tid = r.id;
+        r.pt = r.p;
+    }
+    return r;
+}
+
+// whisper_sample_token_topk, src/whisper.cpp:6519-6592: k draws from the categorical distribution
+static std::vector<whisper_token_data> sample_token_topk_host(const Vocab & vocab, whisper_decoder & dec, int k) {
+    const auto & probs = dec.probs;
+    const auto & logprobs = dec.logprobs;
+    const int n = vocab.n_vocab;
+    whisper_token tid = vocab.token_beg;
+    float pt = 0.0f, ptsum = 0.0f;
+    {
+        double sum_ts = 0.0, max_ts = 0.0;
+        for (int i = vocab.token_beg; i < n; ++i) {
+            sum_ts += probs[i];
+            if (max_ts < probs[i]) {
+                max_ts = probs[i];
+                tid = i;
+            }
+        }
+        pt = (float) (max_ts / (sum_ts + 1e-10));
+        ptsum = (float) sum_ts;
+    }
+    std::discrete_distribution<> dist(probs.begin(), probs.end());
+    std::vector<whisper_token_data> out;
+    out.reserve(k);
+    for (int i = 0; i < k; ++i) {
+        const int id = dist(dec.rng);
+        whisper_token_data t = {id, tid, probs[id], logprobs[id], pt, ptsum, -1, -1, -1, 0.0f};
+        if (t.id >= vocab.token_beg) {
+            t.tid = t.id;
+            t.pt = t.p;
+        }
+        out.push_back(t);
+    }
+    return out;
+}
+
+// whisper_sequence_score, src/whisper.cpp:6595-6641
+static void sequence_score(const whisper_full_params & params, whisper_sequence & s) {
+    if (s.result_len == 0) return;
+    double result = 0.0;
+    for (int i = 0; i < s.result_len; ++i) result += s.tokens[i].plog;
+    s.sum_logprobs = result;
+    s.avg_logprobs = result / s.result_len;
+    double penalty = s.result_len;
+    if (params.length_penalty > 0.0f) penalty = pow((5.0 + penalty) / 6.0, params.length_penalty);
+    s.score = result / penalty;
+    const int n = 32;
+    int cnt = 0;
+    double entropy = 0.0;
+    std::map<whisper_token, int> counts;
+    for (int i = std::max(0, s.result_len - n); i < s.result_len; ++i) {
+        counts[s.tokens[i].id]++;
+        cnt++;
+    }
+    for (const auto & kv : counts) {
+        const double p = kv.second / (double) cnt;
+        entropy -= p * log(p);
+    }
+    s.entropy = entropy;
+}
+
+static bool sequences_equal(const whisper_sequence & a, const whisper_sequence & b) {
+    if (a.tokens.size() != b.tokens.size()) return false;
+    for (int i = (int) a.tokens.size() - 1; i >= 0; --i)
+        if (a.tokens[i].id != b.tokens[i].id) return false;
+    return true;
+}
+
+// ---- single-window helpers used by the low-level API and by language detection --------------------------------
+bool encode_single(whisper_context & ctx, whisper_state & st, int seek, bool keep_embd32) {
+    Engine & e = ctx.eng;
+    if (!e.size_cross(st.cross, 1)) return false;
+    std::vector<EncJob> jobs(1);
+    jobs[0].mel = &st.mel;
+    jobs[0].seek = seek;
+    const int64_t t0 = time_us();
+    const bool ok = e.encode(jobs, st.cross, 0, keep_embd32);
+    st.cross_base = st.cross.data.p;
+    st.cross_layer_stride = st.cross.layer_stride;
+    st.t_encode_us += time_us() - t0;
+    st.n_encode++;
+    return ok;
+}
+
+bool decode_single(whisper_context & ctx, whisper_state & st, const whisper_token * tokens, int n_tokens, int n_past) {
+    Engine & e = ctx.eng;
+    const auto & hp = e.model.hp;
+    if (n_tokens <= 0 || n_past < 0 || n_past + n_tokens > hp.n_text_ctx) {
+        wlog(GGML_LOG_LEVEL_ERROR, "%s: %d tokens at n_past=%d do not fit the text context (%d)\n", __func__, n_tokens, n_past,
+             hp.n_text_ctx);
+        return false;
+    }
+    if (!st.cross_base) {
+        wlog(GGML_LOG_LEVEL_ERROR, "%s: whisper_encode() must be called first\n", __func__);
+        return false;
+    }
+    whisper_decoder & dec = st.decoders[0];
+    if (!dec.kv.reserve(e.self_kv_bytes())) return false;
+    std::vector<DecRow> rows(n_tokens);
+    for (int i = 0; i < n_tokens; ++i) {
+        if (tokens[i] < 0 || tokens[i] >= hp.n_vocab) {
+            wlog(GGML_LOG_LEVEL_ERROR, "%s: token %d out of range\n", __func__, tokens[i]);
+            return false;
+        }
+        rows[i] = {tokens[i], n_past + i, dec.kv.p, st.cross_base};
+    }
+    const int64_t t0 = time_us();
+    std::vector<int> lrows(1, n_tokens - 1);
+    bool ok = e.decode(rows, lrows, st.cross_layer_stride);
+    st.logits.resize((size_t) n_tokens * hp.n_vocab);
+    ok = ok && e.fetch_logits(0, st.logits.data() + (size_t) (n_tokens - 1) * hp.n_vocab);
+    const int64_t dt = time_us() - t0;
+    if (n_tokens == 1) {
+        st.t_decode_us += dt;
+        st.n_decode++;
+    } else if (n_tokens < 16) {
+        st.t_batchd_us += dt;
+        st.n_batchd += n_tokens;
+    } else {
+        st.t_prompt_us += dt;
+        st.n_prompt += n_tokens;
+    }
+    return ok;
+}
+
+// whisper_lang_auto_detect_with_state, src/whisper.cpp:4021-4094
+int lang_auto_detect(whisper_context & ctx, whisper_state & st, int offset_ms, float * lang_probs) {
+    const int seek = offset_ms / 10;
+    if (seek < 0) {
+        wlog(GGML_LOG_LEVEL_ERROR, "%s: offset %dms is before the start of the audio\n", __func__, offset_ms);
+        return -1;
+    }
+    if (seek >= st.mel.n_len_org) {
+        wlog(GGML_LOG_LEVEL_ERROR, "%s: offset %dms is past the end of the audio (%dms)\n", __func__, offset_ms,
+             st.mel.n_len_org * 10);
+        return -2;
+    }
+    if (!encode_single(ctx, st, seek, false)) return -6;
+    const Vocab & vocab = ctx.eng.model.vocab;
+    const whisper_token sot = vocab.token_sot;
+    if (!decode_single(ctx, st, &sot, 1, 0)) return -7;
+    std::vector<std::pair<double, int>> li;
+    const int n_lang = std::min(lang_max_id() + 1, std::max(0, vocab.n_vocab - (vocab.token_sot + 1)));
+    for (int i = 0; i < n_lang; ++i) li.emplace_back(st.logits[vocab.token_sot + 1 + i], i);
+    std::sort(li.begin(), li.end(), [](const std::pair<double, int> & a, const std::pair<double, int> & b) { return a.first > b.first; });
+    const double mx = li[0].first;
+    double sum = 0.0;
+    for (auto & kv : li) {
+        kv.first = exp(kv.first - mx);
+        sum += kv.first;
+    }
+    for (auto & kv : li) kv.first /= sum;
+    if (lang_probs)
+        for (const auto & kv : li) lang_probs[kv.second] = (float) kv.first;
+    return li[0].second;
+}
+
+// ---- the batched whisper_full ---------------------------------------------------------------------------------
+namespace {
+
+struct beam_candidate {
+    int decoder_idx;
+    int seek_delta;
+    bool has_ts;
+    whisper_sequence sequence;
+};
+
+enum class Phase { WINDOW, PROMPT, STEPPING, RANK, DONE };
+
+struct Stream {
+    whisper_state * state = nullptr;
+    whisper_full_params params;
+    const float * samples = nullptr;
+    int n_samples = 0;
+    int rc = 0;
+    Phase phase = Phase::WINDOW;
+
+    int seek_start = 0, seek_end = 0, seek = 0;
+    std::vector<float> temperatures;
+    int n_decoders = 1;
+    int max_prompt_ctx = 0;
+    std::vector<whisper_token> prompt_tokens_buf, prompt_init, prompt;
+    std::string language_buf;
+
+    int it = 0;                  // temperature index
+    float t_cur = 0.0f;
+    int n_decoders_cur = 1;
+    bool device_path = false;
+    int best_decoder_id = 0;
+    int window = 0;              // index into the shared cross pool
+    bool no_timestamps = false;
+};
+
+}  // namespace
+
+static int stream_begin(whisper_context & ctx, Stream & s) {
+    whisper_state * state = s.state;
+    auto & params = s.params;
+    const Vocab & vocab = ctx.eng.model.vocab;
+    const auto & hp = ctx.eng.model.hp;
+
+    // language (auto-detection runs the single-window path for this stream)
+    if (params.language == nullptr || strlen(params.language) == 0 || strcmp(params.language, "auto") == 0 ||
+        params.detect_language) {
+        std::vector<float> probs(lang_max_id() + 1, 0.0f);
+        const int id = lang_auto_detect(ctx, *state, 0, probs.data());
+        if (id < 0) {
+            wlog(GGML_LOG_LEVEL_ERROR, "%s: failed to auto-detect language\n", __func__);
+            return -3;
+        }
+        state->lang_id = id;
+        s.language_buf = lang_str(id);
+        params.language = s.language_buf.c_str();
+        wlog(GGML_LOG_LEVEL_INFO, "%s: auto-detected language: %s (p = %f)\n", __func__, params.language, probs[id]);
+        if (params.detect_language) {
+            s.phase = Phase::DONE;
+            return 0;
+        }
+    }
+    s.seek_start = params.offset_ms / 10;
+    s.seek_end = params.duration_ms == 0 ? state->mel.n_len_org : s.seek_start + params.duration_ms / 10;
+    if (s.seek_end < s.seek_start + 10) {
+        wlog(GGML_LOG_LEVEL_WARN, "%s: input is too short - %d ms < 100 ms. consider padding the input audio with silence\n",
+             __func__, (s.seek_end - s.seek_start) * 10);
+        s.phase = Phase::DONE;
+        return 0;
+    }
+    if (params.temperature_inc > 0.0f) {
+        for (float t = params.temperature; t < 1.0f + 1e-6f; t += params.temperature_inc) s.temperatures.push_back(t);
+    } else {
+        s.temperatures.push_back(params.temperature);
+    }
+    int n_decoders = 1;
+    switch (params.strategy) {
+        case WHISPER_SAMPLING_GREEDY: n_decoders = params.greedy.best_of; break;
+        case WHISPER_SAMPLING_BEAM_SEARCH: n_decoders = std::max(params.greedy.best_of, params.beam_search.beam_size); break;
+    }
+    n_decoders = std::max(1, n_decoders);
+    if (n_decoders > WHISPER_MAX_DECODERS) {
+        wlog(GGML_LOG_LEVEL_ERROR, "%s: too many decoders requested (%d), max = %d\n", __func__, n_decoders, WHISPER_MAX_DECODERS);
+        return -4;
+    }
+    s.n_decoders = n_decoders;
+    for (int j = 1; j < n_decoders; ++j) state->decoders[j].rng = std::mt19937(j);
+
+    if (params.no_context) {
+        state->prompt_past0.clear();
+        state->prompt_past1.clear();
+    }
+    s.max_prompt_ctx = std::min(params.n_max_text_ctx, hp.n_text_ctx / 2);
+    {
+        if (!params.prompt_tokens && params.initial_prompt) {
+            // greedy longest-match tokenisation, see whisper_tokenize in whisper_api.cu
+            s.prompt_tokens_buf.resize(1024);
+            int n = whisper_tokenize(&ctx, params.initial_prompt, s.prompt_tokens_buf.data(), (int) s.prompt_tokens_buf.size());
+            if (n < 0) {
+                s.prompt_tokens_buf.resize(-n);
+                n = whisper_tokenize(&ctx, params.initial_prompt, s.prompt_tokens_buf.data(), (int) s.prompt_tokens_buf.size());
+            }
+            s.prompt_tokens_buf.resize(std::max(0, n));
+            params.prompt_tokens = s.prompt_tokens_buf.data();
+            params.prompt_n_tokens = (int) s.prompt_tokens_buf.size();
+        }
+        if (params.prompt_tokens && params.prompt_n_tokens > 0) {
+            if (params.carry_initial_prompt) {
+                if (state->prompt_past0.empty()) {
+                    const int max_tokens = std::max(1, s.max_prompt_ctx - 1);
+                    if (params.prompt_n_tokens > max_tokens)
+                        wlog(GGML_LOG_LEVEL_WARN, "%s: initial prompt is too long (%d tokens), will use only the last %d tokens\n",
+                             __func__, params.prompt_n_tokens, max_tokens);
+                    const int n_tokens = std::min(params.prompt_n_tokens, max_tokens);
+                    state->prompt_past0.assign(params.prompt_tokens + (params.prompt_n_tokens - n_tokens),
+                                               params.prompt_tokens + params.prompt_n_tokens);
+                }
+            } else {
+                for (int i = 0; i < params.prompt_n_tokens; ++i) state->prompt_past1.push_back(params.prompt_tokens[i]);
+                std::rotate(state->prompt_past1.begin(), state->prompt_past1.end() - params.prompt_n_tokens,
+                            state->prompt_past1.end());
+            }
+        }
+    }
+    if (params.audio_ctx > hp.n_audio_ctx) {
+        wlog(GGML_LOG_LEVEL_ERROR, "%s: audio_ctx is larger than the maximum allowed (%d > %d)\n", __func__, params.audio_ctx,
+             hp.n_audio_ctx);
+        return -5;
+    }
+    if (params.audio_ctx != 0) {
+        wlog(GGML_LOG_LEVEL_ERROR, "%s: audio_ctx = %d is not implemented on the B200 path (only the full 1500-position context)\n",
+             __func__, params.audio_ctx);
+        return -5;
+    }
+    state->exp_n_audio_ctx = 0;
+
+    s.prompt_init = {vocab.token_sot};
+    if (vocab.is_multilingual()) {
+        const int id = lang_id(params.language);
+        state->lang_id = id;
+        s.prompt_init.push_back(vocab.token_sot + 1 + std::max(0, id));
+        s.prompt_init.push_back(params.translate ? vocab.token_translate : vocab.token_transcribe);
+    }
+    {
+        const bool is_distil = hp.n_text_layer == 2 && hp.n_vocab != 51866;
+        if (is_distil && !params.no_timestamps) {
+            wlog(GGML_LOG_LEVEL_WARN, "%s: using first release distilled models - forcing no_timestamps\n", __func__);
+            params.no_timestamps = true;
+        }
+    }
+    if (params.no_timestamps) s.prompt_init.push_back(vocab.token_not);
+    s.no_timestamps = params.no_timestamps;
+    s.seek = s.seek_start;
+    s.phase = Phase::WINDOW;
+    return 0;
+}
+
+// emit the segments of the finished window and advance the seek position (src/whisper.cpp:7609-7772)
+static void stream_finish_window(whisper_context & ctx, Stream & s) {
+    whisper_state * state = s.state;
+    const auto & params = s.params;
+    const Vocab & vocab = ctx.eng.model.vocab;
+    auto & result_all = state->result_all;
+    const whisper_decoder & best = state->decoders[s.best_decoder_id];
+    int seek_delta = best.seek_delta;
+    const int result_len = best.sequence.result_len;
+    const auto & tokens_cur = best.sequence.tokens;
+    const int seek = s.seek;
+
+    const bool is_no_speech = (state->no_speech_prob > params.no_speech_thold && best.sequence.avg_logprobs < params.logprob_thold);
+
+    state->prompt_past1.clear();
+    if (!params.carry_initial_prompt && !s.prompt.empty() && s.prompt.front() == vocab.token_prev) {
+        state->prompt_past1.insert(state->prompt_past1.end(), s.prompt.begin() + 1, s.prompt.end() - s.prompt_init.size());
+    }
+    if (!is_no_speech)
+        for (int i = 0; i < result_len; ++i) state->prompt_past1.push_back(tokens_cur[i].id);
+
+    auto emit = [&](int64_t tt0, int64_t tt1, const std::string & text, int i0, int i1_incl, bool turn) {
+        if (params.print_realtime) {
+            if (params.print_timestamps) printf("[%s --> %s]  %s\n", to_timestamp(tt0, false).c_str(), to_timestamp(tt1, false).c_str(), text.c_str());
+            else {
+                printf("%s", text.c_str());
+                fflush(stdout);
+            }
+        }
+        result_all.push_back({tt0, tt1, text, state->no_speech_prob, {}, turn});
+        for (int j = i0; j <= i1_incl; ++j) result_all.back().tokens.push_back(tokens_cur[j]);
+        if (params.new_segment_callback) params.new_segment_callback(&ctx, state, 1, params.new_segment_callback_user_data);
+    };
+
+    if (!tokens_cur.empty() && ctx.eng.model.n_loaded > 0 && !is_no_speech) {
+        int i0 = 0;
+        int64_t t0 = seek + 2 * (tokens_cur.front().tid - vocab.token_beg);
+        std::string text;
+        bool speaker_turn_next = false;
+        for (int i = 0; i < (int) tokens_cur.size(); ++i) {
+            if (params.print_special || tokens_cur[i].id < vocab.token_eot) text += vocab.id_to_token[tokens_cur[i].id];
+            if (params.tdrz_enable && tokens_cur[i].id == vocab.token_solm) speaker_turn_next = true;
+            if (tokens_cur[i].id > vocab.token_beg && !params.single_segment) {
+                const int64_t t1 = seek + 2 * (tokens_cur[i].tid - vocab.token_beg);
+                if (!text.empty()) emit(t0, t1, text, i0, i, speaker_turn_next);
+                text = "";
+                while (i < (int) tokens_cur.size() && tokens_cur[i].id > vocab.token_beg) i++;
+                i--;
+                t0 = t1;
+                i0 = i + 1;
+                speaker_turn_next = false;
+            }
+        }
+        if (!text.empty()) emit(t0, seek + seek_delta, text, i0, (int) tokens_cur.size() - 1, speaker_turn_next);
+    }
+    const bool single_timestamp_ending = tokens_cur.size() > 1 && tokens_cur[tokens_cur.size() - 2].id < vocab.token_beg &&
+                                         tokens_cur[tokens_cur.size() - 1].id > vocab.token_beg;
+    if (single_timestamp_ending) seek_delta = std::min(s.seek_end - seek, 3000);
+    s.seek += seek_delta;
+    s.phase = Phase::WINDOW;
+}
+
+int run_streams(whisper_context & ctx, std::vector<StreamSpec> & specs) {
+    Engine & e = ctx.eng;
+    std::lock_guard<std::mutex> lock(e.mu);
+    cuda_clear_failure();
+    const Vocab & vocab = e.model.vocab;
+    const auto & hp = e.model.hp;
+    const int n_streams = (int) specs.size();
+    std::vector<Stream> S(n_streams);
+
+    // ---- mel of every stream in one launch ----
+    {
+        const int64_t t0 = time_us();
+        std::vector<MelJob> jobs;
+        for (int i = 0; i < n_streams; ++i) {
+            S[i].state = specs[i].state;
+            S[i].params = specs[i].params;
+            S[i].samples = specs[i].samples;
+            S[i].n_samples = specs[i].n_samples;
+            S[i].window = i;
+            S[i].state->result_all.clear();
+            if (specs[i].n_samples > 0) {
+                MelJob j;
+                if (specs[i].samples_on_device) j.pcm_dev = specs[i].samples;
+                else j.pcm_host = specs[i].samples;
+                j.n_samples = specs[i].n_samples;
+                j.out = &S[i].state->mel;
+                jobs.push_back(j);
+            }
+        }
+        if (!e.run_mel(jobs)) {
+            wlog(GGML_LOG_LEVEL_ERROR, "%s: failed to compute log mel spectrogram\n", __func__);
+            for (auto & sp : specs) sp.rc = -2;
+            return -2;
+        }
+        const int64_t dt = time_us() - t0;
+        for (int i = 0; i < n_streams; ++i) S[i].state->t_mel_us += dt / std::max(1, n_streams);
+    }
+    for (int i = 0; i < n_streams; ++i) {
+        S[i].rc = stream_begin(ctx, S[i]);
+        if (S[i].rc != 0) S[i].phase = Phase::DONE;
+    }
+
+    // static suppression mask (state independent rules); identical params across streams of one call
+    std::vector<uint32_t> static_bits;
+    build_static_suppress(ctx, S[0].params, static_bits);
+    if (!ctx.static_mask.reserve(static_bits.size() * 4)) return -7;
+    WB_CUDA(cudaMemcpy(ctx.static_mask.p, static_bits.data(), static_bits.size() * 4, cudaMemcpyHostToDevice));
+    int space_id = -1;
+    {
+        auto it = vocab.token_to_id.find(" ");
+        if (it != vocab.token_to_id.end()) space_id = it->second;
+    }
+
+    if (!e.size_cross(ctx.batch_cross, n_streams)) return -7;
+    const int n_max = hp.n_text_ctx / 2 - 4;
+    std::vector<float> logits_host((size_t) hp.n_vocab);
+
+    auto fail_stream = [&](Stream & s, int rc) {
+        s.rc = rc;
+        s.phase = Phase::DONE;
+    };
+
+    while (true) {
+        // ---- A. window start: progress / end-of-audio / encoder_begin, then one batched encode ----
+        std::vector<int> enc_ids;
+        for (int si = 0; si < n_streams; ++si) {
+            Stream & s = S[si];
+            if (s.phase != Phase::WINDOW) continue;
+            const auto & p = s.params;
+            if (p.progress_callback) {
+                const int cur = (100 * (s.seek - s.seek_start)) / (s.seek_end - s.seek_start);
+                p.progress_callback(&ctx, s.state, cur, p.progress_callback_user_data);
+            }
+            if (s.seek + 10 >= s.seek_end) {
+                s.phase = Phase::DONE;
+                continue;
+            }
+            if (p.encoder_begin_callback && !p.encoder_begin_callback(&ctx, s.state, p.encoder_begin_callback_user_data)) {
+                wlog(GGML_LOG_LEVEL_ERROR, "%s: encoder_begin_callback returned false - aborting\n", __func__);
+                s.phase = Phase::DONE;
+                continue;
+            }
+            enc_ids.push_back(si);
+        }
+        if (enc_ids.empty()) break;
+        {
+            const int64_t t0 = time_us();
+            // windows are encoded in chunks to bound the activation workspace; K/V rows land at the stream's slot
+            const int chunk = 32;
+            size_t k = 0;
+            bool ok = true;
+            while (k < enc_ids.size() && ok) {
+                // consecutive slots only (the GEMM writes a contiguous row range of the pool)
+                size_t k1 = k + 1;
+                while (k1 < enc_ids.size() && (int) (k1 - k) < chunk && S[enc_ids[k1]].window == S[enc_ids[k1 - 1]].window + 1) ++k1;
+                std::vector<EncJob> jobs;
+                for (size_t q = k; q < k1; ++q) jobs.push_back({&S[enc_ids[q]].state->mel, S[enc_ids[q]].seek});
+                ok = e.encode(jobs, ctx.batch_cross, S[enc_ids[k]].window, false);
+                k = k1;
+            }
+            const int64_t dt = time_us() - t0;
+            for (int si : enc_ids) {
+                Stream & s = S[si];
+                s.state->t_encode_us += dt / (int64_t) enc_ids.size();
+                s.state->n_encode++;
+                if (!ok) {
+                    wlog(GGML_LOG_LEVEL_ERROR, "%s: failed to encode\n", __func__);
+                    fail_stream(s, -6);
+                    continue;
+                }
+                if (s.params.abort_callback && s.params.abort_callback(s.params.abort_callback_user_data)) {
+                    fail_stream(s, -6);
+                    continue;
+                }
+                s.state->cross_base = ctx.batch_cross.window_base(s.window, hp.n_text_state);
+                s.state->cross_layer_stride = ctx.batch_cross.layer_stride;
+                if (s.seek > s.seek_start && s.seek + 500 >= s.seek_end) {
+                    s.state->prompt_past0.clear();
+                    s.state->prompt_past1.clear();
+                }
+                s.best_decoder_id = 0;
+                s.it = 0;
+                s.phase = Phase::PROMPT;
+            }
+        }
+
+        // ---- B. temperature rounds: streams that need a (re)decode at their current temperature go together ----
+        while (true) {
+            std::vector<int> act;
+            for (int si = 0; si < n_streams; ++si)
+                if (S[si].phase == Phase::PROMPT) act.push_back(si);
+            if (act.empty()) break;
+
+            // B1. per-stream decoder init + prompt; one batched prompt pass
+            std::vector<DecRow> rows;
+            std::vector<int> lrows;
+            for (int si : act) {
+                Stream & s = S[si];
+                auto & p = s.params;
+                whisper_state * st = s.state;
+                s.t_cur = s.temperatures[s.it];
+                int ndc = 1;
+                switch (p.strategy) {
+                    case WHISPER_SAMPLING_GREEDY:
+                        if (s.t_cur > 0.0f) ndc = p.greedy.best_of;
+                        break;
+                    case WHISPER_SAMPLING_BEAM_SEARCH:
+                        ndc = s.t_cur > 0.0f ? p.greedy.best_of : p.beam_search.beam_size;
+                        break;
+                }
+                s.n_decoders_cur = std::max(1, ndc);
+                s.device_path = p.strategy == WHISPER_SAMPLING_GREEDY && s.t_cur < 1e-6f && !p.logits_filter_callback;
+                for (int j = 0; j < s.n_decoders_cur; ++j) {
+                    whisper_decoder & d = st->decoders[j];
+                    d.sequence.tokens.clear();
+                    d.sequence.result_len = 0;
+                    d.sequence.sum_logprobs_all = 0.0;
+                    d.sequence.sum_logprobs = -INFINITY;
+                    d.sequence.avg_logprobs = -INFINITY;
+                    d.sequence.entropy = 0.0;
+                    d.sequence.score = -INFINITY;
+                    d.seek_delta = 3000;
+                    d.failed = d.completed = d.has_ts = false;
+                    d.has_pending = false;
+                    if (!d.kv.reserve(e.self_kv_bytes())) return -7;
+                }
+                s.prompt.clear();
+                if (p.n_max_text_ctx > 0 && s.t_cur < 0.5f) {
+                    const bool can0 = p.carry_initial_prompt && !st->prompt_past0.empty();
+                    const bool can1 = !st->prompt_past1.empty();
+                    if (s.max_prompt_ctx > 0 && (can0 || can1)) {
+                        s.prompt.push_back(vocab.token_prev);
+                        int n_take0 = 0;
+                        if (can0) {
+                            n_take0 = (int) st->prompt_past0.size();
+                            s.prompt.insert(s.prompt.end(), st->prompt_past0.end() - n_take0, st->prompt_past0.end());
+                        }
+                        const int n_take1 = std::min<int>(s.max_prompt_ctx - n_take0 - 1, (int) st->prompt_past1.size());
+                        s.prompt.insert(s.prompt.end(), st->prompt_past1.end() - n_take1, st->prompt_past1.end());
+                    }
+                }
+                s.prompt.insert(s.prompt.end(), s.prompt_init.begin(), s.prompt_init.end());
+                for (int i = 0; i < (int) s.prompt.size(); ++i)
+                    rows.push_back({s.prompt[i], i, st->decoders[0].kv.p, st->cross_base});
+                lrows.push_back((int) rows.size() - 1);
+            }
+            {
+                const int64_t t0 = time_us();
+                bool ok = e.decode(rows, lrows, ctx.batch_cross.layer_stride);
+                // no_speech_prob on the raw logits of the prompt pass (src/whisper.cpp:7188-7196)
+                std::vector<SampleRow> sr(act.size());
+                for (size_t a = 0; a < act.size(); ++a) sr[a] = {(int) a, 0, 0, 0, 0, 0};
+                std::vector<float> nosp;
+                ok = ok && e.token_prob(sr, vocab.token_nosp, nosp);
+                const int64_t dt = time_us() - t0;
+                for (size_t a = 0; a < act.size(); ++a) {
+                    Stream & s = S[act[a]];
+                    s.state->t_prompt_us += dt / (int64_t) act.size();
+                    s.state->n_prompt += (int) s.prompt.size();
+                    if (!ok) {
+                        wlog(GGML_LOG_LEVEL_ERROR, "%s: failed to decode\n", __func__);
+                        fail_stream(s, -8);
+                        continue;
+                    }
+                    s.state->no_speech_prob = nosp[a];
+                    s.phase = Phase::STEPPING;
+                }
+                if (!ok) continue;
+            }
+            // B2. process the prompt logits for decoder 0 and fan out to the other decoders
+            {
+                const int64_t t0 = time_us();
+                std::vector<SampleRow> sr;
+                std::vector<int> sr_stream;
+                for (size_t a = 0; a < act.size(); ++a) {
+                    Stream & s = S[act[a]];
+                    if (s.phase != Phase::STEPPING) continue;
+                    whisper_state * st = s.state;
+                    if (s.device_path) {
+                        sr.push_back({(int) a, 0, 0, 0, 0, 3000});
+                        sr_stream.push_back(act[a]);
+                    } else {
+                        if (!e.fetch_logits((int) a, logits_host.data())) {
+                            fail_stream(s, -8);
+                            continue;
+                        }
+                        process_logits_host(ctx, *st, st->decoders[0], s.params, static_bits, logits_host.data(), s.t_cur);
+                        for (int j = 1; j < s.n_decoders_cur; ++j) {
+                            whisper_decoder & d = st->decoders[j];
+                            e.kv_copy_prefix(st->decoders[0].kv.p, d.kv.p, (int) s.prompt.size());
+                            d.probs = st->decoders[0].probs;
+                            d.logits = st->decoders[0].logits;
+                            d.logprobs = st->decoders[0].logprobs;
+                        }
+                    }
+                }
+                if (!sr.empty()) {
+                    // all device-path streams of one call share the parameters that enter the kernel
+                    const auto & p = S[sr_stream[0]].params;
+                    SampleParams prm;
+                    prm.n_vocab = hp.n_vocab;
+                    prm.token_eot = vocab.token_eot;
+                    prm.token_beg = vocab.token_beg;
+                    prm.token_space = space_id;
+                    prm.suppress_blank = p.suppress_blank;
+                    prm.no_timestamps = p.no_timestamps;
+                    prm.max_initial_ts = p.max_initial_ts;
+                    prm.tid0 = (int) std::round(p.max_initial_ts / (30.0f / hp.n_audio_ctx));
+                    prm.temperature = 0.0f;
+                    std::vector<SampleOut> so;
+                    if (!e.sample_greedy(sr, (const uint32_t *) ctx.static_mask.p, prm, so)) {
+                        for (int si : sr_stream) fail_stream(S[si], -8);
+                    } else {
+                        for (size_t q = 0; q < sr.size(); ++q) {
+                            whisper_decoder & d = S[sr_stream[q]].state->decoders[0];
+                            d.pending = {so[q].id, so[q].tid, so[q].p, so[q].plog, so[q].pt, so[q].ptsum, -1, -1, -1, 0.0f};
+                            d.has_pending = true;
+                        }
+                    }
+                }
+                const int64_t dt = time_us() - t0;
+                for (int si : act) S[si].state->t_sample_us += dt / (int64_t) act.size();
+            }
+
+            // B3. token loop (src/whisper.cpp:7219-7544)
+            std::vector<std::vector<beam_candidate>> bc_per_dec;
+            for (int i = 0; i < n_max; ++i) {
+                const int64_t ts0 = time_us();
+                bool any_live = false;
+                for (int si : act) {
+                    Stream & s = S[si];
+                    if (s.phase != Phase::STEPPING) continue;
+                    whisper_state * st = s.state;
+                    const auto & p = s.params;
+                    const bool beam = p.strategy == WHISPER_SAMPLING_BEAM_SEARCH;
+                    if (beam) {
+                        bc_per_dec.assign(s.n_decoders_cur, {});
+                    }
+                    // sampling
+                    for (int j = 0; j < s.n_decoders_cur; ++j) {
+                        whisper_decoder & d = st->decoders[j];
+                        if (d.completed || d.failed) continue;
+                        if (!beam) {
+                            whisper_token_data tok;
+                            if (s.device_path) {
+                                tok = d.pending;
+                                d.has_pending = false;
+                            } else {
+                                tok = sample_token_host(vocab, d, s.t_cur < 1e-6f);
+                            }
+                            d.sequence.tokens.push_back(tok);
+                            d.sequence.sum_logprobs_all += tok.plog;
+                        } else {
+                            const auto toks = sample_token_topk_host(vocab, d, p.beam_search.beam_size);
+                            for (const auto & t : toks) {
+                                bc_per_dec[j].push_back({j, d.seek_delta, d.has_ts, d.sequence});
+                                bc_per_dec[j].back().sequence.tokens.push_back(t);
+                                bc_per_dec[j].back().sequence.sum_logprobs_all += t.plog;
+                            }
+                        }
+                    }
+                    if (beam) {
+                        std::vector<beam_candidate> cands;
+                        for (const auto & bc : bc_per_dec) {
+                            cands.insert(cands.end(), bc.begin(), bc.end());
+                            if (!bc.empty()) st->n_sample += 1;
+                        }
+                        std::sort(cands.begin(), cands.end(), [](const beam_candidate & a, const beam_candidate & b) {
+                            if (a.sequence.sum_logprobs_all != b.sequence.sum_logprobs_all)
+                                return a.sequence.sum_logprobs_all > b.sequence.sum_logprobs_all;
+                            return a.decoder_idx < b.decoder_idx;
+                        });
+                        uint32_t cur_c = 0;
+                        const int n_past_kv = (int) s.prompt.size() + i;
+                        std::vector<int> swapped;
+                        for (int j = 0; j < s.n_decoders_cur; ++j) {
+                            whisper_decoder & d = st->decoders[j];
+                            if (d.completed || d.failed) continue;
+                            if (cur_c >= cands.size()) cur_c = 0;
+                            auto & cur = cands[cur_c++];
+                            while (cands.size() > cur_c && sequences_equal(cands[cur_c].sequence, cur.sequence) && i > 0) ++cur_c;
+                            d.seek_delta = cur.seek_delta;
+                            d.has_ts = cur.has_ts;
+                            d.sequence = cur.sequence;
+                            // KV history of the parent beam: copy into the alternate buffer, swap afterwards
+                            if (cur.decoder_idx != j) {
+                                if (!d.kv_alt.reserve(e.self_kv_bytes())) return -7;
+                                e.kv_copy_prefix(st->decoders[cur.decoder_idx].kv.p, d.kv_alt.p, n_past_kv);
+                                swapped.push_back(j);
+                            }
+                        }
+                        for (int j : swapped) {
+                            std::swap(st->decoders[j].kv.p, st->decoders[j].kv_alt.p);
+                            std::swap(st->decoders[j].kv.cap, st->decoders[j].kv_alt.cap);
+                        }
+                    }
+                    // per-decoder state machine
+                    for (int j = 0; j < s.n_decoders_cur; ++j) {
+                        whisper_decoder & d = st->decoders[j];
+                        if (d.completed || d.failed) continue;
+                        const auto & token = d.sequence.tokens.back();
+                        if (token.id > vocab.token_beg) {
+                            const int seek_delta_new = 2 * (token.id - vocab.token_beg);
+                            if (d.has_ts && d.seek_delta > seek_delta_new && d.sequence.result_len < i) {
+                                d.failed = true;
+                                continue;
+                            }
+                            d.seek_delta = seek_delta_new;
+                            d.sequence.result_len = i + 1;
+                            d.has_ts = true;
+                        }
+                        if (token.id == vocab.token_eot || (p.max_tokens > 0 && i >= p.max_tokens) ||
+                            (d.has_ts && s.seek + d.seek_delta + 10 >= s.seek_end)) {
+                            if (d.sequence.result_len == 0 && !p.no_timestamps) {
+                                if (s.seek + d.seek_delta + 10 >= s.seek_end) {
+                                    d.sequence.result_len = i + 1;
+                                } else {
+                                    d.failed = true;
+                                    continue;
+                                }
+                            }
+                            if (p.single_segment || p.no_timestamps) {
+                                d.sequence.result_len = i + 1;
+                                d.seek_delta = 3000;
+                            }
+                            d.completed = true;
+                            continue;
+                        }
+                        if (e.model.n_loaded == 0) {
+                            d.seek_delta = 3000;
+                            d.completed = true;
+                            continue;
+                        }
+                        if (i == n_max - 1 && (d.sequence.result_len == 0 || d.seek_delta < 1500)) {
+                            d.failed = true;
+                            continue;
+                        }
+                    }
+                    bool all_done = true;
+                    for (int j = 0; j < s.n_decoders_cur; ++j)
+                        if (!(st->decoders[j].completed || st->decoders[j].failed)) all_done = false;
+                    if (all_done) s.phase = Phase::RANK;
+                    else any_live = true;
+                }
+                const int64_t ts1 = time_us();
+                for (int si : act) S[si].state->t_sample_us += (ts1 - ts0) / (int64_t) act.size();
+                if (!any_live) break;
+
+                // next-token rows of every live sequence
+                rows.clear();
+                lrows.clear();
+                std::vector<std::pair<int, int>> owner;     // (stream, decoder) per row
+                for (int si : act) {
+                    Stream & s = S[si];
+                    if (s.phase != Phase::STEPPING) continue;
+                    const int n_past = (int) s.prompt.size() + i;
+                    for (int j = 0; j < s.n_decoders_cur; ++j) {
+                        whisper_decoder & d = s.state->decoders[j];
+                        if (d.failed || d.completed) continue;
+                        d.i_batch = (int) rows.size();
+                        rows.push_back({d.sequence.tokens.back().id, n_past, d.kv.p, s.state->cross_base});
+                        lrows.push_back((int) rows.size() - 1);
+                        owner.emplace_back(si, j);
+                    }
+                }
+                const int64_t td0 = time_us();
+                bool ok = e.decode(rows, lrows, ctx.batch_cross.layer_stride);
+                // selection: device path rows in one kernel, host path rows one by one
+                std::vector<SampleRow> sr;
+                std::vector<int> sr_row;
+                for (size_t r = 0; r < owner.size() && ok; ++r) {
+                    Stream & s = S[owner[r].first];
+                    whisper_decoder & d = s.state->decoders[owner[r].second];
+                    if (s.device_path) {
+                        const auto & tk = d.sequence.tokens;
+                        const int n = (int) tk.size();
+                        sr.push_back({(int) r, n, n > 0 ? tk[n - 1].id : 0, n > 1 ? tk[n - 2].id : 0, d.has_ts ? 1 : 0, d.seek_delta});
+                        sr_row.push_back((int) r);
+                    }
+                }
+                if (ok && !sr.empty()) {
+                    const auto & p = S[owner[sr_row[0]].first].params;
+                    SampleParams prm;
+                    prm.n_vocab = hp.n_vocab;
+                    prm.token_eot = vocab.token_eot;
+                    prm.token_beg = vocab.token_beg;
+                    prm.token_space = space_id;
+                    prm.suppress_blank = p.suppress_blank;
+                    prm.no_timestamps = p.no_timestamps;
+                    prm.max_initial_ts = p.max_initial_ts;
+                    prm.tid0 = (int) std::round(p.max_initial_ts / (30.0f / hp.n_audio_ctx));
+                    prm.temperature = 0.0f;
+                    std::vector<SampleOut> so;
+                    ok = e.sample_greedy(sr, (const uint32_t *) ctx.static_mask.p, prm, so);
+                    for (size_t q = 0; q < sr.size() && ok; ++q) {
+                        whisper_decoder & d = S[owner[sr_row[q]].first].state->decoders[owner[sr_row[q]].second];
+                        d.pending = {so[q].id, so[q].tid, so[q].p, so[q].plog, so[q].pt, so[q].ptsum, -1, -1, -1, 0.0f};
+                        d.has_pending = true;
+                    }
+                }
+                const int64_t td1 = time_us();
+                for (size_t r = 0; r < owner.size() && ok; ++r) {
+                    Stream & s = S[owner[r].first];
+                    if (s.device_path) continue;
+                    whisper_decoder & d = s.state->decoders[owner[r].second];
+                    ok = e.fetch_logits((int) r, logits_host.data());
+                    if (ok) process_logits_host(ctx, *s.state, d, s.params, static_bits, logits_host.data(), s.t_cur);
+                }
+                const int64_t td2 = time_us();
+                // timing buckets as the reference: per-call, by batch width
+                for (int si : act) {
+                    Stream & s = S[si];
+                    if (s.phase != Phase::STEPPING) continue;
+                    int n_rows = 0;
+                    for (const auto & o : owner)
+                        if (o.first == si) n_rows++;
+                    const int64_t share = (td1 - td0) / std::max<int64_t>(1, (int64_t) owner.size()) * n_rows;
+                    if (n_rows == 1) {
+                        s.state->t_decode_us += share;
+                        s.state->n_decode++;
+                    } else {
+                        s.state->t_batchd_us += share;
+                        s.state->n_batchd += n_rows;
+                    }
+                    s.state->t_sample_us += (td2 - td1) / std::max<int64_t>(1, (int64_t) act.size());
+                    s.state->n_sample += n_rows;
+                    if (!ok) {
+                        wlog(GGML_LOG_LEVEL_ERROR, "%s: failed to decode\n", __func__);
+                        fail_stream(s, -9);
+                    } else if (s.params.abort_callback && s.params.abort_callback(s.params.abort_callback_user_data)) {
+                        fail_stream(s, -9);
+                    }
+                }
+                if (!ok) break;
+            }
+            // streams that ran out of steps without all decoders finishing
+            for (int si : act)
+                if (S[si].phase == Phase::STEPPING) S[si].phase = Phase::RANK;
+
+            // B4. rank sequences, decide on fallback (src/whisper.cpp:7546-7606)
+            for (int si : act) {
+                Stream & s = S[si];
+                if (s.phase != Phase::RANK) continue;
+                whisper_state * st = s.state;
+                const auto & p = s.params;
+                double best_score = -INFINITY;
+                for (int j = 0; j < s.n_decoders_cur; ++j) {
+                    whisper_decoder & d = st->decoders[j];
+                    if (d.failed) continue;
+                    d.sequence.tokens.resize(d.sequence.result_len);
+                    sequence_score(p, d.sequence);
+                    if (d.sequence.result_len > 32 && d.sequence.entropy < p.entropy_thold) {
+                        d.failed = true;
+                        st->n_fail_h++;
+                        continue;
+                    }
+                    if (best_score < d.sequence.score) {
+                        best_score = d.sequence.score;
+                        s.best_decoder_id = j;
+                    }
+                }
+                bool success = true;
+                if (s.it != (int) s.temperatures.size() - 1) {
+                    const whisper_decoder & d = st->decoders[s.best_decoder_id];
+                    if (d.failed || (d.sequence.avg_logprobs < p.logprob_thold && st->no_speech_prob < p.no_speech_thold)) {
+                        success = false;
+                        st->n_fail_p++;
+                    }
+                }
+                if (success) {
+                    stream_finish_window(ctx, s);
+                } else {
+                    s.it++;
+                    s.phase = Phase::PROMPT;
+                }
+            }
+        }
+    }
+    int rc = 0;
+    for (int i = 0; i < n_streams; ++i) {
+        specs[i].rc = S[i].rc;
+        if (S[i].rc != 0 && rc == 0) rc = S[i].rc;
+    }
+    if (cuda_failed() && rc == 0) rc = -6;
+    return rc;
+}
+
+}  // namespace wb
