@@ -58,6 +58,14 @@ WB200_API int whisper_b200_dtype(struct whisper_context * ctx);
 /* Number of kernels of this library launched on the context so far. */
 WB200_API long long whisper_b200_kernel_launches(struct whisper_context * ctx);
 
+/* Per-kernel-class timing with CUDA events on the library's stream.  enable(1) resets and starts, enable(0) stops.
+ * read() fills out[3*c + {0,1,2}] = {milliseconds, launches, algorithmic work} for class c and returns the number of
+ * classes, in this order: mel(bytes), im2col(bytes), gemm_conv(flop), layernorm(bytes), gemm_encoder(flop),
+ * encoder_attention(flop), gemm_cross_kv(flop), decoder_misc(bytes), gemm_decoder(bytes), self_attention(bytes),
+ * cross_attention(bytes), gemm_logits(bytes), sample(bytes). */
+WB200_API void whisper_b200_profile_enable(struct whisper_context * ctx, int on);
+WB200_API int whisper_b200_profile_read(struct whisper_context * ctx, double * out, int cap);
+
 /* ---- (2) kernel hooks ------------------------------------------------------------------------------------- */
 
 /* Fused log-mel kernel on one PCM buffer (host pointers).  Output is the reference's final container

@@ -30,7 +30,13 @@ EXT_PROTOTYPES = {
     "whisper_b200_get_cross_kv": (_C.c_int, [_C.c_void_p, _C.c_int, _U16P, _C.c_int]),
     "whisper_b200_dtype": (_C.c_int, [_C.c_void_p]),
     "whisper_b200_kernel_launches": (_C.c_longlong, [_C.c_void_p]),
+    "whisper_b200_profile_enable": (None, [_C.c_void_p, _C.c_int]),
+    "whisper_b200_profile_read": (_C.c_int, [_C.c_void_p, _C.POINTER(_C.c_double), _C.c_int]),
 }
+
+PROFILE_CLASSES = [("mel", "B"), ("im2col", "B"), ("gemm_conv", "flop"), ("layernorm", "B"), ("gemm_encoder", "flop"),
+                   ("encoder_attention", "flop"), ("gemm_cross_kv", "flop"), ("decoder_misc", "B"), ("gemm_decoder", "B"),
+                   ("self_attention", "B"), ("cross_attention", "B"), ("gemm_logits", "B"), ("sample", "B")]
 
 _lib = None
 

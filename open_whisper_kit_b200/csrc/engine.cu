@@ -53,7 +53,57 @@ bool Engine::init(int dev, bool fa) {
     return true;
 }
 
+void Engine::prof_begin(int cls, double work) {
+    if (!prof_on) return;
+    ProfRec r;
+    r.cls = cls;
+    r.work = work;
+    auto get = [&]() {
+        cudaEvent_t e;
+        if (!prof_pool.empty()) {
+            e = prof_pool.back();
+            prof_pool.pop_back();
+        } else {
+            WB_CUDA(cudaEventCreate(&e));
+        }
+        return e;
+    };
+    r.a = get();
+    r.b = get();
+    WB_CUDA(cudaEventRecord(r.a, stream));
+    prof_recs.push_back(r);
+}
+void Engine::prof_end() {
+    if (!prof_on || prof_recs.empty()) return;
+    WB_CUDA(cudaEventRecord(prof_recs.back().b, stream));
+    if (prof_recs.size() >= 4096) prof_collect();
+}
+void Engine::prof_collect() {
+    if (prof_recs.empty()) return;
+    WB_CUDA(cudaStreamSynchronize(stream));
+    for (auto & r : prof_recs) {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            prof_ms[r.cls] += ms;
+            prof_work[r.cls] += r.work;
+            prof_n[r.cls] += 1;
+        }
+        prof_pool.push_back(r.a);
+        prof_pool.push_back(r.b);
+    }
+    prof_recs.clear();
+}
+void Engine::prof_reset() {
+    prof_collect();
+    for (int i = 0; i < PC_COUNT; ++i) {
+        prof_ms[i] = prof_work[i] = 0.0;
+        prof_n[i] = 0;
+    }
+}
+
 Engine::~Engine() {
+    prof_collect();
+    for (auto e : prof_pool) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i)
         if (h_pinned[i]) cudaFreeHost(h_pinned[i]);
     if (stream) cudaStreamDestroy(stream);
@@ -106,7 +156,11 @@ bool Engine::run_mel(const std::vector<MelJob> & jobs) {
         max_frames = std::max(max_frames, g.n_frames_fft);
     }
     WB_CUDA(cudaMemcpyAsync(meta.p, sts.data(), sts.size() * sizeof(MelStream), cudaMemcpyHostToDevice, stream));
+    double mel_bytes = 0.0;
+    for (const auto & j : jobs) mel_bytes += (double) j.n_samples * 4.0 + (double) (j.n_samples / 160) * n_mel * 4.0;
+    prof_begin(PC_MEL, mel_bytes);
     mel_launch(mel_plan, (const MelStream *) meta.p, (int) jobs.size(), max_frames, stream);
+    prof_end();
     n_kernel_launches += 1;
     WB_CUDA(cudaStreamSynchronize(stream));   // sts / host PCM go out of scope
     return !cuda_failed();
@@ -191,20 +245,33 @@ bool Engine::encode(const std::vector<EncJob> & jobs, CrossKV & kv, int win0, bo
     WB_CUDA(cudaMemcpyAsync(d_wins, wins.data(), W * sizeof(EncWindow), cudaMemcpyHostToDevice, stream));
 
     bool ok = true;
+    int gemm_cls = PC_GEMM_CONV;
     auto gemm = [&](const GemmArgs & g) {
+        prof_begin(gemm_cls, 2.0 * g.M * (double) g.N * g.K);
         ok = ok && tc_gemm(g, stream);
+        prof_end();
+        n_kernel_launches += 1;
+    };
+    auto ln = [&](const float * xin, const float * gw, const float * gb, void * y16, float * y32) {
+        prof_begin(PC_LAYERNORM, (double) M * d * 6.0);
+        layernorm(dt, xin, d, gw, gb, hp.eps, (int) M, d, y16, d, y32, d, nullptr, stream);
+        prof_end();
         n_kernel_launches += 1;
     };
 
     // conv stem: two GEMMs over im2col'd time-major activations, GELU fused; positional add fused into the second
+    prof_begin(PC_IM2COL, (double) M1 * k1 * 2.0);
     im2col1(dt, d_wins, W, n_mel, k1, A1, stream);
+    prof_end();
     {
         GemmArgs g;
         g.dtype = dt; g.M = (int) M1; g.N = d; g.K = k1; g.a = A1; g.lda = k1; g.w = model.conv1_w; g.ldw = k1;
         g.bias = model.conv1_b; g.gelu = true; g.out16 = act1; g.ldo16 = d;
         gemm(g);
     }
+    prof_begin(PC_IM2COL, (double) M * 3 * d * 4.0);
     im2col2(act1, W, d, A2, stream);
+    prof_end();
     {
         GemmArgs g;
         g.dtype = dt; g.M = (int) M; g.N = d; g.K = 3 * d; g.a = A2; g.lda = 3 * d; g.w = model.conv2_w; g.ldw = 3 * d;
@@ -213,23 +280,27 @@ bool Engine::encode(const std::vector<EncJob> & jobs, CrossKV & kv, int win0, bo
     }
     n_kernel_launches += 2;
 
+    gemm_cls = PC_GEMM_ENC;
     for (int il = 0; il < hp.n_audio_layer; ++il) {
         const EncLayer & L = model.enc[il];
-        layernorm(dt, x, d, L.ln1_w, L.ln1_b, hp.eps, (int) M, d, h16, d, nullptr, 0, nullptr, stream);
+        ln(x, L.ln1_w, L.ln1_b, h16, nullptr);
         {
             GemmArgs g;
             g.dtype = dt; g.M = (int) M; g.N = 3 * d; g.K = d; g.a = h16; g.lda = d; g.w = L.wqkv; g.ldw = d;
             g.bias = L.bqkv; g.out16 = qkv; g.ldo16 = 3 * d;
             gemm(g);
         }
+        prof_begin(PC_ENC_ATTN, 4.0 * (double) W * T * (double) T * d);
         enc_attention(dt, qkv, att, W, T, d, H, n_phantom(), stream);
+        prof_end();
+        n_kernel_launches += 1;
         {
             GemmArgs g;
             g.dtype = dt; g.M = (int) M; g.N = d; g.K = d; g.a = att; g.lda = d; g.w = L.wo; g.ldw = d;
             g.bias = L.bo; g.resid = x; g.ldr = d; g.out32 = x; g.ldo32 = d;
             gemm(g);
         }
-        layernorm(dt, x, d, L.ln2_w, L.ln2_b, hp.eps, (int) M, d, h16, d, nullptr, 0, nullptr, stream);
+        ln(x, L.ln2_w, L.ln2_b, h16, nullptr);
         {
             GemmArgs g;
             g.dtype = dt; g.M = (int) M; g.N = 4 * d; g.K = d; g.a = h16; g.lda = d; g.w = L.w1; g.ldw = d;
@@ -242,15 +313,14 @@ bool Engine::encode(const std::vector<EncJob> & jobs, CrossKV & kv, int win0, bo
             g.bias = L.b2; g.resid = x; g.ldr = d; g.out32 = x; g.ldo32 = d;
             gemm(g);
         }
-        n_kernel_launches += 3;
     }
     float * e32 = nullptr;
     if (keep_embd32) {
         if (!embd_enc32.reserve(M * d * 4)) return false;
         e32 = (float *) embd_enc32.p;
     }
-    layernorm(dt, x, d, model.e_ln_w, model.e_ln_b, hp.eps, (int) M, d, enc16, d, e32, d, nullptr, stream);
-    n_kernel_launches += 1;
+    ln(x, model.e_ln_w, model.e_ln_b, enc16, e32);
+    gemm_cls = PC_GEMM_CROSS;
 
     // cross K/V for every text layer straight into the pool: K scaled by dh^-0.25 (no bias), V + bias
     const float kscale = powf(64.0f, -0.25f);
@@ -301,47 +371,68 @@ bool Engine::decode(const std::vector<DecRow> & rows, const std::vector<int> & l
     if (RL) WB_CUDA(cudaMemcpyAsync(d_lrows, hp_buf + R * sizeof(DecRow), RL * sizeof(int), cudaMemcpyHostToDevice, stream));
 
     bool ok = true;
+    int gemm_cls = PC_GEMM_DEC;
     auto gemm = [&](const GemmArgs & g) {
+        prof_begin(gemm_cls, ((double) g.N * g.K + (double) g.M * (g.N + g.K)) * 2.0);   // bytes: weights + activations
         ok = ok && tc_gemm(g, stream);
+        prof_end();
+        n_kernel_launches += 1;
+    };
+    auto ln = [&](const float * gw, const float * gb) {
+        prof_begin(PC_LAYERNORM, (double) R * d * 6.0);
+        layernorm(dt, x, d, gw, gb, hp.eps, R, d, h16, d, nullptr, 0, nullptr, stream);
+        prof_end();
         n_kernel_launches += 1;
     };
     const float qk_scale = powf(64.0f, -0.25f);
     const size_t self_layer = (size_t) n_ctx * 2 * d;
 
+    prof_begin(PC_DEC_MISC, (double) R * d * 10.0);
     dec_embed(dt, model.d_te, model.d_pe, d_rows, R, d, x, stream);
+    prof_end();
     n_kernel_launches += 1;
     for (int il = 0; il < hp.n_text_layer; ++il) {
         const DecLayer & L = model.dec[il];
-        layernorm(dt, x, d, L.ln1_w, L.ln1_b, hp.eps, R, d, h16, d, nullptr, 0, nullptr, stream);
+        ln(L.ln1_w, L.ln1_b);
         {
             GemmArgs g;   // Q and K carry dh^-0.25 each (src/whisper.cpp:2506, 2550, 2557); V is biased only
             g.dtype = dt; g.M = R; g.N = 3 * d; g.K = d; g.a = h16; g.lda = d; g.w = L.wqkv; g.ldw = d;
             g.bias = L.bqkv; g.scale = qk_scale; g.scale_cols = 2 * d; g.out16 = qkv; g.ldo16 = 3 * d;
             gemm(g);
         }
+        prof_begin(PC_DEC_MISC, (double) R * 2 * d * 4.0);
         dec_kv_append(qkv, d_rows, R, d, il * self_layer, stream);
+        prof_end();
+        double self_bytes = 0.0;
+        for (const auto & rw : rows) self_bytes += (double) (rw.pos + 1) * 2 * d * 2.0;
+        prof_begin(PC_SELF_ATTN, self_bytes);
         dec_self_attn(dt, qkv, d_rows, R, d, H, il * self_layer, n_ctx, att, stream);
+        prof_end();
+        n_kernel_launches += 2;
         {
             GemmArgs g;
             g.dtype = dt; g.M = R; g.N = d; g.K = d; g.a = att; g.lda = d; g.w = L.wo; g.ldw = d;
             g.bias = L.bo; g.resid = x; g.ldr = d; g.out32 = x; g.ldo32 = d;
             gemm(g);
         }
-        layernorm(dt, x, d, L.lnx_w, L.lnx_b, hp.eps, R, d, h16, d, nullptr, 0, nullptr, stream);
+        ln(L.lnx_w, L.lnx_b);
         {
             GemmArgs g;
             g.dtype = dt; g.M = R; g.N = d; g.K = d; g.a = h16; g.lda = d; g.w = L.wxq; g.ldw = d;
             g.bias = L.bxq; g.out16 = q16; g.ldo16 = d;
             gemm(g);
         }
+        prof_begin(PC_CROSS_ATTN, (double) R * 1500.0 * 2 * d * 2.0);
         dec_cross_attn(dt, q16, d_rows, R, d, H, il * cross_layer_stride, 1500, n_phantom(), att, stream);
+        prof_end();
+        n_kernel_launches += 1;
         {
             GemmArgs g;
             g.dtype = dt; g.M = R; g.N = d; g.K = d; g.a = att; g.lda = d; g.w = L.wxo; g.ldw = d;
             g.bias = L.bxo; g.resid = x; g.ldr = d; g.out32 = x; g.ldo32 = d;
             gemm(g);
         }
-        layernorm(dt, x, d, L.ln2_w, L.ln2_b, hp.eps, R, d, h16, d, nullptr, 0, nullptr, stream);
+        ln(L.ln2_w, L.ln2_b);
         {
             GemmArgs g;
             g.dtype = dt; g.M = R; g.N = 4 * d; g.K = d; g.a = h16; g.lda = d; g.w = L.w1; g.ldw = d;
@@ -354,11 +445,13 @@ bool Engine::decode(const std::vector<DecRow> & rows, const std::vector<int> & l
             g.bias = L.b2; g.resid = x; g.ldr = d; g.out32 = x; g.ldo32 = d;
             gemm(g);
         }
-        n_kernel_launches += 6;
     }
     if (RL > 0) {
         // final LayerNorm only on the rows whose logits are wanted, then the tied-embedding logits GEMM
+        prof_begin(PC_LAYERNORM, (double) RL * d * 6.0);
         layernorm(dt, x, d, model.d_ln_w, model.d_ln_b, hp.eps, RL, d, hl16, d, nullptr, 0, d_lrows, stream);
+        prof_end();
+        gemm_cls = PC_GEMM_LOGITS;
         GemmArgs g;
         g.dtype = dt; g.M = RL; g.N = V; g.K = d; g.a = hl16; g.lda = d; g.w = model.d_te; g.ldw = d;
         g.out32 = (float *) logits.p; g.ldo32 = ld_logits;
@@ -388,7 +481,9 @@ bool Engine::sample_greedy(const std::vector<SampleRow> & srows, const uint32_t 
     char * hb = (char *) pinned(1, in_b + out_b);
     memcpy(hb, srows.data(), in_b);
     WB_CUDA(cudaMemcpyAsync(d_in, hb, in_b, cudaMemcpyHostToDevice, stream));
+    prof_begin(PC_SAMPLE, (double) R * model.hp.n_vocab * 4.0 * 5.0);
     dec_sample_greedy((float *) logits.p, ld_logits, d_in, R, d_mask, prm, d_out, stream);
+    prof_end();
     n_kernel_launches += 1;
     WB_CUDA(cudaMemcpyAsync(hb + in_b, d_out, out_b, cudaMemcpyDeviceToHost, stream));
     WB_CUDA(cudaStreamSynchronize(stream));

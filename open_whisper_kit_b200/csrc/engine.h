@@ -62,6 +62,12 @@ struct EncJob {
     int seek = 0;
 };
 
+// Optional per-kernel-class timing with CUDA events on the engine's stream (bench.py's roofline numbers).
+enum ProfClass {
+    PC_MEL = 0, PC_IM2COL, PC_GEMM_CONV, PC_LAYERNORM, PC_GEMM_ENC, PC_ENC_ATTN, PC_GEMM_CROSS, PC_DEC_MISC, PC_GEMM_DEC,
+    PC_SELF_ATTN, PC_CROSS_ATTN, PC_GEMM_LOGITS, PC_SAMPLE, PC_COUNT
+};
+
 struct Engine {
     Model model;
     bool flash_attn = true;
@@ -79,6 +85,18 @@ struct Engine {
     void * h_pinned[2] = {nullptr, nullptr};   // pinned host staging: [0] decoder rows (H2D), [1] sampler I/O
     size_t h_pinned_cap[2] = {0, 0};
     long long n_kernel_launches = 0;   // launches of our own kernels (bench.py reports them)
+
+    // profiler
+    struct ProfRec { int cls; cudaEvent_t a, b; double work; };
+    bool prof_on = false;
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> prof_pool;
+    double prof_ms[PC_COUNT] = {}, prof_work[PC_COUNT] = {};
+    long long prof_n[PC_COUNT] = {};
+    void prof_begin(int cls, double work);
+    void prof_end();
+    void prof_collect();     // synchronises, folds the pending records into prof_ms / prof_work / prof_n
+    void prof_reset();
 
     int n_phantom() const { return flash_attn ? 36 : 0; }
 

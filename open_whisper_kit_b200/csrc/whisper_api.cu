@@ -715,6 +715,27 @@ WB200_API int whisper_b200_dtype(struct whisper_context * ctx) { return ctx ? (i
 
 WB200_API long long whisper_b200_kernel_launches(struct whisper_context * ctx) { return ctx ? ctx->eng.n_kernel_launches : 0; }
 
+WB200_API void whisper_b200_profile_enable(struct whisper_context * ctx, int on) {
+    if (!ctx) return;
+    std::lock_guard<std::mutex> lock(ctx->eng.mu);
+    cudaSetDevice(ctx->eng.device);
+    ctx->eng.prof_reset();
+    ctx->eng.prof_on = on != 0;
+}
+
+WB200_API int whisper_b200_profile_read(struct whisper_context * ctx, double * out, int cap) {
+    if (!ctx || !out || cap < 3 * PC_COUNT) return -1;
+    std::lock_guard<std::mutex> lock(ctx->eng.mu);
+    cudaSetDevice(ctx->eng.device);
+    ctx->eng.prof_collect();
+    for (int i = 0; i < PC_COUNT; ++i) {
+        out[3 * i + 0] = ctx->eng.prof_ms[i];
+        out[3 * i + 1] = (double) ctx->eng.prof_n[i];
+        out[3 * i + 2] = ctx->eng.prof_work[i];
+    }
+    return PC_COUNT;
+}
+
 WB200_API int whisper_b200_full_device(struct whisper_context * ctx, struct whisper_full_params params, const float * d_samples,
                                        int n_samples, int n_processors) {
     if (!ctx || !ctx->state || !d_samples || n_processors < 1) return -1;
