@@ -85,7 +85,17 @@ WB200_API int whisper_b200_kernel_gemm(int dtype, int M, int N, int K, const uin
                                        const float * bias, float scale, int scale_cols, int gelu, const float * pos,
                                        int pos_rows, const float * resid, uint16_t * out16, float * out32);
 
+/* Weight-streaming GEMM of the decoder step (M <= 128 rows), same epilogue; replaces mul_mat_vec_f / mul_mat_f,
+ * reference ggml/src/ggml-cuda/mmvf.cu:8, mmf.cuh:50. */
+WB200_API int whisper_b200_kernel_skinny_gemm(int dtype, int M, int N, int K, const uint16_t * a, const uint16_t * w,
+                                              const float * bias, float scale, int scale_cols, int gelu,
+                                              const float * resid, uint16_t * out16, float * out32);
+
 WB200_API double whisper_b200_kernel_gemm_bench(int dtype, int M, int N, int K, int gelu, int iters);
+
+/* Average microseconds of one decoder-step kernel launched back to back: which = 0 LayerNorm, 1 cross-attention,
+ * 2 self-attention at position aux, 3 KV append; R rows of width d. */
+WB200_API double whisper_b200_kernel_step_bench(int which, int dtype, int R, int d, int aux, int iters);
 
 #ifdef __cplusplus
 }

@@ -33,78 +33,18 @@ __global__ void kv_append_kernel(const uint4 * __restrict__ qkv, const DecRow * 
     for (int c = threadIdx.x; c < 2 * d8; c += blockDim.x) dst[c] = src[c];
 }
 
-// One warp per (row, head).  Scores over positions 0..pos of the row's slot (causal), softmax in f32, probabilities
-// rounded to the 16-bit operand type before the PV product (as the reference's KQV mul_mat does), f32 accumulation.
-template <typename T16>
-__global__ void self_attn_kernel(const T16 * __restrict__ qkv, const DecRow * __restrict__ rows, int d, int n_head,
-                                 size_t layer_off, int n_ctx, T16 * __restrict__ out) {
-    extern __shared__ float s_scores[];      // [warps][n_ctx]
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int idx = blockIdx.x * (blockDim.x >> 5) + warp;
-    const int r = idx / n_head, h = idx % n_head;
-    float * sc = s_scores + (size_t) warp * n_ctx;
-    const DecRow row = rows[r];
-    const int n_kv = row.pos + 1;
-    const T16 * kbase = reinterpret_cast<const T16 *>(row.self_kv) + layer_off + h * 64;
-    const int ld = 2 * d;
-
-    // q (64 values) in registers of every lane
-    float q[64];
-    {
-        const uint4 * qp = reinterpret_cast<const uint4 *>(qkv + (size_t) r * 3 * d + h * 64);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const uint4 u = qp[i];
-            const T16 * e = reinterpret_cast<const T16 *>(&u);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) q[i * 8 + j] = Half16<T16>::to_f(e[j]);
-        }
-    }
-    float mx = -INFINITY;
-    for (int p = lane; p < n_kv; p += 32) {
-        const uint4 * kp = reinterpret_cast<const uint4 *>(kbase + (size_t) p * ld);
-        float acc = 0.0f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const uint4 u = kp[i];
-            const T16 * e = reinterpret_cast<const T16 *>(&u);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc = fmaf(q[i * 8 + j], Half16<T16>::to_f(e[j]), acc);
-        }
-        sc[p] = acc;
-        mx = fmaxf(mx, acc);
-    }
-    mx = warp_max(mx);
-    float sum = 0.0f;
-    for (int p = lane; p < n_kv; p += 32) {
-        const float e = expf(sc[p] - mx);
-        sc[p] = e;
-        sum += e;
-    }
-    sum = warp_sum(sum);
-    const float inv = 1.0f / sum;
-    __syncwarp();
-    // PV: lane owns dims 2*lane, 2*lane+1
-    const T16 * vbase = kbase + d;
-    float o0 = 0.0f, o1 = 0.0f;
-    for (int p = 0; p < n_kv; ++p) {
-        const float pr = Half16<T16>::to_f(Half16<T16>::from_f(sc[p] * inv));
-        const T16 * vp = vbase + (size_t) p * ld + 2 * lane;
-        o0 = fmaf(pr, Half16<T16>::to_f(vp[0]), o0);
-        o1 = fmaf(pr, Half16<T16>::to_f(vp[1]), o1);
-    }
-    T16 * op = out + (size_t) r * d + h * 64 + 2 * lane;
-    op[0] = Half16<T16>::from_f(o0);
-    op[1] = Half16<T16>::from_f(o1);
-}
-
 // One CTA (128 threads) per (row, head) streaming the window's cross K/V: 8 lanes x 16 bytes cover one 64-value key
 // row, so every warp-wide load instruction reads four whole 128-byte rows.  kv: [xslot][layer][T][2d] (K | V), K already
 // carries dh^-0.25 (cross graph, src/whisper.cpp:2300-2305); score = (q.k) * dh^-0.25 (src/whisper.cpp:2695, 2719).
-template <typename T16>
+//
+// SELF = true runs the same streaming scheme over the row's own self-attention cache (keys 0..pos, scale 1, no
+// phantom keys; Q and K already carry dh^-0.25 each, src/whisper.cpp:2506-2557).  With fused_append the CTA first stores
+// this token's K/V head slice into the cache (single-token steps only: every sequence owns exactly one row, so no
+// other CTA needs the slice).
+template <typename T16, bool SELF>
 __global__ void __launch_bounds__(128)
-cross_attn_kernel(const T16 * __restrict__ q, const DecRow * __restrict__ rows, int d, size_t layer_off, int T,
-                  float kq_scale, int n_phantom, T16 * __restrict__ out) {
+cross_attn_kernel(const T16 * __restrict__ q, int ldq, const DecRow * __restrict__ rows, int d, size_t layer_off, int T_in,
+                  float kq_scale, int n_phantom, int fused_append, T16 * __restrict__ out) {
     extern __shared__ float s_sc[];          // [T]
     __shared__ float s_red[8];
     __shared__ float s_o[4][64];
@@ -112,33 +52,57 @@ cross_attn_kernel(const T16 * __restrict__ q, const DecRow * __restrict__ rows, 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int sub = lane & 7, grp = lane >> 3;     // 8 lanes per key row, 4 key rows per warp instruction
     const DecRow row = rows[r];
-    const T16 * kbase = reinterpret_cast<const T16 *>(row.cross_kv) + layer_off + h * 64;
+    const int T = SELF ? row.pos + 1 : T_in;
+    const T16 * kbase = (SELF ? reinterpret_cast<const T16 *>(row.self_kv) : reinterpret_cast<const T16 *>(row.cross_kv)) +
+                        layer_off + h * 64;
     const int ld = 2 * d;
+    if (SELF && fused_append) {
+        if (tid < 16) {
+            const int which = tid >> 3, c = tid & 7;       // 0: K slice, 1: V slice; 8 x 16 bytes each
+            const uint4 u = *reinterpret_cast<const uint4 *>(q + (size_t) r * ldq + (1 + which) * d + h * 64 + c * 8);
+            T16 * dst = reinterpret_cast<T16 *>(row.self_kv) + layer_off + (size_t) row.pos * ld + which * d + h * 64 + c * 8;
+            *reinterpret_cast<uint4 *>(dst) = u;
+        }
+        __threadfence_block();
+        __syncthreads();
+    }
 
     float qv[8];
     {
-        const uint4 u = *reinterpret_cast<const uint4 *>(q + (size_t) r * d + h * 64 + sub * 8);
+        const uint4 u = *reinterpret_cast<const uint4 *>(q + (size_t) r * ldq + h * 64 + sub * 8);
         const T16 * e = reinterpret_cast<const T16 *>(&u);
 #pragma unroll
         for (int j = 0; j < 8; ++j) qv[j] = Half16<T16>::to_f(e[j]);
     }
+    // keys t = warp*4 + grp + 16*i.  Eight independent 16-byte loads are issued before any is consumed so every
+    // lane keeps 128 bytes in flight (memory-level parallelism instead of one dependent load per iteration).
+    constexpr int U = 8;
     float mx = -INFINITY;
-    for (int t0 = warp * 4; t0 < T; t0 += 16) {
-        const int t = t0 + grp;
-        float acc = 0.0f;
-        if (t < T) {
-            const uint4 u = __ldg(reinterpret_cast<const uint4 *>(kbase + (size_t) t * ld + sub * 8));
-            const T16 * e = reinterpret_cast<const T16 *>(&u);
+    // the trip count must be warp-uniform (full-mask shuffles inside): iterate on a common base, predicate per key
+    for (int base = 0; base < T; base += 16 * U) {
+        const int tb = base + warp * 4 + grp;
+        uint4 kb[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int t = tb + 16 * u;
+            const uint4 * src = reinterpret_cast<const uint4 *>(kbase + (size_t) t * ld + sub * 8);
+            kb[u] = t < T ? (SELF ? *src : __ldg(src)) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int t = tb + 16 * u;
+            const T16 * e = reinterpret_cast<const T16 *>(&kb[u]);
+            float acc = 0.0f;
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc = fmaf(qv[j], Half16<T16>::to_f(e[j]), acc);
-        }
-        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-        acc *= kq_scale;
-        if (t < T) {
-            if (sub == 0) s_sc[t] = acc;
-            mx = fmaxf(mx, acc);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+            acc *= kq_scale;
+            if (t < T) {
+                if (sub == 0) s_sc[t] = acc;
+                mx = fmaxf(mx, acc);
+            }
         }
     }
     mx = warp_max(mx);
@@ -163,14 +127,23 @@ cross_attn_kernel(const T16 * __restrict__ q, const DecRow * __restrict__ rows, 
     float o[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = 0.0f;
-    for (int t0 = warp * 4; t0 < T; t0 += 16) {
-        const int t = t0 + grp;
-        if (t < T) {
-            const float pr = Half16<T16>::to_f(Half16<T16>::from_f(s_sc[t] * inv));
-            const uint4 u = __ldg(reinterpret_cast<const uint4 *>(vbase + (size_t) t * ld + sub * 8));
-            const T16 * e = reinterpret_cast<const T16 *>(&u);
+    for (int base = 0; base < T; base += 16 * U) {
+        const int tb = base + warp * 4 + grp;
+        uint4 vb[U];
+        float pr[U];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = fmaf(pr, Half16<T16>::to_f(e[j]), o[j]);
+        for (int u = 0; u < U; ++u) {
+            const int t = tb + 16 * u;
+            const bool ok = t < T;
+            const uint4 * src = reinterpret_cast<const uint4 *>(vbase + (size_t) t * ld + sub * 8);
+            vb[u] = ok ? (SELF ? *src : __ldg(src)) : make_uint4(0, 0, 0, 0);
+            pr[u] = ok ? Half16<T16>::to_f(Half16<T16>::from_f(s_sc[t] * inv)) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const T16 * e = reinterpret_cast<const T16 *>(&vb[u]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = fmaf(pr[u], Half16<T16>::to_f(e[j]), o[j]);
         }
     }
 #pragma unroll
@@ -323,21 +296,32 @@ sample_greedy_kernel(float * __restrict__ logits, int ld, const SampleRow * __re
     const bool mask_text = ts_lp > lp_text_max;
 
     // pass 4: probs, greedy arg-max (first maximal index), timestamp statistics  (src/whisper.cpp:6460-6517)
-    ArgMax best = {0.0f, 0x7fffffff}, best_ts = {0.0f, 0x7fffffff};
+    ArgMax best = {0.0f, 0x7fffffff}, best_ts = {0.0f, 0x7fffffff}, second = {0.0f, 0x7fffffff};
     double sum_ts = 0.0;
     for (int i = tid; i < V; i += SAMPLE_THREADS) {
         const float v = l[i];
         float p = 0.0f;
         if (v > -INFINITY && !(mask_text && i < beg)) p = expf(v - logZ);
         if (p > 0.0f) {
-            best = amax(best, ArgMax{p, i});
+            const ArgMax cur = {p, i};
+            if (amax(best, cur).i == i) {
+                second = best;
+                best = cur;
+            } else {
+                second = amax(second, cur);
+            }
             if (i >= beg) {
                 best_ts = amax(best_ts, ArgMax{p, i});
             }
         }
         if (i >= beg) sum_ts += (double) p;
     }
-    best = block_amax<SAMPLE_THREADS>(best, sh_a);
+    {   // block-wide top-2: the runner-up is the best of (everyone's second, every loser's best)
+        const ArgMax my_best = best;
+        best = block_amax<SAMPLE_THREADS>(best, sh_a);
+        const ArgMax cand = (my_best.i == best.i) ? second : my_best;
+        second = block_amax<SAMPLE_THREADS>(cand, sh_a);
+    }
     best_ts = block_amax<SAMPLE_THREADS>(best_ts, sh_a);
     sum_ts = block_sum_d<SAMPLE_THREADS>(sum_ts, sh_d);
     if (tid == 0) {
@@ -352,6 +336,8 @@ sample_greedy_kernel(float * __restrict__ logits, int ld, const SampleRow * __re
             o.tid = o.id;
             o.pt = o.p;
         }
+        o.runner_up = second.i == 0x7fffffff ? -1 : second.i;
+        o.gap = (best.i != 0x7fffffff && second.i != 0x7fffffff) ? l[best.i] - l[second.i] : INFINITY;
         outs[r] = o;
     }
 }
@@ -392,22 +378,20 @@ void dec_kv_append(const void * qkv, const DecRow * d_rows, int R, int d, size_t
     WB_CUDA(cudaGetLastError());
 }
 
-template <typename T16>
-static void self_attn_launch(const void * qkv, const DecRow * d_rows, int R, int d, int n_head, size_t layer_off, int n_ctx,
-                             void * out, cudaStream_t st) {
-    const int total = R * n_head;
-    // the kernel maps idx = block*warps + warp -> (row, head); launch exact multiples only
-    const int warps = (total % 4 == 0) ? 4 : ((total % 2 == 0) ? 2 : 1);
-    const size_t smem = (size_t) warps * n_ctx * sizeof(float);
-    self_attn_kernel<T16><<<total / warps, warps * 32, smem, st>>>(reinterpret_cast<const T16 *>(qkv), d_rows, d, n_head,
-                                                                    layer_off, n_ctx, reinterpret_cast<T16 *>(out));
-}
-
 void dec_self_attn(DType dt, const void * qkv, const DecRow * d_rows, int R, int d, int n_head, size_t layer_off_elems,
-                   int n_ctx, void * out, cudaStream_t st) {
+                   int n_ctx, bool fused_append, void * out, cudaStream_t st) {
     if (R <= 0) return;
-    if (dt == DType::F16) self_attn_launch<__half>(qkv, d_rows, R, d, n_head, layer_off_elems, n_ctx, out, st);
-    else self_attn_launch<__nv_bfloat16>(qkv, d_rows, R, d, n_head, layer_off_elems, n_ctx, out, st);
+    dim3 grid(R, n_head);
+    const size_t smem = (size_t) n_ctx * sizeof(float);
+    if (dt == DType::F16)
+        cross_attn_kernel<__half, true><<<grid, 128, smem, st>>>(reinterpret_cast<const __half *>(qkv), 3 * d, d_rows, d,
+                                                                 layer_off_elems, 0, 1.0f, 0, fused_append ? 1 : 0,
+                                                                 reinterpret_cast<__half *>(out));
+    else
+        cross_attn_kernel<__nv_bfloat16, true><<<grid, 128, smem, st>>>(reinterpret_cast<const __nv_bfloat16 *>(qkv), 3 * d,
+                                                                        d_rows, d, layer_off_elems, 0, 1.0f, 0,
+                                                                        fused_append ? 1 : 0,
+                                                                        reinterpret_cast<__nv_bfloat16 *>(out));
     WB_CUDA(cudaGetLastError());
 }
 
@@ -418,12 +402,13 @@ void dec_cross_attn(DType dt, const void * q, const DecRow * d_rows, int R, int 
     const float kq_scale = powf(64.0f, -0.25f);
     const size_t smem = (size_t) T * sizeof(float);
     if (dt == DType::F16)
-        cross_attn_kernel<__half><<<grid, 128, smem, st>>>(reinterpret_cast<const __half *>(q), d_rows, d, layer_off_elems,
-                                                           T, kq_scale, n_phantom, reinterpret_cast<__half *>(out));
+        cross_attn_kernel<__half, false><<<grid, 128, smem, st>>>(reinterpret_cast<const __half *>(q), d, d_rows, d,
+                                                                  layer_off_elems, T, kq_scale, n_phantom, 0,
+                                                                  reinterpret_cast<__half *>(out));
     else
-        cross_attn_kernel<__nv_bfloat16><<<grid, 128, smem, st>>>(reinterpret_cast<const __nv_bfloat16 *>(q), d_rows, d,
-                                                                  layer_off_elems, T, kq_scale, n_phantom,
-                                                                  reinterpret_cast<__nv_bfloat16 *>(out));
+        cross_attn_kernel<__nv_bfloat16, false><<<grid, 128, smem, st>>>(reinterpret_cast<const __nv_bfloat16 *>(q), d, d_rows,
+                                                                         d, layer_off_elems, T, kq_scale, n_phantom, 0,
+                                                                         reinterpret_cast<__nv_bfloat16 *>(out));
     WB_CUDA(cudaGetLastError());
 }
 

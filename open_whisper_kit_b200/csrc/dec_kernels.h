@@ -36,13 +36,16 @@ struct SampleParams {
 struct SampleOut {       // the float fields of whisper_token_data (include/whisper.h)
     int id, tid;
     float p, plog, pt, ptsum;
+    int runner_up;       // second-best token after all rules and its logit distance to the winner (diagnostics:
+    float gap;           // lets a parity test tell a genuine divergence from a near-tie flip)
 };
 
 void dec_embed(DType dt, const void * te, const float * pe, const DecRow * d_rows, int R, int d, float * x,
                cudaStream_t st);
 void dec_kv_append(const void * qkv, const DecRow * d_rows, int R, int d, size_t layer_off_elems, cudaStream_t st);
+// fused_append: also store this token's K/V into the cache (only valid when every sequence has exactly one row).
 void dec_self_attn(DType dt, const void * qkv, const DecRow * d_rows, int R, int d, int n_head, size_t layer_off_elems,
-                   int n_ctx, void * out, cudaStream_t st);
+                   int n_ctx, bool fused_append, void * out, cudaStream_t st);
 void dec_cross_attn(DType dt, const void * q, const DecRow * d_rows, int R, int d, int n_head, size_t layer_off_elems,
                     int T, int n_phantom, void * out, cudaStream_t st);
 void dec_sample_greedy(float * logits, int ld, const SampleRow * d_srows, int R, const uint32_t * d_static_mask,

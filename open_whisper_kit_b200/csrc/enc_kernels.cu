@@ -361,12 +361,60 @@ enc_attn_kernel(const T16 * __restrict__ qkv, T16 * __restrict__ out, int T, int
     }
 }
 
+// Few rows (decoder step): one 128-thread CTA per row so a row's loads spread over four warps.
+template <typename T16>
+__global__ void __launch_bounds__(128)
+layernorm_row_kernel(const float * __restrict__ x, int ldx, const float * __restrict__ gamma, const float * __restrict__ beta,
+                     float eps, int d, T16 * __restrict__ y16, int ldy16, float * __restrict__ y32, int ldy32,
+                     const int * __restrict__ row_map) {
+    __shared__ float s_red[8];
+    const int row = blockIdx.x, tid = threadIdx.x;
+    const float * xr = x + (size_t) (row_map ? row_map[row] : row) * ldx;
+    float v[10];                           // d <= 1280
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const int c = tid + 128 * i;
+        v[i] = c < d ? xr[c] : 0.0f;
+        s += v[i];
+    }
+    s = warp_sum(s);
+    if ((tid & 31) == 0) s_red[tid >> 5] = s;
+    __syncthreads();
+    const float mean = (s_red[0] + s_red[1] + s_red[2] + s_red[3]) / (float) d;
+    float q = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const int c = tid + 128 * i;
+        const float dv = c < d ? v[i] - mean : 0.0f;
+        v[i] = dv;
+        q += dv * dv;
+    }
+    q = warp_sum(q);
+    if ((tid & 31) == 0) s_red[4 + (tid >> 5)] = q;
+    __syncthreads();
+    const float rstd = 1.0f / sqrtf((s_red[4] + s_red[5] + s_red[6] + s_red[7]) / (float) d + eps);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const int c = tid + 128 * i;
+        if (c < d) {
+            const float o = v[i] * rstd * gamma[c] + beta[c];
+            if (y16) y16[(size_t) row * ldy16 + c] = Half16<T16>::from_f(o);
+            if (y32) y32[(size_t) row * ldy32 + c] = o;
+        }
+    }
+}
+
 template <typename T16>
 void layernorm_dispatch(const float * x, int ldx, const float * g, const float * b, float eps, int M, int d, void * y16,
                         int ldy16, float * y32, int ldy32, const int * row_map, cudaStream_t st) {
     const int threads = 256;
     const int blocks = ceil_div(M * 32, threads);
     T16 * y = reinterpret_cast<T16 *>(y16);
+    if (M <= 1024 && d <= 1280) {
+        layernorm_row_kernel<T16><<<M, 128, 0, st>>>(x, ldx, g, b, eps, d, y, ldy16, y32, ldy32, row_map);
+        return;
+    }
     if (d <= 512)
         layernorm_kernel<T16, 16><<<blocks, threads, 0, st>>>(x, ldx, g, b, eps, M, d, y, ldy16, y32, ldy32, row_map);
     else if (d <= 1024)

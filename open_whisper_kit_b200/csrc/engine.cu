@@ -374,7 +374,8 @@ bool Engine::decode(const std::vector<DecRow> & rows, const std::vector<int> & l
     int gemm_cls = PC_GEMM_DEC;
     auto gemm = [&](const GemmArgs & g) {
         prof_begin(gemm_cls, ((double) g.N * g.K + (double) g.M * (g.N + g.K)) * 2.0);   // bytes: weights + activations
-        ok = ok && tc_gemm(g, stream);
+        // few rows: stream the weights with every SM (skinny_gemm.cu); many rows (long prompts): tensor-core tiles
+        ok = ok && (g.M <= 128 ? skinny_gemm(g, skinny_ws, stream) : tc_gemm(g, stream));
         prof_end();
         n_kernel_launches += 1;
     };
@@ -386,6 +387,11 @@ bool Engine::decode(const std::vector<DecRow> & rows, const std::vector<int> & l
     };
     const float qk_scale = powf(64.0f, -0.25f);
     const size_t self_layer = (size_t) n_ctx * 2 * d;
+    // single-token step (every sequence contributes exactly one row): the self-attention kernel appends K/V itself
+    // (rows of one sequence are always contiguous in a batch, so comparing neighbours is enough)
+    bool fuse_append = true;
+    for (int i = 1; i < R && fuse_append; ++i)
+        if (rows[i].self_kv == rows[i - 1].self_kv) fuse_append = false;
 
     prof_begin(PC_DEC_MISC, (double) R * d * 10.0);
     dec_embed(dt, model.d_te, model.d_pe, d_rows, R, d, x, stream);
@@ -400,15 +406,18 @@ bool Engine::decode(const std::vector<DecRow> & rows, const std::vector<int> & l
             g.bias = L.bqkv; g.scale = qk_scale; g.scale_cols = 2 * d; g.out16 = qkv; g.ldo16 = 3 * d;
             gemm(g);
         }
-        prof_begin(PC_DEC_MISC, (double) R * 2 * d * 4.0);
-        dec_kv_append(qkv, d_rows, R, d, il * self_layer, stream);
-        prof_end();
+        if (!fuse_append) {
+            prof_begin(PC_DEC_MISC, (double) R * 2 * d * 4.0);
+            dec_kv_append(qkv, d_rows, R, d, il * self_layer, stream);
+            prof_end();
+            n_kernel_launches += 1;
+        }
         double self_bytes = 0.0;
         for (const auto & rw : rows) self_bytes += (double) (rw.pos + 1) * 2 * d * 2.0;
         prof_begin(PC_SELF_ATTN, self_bytes);
-        dec_self_attn(dt, qkv, d_rows, R, d, H, il * self_layer, n_ctx, att, stream);
+        dec_self_attn(dt, qkv, d_rows, R, d, H, il * self_layer, n_ctx, fuse_append, att, stream);
         prof_end();
-        n_kernel_launches += 2;
+        n_kernel_launches += 1;
         {
             GemmArgs g;
             g.dtype = dt; g.M = R; g.N = d; g.K = d; g.a = att; g.lda = d; g.w = L.wo; g.ldw = d;

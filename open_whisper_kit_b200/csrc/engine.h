@@ -9,6 +9,7 @@
 #include "enc_kernels.h"
 #include "mel.h"
 #include "model.h"
+#include "skinny_gemm.h"
 
 namespace wb {
 
@@ -80,6 +81,7 @@ struct Engine {
     DeviceBlock meta;          // small per-call device arrays
     DeviceBlock pcm_stage;     // H2D staging for PCM
     DeviceBlock logits;        // f32 [rows][ld_logits], valid until the next decode
+    SkinnyWorkspace skinny_ws; // split-K scratch of the decoder-step GEMM
     DeviceBlock embd_enc32;    // f32 [windows*1500][d] of the last encode when requested
     int ld_logits = 0;
     void * h_pinned[2] = {nullptr, nullptr};   // pinned host staging: [0] decoder rows (H2D), [1] sampler I/O

@@ -603,6 +603,13 @@ static void stream_finish_window(whisper_context & ctx, Stream & s) {
 int run_streams(whisper_context & ctx, std::vector<StreamSpec> & specs) {
     Engine & e = ctx.eng;
     std::lock_guard<std::mutex> lock(e.mu);
+    const bool dbg = getenv("WHISPER_B200_DEBUG_TIMING") != nullptr;
+    // diagnostics for parity tests: stash the runner-up token / its logit distance in the (otherwise unused, DTW-only)
+    // fields t_dtw / vlen of whisper_token_data
+    const bool dbg_gaps = getenv("WHISPER_B200_DEBUG_GAPS") != nullptr;
+    const int64_t dbg_t0 = time_us();
+    int64_t dbg_mel = 0, dbg_enc = 0, dbg_prompt = 0, dbg_dec_submit = 0, dbg_sel = 0, dbg_host = 0;
+    int dbg_steps = 0;
     cuda_clear_failure();
     const Vocab & vocab = e.model.vocab;
     const auto & hp = e.model.hp;
@@ -635,6 +642,7 @@ int run_streams(whisper_context & ctx, std::vector<StreamSpec> & specs) {
             return -2;
         }
         const int64_t dt = time_us() - t0;
+        dbg_mel += dt;
         for (int i = 0; i < n_streams; ++i) S[i].state->t_mel_us += dt / std::max(1, n_streams);
     }
     for (int i = 0; i < n_streams; ++i) {
@@ -701,6 +709,7 @@ int run_streams(whisper_context & ctx, std::vector<StreamSpec> & specs) {
                 k = k1;
             }
             const int64_t dt = time_us() - t0;
+            dbg_enc += dt;
             for (int si : enc_ids) {
                 Stream & s = S[si];
                 s.state->t_encode_us += dt / (int64_t) enc_ids.size();
@@ -795,6 +804,7 @@ int run_streams(whisper_context & ctx, std::vector<StreamSpec> & specs) {
                 std::vector<float> nosp;
                 ok = ok && e.token_prob(sr, vocab.token_nosp, nosp);
                 const int64_t dt = time_us() - t0;
+                dbg_prompt += dt;
                 for (size_t a = 0; a < act.size(); ++a) {
                     Stream & s = S[act[a]];
                     s.state->t_prompt_us += dt / (int64_t) act.size();
@@ -856,6 +866,10 @@ int run_streams(whisper_context & ctx, std::vector<StreamSpec> & specs) {
                         for (size_t q = 0; q < sr.size(); ++q) {
                             whisper_decoder & d = S[sr_stream[q]].state->decoders[0];
                             d.pending = {so[q].id, so[q].tid, so[q].p, so[q].plog, so[q].pt, so[q].ptsum, -1, -1, -1, 0.0f};
+                            if (dbg_gaps) {
+                                d.pending.t_dtw = so[q].runner_up;
+                                d.pending.vlen = so[q].gap;
+                            }
                             d.has_pending = true;
                         }
                     }
@@ -1006,7 +1020,10 @@ int run_streams(whisper_context & ctx, std::vector<StreamSpec> & specs) {
                     }
                 }
                 const int64_t td0 = time_us();
+                dbg_host += td0 - ts0;
+                dbg_steps++;
                 bool ok = e.decode(rows, lrows, ctx.batch_cross.layer_stride);
+                dbg_dec_submit += time_us() - td0;
                 // selection: device path rows in one kernel, host path rows one by one
                 std::vector<SampleRow> sr;
                 std::vector<int> sr_row;
@@ -1037,10 +1054,15 @@ int run_streams(whisper_context & ctx, std::vector<StreamSpec> & specs) {
                     for (size_t q = 0; q < sr.size() && ok; ++q) {
                         whisper_decoder & d = S[owner[sr_row[q]].first].state->decoders[owner[sr_row[q]].second];
                         d.pending = {so[q].id, so[q].tid, so[q].p, so[q].plog, so[q].pt, so[q].ptsum, -1, -1, -1, 0.0f};
+                        if (dbg_gaps) {
+                            d.pending.t_dtw = so[q].runner_up;
+                            d.pending.vlen = so[q].gap;
+                        }
                         d.has_pending = true;
                     }
                 }
                 const int64_t td1 = time_us();
+                dbg_sel += td1 - td0;
                 for (size_t r = 0; r < owner.size() && ok; ++r) {
                     Stream & s = S[owner[r].first];
                     if (s.device_path) continue;
@@ -1117,6 +1139,11 @@ int run_streams(whisper_context & ctx, std::vector<StreamSpec> & specs) {
                 }
             }
         }
+    }
+    if (dbg) {
+        fprintf(stderr, "run_streams: %d streams total %.1f ms | mel %.1f | encode %.1f | prompt %.1f | %d steps: host %.1f, "
+                "decode submit %.1f, decode+select (incl. wait) %.1f ms\n", n_streams, (time_us() - dbg_t0) / 1e3, dbg_mel / 1e3,
+                dbg_enc / 1e3, dbg_prompt / 1e3, dbg_steps, dbg_host / 1e3, dbg_dec_submit / 1e3, dbg_sel / 1e3);
     }
     int rc = 0;
     for (int i = 0; i < n_streams; ++i) {

@@ -7,6 +7,9 @@
 
 #include "common.cuh"
 #include "mel.h"
+#include "dec_kernels.h"
+#include "enc_kernels.h"
+#include "skinny_gemm.h"
 #include "tc_gemm.h"
 #include "whisper_b200.h"
 
@@ -113,9 +116,9 @@ WB200_API double whisper_b200_kernel_log_mel_bench(int n_streams, int n_samples,
     return cuda_failed() ? -1.0 : total / iters;
 }
 
-WB200_API int whisper_b200_kernel_gemm(int dtype, int M, int N, int K, const uint16_t * a, const uint16_t * w,
-                                       const float * bias, float scale, int scale_cols, int gelu, const float * pos,
-                                       int pos_rows, const float * resid, uint16_t * out16, float * out32) {
+static int gemm_hook(bool skinny, int dtype, int M, int N, int K, const uint16_t * a, const uint16_t * w, const float * bias,
+                     float scale, int scale_cols, int gelu, const float * pos, int pos_rows, const float * resid,
+                     uint16_t * out16, float * out32) {
     cuda_clear_failure();
     const int ldo = round_up(N, 8);
     DevBuf d_a((size_t) M * K * 2), d_w((size_t) N * K * 2), d_bias((size_t) N * 4), d_pos((size_t) pos_rows * N * 4),
@@ -140,7 +143,13 @@ WB200_API int whisper_b200_kernel_gemm(int dtype, int M, int N, int K, const uin
     g.resid = resid ? d_res.as<float>() : nullptr; g.ldr = ldo;
     g.out16 = out16 ? d_o16.p : nullptr; g.ldo16 = ldo;
     g.out32 = out32 ? d_o32.as<float>() : nullptr; g.ldo32 = ldo;
-    if (!tc_gemm(g, 0)) return -2;
+    SkinnyWorkspace sws;
+    if (skinny) {
+        // twice: the second launch checks that the arrival counters were left at zero
+        if (!skinny_gemm(g, sws, 0) || !skinny_gemm(g, sws, 0)) return -2;
+    } else if (!tc_gemm(g, 0)) {
+        return -2;
+    }
     WB_CUDA(cudaDeviceSynchronize());
     if (out16)
         WB_CUDA(cudaMemcpy2D(out16, (size_t) N * 2, d_o16.p, (size_t) ldo * 2, (size_t) N * 2, M, cudaMemcpyDeviceToHost));
@@ -149,7 +158,19 @@ WB200_API int whisper_b200_kernel_gemm(int dtype, int M, int N, int K, const uin
     return cuda_failed() ? -3 : 0;
 }
 
-// Device-resident GEMM timing (random-ish operands); returns average ms.
+WB200_API int whisper_b200_kernel_gemm(int dtype, int M, int N, int K, const uint16_t * a, const uint16_t * w,
+                                       const float * bias, float scale, int scale_cols, int gelu, const float * pos,
+                                       int pos_rows, const float * resid, uint16_t * out16, float * out32) {
+    return gemm_hook(false, dtype, M, N, K, a, w, bias, scale, scale_cols, gelu, pos, pos_rows, resid, out16, out32);
+}
+
+WB200_API int whisper_b200_kernel_skinny_gemm(int dtype, int M, int N, int K, const uint16_t * a, const uint16_t * w,
+                                              const float * bias, float scale, int scale_cols, int gelu,
+                                              const float * resid, uint16_t * out16, float * out32) {
+    return gemm_hook(true, dtype, M, N, K, a, w, bias, scale, scale_cols, gelu, nullptr, 0, resid, out16, out32);
+}
+
+// Device-resident GEMM timing (random-ish operands); returns average ms.  M <= 128 times the weight-streaming kernel.
 WB200_API double whisper_b200_kernel_gemm_bench(int dtype, int M, int N, int K, int gelu, int iters) {
     cuda_clear_failure();
     DevBuf d_a((size_t) M * K * 2), d_w((size_t) N * K * 2), d_bias((size_t) N * 4), d_o16((size_t) M * N * 2);
@@ -191,10 +212,12 @@ WB200_API double whisper_b200_kernel_gemm_bench(int dtype, int M, int N, int K, 
     cudaEvent_t e0, e1;
     WB_CUDA(cudaEventCreate(&e0));
     WB_CUDA(cudaEventCreate(&e1));
+    SkinnyWorkspace sws;
+    auto run = [&]() { return M <= 128 ? skinny_gemm(g, sws, 0) : tc_gemm(g, 0); };
     for (int i = 0; i < 3; ++i)
-        if (!tc_gemm(g, 0)) return -1.0;
+        if (!run()) return -1.0;
     WB_CUDA(cudaEventRecord(e0, 0));
-    for (int i = 0; i < iters; ++i) tc_gemm(g, 0);
+    for (int i = 0; i < iters; ++i) run();
     WB_CUDA(cudaEventRecord(e1, 0));
     WB_CUDA(cudaEventSynchronize(e1));
     float ms = 0;
@@ -202,6 +225,46 @@ WB200_API double whisper_b200_kernel_gemm_bench(int dtype, int M, int N, int K, 
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     return cuda_failed() ? -1.0 : ms / iters;
+}
+
+// Back-to-back launches of one decoder-step kernel at full clocks (events around the whole loop): average microseconds.
+// which: 0 layernorm [R][d], 1 cross-attention (R rows, d, 1500 keys), 2 self-attention at position `aux`, 3 kv append
+WB200_API double whisper_b200_kernel_step_bench(int which, int dtype, int R, int d, int aux, int iters) {
+    cuda_clear_failure();
+    const DType dt = dtype == 1 ? DType::BF16 : DType::F16;
+    const int H = d / 64, n_ctx = 448;
+    DevBuf x((size_t) R * d * 4), g((size_t) d * 4), y((size_t) R * 3 * d * 2), out((size_t) R * d * 2),
+        cross((size_t) R * 1500 * 2 * d * 2), selfkv((size_t) R * n_ctx * 2 * d * 2), rows((size_t) R * sizeof(DecRow));
+    WB_CUDA(cudaMemset(x.p, 0, (size_t) R * d * 4));
+    WB_CUDA(cudaMemset(g.p, 0, (size_t) d * 4));
+    WB_CUDA(cudaMemset(y.p, 0, (size_t) R * 3 * d * 2));
+    WB_CUDA(cudaMemset(cross.p, 0, (size_t) R * 1500 * 2 * d * 2));
+    WB_CUDA(cudaMemset(selfkv.p, 0, (size_t) R * n_ctx * 2 * d * 2));
+    std::vector<DecRow> hr(R);
+    for (int r = 0; r < R; ++r)
+        hr[r] = {0, aux, (char *) selfkv.p + (size_t) r * n_ctx * 2 * d * 2, (const char *) cross.p + (size_t) r * 1500 * 2 * d * 2};
+    WB_CUDA(cudaMemcpy(rows.p, hr.data(), R * sizeof(DecRow), cudaMemcpyHostToDevice));
+    auto run = [&]() {
+        switch (which) {
+            case 0: layernorm(dt, x.as<float>(), d, g.as<float>(), g.as<float>(), 1e-5f, R, d, out.p, d, nullptr, 0, nullptr, 0); break;
+            case 1: dec_cross_attn(dt, out.p, rows.as<DecRow>(), R, d, H, 0, 1500, 0, y.p, 0); break;
+            case 2: dec_self_attn(dt, y.p, rows.as<DecRow>(), R, d, H, 0, n_ctx, true, out.p, 0); break;
+            default: dec_kv_append(y.p, rows.as<DecRow>(), R, d, 0, 0); break;
+        }
+    };
+    cudaEvent_t e0, e1;
+    WB_CUDA(cudaEventCreate(&e0));
+    WB_CUDA(cudaEventCreate(&e1));
+    for (int i = 0; i < 5; ++i) run();
+    WB_CUDA(cudaEventRecord(e0, 0));
+    for (int i = 0; i < iters; ++i) run();
+    WB_CUDA(cudaEventRecord(e1, 0));
+    WB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    WB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return cuda_failed() ? -1.0 : 1e3 * ms / iters;
 }
 
 }  // extern "C"

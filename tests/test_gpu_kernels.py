@@ -116,7 +116,8 @@ def gelu_ref(v, dtype):
     return 0.5 * x * (1.0 + np.tanh(c * x * (1.0 + a * x * x)))
 
 
-def run_gemm(lib, dtype, M, N, K, bias=False, scale_cols=0, scale=1.0, gelu=False, pos_rows=0, resid=False, seed=0):
+def run_gemm(lib, dtype, M, N, K, bias=False, scale_cols=0, scale=1.0, gelu=False, pos_rows=0, resid=False, seed=0,
+             skinny=False):
     rng = np.random.default_rng(seed)
     a = rng.standard_normal((M, K), dtype=np.float32)
     w = (rng.standard_normal((N, K), dtype=np.float32) / np.sqrt(K)).astype(np.float32)
@@ -126,11 +127,17 @@ def run_gemm(lib, dtype, M, N, K, bias=False, scale_cols=0, scale=1.0, gelu=Fals
     r = rng.standard_normal((M, N)).astype(np.float32) if resid else None
     o16 = np.zeros((M, N), dtype=np.uint16)
     o32 = np.zeros((M, N), dtype=np.float32)
-    rc = lib.whisper_b200_kernel_gemm(dtype, M, N, K, ab.ctypes.data_as(U16P), wb.ctypes.data_as(U16P),
-                                      b.ctypes.data_as(FP) if bias else None, scale, scale_cols, int(gelu),
-                                      p.ctypes.data_as(FP) if pos_rows else None, pos_rows,
-                                      r.ctypes.data_as(FP) if resid else None, o16.ctypes.data_as(U16P),
-                                      o32.ctypes.data_as(FP))
+    if skinny:
+        rc = lib.whisper_b200_kernel_skinny_gemm(dtype, M, N, K, ab.ctypes.data_as(U16P), wb.ctypes.data_as(U16P),
+                                                 b.ctypes.data_as(FP) if bias else None, scale, scale_cols, int(gelu),
+                                                 r.ctypes.data_as(FP) if resid else None, o16.ctypes.data_as(U16P),
+                                                 o32.ctypes.data_as(FP))
+    else:
+        rc = lib.whisper_b200_kernel_gemm(dtype, M, N, K, ab.ctypes.data_as(U16P), wb.ctypes.data_as(U16P),
+                                          b.ctypes.data_as(FP) if bias else None, scale, scale_cols, int(gelu),
+                                          p.ctypes.data_as(FP) if pos_rows else None, pos_rows,
+                                          r.ctypes.data_as(FP) if resid else None, o16.ctypes.data_as(U16P),
+                                          o32.ctypes.data_as(FP))
     assert rc == 0
     ref = from_bits(ab, dtype).astype(np.float64) @ from_bits(wb, dtype).astype(np.float64).T
     if bias:
@@ -179,3 +186,22 @@ def test_tc_gemm_epilogues(lib, dtype):
     # column-range scale (cross K scaled by dh^-0.25, V biased), reference src/whisper.cpp:2300-2318
     ref, o32, _ = run_gemm(lib, dtype, 1500, 768, 384, bias=True, scale_cols=384, scale=64.0 ** -0.25, seed=4)
     assert np.abs(o32 - ref).max() <= 2e-3 * max(1.0, np.abs(ref).max())
+
+
+SKINNY_SHAPES = [(64, 1280, 1280), (64, 3840, 1280), (64, 1280, 5120), (64, 5120, 1280), (1, 384, 384), (5, 1152, 384),
+                 (16, 512, 2048), (100, 1536, 512), (128, 51864, 384), (33, 51866, 128), (7, 200, 64)]
+
+
+@pytest.mark.parametrize("dtype", [0, 1])
+@pytest.mark.parametrize("shape", SKINNY_SHAPES)
+def test_skinny_gemm(lib, shape, dtype):
+    """Decoder-step weight-streaming GEMM (split-K with ordered reduction) vs float64 numpy, all epilogues at once."""
+    M, N, K = shape
+    ref, o32, o16 = run_gemm(lib, dtype, M, N, K, bias=True, scale_cols=N // 3, scale=64.0 ** -0.25, resid=True,
+                             seed=M * 7 + N + K, skinny=True)
+    err = np.abs(o32 - ref).max()
+    print(f"skinny {shape} dtype={dtype}: max|d| = {err:.3e}")
+    assert err <= 2e-3 * max(1.0, np.abs(ref).max())
+    ref, o32, o16 = run_gemm(lib, dtype, M, N, K, bias=True, gelu=True, seed=M + N + K, skinny=True)
+    tol = 2.0 ** -9 if dtype == 0 else 2e-3
+    assert np.abs(o32 - ref).max() <= tol * max(1.0, np.abs(ref).max())
