@@ -52,27 +52,38 @@ def read_peaks():
 
 
 class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons DURING the timed region, through NVML in-process (no fork: spawning nvidia-smi
+    from a process that holds a CUDA context and GBs of pinned memory stalls the very run it is observing)."""
+
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag, self.reasons = index, [], False, set()
         self.sm_max = None
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
-                self.samples.append(float(out[0]))
-                self.sm_max = float(out[1])
-                for n, v in zip(names, out[2:]):
-                    if v.strip().lower().startswith("active"):
-                        self.reasons.add(n)
-            except Exception:
-                pass
-            time.sleep(0.2)
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            names = {
+                getattr(pynvml, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+                getattr(pynvml, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+                getattr(pynvml, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+                getattr(pynvml, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+            }
+            while not self.stop_flag:
+                self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                try:
+                    mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for bit, n in names.items():
+                        if mask & bit:
+                            self.reasons.add(n)
+                except Exception:
+                    pass
+                time.sleep(0.1)
+        except Exception as ex:      # the clocks line is evidence, never a reason to fail the bench
+            self.reasons.add(f"nvml_unavailable:{type(ex).__name__}")
 
     def summary(self):
         if not self.samples:
@@ -124,7 +135,7 @@ def run_reference(args, rank, world):
     path = ensure_model(args.arch, 0, lambda: None)
     w = api.Whisper(ref, path, use_gpu=False, flash_attn=True)
     pcm = modelgen.synth_pcm(WINDOW, seed=7, stream=0)
-    n_tok = (2, 6)
+    n_tok = (4, 20)
 
     def one(max_tokens):
         p = greedy_params(ref, n_threads=n_threads)
@@ -254,6 +265,7 @@ def main():
     sampler.start()
     ms_dev = timed(step_device, args.steps)
     sampler.stop_flag = True
+    sampler.join(timeout=2.0)
     launches = lib.whisper_b200_kernel_launches(ctx) - launches0
     n_tokens = count_tokens(lib, ctx)
     step_e2e()

@@ -62,7 +62,7 @@ WB200_API long long whisper_b200_kernel_launches(struct whisper_context * ctx);
  * read() fills out[3*c + {0,1,2}] = {milliseconds, launches, algorithmic work} for class c and returns the number of
  * classes, in this order: mel(bytes), im2col(bytes), gemm_conv(flop), layernorm(bytes), gemm_encoder(flop),
  * encoder_attention(flop), gemm_cross_kv(flop), decoder_misc(bytes), gemm_decoder(bytes), self_attention(bytes),
- * cross_attention(bytes), gemm_logits(bytes), sample(bytes). */
+ * cross_attention(bytes), gemm_logits(bytes), sample(bytes), layernorm_decoder(bytes). */
 WB200_API void whisper_b200_profile_enable(struct whisper_context * ctx, int on);
 WB200_API int whisper_b200_profile_read(struct whisper_context * ctx, double * out, int cap);
 

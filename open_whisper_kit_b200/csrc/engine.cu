@@ -380,7 +380,7 @@ bool Engine::decode(const std::vector<DecRow> & rows, const std::vector<int> & l
         n_kernel_launches += 1;
     };
     auto ln = [&](const float * gw, const float * gb) {
-        prof_begin(PC_LAYERNORM, (double) R * d * 6.0);
+        prof_begin(PC_LAYERNORM_DEC, (double) R * d * 6.0);
         layernorm(dt, x, d, gw, gb, hp.eps, R, d, h16, d, nullptr, 0, nullptr, stream);
         prof_end();
         n_kernel_launches += 1;
@@ -457,7 +457,7 @@ bool Engine::decode(const std::vector<DecRow> & rows, const std::vector<int> & l
     }
     if (RL > 0) {
         // final LayerNorm only on the rows whose logits are wanted, then the tied-embedding logits GEMM
-        prof_begin(PC_LAYERNORM, (double) RL * d * 6.0);
+        prof_begin(PC_LAYERNORM_DEC, (double) RL * d * 6.0);
         layernorm(dt, x, d, model.d_ln_w, model.d_ln_b, hp.eps, RL, d, hl16, d, nullptr, 0, d_lrows, stream);
         prof_end();
         gemm_cls = PC_GEMM_LOGITS;

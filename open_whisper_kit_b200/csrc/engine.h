@@ -66,7 +66,7 @@ struct EncJob {
 // Optional per-kernel-class timing with CUDA events on the engine's stream (bench.py's roofline numbers).
 enum ProfClass {
     PC_MEL = 0, PC_IM2COL, PC_GEMM_CONV, PC_LAYERNORM, PC_GEMM_ENC, PC_ENC_ATTN, PC_GEMM_CROSS, PC_DEC_MISC, PC_GEMM_DEC,
-    PC_SELF_ATTN, PC_CROSS_ATTN, PC_GEMM_LOGITS, PC_SAMPLE, PC_COUNT
+    PC_SELF_ATTN, PC_CROSS_ATTN, PC_GEMM_LOGITS, PC_SAMPLE, PC_LAYERNORM_DEC, PC_COUNT
 };
 
 struct Engine {

@@ -77,5 +77,6 @@ struct whisper_context {
     whisper_state * state = nullptr;
     std::string path_model;
     wb::CrossKV batch_cross;           // shared pool of the batched whisper_full path
+    std::vector<whisper_state *> spare_states;   // worker states of whisper_full_parallel, kept with their device buffers
     wb::DeviceBlock static_mask;       // device bitmask of always-suppressed tokens for the current run
 };

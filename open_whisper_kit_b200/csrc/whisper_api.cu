@@ -157,6 +157,39 @@ std::vector<int> tokenize(const Vocab & vocab, const std::string & text) {
     return tokens;
 }
 
+// Worker states of the batched calls are recycled: their self-attention caches and mel buffers stay allocated, so a
+// steady stream of whisper_full_parallel calls does not pay cudaMalloc / cudaFree per chunk.
+whisper_state * borrow_state(whisper_context * ctx) {
+    whisper_state * st = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(ctx->eng.mu);
+        if (!ctx->spare_states.empty()) {
+            st = ctx->spare_states.back();
+            ctx->spare_states.pop_back();
+        }
+    }
+    if (!st) return whisper_init_state(ctx);
+    st->t_sample_us = st->t_encode_us = st->t_decode_us = st->t_batchd_us = st->t_prompt_us = st->t_mel_us = 0;
+    st->n_sample = st->n_encode = st->n_decode = st->n_batchd = st->n_prompt = st->n_fail_p = st->n_fail_h = 0;
+    st->result_all.clear();
+    st->prompt_past0.clear();
+    st->prompt_past1.clear();
+    st->lang_id = 0;
+    st->no_speech_prob = 0.0f;
+    st->cross_base = nullptr;
+    for (int j = 0; j < WHISPER_MAX_DECODERS; ++j) st->decoders[j].rng = std::mt19937(j);
+    return st;
+}
+void return_state(whisper_context * ctx, whisper_state * st) {
+    std::lock_guard<std::mutex> lock(ctx->eng.mu);
+    if (ctx->spare_states.size() < 256) {
+        ctx->spare_states.push_back(st);
+    } else {
+        cudaSetDevice(ctx->eng.device);
+        delete st;
+    }
+}
+
 const char * kModelNames[] = {"unknown", "tiny", "base", "small", "medium", "large"};
 
 }  // namespace
@@ -241,6 +274,8 @@ void whisper_free(struct whisper_context * ctx) {
         st->ctx = nullptr;
         delete st;
     }
+    for (whisper_state * st : ctx->spare_states) delete st;
+    ctx->spare_states.clear();
     delete ctx;
 }
 void whisper_free_params(struct whisper_full_params * params) { delete params; }
@@ -547,7 +582,7 @@ int whisper_full_parallel(struct whisper_context * ctx, struct whisper_full_para
             specs[0].n_samples = offset_samples + n_per;
         }
         for (int i = 0; i < n_processors - 1; ++i) {
-            states.push_back(whisper_init_state(ctx));
+            states.push_back(borrow_state(ctx));
             const int start = offset_samples + (i + 1) * n_per;
             const int n_cur = (i == n_processors - 2) ? n_samples - start : n_per;
             auto pc = params;
@@ -588,7 +623,7 @@ int whisper_full_parallel(struct whisper_context * ctx, struct whisper_full_para
             st0->n_decode += states[i]->n_decode;
             st0->n_batchd += states[i]->n_batchd;
             st0->n_prompt += states[i]->n_prompt;
-            whisper_free_state(states[i]);
+            return_state(ctx, states[i]);
         }
         st0->t_mel_us /= n_processors;
         st0->t_sample_us /= n_processors;
@@ -744,7 +779,7 @@ WB200_API int whisper_b200_full_device(struct whisper_context * ctx, struct whis
         std::vector<whisper_state *> states;
         std::vector<StreamSpec> specs(n_processors);
         for (int i = 0; i < n_processors; ++i) {
-            whisper_state * st = i == 0 ? ctx->state : whisper_init_state(ctx);
+            whisper_state * st = i == 0 ? ctx->state : borrow_state(ctx);
             if (i > 0) states.push_back(st);
             auto pc = params;
             pc.offset_ms = 0;
@@ -766,7 +801,7 @@ WB200_API int whisper_b200_full_device(struct whisper_context * ctx, struct whis
                 if (!st0->result_all.empty()) r.t0 = std::max(r.t0, st0->result_all.back().t1);
                 st0->result_all.push_back(std::move(r));
             }
-            whisper_free_state(states[i]);
+            return_state(ctx, states[i]);
         }
         return rc;
     } catch (const std::exception & ex) {

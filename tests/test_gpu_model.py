@@ -255,3 +255,31 @@ def test_beam_and_temperature_fallback_host_path_runs(lib, model_dir):
         p.print_progress = False
         rc, segs = w.full(p, modelgen.synth_pcm(160000, stream=3))
         assert rc == 0
+
+
+def test_reference_cli_and_bench_run_on_our_library(lib, model_dir):
+    """BASELINE.json config 1: the reference's UNMODIFIED whisper-cli (examples/cli/cli.cpp), compiled against our headers and
+    linked to our library, transcribes samples/jfk.wav greedily and prints what the same cli linked to the reference build
+    prints; whisper-bench (examples/bench/bench.cpp) runs its encode/decode timing loop on our library."""
+    import subprocess
+    bindir = os.path.join(os.path.dirname(HERE), "oracle", "_ref")
+    cli, ref_cli, bench = (os.path.join(bindir, n) for n in ("whisper-cli-b200", "whisper-cli-ref", "whisper-bench-b200"))
+    if not (os.path.exists(cli) and os.path.exists(bench)):
+        pytest.skip("reference callers were not built (needs /root/reference at build time)")
+    model = model_path(model_dir, "tiny.en")
+    wav = os.path.join(HERE, "golden", "jfk.wav")
+    args = ["-m", model, "-f", wav, "-bs", "1", "-bo", "1", "-nf", "-ps"]
+    ours = subprocess.run([cli] + args, capture_output=True, text=True, timeout=300)
+    assert ours.returncode == 0, ours.stderr[-2000:]
+    lines = [l for l in ours.stdout.splitlines() if l.startswith("[")]
+    assert lines, ours.stdout
+    if os.path.exists(ref_cli):
+        theirs = subprocess.run([ref_cli] + args + ["-ng", "-nfa", "-t", "4"], capture_output=True, text=True, timeout=600)
+        assert theirs.returncode == 0, theirs.stderr[-2000:]
+        ref_lines = [l for l in theirs.stdout.splitlines() if l.startswith("[")]
+        print("cli output:", lines, "| reference:", ref_lines)
+        # our cli ran with the default flash_attn=true; token-identical on this fixture in both modes (golden_tokens.json)
+        assert lines == ref_lines
+    b = subprocess.run([bench, "-m", model, "-t", "1"], capture_output=True, text=True, timeout=300)
+    assert b.returncode == 0, b.stderr[-2000:]
+    assert "encode time" in b.stderr and "decode time" in b.stderr
