@@ -30,6 +30,30 @@ template <typename T> static inline T round_up(T a, T b) { return ceil_div(a, b)
 enum class DType : int { F16 = 0, BF16 = 1 };
 
 #ifdef __CUDACC__
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------
+// The decoder step is ~390 small dependent kernels; back to back they cost ~4 us each just in launch latency.  Kernels
+// launched through launch_pdl() may be scheduled while their predecessor is still running: they call pdl_trigger() first
+// (lets THEIR successor be scheduled early) and pdl_wait() before touching any memory another kernel may write -- the wait
+// returns only when every earlier grid has completed and flushed, so ordering is unchanged; only launch latency, prologue
+// work and loads of never-written data (weights, cross K/V) overlap the predecessor's tail.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    WB_CUDA(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
+}
+
 template <typename T> struct Half16;
 template <> struct Half16<__half> {
     static __device__ __forceinline__ float to_f(__half v) { return __half2float(v); }

@@ -17,6 +17,8 @@ template <typename T16>
 __global__ void embed_kernel(const T16 * __restrict__ te, const float * __restrict__ pe, const DecRow * __restrict__ rows,
                              int d, float * __restrict__ x) {
     const int r = blockIdx.x;
+    pdl_trigger();
+    pdl_wait();
     const DecRow row = rows[r];
     const T16 * t = te + (size_t) row.token * d;
     const float * p = pe + (size_t) row.pos * d;
@@ -51,6 +53,8 @@ cross_attn_kernel(const T16 * __restrict__ q, int ldq, const DecRow * __restrict
     const int r = blockIdx.x, h = blockIdx.y;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int sub = lane & 7, grp = lane >> 3;     // 8 lanes per key row, 4 key rows per warp instruction
+    pdl_trigger();
+    pdl_wait();
     const DecRow row = rows[r];
     const int T = SELF ? row.pos + 1 : T_in;
     const T16 * kbase = (SELF ? reinterpret_cast<const T16 *>(row.self_kv) : reinterpret_cast<const T16 *>(row.cross_kv)) +
@@ -230,6 +234,8 @@ sample_greedy_kernel(float * __restrict__ logits, int ld, const SampleRow * __re
     __shared__ double sh_d[SAMPLE_THREADS / 32];
     __shared__ ArgMax sh_a[SAMPLE_THREADS / 32];
     const int r = blockIdx.x;
+    pdl_trigger();
+    pdl_wait();
     const SampleRow sr = srows[r];
     float * l = logits + (size_t) sr.logits_row * ld;
     const int V = prm.n_vocab, beg = prm.token_beg, eot = prm.token_eot;
@@ -366,9 +372,10 @@ void dec_embed(DType dt, const void * te, const float * pe, const DecRow * d_row
                cudaStream_t st) {
     if (R <= 0) return;
     if (dt == DType::F16)
-        embed_kernel<__half><<<R, 256, 0, st>>>(reinterpret_cast<const __half *>(te), pe, d_rows, d, x);
+        launch_pdl(embed_kernel<__half>, dim3(R), dim3(256), 0, st, reinterpret_cast<const __half *>(te), pe, d_rows, d, x);
     else
-        embed_kernel<__nv_bfloat16><<<R, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16 *>(te), pe, d_rows, d, x);
+        launch_pdl(embed_kernel<__nv_bfloat16>, dim3(R), dim3(256), 0, st, reinterpret_cast<const __nv_bfloat16 *>(te), pe,
+                   d_rows, d, x);
     WB_CUDA(cudaGetLastError());
 }
 
@@ -384,14 +391,12 @@ void dec_self_attn(DType dt, const void * qkv, const DecRow * d_rows, int R, int
     dim3 grid(R, n_head);
     const size_t smem = (size_t) n_ctx * sizeof(float);
     if (dt == DType::F16)
-        cross_attn_kernel<__half, true><<<grid, 128, smem, st>>>(reinterpret_cast<const __half *>(qkv), 3 * d, d_rows, d,
-                                                                 layer_off_elems, 0, 1.0f, 0, fused_append ? 1 : 0,
-                                                                 reinterpret_cast<__half *>(out));
+        launch_pdl(cross_attn_kernel<__half, true>, grid, dim3(128), smem, st, reinterpret_cast<const __half *>(qkv), 3 * d,
+                   d_rows, d, layer_off_elems, 0, 1.0f, 0, fused_append ? 1 : 0, reinterpret_cast<__half *>(out));
     else
-        cross_attn_kernel<__nv_bfloat16, true><<<grid, 128, smem, st>>>(reinterpret_cast<const __nv_bfloat16 *>(qkv), 3 * d,
-                                                                        d_rows, d, layer_off_elems, 0, 1.0f, 0,
-                                                                        fused_append ? 1 : 0,
-                                                                        reinterpret_cast<__nv_bfloat16 *>(out));
+        launch_pdl(cross_attn_kernel<__nv_bfloat16, true>, grid, dim3(128), smem, st,
+                   reinterpret_cast<const __nv_bfloat16 *>(qkv), 3 * d, d_rows, d, layer_off_elems, 0, 1.0f, 0,
+                   fused_append ? 1 : 0, reinterpret_cast<__nv_bfloat16 *>(out));
     WB_CUDA(cudaGetLastError());
 }
 
@@ -402,20 +407,19 @@ void dec_cross_attn(DType dt, const void * q, const DecRow * d_rows, int R, int 
     const float kq_scale = powf(64.0f, -0.25f);
     const size_t smem = (size_t) T * sizeof(float);
     if (dt == DType::F16)
-        cross_attn_kernel<__half, false><<<grid, 128, smem, st>>>(reinterpret_cast<const __half *>(q), d, d_rows, d,
-                                                                  layer_off_elems, T, kq_scale, n_phantom, 0,
-                                                                  reinterpret_cast<__half *>(out));
+        launch_pdl(cross_attn_kernel<__half, false>, grid, dim3(128), smem, st, reinterpret_cast<const __half *>(q), d, d_rows,
+                   d, layer_off_elems, T, kq_scale, n_phantom, 0, reinterpret_cast<__half *>(out));
     else
-        cross_attn_kernel<__nv_bfloat16, false><<<grid, 128, smem, st>>>(reinterpret_cast<const __nv_bfloat16 *>(q), d, d_rows,
-                                                                         d, layer_off_elems, T, kq_scale, n_phantom, 0,
-                                                                         reinterpret_cast<__nv_bfloat16 *>(out));
+        launch_pdl(cross_attn_kernel<__nv_bfloat16, false>, grid, dim3(128), smem, st,
+                   reinterpret_cast<const __nv_bfloat16 *>(q), d, d_rows, d, layer_off_elems, T, kq_scale, n_phantom, 0,
+                   reinterpret_cast<__nv_bfloat16 *>(out));
     WB_CUDA(cudaGetLastError());
 }
 
 void dec_sample_greedy(float * logits, int ld, const SampleRow * d_srows, int R, const uint32_t * d_static_mask,
                        const SampleParams & prm, SampleOut * d_out, cudaStream_t st) {
     if (R <= 0) return;
-    sample_greedy_kernel<<<R, SAMPLE_THREADS, 0, st>>>(logits, ld, d_srows, d_static_mask, prm, d_out);
+    launch_pdl(sample_greedy_kernel, dim3(R), dim3(SAMPLE_THREADS), 0, st, logits, ld, d_srows, d_static_mask, prm, d_out);
     WB_CUDA(cudaGetLastError());
 }
 

@@ -369,6 +369,8 @@ layernorm_row_kernel(const float * __restrict__ x, int ldx, const float * __rest
                      const int * __restrict__ row_map) {
     __shared__ float s_red[8];
     const int row = blockIdx.x, tid = threadIdx.x;
+    pdl_trigger();
+    pdl_wait();
     const float * xr = x + (size_t) (row_map ? row_map[row] : row) * ldx;
     float v[10];                           // d <= 1280
     float s = 0.0f;
@@ -412,7 +414,7 @@ void layernorm_dispatch(const float * x, int ldx, const float * g, const float *
     const int blocks = ceil_div(M * 32, threads);
     T16 * y = reinterpret_cast<T16 *>(y16);
     if (M <= 1024 && d <= 1280) {
-        layernorm_row_kernel<T16><<<M, 128, 0, st>>>(x, ldx, g, b, eps, d, y, ldy16, y32, ldy32, row_map);
+        launch_pdl(layernorm_row_kernel<T16>, dim3(M), dim3(128), 0, st, x, ldx, g, b, eps, d, y, ldy16, y32, ldy32, row_map);
         return;
     }
     if (d <= 512)

@@ -85,9 +85,8 @@ skinny_gemm_kernel(const SkinnyParams p) {
     const T16 * X = reinterpret_cast<const T16 *>(p.x);
     const T16 * W = reinterpret_cast<const T16 *>(p.w);
 
-    auto load_stage = [&](int stage, int kb) {
+    auto load_x = [&](int stage, int kb) {
         uint8_t * sx = smem + stage * S_STAGE_BYTES;
-        uint8_t * swt = sx + SB * SB * 2;
         const int k0 = kb * SB;
 #pragma unroll
         for (int i = 0; i < (SB * 8) / S_THREADS; ++i) {
@@ -95,6 +94,15 @@ skinny_gemm_kernel(const SkinnyParams p) {
             const int r = idx >> 3, c = idx & 7;
             const bool okx = (m0 + r) < p.M;
             cp16(sx + sw(r, c), X + (size_t) (okx ? m0 + r : 0) * p.ldx + k0 + c * 8, okx);
+        }
+    };
+    auto load_w = [&](int stage, int kb) {
+        uint8_t * swt = smem + stage * S_STAGE_BYTES + SB * SB * 2;
+        const int k0 = kb * SB;
+#pragma unroll
+        for (int i = 0; i < (SB * 8) / S_THREADS; ++i) {
+            const int idx = tid + i * S_THREADS;
+            const int r = idx >> 3, c = idx & 7;
             const bool okw = (n0 + r) < p.N;
             cp16(swt + sw(r, c), W + (size_t) (okw ? n0 + r : 0) * p.ldw + k0 + c * 8, okw);
         }
@@ -106,9 +114,18 @@ skinny_gemm_kernel(const SkinnyParams p) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.0f;
 
+    // Weights are never written by a kernel: their first S-1 tiles are requested BEFORE waiting for the predecessor
+    // grid (PDL), the activation tiles after it.  cp.async groups retire in order, so waiting for an X group implies the
+    // (older) W group.
+    pdl_trigger();
+#pragma unroll
+    for (int s = 0; s < S_STAGES - 1; ++s)
+        if (s < nkb) load_w(s, kb0 + s);
+    cp_commit();
+    pdl_wait();
 #pragma unroll
     for (int s = 0; s < S_STAGES - 1; ++s) {
-        if (s < nkb) load_stage(s, kb0 + s);
+        if (s < nkb) load_x(s, kb0 + s);
         cp_commit();
     }
     for (int it = 0; it < nkb; ++it) {
@@ -116,7 +133,10 @@ skinny_gemm_kernel(const SkinnyParams p) {
         __syncthreads();
         {   // prefetch the stage that was consumed in the previous iteration
             const int nx = it + S_STAGES - 1;
-            if (nx < nkb) load_stage(nx % S_STAGES, kb0 + nx);
+            if (nx < nkb) {
+                load_x(nx % S_STAGES, kb0 + nx);
+                load_w(nx % S_STAGES, kb0 + nx);
+            }
             cp_commit();
         }
         const uint32_t sx = (uint32_t) __cvta_generic_to_shared(smem + (it % S_STAGES) * S_STAGE_BYTES);
@@ -238,13 +258,15 @@ bool skinny_gemm(const GemmArgs & g, SkinnyWorkspace & wsp, cudaStream_t stream)
     cfg.blockDim = dim3(S_THREADS);
     cfg.dynamicSmemBytes = S_SMEM;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 1;
     attr[0].val.clusterDim.y = KS;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     if (g.dtype == DType::F16) {
         static bool set = false;
         if (!set) {
