@@ -44,7 +44,7 @@ __global__ void kv_append_kernel(const uint4 * __restrict__ qkv, const DecRow * 
 // this token's K/V head slice into the cache (single-token steps only: every sequence owns exactly one row, so no
 // other CTA needs the slice).
 template <typename T16, bool SELF>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 9)
 cross_attn_kernel(const T16 * __restrict__ q, int ldq, const DecRow * __restrict__ rows, int d, size_t layer_off, int T_in,
                   float kq_scale, int n_phantom, int fused_append, T16 * __restrict__ out) {
     extern __shared__ float s_sc[];          // [T]

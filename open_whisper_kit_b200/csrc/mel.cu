@@ -19,6 +19,8 @@
 
 #include <math.h>
 #include <string.h>
+
+#include <algorithm>
 #include <vector>
 
 namespace wb {
@@ -89,14 +91,15 @@ template <int I, int N, typename F> __device__ __forceinline__ void static_for(F
 // position (register index) that holds G[k2] after the in-register 25-point FFT:  k2 = ka + 5*kb  ->  5*ka + kb
 __host__ __device__ constexpr int pos25(int k2) { return 5 * (k2 % 5) + (k2 / 5); }
 
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 3)
 mel_kernel(const MelStream * __restrict__ streams, const float * __restrict__ tables,
-           const float * __restrict__ filt_w, const int4 * __restrict__ filt_meta, int n_mel) {
+           const float * __restrict__ filt, int filt_floats, int n_groups, int n_mel) {
     extern __shared__ __align__(16) float smem[];
     float * s_pcm = smem;                                   // kPcmSmem
     float * s_pow = s_pcm + kPcmSmem;                       // 32 * kPowStride
     float * s_tab = s_pow + kFramesPerCta * kPowStride;     // kTabFloats (hann | tw200)
-    float * s_out = s_tab + kTabFloats;                     // n_mel * kOutStride
+    float * s_flt = s_tab + kTabFloats;                     // packed filterbank (see mel_plan_init)
+    float * s_out = s_flt + filt_floats;                    // n_mel * kOutStride
     __shared__ float s_wmax[kThreads / 32];
 
     const MelStream st = streams[blockIdx.y];
@@ -108,6 +111,7 @@ mel_kernel(const MelStream * __restrict__ streams, const float * __restrict__ ta
     const int n_pad = st.n_samples + kFrame / 2;            // samples beyond this are zero
 
     for (int i = tid; i < kTabFloats; i += kThreads) s_tab[i] = __ldg(&tables[i]);
+    for (int i = tid; i < filt_floats; i += kThreads) s_flt[i] = __ldg(&filt[i]);
     const float * s_hann = s_tab;
     const float2 * s_tw200 = reinterpret_cast<const float2 *>(s_tab + kFrame);
 
@@ -184,10 +188,12 @@ mel_kernel(const MelStream * __restrict__ streams, const float * __restrict__ ta
         });
     }
     {
-        // stage A (partner t^4): lower lanes a+b, upper lanes (b-a)*W8^(t&3)
+        // stage A (partner t^4): lower lanes a+b, upper lanes (b-a)*W8^(t&3).  "a+b or b-a" is one FMA with a per-lane
+        // sign (b + sgn*a) instead of computing both and selecting.
         const bool up4 = (t & 4) != 0;
         const bool up2 = (t & 2) != 0;
         const bool up1 = (t & 1) != 0;
+        const float sg4 = up4 ? -1.0f : 1.0f, sg2 = up2 ? -1.0f : 1.0f, sg1 = up1 ? -1.0f : 1.0f;
         float2 wA = make_float2(1.0f, 0.0f);
         if (up4) {
             constexpr float r = 0.70710678118654752440f;
@@ -200,13 +206,13 @@ mel_kernel(const MelStream * __restrict__ streams, const float * __restrict__ ta
         for (int i = 0; i < 25; ++i) {
             float2 a = v[i];
             float2 b = make_float2(__shfl_xor_sync(0xffffffffu, a.x, 4), __shfl_xor_sync(0xffffffffu, a.y, 4));
-            float2 d = up4 ? csub(b, a) : cadd(a, b);
+            float2 d = make_float2(fmaf(sg4, a.x, b.x), fmaf(sg4, a.y, b.y));
             a = cmul(d, wA);
             b = make_float2(__shfl_xor_sync(0xffffffffu, a.x, 2), __shfl_xor_sync(0xffffffffu, a.y, 2));
-            d = up2 ? csub(b, a) : cadd(a, b);
+            d = make_float2(fmaf(sg2, a.x, b.x), fmaf(sg2, a.y, b.y));
             a = rotB ? make_float2(d.y, -d.x) : d;            // * (-i)
             b = make_float2(__shfl_xor_sync(0xffffffffu, a.x, 1), __shfl_xor_sync(0xffffffffu, a.y, 1));
-            v[i] = up1 ? csub(b, a) : cadd(a, b);
+            v[i] = make_float2(fmaf(sg1, a.x, b.x), fmaf(sg1, a.y, b.y));
         }
     }
     // lane t now holds Z[k2 + 25*k1] at position pos25(k2), k1 = bitrev3(t)
@@ -248,17 +254,29 @@ mel_kernel(const MelStream * __restrict__ streams, const float * __restrict__ ta
     __syncwarp();
 
     // ---- stage 6: sparse mel filterbank + log10; lane t takes bins t, t+8, ... ----
+    // Packed table (shared memory): per group g of 8 bins {len_g, off_g}, per bin k_start, then the taps padded to the
+    // group's longest filter and interleaved [tap][lane], so the trip count is warp-uniform and the weight reads are
+    // conflict-free.  f32 FMA accumulation (the reference adds f32 4-term partials into a double, src/whisper.cpp:3140-3156;
+    // the difference is ~1e-7 relative, i.e. ~1e-8 after log10 and /4).
     float vmax = -INFINITY;
     {
         const float * prow = s_pow + fl * kPowStride;
-        for (int j = t; j < n_mel; j += 8) {
-            const int4 meta = __ldg(&filt_meta[j]);                        // {k_start, k_len, w_offset, -}
-            const float * w = filt_w + meta.z;
-            double acc = 0.0;
-            for (int i = 0; i < meta.y; ++i) acc += (double) (prow[meta.x + i] * __ldg(&w[i]));
-            const float lg = log10f(fmaxf((float) acc, 1e-10f));
-            if (live) vmax = fmaxf(vmax, lg);
-            s_out[j * kOutStride + fl] = lg;
+        const int * s_meta = reinterpret_cast<const int *>(s_flt);               // [2*n_groups] | [8*n_groups] k_start
+        const int * s_k0 = s_meta + 2 * n_groups;
+        const float * s_w = s_flt + 2 * n_groups + 8 * n_groups;
+        for (int g = 0; g < n_groups; ++g) {
+            const int len = s_meta[2 * g], off = s_meta[2 * g + 1];
+            const int j = g * 8 + t;
+            const float * pk = prow + s_k0[j];
+            const float * wk = s_w + off + t;
+            float acc = 0.0f;
+            for (int i = 0; i < len; ++i) acc = fmaf(pk[i], wk[8 * i], acc);
+            // log10(x) = log2(x) * log10(2); MUFU.LG2 has <= 2^-22 absolute error
+            const float lg = __log2f(fmaxf(acc, 1e-10f)) * 0.30102999566398119521f;
+            if (j < n_mel) {
+                if (live) vmax = fmaxf(vmax, lg);
+                s_out[j * kOutStride + fl] = lg;
+            }
         }
     }
     vmax = warp_max(vmax);
@@ -303,7 +321,6 @@ __global__ void mel_finalize_kernel(const float * __restrict__ raw, int raw_stri
 MelPlan::~MelPlan() {
     if (d_tables) cudaFree(d_tables);
     if (d_w) cudaFree(d_w);
-    if (d_meta) cudaFree(d_meta);
 }
 
 static void upload_tables(MelPlan & plan) {
@@ -337,8 +354,8 @@ static void upload_tables(MelPlan & plan) {
 bool mel_plan_init(MelPlan & plan, const float * filters, int n_mel, int n_fft_bins) {
     if (n_fft_bins != kBins || n_mel <= 0 || n_mel > 256) return false;
     upload_tables(plan);
-    std::vector<float> w;
-    std::vector<int4> meta(n_mel);
+    const int n_groups = (n_mel + 7) / 8;
+    std::vector<int> k0(8 * n_groups, 0), len(8 * n_groups, 0);
     for (int j = 0; j < n_mel; ++j) {
         const float * row = filters + (size_t) j * kBins;
         int lo = -1, hi = -1;
@@ -347,26 +364,39 @@ bool mel_plan_init(MelPlan & plan, const float * filters, int n_mel, int n_fft_b
                 if (lo < 0) lo = k;
                 hi = k;
             }
-        int4 m;
-        m.z = (int) w.size();
-        m.w = 0;
-        if (lo < 0) {
-            m.x = 0;
-            m.y = 0;
-        } else {
-            m.x = lo;
-            m.y = hi - lo + 1;
-            w.insert(w.end(), row + lo, row + hi + 1);
+        if (lo >= 0) {
+            k0[j] = lo;
+            len[j] = hi - lo + 1;
         }
-        meta[j] = m;
     }
-    if (w.empty()) w.push_back(0.0f);
+    std::vector<int> meta(2 * n_groups);
+    std::vector<float> w;
+    for (int g = 0; g < n_groups; ++g) {
+        int glen = 0;
+        for (int t = 0; t < 8; ++t) glen = std::max(glen, len[g * 8 + t]);
+        meta[2 * g] = glen;
+        meta[2 * g + 1] = (int) w.size();
+        // every lane reads glen taps starting at its k_start: shift the start down so the window stays inside [0, 201)
+        for (int t = 0; t < 8; ++t) k0[g * 8 + t] = std::min(k0[g * 8 + t], kBins - glen);
+        for (int i = 0; i < glen; ++i)
+            for (int t = 0; t < 8; ++t) {
+                const int j = g * 8 + t;
+                const int k = k0[j] + i;
+                w.push_back(j < n_mel ? filters[(size_t) j * kBins + k] : 0.0f);
+            }
+    }
+    std::vector<float> packed(2 * n_groups + 8 * n_groups + w.size());
+    memcpy(packed.data(), meta.data(), meta.size() * 4);
+    memcpy(packed.data() + 2 * n_groups, k0.data(), k0.size() * 4);
+    memcpy(packed.data() + 10 * n_groups, w.data(), w.size() * 4);
+    if (packed.size() * 4 > 64 * 1024) return false;      // a dense (non-triangular) filterbank is not supported
     plan.n_mel = n_mel;
-    WB_CUDA(cudaMalloc(&plan.d_w, w.size() * sizeof(float)));
-    WB_CUDA(cudaMalloc(&plan.d_meta, meta.size() * sizeof(int4)));
-    WB_CUDA(cudaMemcpy(plan.d_w, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
-    WB_CUDA(cudaMemcpy(plan.d_meta, meta.data(), meta.size() * sizeof(int4), cudaMemcpyHostToDevice));
-    plan.smem_bytes = (size_t) (kPcmSmem + kFramesPerCta * kPowStride + kTabFloats + n_mel * kOutStride) * sizeof(float);
+    plan.n_groups = n_groups;
+    plan.filt_floats = (int) ((packed.size() + 3) & ~size_t(3));
+    packed.resize(plan.filt_floats, 0.0f);
+    WB_CUDA(cudaMalloc(&plan.d_w, packed.size() * sizeof(float)));
+    WB_CUDA(cudaMemcpy(plan.d_w, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice));
+    plan.smem_bytes = (size_t) (kPcmSmem + kFramesPerCta * kPowStride + kTabFloats + plan.filt_floats + n_mel * kOutStride) * sizeof(float);
     WB_CUDA(cudaFuncSetAttribute(mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) plan.smem_bytes));
     return !cuda_failed();
 }
@@ -387,7 +417,7 @@ void mel_launch(const MelPlan & plan, const MelStream * d_streams, int n_streams
     if (n_streams <= 0 || max_frames_fft <= 0) return;
     dim3 grid(ceil_div(max_frames_fft, kFramesPerCta), n_streams);
     mel_kernel<<<grid, kThreads, plan.smem_bytes, stream>>>(d_streams, (const float *) plan.d_tables, (const float *) plan.d_w,
-                                                             (const int4 *) plan.d_meta, plan.n_mel);
+                                                             plan.filt_floats, plan.n_groups, plan.n_mel);
     WB_CUDA(cudaGetLastError());
 }
 

@@ -25,8 +25,9 @@ struct MelGeometry {
 struct MelPlan {
     int     n_mel = 0;
     void *  d_tables = nullptr;
-    void *  d_w = nullptr;      // packed non-zero filter weights
-    void *  d_meta = nullptr;   // int4 {k_start, k_len, w_offset, 0} per mel bin
+    void *  d_w = nullptr;      // packed sparse filterbank: group meta | per-bin k_start | taps [group][tap][lane]
+    int     n_groups = 0;       // groups of 8 mel bins
+    int     filt_floats = 0;
     size_t  smem_bytes = 0;
     MelPlan() = default;
     MelPlan(const MelPlan &) = delete;
