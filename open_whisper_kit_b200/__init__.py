@@ -40,7 +40,7 @@ EXT_PROTOTYPES = {
 PROFILE_CLASSES = [("mel", "B"), ("im2col", "B"), ("gemm_conv", "flop"), ("layernorm", "B"), ("gemm_encoder", "flop"),
                    ("encoder_attention", "flop"), ("gemm_cross_kv", "flop"), ("decoder_misc", "B"), ("gemm_decoder", "B"),
                    ("self_attention", "B"), ("cross_attention", "B"), ("gemm_logits", "B"), ("sample", "B"),
-                   ("layernorm_decoder", "B")]
+                   ("layernorm_decoder", "B"), ("decoder_chain", "B")]
 
 _lib = None
 

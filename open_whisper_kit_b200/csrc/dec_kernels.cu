@@ -9,6 +9,8 @@
 //   sample       whisper_process_logits + whisper_sample_token(best) on the host      6177-6445, 6460-6517
 #include "dec_kernels.h"
 
+#include "dec_chain.h"
+
 namespace wb {
 
 namespace {
@@ -46,14 +48,16 @@ __global__ void kv_append_kernel(const uint4 * __restrict__ qkv, const DecRow * 
 template <typename T16, bool SELF>
 __global__ void __launch_bounds__(128, 9)
 cross_attn_kernel(const T16 * __restrict__ q, int ldq, const DecRow * __restrict__ rows, int d, size_t layer_off, int T_in,
-                  float kq_scale, int n_phantom, int fused_append, T16 * __restrict__ out) {
+                  float kq_scale, int n_phantom, int fused_append, T16 * __restrict__ out, const SplitIn qs) {
     extern __shared__ float s_sc[];          // [T]
     __shared__ float s_red[8];
     __shared__ float s_o[4][64];
     const int r = blockIdx.x, h = blockIdx.y;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int sub = lane & 7, grp = lane >> 3;     // 8 lanes per key row, 4 key rows per warp instruction
-    pdl_trigger();
+    // The successor is the next chain / GEMM launch, whose CTAs hold ~100 KB of shared memory while they wait: letting
+    // them in at once would squeeze this kernel's own occupancy, so the cross pass triggers after its K sweep.
+    if (SELF) pdl_trigger();
     pdl_wait();
     const DecRow row = rows[r];
     const int T = SELF ? row.pos + 1 : T_in;
@@ -72,7 +76,40 @@ cross_attn_kernel(const T16 * __restrict__ q, int ldq, const DecRow * __restrict
     }
 
     float qv[8];
-    {
+    if (!SELF && qs.part) {
+        // query straight from the partial tiles of the chain kernel's stream-K GEMM (dec_chain.h).  The 64 values of this
+        // head are one 64-wide tile: thread (quad, slot) adds the contributors slot, slot+8, ... of one float4, the eight
+        // slot sums are combined in slot order (fixed, reproducible), bias added, rounded to 16 bits like the unfused path.
+        float4 * s_q = reinterpret_cast<float4 *>(s_sc);              // [8 slots][16 quads], free until the K sweep
+        {
+            const int quad = tid & 15, slot = tid >> 4;
+            const int ot = (r >> 6) * qs.g.tiles + h;
+            const int first = sg_cta_of(qs.g, ot * qs.g.kpt), last = sg_cta_of(qs.g, ot * qs.g.kpt + qs.g.kpt - 1);
+            const float * src = qs.part + ((size_t) ot * qs.g.maxc) * 4096 + (r & 63) * 64 + quad * 4;
+            float4 a = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            for (int j = slot; j <= last - first; j += 8) {
+                const float4 v = __ldcg(reinterpret_cast<const float4 *>(src + (size_t) j * 4096));
+                a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+            }
+            s_q[slot * 16 + quad] = a;
+        }
+        __syncthreads();
+        {
+            float4 a = s_q[sub * 2], b = s_q[sub * 2 + 1];
+#pragma unroll
+            for (int sl = 1; sl < 8; ++sl) {
+                const float4 u = s_q[sl * 16 + sub * 2], v = s_q[sl * 16 + sub * 2 + 1];
+                a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
+                b.x += v.x; b.y += v.y; b.z += v.z; b.w += v.w;
+            }
+            const float av[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            const int c = h * 64 + sub * 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                qv[j] = Half16<T16>::to_f(Half16<T16>::from_f(av[j] + (qs.bias ? __ldg(qs.bias + c + j) : 0.0f)));
+        }
+        __syncthreads();            // s_sc is about to receive scores
+    } else {
         const uint4 u = *reinterpret_cast<const uint4 *>(q + (size_t) r * ldq + h * 64 + sub * 8);
         const T16 * e = reinterpret_cast<const T16 *>(&u);
 #pragma unroll
@@ -109,6 +146,7 @@ cross_attn_kernel(const T16 * __restrict__ q, int ldq, const DecRow * __restrict
             }
         }
     }
+    if (!SELF) pdl_trigger();
     mx = warp_max(mx);
     if (lane == 0) s_red[warp] = mx;
     __syncthreads();
@@ -392,27 +430,28 @@ void dec_self_attn(DType dt, const void * qkv, const DecRow * d_rows, int R, int
     const size_t smem = (size_t) n_ctx * sizeof(float);
     if (dt == DType::F16)
         launch_pdl(cross_attn_kernel<__half, true>, grid, dim3(128), smem, st, reinterpret_cast<const __half *>(qkv), 3 * d,
-                   d_rows, d, layer_off_elems, 0, 1.0f, 0, fused_append ? 1 : 0, reinterpret_cast<__half *>(out));
+                   d_rows, d, layer_off_elems, 0, 1.0f, 0, fused_append ? 1 : 0, reinterpret_cast<__half *>(out), SplitIn{});
     else
         launch_pdl(cross_attn_kernel<__nv_bfloat16, true>, grid, dim3(128), smem, st,
                    reinterpret_cast<const __nv_bfloat16 *>(qkv), 3 * d, d_rows, d, layer_off_elems, 0, 1.0f, 0,
-                   fused_append ? 1 : 0, reinterpret_cast<__nv_bfloat16 *>(out));
+                   fused_append ? 1 : 0, reinterpret_cast<__nv_bfloat16 *>(out), SplitIn{});
     WB_CUDA(cudaGetLastError());
 }
 
 void dec_cross_attn(DType dt, const void * q, const DecRow * d_rows, int R, int d, int n_head, size_t layer_off_elems,
-                    int T, int n_phantom, void * out, cudaStream_t st) {
+                    int T, int n_phantom, void * out, cudaStream_t st, const SplitIn * q_split) {
+    const SplitIn qs = q_split ? *q_split : SplitIn{};
     if (R <= 0) return;
     dim3 grid(R, n_head);
     const float kq_scale = powf(64.0f, -0.25f);
     const size_t smem = (size_t) T * sizeof(float);
     if (dt == DType::F16)
         launch_pdl(cross_attn_kernel<__half, false>, grid, dim3(128), smem, st, reinterpret_cast<const __half *>(q), d, d_rows,
-                   d, layer_off_elems, T, kq_scale, n_phantom, 0, reinterpret_cast<__half *>(out));
+                   d, layer_off_elems, T, kq_scale, n_phantom, 0, reinterpret_cast<__half *>(out), qs);
     else
         launch_pdl(cross_attn_kernel<__nv_bfloat16, false>, grid, dim3(128), smem, st,
                    reinterpret_cast<const __nv_bfloat16 *>(q), d, d_rows, d, layer_off_elems, T, kq_scale, n_phantom, 0,
-                   reinterpret_cast<__nv_bfloat16 *>(out));
+                   reinterpret_cast<__nv_bfloat16 *>(out), qs);
     WB_CUDA(cudaGetLastError());
 }
 

@@ -46,8 +46,9 @@ void dec_kv_append(const void * qkv, const DecRow * d_rows, int R, int d, size_t
 // fused_append: also store this token's K/V into the cache (only valid when every sequence has exactly one row).
 void dec_self_attn(DType dt, const void * qkv, const DecRow * d_rows, int R, int d, int n_head, size_t layer_off_elems,
                    int n_ctx, bool fused_append, void * out, cudaStream_t st);
+struct SplitIn;   // dec_chain.h: the query as partial tiles of the chain kernel's cross-q GEMM (q is ignored then)
 void dec_cross_attn(DType dt, const void * q, const DecRow * d_rows, int R, int d, int n_head, size_t layer_off_elems,
-                    int T, int n_phantom, void * out, cudaStream_t st);
+                    int T, int n_phantom, void * out, cudaStream_t st, const SplitIn * q_split = nullptr);
 void dec_sample_greedy(float * logits, int ld, const SampleRow * d_srows, int R, const uint32_t * d_static_mask,
                        const SampleParams & prm, SampleOut * d_out, cudaStream_t st);
 void dec_token_prob(const float * logits, int ld, const SampleRow * d_srows, int R, int n_vocab, int token, float * d_out,

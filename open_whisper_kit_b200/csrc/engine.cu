@@ -5,7 +5,10 @@
 // Every GEMM is tc_gemm (tcgen05) with its bias / scale / GELU / residual fused; nothing is computed on the host.
 #include "engine.h"
 
+#include <stdlib.h>
 #include <string.h>
+
+#include <algorithm>
 
 #include "tc_gemm.h"
 
@@ -392,6 +395,7 @@ bool Engine::decode(const std::vector<DecRow> & rows, const std::vector<int> & l
     bool fuse_append = true;
     for (int i = 1; i < R && fuse_append; ++i)
         if (rows[i].self_kv == rows[i - 1].self_kv) fuse_append = false;
+    if (fuse_append && chain_usable(R)) return decode_chain(rows, logit_rows, cross_layer_stride);
 
     prof_begin(PC_DEC_MISC, (double) R * d * 10.0);
     dec_embed(dt, model.d_te, model.d_pe, d_rows, R, d, x, stream);
@@ -468,6 +472,186 @@ bool Engine::decode(const std::vector<DecRow> & rows, const std::vector<int> & l
         n_kernel_launches += 1;
     }
     if (!ok) wlog(GGML_LOG_LEVEL_ERROR, "%s: GEMM launch rejected its arguments\n", __func__);
+    return ok && !cuda_failed();
+}
+
+// ---- single-token decoder step through the persistent chain kernel ---------------------------------------------------
+bool Engine::chain_usable(int R) {
+    if (chain_mode < 0) {
+        const char * e = getenv("WHISPER_B200_CHAIN");
+        const auto & hp = model.hp;
+        const bool geom_ok = hp.n_text_state % 128 == 0 && hp.n_text_state <= 1536 && hp.n_text_ctx <= 2048 &&
+                             hp.n_text_state == hp.n_text_head * 64;
+        chain_mode = (e && atoi(e) == 1) && geom_ok ? 1 : 0;      // opt-in until it beats the unfused sequence
+        if (const char * u = getenv("WHISPER_B200_CHAIN_UNITS")) chain_min_units = std::max(1, atoi(u));
+        if (chain_mode == 1 && chain_init(chain, model.dtype) <= 0) chain_mode = 0;
+    }
+    return chain_mode == 1 && R >= 1 && R <= 128;
+}
+
+bool Engine::decode_chain(const std::vector<DecRow> & rows, const std::vector<int> & logit_rows, size_t cross_layer_stride) {
+    const int R = (int) rows.size(), RL = (int) logit_rows.size();
+    const auto & hp = model.hp;
+    const int d = hp.n_text_state, H = hp.n_text_head, n_ctx = hp.n_text_ctx, V = hp.n_vocab, L = hp.n_text_layer;
+    const DType dt = model.dtype;
+    const int G = chain.grid;
+
+    // stream-K geometries (one per GEMM shape) and the partial-tile scratch they share
+    // the wide GEMMs (QKV, MLP up) own whole 64x32 tiles and finish in place; the d-wide ones are stream-K
+    const SplitGeom g_qkv = chain_geom_direct(R, 3 * d, d), g_m1 = chain_geom_direct(R, 4 * d, d),
+                    g_dd = chain_geom(G, R, d, d, chain_min_units), g_m2 = chain_geom(G, R, d, 4 * d, chain_min_units);
+    size_t part_floats = 0;
+    for (const SplitGeom * g : {&g_dd, &g_m2}) part_floats = std::max(part_floats, chain_part_floats(*g, R));
+    if (!chain_part.reserve(part_floats * 4)) return false;
+    float * part = (float *) chain_part.p;
+
+    bool identity_logits = RL == R;
+    for (int i = 0; i < RL && identity_logits; ++i) identity_logits = logit_rows[i] == i;
+
+    size_t need = 0;
+    auto sz = [&](size_t b) { need += round_up<size_t>(b, 256); };
+    sz((size_t) R * d * 4); sz((size_t) R * d * 2); sz((size_t) R * 3 * d * 2); sz((size_t) R * d * 2); sz((size_t) R * 4 * d * 2);
+    sz((size_t) std::max(1, RL) * d * 2); sz(R * sizeof(DecRow)); sz(std::max(1, RL) * sizeof(int));
+    if (!ws.begin(need)) return false;
+    float * x = (float *) ws.take((size_t) R * d * 4);
+    void * h16 = ws.take((size_t) R * d * 2);
+    void * qkv = ws.take((size_t) R * 3 * d * 2);
+    void * att = ws.take((size_t) R * d * 2);
+    void * mlp = ws.take((size_t) R * 4 * d * 2);
+    void * hl16 = ws.take((size_t) std::max(1, RL) * d * 2);
+    DecRow * d_rows = (DecRow *) ws.take(R * sizeof(DecRow));
+    int * d_lrows = (int *) ws.take(std::max(1, RL) * sizeof(int));
+    if (!logits.reserve((size_t) std::max(1, RL) * ld_logits * 4)) return false;
+
+    char * hp_buf = (char *) pinned(0, R * sizeof(DecRow) + RL * sizeof(int));
+    memcpy(hp_buf, rows.data(), R * sizeof(DecRow));
+    if (RL) memcpy(hp_buf + R * sizeof(DecRow), logit_rows.data(), RL * sizeof(int));
+    WB_CUDA(cudaMemcpyAsync(d_rows, hp_buf, R * sizeof(DecRow), cudaMemcpyHostToDevice, stream));
+    if (RL) WB_CUDA(cudaMemcpyAsync(d_lrows, hp_buf + R * sizeof(DecRow), RL * sizeof(int), cudaMemcpyHostToDevice, stream));
+
+    const float qk_scale = powf(64.0f, -0.25f);
+    const size_t self_layer = (size_t) n_ctx * 2 * d;
+    double self_bytes = 0.0;
+    for (const auto & rw : rows) self_bytes += (double) (rw.pos + 1) * 2 * d * 2.0;
+
+    ChainParams cp;
+    auto reset = [&]() {
+        cp = ChainParams();
+        cp.c.R = R; cp.c.d = d; cp.c.H = H; cp.c.n_ctx = n_ctx; cp.c.eps = hp.eps; cp.c.ref_f16_gelu = dt == DType::F16 ? 1 : 0;
+        cp.c.x = x; cp.c.rows = d_rows; cp.c.te = model.d_te; cp.c.pe = model.d_pe;
+    };
+    double chain_bytes = 0.0;
+    auto add_row = [&](const SplitGeom * g, const float * bias, const float * lw, const float * lb, void * out16, bool embed) {
+        ChainPhase & ph = cp.ph[cp.n_phase++];
+        ph.type = CP_ROW; ph.embed = embed ? 1 : 0;
+        if (g) { ph.g = *g; ph.part = part; }
+        ph.bias = bias; ph.ln_w = lw; ph.ln_b = lb; ph.out16 = out16; ph.ldo16 = d;
+        chain_bytes += (double) R * d * 10.0;
+    };
+    auto add_gemm = [&](const SplitGeom & g, const void * a, int K, const void * w, int N) {      // stream-K -> partial tiles
+        ChainPhase & ph = cp.ph[cp.n_phase++];
+        ph.type = CP_GEMM; ph.nt = 64; ph.N = N; ph.K = K; ph.a = a; ph.lda = K; ph.w = w; ph.ldw = K; ph.g = g; ph.part = part;
+        chain_bytes += ((double) N * K + (double) R * K) * 2.0;
+    };
+    auto add_gemm_direct = [&](const SplitGeom & g, const void * a, int K, const void * w, int N, const float * bias, float scale,
+                               int scale_cols, bool gelu, void * out16) {
+        ChainPhase & ph = cp.ph[cp.n_phase++];
+        ph.type = CP_GEMM; ph.nt = 32; ph.N = N; ph.K = K; ph.a = a; ph.lda = K; ph.w = w; ph.ldw = K; ph.g = g;
+        ph.bias = bias; ph.scale = scale; ph.scale_cols = scale_cols; ph.gelu = gelu ? 1 : 0; ph.out16 = out16; ph.ldo16 = N;
+        chain_bytes += ((double) N * K + (double) R * (K + N)) * 2.0;
+    };
+    auto add_self = [&](int il) {
+        ChainPhase & ph = cp.ph[cp.n_phase++];
+        ph.type = CP_SELF; ph.a = qkv; ph.lda = 3 * d; ph.out16 = att; ph.ldo16 = d; ph.layer_off = il * self_layer;
+        chain_bytes += self_bytes;
+    };
+    // QKV -> self-attention -> out-projection -> residual + LayerNorm -> cross query of layer il (h16 = LayerNorm(x) on entry)
+    auto add_attn_half = [&](int il) {
+        const DecLayer & Lr = model.dec[il];
+        add_gemm_direct(g_qkv, h16, d, Lr.wqkv, 3 * d, Lr.bqkv, qk_scale, 2 * d, false, qkv);
+        add_self(il);
+        add_gemm(g_dd, att, d, Lr.wo, d);
+        add_row(&g_dd, Lr.bo, Lr.lnx_w, Lr.lnx_b, h16, false);
+        add_gemm(g_dd, h16, d, Lr.wxq, d);
+    };
+    // cross out-projection -> residual + LayerNorm -> MLP of layer il; the closing residual/LayerNorm row phase is added by the caller
+    auto add_mlp_half = [&](int il) {
+        const DecLayer & Lr = model.dec[il];
+        add_gemm(g_dd, att, d, Lr.wxo, d);
+        add_row(&g_dd, Lr.bxo, Lr.ln2_w, Lr.ln2_b, h16, false);
+        add_gemm_direct(g_m1, h16, d, Lr.w1, 4 * d, Lr.b1, 1.0f, 0, true, mlp);
+        add_gemm(g_m2, mlp, 4 * d, Lr.w2, d);
+    };
+    static const bool trace_on = getenv("WHISPER_B200_CHAIN_TRACE") != nullptr;
+    if (trace_on && !chain_trace.reserve((size_t) (L + 1) * 32 * 8)) return false;
+    int launch_idx = 0;
+    bool ok = true;
+    auto launch = [&]() {
+        if (trace_on) cp.trace = (unsigned long long *) chain_trace.p + 32 * launch_idx;
+        ++launch_idx;
+        prof_begin(PC_DEC_CHAIN, chain_bytes);
+        ok = ok && chain_launch(chain, dt, cp, stream);
+        prof_end();
+        n_kernel_launches += 1;
+        chain_bytes = 0.0;
+    };
+    for (int il = 0; il <= L; ++il) {
+        reset();
+        if (il == 0) {
+            add_row(nullptr, nullptr, model.dec[0].ln1_w, model.dec[0].ln1_b, h16, true);
+        } else {
+            add_mlp_half(il - 1);
+            if (il < L) add_row(&g_m2, model.dec[il - 1].b2, model.dec[il].ln1_w, model.dec[il].ln1_b, h16, false);
+            else        add_row(&g_m2, model.dec[il - 1].b2, identity_logits ? model.d_ln_w : nullptr,
+                                identity_logits ? model.d_ln_b : nullptr, hl16, false);
+        }
+        if (il < L) add_attn_half(il);
+        launch();
+        if (il < L) {
+            SplitIn qs;
+            qs.part = part; qs.bias = model.dec[il].bxq; qs.g = g_dd;
+            prof_begin(PC_CROSS_ATTN, (double) R * 1500.0 * 2 * d * 2.0);
+            dec_cross_attn(dt, nullptr, d_rows, R, d, H, il * cross_layer_stride, 1500, n_phantom(), att, stream, &qs);
+            prof_end();
+            n_kernel_launches += 1;
+        }
+    }
+    if (RL > 0) {
+        if (!identity_logits) {
+            prof_begin(PC_LAYERNORM_DEC, (double) RL * d * 6.0);
+            layernorm(dt, x, d, model.d_ln_w, model.d_ln_b, hp.eps, RL, d, hl16, d, nullptr, 0, d_lrows, stream);
+            prof_end();
+            n_kernel_launches += 1;
+        }
+        prof_begin(PC_GEMM_LOGITS, ((double) V * d + (double) RL * (V + d)) * 2.0);
+        GemmArgs g;
+        g.dtype = dt; g.M = RL; g.N = V; g.K = d; g.a = hl16; g.lda = d; g.w = model.d_te; g.ldw = d;
+        g.out32 = (float *) logits.p; g.ldo32 = ld_logits;
+        ok = ok && skinny_gemm(g, skinny_ws, stream);
+        prof_end();
+        n_kernel_launches += 1;
+    }
+    if (trace_on && L >= 3) {
+        // average over the middle launches (all have the same 11 phases): phase durations, launch-to-launch gap
+        std::vector<unsigned long long> h((size_t) (L + 1) * 32);
+        WB_CUDA(cudaStreamSynchronize(stream));
+        WB_CUDA(cudaMemcpy(h.data(), chain_trace.p, h.size() * 8, cudaMemcpyDeviceToHost));
+        if (chain_trace_acc.empty()) chain_trace_acc.assign(32, 0.0);
+        for (int l = 1; l < L; ++l) {
+            const unsigned long long * t = h.data() + 32 * l;
+            for (int i = 0; i < 10; ++i) chain_trace_acc[i] += (double) (t[i + 1] - t[i]) * 1e-3;
+            chain_trace_acc[10] += (double) (t[0] - t[15]) * 1e-3;                   // entry -> first phase (PDL wait)
+            chain_trace_acc[11] += (double) (t[15] - (t - 32)[l == 1 ? 6 : 10]) * 1e-3;   // previous chain end -> entry
+        }
+        chain_trace_steps += L - 1;
+        if (chain_trace_steps % ((L - 1) * 20) == 0) {
+            static const char * names[12] = {"xO", "row", "mlp1", "mlp2", "row", "qkv", "self", "O", "row", "xQ", "wait", "gap(cross)"};
+            fprintf(stderr, "chain trace (us, R=%d):", R);
+            for (int i = 0; i < 12; ++i) fprintf(stderr, " %s %.2f", names[i], chain_trace_acc[i] / chain_trace_steps);
+            fprintf(stderr, "  pdl=%d\n", chain.pdl_ok ? 1 : 0);
+        }
+    }
+    if (!ok) wlog(GGML_LOG_LEVEL_ERROR, "%s: chain launch failed\n", __func__);
     return ok && !cuda_failed();
 }
 

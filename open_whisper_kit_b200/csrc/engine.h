@@ -5,6 +5,7 @@
 #include <mutex>
 #include <vector>
 
+#include "dec_chain.h"
 #include "dec_kernels.h"
 #include "enc_kernels.h"
 #include "mel.h"
@@ -66,7 +67,7 @@ struct EncJob {
 // Optional per-kernel-class timing with CUDA events on the engine's stream (bench.py's roofline numbers).
 enum ProfClass {
     PC_MEL = 0, PC_IM2COL, PC_GEMM_CONV, PC_LAYERNORM, PC_GEMM_ENC, PC_ENC_ATTN, PC_GEMM_CROSS, PC_DEC_MISC, PC_GEMM_DEC,
-    PC_SELF_ATTN, PC_CROSS_ATTN, PC_GEMM_LOGITS, PC_SAMPLE, PC_LAYERNORM_DEC, PC_COUNT
+    PC_SELF_ATTN, PC_CROSS_ATTN, PC_GEMM_LOGITS, PC_SAMPLE, PC_LAYERNORM_DEC, PC_DEC_CHAIN, PC_COUNT
 };
 
 struct Engine {
@@ -83,6 +84,13 @@ struct Engine {
     DeviceBlock logits;        // f32 [rows][ld_logits], valid until the next decode
     SkinnyWorkspace skinny_ws; // split-K scratch of the decoder-step GEMM
     DeviceBlock embd_enc32;    // f32 [windows*1500][d] of the last encode when requested
+    ChainLauncher chain;       // persistent single-token decoder-step kernel (dec_chain.cu)
+    DeviceBlock chain_part;    // its stream-K partial tiles
+    int chain_mode = -1;       // -1 undecided, 0 off (WHISPER_B200_CHAIN=0 or unsupported geometry), 1 on
+    int chain_min_units = 2;
+    DeviceBlock chain_trace;   // WHISPER_B200_CHAIN_TRACE=1: per-phase device timestamps of the chain launches
+    std::vector<double> chain_trace_acc;
+    long long chain_trace_steps = 0;
     int ld_logits = 0;
     void * h_pinned[2] = {nullptr, nullptr};   // pinned host staging: [0] decoder rows (H2D), [1] sampler I/O
     size_t h_pinned_cap[2] = {0, 0};
@@ -119,6 +127,9 @@ struct Engine {
     // Runs the decoder over `rows`; logits are produced for rows[logit_rows[i]] into logits row i.
     // cross_layer_stride: element distance between text layers in the cross-K/V pool the rows point into.
     bool decode(const std::vector<DecRow> & rows, const std::vector<int> & logit_rows, size_t cross_layer_stride);
+    // single-token step (one row per sequence, R <= 128) through the chain kernel; same outputs as decode()
+    bool decode_chain(const std::vector<DecRow> & rows, const std::vector<int> & logit_rows, size_t cross_layer_stride);
+    bool chain_usable(int R);
     bool fetch_logits(int row, float * out);                         // D2H one row (n_vocab floats)
     bool sample_greedy(const std::vector<SampleRow> & srows, const uint32_t * d_mask, const SampleParams & prm,
                        std::vector<SampleOut> & out);
