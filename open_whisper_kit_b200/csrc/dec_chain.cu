@@ -14,39 +14,27 @@
 
 #include <algorithm>
 
+#include "ptx.cuh"
+
 namespace wb {
 
 namespace {
 
-constexpr int CB = 64;                                 // tile edge (M, K per stage; N is 64 or 32)
-constexpr int C_THREADS = 128;
-constexpr int C_STAGES = 6;
-constexpr int C_STAGE_BYTES = 2 * CB * CB * 2;         // X tile + W tile, 16 KB
-constexpr int C_SMEM = C_STAGES * C_STAGE_BYTES;       // 96 KB -> two CTAs per SM
-// The last ring stage is never a prefetch target, so the row / self-attention phases may use it as scratch while the next
-// GEMM's weights are already landing in stages 0 .. C_STAGES-2.
-constexpr int C_SCRATCH_OFF = (C_STAGES - 1) * C_STAGE_BYTES;
-
-__device__ __forceinline__ void cp16(void * smem, const void * gmem, bool valid) {
-    const uint32_t s = (uint32_t) __cvta_generic_to_shared(smem);
-    const int sz = valid ? 16 : 0;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(sz));
-}
-__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void ldsm4(uint32_t addr, uint32_t & r0, uint32_t & r1, uint32_t & r2, uint32_t & r3) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
-}
-template <typename T16> __device__ __forceinline__ void mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1);
-template <> __device__ __forceinline__ void mma<__half>(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-template <> __device__ __forceinline__ void mma<__nv_bfloat16>(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ uint32_t sw(int row, int chunk) { return (uint32_t) (row * 128 + ((chunk ^ (row & 7)) << 4)); }
+constexpr int CB = 64;                                 // K per stage; weight tile is 64 or 32 rows
+// warps 0-3: accumulator read-back (tcgen05.ld lets warp w read TMEM lanes 32w..32w+31 = token rows), warp 4: TMA
+// producer, warp 5: MMA issuer; all six run the row / self-attention phases
+constexpr int C_THREADS = 192;
+constexpr int C_WARPS = C_THREADS / 32;
+// Ring geometry depends on the row count: R <= 64 -> 4 stages of (8 KB activations + 16 KB weights), else 3 stages of
+// (16 KB + 16 KB).  The A descriptor always spans 128 rows = 16 KB from the start of the activation tile; with 64 live rows
+// the upper half of that span is the start of the stage's own weight tile, i.e. harmless stale rows.
+constexpr int C_RING_BYTES = 96 * 1024;
+constexpr int C_MAX_STAGES = 6;
+constexpr int C_SMEM = C_RING_BYTES + 1024;            // 97 KB incl. alignment slack -> two CTAs per SM
+// Weight tile = 128 rows: issuing one tcgen05.mma costs ~150 cycles whatever its N (measured), so a unit should carry as
+// many weight rows as the tile count of the smallest GEMM allows.
+constexpr int NT = 128;
+constexpr int C_TMEM_COLS = 128;
 
 // ---- grid-wide barrier ---------------------------------------------------------------------------------------------
 // All CTAs of the launch are co-resident (cooperative launch), so a monotonic arrival counter is enough: barrier k of
@@ -76,6 +64,12 @@ __device__ __noinline__ void grid_barrier(unsigned * bar, unsigned target) {
     __syncthreads();
 }
 
+// mbarrier wait that cannot hang the GPU: a protocol error must fail the launch (trap), not spin forever
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t * bar, uint32_t parity) {
+    for (unsigned spins = 0; !ptx::mbar_try_wait(bar, parity); ++spins)
+        if (spins > (1u << 24)) __trap();
+}
+
 template <typename T16> __device__ __forceinline__ float round16(float v) { return Half16<T16>::to_f(Half16<T16>::from_f(v)); }
 
 template <typename T16> __device__ __forceinline__ float gelu_ref(float v, int ref_f16) {
@@ -95,24 +89,20 @@ template <typename T16> __device__ __forceinline__ void store4_16(T16 * dst, flo
 }
 
 // ---- GEMM phase --------------------------------------------------------------------------------------------------------
-// A (virtual) CTA walks a contiguous range of 64 x nt x 64 units.  nt = 64: stream-K, one f32 partial tile out per output
-// tile touched.  nt = 32: "direct" -- the range is exactly one output tile over the full K, so bias / scale / GELU and the
-// 16-bit store happen here.  The four warps split the 64 rows (16 each): every accumulator lives in one warp, so a tile is
-// finished straight from registers.  Everything the loop needs is held in registers (GemmRegs): the phase descriptors are
-// kernel parameters, and this code is inlined at its single call site so they are read from the constant bank once.
+// out[R <= 128][N] = act[R][K] * W[N][K]^T on the 5th-generation tensor cores: legacy mma.sync tops out near 180 TFLOP/s
+// on this part (measured: the step's 102 GFLOP of 64-row GEMMs cost 0.5 ms that way, twice their HBM time).  A (virtual)
+// CTA walks a contiguous range of units; a unit is one 64-deep k-block of one weight tile:
+//   A operand = activation tile, 128 token rows x 64 k (M = 128; rows >= R are zero-filled by TMA or stale -- they only
+//               produce accumulator rows nobody reads), B operand = weight tile, nt x 64 k, both K-major, 128-byte swizzle;
+//   warp 4 (one lane) feeds a ring of stages with two TMA loads per unit, completion on the stage's `full` mbarrier;
+//   warp 5 (one lane) issues 4 tcgen05.mma (K = 16 each) per unit into a 128 x nt f32 accumulator in TMEM; tcgen05.commit
+//   hands the stage back (`empty`) and, at the end of an output tile, publishes the accumulator (`acc_full`);
+//   warps 0-3 read their 32 accumulator lanes back, finish the tile and release TMEM (`acc_empty`).
+// nt = 64: stream-K, every CTA emits one f32 partial tile per output tile its range touches.  nt = 32: "direct" -- the
+// range is exactly one output tile over the full K, so bias / scale / GELU and the 16-bit store happen here.
 struct GemmRegs {
-    const void * a, * w;
-    int lda, ldw, nt, kpt, tiles, U, G;
+    int direct, kpt, U, G;
 };
-struct Cursor {          // (k-block, n-tile, m-block) of the next unit a loader will fetch
-    int kb, tile, mb;
-};
-__device__ __forceinline__ GemmRegs gemm_regs(const ChainPhase & ph) {
-    GemmRegs g;
-    g.a = ph.a; g.w = ph.w; g.lda = ph.lda; g.ldw = ph.ldw; g.nt = ph.nt; g.kpt = ph.g.kpt; g.tiles = ph.g.tiles;
-    g.U = ph.g.U; g.G = ph.g.G;
-    return g;
-}
 __device__ __forceinline__ void range_of(const GemmRegs & g, int vc, int & u0, int & nu) {
     u0 = 0; nu = 0;
     if (vc < g.G) {
@@ -120,47 +110,16 @@ __device__ __forceinline__ void range_of(const GemmRegs & g, int vc, int & u0, i
         nu = (int) ((unsigned) g.U * (unsigned) (vc + 1) / (unsigned) g.G) - u0;
     }
 }
-__device__ __forceinline__ Cursor cursor_at(const GemmRegs & g, int u) {
-    Cursor c;
-    const int ot = u / g.kpt;
-    c.kb = u - ot * g.kpt;
-    c.mb = ot / g.tiles;
-    c.tile = ot - c.mb * g.tiles;
-    return c;
-}
-__device__ __forceinline__ void cursor_next(const GemmRegs & g, Cursor & c) {
-    if (++c.kb == g.kpt) {
-        c.kb = 0;
-        if (++c.tile == g.tiles) { c.tile = 0; ++c.mb; }
-    }
-}
-template <typename T16> __device__ __forceinline__ void load_w(const GemmRegs & g, Cursor & c, uint8_t * stage) {
-    const int r0 = threadIdx.x >> 3, ch = threadIdx.x & 7;
-    const T16 * W = reinterpret_cast<const T16 *>(g.w) + (size_t) (c.tile * g.nt + r0) * g.ldw + c.kb * CB + ch * 8;
-    uint8_t * st = stage + CB * CB * 2;
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-        if (j * 16 < g.nt) cp16(st + sw(r0 + j * 16, ch), W + (size_t) (j * 16) * g.ldw, true);
-    cursor_next(g, c);
-}
-template <typename T16> __device__ __forceinline__ void load_x(const GemmRegs & g, Cursor & c, int R, uint8_t * stage) {
-    const int r0 = threadIdx.x >> 3, ch = threadIdx.x & 7;
-    const T16 * X = reinterpret_cast<const T16 *>(g.a) + c.kb * CB + ch * 8;
-    const int m0 = c.mb * CB + r0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const bool ok = m0 + j * 16 < R;
-        cp16(stage + sw(r0 + j * 16, ch), X + (size_t) (ok ? m0 + j * 16 : 0) * g.lda, ok);
-    }
-    cursor_next(g, c);
-}
 
-__device__ __forceinline__ float block_sum4(float v, float * s_red) {       // 4 warps; safe to call back to back
+__device__ __forceinline__ float block_sum(float v, float * s_red) {       // C_WARPS warps; safe to call back to back
     v = warp_sum(v);
     __syncthreads();
     if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
     __syncthreads();
-    return (s_red[0] + s_red[1]) + (s_red[2] + s_red[3]);
+    float r = 0.0f;
+#pragma unroll
+    for (int w = 0; w < C_WARPS; ++w) r += s_red[w];
+    return r;
 }
 
 // ---- residual / LayerNorm phase: one CTA per token row ----------------------------------------------------------------
@@ -172,7 +131,8 @@ __device__ __forceinline__ void row_phase(const ChainCommon & p, const ChainPhas
     const int d = p.d, nq = d >> 2;
     constexpr int NB = 8;                     // partial tiles in flight per quad
     float s = 0.0f;
-    const DecRow row = p.rows[r];
+    DecRow row = {};
+    if (ph.embed) row = p.rows[r];
 #pragma unroll 1
     for (int q = tid; q < nq; q += C_THREADS) {
         const int c = q * 4;
@@ -185,16 +145,16 @@ __device__ __forceinline__ void row_phase(const ChainCommon & p, const ChainPhas
         } else {
             // x + (partial tiles in contributor order + bias); NB independent loads in flight
             v = __ldcg(reinterpret_cast<const float4 *>(p.x + (size_t) r * d + c));
-            const int ot = (r >> 6) * ph.g.tiles + (c >> 6);
+            const int ot = c / SG_TILE_COLS;
             const int cnt = sg_cta_of(ph.g, ot * ph.g.kpt + ph.g.kpt - 1) - sg_cta_of(ph.g, ot * ph.g.kpt) + 1;
-            const float * src = ph.part + ((size_t) ot * ph.g.maxc) * 4096 + (r & 63) * 64 + (c & 63);
+            const float * src = ph.part + ((size_t) ot * ph.g.maxc) * SG_TILE_FLOATS + r * SG_TILE_COLS + (c % SG_TILE_COLS);
             float4 a = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 #pragma unroll 1
             for (int j0 = 0; j0 < cnt; j0 += NB) {
                 float4 t[NB];
 #pragma unroll
                 for (int u = 0; u < NB; ++u)
-                    t[u] = j0 + u < cnt ? __ldcg(reinterpret_cast<const float4 *>(src + (size_t) (j0 + u) * 4096)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    t[u] = j0 + u < cnt ? __ldcg(reinterpret_cast<const float4 *>(src + (size_t) (j0 + u) * SG_TILE_FLOATS)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 #pragma unroll
                 for (int u = 0; u < NB; ++u) { a.x += t[u].x; a.y += t[u].y; a.z += t[u].z; a.w += t[u].w; }
             }
@@ -209,7 +169,7 @@ __device__ __forceinline__ void row_phase(const ChainCommon & p, const ChainPhas
         s += (v.x + v.y) + (v.z + v.w);
     }
     if (!ph.ln_w) return;
-    const float mean = block_sum4(s, s_red) / (float) d;
+    const float mean = block_sum(s, s_red) / (float) d;
     float qq = 0.0f;
 #pragma unroll 1
     for (int q = tid; q < nq; q += C_THREADS) {           // every thread re-reads only what it wrote
@@ -217,7 +177,7 @@ __device__ __forceinline__ void row_phase(const ChainCommon & p, const ChainPhas
         const float a = v.x - mean, b = v.y - mean, c = v.z - mean, e = v.w - mean;
         qq += (a * a + b * b) + (c * c + e * e);
     }
-    const float var = block_sum4(qq, s_red) / (float) d;
+    const float var = block_sum(qq, s_red) / (float) d;
     const float rstd = 1.0f / sqrtf(var + p.eps);
     T16 * out = reinterpret_cast<T16 *>(ph.out16) + (size_t) r * ph.ldo16;
 #pragma unroll 1
@@ -241,11 +201,11 @@ __device__ __forceinline__ void self_phase(const ChainCommon & p, const ChainPha
     const int sub = lane & 7, grp = lane >> 3;
     float * sc = s_sc_all + warp * (p.n_ctx + 4);
     const int d = p.d, ld = 2 * d;
-    constexpr int U = 4;
+    constexpr int U = 16;          // 64 keys per batch: the phase is a chain of L2/HBM round trips, so make each one count
     const int items = p.R * p.H;
     const T16 * qkv = reinterpret_cast<const T16 *>(ph.a);
 #pragma unroll 1
-    for (int item = blockIdx.x * 4 + warp; item < items; item += gridDim.x * 4) {
+    for (int item = blockIdx.x * C_WARPS + warp; item < items; item += gridDim.x * C_WARPS) {
         const int r = item / p.H, h = item - r * p.H;
         const DecRow row = p.rows[r];
         const int T = row.pos;                          // keys already in the cache
@@ -338,8 +298,14 @@ __device__ __forceinline__ void self_phase(const ChainCommon & p, const ChainPha
 template <typename T16>
 __global__ void __launch_bounds__(C_THREADS, 2)
 dec_chain_kernel(const __grid_constant__ ChainParams p) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ float s_red[4];
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ float s_red[C_WARPS];
+    __shared__ __align__(8) uint64_t s_full[C_MAX_STAGES];   // TMA -> MMA: both tiles of a stage have landed
+    __shared__ __align__(8) uint64_t s_empty[C_MAX_STAGES];  // MMA -> TMA: the MMAs reading a stage have retired
+    __shared__ __align__(8) uint64_t s_acc_full, s_acc_empty;   // MMA -> read-back: tile complete; read-back -> MMA: TMEM drained
+    __shared__ uint32_t s_tmem;
+    // 128-byte swizzle atoms are 1024 bytes: align the ring
+    uint8_t * smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int R = p.c.R;
     auto stamp = [&](int slot) {
@@ -351,28 +317,60 @@ dec_chain_kernel(const __grid_constant__ ChainParams p) {
     };
     stamp(15);
     pdl_trigger();
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C_MAX_STAGES; ++s) {
+            ptx::mbar_init(&s_full[s], 1);
+            ptx::mbar_init(&s_empty[s], 1);
+        }
+        ptx::mbar_init(&s_acc_full, 1);
+        ptx::mbar_init(&s_acc_empty, 4);
+        ptx::fence_mbar_init();
+    }
+    if (warp == 0) {
+        ptx::tmem_alloc(&s_tmem, C_TMEM_COLS);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem = s_tmem;
 
-    // state of the GEMM phase whose first weight stages are in flight (phase index pf)
-    int pf = -1, u0 = 0, nu = 0;
+    const unsigned S = R <= 64 ? 4u : 3u;
+    const uint32_t x_bytes = R <= 64 ? 8192u : 16384u, stage_bytes = x_bytes + NT * 128u;
+    auto stage_ptr = [&](unsigned gc) { return smem + (gc % S) * stage_bytes; };
+    const bool is_producer = warp == 4 && lane == 0, is_mma = warp == 5 && lane == 0;
+
+    // Every thread tracks the same counters: units (gcount) and output tiles (tcount) this CTA has been through; unit gc
+    // lives in ring stage gc % S, and the mbarrier parities follow from the counters alone.
+    unsigned gcount = 0, tcount = 0;
+    int pf = -1, u0 = 0, nu = 0, npre = 0;      // GEMM phase whose first weight tiles are already in flight, its range
     GemmRegs g = {};
-    Cursor wcur = {}, xcur = {};
     unsigned target = p.bar_base;
 #pragma unroll 1
     for (int i = 0; i < p.n_phase; ++i) {
-        // Weights are never written on the device: the first stages of the next GEMM phase are requested before the
-        // barrier (or grid dependency) that guards its activations -- one commit group, older than any activation group.
+        // Weights are never written on the device: the weight tiles of the next GEMM phase's first stages are requested
+        // before the barrier (or grid dependency) that guards its activations.  Every MMA of earlier phases has retired
+        // (their tiles were read back), so the stages are free; one stage is left alone as scratch for the other phases.
         if (pf < i) {
             pf = p.n_phase;
             for (int j = i; j < p.n_phase; ++j)
                 if (p.ph[j].type == CP_GEMM) { pf = j; break; }
             if (pf < p.n_phase) {
-                g = gemm_regs(p.ph[pf]);
+                const ChainPhase & q = p.ph[pf];
+                g.direct = q.direct; g.kpt = q.g.kpt; g.U = q.g.U; g.G = q.g.G;
                 range_of(g, blockIdx.x, u0, nu);
-                wcur = cursor_at(g, u0);
-                xcur = wcur;
-#pragma unroll 1
-                for (int s = 0; s < C_STAGES - 1 && s < nu; ++s) load_w<T16>(g, wcur, smem + s * C_STAGE_BYTES);
-                cp_commit();
+                npre = min(nu, (int) S - 1);
+                if (is_producer) {
+                    const TMap * tw = &p.tm[2 * q.tm + 1];
+                    const uint32_t tx = x_bytes + NT * 128u;
+                    for (int s = 0; s < npre; ++s) {
+                        const unsigned gc = gcount + s;
+                        const int u = u0 + s, tile = u / g.kpt, kb = u - tile * g.kpt;
+                        if (gc >= S) mbar_wait_bounded(&s_empty[gc % S], ((gc / S) - 1u) & 1u);
+                        ptx::mbar_arrive_expect_tx(&s_full[gc % S], tx);
+                        ptx::tma_load_2d(stage_ptr(gc) + x_bytes, tw, &s_full[gc % S], kb * CB, tile * NT);
+                    }
+                }
             }
         }
         if (i == 0) {
@@ -383,108 +381,137 @@ dec_chain_kernel(const __grid_constant__ ChainParams p) {
         }
         stamp(i);
         const ChainPhase & ph = p.ph[i];
-        if (ph.type == CP_ROW) {
-            row_phase<T16>(p.c, ph, s_red, reinterpret_cast<float4 *>(smem + C_SCRATCH_OFF));
-        } else if (ph.type == CP_SELF) {
-            self_phase<T16>(p.c, ph, reinterpret_cast<float *>(smem + C_SCRATCH_OFF));
+        if (ph.type == CP_ROW || ph.type == CP_SELF) {
+            // a stage the prefetch above never targets is scratch for these phases
+            uint8_t * scratch = stage_ptr(gcount + S - 1);
+            if (ph.type == CP_ROW) row_phase<T16>(p.c, ph, s_red, reinterpret_cast<float4 *>(scratch));
+            else self_phase<T16>(p.c, ph, reinterpret_cast<float *>(scratch));
+            ptx::fence_proxy_async_smem();      // generic-proxy writes to the scratch stage vs. the TMA writes that follow
         } else if (ph.type == CP_GEMM) {
-            const int np_n = g.nt >> 4;                  // 16-column groups per tile: 4 or 2
-            const int arow = warp * 16 + (lane & 7) + 8 * ((lane >> 3) & 1), acol = lane >> 4;
-            const int brow = (lane & 7) + 8 * (lane >> 4), bcol = (lane >> 3) & 1;
-            const int gq = lane >> 2, tq = lane & 3;
+            const TMap * ta = &p.tm[2 * ph.tm], * tw = &p.tm[2 * ph.tm + 1];
+            const uint32_t tx = x_bytes + NT * 128u;
 #pragma unroll 1
             for (int vc = blockIdx.x; vc < g.G; vc += gridDim.x) {
                 if (vc != (int) blockIdx.x) {            // further virtual CTAs of this phase: nothing was prefetched
                     range_of(g, vc, u0, nu);
-                    wcur = cursor_at(g, u0);
-                    xcur = wcur;
-#pragma unroll 1
-                    for (int s = 0; s < C_STAGES - 1 && s < nu; ++s) load_w<T16>(g, wcur, smem + s * C_STAGE_BYTES);
-                    cp_commit();
+                    npre = 0;
                 }
-                Cursor ccur = xcur;                      // unit being multiplied
-#pragma unroll 1
-                for (int s = 0; s < C_STAGES - 1; ++s) {
-                    if (s < nu) load_x<T16>(g, xcur, R, smem + s * C_STAGE_BYTES);
-                    cp_commit();
-                }
-                float acc[8][4];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0f;
-#pragma unroll 1
-                for (int it = 0; it < nu; ++it) {
-                    cp_wait<C_STAGES - 2>();
-                    __syncthreads();
-                    if (it + C_STAGES - 1 < nu) {
-                        uint8_t * st = smem + ((it + C_STAGES - 1) % C_STAGES) * C_STAGE_BYTES;
-                        load_x<T16>(g, xcur, R, st);
-                        load_w<T16>(g, wcur, st);
+                const int tile0 = u0 / g.kpt, kb0 = u0 - tile0 * g.kpt;
+                if (is_producer) {
+                    // ===== TMA producer =====
+                    int tile = tile0, kb = kb0;
+                    long long t_wait = 0, t_begin = clock64();
+                    for (int it = 0; it < nu; ++it) {
+                        const unsigned gc = gcount + it;
+                        uint8_t * st = stage_ptr(gc);
+                        if (it >= npre) {
+                            const long long t0 = clock64();
+                            if (gc >= S) mbar_wait_bounded(&s_empty[gc % S], ((gc / S) - 1u) & 1u);
+                            t_wait += clock64() - t0;
+                            ptx::mbar_arrive_expect_tx(&s_full[gc % S], tx);
+                            ptx::tma_load_2d(st + x_bytes, tw, &s_full[gc % S], kb * CB, tile * NT);
+                        }
+                        ptx::tma_load_2d(st, ta, &s_full[gc % S], kb * CB, 0);
+                        if (++kb == g.kpt) { kb = 0; ++tile; }
                     }
-                    cp_commit();
-                    const uint32_t sx = (uint32_t) __cvta_generic_to_shared(smem + (it % C_STAGES) * C_STAGE_BYTES);
-                    const uint32_t swt = sx + CB * CB * 2;
+                    if (p.trace && blockIdx.x == 0 && g.direct && ph.gelu == 0) { p.trace[20] = (unsigned long long) t_wait; p.trace[21] = (unsigned long long) (clock64() - t_begin); }
+                } else if (is_mma) {
+                    // ===== MMA issuer =====
+                    const uint32_t idesc = ptx::make_idesc_f16(Half16<T16>::kind, 128, NT);
+                    int kb = kb0;
+                    unsigned tc = tcount;
+                    bool fresh = true;                   // the next MMA starts a new output tile
+                    long long t_wait = 0, t_begin = clock64();
+                    for (int it = 0; it < nu; ++it) {
+                        const unsigned gc = gcount + it;
+                        const long long t0 = clock64();
+                        mbar_wait_bounded(&s_full[gc % S], (gc / S) & 1u);
+                        t_wait += clock64() - t0;
+                        if (fresh && tc >= 1) mbar_wait_bounded(&s_acc_empty, (tc - 1u) & 1u);    // TMEM drained
+                        ptx::tc_fence_after();
+                        const uint32_t sx = ptx::smem_u32(stage_ptr(gc));
+                        const uint64_t da = ptx::make_sw128_kmajor_desc(sx), db = ptx::make_sw128_kmajor_desc(sx + x_bytes);
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        uint32_t a[4];
-                        ldsm4(sx + sw(arow, ks * 2 + acol), a[0], a[1], a[2], a[3]);
-#pragma unroll
-                        for (int np = 0; np < 4; ++np) {
-                            if (np < np_n) {
-                                uint32_t b0, b1, b2, b3;
-                                ldsm4(swt + sw(np * 16 + brow, ks * 2 + bcol), b0, b1, b2, b3);
-                                mma<T16>(acc[2 * np], a, b0, b1);
-                                mma<T16>(acc[2 * np + 1], a, b2, b3);
-                            }
+                        for (int k = 0; k < 4; ++k)      // +32 bytes along K inside the swizzle atom = +2 in 16-byte units
+                            ptx::umma_f16(tmem, da + (uint64_t) (2 * k), db + (uint64_t) (2 * k), idesc, (uint32_t) (!fresh || k != 0));
+                        ptx::umma_commit(&s_empty[gc % S]);
+                        fresh = false;
+                        if (++kb == g.kpt || it == nu - 1) {
+                            ptx::umma_commit(&s_acc_full);
+                            kb = 0;
+                            ++tc;
+                            fresh = true;
                         }
                     }
-                    if (ccur.kb == g.kpt - 1 || it == nu - 1) {
-                        const int ot = ccur.mb * g.tiles + ccur.tile;
-                        if (g.nt == 64) {        // this CTA's partial tile of output tile `ot`
-                            const int first = sg_cta_of(ph.g, ot * g.kpt);
-                            float * dst = ph.part + ((size_t) ot * ph.g.maxc + (vc - first)) * 4096 + (warp * 16 + gq) * 64 + 2 * tq;
-#pragma unroll
-                            for (int n8 = 0; n8 < 8; ++n8) {
-                                __stcg(reinterpret_cast<float2 *>(dst + n8 * 8), make_float2(acc[n8][0], acc[n8][1]));
-                                __stcg(reinterpret_cast<float2 *>(dst + 8 * 64 + n8 * 8), make_float2(acc[n8][2], acc[n8][3]));
-                            }
-                        } else {                 // whole tile: bias, scale, GELU, 16-bit store
-                            const int m = ccur.mb * CB + warp * 16 + gq, n = ccur.tile * 32 + 2 * tq;
-                            T16 * out = reinterpret_cast<T16 *>(ph.out16);
+                    if (p.trace && blockIdx.x == 0 && g.direct && ph.gelu == 0) { p.trace[22] = (unsigned long long) t_wait; p.trace[23] = (unsigned long long) (clock64() - t_begin); }
+                } else if (warp < 4) {
+                    // ===== accumulator read-back =====
+                    int tile = tile0, kb = kb0;
+                    unsigned tc = tcount;
+                    const int row = warp * 32 + lane;
+#pragma unroll 1
+                    for (int it = 0; it < nu; ++it) {
+                        if (++kb != g.kpt && it != nu - 1) continue;
+                        mbar_wait_bounded(&s_acc_full, tc & 1u);
+                        ptx::tc_fence_after();
+                        if (warp * 32 < R) {             // warp-uniform: this warp's 32 accumulator lanes hold live rows
                             const float * bias = ph.bias;
-                            const float scale = ph.scale;
-                            const int scale_cols = ph.scale_cols, gelu = ph.gelu, ldo = ph.ldo16, ref16 = p.c.ref_f16_gelu;
+                            const int gelu = ph.gelu, ref16 = p.c.ref_f16_gelu, scale_cols = ph.scale_cols;
+                            const float scale_v = ph.scale;
+                            const int first = g.direct ? 0 : sg_cta_of(ph.g, tile * g.kpt);
+                            float * dst = g.direct ? nullptr : ph.part + ((size_t) tile * ph.g.maxc + (vc - first)) * SG_TILE_FLOATS + row * NT;
+                            T16 * out = g.direct ? reinterpret_cast<T16 *>(ph.out16) + (size_t) row * ph.ldo16 + tile * NT : nullptr;
 #pragma unroll 1
-                            for (int n8 = 0; n8 < 4; ++n8) {
-                                const int col = n + n8 * 8;
-                                float v[4];
+                            for (int c32 = 0; c32 < NT / 32; ++c32) {
+                                uint32_t r[32];
+                                ptx::tmem_ld_32x32(tmem + ((uint32_t) (warp * 32) << 16) + (uint32_t) (c32 * 32), r);
+                                ptx::tmem_ld_wait();
+                                if (row >= R) continue;
+                                if (!g.direct) {         // this CTA's partial tile of output tile `tile`
 #pragma unroll
-                                for (int e = 0; e < 4; ++e) v[e] = n8 == 0 ? acc[0][e] : n8 == 1 ? acc[1][e] : n8 == 2 ? acc[2][e] : acc[3][e];
-                                const float b0 = bias ? __ldg(bias + col) : 0.0f, b1 = bias ? __ldg(bias + col + 1) : 0.0f;
-                                v[0] += b0; v[1] += b1; v[2] += b0; v[3] += b1;
-                                if (col < scale_cols) { v[0] *= scale; v[1] *= scale; v[2] *= scale; v[3] *= scale; }
-                                if (gelu) {
+                                    for (int j = 0; j < 32; j += 4)
+                                        __stcg(reinterpret_cast<float4 *>(dst + c32 * 32 + j),
+                                               make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
+                                } else {                 // whole tile: bias, scale, GELU, 16-bit store
+                                    const int n0 = tile * NT + c32 * 32;
+                                    const float scale = n0 < scale_cols ? scale_v : 1.0f;
+#pragma unroll 1
+                                    for (int j = 0; j < 32; j += 8) {
+                                        union { T16 h[8]; uint4 u; } pk;
 #pragma unroll
-                                    for (int e = 0; e < 4; ++e) v[e] = gelu_ref<T16>(v[e], ref16);
+                                        for (int q = 0; q < 8; ++q) {
+                                            float v = __uint_as_float(j == 0 ? r[q] : j == 8 ? r[8 + q] : j == 16 ? r[16 + q] : r[24 + q]);
+                                            if (bias) v += __ldg(bias + n0 + j + q);
+                                            v *= scale;
+                                            if (gelu) v = gelu_ref<T16>(v, ref16);
+                                            pk.h[q] = Half16<T16>::from_f(v);
+                                        }
+                                        *reinterpret_cast<uint4 *>(out + c32 * 32 + j) = pk.u;
+                                    }
                                 }
-                                union { T16 h[2]; uint32_t u32; } lo, hi;
-                                lo.h[0] = Half16<T16>::from_f(v[0]); lo.h[1] = Half16<T16>::from_f(v[1]);
-                                hi.h[0] = Half16<T16>::from_f(v[2]); hi.h[1] = Half16<T16>::from_f(v[3]);
-                                if (m < R) *reinterpret_cast<uint32_t *>(out + (size_t) m * ldo + col) = lo.u32;
-                                if (m + 8 < R) *reinterpret_cast<uint32_t *>(out + (size_t) (m + 8) * ldo + col) = hi.u32;
                             }
                         }
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0f;
+                        ptx::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive(&s_acc_empty);
+                        kb = 0;
+                        ++tile;
+                        ++tc;
                     }
-                    cursor_next(g, ccur);
                 }
-                cp_wait<0>();
-                __syncthreads();
+                // every thread advances the counters identically
+                if (nu > 0) tcount += (unsigned) ((u0 + nu - 1) / g.kpt - tile0 + 1);
+                gcount += (unsigned) nu;
             }
-            if (blockIdx.x >= (unsigned) g.G) cp_wait<0>();      // no work here: retire the (empty) prefetch group
         }
     }
     stamp(p.n_phase);
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem, C_TMEM_COLS);
+    }
 }
 
 }  // namespace
@@ -518,9 +545,10 @@ int chain_init(ChainLauncher & cl, DType dt) {
 
 SplitGeom chain_geom_direct(int R, int N, int K) {
     SplitGeom g;
-    g.tiles = N / 32;
+    g.tiles = N / NT;
     g.kpt = K / CB;
-    g.G = ceil_div(R, CB) * g.tiles;          // virtual CTAs: one whole 64x32 tile each
+    (void) R;
+    g.G = g.tiles;                            // virtual CTAs: one whole R x 128 tile each
     g.U = g.G * g.kpt;
     g.maxc = 0;
     return g;
@@ -528,13 +556,13 @@ SplitGeom chain_geom_direct(int R, int N, int K) {
 
 SplitGeom chain_geom(int grid, int R, int N, int K, int min_units) {
     SplitGeom g;
-    g.tiles = N / CB;
+    g.tiles = N / NT;
     g.kpt = K / CB;
-    const int mblocks = ceil_div(R, CB);
-    g.U = mblocks * g.tiles * g.kpt;
+    (void) R;
+    g.U = g.tiles * g.kpt;
     g.G = std::max(1, std::min(grid, g.U / std::max(1, min_units)));
     g.maxc = 1;
-    for (int ot = 0; ot < mblocks * g.tiles; ++ot) {
+    for (int ot = 0; ot < g.tiles; ++ot) {
         const int first = (int) ((((long long) ot * g.kpt + 1) * g.G - 1) / g.U);
         const int last = (int) ((((long long) ot * g.kpt + g.kpt) * g.G - 1) / g.U);
         g.maxc = std::max(g.maxc, last - first + 1);
@@ -543,7 +571,8 @@ SplitGeom chain_geom(int grid, int R, int N, int K, int min_units) {
 }
 
 size_t chain_part_floats(const SplitGeom & g, int R) {
-    return (size_t) ceil_div(R, CB) * g.tiles * g.maxc * 4096;
+    (void) R;
+    return (size_t) g.tiles * g.maxc * SG_TILE_FLOATS;
 }
 
 bool chain_launch(ChainLauncher & cl, DType dt, ChainParams & p, cudaStream_t stream) {

@@ -10,18 +10,22 @@
 
 #include "common.cuh"
 #include "dec_kernels.h"
+#include "tc_gemm.h"
 
 namespace wb {
 
-// Stream-K geometry of one GEMM phase.  The (m-block, n-tile, k-block) space is flattened into U units of one 64x64x64
+// Stream-K geometry of one GEMM phase.  The (n-tile, k-block) space is flattened into U units of one 128 x 64
 // weight block each and cut into G equal contiguous ranges, one per CTA, so every SM streams the same number of weight
 // bytes whatever N and K are.  A CTA emits one f32 partial 64x64 tile per output tile its range touches; whoever consumes
 // the GEMM output (the residual/LayerNorm phase, the GELU phase, self-attention, the cross-attention kernel) adds the
 // partial tiles of a tile in contributor order -- fixed by this geometry alone, hence bit-reproducible and atomic-free.
+constexpr int SG_TILE_COLS = 128;                          // weight rows (= output columns) per tile
+constexpr int SG_TILE_FLOATS = 128 * SG_TILE_COLS;         // one partial tile: up to 128 token rows, f32 (rows >= R unused)
+
 struct SplitGeom {
-    int tiles = 0;      // N / 64
+    int tiles = 0;      // N / 128
     int kpt = 0;        // K / 64: k-blocks per output tile
-    int U = 0;          // m_blocks * tiles * kpt
+    int U = 0;          // tiles * kpt
     int G = 0;          // CTAs taking part
     int maxc = 0;       // partial-tile slots reserved per output tile
 };
@@ -32,12 +36,12 @@ __device__ __forceinline__ int sg_cta_of(const SplitGeom & g, int u) {      // C
 }
 // sum of the partial tiles of element quad (row r, columns col..col+3) of the GEMM output
 __device__ __forceinline__ float4 sg_load4(const SplitGeom & g, const float * __restrict__ part, int r, int col) {
-    const int ot = (r >> 6) * g.tiles + (col >> 6);
+    const int ot = col / SG_TILE_COLS;
     const int first = sg_cta_of(g, ot * g.kpt), last = sg_cta_of(g, ot * g.kpt + g.kpt - 1);
-    const float * p = part + ((size_t) ot * g.maxc) * 4096 + (r & 63) * 64 + (col & 63);
+    const float * p = part + ((size_t) ot * g.maxc) * SG_TILE_FLOATS + r * SG_TILE_COLS + (col % SG_TILE_COLS);
     float4 s = __ldcg(reinterpret_cast<const float4 *>(p));
     for (int j = 1; j <= last - first; ++j) {
-        const float4 v = __ldcg(reinterpret_cast<const float4 *>(p + (size_t) j * 4096));
+        const float4 v = __ldcg(reinterpret_cast<const float4 *>(p + (size_t) j * SG_TILE_FLOATS));
         s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
     return s;
@@ -49,11 +53,12 @@ struct SplitIn {
     const float * part = nullptr;
     const float * bias = nullptr;
     SplitGeom g;
+    unsigned long long * trace = nullptr;   // development aid: [0] start of CTA (0,0), [1] latest CTA end (%globaltimer)
 };
 
 enum ChainPhaseType : int {
     CP_ROW = 0,      // x[r] (+)= bias + partial sums (or token + position embedding), optional LayerNorm -> out16
-    CP_GEMM = 1,     // a[R][K] * w[N][K]^T: nt = 64 stream-K -> partial tiles; nt = 32 direct -> bias/scale/GELU -> out16
+    CP_GEMM = 1,     // a[R][K] * w[N][K]^T in 128-column tiles: stream-K -> partial tiles, or direct -> bias/scale/GELU -> out16
     CP_SELF = 3,     // masked self-attention over the row's own cache (+ K/V append); a = q | k | v rows [R][3d] 16-bit
 };
 
@@ -61,10 +66,10 @@ struct ChainPhase {
     int type = 0;
     int embed = 0;                 // CP_ROW: start from te[token] + pe[pos] instead of x
     int gelu = 0;                  // CP_GEMM direct
-    int nt = 64;                   // CP_GEMM: output tile width (64 stream-K, 32 direct)
+    int direct = 0;                // CP_GEMM: 0 stream-K -> partial tiles, 1 whole tiles -> bias / scale / GELU -> out16
     int N = 0, K = 0;              // CP_GEMM
-    const void * a = nullptr;  int lda = 0;     // CP_GEMM: activations; CP_SELF: q | k | v rows
-    const void * w = nullptr;  int ldw = 0;
+    int tm = 0;                    // CP_GEMM: ChainParams::tm[2*tm] = activations map, [2*tm+1] = weights map
+    const void * a = nullptr;  int lda = 0;     // CP_SELF: q | k | v rows
     SplitGeom g;                   // CP_GEMM: its own geometry; consumers: the producer's
     float * part = nullptr;        // partial tiles
     const float * bias = nullptr;
@@ -75,6 +80,7 @@ struct ChainPhase {
 };
 
 constexpr int CHAIN_MAX_PHASES = 12;
+constexpr int CHAIN_MAX_GEMMS = 6;
 
 struct ChainCommon {
     int R = 0, d = 0, H = 0, n_ctx = 0;
@@ -93,6 +99,7 @@ struct ChainParams {
     unsigned bar_base = 0;
     unsigned long long * trace = nullptr;   // development aid: [32] %globaltimer stamps of CTA 0 (phase starts, end, entry)
     ChainPhase ph[CHAIN_MAX_PHASES];
+    TMap tm[2 * CHAIN_MAX_GEMMS];        // TMA descriptors of the GEMM phases (activations, weights)
 };
 
 struct ChainLauncher {

@@ -11,6 +11,8 @@
 
 #include "dec_chain.h"
 
+#include <stdlib.h>
+
 namespace wb {
 
 namespace {
@@ -45,7 +47,16 @@ __global__ void kv_append_kernel(const uint4 * __restrict__ qkv, const DecRow * 
 // phantom keys; Q and K already carry dh^-0.25 each, src/whisper.cpp:2506-2557).  With fused_append the CTA first stores
 // this token's K/V head slice into the cache (single-token steps only: every sequence owns exactly one row, so no
 // other CTA needs the slice).
-template <typename T16, bool SELF>
+// 16-byte read of data that is streamed exactly once (cross K/V: 491 MB per launch): no L1 allocation.  With the default
+// path every in-flight line needs an L1 line, and after a kernel that configured the SM for ~200 KB of shared memory only
+// 28 KB of L1 are left -- measured: the same launch takes 115 us instead of 81 us behind the chain kernel.
+__device__ __forceinline__ uint4 ld_stream16(const uint4 * p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+template <typename T16, bool SELF, bool QSPLIT>
 __global__ void __launch_bounds__(128, 9)
 cross_attn_kernel(const T16 * __restrict__ q, int ldq, const DecRow * __restrict__ rows, int d, size_t layer_off, int T_in,
                   float kq_scale, int n_phantom, int fused_append, T16 * __restrict__ out, const SplitIn qs) {
@@ -59,6 +70,11 @@ cross_attn_kernel(const T16 * __restrict__ q, int ldq, const DecRow * __restrict
     // them in at once would squeeze this kernel's own occupancy, so the cross pass triggers after its K sweep.
     if (SELF) pdl_trigger();
     pdl_wait();
+    if (QSPLIT && qs.trace && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        qs.trace[0] = now;
+    }
     const DecRow row = rows[r];
     const int T = SELF ? row.pos + 1 : T_in;
     const T16 * kbase = (SELF ? reinterpret_cast<const T16 *>(row.self_kv) : reinterpret_cast<const T16 *>(row.cross_kv)) +
@@ -76,19 +92,19 @@ cross_attn_kernel(const T16 * __restrict__ q, int ldq, const DecRow * __restrict
     }
 
     float qv[8];
-    if (!SELF && qs.part) {
+    if (!SELF && QSPLIT) {
         // query straight from the partial tiles of the chain kernel's stream-K GEMM (dec_chain.h).  The 64 values of this
-        // head are one 64-wide tile: thread (quad, slot) adds the contributors slot, slot+8, ... of one float4, the eight
+        // head sit inside one tile: thread (quad, slot) adds the contributors slot, slot+8, ... of one float4, the eight
         // slot sums are combined in slot order (fixed, reproducible), bias added, rounded to 16 bits like the unfused path.
         float4 * s_q = reinterpret_cast<float4 *>(s_sc);              // [8 slots][16 quads], free until the K sweep
         {
             const int quad = tid & 15, slot = tid >> 4;
-            const int ot = (r >> 6) * qs.g.tiles + h;
+            const int ot = (h * 64) / SG_TILE_COLS;
             const int first = sg_cta_of(qs.g, ot * qs.g.kpt), last = sg_cta_of(qs.g, ot * qs.g.kpt + qs.g.kpt - 1);
-            const float * src = qs.part + ((size_t) ot * qs.g.maxc) * 4096 + (r & 63) * 64 + quad * 4;
+            const float * src = qs.part + ((size_t) ot * qs.g.maxc) * SG_TILE_FLOATS + r * SG_TILE_COLS + (h * 64) % SG_TILE_COLS + quad * 4;
             float4 a = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             for (int j = slot; j <= last - first; j += 8) {
-                const float4 v = __ldcg(reinterpret_cast<const float4 *>(src + (size_t) j * 4096));
+                const float4 v = __ldcg(reinterpret_cast<const float4 *>(src + (size_t) j * SG_TILE_FLOATS));
                 a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
             }
             s_q[slot * 16 + quad] = a;
@@ -127,7 +143,7 @@ cross_attn_kernel(const T16 * __restrict__ q, int ldq, const DecRow * __restrict
         for (int u = 0; u < U; ++u) {
             const int t = tb + 16 * u;
             const uint4 * src = reinterpret_cast<const uint4 *>(kbase + (size_t) t * ld + sub * 8);
-            kb[u] = t < T ? (SELF ? *src : __ldg(src)) : make_uint4(0, 0, 0, 0);
+            kb[u] = t < T ? (SELF ? *src : (QSPLIT ? ld_stream16(src) : __ldg(src))) : make_uint4(0, 0, 0, 0);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -178,7 +194,7 @@ cross_attn_kernel(const T16 * __restrict__ q, int ldq, const DecRow * __restrict
             const int t = tb + 16 * u;
             const bool ok = t < T;
             const uint4 * src = reinterpret_cast<const uint4 *>(vbase + (size_t) t * ld + sub * 8);
-            vb[u] = ok ? (SELF ? *src : __ldg(src)) : make_uint4(0, 0, 0, 0);
+            vb[u] = ok ? (SELF ? *src : (QSPLIT ? ld_stream16(src) : __ldg(src))) : make_uint4(0, 0, 0, 0);
             pr[u] = ok ? Half16<T16>::to_f(Half16<T16>::from_f(s_sc[t] * inv)) : 0.0f;
         }
 #pragma unroll
@@ -201,6 +217,11 @@ cross_attn_kernel(const T16 * __restrict__ q, int ldq, const DecRow * __restrict
     if (tid < 64) {
         const float v = s_o[0][tid] + s_o[1][tid] + s_o[2][tid] + s_o[3][tid];
         out[(size_t) r * d + h * 64 + tid] = Half16<T16>::from_f(v);
+    }
+    if (QSPLIT && qs.trace && tid == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        atomicMax(qs.trace + 1, now);
     }
 }
 
@@ -429,10 +450,10 @@ void dec_self_attn(DType dt, const void * qkv, const DecRow * d_rows, int R, int
     dim3 grid(R, n_head);
     const size_t smem = (size_t) n_ctx * sizeof(float);
     if (dt == DType::F16)
-        launch_pdl(cross_attn_kernel<__half, true>, grid, dim3(128), smem, st, reinterpret_cast<const __half *>(qkv), 3 * d,
+        launch_pdl(cross_attn_kernel<__half, true, false>, grid, dim3(128), smem, st, reinterpret_cast<const __half *>(qkv), 3 * d,
                    d_rows, d, layer_off_elems, 0, 1.0f, 0, fused_append ? 1 : 0, reinterpret_cast<__half *>(out), SplitIn{});
     else
-        launch_pdl(cross_attn_kernel<__nv_bfloat16, true>, grid, dim3(128), smem, st,
+        launch_pdl(cross_attn_kernel<__nv_bfloat16, true, false>, grid, dim3(128), smem, st,
                    reinterpret_cast<const __nv_bfloat16 *>(qkv), 3 * d, d_rows, d, layer_off_elems, 0, 1.0f, 0,
                    fused_append ? 1 : 0, reinterpret_cast<__nv_bfloat16 *>(out), SplitIn{});
     WB_CUDA(cudaGetLastError());
@@ -446,12 +467,21 @@ void dec_cross_attn(DType dt, const void * q, const DecRow * d_rows, int R, int 
     const float kq_scale = powf(64.0f, -0.25f);
     const size_t smem = (size_t) T * sizeof(float);
     if (dt == DType::F16)
-        launch_pdl(cross_attn_kernel<__half, false>, grid, dim3(128), smem, st, reinterpret_cast<const __half *>(q), d, d_rows,
-                   d, layer_off_elems, T, kq_scale, n_phantom, 0, reinterpret_cast<__half *>(out), qs);
+        if (q_split)
+            launch_pdl(cross_attn_kernel<__half, false, true>, grid, dim3(128), smem, st, reinterpret_cast<const __half *>(q), d,
+                       d_rows, d, layer_off_elems, T, kq_scale, n_phantom, 0, reinterpret_cast<__half *>(out), qs);
+        else
+            launch_pdl(cross_attn_kernel<__half, false, false>, grid, dim3(128), smem, st, reinterpret_cast<const __half *>(q), d,
+                       d_rows, d, layer_off_elems, T, kq_scale, n_phantom, 0, reinterpret_cast<__half *>(out), qs);
     else
-        launch_pdl(cross_attn_kernel<__nv_bfloat16, false>, grid, dim3(128), smem, st,
-                   reinterpret_cast<const __nv_bfloat16 *>(q), d, d_rows, d, layer_off_elems, T, kq_scale, n_phantom, 0,
-                   reinterpret_cast<__nv_bfloat16 *>(out), qs);
+        if (q_split)
+            launch_pdl(cross_attn_kernel<__nv_bfloat16, false, true>, grid, dim3(128), smem, st,
+                       reinterpret_cast<const __nv_bfloat16 *>(q), d, d_rows, d, layer_off_elems, T, kq_scale, n_phantom, 0,
+                       reinterpret_cast<__nv_bfloat16 *>(out), qs);
+        else
+            launch_pdl(cross_attn_kernel<__nv_bfloat16, false, false>, grid, dim3(128), smem, st,
+                       reinterpret_cast<const __nv_bfloat16 *>(q), d, d_rows, d, layer_off_elems, T, kq_scale, n_phantom, 0,
+                       reinterpret_cast<__nv_bfloat16 *>(out), qs);
     WB_CUDA(cudaGetLastError());
 }
 

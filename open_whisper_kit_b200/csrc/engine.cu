@@ -534,8 +534,30 @@ bool Engine::decode_chain(const std::vector<DecRow> & rows, const std::vector<in
     double self_bytes = 0.0;
     for (const auto & rw : rows) self_bytes += (double) (rw.pos + 1) * 2 * d * 2.0;
 
+    // TMA descriptors: the three GEMM inputs of this call, and (cached) one per weight matrix
+    const int box_x = R <= 64 ? 64 : 128;
+    TMap tm_h16, tm_att, tm_mlp;
+    if (!tc_make_tmap(&tm_h16, h16, R, d, d, box_x, dt) || !tc_make_tmap(&tm_att, att, R, d, d, box_x, dt) ||
+        !tc_make_tmap(&tm_mlp, mlp, R, 4 * d, 4 * d, box_x, dt)) return false;
+    if (chain_wmaps.empty()) {
+        chain_wmaps.resize((size_t) L * 6);
+        for (int il = 0; il < L; ++il) {
+            const DecLayer & Lr = model.dec[il];
+            TMap * m = &chain_wmaps[(size_t) il * 6];
+            if (!tc_make_tmap(&m[0], Lr.wqkv, 3 * d, d, d, 128, dt) || !tc_make_tmap(&m[1], Lr.wo, d, d, d, 128, dt) ||
+                !tc_make_tmap(&m[2], Lr.wxq, d, d, d, 128, dt) || !tc_make_tmap(&m[3], Lr.wxo, d, d, d, 128, dt) ||
+                !tc_make_tmap(&m[4], Lr.w1, 4 * d, d, d, 128, dt) || !tc_make_tmap(&m[5], Lr.w2, d, 4 * d, 4 * d, 128, dt)) {
+                chain_wmaps.clear();
+                return false;
+            }
+        }
+    }
+    enum { W_QKV = 0, W_O, W_XQ, W_XO, W_1, W_2 };
+
     ChainParams cp;
+    int n_gemm = 0;
     auto reset = [&]() {
+        n_gemm = 0;
         cp = ChainParams();
         cp.c.R = R; cp.c.d = d; cp.c.H = H; cp.c.n_ctx = n_ctx; cp.c.eps = hp.eps; cp.c.ref_f16_gelu = dt == DType::F16 ? 1 : 0;
         cp.c.x = x; cp.c.rows = d_rows; cp.c.te = model.d_te; cp.c.pe = model.d_pe;
@@ -548,15 +570,17 @@ bool Engine::decode_chain(const std::vector<DecRow> & rows, const std::vector<in
         ph.bias = bias; ph.ln_w = lw; ph.ln_b = lb; ph.out16 = out16; ph.ldo16 = d;
         chain_bytes += (double) R * d * 10.0;
     };
-    auto add_gemm = [&](const SplitGeom & g, const void * a, int K, const void * w, int N) {      // stream-K -> partial tiles
+    auto add_gemm = [&](const SplitGeom & g, const TMap & ta, int K, const TMap & tw, int N) {      // stream-K -> partial tiles
         ChainPhase & ph = cp.ph[cp.n_phase++];
-        ph.type = CP_GEMM; ph.nt = 64; ph.N = N; ph.K = K; ph.a = a; ph.lda = K; ph.w = w; ph.ldw = K; ph.g = g; ph.part = part;
+        ph.type = CP_GEMM; ph.direct = 0; ph.N = N; ph.K = K; ph.g = g; ph.part = part;
+        ph.tm = n_gemm; cp.tm[2 * n_gemm] = ta; cp.tm[2 * n_gemm + 1] = tw; ++n_gemm;
         chain_bytes += ((double) N * K + (double) R * K) * 2.0;
     };
-    auto add_gemm_direct = [&](const SplitGeom & g, const void * a, int K, const void * w, int N, const float * bias, float scale,
+    auto add_gemm_direct = [&](const SplitGeom & g, const TMap & ta, int K, const TMap & tw, int N, const float * bias, float scale,
                                int scale_cols, bool gelu, void * out16) {
         ChainPhase & ph = cp.ph[cp.n_phase++];
-        ph.type = CP_GEMM; ph.nt = 32; ph.N = N; ph.K = K; ph.a = a; ph.lda = K; ph.w = w; ph.ldw = K; ph.g = g;
+        ph.type = CP_GEMM; ph.direct = 1; ph.N = N; ph.K = K; ph.g = g;
+        ph.tm = n_gemm; cp.tm[2 * n_gemm] = ta; cp.tm[2 * n_gemm + 1] = tw; ++n_gemm;
         ph.bias = bias; ph.scale = scale; ph.scale_cols = scale_cols; ph.gelu = gelu ? 1 : 0; ph.out16 = out16; ph.ldo16 = N;
         chain_bytes += ((double) N * K + (double) R * (K + N)) * 2.0;
     };
@@ -568,22 +592,25 @@ bool Engine::decode_chain(const std::vector<DecRow> & rows, const std::vector<in
     // QKV -> self-attention -> out-projection -> residual + LayerNorm -> cross query of layer il (h16 = LayerNorm(x) on entry)
     auto add_attn_half = [&](int il) {
         const DecLayer & Lr = model.dec[il];
-        add_gemm_direct(g_qkv, h16, d, Lr.wqkv, 3 * d, Lr.bqkv, qk_scale, 2 * d, false, qkv);
+        const TMap * wm = &chain_wmaps[(size_t) il * 6];
+        add_gemm_direct(g_qkv, tm_h16, d, wm[W_QKV], 3 * d, Lr.bqkv, qk_scale, 2 * d, false, qkv);
         add_self(il);
-        add_gemm(g_dd, att, d, Lr.wo, d);
+        add_gemm(g_dd, tm_att, d, wm[W_O], d);
         add_row(&g_dd, Lr.bo, Lr.lnx_w, Lr.lnx_b, h16, false);
-        add_gemm(g_dd, h16, d, Lr.wxq, d);
+        add_gemm(g_dd, tm_h16, d, wm[W_XQ], d);
     };
     // cross out-projection -> residual + LayerNorm -> MLP of layer il; the closing residual/LayerNorm row phase is added by the caller
     auto add_mlp_half = [&](int il) {
         const DecLayer & Lr = model.dec[il];
-        add_gemm(g_dd, att, d, Lr.wxo, d);
+        const TMap * wm = &chain_wmaps[(size_t) il * 6];
+        add_gemm(g_dd, tm_att, d, wm[W_XO], d);
         add_row(&g_dd, Lr.bxo, Lr.ln2_w, Lr.ln2_b, h16, false);
-        add_gemm_direct(g_m1, h16, d, Lr.w1, 4 * d, Lr.b1, 1.0f, 0, true, mlp);
-        add_gemm(g_m2, mlp, 4 * d, Lr.w2, d);
+        add_gemm_direct(g_m1, tm_h16, d, wm[W_1], 4 * d, Lr.b1, 1.0f, 0, true, mlp);
+        add_gemm(g_m2, tm_mlp, 4 * d, wm[W_2], d);
     };
     static const bool trace_on = getenv("WHISPER_B200_CHAIN_TRACE") != nullptr;
     if (trace_on && !chain_trace.reserve((size_t) (L + 1) * 32 * 8)) return false;
+    if (trace_on) WB_CUDA(cudaMemsetAsync(chain_trace.p, 0, (size_t) (L + 1) * 32 * 8, stream));
     int launch_idx = 0;
     bool ok = true;
     auto launch = [&]() {
@@ -610,6 +637,7 @@ bool Engine::decode_chain(const std::vector<DecRow> & rows, const std::vector<in
         if (il < L) {
             SplitIn qs;
             qs.part = part; qs.bias = model.dec[il].bxq; qs.g = g_dd;
+            if (trace_on) qs.trace = (unsigned long long *) chain_trace.p + 32 * il + 27;
             prof_begin(PC_CROSS_ATTN, (double) R * 1500.0 * 2 * d * 2.0);
             dec_cross_attn(dt, nullptr, d_rows, R, d, H, il * cross_layer_stride, 1500, n_phantom(), att, stream, &qs);
             prof_end();
@@ -642,13 +670,22 @@ bool Engine::decode_chain(const std::vector<DecRow> & rows, const std::vector<in
             for (int i = 0; i < 10; ++i) chain_trace_acc[i] += (double) (t[i + 1] - t[i]) * 1e-3;
             chain_trace_acc[10] += (double) (t[0] - t[15]) * 1e-3;                   // entry -> first phase (PDL wait)
             chain_trace_acc[11] += (double) (t[15] - (t - 32)[l == 1 ? 6 : 10]) * 1e-3;   // previous chain end -> entry
+            chain_trace_acc[12] += (double) ((t - 32)[27] - (t - 32)[l == 1 ? 6 : 10]) * 1e-3;   // previous chain end -> cross start
+            chain_trace_acc[13] += (double) ((t - 32)[28] - (t - 32)[27]) * 1e-3;                 // cross kernel, first start -> last end
+            chain_trace_acc[14] += (double) ((long long) t[15] - (long long) (t - 32)[28]) * 1e-3;   // cross end -> chain entry (negative: overlapped)
         }
         chain_trace_steps += L - 1;
         if (chain_trace_steps % ((L - 1) * 20) == 0) {
-            static const char * names[12] = {"xO", "row", "mlp1", "mlp2", "row", "qkv", "self", "O", "row", "xQ", "wait", "gap(cross)"};
+            static const char * names[15] = {"xO", "row", "mlp1", "mlp2", "row", "qkv", "self", "O", "row", "xQ", "wait", "gap(cross)",
+                                             "end->cross", "cross", "cross->entry"};
             fprintf(stderr, "chain trace (us, R=%d):", R);
-            for (int i = 0; i < 12; ++i) fprintf(stderr, " %s %.2f", names[i], chain_trace_acc[i] / chain_trace_steps);
+            for (int i = 0; i < 15; ++i) fprintf(stderr, " %s %.2f", names[i], chain_trace_acc[i] / chain_trace_steps);
             fprintf(stderr, "  pdl=%d\n", chain.pdl_ok ? 1 : 0);
+            {
+                const unsigned long long * t = h.data() + 32 * (L / 2);
+                fprintf(stderr, "   qkv phase, CTA 0 (cycles): producer waited for free stages %llu of %llu; MMA issuer waited for data %llu of %llu\n",
+                        t[20], t[21], t[22], t[23]);
+            }
         }
     }
     if (!ok) wlog(GGML_LOG_LEVEL_ERROR, "%s: chain launch failed\n", __func__);

@@ -86,6 +86,7 @@ struct Engine {
     DeviceBlock embd_enc32;    // f32 [windows*1500][d] of the last encode when requested
     ChainLauncher chain;       // persistent single-token decoder-step kernel (dec_chain.cu)
     DeviceBlock chain_part;    // its stream-K partial tiles
+    std::vector<TMap> chain_wmaps;   // TMA descriptors of the decoder weights, [layer][qkv, o, xq, xo, w1, w2]
     int chain_mode = -1;       // -1 undecided, 0 off (WHISPER_B200_CHAIN=0 or unsupported geometry), 1 on
     int chain_min_units = 2;
     DeviceBlock chain_trace;   // WHISPER_B200_CHAIN_TRACE=1: per-phase device timestamps of the chain launches

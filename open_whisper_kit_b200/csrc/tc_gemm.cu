@@ -347,6 +347,11 @@ template <int BN, typename T16> void launch(const GemmArgs & g, const EpiParams 
 
 }  // namespace
 
+bool tc_make_tmap(TMap * tm, const void * base, int rows, int cols, int ld_elems, int box_rows, DType dt) {
+    static_assert(sizeof(TMap) == sizeof(CUtensorMap), "TMap must mirror CUtensorMap");
+    return make_tmap(reinterpret_cast<CUtensorMap *>(tm), base, rows, cols, ld_elems, box_rows, dt);
+}
+
 bool tc_gemm(const GemmArgs & g, cudaStream_t stream) {
     if (g.M <= 0 || g.N <= 0 || g.K <= 0) return true;
     // TMA needs 16-byte aligned bases and row pitches; the epilogue's vector stores need aligned leading dims.

@@ -26,4 +26,11 @@ struct GemmArgs {
 // Returns false when the arguments violate the kernel's alignment contract or the launch failed.
 bool tc_gemm(const GemmArgs & g, cudaStream_t stream);
 
+// A CUtensorMap by another name (keeps <cuda.h> out of the headers): 2-D tiled map over a row-major 16-bit matrix
+// [rows][ld_elems] with a box of box_rows x 64 elements and the 128-byte swizzle (the layout tcgen05 descriptors expect).
+struct alignas(64) TMap {
+    unsigned char bytes[128];
+};
+bool tc_make_tmap(TMap * tm, const void * base, int rows, int cols, int ld_elems, int box_rows, DType dt);
+
 }  // namespace wb
