@@ -28,4 +28,9 @@ void layernorm(DType dt, const float * x, int ldx, const float * gamma, const fl
 void enc_attention(DType dt, const void * qkv, void * out, int n_windows, int T, int d, int n_head, int n_phantom,
                    cudaStream_t st);
 
+// The same attention on tcgen05 / TMEM (enc_attn_tc.cu); vt_scratch holds V^T, enc_attention_tc_scratch_bytes() bytes.
+size_t enc_attention_tc_scratch_bytes(int n_windows, int T, int n_head);
+bool enc_attention_tc(DType dt, const void * qkv, void * out, void * vt_scratch, int n_windows, int T, int d, int n_head,
+                      int n_phantom, cudaStream_t st);
+
 }  // namespace wb

@@ -223,6 +223,9 @@ bool Engine::encode(const std::vector<EncJob> & jobs, CrossKV & kv, int win0, bo
     auto sz = [&](size_t b) { need += round_up<size_t>(b, 256); return b; };
     sz(M1 * k1 * 2); sz(M1 * d * 2); sz(M * 3 * d * 2); sz(M * d * 4); sz(M * d * 2); sz(M * 3 * d * 2); sz(M * d * 2);
     sz(M * 4 * d * 2); sz(M * d * 2); sz(W * sizeof(EncWindow));
+    static const bool legacy_attn = getenv("WHISPER_B200_ENC_ATTN") && !strcmp(getenv("WHISPER_B200_ENC_ATTN"), "legacy");
+    const size_t vt_bytes = legacy_attn ? 0 : enc_attention_tc_scratch_bytes(W, T, H);
+    sz(vt_bytes);
     if (!ws.begin(need)) return false;
     void * A1 = ws.take(M1 * k1 * 2);
     void * act1 = ws.take(M1 * d * 2);
@@ -234,6 +237,7 @@ bool Engine::encode(const std::vector<EncJob> & jobs, CrossKV & kv, int win0, bo
     void * mlp = ws.take(M * 4 * d * 2);
     void * enc16 = ws.take(M * d * 2);
     EncWindow * d_wins = (EncWindow *) ws.take(W * sizeof(EncWindow));
+    void * vt = vt_bytes ? ws.take(vt_bytes) : nullptr;
 
     std::vector<EncWindow> wins(W);
     for (int i = 0; i < W; ++i) {
@@ -294,9 +298,14 @@ bool Engine::encode(const std::vector<EncJob> & jobs, CrossKV & kv, int win0, bo
             gemm(g);
         }
         prof_begin(PC_ENC_ATTN, 4.0 * (double) W * T * (double) T * d);
-        enc_attention(dt, qkv, att, W, T, d, H, n_phantom(), stream);
+        if (legacy_attn) {
+            enc_attention(dt, qkv, att, W, T, d, H, n_phantom(), stream);
+            n_kernel_launches += 1;
+        } else {
+            ok = ok && enc_attention_tc(dt, qkv, att, vt, W, T, d, H, n_phantom(), stream);
+            n_kernel_launches += 2;
+        }
         prof_end();
-        n_kernel_launches += 1;
         {
             GemmArgs g;
             g.dtype = dt; g.M = (int) M; g.N = d; g.K = d; g.a = att; g.lda = d; g.w = L.wo; g.ldw = d;

@@ -352,6 +352,20 @@ bool tc_make_tmap(TMap * tm, const void * base, int rows, int cols, int ld_elems
     return make_tmap(reinterpret_cast<CUtensorMap *>(tm), base, rows, cols, ld_elems, box_rows, dt);
 }
 
+bool tc_make_tmap3d(TMap * tm, const void * base, size_t d0, size_t d1, size_t d2, size_t stride1_bytes, size_t stride2_bytes,
+                    int box0, int box1, DType dt) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[3] = {(cuuint64_t) d0, (cuuint64_t) d1, (cuuint64_t) d2};
+    cuuint64_t strides[2] = {(cuuint64_t) stride1_bytes, (cuuint64_t) stride2_bytes};
+    cuuint32_t box[3] = {(cuuint32_t) box0, (cuuint32_t) box1, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(reinterpret_cast<CUtensorMap *>(tm), dt == DType::F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                    3, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
 bool tc_gemm(const GemmArgs & g, cudaStream_t stream) {
     if (g.M <= 0 || g.N <= 0 || g.K <= 0) return true;
     // TMA needs 16-byte aligned bases and row pitches; the epilogue's vector stores need aligned leading dims.

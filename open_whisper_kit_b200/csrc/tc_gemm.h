@@ -32,5 +32,8 @@ struct alignas(64) TMap {
     unsigned char bytes[128];
 };
 bool tc_make_tmap(TMap * tm, const void * base, int rows, int cols, int ld_elems, int box_rows, DType dt);
+// 3-D variant: dims {d0 (contiguous), d1, d2}, byte strides of d1 and d2, box {box0, box1, 1}, 128-byte swizzle.
+bool tc_make_tmap3d(TMap * tm, const void * base, size_t d0, size_t d1, size_t d2, size_t stride1_bytes, size_t stride2_bytes,
+                    int box0, int box1, DType dt);
 
 }  // namespace wb
