@@ -69,6 +69,15 @@ cross_attn_kernel(const T16 * __restrict__ q, int ldq, const DecRow * __restrict
     // The successor is the next chain / GEMM launch, whose CTAs hold ~100 KB of shared memory while they wait: letting
     // them in at once would squeeze this kernel's own occupancy, so the cross pass triggers after its K sweep.
     if (SELF) pdl_trigger();
+    if (!SELF) {
+        // The cross K/V and the row descriptors were written before this decoder call began (encoder stage, H2D copy), so
+        // they may be touched before the grid dependency resolves: pull the first batch of keys into L2 meanwhile.
+        const DecRow row0 = rows[r];
+        const T16 * kb0 = reinterpret_cast<const T16 *>(row0.cross_kv) + layer_off + h * 64 + (size_t) (warp * 4 + grp) * (2 * d) + sub * 8;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (warp * 4 + grp + 16 * u < T_in) asm volatile("prefetch.global.L2 [%0];" ::"l"(kb0 + (size_t) (16 * u) * (2 * d)));
+    }
     pdl_wait();
     if (QSPLIT && qs.trace && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
         unsigned long long now;

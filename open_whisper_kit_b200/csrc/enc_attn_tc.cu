@@ -10,9 +10,10 @@
 //                      maps, so rows past T inside a window are out of bounds = zero-filled;
 //   warp 5 (one lane): MMA issuer   -- S = Q K^T (4 x tcgen05.mma 128x128x16) into TMEM, then, once the softmax warps have
 //                      published P in shared memory, PV = P V (8 x tcgen05.mma 128x64x16) into a second TMEM buffer;
-//   warps 0-3: softmax, one query row per thread (tcgen05.ld 32x32b gives a thread its own row): row max, exp2, P as 16-bit
-//              into the 128-byte-swizzled A-operand layout, running max / sum, O kept in registers and rescaled there
-//              (O = O * corr + PV read back from TMEM) -- no read-modify-write of TMEM.
+//   warps 0-7: softmax, two threads per query row (tcgen05.ld 32x32b gives a thread its own row; warps w and w+4 may read
+//              the same 32 lanes and take 64 score columns each): row max, exp2, P as 16-bit into the 128-byte-swizzled
+//              A-operand layout, running max / sum, O kept in registers and rescaled there (O = O * corr + PV read back
+//              from TMEM) -- no read-modify-write of TMEM.
 // V is consumed as V^T (K-major B operand), produced by a small transpose kernel per layer.
 #include "enc_kernels.h"
 
@@ -25,7 +26,7 @@ namespace wb {
 
 namespace {
 
-constexpr int FA_THREADS = 192;
+constexpr int FA_THREADS = 320;     // 8 softmax warps (two threads per query row) + TMA producer + MMA issuer
 constexpr int FA_BQ = 128, FA_BK = 128, FA_DH = 64;
 constexpr int FA_TILE_BYTES = 128 * 128;                // 128 rows x 64 x 16-bit
 constexpr int FA_OFF_Q = 0, FA_OFF_K = FA_TILE_BYTES, FA_OFF_V = 3 * FA_TILE_BYTES, FA_OFF_P = 4 * FA_TILE_BYTES;
@@ -78,6 +79,7 @@ enc_attn_tc_kernel(const __grid_constant__ TMap tm_qk, const __grid_constant__ T
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t b_q, b_kfull[2], b_kempty[2], b_vfull, b_vempty, b_s, b_p, b_pv;
     __shared__ uint32_t s_tmem;
+    __shared__ float s_mx[2][2][FA_BQ];      // [tile parity][column half][row]: row maxima exchanged between the two halves
     uint8_t * smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * FA_BQ, head = blockIdx.y, win = blockIdx.z;
@@ -92,7 +94,7 @@ enc_attn_tc_kernel(const __grid_constant__ TMap tm_qk, const __grid_constant__ T
         ptx::mbar_init(&b_vfull, 1);
         ptx::mbar_init(&b_vempty, 1);
         ptx::mbar_init(&b_s, 1);
-        ptx::mbar_init(&b_p, 128);
+        ptx::mbar_init(&b_p, 256);
         ptx::mbar_init(&b_pv, 1);
         ptx::fence_mbar_init();
     }
@@ -105,7 +107,7 @@ enc_attn_tc_kernel(const __grid_constant__ TMap tm_qk, const __grid_constant__ T
     ptx::tc_fence_after();
     const uint32_t tmem = s_tmem;
 
-    if (warp == 4) {
+    if (warp == 8) {
         // ===== TMA producer =====
         if (lane == 0) {
             ptx::prefetch_tensormap(&tm_qk);
@@ -124,30 +126,34 @@ enc_attn_tc_kernel(const __grid_constant__ TMap tm_qk, const __grid_constant__ T
                 ptx::tma_load_3d(vs + FA_TILE_BYTES / 2, &tm_vt, &b_vfull, j * FA_BK + 64, 0, win * H + head);
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == 9) {
         // ===== MMA issuer =====
+        // Order per tile: (P_j published) -> S_{j+1} first, then PV_j.  Issuing a tcgen05.mma costs ~150 cycles whatever its
+        // shape, PV is 8 of them: with S_{j+1} ahead of PV_j the softmax warps start on tile j+1 while PV_j is still being
+        // issued, and only need PV_j when they come to rescale O.
         if (lane == 0) {
             const uint32_t idesc_s = ptx::make_idesc_f16(Half16<T16>::kind, 128, FA_BK);
             const uint32_t idesc_pv = ptx::make_idesc_f16(Half16<T16>::kind, 128, FA_DH);
             const uint64_t dq = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + FA_OFF_Q));
             const uint64_t dp = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + FA_OFF_P));
-            fa_wait(&b_q, 0);
-            for (int j = 0; j < n_tiles; ++j) {
+            const uint64_t dv = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + FA_OFF_V));
+            auto issue_s = [&](int j) {
                 const int s = j & 1;
-                const uint32_t ph = (j >> 1) & 1;
-                // S = Q K^T.  The S buffer is free: the softmax warps published P (tile j-1) after their last read of it.
-                fa_wait(&b_kfull[s], ph);
+                fa_wait(&b_kfull[s], (j >> 1) & 1);
                 ptx::tc_fence_after();
                 const uint64_t dk = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + FA_OFF_K + s * FA_TILE_BYTES));
 #pragma unroll
                 for (int k = 0; k < 4; ++k) ptx::umma_f16(tmem, dq + (uint64_t) (2 * k), dk + (uint64_t) (2 * k), idesc_s, (uint32_t) (k != 0));
                 ptx::umma_commit(&b_kempty[s]);
                 ptx::umma_commit(&b_s);
-                // PV = P V  (keys are the reduction dimension: 2 k-blocks of 64)
-                fa_wait(&b_p, j & 1);
+            };
+            fa_wait(&b_q, 0);
+            issue_s(0);
+            for (int j = 0; j < n_tiles; ++j) {
+                fa_wait(&b_p, j & 1);               // P_j is in shared memory; S_j and PV_{j-1} have been read back
+                if (j + 1 < n_tiles) issue_s(j + 1);
                 fa_wait(&b_vfull, j & 1);
                 ptx::tc_fence_after();
-                const uint64_t dv = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + FA_OFF_V));
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     // k-block = k / 4 (P: 16 KB apart, V^T: 8 KB apart, in 16-byte units), 16-key step inside it = k % 4
@@ -160,26 +166,27 @@ enc_attn_tc_kernel(const __grid_constant__ TMap tm_qk, const __grid_constant__ T
             }
         }
     } else {
-        // ===== softmax: thread = query row =====
-        const int row = warp * 32 + lane;                               // TMEM lane and row inside the tile
-        const uint32_t t_lane = tmem + ((uint32_t) (warp * 32) << 16);
-        uint8_t * prow = smem + FA_OFF_P + row * 128;
-        float o[FA_DH];
+        // ===== softmax: two threads per query row (warps w and w+4 read the same 32 TMEM lanes), 64 score columns each =====
+        const int quarter = warp & 3, half = warp >> 2;
+        const int row = quarter * 32 + lane;                            // TMEM lane and row inside the tile
+        const uint32_t t_lane = tmem + ((uint32_t) (quarter * 32) << 16);
+        uint8_t * prow = smem + FA_OFF_P + half * FA_TILE_BYTES + row * 128;       // this thread's k-block of P
+        float o[32];
 #pragma unroll
-        for (int i = 0; i < FA_DH; ++i) o[i] = 0.0f;
-        float m_run = -INFINITY, l_run = 0.0f;
+        for (int i = 0; i < 32; ++i) o[i] = 0.0f;
+        float m_run = -INFINITY, l_run = 0.0f, corr_prev = 0.0f;
 #pragma unroll 1
         for (int j = 0; j < n_tiles; ++j) {
             fa_wait(&b_s, j & 1);
             ptx::tc_fence_after();
-            const int key0 = j * FA_BK;
-            const bool edge = key0 + FA_BK > T;
-            // pass 1: row maximum of the raw scores
+            const int key0 = j * FA_BK + half * 64;
+            const bool edge = key0 + 64 > T;
+            // pass 1: maximum of this thread's 64 raw scores, then of the whole row
             float mx = -INFINITY;
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < 2; ++c) {
                 uint32_t r[32];
-                ptx::tmem_ld_32x32(t_lane + (uint32_t) (c * 32), r);
+                ptx::tmem_ld_32x32(t_lane + (uint32_t) (half * 64 + c * 32), r);
                 ptx::tmem_ld_wait();
                 if (edge) {
 #pragma unroll
@@ -190,15 +197,29 @@ enc_attn_tc_kernel(const __grid_constant__ TMap tm_qk, const __grid_constant__ T
                     for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
                 }
             }
+            s_mx[j & 1][half][row] = mx;
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");      // the two warps that share these rows
+            mx = fmaxf(mx, s_mx[j & 1][half ^ 1][row]);
             const float m_new = fmaxf(m_run, mx);
             const float corr = ex2((m_run - m_new) * scale_log2e);       // m_run = -inf on the first tile -> 0
             const float mb = m_new * scale_log2e;
-            // pass 2: P = exp2(s * scale - m), 16-bit, into the swizzled A-operand layout (k-block = 64 keys)
+            // O = O * corr + P V of the previous tile (its MMAs were issued behind this tile's S)
+            if (j > 0) {
+                fa_wait(&b_pv, (j - 1) & 1);
+                ptx::tc_fence_after();
+                uint32_t r[32];
+                ptx::tmem_ld_32x32(t_lane + 128u + (uint32_t) (half * 32), r);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o[i] = fmaf(o[i], corr_prev, __uint_as_float(r[i]));
+            }
+            corr_prev = corr;
+            // pass 2: P = exp2(s * scale - m), 16-bit, into the swizzled A-operand layout (this thread: one 128-byte row)
             float rs = 0.0f;
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < 2; ++c) {
                 uint32_t r[32];
-                ptx::tmem_ld_32x32(t_lane + (uint32_t) (c * 32), r);
+                ptx::tmem_ld_32x32(t_lane + (uint32_t) (half * 64 + c * 32), r);
                 ptx::tmem_ld_wait();
                 uint32_t pk[16];
 #pragma unroll
@@ -212,11 +233,10 @@ enc_attn_tc_kernel(const __grid_constant__ TMap tm_qk, const __grid_constant__ T
                     rs += p0 + p1;
                     pk[i >> 1] = pack2<T16>(p0, p1);
                 }
-                uint8_t * dst = prow + (c >> 1) * FA_TILE_BYTES;           // k-block
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const int chunk = (c & 1) * 4 + q;                      // 16-byte chunk inside the 128-byte row
-                    *reinterpret_cast<uint4 *>(dst + ((chunk ^ (row & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                    const int chunk = c * 4 + q;                            // 16-byte chunk inside the 128-byte row
+                    *reinterpret_cast<uint4 *>(prow + ((chunk ^ (row & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
                 }
             }
             l_run = l_run * corr + rs;
@@ -224,21 +244,21 @@ enc_attn_tc_kernel(const __grid_constant__ TMap tm_qk, const __grid_constant__ T
             ptx::fence_proxy_async_smem();           // P was written through the generic proxy; the tensor core reads it through the async one
             ptx::tc_fence_before();
             ptx::mbar_arrive(&b_p);
-            // O = O * corr + P V
-            fa_wait(&b_pv, j & 1);
+        }
+        {   // last tile's P V
+            fa_wait(&b_pv, (n_tiles - 1) & 1);
             ptx::tc_fence_after();
+            uint32_t r[32];
+            ptx::tmem_ld_32x32(t_lane + 128u + (uint32_t) (half * 32), r);
+            ptx::tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t r[32];
-                ptx::tmem_ld_32x32(t_lane + 128u + (uint32_t) (c * 32), r);
-                ptx::tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) o[c * 32 + i] = fmaf(o[c * 32 + i], corr, __uint_as_float(r[i]));
-            }
+            for (int i = 0; i < 32; ++i) o[i] = fmaf(o[i], corr_prev, __uint_as_float(r[i]));
             ptx::tc_fence_before();
         }
-        // phantom keys (score 0, value 0), normalise, store
-        float f = 1.0f, l = l_run;
+        // row sum over both halves, phantom keys (score 0, value 0), normalise, store this thread's 32 of the 64 values
+        s_mx[0][half][row] = l_run;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+        float l = l_run + s_mx[0][half ^ 1][row], f = 1.0f;
         if (n_phantom > 0) {
             const float m_new = fmaxf(m_run, 0.0f);
             f = ex2((m_run - m_new) * scale_log2e);
@@ -247,9 +267,9 @@ enc_attn_tc_kernel(const __grid_constant__ TMap tm_qk, const __grid_constant__ T
         const float inv = f / l;
         const int q = q0 + row;
         if (q < T) {
-            T16 * orow = out + ((size_t) win * T + q) * (size_t) d + head * FA_DH;
+            T16 * orow = out + ((size_t) win * T + q) * (size_t) d + head * FA_DH + half * 32;
 #pragma unroll
-            for (int i = 0; i < FA_DH; i += 8) {
+            for (int i = 0; i < 32; i += 8) {
                 *reinterpret_cast<uint4 *>(orow + i) =
                     make_uint4(pack2<T16>(o[i] * inv, o[i + 1] * inv), pack2<T16>(o[i + 2] * inv, o[i + 3] * inv),
                                pack2<T16>(o[i + 4] * inv, o[i + 5] * inv), pack2<T16>(o[i + 6] * inv, o[i + 7] * inv));
