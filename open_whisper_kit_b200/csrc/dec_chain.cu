@@ -12,6 +12,8 @@
 // for both tile widths, accumulators small enough to finish from registers (no cross-warp reduction), rolled loops.
 #include "dec_chain.h"
 
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "ptx.cuh"
@@ -25,12 +27,15 @@ constexpr int CB = 64;                                 // K per stage; weight ti
 // producer, warp 5: MMA issuer; all six run the row / self-attention phases
 constexpr int C_THREADS = 192;
 constexpr int C_WARPS = C_THREADS / 32;
-// Ring geometry depends on the row count: R <= 64 -> 4 stages of (8 KB activations + 16 KB weights), else 3 stages of
+// Ring geometry depends on the row count: R <= 64 -> 3 stages of (8 KB activations + 16 KB weights), else 2 stages of
 // (16 KB + 16 KB).  The A descriptor always spans 128 rows = 16 KB from the start of the activation tile; with 64 live rows
 // the upper half of that span is the start of the stage's own weight tile, i.e. harmless stale rows.
-constexpr int C_RING_BYTES = 96 * 1024;
+constexpr int C_RING_BYTES = 72 * 1024;
 constexpr int C_MAX_STAGES = 6;
-constexpr int C_SMEM = C_RING_BYTES + 1024;            // 97 KB incl. alignment slack -> two CTAs per SM
+// 73 KB incl. alignment slack: two CTAs per SM inside the 164 KB shared-memory carve-out.  A larger ring would push the SM
+// to the 228 KB carve-out, and the kernels that run between chain launches keep whatever carve-out they find: the
+// cross-attention kernel was measured at 115 us with the 28 KB of L1 that leaves, against 82 us normally.
+constexpr int C_SMEM = C_RING_BYTES + 1024;
 // Weight tile = 128 rows: issuing one tcgen05.mma costs ~150 cycles whatever its N (measured), so a unit should carry as
 // many weight rows as the tile count of the smallest GEMM allows.
 constexpr int NT = 128;
@@ -335,7 +340,7 @@ dec_chain_kernel(const __grid_constant__ ChainParams p) {
     ptx::tc_fence_after();
     const uint32_t tmem = s_tmem;
 
-    const unsigned S = R <= 64 ? 4u : 3u;
+    const unsigned S = R <= 64 ? 3u : 2u;
     const uint32_t x_bytes = R <= 64 ? 8192u : 16384u, stage_bytes = x_bytes + NT * 128u;
     auto stage_ptr = [&](unsigned gc) { return smem + (gc % S) * stage_bytes; };
     const bool is_producer = warp == 4 && lane == 0, is_mma = warp == 5 && lane == 0;
@@ -593,6 +598,13 @@ bool chain_launch(ChainLauncher & cl, DType dt, ChainParams & p, cudaStream_t st
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     void * args[] = {(void *) &p};
+    static const bool no_coop = getenv("WHISPER_B200_CHAIN_COOP") && atoi(getenv("WHISPER_B200_CHAIN_COOP")) == 0;
+    if (no_coop) {      // development aid: plain launch (co-residency then rests on nothing else running on the device)
+        cfg.attrs = attr + 1;
+        cfg.numAttrs = 1;
+        WB_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
+        return !cuda_failed();
+    }
     if (cl.pdl_ok) {
         cfg.numAttrs = 2;
         const cudaError_t e = cudaLaunchKernelExC(&cfg, fn, args);

@@ -491,11 +491,14 @@ bool Engine::chain_usable(int R) {
         const auto & hp = model.hp;
         const bool geom_ok = hp.n_text_state % 128 == 0 && hp.n_text_state <= 1536 && hp.n_text_ctx <= 2048 &&
                              hp.n_text_state == hp.n_text_head * 64;
-        chain_mode = (e && atoi(e) == 1) && geom_ok ? 1 : 0;      // opt-in until it beats the unfused sequence
+        // 1: the whole layer between two cross-attention launches is one chain launch; 2: hybrid -- only the stream-K GEMM +
+        // residual/LayerNorm groups are chain launches, the wide GEMMs and self-attention stay separate kernels
+        chain_mode = e && geom_ok ? atoi(e) : 0;                  // opt-in until it beats the unfused sequence
+        if (chain_mode < 0 || chain_mode > 2) chain_mode = 0;
         if (const char * u = getenv("WHISPER_B200_CHAIN_UNITS")) chain_min_units = std::max(1, atoi(u));
-        if (chain_mode == 1 && chain_init(chain, model.dtype) <= 0) chain_mode = 0;
+        if (chain_mode && chain_init(chain, model.dtype) <= 0) chain_mode = 0;
     }
-    return chain_mode == 1 && R >= 1 && R <= 128;
+    return chain_mode != 0 && R >= 1 && R <= 128;
 }
 
 bool Engine::decode_chain(const std::vector<DecRow> & rows, const std::vector<int> & logit_rows, size_t cross_layer_stride) {
@@ -631,26 +634,69 @@ bool Engine::decode_chain(const std::vector<DecRow> & rows, const std::vector<in
         n_kernel_launches += 1;
         chain_bytes = 0.0;
     };
-    for (int il = 0; il <= L; ++il) {
-        reset();
-        if (il == 0) {
-            add_row(nullptr, nullptr, model.dec[0].ln1_w, model.dec[0].ln1_b, h16, true);
-        } else {
-            add_mlp_half(il - 1);
-            if (il < L) add_row(&g_m2, model.dec[il - 1].b2, model.dec[il].ln1_w, model.dec[il].ln1_b, h16, false);
-            else        add_row(&g_m2, model.dec[il - 1].b2, identity_logits ? model.d_ln_w : nullptr,
-                                identity_logits ? model.d_ln_b : nullptr, hl16, false);
+    auto cross = [&](int il) {
+        SplitIn qs;
+        qs.part = part; qs.bias = model.dec[il].bxq; qs.g = g_dd;
+        if (trace_on) qs.trace = (unsigned long long *) chain_trace.p + 32 * il + 27;
+        prof_begin(PC_CROSS_ATTN, (double) R * 1500.0 * 2 * d * 2.0);
+        dec_cross_attn(dt, nullptr, d_rows, R, d, H, il * cross_layer_stride, 1500, n_phantom(), att, stream, &qs);
+        prof_end();
+        n_kernel_launches += 1;
+    };
+    if (chain_mode == 1) {
+        for (int il = 0; il <= L; ++il) {
+            reset();
+            if (il == 0) {
+                add_row(nullptr, nullptr, model.dec[0].ln1_w, model.dec[0].ln1_b, h16, true);
+            } else {
+                add_mlp_half(il - 1);
+                if (il < L) add_row(&g_m2, model.dec[il - 1].b2, model.dec[il].ln1_w, model.dec[il].ln1_b, h16, false);
+                else        add_row(&g_m2, model.dec[il - 1].b2, identity_logits ? model.d_ln_w : nullptr,
+                                    identity_logits ? model.d_ln_b : nullptr, hl16, false);
+            }
+            if (il < L) add_attn_half(il);
+            launch();
+            if (il < L) cross(il);
         }
-        if (il < L) add_attn_half(il);
-        launch();
-        if (il < L) {
-            SplitIn qs;
-            qs.part = part; qs.bias = model.dec[il].bxq; qs.g = g_dd;
-            if (trace_on) qs.trace = (unsigned long long *) chain_trace.p + 32 * il + 27;
-            prof_begin(PC_CROSS_ATTN, (double) R * 1500.0 * 2 * d * 2.0);
-            dec_cross_attn(dt, nullptr, d_rows, R, d, H, il * cross_layer_stride, 1500, n_phantom(), att, stream, &qs);
+    } else {
+        // hybrid: chain launches only where a stream-K GEMM feeds a residual + LayerNorm (and the cross query GEMM)
+        auto skinny = [&](const void * a, int K, const void * w, int N, const float * bias, float scale, int scale_cols, bool gelu,
+                          void * out16) {
+            GemmArgs g;
+            g.dtype = dt; g.M = R; g.N = N; g.K = K; g.a = a; g.lda = K; g.w = w; g.ldw = K; g.bias = bias;
+            g.scale = scale; g.scale_cols = scale_cols; g.gelu = gelu; g.out16 = out16; g.ldo16 = N;
+            prof_begin(PC_GEMM_DEC, ((double) N * K + (double) R * (N + K)) * 2.0);
+            ok = ok && skinny_gemm(g, skinny_ws, stream);
             prof_end();
             n_kernel_launches += 1;
+        };
+        reset();
+        add_row(nullptr, nullptr, model.dec[0].ln1_w, model.dec[0].ln1_b, h16, true);
+        launch();
+        for (int il = 0; il < L; ++il) {
+            const DecLayer & Lr = model.dec[il];
+            const TMap * wm = &chain_wmaps[(size_t) il * 6];
+            skinny(h16, d, Lr.wqkv, 3 * d, Lr.bqkv, qk_scale, 2 * d, false, qkv);
+            prof_begin(PC_SELF_ATTN, self_bytes);
+            dec_self_attn(dt, qkv, d_rows, R, d, H, il * self_layer, n_ctx, true, att, stream);
+            prof_end();
+            n_kernel_launches += 1;
+            reset();
+            add_gemm(g_dd, tm_att, d, wm[W_O], d);
+            add_row(&g_dd, Lr.bo, Lr.lnx_w, Lr.lnx_b, h16, false);
+            add_gemm(g_dd, tm_h16, d, wm[W_XQ], d);
+            launch();
+            cross(il);
+            reset();
+            add_gemm(g_dd, tm_att, d, wm[W_XO], d);
+            add_row(&g_dd, Lr.bxo, Lr.ln2_w, Lr.ln2_b, h16, false);
+            launch();
+            skinny(h16, d, Lr.w1, 4 * d, Lr.b1, 1.0f, 0, true, mlp);
+            reset();
+            add_gemm(g_m2, tm_mlp, 4 * d, wm[W_2], d);
+            if (il + 1 < L) add_row(&g_m2, Lr.b2, model.dec[il + 1].ln1_w, model.dec[il + 1].ln1_b, h16, false);
+            else            add_row(&g_m2, Lr.b2, identity_logits ? model.d_ln_w : nullptr, identity_logits ? model.d_ln_b : nullptr, hl16, false);
+            launch();
         }
     }
     if (RL > 0) {
@@ -668,7 +714,7 @@ bool Engine::decode_chain(const std::vector<DecRow> & rows, const std::vector<in
         prof_end();
         n_kernel_launches += 1;
     }
-    if (trace_on && L >= 3) {
+    if (trace_on && L >= 3 && chain_mode == 1) {
         // average over the middle launches (all have the same 11 phases): phase durations, launch-to-launch gap
         std::vector<unsigned long long> h((size_t) (L + 1) * 32);
         WB_CUDA(cudaStreamSynchronize(stream));

@@ -16,9 +16,10 @@ from test_gpu_model import model_path, pcm_for
 pytestmark = pytest.mark.gpu
 
 
-def _with_chain(on, fn):
+def _with_chain(mode, fn):
+    """mode 0: separate launches, 1: one chain launch per layer half, 2: hybrid (see Engine::chain_usable)."""
     old = os.environ.get("WHISPER_B200_CHAIN")
-    os.environ["WHISPER_B200_CHAIN"] = "1" if on else "0"
+    os.environ["WHISPER_B200_CHAIN"] = str(int(mode))
     try:
         return fn()
     finally:
@@ -28,8 +29,9 @@ def _with_chain(on, fn):
             os.environ["WHISPER_B200_CHAIN"] = old
 
 
+@pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("arch,fa", [("tiny.en", False), ("base.en", True), ("tiny", False)])
-def test_chain_step_logits_match_unfused(lib, model_dir, arch, fa):
+def test_chain_step_logits_match_unfused(lib, model_dir, arch, fa, mode):
     pcm = pcm_for({"kind": "jfk"})
 
     def run(on):
@@ -45,15 +47,16 @@ def test_chain_step_logits_match_unfused(lib, model_dir, arch, fa):
                 return np.stack(out)
         return _with_chain(on, body)
 
-    a, b = run(True), run(False)
+    a, b = run(mode), run(0)
     d = np.abs(a - b).max(axis=1)
-    print(f"{arch} fa={fa}: chain vs unfused logits max|d| per step: {d.max():.3e}")
+    print(f"{arch} fa={fa} mode={mode}: chain vs unfused logits max|d| per step: {d.max():.3e}")
     assert d.max() <= 4e-3
     assert (a[:, :50000].argmax(axis=1) == b[:, :50000].argmax(axis=1)).all()
 
 
-def test_chain_batched_two_row_blocks(lib, model_dir):
-    """70 sequences in one decoder batch: rows 64..69 live in the second 64-row block of every GEMM phase."""
+@pytest.mark.parametrize("mode", [1, 2])
+def test_chain_batched_more_than_64_rows(lib, model_dir, mode):
+    """70 sequences in one decoder batch: more than 64 live accumulator rows (the 16 KB activation-tile geometry)."""
     n_win = 70
     pcm = np.concatenate([modelgen.synth_pcm(480000, seed=11, stream=i) for i in range(n_win)])
 
@@ -67,7 +70,7 @@ def test_chain_batched_two_row_blocks(lib, model_dir):
                 return [tuple(s.tokens) for s in segs]
         return _with_chain(on, body)
 
-    a, b = run(True), run(False)
+    a, b = run(mode), run(0)
     assert len(a) == len(b) == n_win
     same = sum(x == y for x, y in zip(a, b))
     print(f"windows with identical token sequences: {same}/{n_win}")

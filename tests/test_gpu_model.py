@@ -206,6 +206,49 @@ def test_low_level_api_vs_live_reference(lib, model_dir):
         assert worst <= 2e-2
 
 
+def test_large_v3_turbo_geometry_vs_live_reference(lib, model_dir):
+    """The geometry of BASELINE.json configs 3/4 (128 mel bins, d = 1280, 20 heads, 32 encoder layers; turbo = 4 text layers so
+    the CPU reference stays affordable): mel -> encoder -> prompt + teacher-forced single-token steps against the live reference."""
+    ref, _ = reflib.load()
+    if ref is None:
+        pytest.skip("oracle/_ref was not built / did not travel")
+    path = model_path(model_dir, "large-v3-turbo")
+    pcm = pcm_for({"kind": "jfk"})
+    n_thr = min(os.cpu_count() or 4, 32)
+    with api.Whisper(lib, path, flash_attn=False) as w, api.Whisper(ref, path, use_gpu=False, flash_attn=False) as r:
+        assert w.pcm_to_mel(pcm) == 0 and r.pcm_to_mel(pcm, n_thr) == 0
+        mel = get_mel(lib, w)
+        n_len, n_len_org, n_mel = C.c_int(), C.c_int(), C.c_int()
+        assert ref.ref_mel_dims(r.ctx, C.byref(n_len), C.byref(n_len_org), C.byref(n_mel)) == 0
+        assert (n_mel.value, n_len.value) == mel.shape == (128, mel.shape[1])
+        rmel = np.empty(mel.shape, np.float32)
+        assert ref.ref_mel_copy(r.ctx, rmel.ctypes.data_as(FP)) == 0
+        dm = np.abs(mel - rmel)
+        print(f"128-bin mel max|d| = {dm.max():.3e}")
+        assert dm.max() <= 5e-5 and (dm <= 1e-5 * np.maximum(np.abs(rmel), 1.0)).mean() >= 0.999
+        assert w.encode(0) == 0 and r.encode(0, n_thr) == 0
+        enc = get_enc(lib, w, 1280)
+        renc = np.empty((1500, 1280), np.float32)
+        assert ref.ref_embd_enc_copy(r.ctx, renc.ctypes.data_as(FP), renc.size) == 0
+        de = np.abs(enc - renc)
+        print(f"large-v3-turbo embd_enc max|d| = {de.max():.3e} mean|d| = {de.mean():.3e} (rms {np.sqrt((renc ** 2).mean()):.3f})")
+        assert de.max() <= 2e-2
+        toks = [lib.whisper_token_sot(w.ctx), lib.whisper_token_lang(w.ctx, 0), lib.whisper_token_transcribe(w.ctx)]
+        rc1, lg = w.decode(toks, 0)
+        rc2, rlg = r.decode(toks, 0, n_thr)
+        assert rc1 == 0 and rc2 == 0
+        worst = np.abs(lg - rlg).max()
+        for step in range(4):
+            nxt = int(rlg.argmax())
+            rc1, lg = w.decode([nxt], len(toks))
+            rc2, rlg = r.decode([nxt], len(toks), n_thr)
+            toks.append(nxt)
+            assert rc1 == 0 and rc2 == 0
+            worst = max(worst, np.abs(lg - rlg).max())
+        print(f"large-v3-turbo logits max|d| over prompt + 4 steps = {worst:.3e}")
+        assert worst <= 2e-2
+
+
 def test_set_mel_empty_runs_like_whisper_bench(lib, model_dir):
     """examples/bench/bench.cpp:84 feeds an empty mel (encoder input all zeros) and times encode/decode."""
     with api.Whisper(lib, model_path(model_dir, "tiny.en")) as w:

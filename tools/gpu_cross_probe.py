@@ -4,7 +4,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for chain, ld in (("0", "0"), ("1", "0")):
+for chain, ld in (("0", "0"), ("1", "0"), ("2", "0")):
     env = dict(os.environ, WHISPER_B200_CHAIN=chain, WHISPER_B200_CROSS_LD=ld, WHISPER_B200_CHAIN_UNITS="4")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gpu_decode_probe.py"), "large-v3", "64", "2", "60"], env=env,
                        capture_output=True, text=True)
