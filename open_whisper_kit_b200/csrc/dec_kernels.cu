@@ -68,7 +68,15 @@ cross_attn_kernel(const T16 * __restrict__ q, int ldq, const DecRow * __restrict
     const int sub = lane & 7, grp = lane >> 3;     // 8 lanes per key row, 4 key rows per warp instruction
     // The successor is the next chain / GEMM launch, whose CTAs hold ~100 KB of shared memory while they wait: letting
     // them in at once would squeeze this kernel's own occupancy, so the cross pass triggers after its K sweep.
-    if (SELF) pdl_trigger();
+    if (SELF) {
+        pdl_trigger();
+        // keys of earlier positions were written by earlier decoder calls: safe to touch before the dependency resolves
+        const DecRow row0 = rows[r];
+        const T16 * kb0 = reinterpret_cast<const T16 *>(row0.self_kv) + layer_off + h * 64 + (size_t) (warp * 4 + grp) * (2 * d) + sub * 8;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (warp * 4 + grp + 16 * u < row0.pos) asm volatile("prefetch.global.L2 [%0];" ::"l"(kb0 + (size_t) (16 * u) * (2 * d)));
+    }
     if (!SELF) {
         // The cross K/V and the row descriptors were written before this decoder call began (encoder stage, H2D copy), so
         // they may be touched before the grid dependency resolves: pull the first batch of keys into L2 meanwhile.

@@ -370,6 +370,14 @@ layernorm_row_kernel(const float * __restrict__ x, int ldx, const float * __rest
     __shared__ float s_red[8];
     const int row = blockIdx.x, tid = threadIdx.x;
     pdl_trigger();
+    // gamma / beta are weights (never written on the device): fetch them while the predecessor is still running
+    float gw[10], gb[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const int c = tid + 128 * i;
+        gw[i] = c < d ? __ldg(gamma + c) : 0.0f;
+        gb[i] = c < d ? __ldg(beta + c) : 0.0f;
+    }
     pdl_wait();
     const float * xr = x + (size_t) (row_map ? row_map[row] : row) * ldx;
     float v[10];                           // d <= 1280
@@ -400,7 +408,7 @@ layernorm_row_kernel(const float * __restrict__ x, int ldx, const float * __rest
     for (int i = 0; i < 10; ++i) {
         const int c = tid + 128 * i;
         if (c < d) {
-            const float o = v[i] * rstd * gamma[c] + beta[c];
+            const float o = v[i] * rstd * gw[i] + gb[i];
             if (y16) y16[(size_t) row * ldy16 + c] = Half16<T16>::from_f(o);
             if (y32) y32[(size_t) row * ldy32 + c] = o;
         }

@@ -122,6 +122,9 @@ skinny_gemm_kernel(const SkinnyParams p) {
     for (int s = 0; s < S_STAGES - 1; ++s)
         if (s < nkb) load_w(s, kb0 + s);
     cp_commit();
+    // the bias slice of this tile is a weight too: have it in L2 by the time the epilogue asks for it
+    if (p.bias && tid == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.bias + n0));
+    if (p.bias && tid == 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.bias + n0 + 32));
     pdl_wait();
 #pragma unroll
     for (int s = 0; s < S_STAGES - 1; ++s) {
