@@ -249,6 +249,32 @@ def test_large_v3_turbo_geometry_vs_live_reference(lib, model_dir):
         assert worst <= 2e-2
 
 
+def test_bf16_operands_track_f16(lib, model_dir, monkeypatch):
+    """WHISPER_B200_DTYPE=bf16 (the operand type BASELINE.json names) runs every kernel of the path -- tcgen05 GEMMs and
+    attention, decoder step -- and stays close to the f16 run (bf16 has 3 fewer mantissa bits: ~8x the rounding error)."""
+    pcm = pcm_for({"kind": "jfk"})
+
+    def run(dtype):
+        monkeypatch.setenv("WHISPER_B200_DTYPE", dtype)
+        with api.Whisper(lib, model_path(model_dir, "base.en"), flash_attn=False) as w:
+            assert lib.whisper_b200_dtype(w.ctx) == (1 if dtype == "bf16" else 0)
+            assert w.pcm_to_mel(pcm) == 0 and w.encode(0) == 0
+            enc = get_enc(lib, w, 512)
+            toks, out = [lib.whisper_token_sot(w.ctx)], []
+            for step in range(6):
+                rc, lg = w.decode(toks[-1:] if step else toks, 0 if step == 0 else len(toks) - 1)
+                assert rc == 0
+                out.append(lg)
+                toks.append(int(lg[:50000].argmax()))
+            return enc, np.stack(out)
+
+    e16, l16 = run("f16")
+    eb, lb = run("bf16")
+    de, dl = np.abs(e16 - eb).max(), np.abs(l16[0] - lb[0]).max()
+    print(f"bf16 vs f16: embd_enc max|d| = {de:.3e}, first-step logits max|d| = {dl:.3e}")
+    assert np.isfinite(lb).all() and de <= 6e-2 and dl <= 1.5e-1
+
+
 def test_set_mel_empty_runs_like_whisper_bench(lib, model_dir):
     """examples/bench/bench.cpp:84 feeds an empty mel (encoder input all zeros) and times encode/decode."""
     with api.Whisper(lib, model_path(model_dir, "tiny.en")) as w:
