@@ -5,20 +5,19 @@
 // reference's padded flash-attention scratch (src/whisper.cpp:2055, 2141-2159).
 //
 // One CTA = 128 queries of one (window, head); two CTAs per SM so that one CTA's softmax overlaps the other's MMAs.
-//   warp 4 (one lane): TMA producer -- Q tile once, then K tiles [128 keys][64] (two stages) and V^T tiles [64][128 keys]
-//                      (one stage: V_j is only needed after softmax_j, long after PV_{j-1} released the buffer); 3-D tensor
-//                      maps, so rows past T inside a window are out of bounds = zero-filled;
-//   warp 5 (one lane): MMA issuer   -- S = Q K^T (4 x tcgen05.mma 128x128x16) into TMEM, then, once the softmax warps have
-//                      published P in shared memory, PV = P V (8 x tcgen05.mma 128x64x16) into a second TMEM buffer;
-//   warps 0-7: softmax, two threads per query row (tcgen05.ld 32x32b gives a thread its own row; warps w and w+4 may read
-//              the same 32 lanes and take 64 score columns each): row max, exp2, P as 16-bit into the 128-byte-swizzled
-//              A-operand layout, running max / sum, O kept in registers and rescaled there (O = O * corr + PV read back
-//              from TMEM) -- no read-modify-write of TMEM.
+//   warp 4 (one lane): TMA producer -- Q tile once, then K tiles [64 keys][64] and V^T tiles [80][64 keys] through two-stage
+//                      rings; 3-D tensor maps, so rows past T inside a window are out of bounds = zero-filled;
+//   warp 5 (one lane): MMA issuer   -- S = Q K^T (4 x tcgen05.mma 128x64x16) into one of two TMEM buffers, and, once the
+//                      softmax warps have published P in one of two shared-memory buffers, PV += P V (4 x 128x80x16);
+//   warps 0-3: softmax, one query row per thread (tcgen05.ld 32x32b gives a thread its own row): ONE pass over S per key
+//              tile -- exp2 against the row maximum of the earlier tiles ("stale" maximum, two exponentials per MUFU op
+//              straight into the 128-byte-swizzled 16-bit A-operand layout), O and the row sum accumulate in TMEM across all
+//              key tiles; a row whose scores outgrow its maximum by 2^12 takes the new one and rescales its TMEM lane.
 // V is consumed as V^T (K-major B operand), produced by a small transpose kernel per layer.
-// Measured (B200, large-v3, 64 windows): 339 TFLOP/s against 245 for the mma.sync kernel it replaces.  Per key tile the MMA
-// issuer spends ~520 cycles issuing S, ~770 issuing PV and ~2400 waiting for the softmax warps, whose own chain (S landed ->
-// row max -> exchange -> PV read-back -> exponentials -> publish P) is latency- not throughput-bound; the second CTA per SM
-// is what fills the gaps.
+// Measured (B200, large-v3, 64 windows, in the bench step): ~335 TFLOP/s against 245 for the mma.sync kernel it replaces.
+// Per 64-key tile the MMA issuer spends ~430 cycles issuing S, ~430 issuing PV and ~900 waiting for P; a softmax thread
+// spends ~1200 of its ~1950 cycles in tcgen05.ld + FFMA / cvt / MUFU for its 64 scores: with one softmax warp per SM
+// sub-partition and CTA the phase is bound by instruction latency, not by the tensor or MUFU pipes (21 % / 38 % busy).
 #include "enc_kernels.h"
 
 #include <math.h>
@@ -30,16 +29,19 @@ namespace wb {
 
 namespace {
 
-constexpr int FA_THREADS = 320;     // 8 softmax warps (two threads per query row) + TMA producer + MMA issuer
-constexpr int FA_BQ = 128, FA_BK = 128, FA_DH = 64;
-constexpr int FA_TILE_BYTES = 128 * 128;                // 128 rows x 64 x 16-bit
+constexpr int FA_THREADS = 192;     // 4 softmax warps (thread = query row) + TMA producer + MMA issuer
+constexpr int FA_BQ = 128, FA_BK = 64, FA_DH = 64;
+constexpr int FA_Q_BYTES = 128 * 128;                   // 128 queries x 64 x 16-bit
+constexpr int FA_K_BYTES = FA_BK * 128;                 // 64 keys x 64 x 16-bit
 // V^T carries 16 extra rows per head: row 64 is all ones (rows 65..79 zero), so column 64 of P V is the row sum of P exactly
 // as the tensor core saw it (16-bit P): the softmax warps never add up their exponentials.
 constexpr int FA_VROWS = FA_DH + 16;
-constexpr int FA_VBLK_BYTES = FA_VROWS * 128;           // one k-block of V^T: [80 rows][64 keys]
-constexpr int FA_OFF_Q = 0, FA_OFF_K = FA_TILE_BYTES, FA_OFF_P = 3 * FA_TILE_BYTES, FA_OFF_V = 5 * FA_TILE_BYTES;
-constexpr int FA_SMEM = 5 * FA_TILE_BYTES + 2 * FA_VBLK_BYTES + 1024;   // Q + 2 K + P (two k-blocks) + V^T + slack = 101 KB: two CTAs per SM
-constexpr int FA_TMEM_COLS = 256;                       // S: columns 0..127, PV: columns 128..207
+constexpr int FA_V_BYTES = FA_VROWS * 128;              // [80 rows][64 keys]
+constexpr int FA_P_BYTES = 128 * 128;                   // [128 queries][64 keys]
+constexpr int FA_OFF_Q = 0, FA_OFF_K = FA_Q_BYTES, FA_OFF_V = FA_OFF_K + 2 * FA_K_BYTES, FA_OFF_P = FA_OFF_V + 2 * FA_V_BYTES;
+constexpr int FA_SMEM = FA_OFF_P + 2 * FA_P_BYTES + 1024;   // Q + 2 K + 2 V^T + 2 P + alignment slack = 85 KB: two CTAs per SM
+constexpr int FA_TMEM_COLS = 256;                       // S (two buffers): columns 0..63, 64..127; PV: columns 128..207
+static_assert(FA_OFF_P % 1024 == 0 && FA_OFF_V % 1024 == 0, "128-byte swizzle atoms are 1024 bytes");
 
 __device__ __forceinline__ void fa_wait(uint64_t * bar, uint32_t parity) {       // bounded: a protocol error must trap, not hang
     for (unsigned spins = 0; !ptx::mbar_try_wait(bar, parity); ++spins)
@@ -95,12 +97,11 @@ v_transpose_kernel(const T16 * __restrict__ qkv, T16 * __restrict__ vt, int T, i
 
 template <typename T16>
 __global__ void __launch_bounds__(FA_THREADS, 2)
-enc_attn_tc_kernel(const __grid_constant__ TMap tm_qk, const __grid_constant__ TMap tm_vt, T16 * __restrict__ out, int T, int d,
-                   int H, float scale_log2e, int n_phantom) {
+enc_attn_tc_kernel(const __grid_constant__ TMap tm_q, const __grid_constant__ TMap tm_k, const __grid_constant__ TMap tm_vt,
+                   T16 * __restrict__ out, int T, int d, int H, float scale_log2e, int n_phantom) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t b_q, b_kfull[2], b_kempty[2], b_vfull, b_vempty, b_s, b_p, b_pv;
+    __shared__ __align__(8) uint64_t b_q, b_kfull[2], b_kempty[2], b_vfull[2], b_vempty[2], b_s[2], b_p[2], b_pv[2];
     __shared__ uint32_t s_tmem;
-    __shared__ float s_mx[2][2][FA_BQ];      // [tile parity][column half][row]: row maxima exchanged between the two halves
     uint8_t * smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * FA_BQ, head = blockIdx.y, win = blockIdx.z;
@@ -111,12 +112,12 @@ enc_attn_tc_kernel(const __grid_constant__ TMap tm_qk, const __grid_constant__ T
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&b_kfull[i], 1);
             ptx::mbar_init(&b_kempty[i], 1);
+            ptx::mbar_init(&b_vfull[i], 1);
+            ptx::mbar_init(&b_vempty[i], 1);
+            ptx::mbar_init(&b_s[i], 1);
+            ptx::mbar_init(&b_p[i], 128);
+            ptx::mbar_init(&b_pv[i], 1);
         }
-        ptx::mbar_init(&b_vfull, 1);
-        ptx::mbar_init(&b_vempty, 1);
-        ptx::mbar_init(&b_s, 1);
-        ptx::mbar_init(&b_p, 256);
-        ptx::mbar_init(&b_pv, 1);
         ptx::fence_mbar_init();
     }
     if (warp == 0) {
@@ -127,174 +128,177 @@ enc_attn_tc_kernel(const __grid_constant__ TMap tm_qk, const __grid_constant__ T
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem = s_tmem;
-
-    if (warp == 8) {
+    // tile j uses buffer j & 1 of every ring; its k-th use of that buffer (k = j >> 1) completes phase k of the buffer's barriers
+    if (warp == 4) {
         // ===== TMA producer =====
         if (lane == 0) {
-            ptx::prefetch_tensormap(&tm_qk);
+            ptx::prefetch_tensormap(&tm_q);
+            ptx::prefetch_tensormap(&tm_k);
             ptx::prefetch_tensormap(&tm_vt);
-            ptx::mbar_arrive_expect_tx(&b_q, FA_TILE_BYTES);
-            ptx::tma_load_3d(smem + FA_OFF_Q, &tm_qk, &b_q, head * FA_DH, q0, win);
+            ptx::mbar_arrive_expect_tx(&b_q, FA_Q_BYTES);
+            ptx::tma_load_3d(smem + FA_OFF_Q, &tm_q, &b_q, head * FA_DH, q0, win);
             for (int j = 0; j < n_tiles; ++j) {
                 const int s = j & 1;
                 if (j >= 2) fa_wait(&b_kempty[s], ((j >> 1) - 1) & 1);
-                ptx::mbar_arrive_expect_tx(&b_kfull[s], FA_TILE_BYTES);
-                ptx::tma_load_3d(smem + FA_OFF_K + s * FA_TILE_BYTES, &tm_qk, &b_kfull[s], d + head * FA_DH, j * FA_BK, win);
-                if (j >= 1) fa_wait(&b_vempty, (j - 1) & 1);
-                ptx::mbar_arrive_expect_tx(&b_vfull, 2 * FA_VBLK_BYTES);
-                uint8_t * vs = smem + FA_OFF_V;                          // two k-blocks: [80 rows][64 keys] each
-                ptx::tma_load_3d(vs, &tm_vt, &b_vfull, j * FA_BK, 0, win * H + head);
-                ptx::tma_load_3d(vs + FA_VBLK_BYTES, &tm_vt, &b_vfull, j * FA_BK + 64, 0, win * H + head);
+                ptx::mbar_arrive_expect_tx(&b_kfull[s], FA_K_BYTES);
+                ptx::tma_load_3d(smem + FA_OFF_K + s * FA_K_BYTES, &tm_k, &b_kfull[s], d + head * FA_DH, j * FA_BK, win);
+                if (j >= 2) fa_wait(&b_vempty[s], ((j >> 1) - 1) & 1);
+                ptx::mbar_arrive_expect_tx(&b_vfull[s], FA_V_BYTES);
+                ptx::tma_load_3d(smem + FA_OFF_V + s * FA_V_BYTES, &tm_vt, &b_vfull[s], j * FA_BK, 0, win * H + head);
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == 5) {
         // ===== MMA issuer =====
-        // Order per tile: (P_j published) -> S_{j+1} first, then PV_j.  Issuing a tcgen05.mma costs ~150 cycles whatever its
-        // shape, PV is 8 of them: with S_{j+1} ahead of PV_j the softmax warps start on tile j+1 while PV_j is still being
-        // issued, and only need PV_j when they come to rescale O.
+        // S is double-buffered in TMEM and P in shared memory: S_{j+1} is already computed while the softmax warps work on
+        // S_j, and PV_j reads P_j while they write P_{j+1}, so the two hand-offs per tile (commit -> mbarrier -> wake-up, ~1 us
+        // together as measured) overlap with work instead of serialising it.  PV accumulates in TMEM over all key tiles.
         if (lane == 0) {
             const uint32_t idesc_s = ptx::make_idesc_f16(Half16<T16>::kind, 128, FA_BK);
             const uint32_t idesc_pv = ptx::make_idesc_f16(Half16<T16>::kind, 128, FA_VROWS);
             const uint64_t dq = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + FA_OFF_Q));
-            const uint64_t dp = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + FA_OFF_P));
-            const uint64_t dv = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + FA_OFF_V));
             auto issue_s = [&](int j) {
                 const int s = j & 1;
                 fa_wait(&b_kfull[s], (j >> 1) & 1);
                 ptx::tc_fence_after();
-                const uint64_t dk = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + FA_OFF_K + s * FA_TILE_BYTES));
+                const uint64_t dk = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + FA_OFF_K + s * FA_K_BYTES));
 #pragma unroll
-                for (int k = 0; k < 4; ++k) ptx::umma_f16(tmem, dq + (uint64_t) (2 * k), dk + (uint64_t) (2 * k), idesc_s, (uint32_t) (k != 0));
+                for (int k = 0; k < 4; ++k)
+                    ptx::umma_f16(tmem + (uint32_t) (s * FA_BK), dq + (uint64_t) (2 * k), dk + (uint64_t) (2 * k), idesc_s, (uint32_t) (k != 0));
                 ptx::umma_commit(&b_kempty[s]);
-                ptx::umma_commit(&b_s);
+                ptx::umma_commit(&b_s[s]);
             };
             fa_wait(&b_q, 0);
             issue_s(0);
+            if (n_tiles > 1) issue_s(1);
             for (int j = 0; j < n_tiles; ++j) {
-                fa_wait(&b_p, j & 1);               // P_j is in shared memory; S_j and PV_{j-1} have been read back
-                if (j + 1 < n_tiles) issue_s(j + 1);
-                fa_wait(&b_vfull, j & 1);
+                const int s = j & 1;
+                fa_wait(&b_p[s], (j >> 1) & 1);      // P_j is in shared memory, S_j has been read, the accumulator is consistent
+                fa_wait(&b_vfull[s], (j >> 1) & 1);
                 ptx::tc_fence_after();
+                const uint64_t dp = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + FA_OFF_P + s * FA_P_BYTES));
+                const uint64_t dv = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + FA_OFF_V + s * FA_V_BYTES));
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    // k-block = k / 4 (P: 16 KB apart, V^T: 10 KB apart, in 16-byte units), 16-key step inside it = k % 4
-                    const uint64_t ap = dp + (uint64_t) ((k >> 2) * (FA_TILE_BYTES >> 4) + 2 * (k & 3));
-                    const uint64_t bv = dv + (uint64_t) ((k >> 2) * (FA_VBLK_BYTES >> 4) + 2 * (k & 3));
-                    ptx::umma_f16(tmem + 128u, ap, bv, idesc_pv, (uint32_t) (k != 0));
-                }
-                ptx::umma_commit(&b_vempty);
-                ptx::umma_commit(&b_pv);
+                for (int k = 0; k < 4; ++k)          // 64 keys = four 16-key steps
+                    ptx::umma_f16(tmem + 128u, dp + (uint64_t) (2 * k), dv + (uint64_t) (2 * k), idesc_pv, (uint32_t) (j != 0 || k != 0));
+                ptx::umma_commit(&b_vempty[s]);
+                ptx::umma_commit(&b_pv[s]);
+                if (j + 2 < n_tiles) issue_s(j + 2);     // S buffer s is free: the softmax warps published P_j after reading it
             }
         }
     } else {
-        // ===== softmax: two threads per query row (warps w and w+4 read the same 32 TMEM lanes), 64 score columns each =====
-        const int quarter = warp & 3, half = warp >> 2;
-        const int row = quarter * 32 + lane;                            // TMEM lane and row inside the tile
-        const uint32_t t_lane = tmem + ((uint32_t) (quarter * 32) << 16);
-        uint8_t * prow = smem + FA_OFF_P + half * FA_TILE_BYTES + row * 128;       // this thread's k-block of P
-        float o[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = 0.0f;
-        float m_run = -INFINITY, l_run = 0.0f, corr_prev = 0.0f;
+        // ===== softmax: thread = query row =====
+        // P = exp2((s - m) * scale) against the row maximum m of the tiles seen BEFORE this one: P may then exceed 1, which a
+        // 16-bit float represents just as well, and nothing depends on this tile's own maximum -- one pass over S, no
+        // per-tile correction of O.  Only when a tile's scores outgrow m by more than 2^kGrow does the row take the new
+        // maximum, redo the tile and rescale its accumulator lane in TMEM (tcgen05.ld / st); the first tile always does.
+        constexpr float kGrow = 12.0f;
+        const int row = warp * 32 + lane;                               // TMEM lane and row inside the tile
+        const uint32_t t_lane = tmem + ((uint32_t) (warp * 32) << 16);
+        float m_run = -INFINITY;
 #pragma unroll 1
         for (int j = 0; j < n_tiles; ++j) {
-            fa_wait(&b_s, j & 1);
+            const int s = j & 1;
+            fa_wait(&b_s[s], (j >> 1) & 1);
             ptx::tc_fence_after();
-            const int key0 = j * FA_BK + half * 64;
-            const bool edge = key0 + 64 > T;
-            // pass 1: maximum of this thread's 64 raw scores, then of the whole row
+            const int key0 = j * FA_BK;
+            const bool edge = key0 + FA_BK > T;
+            const uint32_t t_s = t_lane + (uint32_t) (s * FA_BK);
+            uint32_t pk[32];
             float mx = -INFINITY;
+            auto exp_tile = [&](float mb, bool track_max) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t r[32];
+                    ptx::tmem_ld_32x32(t_s + (uint32_t) (c * 32), r);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        float s0 = __uint_as_float(r[i]), s1 = __uint_as_float(r[i + 1]);
+                        if (edge) {
+                            if (key0 + c * 32 + i >= T) s0 = -INFINITY;
+                            if (key0 + c * 32 + i + 1 >= T) s1 = -INFINITY;
+                        }
+                        if (track_max) mx = fmaxf(mx, fmaxf(s0, s1));
+                        pk[c * 16 + (i >> 1)] = ex2_pack<T16>(fmaf(s0, scale_log2e, -mb), fmaf(s1, scale_log2e, -mb));
+                    }
+                }
+            };
+            if (j == 0) {                 // no maximum yet: find it first (warp-uniform)
 #pragma unroll 1
-            for (int c = 0; c < 2; ++c) {
-                uint32_t r[32];
-                ptx::tmem_ld_32x32(t_lane + (uint32_t) (half * 64 + c * 32), r);
-                ptx::tmem_ld_wait();
-                if (edge) {
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t r[32];
+                    ptx::tmem_ld_32x32(t_s + (uint32_t) (c * 32), r);
+                    ptx::tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
-                        if (key0 + c * 32 + i < T) mx = fmaxf(mx, __uint_as_float(r[i]));
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+                        if (!edge || key0 + c * 32 + i < T) m_run = fmaxf(m_run, __uint_as_float(r[i]));
                 }
             }
-            s_mx[j & 1][half][row] = mx;
-            asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");      // the two warps that share these rows
-            mx = fmaxf(mx, s_mx[j & 1][half ^ 1][row]);
-            const float m_new = fmaxf(m_run, mx);
-            const float corr = ex2((m_run - m_new) * scale_log2e);       // m_run = -inf on the first tile -> 0
-            const float mb = m_new * scale_log2e;
-            // O = O * corr + P V of the previous tile (its MMAs were issued behind this tile's S)
-            if (j > 0) {
-                fa_wait(&b_pv, (j - 1) & 1);
-                ptx::tc_fence_after();
-                uint32_t r[32];
-                ptx::tmem_ld_32x32(t_lane + 128u + (uint32_t) (half * 32), r);
-                const uint32_t rsum = ptx::tmem_ld_32x1(t_lane + 128u + 64u);
-                ptx::tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) o[i] = fmaf(o[i], corr_prev, __uint_as_float(r[i]));
-                l_run = fmaf(l_run, corr_prev, __uint_as_float(rsum));
-            }
-            corr_prev = corr;
-            // pass 2: P = exp2(s * scale - m), 16-bit, into the swizzled A-operand layout (this thread: one 128-byte row)
+            exp_tile(m_run * scale_log2e, true);
+            const bool grow = (mx - m_run) * scale_log2e > kGrow;
+            if (__any_sync(0xffffffffu, grow)) {
+                const float m_new = grow ? mx : m_run;
+                const float f = ex2((m_run - m_new) * scale_log2e);          // 1 for the rows that keep their maximum
+                m_run = m_new;
+                exp_tile(m_run * scale_log2e, false);
+                if (j > 0) {              // rescale this row's accumulator (64 values + the row sum); PV_{j-1} must have landed
+                    fa_wait(&b_pv[(j - 1) & 1], ((j - 1) >> 1) & 1);
+                    ptx::tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < 2; ++c) {
-                uint32_t r[32];
-                ptx::tmem_ld_32x32(t_lane + (uint32_t) (half * 64 + c * 32), r);
-                ptx::tmem_ld_wait();
-                uint32_t pk[16];
+                    for (int c = 0; c < 2; ++c) {
+                        uint32_t r[32];
+                        ptx::tmem_ld_32x32(t_lane + 128u + (uint32_t) (c * 32), r);
+                        ptx::tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    float x0 = fmaf(__uint_as_float(r[i]), scale_log2e, -mb);
-                    float x1 = fmaf(__uint_as_float(r[i + 1]), scale_log2e, -mb);
-                    if (edge) {
-                        if (key0 + c * 32 + i >= T) x0 = -INFINITY;
-                        if (key0 + c * 32 + i + 1 >= T) x1 = -INFINITY;
+                        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
+                        ptx::tmem_st_32x32(t_lane + 128u + (uint32_t) (c * 32), r);
                     }
-                    pk[i >> 1] = ex2_pack<T16>(x0, x1);
-                }
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int chunk = c * 4 + q;                            // 16-byte chunk inside the 128-byte row
-                    *reinterpret_cast<uint4 *>(prow + ((chunk ^ (row & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                    const uint32_t l = ptx::tmem_ld_32x1(t_lane + 128u + 64u);
+                    ptx::tmem_ld_wait();
+                    ptx::tmem_st_32x1(t_lane + 128u + 64u, __float_as_uint(__uint_as_float(l) * f));
+                    ptx::tmem_st_wait();
                 }
             }
-            m_run = m_new;
+            // P buffer s is free once PV_{j-2} has read it
+            if (j >= 2) fa_wait(&b_pv[s], ((j >> 1) - 1) & 1);
+            uint8_t * prow = smem + FA_OFF_P + s * FA_P_BYTES + row * 128;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                *reinterpret_cast<uint4 *>(prow + ((q ^ (row & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
             ptx::fence_proxy_async_smem();           // P was written through the generic proxy; the tensor core reads it through the async one
             ptx::tc_fence_before();
-            ptx::mbar_arrive(&b_p);
+            ptx::mbar_arrive(&b_p[s]);
         }
-        {   // last tile's P V
-            fa_wait(&b_pv, (n_tiles - 1) & 1);
-            ptx::tc_fence_after();
-            uint32_t r[32];
-            ptx::tmem_ld_32x32(t_lane + 128u + (uint32_t) (half * 32), r);
-            const uint32_t rsum = ptx::tmem_ld_32x1(t_lane + 128u + 64u);
-            ptx::tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = fmaf(o[i], corr_prev, __uint_as_float(r[i]));
-            l_run = fmaf(l_run, corr_prev, __uint_as_float(rsum));
-            ptx::tc_fence_before();
-        }
-        // phantom keys (score 0, value 0), normalise, store this thread's 32 of the 64 values
-        float l = l_run, f = 1.0f;
-        if (n_phantom > 0) {
+        // O and the row sum l (column 64: the ones row of V^T) sit in TMEM, both relative to m_run
+        fa_wait(&b_pv[(n_tiles - 1) & 1], ((n_tiles - 1) >> 1) & 1);
+        ptx::tc_fence_after();
+        float l = __uint_as_float(ptx::tmem_ld_32x1(t_lane + 128u + 64u)), f = 1.0f;
+        ptx::tmem_ld_wait();
+        if (n_phantom > 0) {              // phantom keys: score 0, value 0
             const float m_new = fmaxf(m_run, 0.0f);
             f = ex2((m_run - m_new) * scale_log2e);
             l = l * f + (float) n_phantom * ex2(-m_new * scale_log2e);
         }
         const float inv = f / l;
         const int q = q0 + row;
-        if (q < T) {
-            T16 * orow = out + ((size_t) win * T + q) * (size_t) d + head * FA_DH + half * 32;
+        T16 * orow = out + ((size_t) win * T + (q < T ? q : 0)) * (size_t) d + head * FA_DH;
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32(t_lane + 128u + (uint32_t) (c * 32), r);
+            ptx::tmem_ld_wait();
+            if (q < T) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-                *reinterpret_cast<uint4 *>(orow + i) =
-                    make_uint4(pack2<T16>(o[i] * inv, o[i + 1] * inv), pack2<T16>(o[i + 2] * inv, o[i + 3] * inv),
-                               pack2<T16>(o[i + 4] * inv, o[i + 5] * inv), pack2<T16>(o[i + 6] * inv, o[i + 7] * inv));
+                for (int i = 0; i < 32; i += 8) {
+                    *reinterpret_cast<uint4 *>(orow + c * 32 + i) =
+                        make_uint4(pack2<T16>(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv),
+                                   pack2<T16>(__uint_as_float(r[i + 2]) * inv, __uint_as_float(r[i + 3]) * inv),
+                                   pack2<T16>(__uint_as_float(r[i + 4]) * inv, __uint_as_float(r[i + 5]) * inv),
+                                   pack2<T16>(__uint_as_float(r[i + 6]) * inv, __uint_as_float(r[i + 7]) * inv));
+                }
             }
         }
+        ptx::tc_fence_before();
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -315,9 +319,10 @@ bool enc_attention_tc(DType dt, const void * qkv, void * out, void * vt_scratch,
                       int n_phantom, cudaStream_t st) {
     if (d != n_head * FA_DH || (d % 8) != 0) return false;
     const int TP = round_up(T, 8);
-    TMap tm_qk, tm_vt;
-    // qkv as {3d, T, W}: a 128-row box that runs past T inside a window is zero-filled instead of reading the next window
-    if (!tc_make_tmap3d(&tm_qk, qkv, 3 * d, T, n_windows, (size_t) 3 * d * 2, (size_t) T * 3 * d * 2, 64, 128, dt)) return false;
+    TMap tm_q, tm_k, tm_vt;
+    // qkv as {3d, T, W}: a box that runs past T inside a window is zero-filled instead of reading the next window
+    if (!tc_make_tmap3d(&tm_q, qkv, 3 * d, T, n_windows, (size_t) 3 * d * 2, (size_t) T * 3 * d * 2, 64, FA_BQ, dt)) return false;
+    if (!tc_make_tmap3d(&tm_k, qkv, 3 * d, T, n_windows, (size_t) 3 * d * 2, (size_t) T * 3 * d * 2, 64, FA_BK, dt)) return false;
     // V^T (+ ones row) as {T, 80, W*H} with row pitch TP
     if (!tc_make_tmap3d(&tm_vt, vt_scratch, T, FA_VROWS, n_windows * n_head, (size_t) TP * 2, (size_t) FA_VROWS * TP * 2, 64, FA_VROWS, dt)) return false;
     const float scale_log2e = (1.0f / sqrtf((float) FA_DH)) * 1.4426950408889634f;
@@ -329,7 +334,7 @@ bool enc_attention_tc(DType dt, const void * qkv, void * out, void * vt_scratch,
             set = true;
         }
         v_transpose_kernel<__half><<<tgrid, 256, 0, st>>>(reinterpret_cast<const __half *>(qkv), reinterpret_cast<__half *>(vt_scratch), T, TP, d, n_head);
-        enc_attn_tc_kernel<__half><<<grid, FA_THREADS, FA_SMEM, st>>>(tm_qk, tm_vt, reinterpret_cast<__half *>(out), T, d, n_head, scale_log2e, n_phantom);
+        enc_attn_tc_kernel<__half><<<grid, FA_THREADS, FA_SMEM, st>>>(tm_q, tm_k, tm_vt, reinterpret_cast<__half *>(out), T, d, n_head, scale_log2e, n_phantom);
     } else {
         static bool set = false;
         if (!set) {
@@ -337,7 +342,7 @@ bool enc_attention_tc(DType dt, const void * qkv, void * out, void * vt_scratch,
             set = true;
         }
         v_transpose_kernel<__nv_bfloat16><<<tgrid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16 *>(qkv), reinterpret_cast<__nv_bfloat16 *>(vt_scratch), T, TP, d, n_head);
-        enc_attn_tc_kernel<__nv_bfloat16><<<grid, FA_THREADS, FA_SMEM, st>>>(tm_qk, tm_vt, reinterpret_cast<__nv_bfloat16 *>(out), T, d, n_head, scale_log2e, n_phantom);
+        enc_attn_tc_kernel<__nv_bfloat16><<<grid, FA_THREADS, FA_SMEM, st>>>(tm_q, tm_k, tm_vt, reinterpret_cast<__nv_bfloat16 *>(out), T, d, n_head, scale_log2e, n_phantom);
     }
     WB_CUDA(cudaGetLastError());
     return !cuda_failed();
