@@ -62,7 +62,7 @@ WB200_API long long whisper_b200_kernel_launches(struct whisper_context * ctx);
  * read() fills out[3*c + {0,1,2}] = {milliseconds, launches, algorithmic work} for class c and returns the number of
  * classes, in this order: mel(bytes), im2col(bytes), gemm_conv(flop), layernorm(bytes), gemm_encoder(flop),
  * encoder_attention(flop), gemm_cross_kv(flop), decoder_misc(bytes), gemm_decoder(bytes), self_attention(bytes),
- * cross_attention(bytes), gemm_logits(bytes), sample(bytes), layernorm_decoder(bytes). */
+ * cross_attention(bytes), gemm_logits(bytes), sample(bytes), layernorm_decoder(bytes), decoder_chain(bytes). */
 WB200_API void whisper_b200_profile_enable(struct whisper_context * ctx, int on);
 WB200_API int whisper_b200_profile_read(struct whisper_context * ctx, double * out, int cap);
 
@@ -96,6 +96,11 @@ WB200_API double whisper_b200_kernel_gemm_bench(int dtype, int M, int N, int K, 
 /* Average microseconds of one decoder-step kernel launched back to back: which = 0 LayerNorm, 1 cross-attention,
  * 2 self-attention at position aux, 3 KV append; R rows of width d. */
 WB200_API double whisper_b200_kernel_step_bench(int which, int dtype, int R, int d, int aux, int iters);
+
+/* Stream-K geometry of one GEMM phase of the persistent decoder-step kernel (csrc/dec_chain.h, host logic only -- needs
+ * no device): out[0..4] = {tiles, k-blocks per tile, units, CTAs taking part, partial-tile slots per output tile}.
+ * direct != 0: every CTA owns one whole 128-column tile.  Returns 0, or -1 for shapes the kernel does not take. */
+WB200_API int whisper_b200_chain_geometry(int grid, int rows, int N, int K, int min_units, int direct, int * out);
 
 #ifdef __cplusplus
 }

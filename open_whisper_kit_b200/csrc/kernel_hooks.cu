@@ -7,6 +7,7 @@
 
 #include "common.cuh"
 #include "mel.h"
+#include "dec_chain.h"
 #include "dec_kernels.h"
 #include "enc_kernels.h"
 #include "skinny_gemm.h"
@@ -265,6 +266,13 @@ WB200_API double whisper_b200_kernel_step_bench(int which, int dtype, int R, int
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     return cuda_failed() ? -1.0 : 1e3 * ms / iters;
+}
+
+WB200_API int whisper_b200_chain_geometry(int grid, int rows, int N, int K, int min_units, int direct, int * out) {
+    if (!out || grid <= 0 || rows <= 0 || rows > 128 || N <= 0 || K <= 0 || N % SG_TILE_COLS != 0 || K % 64 != 0) return -1;
+    const SplitGeom g = direct ? chain_geom_direct(rows, N, K) : chain_geom(grid, rows, N, K, min_units);
+    out[0] = g.tiles; out[1] = g.kpt; out[2] = g.U; out[3] = g.G; out[4] = g.maxc;
+    return 0;
 }
 
 }  // extern "C"
