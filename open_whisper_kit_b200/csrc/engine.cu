@@ -754,6 +754,15 @@ bool Engine::fetch_logits(int row, float * out) {
     return !cuda_failed();
 }
 
+bool Engine::fetch_logits_rows(int row0, int n_rows, float * out) {
+    if (n_rows <= 0) return true;
+    const size_t w = (size_t) model.hp.n_vocab * 4;
+    WB_CUDA(cudaMemcpy2DAsync(out, w, (const float *) logits.p + (size_t) row0 * ld_logits, (size_t) ld_logits * 4, w, n_rows,
+                              cudaMemcpyDeviceToHost, stream));
+    WB_CUDA(cudaStreamSynchronize(stream));
+    return !cuda_failed();
+}
+
 bool Engine::sample_greedy(const std::vector<SampleRow> & srows, const uint32_t * d_mask, const SampleParams & prm,
                            std::vector<SampleOut> & out) {
     const int R = (int) srows.size();

@@ -132,6 +132,7 @@ struct Engine {
     bool decode_chain(const std::vector<DecRow> & rows, const std::vector<int> & logit_rows, size_t cross_layer_stride);
     bool chain_usable(int R);
     bool fetch_logits(int row, float * out);                         // D2H one row (n_vocab floats)
+    bool fetch_logits_rows(int row0, int n_rows, float * out);       // D2H rows [row0, row0 + n_rows) packed [n_rows][n_vocab]
     bool sample_greedy(const std::vector<SampleRow> & srows, const uint32_t * d_mask, const SampleParams & prm,
                        std::vector<SampleOut> & out);
     bool token_prob(const std::vector<SampleRow> & srows, int token, std::vector<float> & out);

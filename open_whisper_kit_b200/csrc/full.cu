@@ -19,9 +19,11 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <map>
 #include <regex>
+#include <thread>
 
 namespace wb {
 
@@ -100,6 +102,27 @@ static void compute_logprobs(const float * logits, int n, std::vector<float> & l
     logsumexp = logf(logsumexp) + logit_max;
     logprobs.resize(n);
     for (int i = 0; i < n; ++i) logprobs[i] = logits[i] > -INFINITY ? logits[i] - logsumexp : -INFINITY;
+}
+
+// The host sampling path works per decoder on private state (its logits / probs copies, its mt19937), as the reference's
+// worker threads do (src/whisper.cpp:7504-7538): run fn(0..n-1) on up to 32 host threads.  Exactly the same arithmetic
+// per item as the serial loop, so results do not depend on the thread count.
+template <typename F> static void parallel_for(int n, F && fn) {
+    const int hw = (int) std::thread::hardware_concurrency();
+    const int n_thr = std::max(1, std::min(n, std::min(hw > 0 ? hw : 4, 32)));
+    if (n_thr <= 1) {
+        for (int i = 0; i < n; ++i) fn(i);
+        return;
+    }
+    std::atomic<int> next{0};
+    std::vector<std::thread> pool;
+    pool.reserve(n_thr - 1);
+    auto work = [&]() {
+        for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) fn(i);
+    };
+    for (int t = 1; t < n_thr; ++t) pool.emplace_back(work);
+    work();
+    for (auto & th : pool) th.join();
 }
 
 // whisper_process_logits, src/whisper.cpp:6177-6445 (grammar branch omitted: out of scope)
@@ -663,7 +686,7 @@ int run_streams(whisper_context & ctx, std::vector<StreamSpec> & specs) {
 
     if (!e.size_cross(ctx.batch_cross, n_streams)) return -7;
     const int n_max = hp.n_text_ctx / 2 - 4;
-    std::vector<float> logits_host((size_t) hp.n_vocab);
+    std::vector<float> logits_host((size_t) hp.n_vocab), logits_rows_host;
 
     auto fail_stream = [&](Stream & s, int rc) {
         s.rc = rc;
@@ -883,6 +906,22 @@ int run_streams(whisper_context & ctx, std::vector<StreamSpec> & specs) {
             for (int i = 0; i < n_max; ++i) {
                 const int64_t ts0 = time_us();
                 bool any_live = false;
+                {   // this iteration's host draws: every live decoder draws from its own distribution with its own mt19937, so the
+                    // draws of different decoders are independent and are made on the host threads; consumed in order below
+                    std::vector<std::pair<int, int>> jobs;
+                    for (int si : act) {
+                        Stream & s = S[si];
+                        if (s.phase != Phase::STEPPING || (s.device_path && s.params.strategy != WHISPER_SAMPLING_BEAM_SEARCH)) continue;
+                        for (int j = 0; j < s.n_decoders_cur; ++j)
+                            if (!s.state->decoders[j].completed && !s.state->decoders[j].failed) jobs.push_back({si, j});
+                    }
+                    parallel_for((int) jobs.size(), [&](int q) {
+                        Stream & s = S[jobs[q].first];
+                        whisper_decoder & d = s.state->decoders[jobs[q].second];
+                        if (s.params.strategy == WHISPER_SAMPLING_BEAM_SEARCH) d.sampled = sample_token_topk_host(vocab, d, s.params.beam_search.beam_size);
+                        else d.sampled.assign(1, sample_token_host(vocab, d, s.t_cur < 1e-6f));
+                    });
+                }
                 for (int si : act) {
                     Stream & s = S[si];
                     if (s.phase != Phase::STEPPING) continue;
@@ -902,12 +941,12 @@ int run_streams(whisper_context & ctx, std::vector<StreamSpec> & specs) {
                                 tok = d.pending;
                                 d.has_pending = false;
                             } else {
-                                tok = sample_token_host(vocab, d, s.t_cur < 1e-6f);
+                                tok = d.sampled[0];
                             }
                             d.sequence.tokens.push_back(tok);
                             d.sequence.sum_logprobs_all += tok.plog;
                         } else {
-                            const auto toks = sample_token_topk_host(vocab, d, p.beam_search.beam_size);
+                            const auto & toks = d.sampled;
                             for (const auto & t : toks) {
                                 bc_per_dec[j].push_back({j, d.seek_delta, d.has_ts, d.sequence});
                                 bc_per_dec[j].back().sequence.tokens.push_back(t);
@@ -1063,12 +1102,23 @@ int run_streams(whisper_context & ctx, std::vector<StreamSpec> & specs) {
                 }
                 const int64_t td1 = time_us();
                 dbg_sel += td1 - td0;
-                for (size_t r = 0; r < owner.size() && ok; ++r) {
-                    Stream & s = S[owner[r].first];
-                    if (s.device_path) continue;
-                    whisper_decoder & d = s.state->decoders[owner[r].second];
-                    ok = e.fetch_logits((int) r, logits_host.data());
-                    if (ok) process_logits_host(ctx, *s.state, d, s.params, static_bits, logits_host.data(), s.t_cur);
+                {   // host-path rows: one D2H for the lot, then whisper_process_logits per decoder on the host threads
+                    std::vector<int> host_rows;
+                    for (size_t r = 0; r < owner.size(); ++r)
+                        if (!S[owner[r].first].device_path) host_rows.push_back((int) r);
+                    if (ok && !host_rows.empty()) {
+                        const int r_lo = host_rows.front(), r_hi = host_rows.back();
+                        logits_rows_host.resize((size_t) (r_hi - r_lo + 1) * hp.n_vocab);
+                        ok = e.fetch_logits_rows(r_lo, r_hi - r_lo + 1, logits_rows_host.data());
+                        if (ok)
+                            parallel_for((int) host_rows.size(), [&](int q) {
+                                const int r = host_rows[q];
+                                Stream & s = S[owner[r].first];
+                                whisper_decoder & d = s.state->decoders[owner[r].second];
+                                process_logits_host(ctx, *s.state, d, s.params, static_bits,
+                                                    logits_rows_host.data() + (size_t) (r - r_lo) * hp.n_vocab, s.t_cur);
+                            });
+                    }
                 }
                 const int64_t td2 = time_us();
                 // timing buckets as the reference: per-call, by batch width

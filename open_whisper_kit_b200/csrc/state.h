@@ -38,6 +38,7 @@ struct whisper_decoder {
     std::vector<float> probs, logits, logprobs;
     std::vector<std::pair<double, int>> logits_id;
     std::mt19937 rng;
+    std::vector<whisper_token_data> sampled;   // this iteration's host draws (made in parallel across decoders, consumed in order)
 
     // device path: the token selected on the device right after the decode step, consumed by the next iteration
     bool has_pending = false;
