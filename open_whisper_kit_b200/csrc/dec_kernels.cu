@@ -301,19 +301,55 @@ template <int NT> __device__ ArgMax block_amax(ArgMax a, ArgMax * sh) {
 
 constexpr int SAMPLE_THREADS = 1024;
 
-// One CTA per decoder row.  Rule order follows whisper_process_logits line by line; the masked logits are written
-// back in place so the later passes (max, sum-exp, timestamp mass, arg-max) read them from L2.
+// One CTA per decoder row, two passes over the row (207 KB, L2-resident right after the logits GEMM).  Rule order follows
+// whisper_process_logits line by line (`allowed`); pass A is an online log-sum-exp that also yields the timestamp mass and
+// the best text logit (src/whisper.cpp:6137-6158, 6336-6361), pass B turns the surviving logits into probabilities exactly
+// as the reference does and takes the arg-max / timestamp statistics (src/whisper.cpp:6460-6517).
+struct LseAcc {          // running maximum and sum of exp(v - m)
+    float m, s;
+};
+__device__ __forceinline__ void lse_add(LseAcc & a, float v) {
+    if (v > a.m) {
+        a.s = a.s * expf(a.m - v) + 1.0f;       // a.m = -inf: 0 * exp(-inf) + 1
+        a.m = v;
+    } else {
+        a.s += expf(v - a.m);
+    }
+}
+__device__ __forceinline__ LseAcc lse_merge(LseAcc a, LseAcc b) {
+    if (b.m == -INFINITY) return a;
+    if (a.m == -INFINITY) return b;
+    const float m = fmaxf(a.m, b.m);
+    return {m, a.s * expf(a.m - m) + b.s * expf(b.m - m)};
+}
+template <int NT> __device__ LseAcc block_lse(LseAcc a, LseAcc * sh) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        LseAcc b;
+        b.m = __shfl_xor_sync(0xffffffffu, a.m, o);
+        b.s = __shfl_xor_sync(0xffffffffu, a.s, o);
+        a = lse_merge(a, b);
+    }
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = a;
+    __syncthreads();
+    LseAcc r = sh[0];
+    for (int i = 1; i < NT / 32; ++i) r = lse_merge(r, sh[i]);
+    __syncthreads();
+    return r;
+}
+
 __global__ void __launch_bounds__(SAMPLE_THREADS)
 sample_greedy_kernel(float * __restrict__ logits, int ld, const SampleRow * __restrict__ srows,
                      const uint32_t * __restrict__ static_mask, SampleParams prm, SampleOut * __restrict__ outs) {
     __shared__ float sh_f[SAMPLE_THREADS / 32];
     __shared__ double sh_d[SAMPLE_THREADS / 32];
     __shared__ ArgMax sh_a[SAMPLE_THREADS / 32];
+    __shared__ LseAcc sh_l[SAMPLE_THREADS / 32];
     const int r = blockIdx.x;
     pdl_trigger();
     pdl_wait();
     const SampleRow sr = srows[r];
-    float * l = logits + (size_t) sr.logits_row * ld;
+    const float * l = logits + (size_t) sr.logits_row * ld;
     const int V = prm.n_vocab, beg = prm.token_beg, eot = prm.token_eot;
     const int tid = threadIdx.x;
 
@@ -323,13 +359,8 @@ sample_greedy_kernel(float * __restrict__ logits, int ld, const SampleRow * __re
     const int init_lim = (is_initial && prm.max_initial_ts > 0.0f) ? beg + prm.tid0 + 1 : V;
     const int mono_lim = sr.has_ts ? beg + sr.seek_delta / 2 : beg;
     const float inv_temp = prm.temperature > 0.0f ? prm.temperature : 1.0f;
-
-    // pass 1: rules -> masked logits; track max over all, over timestamps, over text
-    float m_all = -INFINITY;
-    for (int i = tid; i < V; i += SAMPLE_THREADS) {
-        float v = l[i];
-        if (prm.temperature > 0.0f) v = v / inv_temp;
-        bool kill = (static_mask[i >> 5] >> (i & 31)) & 1u;
+    auto allowed = [&](int i) {
+        bool kill = (__ldg(static_mask + (i >> 5)) >> (i & 31)) & 1u;
         if (is_initial && prm.suppress_blank && (i == eot || i == prm.token_space)) kill = true;
         if (prm.no_timestamps && i >= beg) kill = true;
         if (last_ts) {
@@ -341,49 +372,41 @@ sample_greedy_kernel(float * __restrict__ logits, int ld, const SampleRow * __re
         }
         if (i >= init_lim) kill = true;
         if (i >= beg && i < mono_lim) kill = true;
-        if (kill) v = -INFINITY;
-        l[i] = v;
-        m_all = fmaxf(m_all, v);
-    }
-    m_all = block_max<SAMPLE_THREADS>(m_all, sh_f);
-    __syncthreads();
+        return !kill;
+    };
+    auto value = [&](int i) {
+        float v = l[i];
+        if (prm.temperature > 0.0f) v = v / inv_temp;
+        return v;
+    };
 
-    // pass 2: log-sum-exp  (whisper_compute_logprobs, src/whisper.cpp:6137-6158)
-    float se = 0.0f;
+    // pass A: log-sum-exp over the allowed tokens, the same over the timestamp tokens, best text logit
+    LseAcc all = {-INFINITY, 0.0f}, ts = {-INFINITY, 0.0f};
+    float m_text = -INFINITY;
     for (int i = tid; i < V; i += SAMPLE_THREADS) {
-        const float v = l[i];
-        if (v > -INFINITY) se += expf(v - m_all);
+        if (!allowed(i)) continue;
+        const float v = value(i);
+        if (v == -INFINITY) continue;
+        lse_add(all, v);
+        if (i >= beg) lse_add(ts, v);
+        else m_text = fmaxf(m_text, v);
     }
-    se = block_sum<SAMPLE_THREADS>(se, sh_f);
-    const float logZ = logf(se) + m_all;
+    all = block_lse<SAMPLE_THREADS>(all, sh_l);
+    ts = block_lse<SAMPLE_THREADS>(ts, sh_l);
+    m_text = block_max<SAMPLE_THREADS>(m_text, sh_f);
+    const float logZ = logf(all.s) + all.m;
+    // if the probability mass of all timestamps exceeds that of any single text token, only timestamps survive
+    const bool mask_text = ts.s > 0.0f && (logf(ts.s) + ts.m) - logZ > m_text - logZ;
 
-    // pass 3: timestamp mass vs best text token  (src/whisper.cpp:6336-6361)
-    float lp_ts_max = -INFINITY, lp_text_max = -INFINITY;
-    for (int i = tid; i < V; i += SAMPLE_THREADS) {
-        const float v = l[i];
-        const float lp = v > -INFINITY ? v - logZ : -INFINITY;
-        if (i >= beg) lp_ts_max = fmaxf(lp_ts_max, lp);
-        else lp_text_max = fmaxf(lp_text_max, lp);
-    }
-    lp_ts_max = block_max<SAMPLE_THREADS>(lp_ts_max, sh_f);
-    lp_text_max = block_max<SAMPLE_THREADS>(lp_text_max, sh_f);
-    float ts_se = 0.0f;
-    for (int i = beg + tid; i < V; i += SAMPLE_THREADS) {
-        const float v = l[i];
-        if (v > -INFINITY) ts_se += expf((v - logZ) - lp_ts_max);
-    }
-    ts_se = block_sum<SAMPLE_THREADS>(ts_se, sh_f);
-    float ts_lp = -INFINITY;
-    if (ts_se > 0.0f) ts_lp = logf(ts_se) + lp_ts_max;
-    const bool mask_text = ts_lp > lp_text_max;
-
-    // pass 4: probs, greedy arg-max (first maximal index), timestamp statistics  (src/whisper.cpp:6460-6517)
+    // pass B: probs, greedy arg-max (first maximal index), timestamp statistics
     ArgMax best = {0.0f, 0x7fffffff}, best_ts = {0.0f, 0x7fffffff}, second = {0.0f, 0x7fffffff};
     double sum_ts = 0.0;
     for (int i = tid; i < V; i += SAMPLE_THREADS) {
-        const float v = l[i];
         float p = 0.0f;
-        if (v > -INFINITY && !(mask_text && i < beg)) p = expf(v - logZ);
+        if (allowed(i) && !(mask_text && i < beg)) {
+            const float v = value(i);
+            if (v > -INFINITY) p = expf(v - logZ);
+        }
         if (p > 0.0f) {
             const ArgMax cur = {p, i};
             if (amax(best, cur).i == i) {
@@ -392,9 +415,7 @@ sample_greedy_kernel(float * __restrict__ logits, int ld, const SampleRow * __re
             } else {
                 second = amax(second, cur);
             }
-            if (i >= beg) {
-                best_ts = amax(best_ts, ArgMax{p, i});
-            }
+            if (i >= beg) best_ts = amax(best_ts, ArgMax{p, i});
         }
         if (i >= beg) sum_ts += (double) p;
     }
@@ -410,7 +431,7 @@ sample_greedy_kernel(float * __restrict__ logits, int ld, const SampleRow * __re
         SampleOut o;
         o.id = best.i == 0x7fffffff ? 0 : best.i;
         o.p = best.i == 0x7fffffff ? 0.0f : best.v;
-        o.plog = best.i == 0x7fffffff ? 0.0f : (l[o.id] - logZ);
+        o.plog = best.i == 0x7fffffff ? 0.0f : (value(o.id) - logZ);
         o.tid = best_ts.i == 0x7fffffff ? 0 : best_ts.i;
         o.pt = (float) ((double) (best_ts.i == 0x7fffffff ? 0.0f : best_ts.v) / (sum_ts + 1e-10));
         o.ptsum = (float) sum_ts;
@@ -419,7 +440,7 @@ sample_greedy_kernel(float * __restrict__ logits, int ld, const SampleRow * __re
             o.pt = o.p;
         }
         o.runner_up = second.i == 0x7fffffff ? -1 : second.i;
-        o.gap = (best.i != 0x7fffffff && second.i != 0x7fffffff) ? l[best.i] - l[second.i] : INFINITY;
+        o.gap = (best.i != 0x7fffffff && second.i != 0x7fffffff) ? value(best.i) - value(second.i) : INFINITY;
         outs[r] = o;
     }
 }
