@@ -91,6 +91,11 @@ WB200_API int whisper_b200_kernel_skinny_gemm(int dtype, int M, int N, int K, co
                                               const float * bias, float scale, int scale_cols, int gelu,
                                               const float * resid, uint16_t * out16, float * out32);
 
+/* The same GEMM on tcgen05 / TMEM fed by TMA (csrc/tc_skinny.cu), the default of the decoder step. */
+WB200_API int whisper_b200_kernel_tc_skinny_gemm(int dtype, int M, int N, int K, const uint16_t * a, const uint16_t * w,
+                                                 const float * bias, float scale, int scale_cols, int gelu,
+                                                 const float * resid, uint16_t * out16, float * out32);
+
 WB200_API double whisper_b200_kernel_gemm_bench(int dtype, int M, int N, int K, int gelu, int iters);
 
 /* Average microseconds of one decoder-step kernel launched back to back: which = 0 LayerNorm, 1 cross-attention,

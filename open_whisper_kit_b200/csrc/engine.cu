@@ -11,6 +11,7 @@
 #include <algorithm>
 
 #include "tc_gemm.h"
+#include "tc_skinny.h"
 
 namespace wb {
 
@@ -387,7 +388,9 @@ bool Engine::decode(const std::vector<DecRow> & rows, const std::vector<int> & l
     auto gemm = [&](const GemmArgs & g) {
         prof_begin(gemm_cls, ((double) g.N * g.K + (double) g.M * (g.N + g.K)) * 2.0);   // bytes: weights + activations
         // few rows: stream the weights with every SM (skinny_gemm.cu); many rows (long prompts): tensor-core tiles
-        ok = ok && (g.M <= 128 ? skinny_gemm(g, skinny_ws, stream) : tc_gemm(g, stream));
+        // few rows: stream the weights with every SM -- tcgen05 version (tc_skinny.cu) unless WHISPER_B200_TC_SKINNY=0
+        static const bool tcs = !(getenv("WHISPER_B200_TC_SKINNY") && atoi(getenv("WHISPER_B200_TC_SKINNY")) == 0);
+        ok = ok && (g.M <= 128 ? (tcs && tc_skinny_usable(g) ? tc_skinny_gemm(g, stream) : skinny_gemm(g, skinny_ws, stream)) : tc_gemm(g, stream));
         prof_end();
         n_kernel_launches += 1;
     };

@@ -2,6 +2,7 @@
 // They take HOST buffers, run the CUDA kernel and copy the result back, so the parity tests can compare
 // each kernel with the oracle on identical inputs; the *_bench variants time the kernel with CUDA events
 // on device-resident data.
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -12,6 +13,7 @@
 #include "enc_kernels.h"
 #include "skinny_gemm.h"
 #include "tc_gemm.h"
+#include "tc_skinny.h"
 #include "whisper_b200.h"
 
 using namespace wb;
@@ -117,7 +119,7 @@ WB200_API double whisper_b200_kernel_log_mel_bench(int n_streams, int n_samples,
     return cuda_failed() ? -1.0 : total / iters;
 }
 
-static int gemm_hook(bool skinny, int dtype, int M, int N, int K, const uint16_t * a, const uint16_t * w, const float * bias,
+static int gemm_hook(int skinny /* 0 tc_gemm, 1 skinny_gemm, 2 tc_skinny_gemm */, int dtype, int M, int N, int K, const uint16_t * a, const uint16_t * w, const float * bias,
                      float scale, int scale_cols, int gelu, const float * pos, int pos_rows, const float * resid,
                      uint16_t * out16, float * out32) {
     cuda_clear_failure();
@@ -145,7 +147,9 @@ static int gemm_hook(bool skinny, int dtype, int M, int N, int K, const uint16_t
     g.out16 = out16 ? d_o16.p : nullptr; g.ldo16 = ldo;
     g.out32 = out32 ? d_o32.as<float>() : nullptr; g.ldo32 = ldo;
     SkinnyWorkspace sws;
-    if (skinny) {
+    if (skinny == 2) {
+        if (!tc_skinny_gemm(g, 0)) return -2;
+    } else if (skinny) {
         // twice: the second launch checks that the arrival counters were left at zero
         if (!skinny_gemm(g, sws, 0) || !skinny_gemm(g, sws, 0)) return -2;
     } else if (!tc_gemm(g, 0)) {
@@ -162,13 +166,19 @@ static int gemm_hook(bool skinny, int dtype, int M, int N, int K, const uint16_t
 WB200_API int whisper_b200_kernel_gemm(int dtype, int M, int N, int K, const uint16_t * a, const uint16_t * w,
                                        const float * bias, float scale, int scale_cols, int gelu, const float * pos,
                                        int pos_rows, const float * resid, uint16_t * out16, float * out32) {
-    return gemm_hook(false, dtype, M, N, K, a, w, bias, scale, scale_cols, gelu, pos, pos_rows, resid, out16, out32);
+    return gemm_hook(0, dtype, M, N, K, a, w, bias, scale, scale_cols, gelu, pos, pos_rows, resid, out16, out32);
 }
 
 WB200_API int whisper_b200_kernel_skinny_gemm(int dtype, int M, int N, int K, const uint16_t * a, const uint16_t * w,
                                               const float * bias, float scale, int scale_cols, int gelu,
                                               const float * resid, uint16_t * out16, float * out32) {
-    return gemm_hook(true, dtype, M, N, K, a, w, bias, scale, scale_cols, gelu, nullptr, 0, resid, out16, out32);
+    return gemm_hook(1, dtype, M, N, K, a, w, bias, scale, scale_cols, gelu, nullptr, 0, resid, out16, out32);
+}
+
+WB200_API int whisper_b200_kernel_tc_skinny_gemm(int dtype, int M, int N, int K, const uint16_t * a, const uint16_t * w,
+                                                 const float * bias, float scale, int scale_cols, int gelu,
+                                                 const float * resid, uint16_t * out16, float * out32) {
+    return gemm_hook(2, dtype, M, N, K, a, w, bias, scale, scale_cols, gelu, nullptr, 0, resid, out16, out32);
 }
 
 // Device-resident GEMM timing (random-ish operands); returns average ms.  M <= 128 times the weight-streaming kernel.
@@ -214,7 +224,8 @@ WB200_API double whisper_b200_kernel_gemm_bench(int dtype, int M, int N, int K, 
     WB_CUDA(cudaEventCreate(&e0));
     WB_CUDA(cudaEventCreate(&e1));
     SkinnyWorkspace sws;
-    auto run = [&]() { return M <= 128 ? skinny_gemm(g, sws, 0) : tc_gemm(g, 0); };
+    static const bool tcs = !(getenv("WHISPER_B200_TC_SKINNY") && atoi(getenv("WHISPER_B200_TC_SKINNY")) == 0);
+    auto run = [&]() { return M <= 128 ? (tcs ? tc_skinny_gemm(g, 0) : skinny_gemm(g, sws, 0)) : tc_gemm(g, 0); };
     for (int i = 0; i < 3; ++i)
         if (!run()) return -1.0;
     WB_CUDA(cudaEventRecord(e0, 0));

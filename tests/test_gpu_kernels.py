@@ -118,6 +118,7 @@ def gelu_ref(v, dtype):
 
 def run_gemm(lib, dtype, M, N, K, bias=False, scale_cols=0, scale=1.0, gelu=False, pos_rows=0, resid=False, seed=0,
              skinny=False):
+    # skinny: False = tiled tcgen05 GEMM, True/1 = HMMA weight-streaming GEMM, 2 = tcgen05 weight-streaming GEMM
     rng = np.random.default_rng(seed)
     a = rng.standard_normal((M, K), dtype=np.float32)
     w = (rng.standard_normal((N, K), dtype=np.float32) / np.sqrt(K)).astype(np.float32)
@@ -128,7 +129,8 @@ def run_gemm(lib, dtype, M, N, K, bias=False, scale_cols=0, scale=1.0, gelu=Fals
     o16 = np.zeros((M, N), dtype=np.uint16)
     o32 = np.zeros((M, N), dtype=np.float32)
     if skinny:
-        rc = lib.whisper_b200_kernel_skinny_gemm(dtype, M, N, K, ab.ctypes.data_as(U16P), wb.ctypes.data_as(U16P),
+        fn = lib.whisper_b200_kernel_tc_skinny_gemm if skinny == 2 else lib.whisper_b200_kernel_skinny_gemm
+        rc = fn(dtype, M, N, K, ab.ctypes.data_as(U16P), wb.ctypes.data_as(U16P),
                                                  b.ctypes.data_as(FP) if bias else None, scale, scale_cols, int(gelu),
                                                  r.ctypes.data_as(FP) if resid else None, o16.ctypes.data_as(U16P),
                                                  o32.ctypes.data_as(FP))
@@ -203,5 +205,23 @@ def test_skinny_gemm(lib, shape, dtype):
     print(f"skinny {shape} dtype={dtype}: max|d| = {err:.3e}")
     assert err <= 2e-3 * max(1.0, np.abs(ref).max())
     ref, o32, o16 = run_gemm(lib, dtype, M, N, K, bias=True, gelu=True, seed=M + N + K, skinny=True)
+    tol = 2.0 ** -9 if dtype == 0 else 2e-3
+    assert np.abs(o32 - ref).max() <= tol * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("dtype", [0, 1])
+@pytest.mark.parametrize("shape", SKINNY_SHAPES)
+def test_tc_skinny_gemm(lib, shape, dtype):
+    """Same contract as test_skinny_gemm for the tcgen05 weight-streaming GEMM (TMA operands, TMEM accumulator,
+    cluster split-K with ordered DSMEM reduction), including the half-precision output copy."""
+    M, N, K = shape
+    ref, o32, o16 = run_gemm(lib, dtype, M, N, K, bias=True, scale_cols=N // 3, scale=64.0 ** -0.25, resid=True,
+                             seed=M * 7 + N + K, skinny=2)
+    err = np.abs(o32 - ref).max()
+    print(f"tc_skinny {shape} dtype={dtype}: max|d| = {err:.3e}")
+    assert err <= 2e-3 * max(1.0, np.abs(ref).max())
+    half_tol = 2.0 ** -9 if dtype == 0 else 2.0 ** -7
+    assert np.abs(o16 - ref).max() <= half_tol * max(1.0, np.abs(ref).max())
+    ref, o32, o16 = run_gemm(lib, dtype, M, N, K, bias=True, gelu=True, seed=M + N + K, skinny=2)
     tol = 2.0 ** -9 if dtype == 0 else 2e-3
     assert np.abs(o32 - ref).max() <= tol * max(1.0, np.abs(ref).max())
