@@ -17,9 +17,14 @@
 #include <cooperative_groups.h>
 #include <cuda.h>
 
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <type_traits>
 #include <unordered_map>
+#include <vector>
 
 #include "ptx.cuh"
 
@@ -31,7 +36,11 @@ namespace {
 
 constexpr int TB = 64;                 // output tile columns and k per stage
 constexpr int T_THREADS = 192;
-constexpr int T_STAGES = 4;
+// k-blocks in flight per CTA: the loop is bound by load latency (~1.2 us a round trip), so deeper is faster -- but two CTAs
+// of 5 x 16 KB still fit the 164 KB shared-memory carve-out; one more stage moves the SM to the 228 KB carve-out, which
+// stays in force for the cross-attention kernel that follows and costs it a third of its speed (28 KB of L1 left).
+constexpr int T_STAGES = 5;
+constexpr int T_CTRL_BYTES = 128;         // mbarriers + TMEM base address, behind the ring
 constexpr int T_PITCH = 68;               // floats per row of the f32 tile in shared memory
 
 struct TcSkinnyParams {
@@ -39,10 +48,22 @@ struct TcSkinnyParams {
     const float * bias;
     float scale; int scale_cols;
     int gelu, ref_f16_gelu;
+    int vec_io;                        // bias / residual / outputs are 16-byte (8-byte for 16-bit) addressable per 4 columns
     const float * resid; int ldr;
     void * out16; int ldo16;
     float * out32; int ldo32;
+    unsigned long long * trace;        // development aid (WHISPER_B200_TCS_TRACE): 8 time stamps per CTA, or null
 };
+
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define TS_STAMP(i)                                                                                       \
+    do {                                                                                                  \
+        if (p.trace && tid == 0) p.trace[((size_t) (blockIdx.y * gridDim.x + blockIdx.x)) * 8 + (i)] = gtime(); \
+    } while (0)
 
 __device__ __forceinline__ void ts_wait(uint64_t * bar, uint32_t parity) {        // bounded: trap instead of hanging the GPU
     for (unsigned spins = 0; !ptx::mbar_try_wait(bar, parity); ++spins)
@@ -61,10 +82,8 @@ template <typename T16> __device__ __forceinline__ float gelu_ts(float v, int re
 template <typename T16>
 __global__ void __launch_bounds__(T_THREADS, 2)
 tc_skinny_kernel(const __grid_constant__ TMap tm_x, const __grid_constant__ TMap tm_w, const TcSkinnyParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t b_full[T_STAGES], b_empty[T_STAGES], b_acc;
-    __shared__ uint32_t s_tmem;
-    uint8_t * smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // no static shared memory and no alignment slack: the dynamic window starts 1024-byte aligned (checked below)
+    extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nt = blockIdx.x, ks = blockIdx.y;
     const int n0 = nt * TB;
@@ -72,9 +91,17 @@ tc_skinny_kernel(const __grid_constant__ TMap tm_x, const __grid_constant__ TMap
     const int kb0 = (int) ((long long) kblocks * ks / p.KS), kb1 = (int) ((long long) kblocks * (ks + 1) / p.KS);
     const int nkb = kb1 - kb0;
     const uint32_t x_bytes = (uint32_t) p.rows_pad * 128u, stage_bytes = x_bytes + TB * 128u;
-    float * tile_sum = reinterpret_cast<float *>(smem + T_STAGES * stage_bytes);          // [rows_pad][T_PITCH] f32
+    uint64_t * b_full = reinterpret_cast<uint64_t *>(smem + T_STAGES * stage_bytes);
+    uint64_t * b_empty = b_full + T_STAGES;
+    uint64_t & b_acc = b_empty[T_STAGES];
+    uint32_t & s_tmem = *reinterpret_cast<uint32_t *>(b_empty + T_STAGES + 1);
+    static_assert((2 * T_STAGES + 2) * 8 <= T_CTRL_BYTES, "control block");
+    // [rows_pad][T_PITCH] f32; overlays the operand ring, which is dead once the last MMA has completed
+    float * tile_sum = reinterpret_cast<float *>(smem);
 
+    TS_STAMP(0);          // CTA start
     if (tid == 0) {
+        if (ptx::smem_u32(smem) & 1023u) __trap();
         for (int s = 0; s < T_STAGES; ++s) {
             ptx::mbar_init(&b_full[s], 1);
             ptx::mbar_init(&b_empty[s], 1);
@@ -133,11 +160,13 @@ tc_skinny_kernel(const __grid_constant__ TMap tm_x, const __grid_constant__ TMap
         // ===== accumulator -> this CTA's f32 tile in shared memory =====
         // (a CTA whose K slice is empty contributes zeros)
         pdl_wait();
+        TS_STAMP(1);      // predecessor grid complete
         const int row = warp * 32 + lane;
         if (nkb > 0) {
             ts_wait(&b_acc, 0);
             ptx::tc_fence_after();
         }
+        TS_STAMP(2);      // accumulator complete
         if (warp * 32 < p.rows_pad) {
 #pragma unroll 1
             for (int c = 0; c < 2; ++c) {
@@ -162,47 +191,102 @@ tc_skinny_kernel(const __grid_constant__ TMap tm_x, const __grid_constant__ TMap
     }
     __syncthreads();
     pdl_wait();          // every thread takes part in the epilogue below (residual reads, output writes)
+    TS_STAMP(3);          // tile in shared memory
 
     // ---- cluster-wide reduction and epilogue: every CTA of the cluster (one per K split) finishes a slice of the tile ----
-    const int n_elem = p.rows_pad * TB;
-    int e_lo = 0, e_hi = n_elem;
+    // Work unit = four consecutive columns of one row (float4): all loads of a batch of units -- the KS partial tiles over
+    // DSMEM, bias, residual -- are issued before the first use, so a thread pays one round trip per batch, not per element.
+    const int n_vec = p.rows_pad * (TB / 4);
+    int v_lo = 0, v_hi = n_vec;
     cg::cluster_group cluster = cg::this_cluster();
     if (p.KS > 1) {
         cluster.sync();
-        e_lo = (int) ((long long) n_elem * ks / p.KS) & ~3;
-        e_hi = ks == p.KS - 1 ? n_elem : ((int) ((long long) n_elem * (ks + 1) / p.KS) & ~3);
+        TS_STAMP(4);      // all K splits of the tile are in shared memory
+        v_lo = (int) ((long long) n_vec * ks / p.KS);
+        v_hi = (int) ((long long) n_vec * (ks + 1) / p.KS);
     }
     T16 * out16 = reinterpret_cast<T16 *>(p.out16);
     auto finish = [&](auto ks_tag) {
         constexpr int KSC = decltype(ks_tag)::value;
+        constexpr int U = KSC == 1 ? 4 : (KSC == 2 ? 4 : (KSC <= 4 ? 2 : 1));       // units in flight per thread
         const float * peer[KSC];
 #pragma unroll
         for (int r = 0; r < KSC; ++r) peer[r] = KSC > 1 ? cluster.map_shared_rank(tile_sum, r) : tile_sum;
-        for (int e = e_lo + tid; e < e_hi; e += T_THREADS) {
-            float part[KSC];
-            const int ea = (e >> 6) * T_PITCH + (e & 63);
+        for (int base = v_lo; base < v_hi; base += U * T_THREADS) {
+            float4 part[U][KSC], rs[U], bs[U];
+            bool live[U];
 #pragma unroll
-            for (int r = 0; r < KSC; ++r) part[r] = peer[r][ea];         // all remote loads in flight together
-            float x = part[0];
+            for (int u = 0; u < U; ++u) {
+                const int v = base + u * T_THREADS + tid;
+                const int m = v >> 4, n = n0 + ((v & 15) << 2);
+                live[u] = v < v_hi && m < p.M && n < p.N;
+                rs[u] = bs[u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (live[u]) {
+                    if (p.vec_io && n + 3 < p.N) {
+                        if (p.bias) bs[u] = __ldg(reinterpret_cast<const float4 *>(p.bias + n));
+                        if (p.resid) rs[u] = *reinterpret_cast<const float4 *>(p.resid + (size_t) m * p.ldr + n);
+                    } else {
+                        float b4[4] = {0.0f, 0.0f, 0.0f, 0.0f}, r4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                        for (int i = 0; i < 4; ++i)
+                            if (n + i < p.N) {
+                                if (p.bias) b4[i] = __ldg(p.bias + n + i);
+                                if (p.resid) r4[i] = p.resid[(size_t) m * p.ldr + n + i];
+                            }
+                        bs[u] = make_float4(b4[0], b4[1], b4[2], b4[3]);
+                        rs[u] = make_float4(r4[0], r4[1], r4[2], r4[3]);
+                    }
+                    const int ea = m * T_PITCH + ((v & 15) << 2);
 #pragma unroll
-            for (int r = 1; r < KSC; ++r) x += part[r];                   // fixed rank order
-            const int m = e >> 6, n = n0 + (e & 63);
-            if (m >= p.M || n >= p.N) continue;
-            if (p.bias) x += __ldg(p.bias + n);
-            if (n < p.scale_cols) x *= p.scale;
-            if (p.gelu) x = gelu_ts<T16>(x, p.ref_f16_gelu);
-            if (p.resid) x += p.resid[(size_t) m * p.ldr + n];
-            if (p.out32) p.out32[(size_t) m * p.ldo32 + n] = x;
-            if (out16) out16[(size_t) m * p.ldo16 + n] = Half16<T16>::from_f(x);
+                    for (int r = 0; r < KSC; ++r) part[u][r] = *reinterpret_cast<const float4 *>(peer[r] + ea);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (!live[u]) continue;
+                const int v = base + u * T_THREADS + tid;
+                const int m = v >> 4, n = n0 + ((v & 15) << 2);
+                float x[4] = {part[u][0].x, part[u][0].y, part[u][0].z, part[u][0].w};
+#pragma unroll
+                for (int r = 1; r < KSC; ++r) {                                   // fixed rank order
+                    x[0] += part[u][r].x; x[1] += part[u][r].y; x[2] += part[u][r].z; x[3] += part[u][r].w;
+                }
+                const float b4[4] = {bs[u].x, bs[u].y, bs[u].z, bs[u].w}, r4[4] = {rs[u].x, rs[u].y, rs[u].z, rs[u].w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float y = x[i] + b4[i];
+                    if (n + i < p.scale_cols) y *= p.scale;
+                    if (p.gelu) y = gelu_ts<T16>(y, p.ref_f16_gelu);
+                    x[i] = y + r4[i];
+                }
+                if (p.vec_io && n + 3 < p.N) {
+                    if (p.out32) *reinterpret_cast<float4 *>(p.out32 + (size_t) m * p.ldo32 + n) = make_float4(x[0], x[1], x[2], x[3]);
+                    if (out16) {
+                        const T16 h[4] = {Half16<T16>::from_f(x[0]), Half16<T16>::from_f(x[1]), Half16<T16>::from_f(x[2]), Half16<T16>::from_f(x[3])};
+                        *reinterpret_cast<uint2 *>(out16 + (size_t) m * p.ldo16 + n) = *reinterpret_cast<const uint2 *>(h);
+                    }
+                } else {
+                    for (int i = 0; i < 4; ++i)
+                        if (n + i < p.N) {
+                            if (p.out32) p.out32[(size_t) m * p.ldo32 + n + i] = x[i];
+                            if (out16) out16[(size_t) m * p.ldo16 + n + i] = Half16<T16>::from_f(x[i]);
+                        }
+                }
+            }
         }
     };
     switch (p.KS) {
         case 1: finish(std::integral_constant<int, 1>{}); break;
         case 2: finish(std::integral_constant<int, 2>{}); break;
+        case 3: finish(std::integral_constant<int, 3>{}); break;
         case 4: finish(std::integral_constant<int, 4>{}); break;
+        case 5: finish(std::integral_constant<int, 5>{}); break;
+        case 6: finish(std::integral_constant<int, 6>{}); break;
+        case 7: finish(std::integral_constant<int, 7>{}); break;
         default: finish(std::integral_constant<int, 8>{}); break;
     }
+    TS_STAMP(5);          // outputs written
     if (p.KS > 1) cluster.sync();     // peers may still be reading this CTA's tile
+    TS_STAMP(6);
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 0) {
@@ -218,6 +302,62 @@ struct WKey {
 };
 struct WKeyHash {
     size_t operator()(const WKey & k) const { return std::hash<const void *>()(k.w) ^ ((size_t) k.N * 1315423911u) ^ ((size_t) k.K << 20); }
+};
+
+// ---- development trace: WHISPER_B200_TCS_TRACE=<first launch>:<launches> records per-CTA time stamps, printed at exit ----
+struct TraceRec { int n_tiles, KS, M, N, K; };
+struct TcsTrace {
+    bool on = false;
+    long first = 0, count = 0, seen = 0;
+    unsigned long long * dev = nullptr;
+    std::vector<TraceRec> recs;
+    static constexpr size_t kPerLaunch = 1024 * 8;       // up to 1024 CTAs x 8 stamps
+    TcsTrace() {
+        const char * e = getenv("WHISPER_B200_TCS_TRACE");
+        if (!e) return;
+        first = atol(e);
+        const char * c = strchr(e, ':');
+        count = c ? atol(c + 1) : 200;
+        if (count <= 0) return;
+        if (cudaMalloc(&dev, (size_t) count * kPerLaunch * 8) != cudaSuccess) return;
+        cudaMemset(dev, 0, (size_t) count * kPerLaunch * 8);
+        on = true;
+    }
+    unsigned long long * slot(const TraceRec & r) {
+        if (!on) return nullptr;
+        const long i = seen++;
+        if (i < first || i >= first + count || (size_t) r.n_tiles * r.KS > 1024) return nullptr;
+        recs.push_back(r);
+        return dev + (size_t) (recs.size() - 1) * kPerLaunch;
+    }
+    ~TcsTrace() {
+        if (!on || recs.empty()) return;
+        cudaDeviceSynchronize();
+        std::vector<unsigned long long> h(recs.size() * kPerLaunch);
+        if (cudaMemcpy(h.data(), dev, h.size() * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return;
+        unsigned long long prev_end = 0;
+        fprintf(stderr, "tcs_trace: per launch, ns relative to the first CTA start: [min median max] of each stamp over the CTAs\n");
+        fprintf(stderr, "tcs_trace: stamps = start, dep_done, acc_done, tile_smem, cluster_in, out_written, end\n");
+        for (size_t l = 0; l < recs.size(); ++l) {
+            const TraceRec & r = recs[l];
+            const int n = r.n_tiles * r.KS;
+            const unsigned long long * t = h.data() + l * kPerLaunch;
+            unsigned long long t0 = ~0ull, t_end = 0;
+            for (int c = 0; c < n; ++c) { if (t[c * 8] && t[c * 8] < t0) t0 = t[c * 8]; if (t[c * 8 + 6] > t_end) t_end = t[c * 8 + 6]; }
+            fprintf(stderr, "tcs_trace %3zu M=%d N=%d K=%d grid=%dx%d gap_from_prev_end=%lld |", l, r.M, r.N, r.K, r.n_tiles, r.KS,
+                    prev_end ? (long long) (t0 - prev_end) : 0ll);
+            for (int s = 0; s < 7; ++s) {
+                if (r.KS == 1 && s == 4) continue;
+                std::vector<long long> v;
+                for (int c = 0; c < n; ++c) if (t[c * 8 + s]) v.push_back((long long) (t[c * 8 + s] - t0));
+                if (v.empty()) continue;
+                std::sort(v.begin(), v.end());
+                fprintf(stderr, " s%d[%lld %lld %lld]", s, v.front(), v[v.size() / 2], v.back());
+            }
+            fprintf(stderr, "\n");
+            prev_end = t_end;
+        }
+    }
 };
 
 }  // namespace
@@ -238,10 +378,11 @@ bool tc_skinny_gemm(const GemmArgs & g, cudaStream_t stream) {
         if (n_sm <= 0) n_sm = 148;
     }
     const int n_tiles = ceil_div(g.N, TB), kblocks = g.K / TB;
-    // K splits = cluster size (<= 8 portable): enough CTAs to keep one wave of SMs streaming, >= 2 k-blocks each
-    int want = std::min(ceil_div(n_sm, n_tiles), std::max(1, kblocks / 2));
-    int KS = 1;
-    while (KS < 8 && KS * 2 <= want) KS *= 2;
+    // K splits = cluster size (<= 8 portable).  Enough CTAs to give every SM work, and enough that a CTA's whole K range is
+    // in flight at once (T_STAGES k-blocks) while the grid still fits one wave of two CTAs per SM; >= 2 k-blocks per CTA.
+    int KS = std::max(ceil_div(n_sm, n_tiles), ceil_div(kblocks, T_STAGES));
+    KS = std::min(KS, 8);
+    while (KS > 1 && (n_tiles * KS > 2 * n_sm || KS > kblocks / 2)) --KS;
 
     static std::mutex mu;
     static std::unordered_map<WKey, TMap, WKeyHash> wmaps;
@@ -264,7 +405,12 @@ bool tc_skinny_gemm(const GemmArgs & g, cudaStream_t stream) {
     p.bias = g.bias; p.scale = g.scale; p.scale_cols = g.scale_cols;
     p.gelu = g.gelu ? 1 : 0; p.ref_f16_gelu = g.dtype == DType::F16 ? 1 : 0;
     p.resid = g.resid; p.ldr = g.ldr; p.out16 = g.out16; p.ldo16 = g.ldo16; p.out32 = g.out32; p.ldo32 = g.ldo32;
-    const int smem = T_STAGES * (rows_pad * 128 + TB * 128) + rows_pad * T_PITCH * 4 + 1024;
+    static TcsTrace trace;
+    p.trace = trace.slot({n_tiles, KS, g.M, g.N, g.K});
+    auto al = [](const void * q, uintptr_t a) { return (reinterpret_cast<uintptr_t>(q) & (a - 1)) == 0; };
+    p.vec_io = al(g.bias, 16) && al(g.resid, 16) && g.ldr % 4 == 0 && al(g.out32, 16) && g.ldo32 % 4 == 0 && al(g.out16, 8) &&
+               g.ldo16 % 4 == 0;
+    const int smem = T_STAGES * (rows_pad * 128 + TB * 128) + T_CTRL_BYTES;
 
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(n_tiles, KS, 1);
@@ -280,7 +426,7 @@ bool tc_skinny_gemm(const GemmArgs & g, cudaStream_t stream) {
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 2;
-    constexpr int kMaxSmem = T_STAGES * (128 * 128 + TB * 128) + 128 * T_PITCH * 4 + 1024;
+    constexpr int kMaxSmem = T_STAGES * (128 * 128 + TB * 128) + T_CTRL_BYTES;
     if (g.dtype == DType::F16) {
         static bool set = false;
         if (!set) {
