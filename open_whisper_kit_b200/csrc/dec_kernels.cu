@@ -9,9 +9,13 @@
 //   sample       whisper_process_logits + whisper_sample_token(best) on the host      6177-6445, 6460-6517
 #include "dec_kernels.h"
 
+#include <cooperative_groups.h>
+
 #include "dec_chain.h"
 
 #include <stdlib.h>
+
+namespace cg = cooperative_groups;
 
 namespace wb {
 
@@ -299,59 +303,65 @@ template <int NT> __device__ ArgMax block_amax(ArgMax a, ArgMax * sh) {
     return r;
 }
 
-constexpr int SAMPLE_THREADS = 1024;
+constexpr int SAMPLE_THREADS = 512;
+constexpr int SAMPLE_CTAS = 2;                 // CTAs (one cluster) per decoder row
+constexpr int SAMPLE_VEC = 13;                 // float4 per thread: 2 * 512 * 13 * 4 = 53248 >= n_vocab of every whisper model
+constexpr int SAMPLE_MASK_WORDS = SAMPLE_THREADS * SAMPLE_VEC * 4 / 32;       // mask words of one CTA's half row
 
-// One CTA per decoder row, two passes over the row (207 KB, L2-resident right after the logits GEMM).  Rule order follows
-// whisper_process_logits line by line (`allowed`); pass A is an online log-sum-exp that also yields the timestamp mass and
-// the best text logit (src/whisper.cpp:6137-6158, 6336-6361), pass B turns the surviving logits into probabilities exactly
-// as the reference does and takes the arg-max / timestamp statistics (src/whisper.cpp:6460-6517).
-struct LseAcc {          // running maximum and sum of exp(v - m)
-    float m, s;
+struct SampleXchg {                            // one slot per cluster-wide reduction: slots are never reused inside a launch
+    float f[4];
+    double d;
+    ArgMax a[2];
 };
-__device__ __forceinline__ void lse_add(LseAcc & a, float v) {
-    if (v > a.m) {
-        a.s = a.s * expf(a.m - v) + 1.0f;       // a.m = -inf: 0 * exp(-inf) + 1
-        a.m = v;
-    } else {
-        a.s += expf(v - a.m);
-    }
-}
-__device__ __forceinline__ LseAcc lse_merge(LseAcc a, LseAcc b) {
-    if (b.m == -INFINITY) return a;
-    if (a.m == -INFINITY) return b;
-    const float m = fmaxf(a.m, b.m);
-    return {m, a.s * expf(a.m - m) + b.s * expf(b.m - m)};
-}
-template <int NT> __device__ LseAcc block_lse(LseAcc a, LseAcc * sh) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        LseAcc b;
-        b.m = __shfl_xor_sync(0xffffffffu, a.m, o);
-        b.s = __shfl_xor_sync(0xffffffffu, a.s, o);
-        a = lse_merge(a, b);
-    }
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = a;
-    __syncthreads();
-    LseAcc r = sh[0];
-    for (int i = 1; i < NT / 32; ++i) r = lse_merge(r, sh[i]);
-    __syncthreads();
-    return r;
-}
 
-__global__ void __launch_bounds__(SAMPLE_THREADS)
+// One cluster of two CTAs per decoder row, each CTA owns half of it.  The row (207 KB, L2-resident right after the logits
+// GEMM) is read ONCE, all loads in flight together, into registers (thread t of CTA c holds elements 4 q .. 4 q + 3 for
+// q = 6656 c + t + 512 j); every later pass works on registers, block-wide results are exchanged through DSMEM and combined
+// in rank order by both CTAs.  The rules of whisper_process_logits are applied in its order (`allowed`) by overwriting the
+// register copy with -inf; the log-softmax, the timestamp-mass rule and the probabilities then follow the reference's own
+// formulation step by step (src/whisper.cpp:6137-6171, 6336-6361); arg-max / timestamp statistics are whisper_sample_token's
+// (6460-6517).
+__global__ void __cluster_dims__(SAMPLE_CTAS, 1, 1) __launch_bounds__(SAMPLE_THREADS)
 sample_greedy_kernel(float * __restrict__ logits, int ld, const SampleRow * __restrict__ srows,
                      const uint32_t * __restrict__ static_mask, SampleParams prm, SampleOut * __restrict__ outs) {
     __shared__ float sh_f[SAMPLE_THREADS / 32];
     __shared__ double sh_d[SAMPLE_THREADS / 32];
     __shared__ ArgMax sh_a[SAMPLE_THREADS / 32];
-    __shared__ LseAcc sh_l[SAMPLE_THREADS / 32];
-    const int r = blockIdx.x;
+    __shared__ uint32_t sh_mask[SAMPLE_MASK_WORDS];
+    __shared__ SampleXchg sh_x[5];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int) cluster.block_rank();
+    const int r = blockIdx.x / SAMPLE_CTAS;
+    const int tid = threadIdx.x;
+    const int V = prm.n_vocab, beg = prm.token_beg, eot = prm.token_eot;
+    const int q0 = rank * (SAMPLE_THREADS * SAMPLE_VEC);             // first float4 of this CTA's half
     pdl_trigger();
+    // the static suppression mask is written once per whisper_full call, before any decoder launch
+    for (int w = tid; w < SAMPLE_MASK_WORDS; w += SAMPLE_THREADS) {
+        const int gw = q0 / 8 + w;
+        sh_mask[w] = gw < (V + 31) / 32 ? __ldg(static_mask + gw) : 0u;
+    }
     pdl_wait();
     const SampleRow sr = srows[r];
     const float * l = logits + (size_t) sr.logits_row * ld;
-    const int V = prm.n_vocab, beg = prm.token_beg, eot = prm.token_eot;
-    const int tid = threadIdx.x;
+
+    float v[SAMPLE_VEC * 4];
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(l) & 15) == 0;
+#pragma unroll
+    for (int j = 0; j < SAMPLE_VEC; ++j) {
+        const int i0 = 4 * (q0 + tid + SAMPLE_THREADS * j);
+        if (vec_ok && i0 + 3 < V) {
+            const float4 q = *reinterpret_cast<const float4 *>(l + i0);
+            v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
+        } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) v[4 * j + c] = i0 + c < V ? l[i0 + c] : -INFINITY;
+        }
+    }
+    __syncthreads();      // sh_mask
+
+    // cluster-wide combination of a block-wide result: publish, sync, read the peer's, combine as (rank 0, rank 1)
+    const SampleXchg * peer_x = cluster.map_shared_rank(sh_x, rank ^ 1);
 
     const bool is_initial = sr.n_tokens == 0;
     const bool last_ts = sr.n_tokens > 0 && sr.last >= beg;
@@ -359,8 +369,8 @@ sample_greedy_kernel(float * __restrict__ logits, int ld, const SampleRow * __re
     const int init_lim = (is_initial && prm.max_initial_ts > 0.0f) ? beg + prm.tid0 + 1 : V;
     const int mono_lim = sr.has_ts ? beg + sr.seek_delta / 2 : beg;
     const float inv_temp = prm.temperature > 0.0f ? prm.temperature : 1.0f;
-    auto allowed = [&](int i) {
-        bool kill = (__ldg(static_mask + (i >> 5)) >> (i & 31)) & 1u;
+    auto allowed = [&](int i, uint32_t mask_word) {
+        bool kill = (mask_word >> (i & 31)) & 1u;
         if (is_initial && prm.suppress_blank && (i == eot || i == prm.token_space)) kill = true;
         if (prm.no_timestamps && i >= beg) kill = true;
         if (last_ts) {
@@ -374,60 +384,118 @@ sample_greedy_kernel(float * __restrict__ logits, int ld, const SampleRow * __re
         if (i >= beg && i < mono_lim) kill = true;
         return !kill;
     };
-    auto value = [&](int i) {
-        float v = l[i];
-        if (prm.temperature > 0.0f) v = v / inv_temp;
-        return v;
-    };
 
-    // pass A: log-sum-exp over the allowed tokens, the same over the timestamp tokens, best text logit
-    LseAcc all = {-INFINITY, 0.0f}, ts = {-INFINITY, 0.0f};
-    float m_text = -INFINITY;
-    for (int i = tid; i < V; i += SAMPLE_THREADS) {
-        if (!allowed(i)) continue;
-        const float v = value(i);
-        if (v == -INFINITY) continue;
-        lse_add(all, v);
-        if (i >= beg) lse_add(ts, v);
-        else m_text = fmaxf(m_text, v);
+    // rules -> -inf; maxima of all / timestamp / text logits
+    float mx = -INFINITY, mx_ts = -INFINITY, mx_text = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < SAMPLE_VEC; ++j) {
+        const int ql = tid + SAMPLE_THREADS * j;                // float4 index inside this CTA's half
+        const int i0 = 4 * (q0 + ql);
+        const uint32_t mw = sh_mask[ql >> 3];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int i = i0 + c;
+            float x = v[4 * j + c];
+            if (prm.temperature > 0.0f) x = x / inv_temp;
+            if (i >= V || !allowed(i, mw)) x = -INFINITY;
+            v[4 * j + c] = x;
+            mx = fmaxf(mx, x);
+            if (i >= beg) mx_ts = fmaxf(mx_ts, x);
+            else mx_text = fmaxf(mx_text, x);
+        }
     }
-    all = block_lse<SAMPLE_THREADS>(all, sh_l);
-    ts = block_lse<SAMPLE_THREADS>(ts, sh_l);
-    m_text = block_max<SAMPLE_THREADS>(m_text, sh_f);
-    const float logZ = logf(all.s) + all.m;
-    // if the probability mass of all timestamps exceeds that of any single text token, only timestamps survive
-    const bool mask_text = ts.s > 0.0f && (logf(ts.s) + ts.m) - logZ > m_text - logZ;
+    mx = block_max<SAMPLE_THREADS>(mx, sh_f);
+    mx_ts = block_max<SAMPLE_THREADS>(mx_ts, sh_f);
+    mx_text = block_max<SAMPLE_THREADS>(mx_text, sh_f);
+    if (tid == 0) {
+        sh_x[0].f[0] = mx; sh_x[0].f[1] = mx_ts; sh_x[0].f[2] = mx_text;
+    }
+    cluster.sync();
+    mx = fmaxf(mx, peer_x[0].f[0]);
+    mx_ts = fmaxf(mx_ts, peer_x[0].f[1]);
+    mx_text = fmaxf(mx_text, peer_x[0].f[2]);
 
-    // pass B: probs, greedy arg-max (first maximal index), timestamp statistics
+    // log-softmax denominator (whisper_compute_logprobs)
+    float se = 0.0f;
+#pragma unroll
+    for (int k = 0; k < SAMPLE_VEC * 4; ++k)
+        if (v[k] > -INFINITY) se += expf(v[k] - mx);
+    se = block_sum<SAMPLE_THREADS>(se, sh_f);
+    if (tid == 0) sh_x[1].f[0] = se;
+    cluster.sync();
+    se = rank == 0 ? se + peer_x[1].f[0] : peer_x[1].f[0] + se;
+    const float logZ = logf(se) + mx;
+
+    // if the probability mass of all timestamps exceeds that of any single text token, only timestamps survive
+    bool mask_text = false;
+    {
+        const float lp_max_ts = mx_ts - logZ;
+        float ts = 0.0f;
+#pragma unroll
+        for (int j = 0; j < SAMPLE_VEC; ++j) {
+            const int i0 = 4 * (q0 + tid + SAMPLE_THREADS * j);
+            if (i0 + 3 < beg) continue;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (i0 + c >= beg && v[4 * j + c] > -INFINITY) ts += expf((v[4 * j + c] - logZ) - lp_max_ts);
+        }
+        ts = block_sum<SAMPLE_THREADS>(ts, sh_f);
+        if (tid == 0) sh_x[2].f[0] = ts;
+        cluster.sync();
+        ts = rank == 0 ? ts + peer_x[2].f[0] : peer_x[2].f[0] + ts;
+        const float timestamp_logprob = ts > 0.0f ? logf(ts) + lp_max_ts : -INFINITY;
+        mask_text = timestamp_logprob > mx_text - logZ;
+    }
+
+    // probs, greedy arg-max (first maximal index), timestamp statistics
     ArgMax best = {0.0f, 0x7fffffff}, best_ts = {0.0f, 0x7fffffff}, second = {0.0f, 0x7fffffff};
     double sum_ts = 0.0;
-    for (int i = tid; i < V; i += SAMPLE_THREADS) {
-        float p = 0.0f;
-        if (allowed(i) && !(mask_text && i < beg)) {
-            const float v = value(i);
-            if (v > -INFINITY) p = expf(v - logZ);
-        }
-        if (p > 0.0f) {
-            const ArgMax cur = {p, i};
-            if (amax(best, cur).i == i) {
-                second = best;
-                best = cur;
-            } else {
-                second = amax(second, cur);
+#pragma unroll
+    for (int j = 0; j < SAMPLE_VEC; ++j) {
+        const int i0 = 4 * (q0 + tid + SAMPLE_THREADS * j);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int i = i0 + c;
+            const float x = v[4 * j + c];
+            float p = 0.0f;
+            if (x > -INFINITY && !(mask_text && i < beg)) p = expf(x - logZ);
+            if (p > 0.0f) {
+                const ArgMax cur = {p, i};
+                if (amax(best, cur).i == i) {
+                    second = best;
+                    best = cur;
+                } else {
+                    second = amax(second, cur);
+                }
+                if (i >= beg) {
+                    best_ts = amax(best_ts, cur);
+                    sum_ts += (double) p;
+                }
             }
-            if (i >= beg) best_ts = amax(best_ts, ArgMax{p, i});
         }
-        if (i >= beg) sum_ts += (double) p;
     }
-    {   // block-wide top-2: the runner-up is the best of (everyone's second, every loser's best)
-        const ArgMax my_best = best;
-        best = block_amax<SAMPLE_THREADS>(best, sh_a);
-        const ArgMax cand = (my_best.i == best.i) ? second : my_best;
-        second = block_amax<SAMPLE_THREADS>(cand, sh_a);
-    }
+    // cluster-wide top-2: the runner-up is the best of (everyone's second, every loser's best)
+    const ArgMax my_best = best;
+    best = block_amax<SAMPLE_THREADS>(best, sh_a);
     best_ts = block_amax<SAMPLE_THREADS>(best_ts, sh_a);
     sum_ts = block_sum_d<SAMPLE_THREADS>(sum_ts, sh_d);
     if (tid == 0) {
+        sh_x[3].a[0] = best; sh_x[3].a[1] = best_ts; sh_x[3].d = sum_ts;
+    }
+    cluster.sync();
+    best = amax(best, peer_x[3].a[0]);
+    best_ts = amax(best_ts, peer_x[3].a[1]);
+    sum_ts = rank == 0 ? sum_ts + peer_x[3].d : peer_x[3].d + sum_ts;
+    second = block_amax<SAMPLE_THREADS>((my_best.i == best.i) ? second : my_best, sh_a);
+    if (tid == 0) sh_x[4].a[0] = second;
+    cluster.sync();
+    second = amax(second, peer_x[4].a[0]);
+    if (tid == 0 && rank == 0) {
+        auto value = [&](int i) {
+            float x = l[i];
+            if (prm.temperature > 0.0f) x = x / inv_temp;
+            return x;
+        };
         SampleOut o;
         o.id = best.i == 0x7fffffff ? 0 : best.i;
         o.p = best.i == 0x7fffffff ? 0.0f : best.v;
@@ -443,6 +511,7 @@ sample_greedy_kernel(float * __restrict__ logits, int ld, const SampleRow * __re
         o.gap = (best.i != 0x7fffffff && second.i != 0x7fffffff) ? value(best.i) - value(second.i) : INFINITY;
         outs[r] = o;
     }
+    cluster.sync();       // the peer may still be reading this CTA's exchange slots
 }
 
 // softmax probability of one token on the RAW logits row (no_speech_prob, src/whisper.cpp:7188-7196)
@@ -526,7 +595,7 @@ void dec_cross_attn(DType dt, const void * q, const DecRow * d_rows, int R, int 
 void dec_sample_greedy(float * logits, int ld, const SampleRow * d_srows, int R, const uint32_t * d_static_mask,
                        const SampleParams & prm, SampleOut * d_out, cudaStream_t st) {
     if (R <= 0) return;
-    launch_pdl(sample_greedy_kernel, dim3(R), dim3(SAMPLE_THREADS), 0, st, logits, ld, d_srows, d_static_mask, prm, d_out);
+    launch_pdl(sample_greedy_kernel, dim3(R * SAMPLE_CTAS), dim3(SAMPLE_THREADS), 0, st, logits, ld, d_srows, d_static_mask, prm, d_out);
     WB_CUDA(cudaGetLastError());
 }
 

@@ -99,6 +99,37 @@ tc_skinny_kernel(const __grid_constant__ TMap tm_x, const __grid_constant__ TMap
     // [rows_pad][T_PITCH] f32; overlays the operand ring, which is dead once the last MMA has completed
     float * tile_sum = reinterpret_cast<float *>(smem);
 
+    // Epilogue work unit = four consecutive columns of one row (float4); this CTA finishes units [v_lo, v_hi) of the tile.
+    const int n_vec = p.rows_pad * (TB / 4);
+    const int v_lo = p.KS > 1 ? (int) ((long long) n_vec * ks / p.KS) : 0;
+    const int v_hi = p.KS > 1 ? (int) ((long long) n_vec * (ks + 1) / p.KS) : n_vec;
+    const int U_rt = p.KS <= 2 ? 4 : (p.KS <= 4 ? 2 : 1);         // units a thread keeps in flight (= U of finish<KS>)
+    auto load_br = [&](int v, float4 & b, float4 & r) {            // bias and residual of unit v (zeros when absent / outside)
+        const int m = v >> 4, n = n0 + ((v & 15) << 2);
+        b = r = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (v >= v_hi || m >= p.M || n >= p.N) return;
+        if (p.vec_io && n + 3 < p.N) {
+            if (p.bias) b = __ldg(reinterpret_cast<const float4 *>(p.bias + n));
+            if (p.resid) r = *reinterpret_cast<const float4 *>(p.resid + (size_t) m * p.ldr + n);
+        } else {
+            float b4[4] = {0.0f, 0.0f, 0.0f, 0.0f}, r4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            for (int i = 0; i < 4; ++i)
+                if (n + i < p.N) {
+                    if (p.bias) b4[i] = __ldg(p.bias + n + i);
+                    if (p.resid) r4[i] = p.resid[(size_t) m * p.ldr + n + i];
+                }
+            b = make_float4(b4[0], b4[1], b4[2], b4[3]);
+            r = make_float4(r4[0], r4[1], r4[2], r4[3]);
+        }
+    };
+    // the first batch's bias / residual are requested as soon as the predecessor grid is complete, under the main loop
+    float4 pre_b[4], pre_r[4];
+    auto preload = [&]() {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (u < U_rt) load_br(v_lo + u * T_THREADS + tid, pre_b[u], pre_r[u]);
+    };
+
     TS_STAMP(0);          // CTA start
     if (tid == 0) {
         if (ptx::smem_u32(smem) & 1023u) __trap();
@@ -140,6 +171,8 @@ tc_skinny_kernel(const __grid_constant__ TMap tm_x, const __grid_constant__ TMap
                 ptx::tma_load_2d(smem + s * stage_bytes, &tm_x, &b_full[s], (kb0 + i) * TB, 0);
             }
         }
+        pdl_wait();
+        preload();
     } else if (warp == 5) {
         if (lane == 0) {
             // ===== MMA issuer =====
@@ -156,11 +189,14 @@ tc_skinny_kernel(const __grid_constant__ TMap tm_x, const __grid_constant__ TMap
             }
             ptx::umma_commit(&b_acc);
         }
+        pdl_wait();
+        preload();
     } else {
         // ===== accumulator -> this CTA's f32 tile in shared memory =====
         // (a CTA whose K slice is empty contributes zeros)
         pdl_wait();
         TS_STAMP(1);      // predecessor grid complete
+        preload();
         const int row = warp * 32 + lane;
         if (nkb > 0) {
             ts_wait(&b_acc, 0);
@@ -190,20 +226,16 @@ tc_skinny_kernel(const __grid_constant__ TMap tm_x, const __grid_constant__ TMap
         ptx::tc_fence_before();
     }
     __syncthreads();
-    pdl_wait();          // every thread takes part in the epilogue below (residual reads, output writes)
     TS_STAMP(3);          // tile in shared memory
 
     // ---- cluster-wide reduction and epilogue: every CTA of the cluster (one per K split) finishes a slice of the tile ----
-    // Work unit = four consecutive columns of one row (float4): all loads of a batch of units -- the KS partial tiles over
-    // DSMEM, bias, residual -- are issued before the first use, so a thread pays one round trip per batch, not per element.
-    const int n_vec = p.rows_pad * (TB / 4);
-    int v_lo = 0, v_hi = n_vec;
+    // All loads of a batch of units -- the KS partial tiles over DSMEM, bias, residual -- are issued before the first use, so a
+    // thread pays one round trip per batch, not per element.  A CTA tells its peers that it is done reading their tiles as
+    // soon as its last batch is in registers; the wait for the peers' same signal overlaps its arithmetic and stores.
     cg::cluster_group cluster = cg::this_cluster();
     if (p.KS > 1) {
         cluster.sync();
         TS_STAMP(4);      // all K splits of the tile are in shared memory
-        v_lo = (int) ((long long) n_vec * ks / p.KS);
-        v_hi = (int) ((long long) n_vec * (ks + 1) / p.KS);
     }
     T16 * out16 = reinterpret_cast<T16 *>(p.out16);
     auto finish = [&](auto ks_tag) {
@@ -220,26 +252,20 @@ tc_skinny_kernel(const __grid_constant__ TMap tm_x, const __grid_constant__ TMap
                 const int v = base + u * T_THREADS + tid;
                 const int m = v >> 4, n = n0 + ((v & 15) << 2);
                 live[u] = v < v_hi && m < p.M && n < p.N;
-                rs[u] = bs[u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (base == v_lo) {
+                    bs[u] = pre_b[u];
+                    rs[u] = pre_r[u];
+                } else {
+                    load_br(v, bs[u], rs[u]);
+                }
                 if (live[u]) {
-                    if (p.vec_io && n + 3 < p.N) {
-                        if (p.bias) bs[u] = __ldg(reinterpret_cast<const float4 *>(p.bias + n));
-                        if (p.resid) rs[u] = *reinterpret_cast<const float4 *>(p.resid + (size_t) m * p.ldr + n);
-                    } else {
-                        float b4[4] = {0.0f, 0.0f, 0.0f, 0.0f}, r4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-                        for (int i = 0; i < 4; ++i)
-                            if (n + i < p.N) {
-                                if (p.bias) b4[i] = __ldg(p.bias + n + i);
-                                if (p.resid) r4[i] = p.resid[(size_t) m * p.ldr + n + i];
-                            }
-                        bs[u] = make_float4(b4[0], b4[1], b4[2], b4[3]);
-                        rs[u] = make_float4(r4[0], r4[1], r4[2], r4[3]);
-                    }
                     const int ea = m * T_PITCH + ((v & 15) << 2);
 #pragma unroll
                     for (int r = 0; r < KSC; ++r) part[u][r] = *reinterpret_cast<const float4 *>(peer[r] + ea);
                 }
             }
+            if (KSC > 1 && base + U * T_THREADS >= v_hi)        // last batch is in flight: release the peers' tiles
+                asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 if (!live[u]) continue;
@@ -285,7 +311,7 @@ tc_skinny_kernel(const __grid_constant__ TMap tm_x, const __grid_constant__ TMap
         default: finish(std::integral_constant<int, 8>{}); break;
     }
     TS_STAMP(5);          // outputs written
-    if (p.KS > 1) cluster.sync();     // peers may still be reading this CTA's tile
+    if (p.KS > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");     // peers may still be reading this CTA's tile
     TS_STAMP(6);
     ptx::tc_fence_before();
     __syncthreads();
