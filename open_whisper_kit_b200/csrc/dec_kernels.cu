@@ -72,23 +72,23 @@ cross_attn_kernel(const T16 * __restrict__ q, int ldq, const DecRow * __restrict
     const int sub = lane & 7, grp = lane >> 3;     // 8 lanes per key row, 4 key rows per warp instruction
     // The successor is the next chain / GEMM launch, whose CTAs hold ~100 KB of shared memory while they wait: letting
     // them in at once would squeeze this kernel's own occupancy, so the cross pass triggers after its K sweep.
-    if (SELF) {
-        pdl_trigger();
-        // keys of earlier positions were written by earlier decoder calls: safe to touch before the dependency resolves
-        const DecRow row0 = rows[r];
-        const T16 * kb0 = reinterpret_cast<const T16 *>(row0.self_kv) + layer_off + h * 64 + (size_t) (warp * 4 + grp) * (2 * d) + sub * 8;
+    // The row descriptors (and the cross K/V) were written before this decoder call began (H2D copy, encoder stage), and the
+    // self K/V of earlier positions by earlier decoder calls: all of it may be touched before the grid dependency resolves.
+    // Pull the first batch of keys -- and, for the short self pass, values -- into L2 meanwhile.
+    // The cross pass's successor is the next GEMM launch, whose CTAs hold ~80 KB of shared memory while they wait: letting
+    // them in at once would squeeze this kernel's own occupancy, so the cross pass triggers after its K sweep.
+    if (SELF) pdl_trigger();
+    const DecRow row = rows[r];
+    {
+        const int T_pre = SELF ? row.pos : T_in;
+        const T16 * kb0 = (SELF ? reinterpret_cast<const T16 *>(row.self_kv) : reinterpret_cast<const T16 *>(row.cross_kv)) +
+                          layer_off + h * 64 + (size_t) (warp * 4 + grp) * (2 * d) + sub * 8;
 #pragma unroll
         for (int u = 0; u < 8; ++u)
-            if (warp * 4 + grp + 16 * u < row0.pos) asm volatile("prefetch.global.L2 [%0];" ::"l"(kb0 + (size_t) (16 * u) * (2 * d)));
-    }
-    if (!SELF) {
-        // The cross K/V and the row descriptors were written before this decoder call began (encoder stage, H2D copy), so
-        // they may be touched before the grid dependency resolves: pull the first batch of keys into L2 meanwhile.
-        const DecRow row0 = rows[r];
-        const T16 * kb0 = reinterpret_cast<const T16 *>(row0.cross_kv) + layer_off + h * 64 + (size_t) (warp * 4 + grp) * (2 * d) + sub * 8;
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-            if (warp * 4 + grp + 16 * u < T_in) asm volatile("prefetch.global.L2 [%0];" ::"l"(kb0 + (size_t) (16 * u) * (2 * d)));
+            if (warp * 4 + grp + 16 * u < T_pre) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(kb0 + (size_t) (16 * u) * (2 * d)));
+                if (SELF) asm volatile("prefetch.global.L2 [%0];" ::"l"(kb0 + (size_t) (16 * u) * (2 * d) + d));
+            }
     }
     pdl_wait();
     if (QSPLIT && qs.trace && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
@@ -96,11 +96,13 @@ cross_attn_kernel(const T16 * __restrict__ q, int ldq, const DecRow * __restrict
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
         qs.trace[0] = now;
     }
-    const DecRow row = rows[r];
     const int T = SELF ? row.pos + 1 : T_in;
     const T16 * kbase = (SELF ? reinterpret_cast<const T16 *>(row.self_kv) : reinterpret_cast<const T16 *>(row.cross_kv)) +
                         layer_off + h * 64;
     const int ld = 2 * d;
+    // The step's own key / value (position row.pos) come straight from the projection output; their copy into the cache is
+    // only for later steps, so nothing in this launch waits for it.
+    const T16 * knew = (SELF && fused_append) ? q + (size_t) r * ldq + d + h * 64 : nullptr;
     if (SELF && fused_append) {
         if (tid < 16) {
             const int which = tid >> 3, c = tid & 7;       // 0: K slice, 1: V slice; 8 x 16 bytes each
@@ -108,8 +110,6 @@ cross_attn_kernel(const T16 * __restrict__ q, int ldq, const DecRow * __restrict
             T16 * dst = reinterpret_cast<T16 *>(row.self_kv) + layer_off + (size_t) row.pos * ld + which * d + h * 64 + c * 8;
             *reinterpret_cast<uint4 *>(dst) = u;
         }
-        __threadfence_block();
-        __syncthreads();
     }
 
     float qv[8];
@@ -163,7 +163,8 @@ cross_attn_kernel(const T16 * __restrict__ q, int ldq, const DecRow * __restrict
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int t = tb + 16 * u;
-            const uint4 * src = reinterpret_cast<const uint4 *>(kbase + (size_t) t * ld + sub * 8);
+            const uint4 * src = reinterpret_cast<const uint4 *>((SELF && knew && t == row.pos) ? knew + sub * 8
+                                                                                                  : kbase + (size_t) t * ld + sub * 8);
             kb[u] = t < T ? (SELF ? *src : (QSPLIT ? ld_stream16(src) : __ldg(src))) : make_uint4(0, 0, 0, 0);
         }
 #pragma unroll
@@ -214,7 +215,8 @@ cross_attn_kernel(const T16 * __restrict__ q, int ldq, const DecRow * __restrict
         for (int u = 0; u < U; ++u) {
             const int t = tb + 16 * u;
             const bool ok = t < T;
-            const uint4 * src = reinterpret_cast<const uint4 *>(vbase + (size_t) t * ld + sub * 8);
+            const uint4 * src = reinterpret_cast<const uint4 *>((SELF && knew && t == row.pos) ? knew + d + sub * 8
+                                                                                                  : vbase + (size_t) t * ld + sub * 8);
             vb[u] = ok ? (SELF ? *src : (QSPLIT ? ld_stream16(src) : __ldg(src))) : make_uint4(0, 0, 0, 0);
             pr[u] = ok ? Half16<T16>::to_f(Half16<T16>::from_f(s_sc[t] * inv)) : 0.0f;
         }
@@ -305,8 +307,8 @@ template <int NT> __device__ ArgMax block_amax(ArgMax a, ArgMax * sh) {
 
 constexpr int SAMPLE_THREADS = 512;
 constexpr int SAMPLE_CTAS = 2;                 // CTAs (one cluster) per decoder row
-constexpr int SAMPLE_VEC = 13;                 // float4 per thread: 2 * 512 * 13 * 4 = 53248 >= n_vocab of every whisper model
-constexpr int SAMPLE_MASK_WORDS = SAMPLE_THREADS * SAMPLE_VEC * 4 / 32;       // mask words of one CTA's half row
+constexpr int SAMPLE_HALF = 26624;             // elements per CTA: 2 * 26624 = 53248 >= n_vocab of every whisper model
+constexpr int SAMPLE_SMEM = SAMPLE_HALF * 4;   // the CTA's half row after the rules, f32
 
 struct SampleXchg {                            // one slot per cluster-wide reduction: slots are never reused inside a launch
     float f[4];
@@ -315,60 +317,46 @@ struct SampleXchg {                            // one slot per cluster-wide redu
 };
 
 // One cluster of two CTAs per decoder row, each CTA owns half of it.  The row (207 KB, L2-resident right after the logits
-// GEMM) is read ONCE, all loads in flight together, into registers (thread t of CTA c holds elements 4 q .. 4 q + 3 for
-// q = 6656 c + t + 512 j); every later pass works on registers, block-wide results are exchanged through DSMEM and combined
-// in rank order by both CTAs.  The rules of whisper_process_logits are applied in its order (`allowed`) by overwriting the
-// register copy with -inf; the log-softmax, the timestamp-mass rule and the probabilities then follow the reference's own
-// formulation step by step (src/whisper.cpp:6137-6171, 6336-6361); arg-max / timestamp statistics are whisper_sample_token's
-// (6460-6517).
+// GEMM) is read ONCE, thirteen 16-byte loads in flight per thread; the rules of whisper_process_logits are applied in its
+// order (`allowed`) on the way into shared memory (suppressed = -inf), and every later pass is a short rolled loop over
+// shared memory (a fully unrolled register-resident version was instruction-fetch-bound: 10 k SASS instructions).
+// Block-wide results are exchanged through DSMEM and combined in rank order by both CTAs.  The log-softmax, the
+// timestamp-mass rule and the probabilities follow the reference's own formulation step by step
+// (src/whisper.cpp:6137-6171, 6336-6361); arg-max / timestamp statistics are whisper_sample_token's (6460-6517).
 __global__ void __cluster_dims__(SAMPLE_CTAS, 1, 1) __launch_bounds__(SAMPLE_THREADS)
 sample_greedy_kernel(float * __restrict__ logits, int ld, const SampleRow * __restrict__ srows,
                      const uint32_t * __restrict__ static_mask, SampleParams prm, SampleOut * __restrict__ outs) {
+    extern __shared__ __align__(16) float sh_v[];          // [SAMPLE_HALF]
     __shared__ float sh_f[SAMPLE_THREADS / 32];
     __shared__ double sh_d[SAMPLE_THREADS / 32];
     __shared__ ArgMax sh_a[SAMPLE_THREADS / 32];
-    __shared__ uint32_t sh_mask[SAMPLE_MASK_WORDS];
+    __shared__ uint32_t sh_mask[SAMPLE_HALF / 32];
     __shared__ SampleXchg sh_x[5];
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int) cluster.block_rank();
     const int r = blockIdx.x / SAMPLE_CTAS;
     const int tid = threadIdx.x;
     const int V = prm.n_vocab, beg = prm.token_beg, eot = prm.token_eot;
-    const int q0 = rank * (SAMPLE_THREADS * SAMPLE_VEC);             // first float4 of this CTA's half
+    const int lo = rank * SAMPLE_HALF;                                   // first element of this CTA's half
+    const int n4 = (min(max(V - lo, 0), SAMPLE_HALF) + 3) >> 2;          // float4 units that hold at least one valid element
     pdl_trigger();
     // the static suppression mask is written once per whisper_full call, before any decoder launch
-    for (int w = tid; w < SAMPLE_MASK_WORDS; w += SAMPLE_THREADS) {
-        const int gw = q0 / 8 + w;
+    for (int w = tid; w < SAMPLE_HALF / 32; w += SAMPLE_THREADS) {
+        const int gw = lo / 32 + w;
         sh_mask[w] = gw < (V + 31) / 32 ? __ldg(static_mask + gw) : 0u;
     }
     pdl_wait();
     const SampleRow sr = srows[r];
     const float * l = logits + (size_t) sr.logits_row * ld;
-
-    float v[SAMPLE_VEC * 4];
-    const bool vec_ok = (reinterpret_cast<uintptr_t>(l) & 15) == 0;
-#pragma unroll
-    for (int j = 0; j < SAMPLE_VEC; ++j) {
-        const int i0 = 4 * (q0 + tid + SAMPLE_THREADS * j);
-        if (vec_ok && i0 + 3 < V) {
-            const float4 q = *reinterpret_cast<const float4 *>(l + i0);
-            v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
-        } else {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) v[4 * j + c] = i0 + c < V ? l[i0 + c] : -INFINITY;
-        }
-    }
     __syncthreads();      // sh_mask
-
-    // cluster-wide combination of a block-wide result: publish, sync, read the peer's, combine as (rank 0, rank 1)
-    const SampleXchg * peer_x = cluster.map_shared_rank(sh_x, rank ^ 1);
 
     const bool is_initial = sr.n_tokens == 0;
     const bool last_ts = sr.n_tokens > 0 && sr.last >= beg;
     const bool pen_ts = sr.n_tokens < 2 || sr.penult >= beg;
     const int init_lim = (is_initial && prm.max_initial_ts > 0.0f) ? beg + prm.tid0 + 1 : V;
     const int mono_lim = sr.has_ts ? beg + sr.seek_delta / 2 : beg;
-    const float inv_temp = prm.temperature > 0.0f ? prm.temperature : 1.0f;
+    const bool use_temp = prm.temperature > 0.0f;
+    const float temp = use_temp ? prm.temperature : 1.0f;
     auto allowed = [&](int i, uint32_t mask_word) {
         bool kill = (mask_word >> (i & 31)) & 1u;
         if (is_initial && prm.suppress_blank && (i == eot || i == prm.token_space)) kill = true;
@@ -385,28 +373,54 @@ sample_greedy_kernel(float * __restrict__ logits, int ld, const SampleRow * __re
         return !kill;
     };
 
-    // rules -> -inf; maxima of all / timestamp / text logits
+    // pass 0: global -> rules -> shared memory; maxima of all / timestamp / text logits
     float mx = -INFINITY, mx_ts = -INFINITY, mx_text = -INFINITY;
+    {
+        constexpr int NB = SAMPLE_HALF / 4 / SAMPLE_THREADS;             // 13 float4 per thread
+        const bool vec_ok = (reinterpret_cast<uintptr_t>(l) & 15) == 0;
+        float4 q[NB];
 #pragma unroll
-    for (int j = 0; j < SAMPLE_VEC; ++j) {
-        const int ql = tid + SAMPLE_THREADS * j;                // float4 index inside this CTA's half
-        const int i0 = 4 * (q0 + ql);
-        const uint32_t mw = sh_mask[ql >> 3];
+        for (int j = 0; j < NB; ++j) {
+            const int u = tid + SAMPLE_THREADS * j, i0 = lo + 4 * u;
+            if (vec_ok && i0 + 3 < V) {
+                q[j] = *reinterpret_cast<const float4 *>(l + i0);
+            } else {
+                q[j].x = i0 < V ? l[i0] : -INFINITY;
+                q[j].y = i0 + 1 < V ? l[i0 + 1] : -INFINITY;
+                q[j].z = i0 + 2 < V ? l[i0 + 2] : -INFINITY;
+                q[j].w = i0 + 3 < V ? l[i0 + 3] : -INFINITY;
+            }
+        }
+#pragma unroll 1
+        for (int j = 0; j < NB; ++j) {
+            const int u = tid + SAMPLE_THREADS * j, i0 = lo + 4 * u;
+            const uint32_t mw = sh_mask[u >> 3];
+            float x[4];
+            {   // q[j] with a rolled j: select instead of a dynamically indexed register array
+                float4 t = q[0];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int i = i0 + c;
-            float x = v[4 * j + c];
-            if (prm.temperature > 0.0f) x = x / inv_temp;
-            if (i >= V || !allowed(i, mw)) x = -INFINITY;
-            v[4 * j + c] = x;
-            mx = fmaxf(mx, x);
-            if (i >= beg) mx_ts = fmaxf(mx_ts, x);
-            else mx_text = fmaxf(mx_text, x);
+                for (int k = 1; k < NB; ++k)
+                    if (j == k) t = q[k];
+                x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w;
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int i = i0 + c;
+                float y = x[c];
+                if (use_temp && i < V) y = y / temp;
+                if (i >= V || !allowed(i, mw)) y = -INFINITY;
+                x[c] = y;
+                mx = fmaxf(mx, y);
+                if (i >= beg) mx_ts = fmaxf(mx_ts, y);
+                else mx_text = fmaxf(mx_text, y);
+            }
+            *reinterpret_cast<float4 *>(sh_v + 4 * u) = make_float4(x[0], x[1], x[2], x[3]);
         }
     }
-    mx = block_max<SAMPLE_THREADS>(mx, sh_f);
+    mx = block_max<SAMPLE_THREADS>(mx, sh_f);            // (its barriers also publish sh_v)
     mx_ts = block_max<SAMPLE_THREADS>(mx_ts, sh_f);
     mx_text = block_max<SAMPLE_THREADS>(mx_text, sh_f);
+    const SampleXchg * peer_x = cluster.map_shared_rank(sh_x, rank ^ 1);
     if (tid == 0) {
         sh_x[0].f[0] = mx; sh_x[0].f[1] = mx_ts; sh_x[0].f[2] = mx_text;
     }
@@ -416,28 +430,34 @@ sample_greedy_kernel(float * __restrict__ logits, int ld, const SampleRow * __re
     mx_text = fmaxf(mx_text, peer_x[0].f[2]);
 
     // log-softmax denominator (whisper_compute_logprobs)
-    float se = 0.0f;
-#pragma unroll
-    for (int k = 0; k < SAMPLE_VEC * 4; ++k)
-        if (v[k] > -INFINITY) se += expf(v[k] - mx);
+    float se;
+    {
+        float s4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        for (int u = tid; u < n4; u += SAMPLE_THREADS) {
+            const float4 t = *reinterpret_cast<const float4 *>(sh_v + 4 * u);
+            if (t.x > -INFINITY) s4[0] += expf(t.x - mx);
+            if (t.y > -INFINITY) s4[1] += expf(t.y - mx);
+            if (t.z > -INFINITY) s4[2] += expf(t.z - mx);
+            if (t.w > -INFINITY) s4[3] += expf(t.w - mx);
+        }
+        se = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+    }
     se = block_sum<SAMPLE_THREADS>(se, sh_f);
     if (tid == 0) sh_x[1].f[0] = se;
     cluster.sync();
     se = rank == 0 ? se + peer_x[1].f[0] : peer_x[1].f[0] + se;
     const float logZ = logf(se) + mx;
 
+    // local element range of the timestamp tokens / of the tokens that can still win
+    const int ts_lo = min(max(beg - lo, 0), 4 * n4), ts_hi = 4 * n4;
     // if the probability mass of all timestamps exceeds that of any single text token, only timestamps survive
     bool mask_text = false;
     {
         const float lp_max_ts = mx_ts - logZ;
         float ts = 0.0f;
-#pragma unroll
-        for (int j = 0; j < SAMPLE_VEC; ++j) {
-            const int i0 = 4 * (q0 + tid + SAMPLE_THREADS * j);
-            if (i0 + 3 < beg) continue;
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-                if (i0 + c >= beg && v[4 * j + c] > -INFINITY) ts += expf((v[4 * j + c] - logZ) - lp_max_ts);
+        for (int e = ts_lo + tid; e < ts_hi; e += SAMPLE_THREADS) {
+            const float x = sh_v[e];
+            if (x > -INFINITY) ts += expf((x - logZ) - lp_max_ts);
         }
         ts = block_sum<SAMPLE_THREADS>(ts, sh_f);
         if (tid == 0) sh_x[2].f[0] = ts;
@@ -447,35 +467,55 @@ sample_greedy_kernel(float * __restrict__ logits, int ld, const SampleRow * __re
         mask_text = timestamp_logprob > mx_text - logZ;
     }
 
-    // probs, greedy arg-max (first maximal index), timestamp statistics
-    ArgMax best = {0.0f, 0x7fffffff}, best_ts = {0.0f, 0x7fffffff}, second = {0.0f, 0x7fffffff};
-    double sum_ts = 0.0;
-#pragma unroll
-    for (int j = 0; j < SAMPLE_VEC; ++j) {
-        const int i0 = 4 * (q0 + tid + SAMPLE_THREADS * j);
+    // Greedy arg-max = first index of the maximal PROBABILITY expf(logit - logZ) (src/whisper.cpp:6460-6517).  expf is
+    // monotone, so the winner is within rounding distance of its thread's largest logit: each thread finds its two largest
+    // logits (cheap compares), evaluates probabilities only for the elements that close to its maximum, and the block /
+    // cluster arg-max runs on (probability, lower index) exactly as the reference's scan would decide.
+    const int u_lo = mask_text ? (ts_lo >> 2) : 0;        // masked text: start at the float4 that holds token_beg
+    float b1 = -INFINITY, b2 = -INFINITY;
+    int i1 = 0x7fffffff, i2 = 0x7fffffff;
+    for (int u = u_lo + tid; u < n4; u += SAMPLE_THREADS) {
+        const float4 t = *reinterpret_cast<const float4 *>(sh_v + 4 * u);
+        const float x[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            const int i = i0 + c;
-            const float x = v[4 * j + c];
-            float p = 0.0f;
-            if (x > -INFINITY && !(mask_text && i < beg)) p = expf(x - logZ);
-            if (p > 0.0f) {
-                const ArgMax cur = {p, i};
-                if (amax(best, cur).i == i) {
-                    second = best;
-                    best = cur;
-                } else {
-                    second = amax(second, cur);
-                }
-                if (i >= beg) {
-                    best_ts = amax(best_ts, cur);
-                    sum_ts += (double) p;
+            const int i = lo + 4 * u + c;
+            const float y = (mask_text && i < beg) ? -INFINITY : x[c];
+            if (y > b1) {               // indices increase along the scan: strict compares keep the lower index on ties
+                b2 = b1; i2 = i1;
+                b1 = y; i1 = i;
+            } else if (y > b2) {
+                b2 = y; i2 = i;
+            }
+        }
+    }
+    ArgMax best = {0.0f, 0x7fffffff}, best_ts = {0.0f, 0x7fffffff};
+    double sum_ts = 0.0;
+    if (b1 > -INFINITY) {
+        const float margin = 2e-6f * fmaxf(1.0f, fabsf(b1 - logZ));       // > 2 ulp of (logit - logZ) plus expf's error
+        for (int u = u_lo + tid; u < n4; u += SAMPLE_THREADS) {
+            const float4 t = *reinterpret_cast<const float4 *>(sh_v + 4 * u);
+            const float x[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int i = lo + 4 * u + c;
+                if (x[c] >= b1 - margin && !(mask_text && i < beg)) {
+                    const float pr = expf(x[c] - logZ);
+                    if (pr > 0.0f) best = amax(best, ArgMax{pr, i});
                 }
             }
         }
     }
-    // cluster-wide top-2: the runner-up is the best of (everyone's second, every loser's best)
-    const ArgMax my_best = best;
+    for (int e = ts_lo + tid; e < ts_hi; e += SAMPLE_THREADS) {      // timestamp statistics: every probability is needed
+        const float x = sh_v[e];
+        if (x > -INFINITY) {
+            const float pr = expf(x - logZ);
+            if (pr > 0.0f) {
+                best_ts = amax(best_ts, ArgMax{pr, lo + e});
+                sum_ts += (double) pr;
+            }
+        }
+    }
     best = block_amax<SAMPLE_THREADS>(best, sh_a);
     best_ts = block_amax<SAMPLE_THREADS>(best_ts, sh_a);
     sum_ts = block_sum_d<SAMPLE_THREADS>(sum_ts, sh_d);
@@ -486,14 +526,17 @@ sample_greedy_kernel(float * __restrict__ logits, int ld, const SampleRow * __re
     best = amax(best, peer_x[3].a[0]);
     best_ts = amax(best_ts, peer_x[3].a[1]);
     sum_ts = rank == 0 ? sum_ts + peer_x[3].d : peer_x[3].d + sum_ts;
-    second = block_amax<SAMPLE_THREADS>((my_best.i == best.i) ? second : my_best, sh_a);
+    // runner-up by logit (diagnostics): the best of everyone's second and every loser's best
+    ArgMax second = (i1 == best.i) ? ArgMax{b2, i2} : ArgMax{b1, i1};
+    if (second.v == -INFINITY) second.i = 0x7fffffff;
+    second = block_amax<SAMPLE_THREADS>(second, sh_a);
     if (tid == 0) sh_x[4].a[0] = second;
     cluster.sync();
     second = amax(second, peer_x[4].a[0]);
     if (tid == 0 && rank == 0) {
         auto value = [&](int i) {
             float x = l[i];
-            if (prm.temperature > 0.0f) x = x / inv_temp;
+            if (use_temp) x = x / temp;
             return x;
         };
         SampleOut o;
@@ -595,7 +638,13 @@ void dec_cross_attn(DType dt, const void * q, const DecRow * d_rows, int R, int 
 void dec_sample_greedy(float * logits, int ld, const SampleRow * d_srows, int R, const uint32_t * d_static_mask,
                        const SampleParams & prm, SampleOut * d_out, cudaStream_t st) {
     if (R <= 0) return;
-    launch_pdl(sample_greedy_kernel, dim3(R * SAMPLE_CTAS), dim3(SAMPLE_THREADS), 0, st, logits, ld, d_srows, d_static_mask, prm, d_out);
+    static bool set = false;
+    if (!set) {
+        WB_CUDA(cudaFuncSetAttribute(sample_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SAMPLE_SMEM));
+        set = true;
+    }
+    launch_pdl(sample_greedy_kernel, dim3(R * SAMPLE_CTAS), dim3(SAMPLE_THREADS), SAMPLE_SMEM, st, logits, ld, d_srows, d_static_mask, prm,
+               d_out);
     WB_CUDA(cudaGetLastError());
 }
 
