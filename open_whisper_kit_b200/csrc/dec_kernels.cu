@@ -81,13 +81,15 @@ cross_attn_kernel(const T16 * __restrict__ q, int ldq, const DecRow * __restrict
     const DecRow row = rows[r];
     {
         const int T_pre = SELF ? row.pos : T_in;
-        const T16 * kb0 = (SELF ? reinterpret_cast<const T16 *>(row.self_kv) : reinterpret_cast<const T16 *>(row.cross_kv)) +
-                          layer_off + h * 64 + (size_t) (warp * 4 + grp) * (2 * d) + sub * 8;
+        const int ld0 = SELF ? 2 * d : 64;
+        const T16 * kb0 = (SELF ? reinterpret_cast<const T16 *>(row.self_kv) + layer_off + h * 64
+                                : reinterpret_cast<const T16 *>(row.cross_kv) + layer_off + (size_t) h * 2 * T_in * 64) +
+                          (size_t) (warp * 4 + grp) * ld0 + sub * 8;
 #pragma unroll
         for (int u = 0; u < 8; ++u)
             if (warp * 4 + grp + 16 * u < T_pre) {
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(kb0 + (size_t) (16 * u) * (2 * d)));
-                if (SELF) asm volatile("prefetch.global.L2 [%0];" ::"l"(kb0 + (size_t) (16 * u) * (2 * d) + d));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(kb0 + (size_t) (16 * u) * ld0));
+                if (SELF) asm volatile("prefetch.global.L2 [%0];" ::"l"(kb0 + (size_t) (16 * u) * ld0 + d));
             }
     }
     pdl_wait();
@@ -97,9 +99,10 @@ cross_attn_kernel(const T16 * __restrict__ q, int ldq, const DecRow * __restrict
         qs.trace[0] = now;
     }
     const int T = SELF ? row.pos + 1 : T_in;
-    const T16 * kbase = (SELF ? reinterpret_cast<const T16 *>(row.self_kv) : reinterpret_cast<const T16 *>(row.cross_kv)) +
-                        layer_off + h * 64;
-    const int ld = 2 * d;
+    // self K/V: [position][K | V] rows of 2d; cross K/V: [head][K | V][T][64], one contiguous block per (window, head)
+    const T16 * kbase = SELF ? reinterpret_cast<const T16 *>(row.self_kv) + layer_off + h * 64
+                             : reinterpret_cast<const T16 *>(row.cross_kv) + layer_off + (size_t) h * 2 * T_in * 64;
+    const int ld = SELF ? 2 * d : 64;
     // The step's own key / value (position row.pos) come straight from the projection output; their copy into the cache is
     // only for later steps, so nothing in this launch waits for it.
     const T16 * knew = (SELF && fused_append) ? q + (size_t) r * ldq + d + h * 64 : nullptr;
@@ -203,7 +206,7 @@ cross_attn_kernel(const T16 * __restrict__ q, int ldq, const DecRow * __restrict
     if (n_phantom > 0) sum += (float) n_phantom * expf(-mx);
     const float inv = 1.0f / sum;
 
-    const T16 * vbase = kbase + d;
+    const T16 * vbase = SELF ? kbase + d : kbase + (size_t) T_in * 64;
     float o[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = 0.0f;

@@ -11,7 +11,7 @@ struct DecRow {
     int          token;
     int          pos;       // position in the text context (n_past + i)
     void *       self_kv;   // this sequence's self-attention cache   [n_text_layer][n_text_ctx][2d]  (K | V)
-    const void * cross_kv;  // this window's cross K/V, layer 0       [1500][2d] (K | V); layers are layer_stride apart
+    const void * cross_kv;  // this window's cross K/V, layer 0       [n_head][K | V][1500][64]; layers are layer_stride apart
 };
 
 // Per-row decoder state the logit rules depend on (reference whisper_decoder, src/whisper.cpp:797-820).

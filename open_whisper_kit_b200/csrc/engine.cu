@@ -344,6 +344,7 @@ bool Engine::encode(const std::vector<EncJob> & jobs, CrossKV & kv, int win0, bo
         g.bias = L.bxkv; g.scale = kscale; g.scale_cols = d;
         g.out16 = (char *) kv.data.p + (il * kv.layer_stride + (size_t) win0 * T * 2 * d) * 2;
         g.ldo16 = 2 * d;
+        g.head_major_T = T;       // [window][head][K|V][T][64]: the decoder streams one (window, head) block per CTA
         gemm(g);
     }
     WB_CUDA(cudaStreamSynchronize(stream));

@@ -55,6 +55,7 @@ struct EpiParams {
     int ldr;
     void * out16;
     int ldo16;
+    int hm_T;          // head-major remap of out16 (GemmArgs::head_major_T)
     float * out32;
     int ldo32;
 };
@@ -257,6 +258,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 }
                 if (out16) {
                     T16 * o = out16 + (size_t) row * ep.ldo16 + col0;
+                    if (ep.hm_T > 0) {          // cross-K/V pool: [window][head][K|V][T][64]; a 32-column chunk stays inside one head
+                        const int w = row / ep.hm_T, t = row - w * ep.hm_T, half = ep.N >> 1;
+                        const int kv = col0 >= half ? 1 : 0, hc = col0 - kv * half;
+                        o = out16 + (size_t) w * ep.hm_T * ep.N + ((size_t) ((hc >> 6) * 2 + kv) * ep.hm_T + t) * 64 + (hc & 63);
+                    }
                     if (full) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 8) {
@@ -372,6 +378,7 @@ bool tc_gemm(const GemmArgs & g, cudaStream_t stream) {
     if ((g.lda % 8) || (g.ldw % 8) || (reinterpret_cast<uintptr_t>(g.a) & 15) || (reinterpret_cast<uintptr_t>(g.w) & 15))
         return false;
     if (g.out16 && (g.ldo16 % 8)) return false;
+    if (g.head_major_T > 0 && (!g.out16 || g.N % 128 || g.M % g.head_major_T)) return false;
     if (g.out32 && (g.ldo32 % 4)) return false;
     if (g.resid && (g.ldr % 4)) return false;
     EpiParams ep;
@@ -388,6 +395,7 @@ bool tc_gemm(const GemmArgs & g, cudaStream_t stream) {
     ep.ldr = g.ldr;
     ep.out16 = g.out16;
     ep.ldo16 = g.ldo16;
+    ep.hm_T = g.head_major_T;
     ep.out32 = g.out32;
     ep.ldo32 = g.ldo32;
     static int n_sm = 0;

@@ -20,6 +20,9 @@ struct GemmArgs {
     const float * pos = nullptr; int pos_rows = 0;
     const float * resid = nullptr; int ldr = 0; // may alias out32
     void * out16 = nullptr;     int ldo16 = 0;
+    // > 0 (tc_gemm only): out16 is the cross-K/V pool.  Rows are (window, t < head_major_T), columns (kv, head, 64); element
+    // (w, t, kv, h, c) goes to out16[w * T * N + ((h * 2 + kv) * T + t) * 64 + c] -- each (window, head) stream contiguous.
+    int head_major_T = 0;
     float * out32 = nullptr;    int ldo32 = 0;
 };
 

@@ -249,6 +249,37 @@ def test_large_v3_turbo_geometry_vs_live_reference(lib, model_dir):
         assert worst <= 2e-2
 
 
+def test_cross_kv_pool_matches_live_reference(lib, model_dir):
+    """Cross-attention K/V (src/whisper.cpp:2272-2346) read back from the head-major device pool ([head][K|V][1500][64] per
+    window and layer, written by the GEMM epilogue) and handed out in the reference's [1500][K | V] order, against the
+    reference's own kv_cross (K = [layer][1500][d], V = [layer][d][1500] without flash attention)."""
+    ref, _ = reflib.load()
+    if ref is None:
+        pytest.skip("oracle/_ref was not built / did not travel")
+    path = model_path(model_dir, "tiny.en")
+    pcm = pcm_for({"kind": "jfk"})
+    n_thr = min(os.cpu_count() or 4, 32)
+    d, n_layer = 384, 4
+    with api.Whisper(lib, path, flash_attn=False) as w, api.Whisper(ref, path, use_gpu=False, flash_attn=False) as r:
+        assert w.pcm_to_mel(pcm) == 0 and r.pcm_to_mel(pcm, n_thr) == 0
+        assert w.encode(0) == 0 and r.encode(0, n_thr) == 0
+        n = ref.ref_kv_cross_copy(r.ctx, 0, None, 0)
+        used = n_layer * 1500 * d          # the buffer is allocated for a padded context; layers are packed at 1500 rows
+        assert n >= used
+        rk, rv = np.empty(n, np.float32), np.empty(n, np.float32)
+        assert ref.ref_kv_cross_copy(r.ctx, 0, rk.ctypes.data_as(FP), n) == n
+        assert ref.ref_kv_cross_copy(r.ctx, 1, rv.ctypes.data_as(FP), n) == n
+        rk = rk[:used].reshape(n_layer, 1500, d)
+        rv = rv[:used].reshape(n_layer, d, 1500).transpose(0, 2, 1)
+        for il in range(n_layer):
+            buf = np.zeros(1500 * 2 * d, np.uint16)
+            assert lib.whisper_b200_get_cross_kv(w.ctx, il, buf.ctypes.data_as(C.POINTER(C.c_uint16)), buf.size) == 0
+            kv = buf.view(np.float16).astype(np.float32).reshape(1500, 2 * d)
+            dk, dv = np.abs(kv[:, :d] - rk[il]).max(), np.abs(kv[:, d:] - rv[il]).max()
+            print(f"layer {il}: cross K max|d| = {dk:.3e}, V max|d| = {dv:.3e} (rms K {np.sqrt((rk[il] ** 2).mean()):.3f})")
+            assert dk <= 2e-2 and dv <= 2e-2
+
+
 def test_bf16_operands_track_f16(lib, model_dir, monkeypatch):
     """WHISPER_B200_DTYPE=bf16 (the operand type BASELINE.json names) runs every kernel of the path -- tcgen05 GEMMs and
     attention, decoder step -- and stays close to the f16 run (bf16 has 3 fewer mantissa bits: ~8x the rounding error)."""
