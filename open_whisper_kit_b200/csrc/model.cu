@@ -218,6 +218,59 @@ struct Uploader {
     }
 };
 
+// ---- ggml 32-element block formats -> f16 (host, at load time) ------------------------------------------------
+// Layouts and arithmetic restate dequantize_row_q4_0 / q4_1 / q5_0 / q5_1 / q8_0 (reference ggml/src/ggml-quants.c:307-415,
+// structs ggml/src/ggml-common.h): value = q * d (+ m) in f32, then rounded once to f16 (the type our GEMMs read).
+int quant_block_bytes(int ttype) {
+    switch (ttype) {
+        case 2: return 18;   // q4_0: f16 d, 16 x 2 nibbles
+        case 3: return 20;   // q4_1: f16 d, f16 m, 16 x 2 nibbles
+        case 6: return 22;   // q5_0: f16 d, u32 fifth bits, 16 x 2 nibbles
+        case 7: return 24;   // q5_1: f16 d, f16 m, u32 fifth bits, 16 x 2 nibbles
+        case 8: return 34;   // q8_0: f16 d, 32 x i8
+        default: return 0;
+    }
+}
+void dequantize_blocks(int ttype, const unsigned char * raw, size_t n_blocks, __half * out) {
+    const int bb = quant_block_bytes(ttype);
+    auto h2f = [](const unsigned char * p) {
+        __half h;
+        memcpy(&h, p, 2);
+        return __half2float(h);
+    };
+    for (size_t b = 0; b < n_blocks; ++b) {
+        const unsigned char * p = raw + b * bb;
+        __half * y = out + b * 32;
+        const float d = h2f(p);
+        if (ttype == 8) {
+            const signed char * q = reinterpret_cast<const signed char *>(p + 2);
+            for (int j = 0; j < 32; ++j) y[j] = __float2half_rn((float) q[j] * d);
+            continue;
+        }
+        const bool has_m = ttype == 3 || ttype == 7, has_h = ttype == 6 || ttype == 7;
+        const float m = has_m ? h2f(p + 2) : 0.0f;
+        const unsigned char * q = p + 2 + (has_m ? 2 : 0);
+        uint32_t qh = 0;
+        if (has_h) {
+            memcpy(&qh, q, 4);
+            q += 4;
+        }
+        for (int j = 0; j < 16; ++j) {
+            int x0 = q[j] & 0x0F, x1 = q[j] >> 4;
+            if (has_h) {
+                x0 |= ((qh >> j) << 4) & 0x10;
+                x1 |= (qh >> (j + 12)) & 0x10;
+            }
+            if (!has_m) {               // symmetric formats are offset by half their range
+                x0 -= has_h ? 16 : 8;
+                x1 -= has_h ? 16 : 8;
+            }
+            y[j] = __float2half_rn(has_m ? (float) x0 * d + m : (float) x0 * d);
+            y[j + 16] = __float2half_rn(has_m ? (float) x1 * d + m : (float) x1 * d);
+        }
+    }
+}
+
 template <typename T> bool read_pod(whisper_model_loader * l, T & v) { return l->read(l->context, &v, sizeof(T)) == sizeof(T); }
 
 }  // namespace
@@ -255,10 +308,12 @@ bool model_load(whisper_model_loader * loader, Model & m, DType dtype, int devic
         default: m.type = 0;
     }
     hp.ftype %= 1000;   // GGML_QNT_VERSION_FACTOR
-    if (hp.ftype != 0 && hp.ftype != 1) {
+    // 0 f32, 1 f16, 2 q4_0, 3 q4_1, 7 q8_0, 8 q5_0, 9 q5_1 (ggml_ftype, ggml/include/ggml.h); the 32-element block formats are
+    // expanded to 16-bit weights while loading (record by record, whatever its own type says).  K-quants / IQ formats are not.
+    if (hp.ftype != 0 && hp.ftype != 1 && hp.ftype != 2 && hp.ftype != 3 && hp.ftype != 7 && hp.ftype != 8 && hp.ftype != 9) {
         wlog(GGML_LOG_LEVEL_ERROR,
-             "%s: quantised model files (ftype %d) are not supported by the B200 path: use an F16 or F32 file\n", __func__,
-             hp.ftype);
+             "%s: model file ftype %d is not supported by the B200 path (supported: f32, f16, q4_0, q4_1, q5_0, q5_1, q8_0)\n",
+             __func__, hp.ftype);
         return false;
     }
     const int d = hp.n_audio_state;
@@ -343,13 +398,15 @@ bool model_load(whisper_model_loader * loader, Model & m, DType dtype, int devic
 
     // tensor records
     std::map<std::string, HostTensor> tensors;
+    int n_quantised = 0;
     while (true) {
         int32_t n_dims = 0, length = 0, ttype = 0;
         if (!read_pod(loader, n_dims)) break;   // clean EOF
         if (!read_pod(loader, length) || !read_pod(loader, ttype)) break;
-        if (n_dims < 1 || n_dims > 4 || length <= 0 || length > 256 || (ttype != 0 && ttype != 1)) {
-            wlog(GGML_LOG_LEVEL_ERROR, "%s: malformed tensor record (n_dims=%d, name_len=%d, type=%d)\n", __func__, n_dims,
-                 length, ttype);
+        const int qblock = quant_block_bytes(ttype);      // 0: not a block format
+        if (n_dims < 1 || n_dims > 4 || length <= 0 || length > 256 || (ttype != 0 && ttype != 1 && qblock == 0)) {
+            wlog(GGML_LOG_LEVEL_ERROR, "%s: malformed or unsupported tensor record (n_dims=%d, name_len=%d, type=%d)\n", __func__,
+                 n_dims, length, ttype);
             return false;
         }
         HostTensor t;
@@ -359,6 +416,26 @@ bool model_load(whisper_model_loader * loader, Model & m, DType dtype, int devic
             if (!read_pod(loader, t.ne[i]) || t.ne[i] <= 0) return false;
         std::string name(length, '\0');
         if (loader->read(loader->context, &name[0], length) != (size_t) length) return false;
+        if (qblock) {
+            // quantised record: rows of ne[0] elements in blocks of 32 (reference ggml/src/ggml-quants.c:307-415); expand to f16
+            if (t.ne[0] % 32) {
+                wlog(GGML_LOG_LEVEL_ERROR, "%s: tensor '%s': quantised row length %d is not a multiple of 32\n", __func__,
+                     name.c_str(), t.ne[0]);
+                return false;
+            }
+            const size_t n_blocks = t.nelem() / 32;
+            std::vector<unsigned char> raw(n_blocks * qblock);
+            if (loader->read(loader->context, raw.data(), raw.size()) != raw.size()) {
+                wlog(GGML_LOG_LEVEL_ERROR, "%s: tensor '%s' is truncated\n", __func__, name.c_str());
+                return false;
+            }
+            t.data.resize(t.nelem() * 2);
+            dequantize_blocks(ttype, raw.data(), n_blocks, reinterpret_cast<__half *>(t.data.data()));
+            t.ttype = 1;
+            ++n_quantised;
+            tensors[name] = std::move(t);
+            continue;
+        }
         const size_t bytes = t.nelem() * (ttype == 1 ? 2 : 4);
         t.data.resize(bytes);
         if (loader->read(loader->context, t.data.data(), bytes) != bytes) {
@@ -526,6 +603,8 @@ bool model_load(whisper_model_loader * loader, Model & m, DType dtype, int devic
         wlog(GGML_LOG_LEVEL_ERROR, "%s: failed to place the weights on CUDA device %d\n", __func__, device);
         return false;
     }
+    if (n_quantised)
+        wlog(GGML_LOG_LEVEL_INFO, "%s: %d quantised tensors (ftype %d) expanded to 16-bit weights at load\n", __func__, n_quantised, hp.ftype);
     wlog(GGML_LOG_LEVEL_INFO, "%s: %s weights on device %d: %.2f MB\n", __func__, dtype == DType::F16 ? "f16" : "bf16", device,
          m.bytes_device / 1e6);
     return true;

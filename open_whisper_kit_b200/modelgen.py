@@ -191,15 +191,111 @@ def _init(kind, shape, rng, tok_emb_gain):
     raise ValueError(kind)
 
 
-def write_model(path, arch, seed=1234, ftype=1, tok_emb_gain=1.5, with_tensors=True):
+# ---- ggml 32-element block formats (what `examples/quantize` writes) ----------------------------------------------
+# ggml_type of a record / ggml_ftype of the file header (reference ggml/include/ggml.h), bytes per block
+QUANT_TYPES = {"q4_0": (2, 2, 18), "q4_1": (3, 3, 20), "q5_0": (6, 8, 22), "q5_1": (7, 9, 24), "q8_0": (8, 7, 34)}
+GGML_QNT_VERSION = 2
+
+
+def quantize_blocks(x, qtype):
+    """numpy restatement of quantize_row_{q4_0,q4_1,q5_0,q5_1,q8_0}_ref (reference ggml/src/ggml-quants.c:36-222):
+    x f32, size a multiple of 32 -> raw block bytes.  float32 arithmetic, C truncation where the reference casts."""
+    x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1, 32)
+    nb = x.shape[0]
+    f32 = np.float32
+    if qtype == "q8_0":
+        amax = np.abs(x).max(axis=1)
+        d = (amax / f32(127)).astype(f32)
+        idv = np.where(d != 0, f32(1) / np.where(d != 0, d, f32(1)), f32(0)).astype(f32)
+        v = x * idv[:, None]
+        q = (np.sign(v) * np.floor(np.abs(v) + f32(0.5))).astype(np.int8)          # roundf: half away from zero
+        out = np.empty((nb, 34), np.uint8)
+        out[:, 0:2] = d.astype(np.float16).view(np.uint8).reshape(nb, 2)
+        out[:, 2:] = q.view(np.uint8)
+        return out.tobytes()
+    sym = qtype in ("q4_0", "q5_0")
+    bits = 4 if qtype in ("q4_0", "q4_1") else 5
+    top = (1 << bits) - 1
+    if sym:
+        idx = np.abs(x).argmax(axis=1)                       # first element with the largest magnitude
+        mx = x[np.arange(nb), idx]
+        d = (mx / f32(-(1 << (bits - 1)))).astype(f32)
+        mn = np.zeros(nb, f32)
+        off = f32((1 << (bits - 1)) + 0.5)
+    else:
+        mn = x.min(axis=1)
+        d = ((x.max(axis=1) - mn) / f32(top)).astype(f32)
+        off = f32(0.5)
+    idv = np.where(d != 0, f32(1) / np.where(d != 0, d, f32(1)), f32(0)).astype(f32)
+    # the reference build contracts `t * id + off` into one fused multiply-add (gcc -O3 -mfma): the float64 product of two
+    # float32 values is exact, so rounding the float64 sum once more to float32 reproduces it
+    t = (x - mn[:, None]).astype(f32)
+    v = (t.astype(np.float64) * idv[:, None].astype(np.float64) + np.float64(off)).astype(f32)
+    if qtype == "q5_1":
+        q = np.trunc(v).astype(np.int64).astype(np.uint8)                         # (uint8_t) cast, no clamp
+    else:
+        q = np.minimum(top, np.trunc(v).astype(np.int64).astype(np.int8)).astype(np.uint8)      # MIN(top, (int8_t) v)
+    lo, hi = q[:, :16], q[:, 16:]
+    qs = ((lo & 0x0F) | ((hi & 0x0F) << 4)).astype(np.uint8)
+    parts = [d.astype(np.float16).view(np.uint8).reshape(nb, 2)]
+    if not sym:
+        parts.append(mn.astype(np.float16).view(np.uint8).reshape(nb, 2))
+    if bits == 5:
+        sh = np.arange(16, dtype=np.uint32)
+        qh = (((lo.astype(np.uint32) & 0x10) >> 4) << sh).sum(axis=1, dtype=np.uint32) | \
+             (((hi.astype(np.uint32) & 0x10) >> 4) << (sh + 16)).sum(axis=1, dtype=np.uint32)
+        parts.append(qh.astype("<u4").view(np.uint8).reshape(nb, 4))
+    parts.append(qs)
+    return np.concatenate(parts, axis=1).tobytes()
+
+
+def dequantize_blocks(raw, qtype):
+    """numpy restatement of dequantize_row_* (reference ggml/src/ggml-quants.c:307-415): raw block bytes -> f32."""
+    bb = QUANT_TYPES[qtype][2]
+    b = np.frombuffer(raw, np.uint8).reshape(-1, bb)
+    nb = b.shape[0]
+    d = b[:, 0:2].copy().view(np.float16).astype(np.float32).reshape(nb)
+    if qtype == "q8_0":
+        return (b[:, 2:].copy().view(np.int8).astype(np.float32) * d[:, None]).reshape(-1)
+    sym = qtype in ("q4_0", "q5_0")
+    five = qtype in ("q5_0", "q5_1")
+    o = 2
+    m = np.zeros(nb, np.float32)
+    if not sym:
+        m = b[:, 2:4].copy().view(np.float16).astype(np.float32).reshape(nb)
+        o = 4
+    lo = (b[:, o + (4 if five else 0):] & 0x0F).astype(np.int32)
+    hi = (b[:, o + (4 if five else 0):] >> 4).astype(np.int32)
+    if five:
+        qh = b[:, o:o + 4].copy().view("<u4").reshape(nb).astype(np.uint32)
+        j = np.arange(16, dtype=np.uint32)
+        lo |= (((qh[:, None] >> j) << 4) & 0x10).astype(np.int32)
+        hi |= ((qh[:, None] >> (j + 12)) & 0x10).astype(np.int32)
+    if sym:
+        lo -= 16 if five else 8
+        hi -= 16 if five else 8
+    y = np.concatenate([lo, hi], axis=1).astype(np.float32) * d[:, None]
+    if not sym:
+        y = y + m[:, None]           # (symmetric formats: no `+ 0`, the reference keeps the sign of -8 * 0)
+    return y.astype(np.float32).reshape(-1)
+
+
+def write_model(path, arch, seed=1234, ftype=1, tok_emb_gain=1.5, with_tensors=True, qtype=None, dequantized=False):
     """Write a GGML whisper model file.  ftype=1: 2-D+ weights as F16 (conv biases / positional
-    embeddings / 1-D tensors stay F32, as the reference converter does); ftype=0: everything F32."""
+    embeddings / 1-D tensors stay F32, as the reference converter does); ftype=0: everything F32.
+    qtype ('q4_0' | 'q4_1' | 'q5_0' | 'q5_1' | 'q8_0'): what the reference's `quantize` tool makes of the ftype=1 file --
+    every 2-D tensor except the positional embeddings and conv biases becomes block-quantised, the header ftype becomes
+    2000 + ggml_ftype (examples/quantize/quantize.cpp:70-176, examples/common-ggml.cpp:121-140).  dequantized=True writes
+    the F16 file whose weights are exactly those blocks expanded again (the teacher file of the load-time expansion test)."""
+    if qtype is not None:
+        ftype = 1
     n_vocab, n_actx, d, n_head, n_al, n_tctx, n_tl, n_mels = ARCHS[arch]
     multilingual = n_vocab >= 51865
     rng = np.random.default_rng(seed)
     with open(path, "wb") as f:
         f.write(struct.pack("<I", GGML_MAGIC))
-        f.write(struct.pack("<11i", n_vocab, n_actx, d, n_head, n_al, n_tctx, d, n_head, n_tl, n_mels, ftype))
+        hdr_ftype = ftype if qtype is None or dequantized else GGML_QNT_VERSION * 1000 + QUANT_TYPES[qtype][1]
+        f.write(struct.pack("<11i", n_vocab, n_actx, d, n_head, n_al, n_tctx, d, n_head, n_tl, n_mels, hdr_ftype))
         filt = mel_filters(n_mels)
         f.write(struct.pack("<2i", n_mels, N_FFT_BINS))
         f.write(filt.tobytes())
@@ -214,12 +310,19 @@ def write_model(path, arch, seed=1234, ftype=1, tok_emb_gain=1.5, with_tensors=T
             data = _init(kind, shape, rng, tok_emb_gain)
             use_f16 = ftype == 1 and len(shape) >= 2 and kind not in ("enc_pos", "dec_pos", "bias2d")
             ttype = 1 if use_f16 else 0
+            payload = data.astype(np.float16 if use_f16 else np.float32).tobytes()
+            if qtype is not None and len(shape) == 2 and kind not in ("enc_pos", "dec_pos", "bias2d"):
+                raw = quantize_blocks(data.astype(np.float16).astype(np.float32), qtype)     # the tool reads the F16 file
+                if dequantized:
+                    payload = dequantize_blocks(raw, qtype).astype(np.float16).tobytes()
+                else:
+                    ttype, payload = QUANT_TYPES[qtype][0], raw
             nb = name.encode()
             f.write(struct.pack("<3i", len(shape), len(nb), ttype))
             for dim in reversed(shape):  # ggml ne[] order: fastest dimension first
                 f.write(struct.pack("<i", dim))
             f.write(nb)
-            f.write(data.astype(np.float16 if use_f16 else np.float32).tobytes())
+            f.write(payload)
 
 
 def synth_pcm(n_samples, seed=7, stream=0):

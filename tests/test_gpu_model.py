@@ -280,6 +280,59 @@ def test_cross_kv_pool_matches_live_reference(lib, model_dir):
             assert dk <= 2e-2 and dv <= 2e-2
 
 
+def _quant_paths(model_dir, arch, qtype):
+    q = os.path.join(model_dir, f"{arch}-{qtype}.bin")
+    t = os.path.join(model_dir, f"{arch}-{qtype}-expanded.bin")
+    if not os.path.exists(q):
+        modelgen.write_model(q, arch, qtype=qtype)
+        modelgen.write_model(t, arch, qtype=qtype, dequantized=True)
+    return q, t
+
+
+def _enc_and_logits(lib_, path, pcm, toks, **kw):
+    with api.Whisper(lib_, path, flash_attn=False, **kw) as w:
+        n_thr = min(os.cpu_count() or 4, 32)
+        assert w.pcm_to_mel(pcm, n_thr) == 0 and w.encode(0, n_thr) == 0
+        rc, lg = w.decode(toks, 0, n_thr)
+        assert rc == 0
+        return lg.copy()
+
+
+@pytest.mark.parametrize("qtype", sorted(modelgen.QUANT_TYPES))
+def test_quantised_file_loads_as_its_expansion(lib, model_dir, qtype):
+    """A block-quantised GGML file (what the reference's `quantize` tool writes) is expanded to 16-bit weights
+    at load: the run must be BIT-identical to the run on an F16 file holding the oracle's expansion of the same blocks
+    (modelgen.dequantize_blocks, pinned against ggml's dequantize_row_* in tests/test_oracle_pinning.py)."""
+    q, t = _quant_paths(model_dir, "tiny.en", qtype)
+    pcm = pcm_for({"kind": "jfk"})
+    toks = [50257]          # <|startoftranscript|> of the *.en vocabularies
+    a = _enc_and_logits(lib, q, pcm, toks)
+    b = _enc_and_logits(lib, t, pcm, toks)
+    assert np.isfinite(a).all()
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+@pytest.mark.parametrize("qtype", ["q8_0", "q5_0"])
+def test_quantised_model_vs_live_reference(lib, model_dir, qtype):
+    """Same quantised file through the reference CPU path.  The reference multiplies quantised weights with activations it
+    quantises to Q8 blocks on the fly (ggml vec_dot_q*_q8_0), ours multiplies the expanded weights with f16 activations, so
+    the two agree to the activation-quantisation noise, not to the 2e-2 of the F16 files; the greedy token must agree."""
+    ref, _ = reflib.load()
+    if ref is None:
+        pytest.skip("oracle/_ref was not built / did not travel")
+    q, _ = _quant_paths(model_dir, "tiny.en", qtype)
+    pcm = pcm_for({"kind": "jfk"})
+    toks = [50257]
+    a = _enc_and_logits(lib, q, pcm, toks)
+    b = _enc_and_logits(ref, q, pcm, toks, use_gpu=False)
+    dl = np.abs(a - b)
+    top2 = np.sort(b[:50256])[-2:]
+    print(f"{qtype}: logits max|d| = {dl.max():.3e} mean|d| = {dl.mean():.3e}; reference top-2 gap {top2[1] - top2[0]:.3f}")
+    assert dl.max() <= 0.15 and dl.mean() <= 0.02       # measured on B200: 6.6e-2 / 1.1e-2 (q8_0), 6.2e-2 / 1.1e-2 (q5_0)
+    if top2[1] - top2[0] > 2 * dl.max():
+        assert int(a[:50256].argmax()) == int(b[:50256].argmax())
+
+
 def test_bf16_operands_track_f16(lib, model_dir, monkeypatch):
     """WHISPER_B200_DTYPE=bf16 (the operand type BASELINE.json names) runs every kernel of the path -- tcgen05 GEMMs and
     attention, decoder step -- and stays close to the f16 run (bf16 has 3 fewer mantissa bits: ~8x the rounding error)."""

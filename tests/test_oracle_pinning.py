@@ -123,3 +123,45 @@ def test_golden_token_fixture_is_consistent():
     # the per-step top-2 gaps of the reference: near-ties far below any 16-bit implementation's logit error exist
     gaps = np.concatenate([np.array(w["gaps"]) for w in nots["steps"]])
     assert gaps.size == 3520 and gaps.min() < 1e-3 and np.median(gaps) > 0.05
+
+
+# ---- ggml block quantisation (modelgen.quantize_blocks / dequantize_blocks) ----------------------------------------
+QUANT_GOLD = os.path.join(HERE, "golden", "golden_quant.npz")
+
+
+def _quant_inputs():
+    rng = np.random.default_rng(20260118)
+    x = (rng.standard_normal(32 * 257) * 0.07).astype(np.float32)
+    x[:32] = 0.0                                   # an all-zero block (d = 0)
+    x[32:64] = np.float32(0.125)                   # a constant block (q4_1 / q5_1: max == min)
+    x[64] = np.float32(-3.0)                       # one large negative / positive outlier per block
+    x[96 + 17] = np.float32(2.5)
+    return x
+
+
+@pytest.mark.parametrize("qtype", sorted(modelgen.QUANT_TYPES))
+def test_block_quantisers_match_reference_golden(qtype):
+    """The numpy restatement writes the same block bytes and expands them to the same floats as the reference's
+    quantize_row_*_ref / dequantize_row_* (golden vectors made by tests/golden/make_golden_quant.py from oracle/_ref)."""
+    g = np.load(QUANT_GOLD)
+    x = _quant_inputs()
+    raw = modelgen.quantize_blocks(x, qtype)
+    assert raw == g[f"{qtype}/raw"].tobytes()
+    y = modelgen.dequantize_blocks(raw, qtype)
+    assert np.array_equal(y.view(np.uint32), g[f"{qtype}/deq"].view(np.uint32))
+
+
+@pytest.mark.parametrize("qtype", sorted(modelgen.QUANT_TYPES))
+def test_block_quantisers_vs_live_reference(qtype):
+    ref, _ = reflib.load()
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal(32 * 4096) * rng.uniform(0.001, 2.0)).astype(np.float32)
+    bb = modelgen.QUANT_TYPES[qtype][2]
+    raw = np.zeros(len(x) // 32 * bb, np.uint8)
+    getattr(ref, f"quantize_row_{qtype}_ref")(x.ctypes.data_as(FP), raw.ctypes.data_as(C.c_void_p), C.c_int64(len(x)))
+    assert modelgen.quantize_blocks(x, qtype) == raw.tobytes()
+    y = np.empty_like(x)
+    getattr(ref, f"dequantize_row_{qtype}")(raw.ctypes.data_as(C.c_void_p), y.ctypes.data_as(FP), C.c_int64(len(x)))
+    assert np.array_equal(modelgen.dequantize_blocks(raw.tobytes(), qtype).view(np.uint32), y.view(np.uint32))
