@@ -8,20 +8,68 @@
 
 constexpr int W = 64, H = 20, T = 1500, D = 1280, L = 4;      // L layers resident: 4 x 491.5 MB, rotated to defeat L2
 
+__device__ __forceinline__ uint4 ld_na(const uint4 * p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+// mode 3: bulk copies (cp.async.bulk, 16 KB chunks, 4-stage ring) of the contiguous 384 KB block; nobody reads shared memory
+__global__ void __launch_bounds__(128, 3) bulk_kernel(const uint4 * __restrict__ base, int layer, unsigned * sink) {
+    extern __shared__ __align__(128) unsigned char ring[];
+    __shared__ __align__(8) unsigned long long bar[4];
+    const int w = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
+    const size_t off = (((size_t) layer * W + w) * H + h) * 2 * (size_t) T * 8;       // 16-byte units
+    const char * src = reinterpret_cast<const char *>(base + off);
+    constexpr int CH = 16384, NCH = 2 * T * 128 / CH;                               // 23 full chunks (+ remainder ignored)
+    if (tid == 0) {
+        for (int i = 0; i < 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned) __cvta_generic_to_shared(&bar[i])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int c = 0; c < NCH; ++c) {
+            const int s = c & 3;
+            const unsigned b = (unsigned) __cvta_generic_to_shared(&bar[s]);
+            if (c >= 4) {
+                unsigned ok = 0;
+                const unsigned par = ((c >> 2) - 1) & 1;
+                while (!ok) asm volatile("{.reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0,1,0,p;}" : "=r"(ok) : "r"(b), "r"(par) : "memory");
+            }
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(CH) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             (unsigned) __cvta_generic_to_shared(ring + s * CH)),
+                         "l"(src + (size_t) c * CH), "r"(CH), "r"(b)
+                         : "memory");
+        }
+        for (int s = 0; s < 4; ++s) {       // drain
+            const int c = NCH - 4 + s;
+            const unsigned b = (unsigned) __cvta_generic_to_shared(&bar[c & 3]);
+            unsigned ok = 0;
+            const unsigned par = (c >> 2) & 1;
+            while (!ok) asm volatile("{.reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0,1,0,p;}" : "=r"(ok) : "r"(b), "r"(par) : "memory");
+        }
+    }
+    __syncthreads();
+    if (ring[tid] == 77 && sink[1] == 3) sink[0] = 1;
+}
+
 template <int MODE>
-__global__ void __launch_bounds__(128, 9) read_kernel(const uint4 * __restrict__ base, int layer, unsigned * sink) {
+__global__ void __launch_bounds__(MODE == 2 ? 256 : 128, MODE == 2 ? 4 : 9) read_kernel(const uint4 * __restrict__ base, int layer, unsigned * sink) {
     const int w = blockIdx.x, h = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, sub = lane & 7, grp = lane >> 3;
     unsigned acc = 0;
+    constexpr int RB = MODE == 2 ? 256 : 128;       // rows per batch
     for (int pass = 0; pass < 2; ++pass) {          // K sweep, V sweep
-        for (int b = 0; b < T; b += 128) {
+        for (int b = 0; b < T; b += RB) {
             uint4 v[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                const int t = b + warp * 4 + grp + 16 * u;
+                const int t = b + warp * 4 + grp + (RB / 8) * u;
                 size_t off;                          // in 16-byte units
                 if (MODE == 0) off = (((size_t) w * L + layer) * T + t) * (2 * D / 8) + pass * (D / 8) + h * 8 + sub;
-                else off = ((((size_t) layer * W + w) * H + h) * 2 + pass) * (size_t) T * 8 + (size_t) t * 8 + sub;
-                v[u] = t < T ? __ldg(base + off) : make_uint4(0, 0, 0, 0);
+                else off = ((((size_t) layer * W + w) * H + h) * 2 + (MODE == 4 ? (u & 1) : pass)) * (size_t) T * 8 +
+                           (size_t) (MODE == 4 ? (b / 2 + warp * 4 + grp + 16 * (u >> 1) + pass * 750 >= T ? T - 1 : b / 2 + warp * 4 + grp + 16 * (u >> 1) + pass * 750) : t) * 8 + sub;
+                v[u] = t < T ? (MODE == 5 ? ld_na(base + off) : __ldg(base + off)) : make_uint4(0, 0, 0, 0);
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) acc ^= v[u].x ^ v[u].y ^ v[u].z ^ v[u].w;
@@ -35,25 +83,34 @@ int main() {
     uint4 * buf;
     unsigned * sink;
     cudaMalloc(&buf, bytes);
-    cudaMalloc(&sink, 4);
+    cudaMalloc(&sink, 8);
+    cudaMemset(sink, 0, 8);
     cudaMemset(buf, 1, bytes);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    for (int mode = 0; mode < 2; ++mode) {
+    cudaFuncSetAttribute(bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+    const char * names[6] = {"strided 128 B @ 5120 B", "head-major contiguous", "contiguous, 256-thread CTAs", "contiguous, cp.async.bulk 16 KB x 4 stages",
+                             "contiguous, K and V interleaved", "contiguous, L1::no_allocate"};
+    for (int mode = 0; mode < 6; ++mode) {
         for (int rep = 0; rep < 3; ++rep) {
             cudaEventRecord(e0);
             for (int i = 0; i < 32; ++i) {
-                if (mode == 0) read_kernel<0><<<dim3(W, H), 128>>>(buf, i % L, sink);
-                else read_kernel<1><<<dim3(W, H), 128>>>(buf, i % L, sink);
+                switch (mode) {
+                    case 0: read_kernel<0><<<dim3(W, H), 128>>>(buf, i % L, sink); break;
+                    case 1: read_kernel<1><<<dim3(W, H), 128>>>(buf, i % L, sink); break;
+                    case 2: read_kernel<2><<<dim3(W, H), 256>>>(buf, i % L, sink); break;
+                    case 3: bulk_kernel<<<dim3(W, H), 128, 65536>>>(buf, i % L, sink); break;
+                    case 4: read_kernel<4><<<dim3(W, H), 128>>>(buf, i % L, sink); break;
+                    default: read_kernel<5><<<dim3(W, H), 128>>>(buf, i % L, sink); break;
+                }
             }
             cudaEventRecord(e1);
             cudaEventSynchronize(e1);
             float ms;
             cudaEventElapsedTime(&ms, e0, e1);
             const double per = ms / 32 * 1e3, gb = (double) W * T * 2 * D * 2 / 1e9;
-            printf("mode %d (%s): %.2f us per launch, %.0f GB/s\n", mode, mode ? "head-major contiguous" : "strided 128 B @ 5120 B", per,
-                   gb / (per * 1e-6));
+            printf("mode %d (%s): %.2f us per launch, %.0f GB/s\n", mode, names[mode], per, gb / (per * 1e-6));
         }
     }
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
