@@ -421,6 +421,7 @@ struct Stream {
     whisper_full_params params;
     const float * samples = nullptr;
     int n_samples = 0;
+    bool samples_on_device = false;
     int rc = 0;
     Phase phase = Phase::WINDOW;
 
@@ -441,6 +442,8 @@ struct Stream {
 };
 
 }  // namespace
+
+static void signal_energy(const float * signal, int n_samples, int hw, std::vector<float> & out);
 
 static int stream_begin(whisper_context & ctx, Stream & s) {
     whisper_state * state = s.state;
@@ -464,6 +467,20 @@ static int stream_begin(whisper_context & ctx, Stream & s) {
         if (params.detect_language) {
             s.phase = Phase::DONE;
             return 0;
+        }
+    }
+    if (params.token_timestamps) {              // src/whisper.cpp:6863-6871
+        state->t_beg = 0;
+        state->t_last = 0;
+        state->tid_last = 0;
+        if (s.n_samples > 0) {
+            if (s.samples_on_device) {
+                std::vector<float> host((size_t) s.n_samples);
+                if (cudaMemcpy(host.data(), s.samples, (size_t) s.n_samples * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+                signal_energy(host.data(), s.n_samples, 32, state->energy);
+            } else {
+                signal_energy(s.samples, s.n_samples, 32, state->energy);
+            }
         }
     }
     s.seek_start = params.offset_ms / 10;
@@ -561,6 +578,208 @@ static int stream_begin(whisper_context & ctx, Stream & s) {
     return 0;
 }
 
+// ---- [EXPERIMENTAL] token-level timestamps (params.token_timestamps, max_len, split_on_word) -------------------------
+// Host-side restatement of get_signal_energy / voice_length / whisper_exp_compute_token_level_timestamps /
+// whisper_wrap_segment (src/whisper.cpp:8398-8660, 6045-6130): pure bookkeeping on the sampled tokens' (tid, pt, ptsum) and on
+// the PCM envelope, so it runs unchanged behind the device path.
+
+// mean |x| over a window of 2*hw + 1 samples (src/whisper.cpp:8425-8442); same summation order, rows spread over threads
+static void signal_energy(const float * signal, int n_samples, int hw, std::vector<float> & out) {
+    out.assign((size_t) std::max(n_samples, 0), 0.0f);
+    const int n_chunks = (n_samples + 65535) / 65536;
+    parallel_for(n_chunks, [&](int c) {
+        const int i_end = std::min(n_samples, (c + 1) * 65536);
+        for (int i = c * 65536; i < i_end; ++i) {
+            float sum = 0;
+            for (int j = -hw; j <= hw; ++j)
+                if (i + j >= 0 && i + j < n_samples) sum += fabs(signal[i + j]);
+            out[i] = sum / (2 * hw + 1);
+        }
+    });
+}
+
+// heuristic cost of pronouncing a token's text (src/whisper.cpp:8400-8422)
+static float voice_length(const std::string & text) {
+    float res = 0.0f;
+    for (char c : text) {
+        if (c == ' ') res += 0.01f;
+        else if (c == ',') res += 2.00f;
+        else if (c == '.' || c == '!' || c == '?') res += 3.00f;
+        else if (c >= '0' && c <= '9') res += 3.00f;
+        else res += 1.00f;
+    }
+    return res;
+}
+
+static int timestamp_to_sample(int64_t t, int64_t segment_t0, int n_samples) {      // src/whisper.cpp:8444-8449
+    const int64_t relative_t = t - segment_t0;
+    const int sample = (int) ((relative_t * WHISPER_SAMPLE_RATE) / 100);
+    return std::max(0, std::min(n_samples - 1, sample));
+}
+static int64_t sample_to_timestamp(int i_sample, int64_t segment_t0) {               // src/whisper.cpp:8451-8454
+    return (100ll * i_sample) / WHISPER_SAMPLE_RATE + segment_t0;
+}
+
+static void compute_token_level_timestamps(const Vocab & vocab, whisper_state & state, int i_segment, float thold_pt,
+                                           float thold_ptsum) {
+    auto & segment = state.result_all[i_segment];
+    auto & tokens = segment.tokens;
+    const int n_samples = (int) state.energy.size();
+    if (n_samples == 0) {
+        wlog(GGML_LOG_LEVEL_ERROR, "%s: no signal data available\n", __func__);
+        return;
+    }
+    const int64_t t0 = segment.t0, t1 = segment.t1;
+    const int n = (int) tokens.size();
+    if (n == 0) return;
+    if (n == 1) {
+        tokens[0].t0 = t0;
+        tokens[0].t1 = t1;
+        return;
+    }
+    auto & t_beg = state.t_beg;
+    auto & t_last = state.t_last;
+    auto & tid_last = state.tid_last;
+    for (int j = 0; j < n; ++j) {
+        auto & token = tokens[j];
+        if (j == 0) {
+            if (token.id == vocab.token_beg) {
+                tokens[j].t0 = t0;
+                tokens[j].t1 = t0;
+                tokens[j + 1].t0 = t0;
+                t_beg = t0;
+                t_last = t0;
+                tid_last = vocab.token_beg;
+            } else {
+                tokens[j].t0 = t_last;
+            }
+        }
+        const int64_t tt = t_beg + 2 * (token.tid - vocab.token_beg);
+        tokens[j].vlen = voice_length(vocab.id_to_token[token.id]);
+        if (token.pt > thold_pt && token.ptsum > thold_ptsum && token.tid > tid_last && tt <= t1) {
+            if (j > 0) tokens[j - 1].t1 = tt;
+            tokens[j].t0 = tt;
+            tid_last = token.tid;
+        }
+    }
+    tokens[n - 2].t1 = t1;
+    tokens[n - 1].t0 = t1;
+    tokens[n - 1].t1 = t1;
+    t_last = t1;
+
+    // runs of tokens without a timestamp of their own share their interval in proportion to the voice lengths
+    {
+        int p0 = 0, p1 = 0;
+        while (true) {
+            while (p1 < n && tokens[p1].t1 < 0) p1++;
+            if (p1 >= n) p1--;
+            if (p1 > p0) {
+                double psum = 0.0;
+                for (int j = p0; j <= p1; j++) psum += tokens[j].vlen;
+                const double dt = tokens[p1].t1 - tokens[p0].t0;
+                for (int j = p0 + 1; j <= p1; j++) {
+                    const double ct = tokens[j - 1].t0 + dt * tokens[j - 1].vlen / psum;
+                    tokens[j - 1].t1 = ct;
+                    tokens[j].t0 = ct;
+                }
+            }
+            p1++;
+            p0 = p1;
+            if (p1 >= n) break;
+        }
+    }
+    for (int j = 0; j < n - 1; j++) {
+        if (tokens[j].t1 < 0) tokens[j + 1].t0 = tokens[j].t1;
+        if (j > 0 && tokens[j - 1].t1 > tokens[j].t0) {
+            tokens[j].t0 = tokens[j - 1].t1;
+            tokens[j].t1 = std::max(tokens[j].t0, tokens[j].t1);
+        }
+    }
+
+    // expand or contract every token towards the edges of the voiced stretch around it
+    {
+        const int hw = WHISPER_SAMPLE_RATE / 8;
+        const std::vector<float> & energy = state.energy;
+        for (int j = 0; j < n; j++) {
+            if (tokens[j].id >= vocab.token_eot) continue;
+            int s0 = timestamp_to_sample(tokens[j].t0, segment.t0, n_samples);
+            int s1 = timestamp_to_sample(tokens[j].t1, segment.t0, n_samples);
+            const int ss0 = std::max(s0 - hw, 0), ss1 = std::min(s1 + hw, n_samples);
+            const int ns = ss1 - ss0;
+            float sum = 0.0f;
+            for (int k = ss0; k < ss1; k++) sum += energy[k];
+            const float thold = 0.5 * sum / ns;
+            {
+                int k = s0;
+                if (energy[k] > thold && j > 0) {
+                    while (k > 0 && energy[k] > thold) k--;
+                    tokens[j].t0 = sample_to_timestamp(k, segment.t0);
+                    if (tokens[j].t0 < tokens[j - 1].t1) tokens[j].t0 = tokens[j - 1].t1;
+                    else s0 = k;
+                } else {
+                    while (energy[k] < thold && k < s1) k++;
+                    s0 = k;
+                    tokens[j].t0 = sample_to_timestamp(k, segment.t0);
+                }
+            }
+            {
+                int k = s1;
+                if (energy[k] > thold) {
+                    while (k < n_samples - 1 && energy[k] > thold) k++;
+                    tokens[j].t1 = sample_to_timestamp(k, segment.t0);
+                    if (j < n - 1 && tokens[j].t1 > tokens[j + 1].t0) tokens[j].t1 = tokens[j + 1].t0;
+                    else s1 = k;
+                } else {
+                    while (energy[k] < thold && k > s0) k--;
+                    s1 = k;
+                    tokens[j].t1 = sample_to_timestamp(k, segment.t0);
+                }
+            }
+        }
+    }
+}
+
+static int utf8_len(const char * str) {                   // characters, not bytes (src/whisper.cpp:6052-6062)
+    int count = 0;
+    for (; *str; ++str)
+        if ((*str & 0xC0) != 0x80) count++;
+    return count;
+}
+
+// split the last segment so that no piece is longer than max_len characters (src/whisper.cpp:6077-6130)
+static int wrap_segment(const Vocab & vocab, whisper_state & state, int max_len, bool split_on_word) {
+    auto segment = state.result_all.back();
+    int res = 1, acc = 0;
+    std::string text;
+    for (int i = 0; i < (int) segment.tokens.size(); i++) {
+        const auto & token = segment.tokens[i];
+        if (token.id >= vocab.token_eot) continue;
+        const char * txt = vocab.id_to_token[token.id].c_str();
+        const int cur = utf8_len(txt);
+        if (acc + cur > max_len && i > 0 && (!split_on_word || txt[0] == ' ')) {
+            state.result_all.back().text = std::move(text);
+            state.result_all.back().t1 = token.t0;
+            state.result_all.back().tokens.resize(i);
+            state.result_all.back().speaker_turn_next = false;
+            state.result_all.push_back({});
+            state.result_all.back().t0 = token.t0;
+            state.result_all.back().t1 = segment.t1;
+            state.result_all.back().tokens.insert(state.result_all.back().tokens.end(), segment.tokens.begin() + i, segment.tokens.end());
+            state.result_all.back().speaker_turn_next = segment.speaker_turn_next;
+            acc = 0;
+            text = "";
+            segment = state.result_all.back();
+            i = -1;
+            res++;
+        } else {
+            acc += cur;
+            text += txt;
+        }
+    }
+    state.result_all.back().text = std::move(text);
+    return res;
+}
+
 // emit the segments of the finished window and advance the seek position (src/whisper.cpp:7609-7772)
 static void stream_finish_window(whisper_context & ctx, Stream & s) {
     whisper_state * state = s.state;
@@ -592,7 +811,12 @@ static void stream_finish_window(whisper_context & ctx, Stream & s) {
         }
         result_all.push_back({tt0, tt1, text, state->no_speech_prob, {}, turn});
         for (int j = i0; j <= i1_incl; ++j) result_all.back().tokens.push_back(tokens_cur[j]);
-        if (params.new_segment_callback) params.new_segment_callback(&ctx, state, 1, params.new_segment_callback_user_data);
+        int n_new = 1;
+        if (params.token_timestamps) {
+            compute_token_level_timestamps(vocab, *state, (int) result_all.size() - 1, params.thold_pt, params.thold_ptsum);
+            if (params.max_len > 0) n_new = wrap_segment(vocab, *state, params.max_len, params.split_on_word);
+        }
+        if (params.new_segment_callback) params.new_segment_callback(&ctx, state, n_new, params.new_segment_callback_user_data);
     };
 
     if (!tokens_cur.empty() && ctx.eng.model.n_loaded > 0 && !is_no_speech) {
@@ -648,6 +872,7 @@ int run_streams(whisper_context & ctx, std::vector<StreamSpec> & specs) {
             S[i].params = specs[i].params;
             S[i].samples = specs[i].samples;
             S[i].n_samples = specs[i].n_samples;
+            S[i].samples_on_device = specs[i].samples_on_device;
             S[i].window = i;
             S[i].state->result_all.clear();
             if (specs[i].n_samples > 0) {

@@ -67,6 +67,11 @@ struct whisper_state {
     float no_speech_prob = 0.0f;
     int32_t exp_n_audio_ctx = 0;
 
+    // [EXPERIMENTAL] token-level timestamps (reference whisper_state, src/whisper.cpp:919-927)
+    std::vector<float> energy;         // PCM signal energy
+    int64_t t_beg = 0, t_last = 0;
+    whisper_token tid_last = 0;
+
     struct whisper_context * ctx = nullptr;
 };
 

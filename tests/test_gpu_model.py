@@ -173,6 +173,41 @@ def test_token_data_fields_match_live_reference(lib, model_dir):
     assert n_cmp >= 40 and worst <= 2e-2
 
 
+@pytest.mark.parametrize("max_len,sow", [(0, False), (12, False), (16, True)])
+def test_token_level_timestamps_and_max_len_vs_live_reference(lib, model_dir, max_len, sow):
+    """params.token_timestamps / max_len / split_on_word (the cli's -ml / -sow / word-level output): per-token t0 / t1 / vlen
+    and the re-wrapped segments against the reference run live on this host's CPU (src/whisper.cpp:8455-8660, 6077-6130)."""
+    ref, _ = reflib.load()
+    if ref is None:
+        pytest.skip("oracle/_ref was not built / did not travel")
+    path = model_path(model_dir, "tiny.en")
+    pcm = pcm_for({"kind": "synth", "seed": 7, "windows": 2})
+
+    def run(lib_, **kw):
+        with api.Whisper(lib_, path, flash_attn=False, **kw) as w:
+            p = w.greedy_params(no_timestamps=False, n_threads=8)
+            p.token_timestamps = True
+            p.max_len = max_len
+            p.split_on_word = sow
+            rc, segs = w.full(p, pcm)
+            assert rc == 0
+            return segs
+
+    segs, rsegs = run(lib), run(ref, use_gpu=False)
+    n_cmp = 0
+    for a, b in zip(segs, rsegs):
+        if a.tokens != b.tokens:          # after a near-tie flip the sequences are different sequences
+            break
+        assert a.text == b.text and (a.t0, a.t1) == (b.t0, b.t1)
+        for ta, tb in zip(a.token_data, b.token_data):
+            assert (ta.t0, ta.t1) == (tb.t0, tb.t1) and ta.vlen == tb.vlen
+            n_cmp += 1
+    print(f"max_len={max_len} split_on_word={sow}: {len(segs)} segments (reference {len(rsegs)}), {n_cmp} tokens compared")
+    assert n_cmp >= 20 and len(rsegs) >= (3 if max_len else 1)
+    if max_len:
+        assert all(len(s.text) <= max_len or len(s.tokens) <= 2 or sow for s in segs)
+
+
 def test_low_level_api_vs_live_reference(lib, model_dir):
     """whisper_pcm_to_mel -> whisper_encode -> whisper_decode (bench.cpp's call sequence) against the live reference."""
     ref, _ = reflib.load()
