@@ -251,6 +251,171 @@ cross_attn_kernel(const T16 * __restrict__ q, int ldq, const DecRow * __restrict
     }
 }
 
+// ---- cross-attention on a bulk-copy ring --------------------------------------------------------------------------------
+// Same arithmetic as cross_attn_kernel<SELF = false> (same thread -> key / dimension mapping, same reduction orders), but the
+// contiguous 2 x 187.5 KB K / V blocks of one (window, head) arrive through cp.async.bulk in 16 KB chunks (128 keys) into a
+// four-stage shared-memory ring fed by one producer lane: the bare access pattern streams at 7.0 TB/s against 6.6 for
+// 16-byte loads (tools/microbench/readbw.cu).  The first four chunks are requested before the programmatic-launch dependency
+// resolves (cross K/V and the row descriptors were written before this decoder call began).
+constexpr int CB_STAGES = 4, CB_KEYS = 128, CB_CHUNK = CB_KEYS * 128;
+constexpr int CB_WARPS = 8;                       // compute warps; + 1 producer warp
+constexpr int CB_THREADS = (CB_WARPS + 1) * 32;
+
+__device__ __forceinline__ bool cb_try_wait(uint64_t * bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"((uint32_t) __cvta_generic_to_shared(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void cb_wait(uint64_t * bar, uint32_t parity) {          // bounded: trap instead of hanging the GPU
+    for (unsigned spins = 0; !cb_try_wait(bar, parity); ++spins)
+        if (spins > (1u << 26)) __trap();
+}
+
+template <typename T16>
+__global__ void __launch_bounds__(CB_THREADS, 2)
+cross_attn_bulk_kernel(const T16 * __restrict__ q, int ldq, const DecRow * __restrict__ rows, int d, size_t layer_off, int T,
+                       float kq_scale, int n_phantom, T16 * __restrict__ out) {
+    extern __shared__ __align__(128) uint8_t cb_smem[];         // ring [CB_STAGES][CB_CHUNK] | scores [T] f32
+    __shared__ __align__(8) uint64_t b_full[CB_STAGES], b_empty[CB_STAGES];
+    __shared__ float s_red[2 * CB_WARPS];
+    __shared__ float s_o[CB_WARPS][64];
+    float * s_sc = reinterpret_cast<float *>(cb_smem + CB_STAGES * CB_CHUNK);
+    const int r = blockIdx.x, h = blockIdx.y;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int sub = lane & 7, grp = lane >> 3;      // 8 lanes per key row, 4 key rows per warp instruction
+    const int nck = (T + CB_KEYS - 1) / CB_KEYS;    // chunks per sweep; chunk c: sweep c / nck (0 K, 1 V), keys (c % nck) * 128 ..
+    if (tid == 0) {
+        for (int i = 0; i < CB_STAGES; ++i) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t) __cvta_generic_to_shared(&b_full[i])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t) __cvta_generic_to_shared(&b_empty[i])), "r"(CB_WARPS));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == CB_WARPS) {
+        // ===== producer =====
+        if (lane == 0) {
+            const DecRow row = rows[r];
+            const uint8_t * blk = reinterpret_cast<const uint8_t *>(reinterpret_cast<const T16 *>(row.cross_kv) + layer_off +
+                                                                    (size_t) h * 2 * T * 64);
+            for (int c = 0; c < 2 * nck; ++c) {
+                const int s = c % CB_STAGES, sweep = c / nck, j = c - sweep * nck;
+                if (c >= CB_STAGES) cb_wait(&b_empty[s], ((c / CB_STAGES) - 1) & 1);
+                const uint32_t bytes = (uint32_t) (min(CB_KEYS, T - j * CB_KEYS) * 128);
+                const uint32_t bar = (uint32_t) __cvta_generic_to_shared(&b_full[s]);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 (uint32_t) __cvta_generic_to_shared(cb_smem + s * CB_CHUNK)),
+                             "l"(blk + (size_t) sweep * T * 128 + (size_t) j * CB_CHUNK), "r"(bytes), "r"(bar)
+                             : "memory");
+                if (c == nck) pdl_trigger();        // with the compute warps' trigger after the K sweep: let the successor in
+            }
+        }
+        return;
+    }
+
+    // ===== compute warps =====
+    pdl_wait();
+    float qv[8];
+    {
+        const uint4 u = *reinterpret_cast<const uint4 *>(q + (size_t) r * ldq + h * 64 + sub * 8);
+        const T16 * e = reinterpret_cast<const T16 *>(&u);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) qv[j] = Half16<T16>::to_f(e[j]);
+    }
+    auto sync_compute = [] { asm volatile("bar.sync 1, %0;" ::"n"(CB_WARPS * 32) : "memory"); };
+    float mx = -INFINITY;
+    for (int c = 0; c < nck; ++c) {
+        const int s = c % CB_STAGES;
+        cb_wait(&b_full[s], (c / CB_STAGES) & 1);
+        const uint8_t * stage = cb_smem + s * CB_CHUNK;
+#pragma unroll
+        for (int u = 0; u < CB_KEYS / (4 * CB_WARPS); ++u) {
+            const int kl = warp * 4 + grp + 4 * CB_WARPS * u, t = c * CB_KEYS + kl;
+            uint4 kb = make_uint4(0, 0, 0, 0);
+            if (t < T) kb = *reinterpret_cast<const uint4 *>(stage + kl * 128 + sub * 16);
+            const T16 * e = reinterpret_cast<const T16 *>(&kb);
+            float acc = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc = fmaf(qv[j], Half16<T16>::to_f(e[j]), acc);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+            acc *= kq_scale;
+            if (t < T) {
+                if (sub == 0) s_sc[t] = acc;
+                mx = fmaxf(mx, acc);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t) __cvta_generic_to_shared(&b_empty[s])) : "memory");
+    }
+    pdl_trigger();
+    mx = warp_max(mx);
+    if (lane == 0) s_red[warp] = mx;
+    sync_compute();
+    mx = s_red[0];
+#pragma unroll
+    for (int i = 1; i < CB_WARPS; ++i) mx = fmaxf(mx, s_red[i]);
+    if (n_phantom > 0) mx = fmaxf(mx, 0.0f);
+    float sum = 0.0f;
+    for (int t = tid; t < T; t += CB_WARPS * 32) {
+        const float e = expf(s_sc[t] - mx);
+        s_sc[t] = e;
+        sum += e;
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) s_red[CB_WARPS + warp] = sum;
+    sync_compute();
+    sum = s_red[CB_WARPS];
+#pragma unroll
+    for (int i = 1; i < CB_WARPS; ++i) sum += s_red[CB_WARPS + i];
+    if (n_phantom > 0) sum += (float) n_phantom * expf(-mx);
+    const float inv = 1.0f / sum;
+
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = 0.0f;
+    for (int c = nck; c < 2 * nck; ++c) {
+        const int s = c % CB_STAGES, c0 = (c - nck) * CB_KEYS;
+        cb_wait(&b_full[s], (c / CB_STAGES) & 1);
+        const uint8_t * stage = cb_smem + s * CB_CHUNK;
+#pragma unroll
+        for (int u = 0; u < CB_KEYS / (4 * CB_WARPS); ++u) {
+            const int kl = warp * 4 + grp + 4 * CB_WARPS * u, t = c0 + kl;
+            const bool ok = t < T;
+            uint4 vb = make_uint4(0, 0, 0, 0);
+            if (ok) vb = *reinterpret_cast<const uint4 *>(stage + kl * 128 + sub * 16);
+            const float pr = ok ? Half16<T16>::to_f(Half16<T16>::from_f(s_sc[t] * inv)) : 0.0f;
+            const T16 * e = reinterpret_cast<const T16 *>(&vb);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = fmaf(pr, Half16<T16>::to_f(e[j]), o[j]);
+        }
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t) __cvta_generic_to_shared(&b_empty[s])) : "memory");
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        o[j] += __shfl_xor_sync(0xffffffffu, o[j], 8);
+        o[j] += __shfl_xor_sync(0xffffffffu, o[j], 16);
+    }
+    if (grp == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s_o[warp][sub * 8 + j] = o[j];
+    }
+    sync_compute();
+    if (tid < 64) {
+        float v = s_o[0][tid];
+#pragma unroll
+        for (int i = 1; i < CB_WARPS; ++i) v += s_o[i][tid];
+        out[(size_t) r * d + h * 64 + tid] = Half16<T16>::from_f(v);
+    }
+}
+
 // ---- logit rules + greedy selection ------------------------------------------------------------------------
 struct ArgMax {
     float v;
@@ -619,6 +784,27 @@ void dec_cross_attn(DType dt, const void * q, const DecRow * d_rows, int R, int 
     dim3 grid(R, n_head);
     const float kq_scale = powf(64.0f, -0.25f);
     const size_t smem = (size_t) T * sizeof(float);
+    static const bool bulk = !(getenv("WHISPER_B200_CROSS_BULK") && atoi(getenv("WHISPER_B200_CROSS_BULK")) == 0);
+    if (bulk && !q_split) {
+        const size_t bsmem = (size_t) CB_STAGES * CB_CHUNK + round_up<size_t>((size_t) T * sizeof(float), 128);
+        static bool set = false;
+        if (!set) {
+            WB_CUDA(cudaFuncSetAttribute(cross_attn_bulk_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            WB_CUDA(cudaFuncSetAttribute(cross_attn_bulk_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            set = true;
+        }
+        if (bsmem <= 100 * 1024) {
+            if (dt == DType::F16)
+                launch_pdl(cross_attn_bulk_kernel<__half>, grid, dim3(CB_THREADS), bsmem, st, reinterpret_cast<const __half *>(q), d, d_rows,
+                           d, layer_off_elems, T, kq_scale, n_phantom, reinterpret_cast<__half *>(out));
+            else
+                launch_pdl(cross_attn_bulk_kernel<__nv_bfloat16>, grid, dim3(CB_THREADS), bsmem, st,
+                           reinterpret_cast<const __nv_bfloat16 *>(q), d, d_rows, d, layer_off_elems, T, kq_scale, n_phantom,
+                           reinterpret_cast<__nv_bfloat16 *>(out));
+            WB_CUDA(cudaGetLastError());
+            return;
+        }
+    }
     if (dt == DType::F16)
         if (q_split)
             launch_pdl(cross_attn_kernel<__half, false, true>, grid, dim3(128), smem, st, reinterpret_cast<const __half *>(q), d,

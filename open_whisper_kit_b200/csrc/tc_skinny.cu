@@ -266,6 +266,7 @@ tc_skinny_kernel(const __grid_constant__ TMap tm_x, const __grid_constant__ TMap
             }
             if (KSC > 1 && base + U * T_THREADS >= v_hi)        // last batch is in flight: release the peers' tiles
                 asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+            if (KSC > 1 && base + U * T_THREADS >= v_hi) TS_STAMP(7);       // partial tiles of the last batch are in registers
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 if (!live[u]) continue;
@@ -363,7 +364,7 @@ struct TcsTrace {
         if (cudaMemcpy(h.data(), dev, h.size() * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return;
         unsigned long long prev_end = 0;
         fprintf(stderr, "tcs_trace: per launch, ns relative to the first CTA start: [min median max] of each stamp over the CTAs\n");
-        fprintf(stderr, "tcs_trace: stamps = start, dep_done, acc_done, tile_smem, cluster_in, out_written, end\n");
+        fprintf(stderr, "tcs_trace: stamps = s0 start, s1 dep_done, s2 acc_done, s3 tile_smem, s4 cluster_in, s7 partials_loaded, s5 out_written, s6 end\n");
         for (size_t l = 0; l < recs.size(); ++l) {
             const TraceRec & r = recs[l];
             const int n = r.n_tiles * r.KS;
@@ -372,8 +373,8 @@ struct TcsTrace {
             for (int c = 0; c < n; ++c) { if (t[c * 8] && t[c * 8] < t0) t0 = t[c * 8]; if (t[c * 8 + 6] > t_end) t_end = t[c * 8 + 6]; }
             fprintf(stderr, "tcs_trace %3zu M=%d N=%d K=%d grid=%dx%d gap_from_prev_end=%lld |", l, r.M, r.N, r.K, r.n_tiles, r.KS,
                     prev_end ? (long long) (t0 - prev_end) : 0ll);
-            for (int s = 0; s < 7; ++s) {
-                if (r.KS == 1 && s == 4) continue;
+            for (int s = 0; s < 8; ++s) {
+                if (r.KS == 1 && (s == 4 || s == 7)) continue;
                 std::vector<long long> v;
                 for (int c = 0; c < n; ++c) if (t[c * 8 + s]) v.push_back((long long) (t[c * 8 + s] - t0));
                 if (v.empty()) continue;
