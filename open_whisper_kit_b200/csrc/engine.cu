@@ -391,7 +391,24 @@ bool Engine::decode(const std::vector<DecRow> & rows, const std::vector<int> & l
         // few rows: stream the weights with every SM (skinny_gemm.cu); many rows (long prompts): tensor-core tiles
         // few rows: stream the weights with every SM -- tcgen05 version (tc_skinny.cu) unless WHISPER_B200_TC_SKINNY=0
         static const bool tcs = !(getenv("WHISPER_B200_TC_SKINNY") && atoi(getenv("WHISPER_B200_TC_SKINNY")) == 0);
-        ok = ok && (g.M <= 128 ? (tcs && tc_skinny_usable(g) ? tc_skinny_gemm(g, stream) : skinny_gemm(g, skinny_ws, stream)) : tc_gemm(g, stream));
+        if (g.M <= 128) {
+            ok = ok && (tcs && tc_skinny_usable(g) ? tc_skinny_gemm(g, stream) : skinny_gemm(g, skinny_ws, stream));
+        } else if (g.M <= 512 && tcs && !g.pos) {
+            // short prompts (a handful of tokens per window): 128 x 256 tensor-core tiles would leave most SMs without a tile
+            // (N = 1280 -> 10-20 tiles), so stream the weights once per block of 128 rows instead
+            for (int r0 = 0; r0 < g.M && ok; r0 += 128) {
+                GemmArgs c = g;
+                c.M = std::min(128, g.M - r0);
+                c.a = (const char *) g.a + (size_t) r0 * g.lda * 2;
+                if (g.resid) c.resid = g.resid + (size_t) r0 * g.ldr;
+                if (g.out16) c.out16 = (char *) g.out16 + (size_t) r0 * g.ldo16 * 2;
+                if (g.out32) c.out32 = g.out32 + (size_t) r0 * g.ldo32;
+                ok = ok && (tc_skinny_usable(c) ? tc_skinny_gemm(c, stream) : tc_gemm(c, stream));
+                if (r0) n_kernel_launches += 1;
+            }
+        } else {
+            ok = ok && tc_gemm(g, stream);
+        }
         prof_end();
         n_kernel_launches += 1;
     };

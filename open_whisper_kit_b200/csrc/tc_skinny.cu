@@ -407,14 +407,15 @@ bool tc_skinny_gemm(const GemmArgs & g, cudaStream_t stream) {
     const int n_tiles = ceil_div(g.N, TB), kblocks = g.K / TB;
     // K splits = cluster size (<= 8 portable).  Enough CTAs to give every SM work, and enough that a CTA's whole K range is
     // in flight at once (T_STAGES k-blocks) while the grid still fits one wave of two CTAs per SM; >= 2 k-blocks per CTA.
+    const int rows_pad = g.M <= 64 ? 64 : 128;
+    const int cta_per_sm = rows_pad == 64 ? 2 : 1;          // by shared memory: 81 KB / 121 KB per CTA
     int KS = std::max(ceil_div(n_sm, n_tiles), ceil_div(kblocks, T_STAGES));
     KS = std::min(KS, 8);
-    while (KS > 1 && (n_tiles * KS > 2 * n_sm || KS > kblocks / 2)) --KS;
+    while (KS > 1 && (n_tiles * KS > cta_per_sm * n_sm || KS > kblocks / 2)) --KS;
 
     static std::mutex mu;
     static std::unordered_map<WKey, TMap, WKeyHash> wmaps;
     TMap tm_x, tm_w;
-    const int rows_pad = g.M <= 64 ? 64 : 128;
     if (!tc_make_tmap(&tm_x, g.a, g.M, g.K, g.lda, rows_pad, g.dtype)) return false;
     {
         std::lock_guard<std::mutex> lock(mu);

@@ -368,6 +368,24 @@ def test_quantised_model_vs_live_reference(lib, model_dir, qtype):
         assert int(a[:50256].argmax()) == int(b[:50256].argmax())
 
 
+@pytest.mark.parametrize("n_tok", [130, 200, 384])
+def test_short_prompt_row_blocks_vs_live_reference(lib, model_dir, n_tok):
+    """129..512 decoder rows in one call (short prompts of many windows; here one window with a long forced prompt) run the
+    weight-streaming GEMM once per block of 128 rows instead of 128 x 256 tensor-core tiles: last-row logits against the
+    live reference."""
+    ref, _ = reflib.load()
+    if ref is None:
+        pytest.skip("oracle/_ref was not built / did not travel")
+    path = model_path(model_dir, "tiny.en")
+    pcm = pcm_for({"kind": "jfk"})
+    toks = [50257] + [int(t) for t in np.random.default_rng(n_tok).integers(0, 50000, n_tok - 1)]
+    n_thr = min(os.cpu_count() or 4, 32)
+    a = _enc_and_logits(lib, path, pcm, toks)
+    b = _enc_and_logits(ref, path, pcm, toks, use_gpu=False)
+    print(f"{n_tok} prompt rows: last-row logits max|d| = {np.abs(a - b).max():.3e}")
+    assert np.abs(a - b).max() <= 2e-2
+
+
 def test_bf16_operands_track_f16(lib, model_dir, monkeypatch):
     """WHISPER_B200_DTYPE=bf16 (the operand type BASELINE.json names) runs every kernel of the path -- tcgen05 GEMMs and
     attention, decoder step -- and stays close to the f16 run (bf16 has 3 fewer mantissa bits: ~8x the rounding error)."""
