@@ -259,6 +259,7 @@ cross_attn_kernel(const T16 * __restrict__ q, int ldq, const DecRow * __restrict
 // resolves (cross K/V and the row descriptors were written before this decoder call began).
 constexpr int CB_STAGES = 4, CB_KEYS = 128, CB_CHUNK = CB_KEYS * 128;
 constexpr int CB_WARPS = 8;                       // compute warps; + 1 producer warp
+constexpr int CBQ_MAX = DEC_CROSS_GROUP_MAX;      // decoder rows of one window served by one CTA
 constexpr int CB_THREADS = (CB_WARPS + 1) * 32;
 
 __device__ __forceinline__ bool cb_try_wait(uint64_t * bar, uint32_t parity) {
@@ -274,16 +275,21 @@ __device__ __forceinline__ void cb_wait(uint64_t * bar, uint32_t parity) {      
         if (spins > (1u << 26)) __trap();
 }
 
-template <typename T16>
+// NQ > 1: one CTA serves up to NQ consecutive decoder rows that attend to the SAME window (the tokens of a prompt, the beams of
+// a beam search): the K / V stream is read once for all of them.  Per row the arithmetic is exactly the NQ = 1 arithmetic.
+template <typename T16, int NQ>
 __global__ void __launch_bounds__(CB_THREADS, 2)
-cross_attn_bulk_kernel(const T16 * __restrict__ q, int ldq, const DecRow * __restrict__ rows, int d, size_t layer_off, int T,
-                       float kq_scale, int n_phantom, T16 * __restrict__ out) {
-    extern __shared__ __align__(128) uint8_t cb_smem[];         // ring [CB_STAGES][CB_CHUNK] | scores [T] f32
+cross_attn_bulk_kernel(const T16 * __restrict__ q, int ldq, const DecRow * __restrict__ rows, const int2 * __restrict__ groups, int d,
+                       size_t layer_off, int T, float kq_scale, int n_phantom, T16 * __restrict__ out) {
+    extern __shared__ __align__(128) uint8_t cb_smem[];         // ring [CB_STAGES][CB_CHUNK] | scores [NQ][T_pad] f32
     __shared__ __align__(8) uint64_t b_full[CB_STAGES], b_empty[CB_STAGES];
-    __shared__ float s_red[2 * CB_WARPS];
+    __shared__ float s_red[NQ][2 * CB_WARPS];
     __shared__ float s_o[CB_WARPS][64];
+    const int T_pad = (T + 31) & ~31;
     float * s_sc = reinterpret_cast<float *>(cb_smem + CB_STAGES * CB_CHUNK);
-    const int r = blockIdx.x, h = blockIdx.y;
+    const int h = blockIdx.y;
+    const int r0 = NQ > 1 ? groups[blockIdx.x].x : (int) blockIdx.x;
+    const int nq = NQ > 1 ? groups[blockIdx.x].y : 1;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int sub = lane & 7, grp = lane >> 3;      // 8 lanes per key row, 4 key rows per warp instruction
     const int nck = (T + CB_KEYS - 1) / CB_KEYS;    // chunks per sweep; chunk c: sweep c / nck (0 K, 1 V), keys (c % nck) * 128 ..
@@ -299,7 +305,7 @@ cross_attn_bulk_kernel(const T16 * __restrict__ q, int ldq, const DecRow * __res
     if (warp == CB_WARPS) {
         // ===== producer =====
         if (lane == 0) {
-            const DecRow row = rows[r];
+            const DecRow row = rows[r0];
             const uint8_t * blk = reinterpret_cast<const uint8_t *>(reinterpret_cast<const T16 *>(row.cross_kv) + layer_off +
                                                                     (size_t) h * 2 * T * 64);
             for (int c = 0; c < 2 * nck; ++c) {
@@ -320,15 +326,18 @@ cross_attn_bulk_kernel(const T16 * __restrict__ q, int ldq, const DecRow * __res
 
     // ===== compute warps =====
     pdl_wait();
-    float qv[8];
-    {
-        const uint4 u = *reinterpret_cast<const uint4 *>(q + (size_t) r * ldq + h * 64 + sub * 8);
+    float qv[NQ][8];
+#pragma unroll
+    for (int qi = 0; qi < NQ; ++qi) {
+        const uint4 u = qi < nq ? *reinterpret_cast<const uint4 *>(q + (size_t) (r0 + qi) * ldq + h * 64 + sub * 8) : make_uint4(0, 0, 0, 0);
         const T16 * e = reinterpret_cast<const T16 *>(&u);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) qv[j] = Half16<T16>::to_f(e[j]);
+        for (int j = 0; j < 8; ++j) qv[qi][j] = Half16<T16>::to_f(e[j]);
     }
     auto sync_compute = [] { asm volatile("bar.sync 1, %0;" ::"n"(CB_WARPS * 32) : "memory"); };
-    float mx = -INFINITY;
+    float mx[NQ];
+#pragma unroll
+    for (int qi = 0; qi < NQ; ++qi) mx[qi] = -INFINITY;
     for (int c = 0; c < nck; ++c) {
         const int s = c % CB_STAGES;
         cb_wait(&b_full[s], (c / CB_STAGES) & 1);
@@ -339,47 +348,68 @@ cross_attn_bulk_kernel(const T16 * __restrict__ q, int ldq, const DecRow * __res
             uint4 kb = make_uint4(0, 0, 0, 0);
             if (t < T) kb = *reinterpret_cast<const uint4 *>(stage + kl * 128 + sub * 16);
             const T16 * e = reinterpret_cast<const T16 *>(&kb);
-            float acc = 0.0f;
+            float kf[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc = fmaf(qv[j], Half16<T16>::to_f(e[j]), acc);
-            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-            acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-            acc *= kq_scale;
-            if (t < T) {
-                if (sub == 0) s_sc[t] = acc;
-                mx = fmaxf(mx, acc);
+            for (int j = 0; j < 8; ++j) kf[j] = Half16<T16>::to_f(e[j]);
+#pragma unroll
+            for (int qi = 0; qi < NQ; ++qi) {
+                if (NQ > 1 && qi >= nq) break;
+                float acc = 0.0f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc = fmaf(qv[qi][j], kf[j], acc);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+                acc *= kq_scale;
+                if (t < T) {
+                    if (sub == 0) s_sc[qi * T_pad + t] = acc;
+                    mx[qi] = fmaxf(mx[qi], acc);
+                }
             }
         }
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t) __cvta_generic_to_shared(&b_empty[s])) : "memory");
     }
     pdl_trigger();
-    mx = warp_max(mx);
-    if (lane == 0) s_red[warp] = mx;
-    sync_compute();
-    mx = s_red[0];
 #pragma unroll
-    for (int i = 1; i < CB_WARPS; ++i) mx = fmaxf(mx, s_red[i]);
-    if (n_phantom > 0) mx = fmaxf(mx, 0.0f);
-    float sum = 0.0f;
-    for (int t = tid; t < T; t += CB_WARPS * 32) {
-        const float e = expf(s_sc[t] - mx);
-        s_sc[t] = e;
-        sum += e;
+    for (int qi = 0; qi < NQ; ++qi) {
+        const float m = warp_max(mx[qi]);
+        if (lane == 0) s_red[qi][warp] = m;
     }
-    sum = warp_sum(sum);
-    if (lane == 0) s_red[CB_WARPS + warp] = sum;
     sync_compute();
-    sum = s_red[CB_WARPS];
+    float inv[NQ];
 #pragma unroll
-    for (int i = 1; i < CB_WARPS; ++i) sum += s_red[CB_WARPS + i];
-    if (n_phantom > 0) sum += (float) n_phantom * expf(-mx);
-    const float inv = 1.0f / sum;
+    for (int qi = 0; qi < NQ; ++qi) {
+        float m = s_red[qi][0];
+#pragma unroll
+        for (int i = 1; i < CB_WARPS; ++i) m = fmaxf(m, s_red[qi][i]);
+        if (n_phantom > 0) m = fmaxf(m, 0.0f);
+        mx[qi] = m;
+        float sum = 0.0f;
+        if (qi < nq)
+            for (int t = tid; t < T; t += CB_WARPS * 32) {
+                const float e = expf(s_sc[qi * T_pad + t] - m);
+                s_sc[qi * T_pad + t] = e;
+                sum += e;
+            }
+        sum = warp_sum(sum);
+        if (lane == 0) s_red[qi][CB_WARPS + warp] = sum;
+    }
+    sync_compute();
+#pragma unroll
+    for (int qi = 0; qi < NQ; ++qi) {
+        float sum = s_red[qi][CB_WARPS];
+#pragma unroll
+        for (int i = 1; i < CB_WARPS; ++i) sum += s_red[qi][CB_WARPS + i];
+        if (n_phantom > 0) sum += (float) n_phantom * expf(-mx[qi]);
+        inv[qi] = 1.0f / sum;
+    }
 
-    float o[8];
+    float o[NQ][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = 0.0f;
+    for (int qi = 0; qi < NQ; ++qi)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[qi][j] = 0.0f;
     for (int c = nck; c < 2 * nck; ++c) {
         const int s = c % CB_STAGES, c0 = (c - nck) * CB_KEYS;
         cb_wait(&b_full[s], (c / CB_STAGES) & 1);
@@ -390,29 +420,41 @@ cross_attn_bulk_kernel(const T16 * __restrict__ q, int ldq, const DecRow * __res
             const bool ok = t < T;
             uint4 vb = make_uint4(0, 0, 0, 0);
             if (ok) vb = *reinterpret_cast<const uint4 *>(stage + kl * 128 + sub * 16);
-            const float pr = ok ? Half16<T16>::to_f(Half16<T16>::from_f(s_sc[t] * inv)) : 0.0f;
             const T16 * e = reinterpret_cast<const T16 *>(&vb);
+            float vf[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = fmaf(pr, Half16<T16>::to_f(e[j]), o[j]);
+            for (int j = 0; j < 8; ++j) vf[j] = Half16<T16>::to_f(e[j]);
+#pragma unroll
+            for (int qi = 0; qi < NQ; ++qi) {
+                if (NQ > 1 && qi >= nq) break;
+                const float pr = ok ? Half16<T16>::to_f(Half16<T16>::from_f(s_sc[qi * T_pad + t] * inv[qi])) : 0.0f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[qi][j] = fmaf(pr, vf[j], o[qi][j]);
+            }
         }
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t) __cvta_generic_to_shared(&b_empty[s])) : "memory");
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        o[j] += __shfl_xor_sync(0xffffffffu, o[j], 8);
-        o[j] += __shfl_xor_sync(0xffffffffu, o[j], 16);
-    }
-    if (grp == 0) {
+    for (int qi = 0; qi < NQ; ++qi) {
+        if (NQ > 1 && qi >= nq) break;          // CTA-uniform
 #pragma unroll
-        for (int j = 0; j < 8; ++j) s_o[warp][sub * 8 + j] = o[j];
-    }
-    sync_compute();
-    if (tid < 64) {
-        float v = s_o[0][tid];
+        for (int j = 0; j < 8; ++j) {
+            o[qi][j] += __shfl_xor_sync(0xffffffffu, o[qi][j], 8);
+            o[qi][j] += __shfl_xor_sync(0xffffffffu, o[qi][j], 16);
+        }
+        if (qi > 0) sync_compute();            // s_o is reused per row
+        if (grp == 0) {
 #pragma unroll
-        for (int i = 1; i < CB_WARPS; ++i) v += s_o[i][tid];
-        out[(size_t) r * d + h * 64 + tid] = Half16<T16>::from_f(v);
+            for (int j = 0; j < 8; ++j) s_o[warp][sub * 8 + j] = o[qi][j];
+        }
+        sync_compute();
+        if (tid < 64) {
+            float v = s_o[0][tid];
+#pragma unroll
+            for (int i = 1; i < CB_WARPS; ++i) v += s_o[i][tid];
+            out[(size_t) (r0 + qi) * d + h * 64 + tid] = Half16<T16>::from_f(v);
+        }
     }
 }
 
@@ -778,7 +820,7 @@ void dec_self_attn(DType dt, const void * qkv, const DecRow * d_rows, int R, int
 }
 
 void dec_cross_attn(DType dt, const void * q, const DecRow * d_rows, int R, int d, int n_head, size_t layer_off_elems,
-                    int T, int n_phantom, void * out, cudaStream_t st, const SplitIn * q_split) {
+                    int T, int n_phantom, void * out, cudaStream_t st, const SplitIn * q_split, const int2 * d_groups, int n_groups) {
     const SplitIn qs = q_split ? *q_split : SplitIn{};
     if (R <= 0) return;
     dim3 grid(R, n_head);
@@ -786,21 +828,35 @@ void dec_cross_attn(DType dt, const void * q, const DecRow * d_rows, int R, int 
     const size_t smem = (size_t) T * sizeof(float);
     static const bool bulk = !(getenv("WHISPER_B200_CROSS_BULK") && atoi(getenv("WHISPER_B200_CROSS_BULK")) == 0);
     if (bulk && !q_split) {
-        const size_t bsmem = (size_t) CB_STAGES * CB_CHUNK + round_up<size_t>((size_t) T * sizeof(float), 128);
+        const int nq = (d_groups && n_groups > 0) ? CBQ_MAX : 1;
+        const size_t bsmem = (size_t) CB_STAGES * CB_CHUNK + (size_t) nq * ((T + 31) & ~31) * sizeof(float);
         static bool set = false;
         if (!set) {
-            WB_CUDA(cudaFuncSetAttribute(cross_attn_bulk_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            WB_CUDA(cudaFuncSetAttribute(cross_attn_bulk_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            WB_CUDA(cudaFuncSetAttribute(cross_attn_bulk_kernel<__half, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            WB_CUDA(cudaFuncSetAttribute(cross_attn_bulk_kernel<__nv_bfloat16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            WB_CUDA(cudaFuncSetAttribute(cross_attn_bulk_kernel<__half, CBQ_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            WB_CUDA(cudaFuncSetAttribute(cross_attn_bulk_kernel<__nv_bfloat16, CBQ_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
             set = true;
         }
         if (bsmem <= 100 * 1024) {
-            if (dt == DType::F16)
-                launch_pdl(cross_attn_bulk_kernel<__half>, grid, dim3(CB_THREADS), bsmem, st, reinterpret_cast<const __half *>(q), d, d_rows,
-                           d, layer_off_elems, T, kq_scale, n_phantom, reinterpret_cast<__half *>(out));
-            else
-                launch_pdl(cross_attn_bulk_kernel<__nv_bfloat16>, grid, dim3(CB_THREADS), bsmem, st,
-                           reinterpret_cast<const __nv_bfloat16 *>(q), d, d_rows, d, layer_off_elems, T, kq_scale, n_phantom,
-                           reinterpret_cast<__nv_bfloat16 *>(out));
+            const dim3 g(nq > 1 ? n_groups : R, n_head);
+            const __half * qh = reinterpret_cast<const __half *>(q);
+            const __nv_bfloat16 * qb = reinterpret_cast<const __nv_bfloat16 *>(q);
+            if (dt == DType::F16) {
+                if (nq > 1)
+                    launch_pdl(cross_attn_bulk_kernel<__half, CBQ_MAX>, g, dim3(CB_THREADS), bsmem, st, qh, d, d_rows, d_groups, d, layer_off_elems,
+                               T, kq_scale, n_phantom, reinterpret_cast<__half *>(out));
+                else
+                    launch_pdl(cross_attn_bulk_kernel<__half, 1>, g, dim3(CB_THREADS), bsmem, st, qh, d, d_rows, d_groups, d, layer_off_elems, T,
+                               kq_scale, n_phantom, reinterpret_cast<__half *>(out));
+            } else {
+                if (nq > 1)
+                    launch_pdl(cross_attn_bulk_kernel<__nv_bfloat16, CBQ_MAX>, g, dim3(CB_THREADS), bsmem, st, qb, d, d_rows, d_groups, d,
+                               layer_off_elems, T, kq_scale, n_phantom, reinterpret_cast<__nv_bfloat16 *>(out));
+                else
+                    launch_pdl(cross_attn_bulk_kernel<__nv_bfloat16, 1>, g, dim3(CB_THREADS), bsmem, st, qb, d, d_rows, d_groups, d, layer_off_elems,
+                               T, kq_scale, n_phantom, reinterpret_cast<__nv_bfloat16 *>(out));
+            }
             WB_CUDA(cudaGetLastError());
             return;
         }

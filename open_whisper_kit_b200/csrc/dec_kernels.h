@@ -47,8 +47,12 @@ void dec_kv_append(const void * qkv, const DecRow * d_rows, int R, int d, size_t
 void dec_self_attn(DType dt, const void * qkv, const DecRow * d_rows, int R, int d, int n_head, size_t layer_off_elems,
                    int n_ctx, bool fused_append, void * out, cudaStream_t st);
 struct SplitIn;   // dec_chain.h: the query as partial tiles of the chain kernel's cross-q GEMM (q is ignored then)
+// d_groups (optional): n_groups runs {first row, count <= DEC_CROSS_GROUP_MAX} of consecutive rows that share one window's cross
+// K/V (prompt tokens, beams): one CTA per (run, head) then streams the K/V once for all rows of the run.
+constexpr int DEC_CROSS_GROUP_MAX = 4;
 void dec_cross_attn(DType dt, const void * q, const DecRow * d_rows, int R, int d, int n_head, size_t layer_off_elems,
-                    int T, int n_phantom, void * out, cudaStream_t st, const SplitIn * q_split = nullptr);
+                    int T, int n_phantom, void * out, cudaStream_t st, const SplitIn * q_split = nullptr,
+                    const int2 * d_groups = nullptr, int n_groups = 0);
 void dec_sample_greedy(float * logits, int ld, const SampleRow * d_srows, int R, const uint32_t * d_static_mask,
                        const SampleParams & prm, SampleOut * d_out, cudaStream_t st);
 void dec_token_prob(const float * logits, int ld, const SampleRow * d_srows, int R, int n_vocab, int token, float * d_out,

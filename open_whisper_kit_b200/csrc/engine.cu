@@ -365,6 +365,7 @@ bool Engine::decode(const std::vector<DecRow> & rows, const std::vector<int> & l
     auto sz = [&](size_t b) { need += round_up<size_t>(b, 256); };
     sz((size_t) R * d * 4); sz((size_t) R * d * 2); sz((size_t) R * 3 * d * 2); sz((size_t) R * d * 2); sz((size_t) R * d * 2);
     sz((size_t) R * 4 * d * 2); sz((size_t) std::max(1, RL) * d * 2); sz(R * sizeof(DecRow)); sz(std::max(1, RL) * sizeof(int));
+    sz(R * sizeof(int2));
     if (!ws.begin(need)) return false;
     float * x = (float *) ws.take((size_t) R * d * 4);
     void * h16 = ws.take((size_t) R * d * 2);
@@ -375,14 +376,29 @@ bool Engine::decode(const std::vector<DecRow> & rows, const std::vector<int> & l
     void * hl16 = ws.take((size_t) std::max(1, RL) * d * 2);
     DecRow * d_rows = (DecRow *) ws.take(R * sizeof(DecRow));
     int * d_lrows = (int *) ws.take(std::max(1, RL) * sizeof(int));
+    int2 * d_groups = (int2 *) ws.take(R * sizeof(int2));
     if (!logits.reserve((size_t) std::max(1, RL) * ld_logits * 4)) return false;
 
+    // runs of consecutive rows that attend to the same window (prompt tokens of a window, beams of a stream): the cross-
+    // attention streams a window's K/V once per run instead of once per row
+    std::vector<int2> groups;
+    for (int i = 0; i < R; ++i) {
+        if (!groups.empty() && rows[i].cross_kv == rows[groups.back().x].cross_kv && groups.back().y < DEC_CROSS_GROUP_MAX) groups.back().y++;
+        else groups.push_back(make_int2(i, 1));
+    }
+    const int n_groups = (int) groups.size() < R ? (int) groups.size() : 0;      // all runs of length 1: plain one-CTA-per-row launch
+
     // stage the row descriptors through pinned memory so the copy is asynchronous
-    char * hp_buf = (char *) pinned(0, R * sizeof(DecRow) + RL * sizeof(int));
+    char * hp_buf = (char *) pinned(0, R * sizeof(DecRow) + RL * sizeof(int) + R * sizeof(int2));
     memcpy(hp_buf, rows.data(), R * sizeof(DecRow));
     if (RL) memcpy(hp_buf + R * sizeof(DecRow), logit_rows.data(), RL * sizeof(int));
     WB_CUDA(cudaMemcpyAsync(d_rows, hp_buf, R * sizeof(DecRow), cudaMemcpyHostToDevice, stream));
     if (RL) WB_CUDA(cudaMemcpyAsync(d_lrows, hp_buf + R * sizeof(DecRow), RL * sizeof(int), cudaMemcpyHostToDevice, stream));
+    if (n_groups) {
+        char * hg = hp_buf + R * sizeof(DecRow) + RL * sizeof(int);
+        memcpy(hg, groups.data(), n_groups * sizeof(int2));
+        WB_CUDA(cudaMemcpyAsync(d_groups, hg, n_groups * sizeof(int2), cudaMemcpyHostToDevice, stream));
+    }
 
     bool ok = true;
     int gemm_cls = PC_GEMM_DEC;
@@ -466,7 +482,7 @@ bool Engine::decode(const std::vector<DecRow> & rows, const std::vector<int> & l
             gemm(g);
         }
         prof_begin(PC_CROSS_ATTN, (double) R * 1500.0 * 2 * d * 2.0);
-        dec_cross_attn(dt, q16, d_rows, R, d, H, il * cross_layer_stride, 1500, n_phantom(), att, stream);
+        dec_cross_attn(dt, q16, d_rows, R, d, H, il * cross_layer_stride, 1500, n_phantom(), att, stream, nullptr, d_groups, n_groups);
         prof_end();
         n_kernel_launches += 1;
         {

@@ -34,5 +34,7 @@ for name, strategy in (("greedy+timestamps", 0), ("beam5+timestamps", 1)):
         dt = time.time() - t
         n_seg = lib.whisper_full_n_segments(ctx)
         n_tok = sum(lib.whisper_full_n_tokens(ctx, i) for i in range(n_seg))
-        print(f"{name} rep {rep}: rc {rc} {dt*1e3:.1f} ms -> {30.0*n_win/dt:.1f}x real time; {n_seg} segments, {n_tok} tokens", flush=True)
+        ids = [lib.whisper_full_get_token_id(ctx, i, j) for i in range(n_seg) for j in range(lib.whisper_full_n_tokens(ctx, i))]
+        chk = hash(tuple(ids)) & 0xffffffff
+        print(f"{name} rep {rep}: rc {rc} {dt*1e3:.1f} ms -> {30.0*n_win/dt:.1f}x real time; {n_seg} segments, {n_tok} tokens, checksum {chk:08x}", flush=True)
 lib.whisper_free(ctx)
