@@ -404,8 +404,8 @@ bool Engine::decode(const std::vector<DecRow> & rows, const std::vector<int> & l
     int gemm_cls = PC_GEMM_DEC;
     auto gemm = [&](const GemmArgs & g) {
         prof_begin(gemm_cls, ((double) g.N * g.K + (double) g.M * (g.N + g.K)) * 2.0);   // bytes: weights + activations
-        // few rows: stream the weights with every SM (skinny_gemm.cu); many rows (long prompts): tensor-core tiles
-        // few rows: stream the weights with every SM -- tcgen05 version (tc_skinny.cu) unless WHISPER_B200_TC_SKINNY=0
+        // few rows: stream the weights with every SM -- tcgen05 version (tc_skinny.cu) unless WHISPER_B200_TC_SKINNY=0, else
+        // the mma.sync one (skinny_gemm.cu); many rows (long prompts): tensor-core tiles (tc_gemm.cu)
         static const bool tcs = !(getenv("WHISPER_B200_TC_SKINNY") && atoi(getenv("WHISPER_B200_TC_SKINNY")) == 0);
         if (g.M <= 128) {
             ok = ok && (tcs && tc_skinny_usable(g) ? tc_skinny_gemm(g, stream) : skinny_gemm(g, skinny_ws, stream));
