@@ -33,7 +33,8 @@ template <> struct Pack2<__nv_bfloat16> {
 // on the fly:  (max(x, mmax-8) + 4) / 4   (src/whisper.cpp:3228-3244).  Window slicing as whisper_encode_internal
 // (src/whisper.cpp:2381-2403).
 template <typename T16>
-__global__ void im2col1_kernel(const EncWindow * __restrict__ wins, int n_mel, int k_pad, T16 * __restrict__ out) {
+__global__ void im2col1_kernel(const EncWindow * __restrict__ wins, int n_mel, int k_pad, int n_frames /* 2 * audio context */,
+                               T16 * __restrict__ out) {
     __shared__ float tile[32][33];
     const EncWindow w = wins[blockIdx.z];
     const int t0 = blockIdx.x * 32;     // output time block
@@ -47,7 +48,7 @@ __global__ void im2col1_kernel(const EncWindow * __restrict__ wins, int n_mel, i
             const int tl = t0 + tx + k - 1;                  // frame inside the window
             const long long f = (long long) w.seek + tl;     // frame inside the stream's mel
             float v = 0.0f;
-            if (c < n_mel && tl >= 0 && tl < 3000 && f < w.n_len) {
+            if (c < n_mel && tl >= 0 && tl < n_frames && f < w.n_len) {
                 if (w.finalized) {
                     v = w.mel[(size_t) c * w.stride + f];
                 } else {
@@ -61,8 +62,8 @@ __global__ void im2col1_kernel(const EncWindow * __restrict__ wins, int n_mel, i
         for (int r = ty; r < 32; r += 8) {
             const int t = t0 + r;
             const int c = c0 + tx;
-            if (t < 3000 && c < n_mel) {
-                out[((size_t) blockIdx.z * 3000 + t) * k_pad + k * n_mel + c] = Half16<T16>::from_f(tile[tx][r]);
+            if (t < n_frames && c < n_mel) {
+                out[((size_t) blockIdx.z * n_frames + t) * k_pad + k * n_mel + c] = Half16<T16>::from_f(tile[tx][r]);
             }
         }
         __syncthreads();
@@ -72,16 +73,16 @@ __global__ void im2col1_kernel(const EncWindow * __restrict__ wins, int n_mel, i
         const int pad0 = 3 * n_mel;
         for (int r = ty; r < 32; r += 8) {
             const int t = t0 + r;
-            if (t >= 3000) continue;
+            if (t >= n_frames) continue;
             for (int c = pad0 + tx; c < k_pad; c += 32)
-                out[((size_t) blockIdx.z * 3000 + t) * k_pad + c] = Half16<T16>::from_f(0.0f);
+                out[((size_t) blockIdx.z * n_frames + t) * k_pad + c] = Half16<T16>::from_f(0.0f);
         }
     }
 }
 
 // ---- im2col for conv2 (k=3, s=2, p=1) on time-major activations ----------------------------------------------
 // A2[(w, t)][k*d + c] = act1[(w, 2t + k - 1)][c], zero for 2t+k-1 outside [0, 3000).  16-byte vector copies.
-__global__ void im2col2_kernel(const uint4 * __restrict__ act1, int d8 /* d/8 */, uint4 * __restrict__ out,
+__global__ void im2col2_kernel(const uint4 * __restrict__ act1, int d8 /* d/8 */, int T /* audio context */, uint4 * __restrict__ out,
                                long long n_vec /* total uint4 of out */) {
     const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_vec) return;
@@ -89,11 +90,11 @@ __global__ void im2col2_kernel(const uint4 * __restrict__ act1, int d8 /* d/8 */
     const long long m = i / row_vec;             // (w, t)
     const int r = (int) (i % row_vec);
     const int k = r / d8, c8 = r % d8;
-    const long long w = m / 1500;
-    const int t = (int) (m % 1500);
+    const long long w = m / T;
+    const int t = (int) (m % T);
     const int ts = 2 * t + k - 1;
     uint4 v = make_uint4(0, 0, 0, 0);
-    if (ts >= 0 && ts < 3000) v = act1[(w * 3000 + ts) * d8 + c8];
+    if (ts >= 0 && ts < 2 * T) v = act1[(w * 2 * T + ts) * d8 + c8];
     out[i] = v;
 }
 
@@ -435,20 +436,20 @@ void layernorm_dispatch(const float * x, int ldx, const float * g, const float *
 
 }  // namespace
 
-void im2col1(DType dt, const EncWindow * d_wins, int n_windows, int n_mel, int k_pad, void * out, cudaStream_t st) {
-    dim3 grid(ceil_div(3000, 32), ceil_div(n_mel, 32), n_windows), block(32, 8);
+void im2col1(DType dt, const EncWindow * d_wins, int n_windows, int n_mel, int k_pad, int T, void * out, cudaStream_t st) {
+    dim3 grid(ceil_div(2 * T, 32), ceil_div(n_mel, 32), n_windows), block(32, 8);
     if (dt == DType::F16)
-        im2col1_kernel<__half><<<grid, block, 0, st>>>(d_wins, n_mel, k_pad, reinterpret_cast<__half *>(out));
+        im2col1_kernel<__half><<<grid, block, 0, st>>>(d_wins, n_mel, k_pad, 2 * T, reinterpret_cast<__half *>(out));
     else
-        im2col1_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(d_wins, n_mel, k_pad, reinterpret_cast<__nv_bfloat16 *>(out));
+        im2col1_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(d_wins, n_mel, k_pad, 2 * T, reinterpret_cast<__nv_bfloat16 *>(out));
     WB_CUDA(cudaGetLastError());
 }
 
-void im2col2(const void * act1, int n_windows, int d, void * out, cudaStream_t st) {
-    const long long n_vec = (long long) n_windows * 1500 * 3 * (d / 8);
+void im2col2(const void * act1, int n_windows, int d, int T, void * out, cudaStream_t st) {
+    const long long n_vec = (long long) n_windows * T * 3 * (d / 8);
     const int threads = 256;
     im2col2_kernel<<<(unsigned) ceil_div<long long>(n_vec, threads), threads, 0, st>>>(
-        reinterpret_cast<const uint4 *>(act1), d / 8, reinterpret_cast<uint4 *>(out), n_vec);
+        reinterpret_cast<const uint4 *>(act1), d / 8, T, reinterpret_cast<uint4 *>(out), n_vec);
     WB_CUDA(cudaGetLastError());
 }
 

@@ -16,9 +16,9 @@ struct EncWindow {
     int              finalized;
 };
 
-void im2col1(DType dt, const EncWindow * d_wins, int n_windows, int n_mel, int k_pad, void * out /*[W*3000][k_pad]*/,
-             cudaStream_t st);
-void im2col2(const void * act1 /*[W*3000][d]*/, int n_windows, int d, void * out /*[W*1500][3d]*/, cudaStream_t st);
+void im2col1(DType dt, const EncWindow * d_wins, int n_windows, int n_mel, int k_pad, int T /* audio context */,
+             void * out /*[W*2T][k_pad]*/, cudaStream_t st);
+void im2col2(const void * act1 /*[W*2T][d]*/, int n_windows, int d, int T, void * out /*[W*T][3d]*/, cudaStream_t st);
 
 // y = LayerNorm(x[row_map ? row_map[m] : m]) for m < M; 16-bit and/or f32 outputs.
 void layernorm(DType dt, const float * x, int ldx, const float * gamma, const float * beta, float eps, int M, int d,

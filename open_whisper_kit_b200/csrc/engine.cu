@@ -202,10 +202,11 @@ bool Engine::get_mel(const MelBuf & mel, float * out) {
 }
 
 // ---- encoder ----------------------------------------------------------------------------------------------
-bool Engine::size_cross(CrossKV & kv, int n_windows) {
+bool Engine::size_cross(CrossKV & kv, int n_windows, int T) {
     const int d = model.hp.n_audio_state;
     kv.n_windows = n_windows;
-    kv.layer_stride = (size_t) n_windows * 1500 * 2 * d;
+    kv.T = T;
+    kv.layer_stride = (size_t) n_windows * T * 2 * d;
     return kv.data.reserve(kv.layer_stride * model.hp.n_text_layer * 2);
 }
 
@@ -214,11 +215,11 @@ bool Engine::encode(const std::vector<EncJob> & jobs, CrossKV & kv, int win0, bo
     if (W == 0) return true;
     WB_CUDA(cudaSetDevice(device));
     const auto & hp = model.hp;
-    const int d = hp.n_audio_state, H = hp.n_audio_head, T = 1500;
+    const int d = hp.n_audio_state, H = hp.n_audio_head, T = kv.T;      // audio context: 1500 or params.audio_ctx
     const DType dt = model.dtype;
     const int n_mel = hp.n_mels;
     const int k1 = model.conv1_kpad;
-    const size_t M1 = (size_t) W * 3000, M = (size_t) W * T;
+    const size_t M1 = (size_t) W * 2 * T, M = (size_t) W * T;
 
     size_t need = 0;
     auto sz = [&](size_t b) { need += round_up<size_t>(b, 256); return b; };
@@ -269,7 +270,7 @@ bool Engine::encode(const std::vector<EncJob> & jobs, CrossKV & kv, int win0, bo
 
     // conv stem: two GEMMs over im2col'd time-major activations, GELU fused; positional add fused into the second
     prof_begin(PC_IM2COL, (double) M1 * k1 * 2.0);
-    im2col1(dt, d_wins, W, n_mel, k1, A1, stream);
+    im2col1(dt, d_wins, W, n_mel, k1, T, A1, stream);
     prof_end();
     {
         GemmArgs g;
@@ -278,7 +279,7 @@ bool Engine::encode(const std::vector<EncJob> & jobs, CrossKV & kv, int win0, bo
         gemm(g);
     }
     prof_begin(PC_IM2COL, (double) M * 3 * d * 4.0);
-    im2col2(act1, W, d, A2, stream);
+    im2col2(act1, W, d, T, A2, stream);
     prof_end();
     {
         GemmArgs g;
@@ -300,10 +301,10 @@ bool Engine::encode(const std::vector<EncJob> & jobs, CrossKV & kv, int win0, bo
         }
         prof_begin(PC_ENC_ATTN, 4.0 * (double) W * T * (double) T * d);
         if (legacy_attn) {
-            enc_attention(dt, qkv, att, W, T, d, H, n_phantom(), stream);
+            enc_attention(dt, qkv, att, W, T, d, H, n_phantom(T), stream);
             n_kernel_launches += 1;
         } else {
-            ok = ok && enc_attention_tc(dt, qkv, att, vt, W, T, d, H, n_phantom(), stream);
+            ok = ok && enc_attention_tc(dt, qkv, att, vt, W, T, d, H, n_phantom(T), stream);
             n_kernel_launches += 2;
         }
         prof_end();
@@ -481,8 +482,8 @@ bool Engine::decode(const std::vector<DecRow> & rows, const std::vector<int> & l
             g.bias = L.bxq; g.out16 = q16; g.ldo16 = d;
             gemm(g);
         }
-        prof_begin(PC_CROSS_ATTN, (double) R * 1500.0 * 2 * d * 2.0);
-        dec_cross_attn(dt, q16, d_rows, R, d, H, il * cross_layer_stride, 1500, n_phantom(), att, stream, nullptr, d_groups, n_groups);
+        prof_begin(PC_CROSS_ATTN, (double) R * cross_T * 2.0 * d * 2.0);
+        dec_cross_attn(dt, q16, d_rows, R, d, H, il * cross_layer_stride, cross_T, n_phantom(cross_T), att, stream, nullptr, d_groups, n_groups);
         prof_end();
         n_kernel_launches += 1;
         {
@@ -675,8 +676,8 @@ bool Engine::decode_chain(const std::vector<DecRow> & rows, const std::vector<in
         SplitIn qs;
         qs.part = part; qs.bias = model.dec[il].bxq; qs.g = g_dd;
         if (trace_on) qs.trace = (unsigned long long *) chain_trace.p + 32 * il + 27;
-        prof_begin(PC_CROSS_ATTN, (double) R * 1500.0 * 2 * d * 2.0);
-        dec_cross_attn(dt, nullptr, d_rows, R, d, H, il * cross_layer_stride, 1500, n_phantom(), att, stream, &qs);
+        prof_begin(PC_CROSS_ATTN, (double) R * cross_T * 2.0 * d * 2.0);
+        dec_cross_attn(dt, nullptr, d_rows, R, d, H, il * cross_layer_stride, cross_T, n_phantom(cross_T), att, stream, &qs);
         prof_end();
         n_kernel_launches += 1;
     };

@@ -44,12 +44,14 @@ struct MelBuf {
     bool valid = false;
 };
 
-// Cross-attention K/V of a set of windows: [n_text_layer][n_windows*1500][2d] (K | V), 16-bit.
+// Cross-attention K/V of a set of windows: [n_text_layer][n_windows][n_head][K | V][T][64], 16-bit.
+// T = audio context of the encoder run that filled it (1500, or whisper_full_params::audio_ctx).
 struct CrossKV {
     DeviceBlock data;
     int n_windows = 0;
+    int T = 1500;
     size_t layer_stride = 0;   // elements
-    const void * window_base(int w, int d) const { return (const char *) data.p + (size_t) w * 1500 * 2 * d * 2; }
+    const void * window_base(int w, int d) const { return (const char *) data.p + (size_t) w * T * 2 * d * 2; }
 };
 
 struct MelJob {
@@ -109,7 +111,10 @@ struct Engine {
     void prof_collect();     // synchronises, folds the pending records into prof_ms / prof_work / prof_n
     void prof_reset();
 
-    int n_phantom() const { return flash_attn ? 36 : 0; }
+    // zero keys the reference's flash-attention path attends to: its K/V scratch is padded to a multiple of 256 positions
+    // (src/whisper.cpp:2055, 2481)
+    int n_phantom(int T = 1500) const { return flash_attn ? (T + 255) / 256 * 256 - T : 0; }
+    int cross_T = 1500;        // audio context of the cross K/V the next decode() call reads (set by the caller)
 
     bool init(int device, bool flash_attn);
     ~Engine();
@@ -123,7 +128,7 @@ struct Engine {
 
     // Encodes jobs.size() windows; K/V rows for job i land at window index win0 + i of kv (kv must be sized already).
     bool encode(const std::vector<EncJob> & jobs, CrossKV & kv, int win0, bool keep_embd32);
-    bool size_cross(CrossKV & kv, int n_windows);
+    bool size_cross(CrossKV & kv, int n_windows, int T = 1500);
 
     // Runs the decoder over `rows`; logits are produced for rows[logit_rows[i]] into logits row i.
     // cross_layer_stride: element distance between text layers in the cross-K/V pool the rows point into.

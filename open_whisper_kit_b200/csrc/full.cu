@@ -318,7 +318,8 @@ static bool sequences_equal(const whisper_sequence & a, const whisper_sequence &
 // ---- single-window helpers used by the low-level API and by language detection --------------------------------
 bool encode_single(whisper_context & ctx, whisper_state & st, int seek, bool keep_embd32) {
     Engine & e = ctx.eng;
-    if (!e.size_cross(st.cross, 1)) return false;
+    // audio context: the state's experimental override (set by whisper_full from params.audio_ctx, src/whisper.cpp:6986)
+    if (!e.size_cross(st.cross, 1, st.exp_n_audio_ctx > 0 ? st.exp_n_audio_ctx : 1500)) return false;
     std::vector<EncJob> jobs(1);
     jobs[0].mel = &st.mel;
     jobs[0].seek = seek;
@@ -326,6 +327,7 @@ bool encode_single(whisper_context & ctx, whisper_state & st, int seek, bool kee
     const bool ok = e.encode(jobs, st.cross, 0, keep_embd32);
     st.cross_base = st.cross.data.p;
     st.cross_layer_stride = st.cross.layer_stride;
+    st.cross_T = st.cross.T;
     st.t_encode_us += time_us() - t0;
     st.n_encode++;
     return ok;
@@ -355,7 +357,9 @@ bool decode_single(whisper_context & ctx, whisper_state & st, const whisper_toke
     }
     const int64_t t0 = time_us();
     std::vector<int> lrows(1, n_tokens - 1);
+    e.cross_T = st.cross_T;
     bool ok = e.decode(rows, lrows, st.cross_layer_stride);
+    e.cross_T = 1500;
     st.logits.resize((size_t) n_tokens * hp.n_vocab);
     ok = ok && e.fetch_logits(0, st.logits.data() + (size_t) (n_tokens - 1) * hp.n_vocab);
     const int64_t dt = time_us() - t0;
@@ -550,12 +554,8 @@ static int stream_begin(whisper_context & ctx, Stream & s) {
              hp.n_audio_ctx);
         return -5;
     }
-    if (params.audio_ctx != 0) {
-        wlog(GGML_LOG_LEVEL_ERROR, "%s: audio_ctx = %d is not implemented on the B200 path (only the full 1500-position context)\n",
-             __func__, params.audio_ctx);
-        return -5;
-    }
-    state->exp_n_audio_ctx = 0;
+    if (params.audio_ctx < 0) return -5;
+    state->exp_n_audio_ctx = params.audio_ctx;          // 0: the model's 1500 positions (src/whisper.cpp:6981-6986)
 
     s.prompt_init = {vocab.token_sot};
     if (vocab.is_multilingual()) {
@@ -909,7 +909,18 @@ int run_streams(whisper_context & ctx, std::vector<StreamSpec> & specs) {
         if (it != vocab.token_to_id.end()) space_id = it->second;
     }
 
-    if (!e.size_cross(ctx.batch_cross, n_streams)) return -7;
+    // one audio context per batch: the streams of a whisper_full_parallel call share their parameters
+    int batch_T = 0;
+    for (int i = 0; i < n_streams; ++i)
+        if (S[i].rc == 0 && S[i].phase != Phase::DONE) {
+            const int t = S[i].state->exp_n_audio_ctx > 0 ? S[i].state->exp_n_audio_ctx : 1500;
+            if (batch_T != 0 && t != batch_T) return -5;
+            batch_T = t;
+        }
+    if (batch_T == 0) batch_T = 1500;
+    if (!e.size_cross(ctx.batch_cross, n_streams, batch_T)) return -7;
+    e.cross_T = batch_T;
+    struct CrossTReset { Engine & e; ~CrossTReset() { e.cross_T = 1500; } } cross_t_reset{e};
     const int n_max = hp.n_text_ctx / 2 - 4;
     std::vector<float> logits_host((size_t) hp.n_vocab), logits_rows_host;
 
@@ -973,6 +984,7 @@ int run_streams(whisper_context & ctx, std::vector<StreamSpec> & specs) {
                 }
                 s.state->cross_base = ctx.batch_cross.window_base(s.window, hp.n_text_state);
                 s.state->cross_layer_stride = ctx.batch_cross.layer_stride;
+                s.state->cross_T = ctx.batch_cross.T;
                 if (s.seek > s.seek_start && s.seek + 500 >= s.seek_end) {
                     s.state->prompt_past0.clear();
                     s.state->prompt_past1.clear();

@@ -57,6 +57,7 @@ struct whisper_state {
     wb::CrossKV cross;                 // own single-window pool (low-level API); batched runs use a shared pool
     const void * cross_base = nullptr; // layer-0 K/V of the current window
     size_t cross_layer_stride = 0;
+    int cross_T = 1500;                // audio context of that K/V
 
     whisper_decoder decoders[WHISPER_MAX_DECODERS];
 

@@ -738,18 +738,19 @@ WB200_API int whisper_b200_get_encoder_output(struct whisper_context * ctx, floa
 WB200_API int whisper_b200_get_cross_kv(struct whisper_context * ctx, int layer, uint16_t * out, int n_elems) {
     if (!ctx || !ctx->state || !out || !ctx->state->cross.data.p) return -1;
     const int d = ctx->eng.model.hp.n_text_state;
-    const int want = 1500 * 2 * d;
+    const int T = ctx->state->cross.T;
+    const int want = T * 2 * d;
     if (n_elems != want || layer < 0 || layer >= ctx->eng.model.hp.n_text_layer) return -2;
     std::lock_guard<std::mutex> lock(ctx->eng.mu);
     cudaSetDevice(ctx->eng.device);
     const char * src = (const char *) ctx->state->cross.data.p + (size_t) layer * ctx->state->cross.layer_stride * 2;
-    // the pool keeps a window as [head][K | V][1500][64]; hand it out in the reference's [1500][K(d) | V(d)] order
+    // the pool keeps a window as [head][K | V][T][64]; hand it out in the reference's [T][K(d) | V(d)] order
     std::vector<uint16_t> hm((size_t) want);
     if (cudaMemcpy(hm.data(), src, (size_t) want * 2, cudaMemcpyDeviceToHost) != cudaSuccess) return -3;
     for (int h = 0; h < d / 64; ++h)
         for (int kv = 0; kv < 2; ++kv)
-            for (int t = 0; t < 1500; ++t)
-                memcpy(out + (size_t) t * 2 * d + kv * d + h * 64, hm.data() + ((size_t) (h * 2 + kv) * 1500 + t) * 64, 128);
+            for (int t = 0; t < T; ++t)
+                memcpy(out + (size_t) t * 2 * d + kv * d + h * 64, hm.data() + ((size_t) (h * 2 + kv) * T + t) * 64, 128);
     return 0;
 }
 

@@ -208,6 +208,39 @@ def test_token_level_timestamps_and_max_len_vs_live_reference(lib, model_dir, ma
         assert all(len(s.text) <= max_len or len(s.tokens) <= 2 or sow for s in segs)
 
 
+@pytest.mark.parametrize("audio_ctx,fa", [(512, False), (750, False), (768, True)])
+def test_audio_ctx_vs_live_reference(lib, model_dir, audio_ctx, fa):
+    """whisper_full_params::audio_ctx (the cli's -ac): the encoder runs over the first 2 * audio_ctx mel frames of every window,
+    the cross K/V and the decoder's cross-attention over audio_ctx positions (src/whisper.cpp:1982, 2044, 2278, 2383, 2479);
+    with flash attention the phantom keys are pad256(audio_ctx) - audio_ctx.  Tokens, segment times and token probabilities
+    against the reference run live on this host's CPU."""
+    ref, _ = reflib.load()
+    if ref is None:
+        pytest.skip("oracle/_ref was not built / did not travel")
+    path = model_path(model_dir, "tiny.en")
+    pcm = pcm_for({"kind": "synth", "seed": 7, "windows": 2})
+
+    def run(lib_, **kw):
+        with api.Whisper(lib_, path, flash_attn=fa, **kw) as w:
+            p = w.greedy_params(no_timestamps=False, n_threads=8)
+            p.audio_ctx = audio_ctx
+            rc, segs = w.full(p, pcm)
+            assert rc == 0
+            return segs
+
+    segs, rsegs = run(lib), run(ref, use_gpu=False)
+    worst, n_cmp = 0.0, 0
+    for a, b in zip(segs, rsegs):
+        if a.tokens != b.tokens:          # after a near-tie flip the sequences are different sequences
+            break
+        assert a.text == b.text and (a.t0, a.t1) == (b.t0, b.t1)
+        for ta, tb in zip(a.token_data, b.token_data):
+            worst = max(worst, abs(ta.plog - tb.plog), abs(ta.p - tb.p))
+            n_cmp += 1
+    print(f"audio_ctx={audio_ctx} flash={fa}: {n_cmp} tokens compared, worst p / plog deviation {worst:.3e}")
+    assert n_cmp >= 20 and worst <= (2e-2 if not fa else 5e-2)     # measured: 1.2e-3 / 1.1e-3 / 8.6e-3
+
+
 def test_low_level_api_vs_live_reference(lib, model_dir):
     """whisper_pcm_to_mel -> whisper_encode -> whisper_decode (bench.cpp's call sequence) against the live reference."""
     ref, _ = reflib.load()
