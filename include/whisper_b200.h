@@ -107,6 +107,12 @@ WB200_API double whisper_b200_kernel_step_bench(int which, int dtype, int R, int
  * direct != 0: every CTA owns one whole 128-column tile.  Returns 0, or -1 for shapes the kernel does not take. */
 WB200_API int whisper_b200_chain_geometry(int grid, int rows, int N, int K, int min_units, int direct, int * out);
 
+/* The model loader's expansion of quantised GGML blocks to f16 (csrc/model.cu, host logic only -- needs no device).
+ * ggml_type: 2 q4_0, 3 q4_1, 6 q5_0, 7 q5_1, 8 q8_0 (32 elements per block), 10..14 q2_K..q6_K (256 per block); restates
+ * dequantize_row_* of the reference (ggml/src/ggml-quants.c:307-415, 784-1791).  out16 receives n_blocks * 32 (or 256) IEEE
+ * half bit patterns.  Returns the number of elements written, or -1 for a type the loader does not take. */
+WB200_API long long whisper_b200_dequantize_blocks(int ggml_type, const void * raw, long long n_blocks, uint16_t * out16);
+
 #ifdef __cplusplus
 }
 #endif

@@ -38,6 +38,7 @@ EXT_PROTOTYPES = {
     "whisper_b200_profile_enable": (None, [_C.c_void_p, _C.c_int]),
     "whisper_b200_profile_read": (_C.c_int, [_C.c_void_p, _C.POINTER(_C.c_double), _C.c_int]),
     "whisper_b200_chain_geometry": (_C.c_int, [_C.c_int] * 6 + [_IP]),
+    "whisper_b200_dequantize_blocks": (_C.c_longlong, [_C.c_int, _C.c_void_p, _C.c_longlong, _U16P]),
 }
 
 PROFILE_CLASSES = [("mel", "B"), ("im2col", "B"), ("gemm_conv", "flop"), ("layernorm", "B"), ("gemm_encoder", "flop"),

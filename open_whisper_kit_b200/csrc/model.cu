@@ -7,6 +7,7 @@
 // type of the tensor path; Q/K/V (and cross K/V) weights are concatenated so one GEMM produces them; conv weights
 // are re-ordered to [out][k][in] so the conv stem runs as a GEMM over time-major activations.
 #include "model.h"
+#include "whisper_b200.h"
 
 #include <math.h>
 #include <stdarg.h>
@@ -231,6 +232,133 @@ int quant_block_bytes(int ttype) {
         default: return 0;
     }
 }
+// 256-element super-block formats ("K-quants", reference ggml/src/ggml-common.h:262-336)
+int kquant_block_bytes(int ttype) {
+    switch (ttype) {
+        case 10: return 84;    // q2_K: scales[16], qs[64], f16 d, f16 dmin
+        case 11: return 110;   // q3_K: hmask[32], qs[64], scales[12], f16 d
+        case 12: return 144;   // q4_K: f16 d, f16 dmin, scales[12], qs[128]
+        case 13: return 176;   // q5_K: f16 d, f16 dmin, scales[12], qh[32], qs[128]
+        case 14: return 210;   // q6_K: ql[128], qh[64], i8 scales[16], f16 d
+        default: return 0;
+    }
+}
+// 6-bit scale / min pairs of q4_K and q5_K (get_scale_min_k4, ggml/src/ggml-quants.c:703-710)
+static inline void scale_min_k4(int j, const unsigned char * q, int & sc, int & m) {
+    if (j < 4) {
+        sc = q[j] & 63;
+        m = q[j + 4] & 63;
+    } else {
+        sc = (q[j + 4] & 0xF) | ((q[j - 4] >> 6) << 4);
+        m = (q[j + 4] >> 4) | ((q[j] >> 6) << 4);
+    }
+}
+// Restates dequantize_row_q2_K / q3_K / q4_K / q5_K / q6_K (ggml/src/ggml-quants.c:784-814, 1128-1176, 1352-1374, 1554-1579,
+// 1762-1791): same f32 expressions in the same order, then one rounding to f16.
+void dequantize_kblocks(int ttype, const unsigned char * raw, size_t n_blocks, __half * out) {
+    const int bb = kquant_block_bytes(ttype);
+    auto h2f = [](const unsigned char * p) {
+        __half h;
+        memcpy(&h, p, 2);
+        return __half2float(h);
+    };
+    for (size_t b = 0; b < n_blocks; ++b) {
+        const unsigned char * p = raw + b * bb;
+        __half * y = out + b * 256;
+        if (ttype == 10) {
+            const unsigned char * scales = p, * q = p + 16;
+            const float d = h2f(p + 80), mn = h2f(p + 82);
+            int is = 0;
+            for (int n = 0; n < 256; n += 128) {
+                int shift = 0;
+                for (int j = 0; j < 4; ++j) {
+                    for (int half = 0; half < 2; ++half) {
+                        const unsigned char sc = scales[is++];
+                        const float dl = d * (sc & 0xF), ml = mn * (sc >> 4);
+                        for (int l = 0; l < 16; ++l) *y++ = __float2half_rn(dl * (float) ((signed char) ((q[l + 16 * half] >> shift) & 3)) - ml);
+                    }
+                    shift += 2;
+                }
+                q += 32;
+            }
+        } else if (ttype == 11) {
+            const unsigned char * hm = p, * q = p + 32;
+            const float d_all = h2f(p + 108);
+            uint32_t aux[4];
+            memcpy(aux, p + 96, 12);
+            const uint32_t kmask1 = 0x03030303, kmask2 = 0x0f0f0f0f, tmp = aux[2];
+            aux[2] = ((aux[0] >> 4) & kmask2) | (((tmp >> 4) & kmask1) << 4);
+            aux[3] = ((aux[1] >> 4) & kmask2) | (((tmp >> 6) & kmask1) << 4);
+            aux[0] = (aux[0] & kmask2) | (((tmp >> 0) & kmask1) << 4);
+            aux[1] = (aux[1] & kmask2) | (((tmp >> 2) & kmask1) << 4);
+            const signed char * scales = reinterpret_cast<const signed char *>(aux);
+            int is = 0;
+            unsigned char m = 1;
+            for (int n = 0; n < 256; n += 128) {
+                int shift = 0;
+                for (int j = 0; j < 4; ++j) {
+                    for (int half = 0; half < 2; ++half) {
+                        const float dl = d_all * (scales[is++] - 32);
+                        for (int l = 0; l < 16; ++l) {
+                            const int qv = (signed char) ((q[l + 16 * half] >> shift) & 3) - ((hm[l + 16 * half] & m) ? 0 : 4);
+                            *y++ = __float2half_rn(dl * (float) qv);
+                        }
+                    }
+                    shift += 2;
+                    m <<= 1;
+                }
+                q += 32;
+            }
+        } else if (ttype == 12 || ttype == 13) {
+            const float d = h2f(p), mn = h2f(p + 2);
+            const unsigned char * scales = p + 4;
+            const unsigned char * qh = p + 16;                       // q5_K only
+            const unsigned char * q = ttype == 12 ? p + 16 : p + 48;
+            int is = 0;
+            unsigned char u1 = 1, u2 = 2;
+            for (int j = 0; j < 256; j += 64) {
+                int sc, m;
+                scale_min_k4(is + 0, scales, sc, m);
+                const float d1 = d * sc, m1 = mn * m;
+                scale_min_k4(is + 1, scales, sc, m);
+                const float d2 = d * sc, m2 = mn * m;
+                for (int l = 0; l < 32; ++l) {
+                    const int v = (q[l] & 0xF) + ((ttype == 13 && (qh[l] & u1)) ? 16 : 0);
+                    *y++ = __float2half_rn(d1 * (float) v - m1);
+                }
+                for (int l = 0; l < 32; ++l) {
+                    const int v = (q[l] >> 4) + ((ttype == 13 && (qh[l] & u2)) ? 16 : 0);
+                    *y++ = __float2half_rn(d2 * (float) v - m2);
+                }
+                q += 32;
+                is += 2;
+                u1 <<= 2;
+                u2 <<= 2;
+            }
+        } else {      // 14: q6_K
+            const unsigned char * ql = p, * qh = p + 128;
+            const signed char * sc = reinterpret_cast<const signed char *>(p + 192);
+            const float d = h2f(p + 208);
+            for (int n = 0; n < 256; n += 128) {
+                for (int l = 0; l < 32; ++l) {
+                    const int is = l / 16;
+                    const signed char q1 = (signed char) ((ql[l + 0] & 0xF) | (((qh[l] >> 0) & 3) << 4)) - 32;
+                    const signed char q2 = (signed char) ((ql[l + 32] & 0xF) | (((qh[l] >> 2) & 3) << 4)) - 32;
+                    const signed char q3 = (signed char) ((ql[l + 0] >> 4) | (((qh[l] >> 4) & 3) << 4)) - 32;
+                    const signed char q4 = (signed char) ((ql[l + 32] >> 4) | (((qh[l] >> 6) & 3) << 4)) - 32;
+                    y[l + 0] = __float2half_rn(d * sc[is + 0] * q1);
+                    y[l + 32] = __float2half_rn(d * sc[is + 2] * q2);
+                    y[l + 64] = __float2half_rn(d * sc[is + 4] * q3);
+                    y[l + 96] = __float2half_rn(d * sc[is + 6] * q4);
+                }
+                y += 128;
+                ql += 64;
+                qh += 32;
+                sc += 8;
+            }
+        }
+    }
+}
 void dequantize_blocks(int ttype, const unsigned char * raw, size_t n_blocks, __half * out) {
     const int bb = quant_block_bytes(ttype);
     auto h2f = [](const unsigned char * p) {
@@ -309,10 +437,13 @@ bool model_load(whisper_model_loader * loader, Model & m, DType dtype, int devic
     }
     hp.ftype %= 1000;   // GGML_QNT_VERSION_FACTOR
     // 0 f32, 1 f16, 2 q4_0, 3 q4_1, 7 q8_0, 8 q5_0, 9 q5_1 (ggml_ftype, ggml/include/ggml.h); the 32-element block formats are
-    // expanded to 16-bit weights while loading (record by record, whatever its own type says).  K-quants / IQ formats are not.
-    if (hp.ftype != 0 && hp.ftype != 1 && hp.ftype != 2 && hp.ftype != 3 && hp.ftype != 7 && hp.ftype != 8 && hp.ftype != 9) {
+    // and 10..14 q2_K..q6_K are expanded to 16-bit weights while loading (record by record, whatever its own type says).
+    // IQ / MXFP4 formats are not.
+    if (hp.ftype != 0 && hp.ftype != 1 && hp.ftype != 2 && hp.ftype != 3 && hp.ftype != 7 && hp.ftype != 8 && hp.ftype != 9 &&
+        !(hp.ftype >= 10 && hp.ftype <= 14)) {
         wlog(GGML_LOG_LEVEL_ERROR,
-             "%s: model file ftype %d is not supported by the B200 path (supported: f32, f16, q4_0, q4_1, q5_0, q5_1, q8_0)\n",
+             "%s: model file ftype %d is not supported by the B200 path (supported: f32, f16, q4_0, q4_1, q5_0, q5_1, q8_0, "
+             "q2_K ... q6_K)\n",
              __func__, hp.ftype);
         return false;
     }
@@ -403,7 +534,9 @@ bool model_load(whisper_model_loader * loader, Model & m, DType dtype, int devic
         int32_t n_dims = 0, length = 0, ttype = 0;
         if (!read_pod(loader, n_dims)) break;   // clean EOF
         if (!read_pod(loader, length) || !read_pod(loader, ttype)) break;
-        const int qblock = quant_block_bytes(ttype);      // 0: not a block format
+        const int kblock = kquant_block_bytes(ttype);     // 256-element super-blocks
+        const int qblock = kblock ? kblock : quant_block_bytes(ttype);      // 0: not a block format
+        const int qelems = kblock ? 256 : 32;
         if (n_dims < 1 || n_dims > 4 || length <= 0 || length > 256 || (ttype != 0 && ttype != 1 && qblock == 0)) {
             wlog(GGML_LOG_LEVEL_ERROR, "%s: malformed or unsupported tensor record (n_dims=%d, name_len=%d, type=%d)\n", __func__,
                  n_dims, length, ttype);
@@ -418,19 +551,20 @@ bool model_load(whisper_model_loader * loader, Model & m, DType dtype, int devic
         if (loader->read(loader->context, &name[0], length) != (size_t) length) return false;
         if (qblock) {
             // quantised record: rows of ne[0] elements in blocks of 32 (reference ggml/src/ggml-quants.c:307-415); expand to f16
-            if (t.ne[0] % 32) {
-                wlog(GGML_LOG_LEVEL_ERROR, "%s: tensor '%s': quantised row length %d is not a multiple of 32\n", __func__,
-                     name.c_str(), t.ne[0]);
+            if (t.ne[0] % qelems) {
+                wlog(GGML_LOG_LEVEL_ERROR, "%s: tensor '%s': quantised row length %d is not a multiple of %d\n", __func__,
+                     name.c_str(), t.ne[0], qelems);
                 return false;
             }
-            const size_t n_blocks = t.nelem() / 32;
+            const size_t n_blocks = t.nelem() / qelems;
             std::vector<unsigned char> raw(n_blocks * qblock);
             if (loader->read(loader->context, raw.data(), raw.size()) != raw.size()) {
                 wlog(GGML_LOG_LEVEL_ERROR, "%s: tensor '%s' is truncated\n", __func__, name.c_str());
                 return false;
             }
             t.data.resize(t.nelem() * 2);
-            dequantize_blocks(ttype, raw.data(), n_blocks, reinterpret_cast<__half *>(t.data.data()));
+            if (kblock) dequantize_kblocks(ttype, raw.data(), n_blocks, reinterpret_cast<__half *>(t.data.data()));
+            else dequantize_blocks(ttype, raw.data(), n_blocks, reinterpret_cast<__half *>(t.data.data()));
             t.ttype = 1;
             ++n_quantised;
             tensors[name] = std::move(t);
@@ -611,3 +745,17 @@ bool model_load(whisper_model_loader * loader, Model & m, DType dtype, int devic
 }
 
 }  // namespace wb
+
+extern "C" WB200_API long long whisper_b200_dequantize_blocks(int ggml_type, const void * raw, long long n_blocks, uint16_t * out16) {
+    if (!raw || !out16 || n_blocks < 0) return -1;
+    __half * out = reinterpret_cast<__half *>(out16);
+    if (wb::kquant_block_bytes(ggml_type)) {
+        wb::dequantize_kblocks(ggml_type, (const unsigned char *) raw, (size_t) n_blocks, out);
+        return n_blocks * 256;
+    }
+    if (wb::quant_block_bytes(ggml_type)) {
+        wb::dequantize_blocks(ggml_type, (const unsigned char *) raw, (size_t) n_blocks, out);
+        return n_blocks * 32;
+    }
+    return -1;
+}

@@ -280,7 +280,101 @@ def dequantize_blocks(raw, qtype):
     return y.astype(np.float32).reshape(-1)
 
 
-def write_model(path, arch, seed=1234, ftype=1, tok_emb_gain=1.5, with_tensors=True, qtype=None, dequantized=False):
+# ---- 256-element super-block formats ("K-quants") -------------------------------------------------------------------
+# ggml_type == ggml_ftype for these (reference ggml/include/ggml.h:400-404, 450-454), bytes per block
+KQUANT_TYPES = {"q2_K": (10, 10, 84), "q3_K": (11, 11, 110), "q4_K": (12, 12, 144), "q5_K": (13, 13, 176), "q6_K": (14, 14, 210)}
+
+
+def _scale_min_k4(sc):
+    """sc: [nb][12] uint8 -> (scales [nb][8], mins [nb][8]) as in get_scale_min_k4 (ggml/src/ggml-quants.c:703-710)."""
+    sc = sc.astype(np.int32)
+    d = np.empty((sc.shape[0], 8), np.int32)
+    m = np.empty((sc.shape[0], 8), np.int32)
+    d[:, :4] = sc[:, 0:4] & 63
+    m[:, :4] = sc[:, 4:8] & 63
+    d[:, 4:] = (sc[:, 8:12] & 0xF) | ((sc[:, 0:4] >> 6) << 4)
+    m[:, 4:] = (sc[:, 8:12] >> 4) | ((sc[:, 4:8] >> 6) << 4)
+    return d, m
+
+
+def dequantize_kblocks(raw, qtype):
+    """numpy restatement of dequantize_row_q2_K / q3_K / q4_K / q5_K / q6_K (reference ggml/src/ggml-quants.c:784-814,
+    1128-1176, 1352-1374, 1554-1579, 1762-1791): raw block bytes -> f32, same f32 expressions (no fused multiply-add)."""
+    bb = KQUANT_TYPES[qtype][2]
+    b = np.frombuffer(raw, np.uint8).reshape(-1, bb)
+    nb = b.shape[0]
+    f32 = np.float32
+
+    def h(col):
+        return b[:, col:col + 2].copy().view(np.float16).astype(f32).reshape(nb)
+
+    y = np.empty((nb, 256), f32)
+    if qtype == "q2_K":
+        scales, q = b[:, 0:16].astype(np.int32), b[:, 16:80].astype(np.int32)
+        d, mn = h(80), h(82)
+        o, i_s = 0, 0
+        for n in range(2):
+            for j in range(4):
+                for half in range(2):
+                    sc = scales[:, i_s]
+                    i_s += 1
+                    dl = d * (sc & 0xF).astype(f32)
+                    ml = mn * (sc >> 4).astype(f32)
+                    v = (q[:, 32 * n + 16 * half:32 * n + 16 * half + 16] >> (2 * j)) & 3
+                    y[:, o:o + 16] = dl[:, None] * v.astype(f32) - ml[:, None]
+                    o += 16
+    elif qtype == "q3_K":
+        hm, q = b[:, 0:32].astype(np.int32), b[:, 32:96].astype(np.int32)
+        d_all = h(108)
+        aux = b[:, 96:108].copy().view("<u4").astype(np.uint32)              # [nb][3]
+        k1, k2 = np.uint32(0x03030303), np.uint32(0x0f0f0f0f)
+        a0, a1, tmp = aux[:, 0], aux[:, 1], aux[:, 2]
+        out = np.stack([(a0 & k2) | (((tmp >> 0) & k1) << 4), (a1 & k2) | (((tmp >> 2) & k1) << 4),
+                        ((a0 >> 4) & k2) | (((tmp >> 4) & k1) << 4), ((a1 >> 4) & k2) | (((tmp >> 6) & k1) << 4)], axis=1)
+        scales = np.ascontiguousarray(out.astype("<u4")).view(np.int8).reshape(nb, 16).astype(np.int32)
+        o, i_s = 0, 0
+        for n in range(2):
+            for j in range(4):
+                mbit = 1 << (4 * n + j)
+                for half in range(2):
+                    dl = d_all * (scales[:, i_s] - 32).astype(f32)
+                    i_s += 1
+                    sl = slice(16 * half, 16 * half + 16)
+                    v = ((q[:, 32 * n:32 * n + 32][:, sl] >> (2 * j)) & 3) - np.where(hm[:, sl] & mbit, 0, 4)
+                    y[:, o:o + 16] = dl[:, None] * v.astype(f32)
+                    o += 16
+    elif qtype in ("q4_K", "q5_K"):
+        d, mn = h(0), h(2)
+        sc, m = _scale_min_k4(b[:, 4:16])
+        five = qtype == "q5_K"
+        qh = b[:, 16:48].astype(np.int32) if five else None
+        q = b[:, 48:176].astype(np.int32) if five else b[:, 16:144].astype(np.int32)
+        for g in range(4):
+            ql = q[:, 32 * g:32 * g + 32]
+            lo, hi = ql & 0xF, ql >> 4
+            if five:
+                lo = lo + np.where(qh & (1 << (2 * g)), 16, 0)
+                hi = hi + np.where(qh & (2 << (2 * g)), 16, 0)
+            d1, m1 = d * sc[:, 2 * g].astype(f32), mn * m[:, 2 * g].astype(f32)
+            d2, m2 = d * sc[:, 2 * g + 1].astype(f32), mn * m[:, 2 * g + 1].astype(f32)
+            y[:, 64 * g:64 * g + 32] = d1[:, None] * lo.astype(f32) - m1[:, None]
+            y[:, 64 * g + 32:64 * g + 64] = d2[:, None] * hi.astype(f32) - m2[:, None]
+    else:       # q6_K
+        ql, qh = b[:, 0:128].astype(np.int32), b[:, 128:192].astype(np.int32)
+        sc = b[:, 192:208].copy().view(np.int8).astype(f32)
+        d = h(208)
+        for n in range(2):
+            l_, h_, s_ = ql[:, 64 * n:64 * n + 64], qh[:, 32 * n:32 * n + 32], sc[:, 8 * n:8 * n + 8]
+            qs = [((l_[:, 0:32] & 0xF) | (((h_ >> 0) & 3) << 4)) - 32, ((l_[:, 32:64] & 0xF) | (((h_ >> 2) & 3) << 4)) - 32,
+                  ((l_[:, 0:32] >> 4) | (((h_ >> 4) & 3) << 4)) - 32, ((l_[:, 32:64] >> 4) | (((h_ >> 6) & 3) << 4)) - 32]
+            for k in range(4):
+                scl = np.repeat(s_[:, 2 * k:2 * k + 2], 16, axis=1)            # is = l / 16
+                y[:, 128 * n + 32 * k:128 * n + 32 * k + 32] = (d[:, None] * scl) * qs[k].astype(f32)
+    return y.reshape(-1)
+
+
+def write_model(path, arch, seed=1234, ftype=1, tok_emb_gain=1.5, with_tensors=True, qtype=None, dequantized=False,
+                quantize_fn=None):
     """Write a GGML whisper model file.  ftype=1: 2-D+ weights as F16 (conv biases / positional
     embeddings / 1-D tensors stay F32, as the reference converter does); ftype=0: everything F32.
     qtype ('q4_0' | 'q4_1' | 'q5_0' | 'q5_1' | 'q8_0'): what the reference's `quantize` tool makes of the ftype=1 file --
@@ -289,12 +383,14 @@ def write_model(path, arch, seed=1234, ftype=1, tok_emb_gain=1.5, with_tensors=T
     the F16 file whose weights are exactly those blocks expanded again (the teacher file of the load-time expansion test)."""
     if qtype is not None:
         ftype = 1
+    kq = qtype in KQUANT_TYPES          # K-quants: blocks come from `quantize_fn` (the reference's quantiser, see tests)
     n_vocab, n_actx, d, n_head, n_al, n_tctx, n_tl, n_mels = ARCHS[arch]
     multilingual = n_vocab >= 51865
     rng = np.random.default_rng(seed)
     with open(path, "wb") as f:
         f.write(struct.pack("<I", GGML_MAGIC))
-        hdr_ftype = ftype if qtype is None or dequantized else GGML_QNT_VERSION * 1000 + QUANT_TYPES[qtype][1]
+        types = KQUANT_TYPES if kq else QUANT_TYPES
+        hdr_ftype = ftype if qtype is None or dequantized else GGML_QNT_VERSION * 1000 + types[qtype][1]
         f.write(struct.pack("<11i", n_vocab, n_actx, d, n_head, n_al, n_tctx, d, n_head, n_tl, n_mels, hdr_ftype))
         filt = mel_filters(n_mels)
         f.write(struct.pack("<2i", n_mels, N_FFT_BINS))
@@ -312,11 +408,13 @@ def write_model(path, arch, seed=1234, ftype=1, tok_emb_gain=1.5, with_tensors=T
             ttype = 1 if use_f16 else 0
             payload = data.astype(np.float16 if use_f16 else np.float32).tobytes()
             if qtype is not None and len(shape) == 2 and kind not in ("enc_pos", "dec_pos", "bias2d"):
-                raw = quantize_blocks(data.astype(np.float16).astype(np.float32), qtype)     # the tool reads the F16 file
+                src = data.astype(np.float16).astype(np.float32)                              # the tool reads the F16 file
+                raw = quantize_fn(src, qtype) if kq else quantize_blocks(src, qtype)
                 if dequantized:
-                    payload = dequantize_blocks(raw, qtype).astype(np.float16).tobytes()
+                    expand = dequantize_kblocks if kq else dequantize_blocks
+                    payload = expand(raw, qtype).astype(np.float16).tobytes()
                 else:
-                    ttype, payload = QUANT_TYPES[qtype][0], raw
+                    ttype, payload = types[qtype][0], raw
             nb = name.encode()
             f.write(struct.pack("<3i", len(shape), len(nb), ttype))
             for dim in reversed(shape):  # ggml ne[] order: fastest dimension first

@@ -1,6 +1,7 @@
 """Golden vectors for the ggml block formats, produced by the UNMODIFIED reference (oracle/_ref):
 quantize_row_{q4_0,q4_1,q5_0,q5_1,q8_0}_ref and dequantize_row_* of ggml/src/ggml-quants.c on the fixed input of
-tests/test_oracle_pinning.py::_quant_inputs.  Run in the build container: python tests/golden/make_golden_quant.py"""
+tests/test_oracle_pinning.py::_quant_inputs, and dequantize_row_* (incl. q2_K..q6_K) on the seeded random blocks of
+_random_blocks.  Run in the build container: python tests/golden/make_golden_quant.py"""
 import ctypes as C
 import os
 import sys
@@ -26,5 +27,11 @@ for qtype, (_, _, bb) in modelgen.QUANT_TYPES.items():
     y = np.empty_like(x)
     getattr(ref, f"dequantize_row_{qtype}")(raw.ctypes.data_as(C.c_void_p), y.ctypes.data_as(FP), C.c_int64(len(x)))
     out[f"{qtype}/raw"], out[f"{qtype}/deq"] = raw, y
+from test_oracle_pinning import _random_blocks  # noqa: E402
+for qtype in list(modelgen.QUANT_TYPES) + list(modelgen.KQUANT_TYPES):
+    raw, n_el = _random_blocks(qtype)
+    y = np.empty(raw.shape[0] * n_el, np.float32)
+    getattr(ref, f"dequantize_row_{qtype}")(raw.ctypes.data_as(C.c_void_p), y.ctypes.data_as(FP), C.c_int64(y.size))
+    out[f"{qtype}/rand_deq16"] = y.astype(np.float16)           # what the loader must store: the f32 expansion rounded once
 np.savez_compressed(os.path.join(HERE, "golden_quant.npz"), **out)
 print("wrote golden_quant.npz from reference build", variant)

@@ -380,6 +380,38 @@ def test_quantised_file_loads_as_its_expansion(lib, model_dir, qtype):
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
 
 
+def _ref_kquantizer(ref):
+    def fn(x, qtype):
+        x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1)
+        raw = np.zeros(len(x) // 256 * modelgen.KQUANT_TYPES[qtype][2], np.uint8)
+        getattr(ref, f"quantize_row_{qtype}_ref")(x.ctypes.data_as(FP), raw.ctypes.data_as(C.c_void_p), C.c_int64(len(x)))
+        return raw.tobytes()
+    return fn
+
+
+@pytest.mark.parametrize("qtype", ["q4_K", "q6_K"])
+def test_kquant_file_loads_as_its_expansion(lib, model_dir, qtype):
+    """A K-quant file (256-element super-blocks, quantised here by the reference's own quantize_row_*_ref) against the F16 file
+    holding the oracle's expansion of the same blocks: bit-identical logits; and against the reference's CPU run of the same
+    file.  base.en: the smallest geometry whose rows are multiples of 256."""
+    ref, _ = reflib.load()
+    if ref is None:
+        pytest.skip("oracle/_ref was not built / did not travel")
+    q = os.path.join(model_dir, f"base.en-{qtype}.bin")
+    t = os.path.join(model_dir, f"base.en-{qtype}-expanded.bin")
+    if not os.path.exists(q):
+        modelgen.write_model(q, "base.en", qtype=qtype, quantize_fn=_ref_kquantizer(ref))
+        modelgen.write_model(t, "base.en", qtype=qtype, quantize_fn=_ref_kquantizer(ref), dequantized=True)
+    pcm = pcm_for({"kind": "jfk"})
+    a = _enc_and_logits(lib, q, pcm, [50257])
+    b = _enc_and_logits(lib, t, pcm, [50257])
+    assert np.isfinite(a).all() and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    r = _enc_and_logits(ref, q, pcm, [50257], use_gpu=False)
+    dl = np.abs(a - r)
+    print(f"{qtype}: vs reference CPU run logits max|d| = {dl.max():.3e} mean|d| = {dl.mean():.3e}")
+    assert dl.max() <= 0.2 and dl.mean() <= 0.03        # measured on B200: 7.2e-2 / 1.4e-2 (q4_K), 7.9e-2 / 1.4e-2 (q6_K)
+
+
 @pytest.mark.parametrize("qtype", ["q8_0", "q5_0"])
 def test_quantised_model_vs_live_reference(lib, model_dir, qtype):
     """Same quantised file through the reference CPU path.  The reference multiplies quantised weights with activations it

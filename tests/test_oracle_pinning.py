@@ -165,3 +165,58 @@ def test_block_quantisers_vs_live_reference(qtype):
     y = np.empty_like(x)
     getattr(ref, f"dequantize_row_{qtype}")(raw.ctypes.data_as(C.c_void_p), y.ctypes.data_as(FP), C.c_int64(len(x)))
     assert np.array_equal(modelgen.dequantize_blocks(raw.tobytes(), qtype).view(np.uint32), y.view(np.uint32))
+
+
+# ---- expansion of quantised blocks: numpy restatement, the product's loader (host-only hook) and the reference ----------
+_SCALE_COLS = {"q4_0": (0,), "q4_1": (0, 2), "q5_0": (0,), "q5_1": (0, 2), "q8_0": (0,),
+               "q2_K": (80, 82), "q3_K": (108,), "q4_K": (0, 2), "q5_K": (0, 2), "q6_K": (208,)}
+ALL_QTYPES = sorted(modelgen.QUANT_TYPES) + sorted(modelgen.KQUANT_TYPES)
+
+
+def _random_blocks(qtype, n_blocks=257):
+    """Seeded random block bytes (every bit pattern of the packed fields occurs) with small finite f16 scales."""
+    k = qtype in modelgen.KQUANT_TYPES
+    bb = (modelgen.KQUANT_TYPES if k else modelgen.QUANT_TYPES)[qtype][2]
+    rng = np.random.default_rng(sum(map(ord, qtype)))
+    raw = rng.integers(0, 256, (n_blocks, bb), dtype=np.uint8)
+    for c in _SCALE_COLS[qtype]:
+        raw[:, c:c + 2] = rng.uniform(-0.03, 0.03, n_blocks).astype(np.float16).view(np.uint8).reshape(n_blocks, 2)
+    return raw, (256 if k else 32)
+
+
+def _numpy_expand16(raw, qtype):
+    fn = modelgen.dequantize_kblocks if qtype in modelgen.KQUANT_TYPES else modelgen.dequantize_blocks
+    return fn(raw.tobytes(), qtype).astype(np.float16)
+
+
+@pytest.mark.parametrize("qtype", ALL_QTYPES)
+def test_block_expansion_matches_reference_golden(qtype):
+    raw, _ = _random_blocks(qtype)
+    g = np.load(QUANT_GOLD)[f"{qtype}/rand_deq16"]
+    assert np.array_equal(_numpy_expand16(raw, qtype).view(np.uint16), g.view(np.uint16))
+
+
+@pytest.mark.parametrize("qtype", ALL_QTYPES)
+def test_loader_block_expansion_is_the_oracles(qtype):
+    """csrc/model.cu's load-time expansion (exported host-only hook, no device needed) == the pinned numpy restatement."""
+    import open_whisper_kit_b200 as pkg
+    lib = pkg.load()
+    raw, n_el = _random_blocks(qtype)
+    tt = (modelgen.KQUANT_TYPES if qtype in modelgen.KQUANT_TYPES else modelgen.QUANT_TYPES)[qtype][0]
+    out = np.zeros(raw.shape[0] * n_el, np.uint16)
+    n = lib.whisper_b200_dequantize_blocks(tt, raw.ctypes.data_as(C.c_void_p), raw.shape[0], out.ctypes.data_as(C.POINTER(C.c_uint16)))
+    assert n == out.size
+    assert np.array_equal(out, _numpy_expand16(raw, qtype).view(np.uint16))
+    assert lib.whisper_b200_dequantize_blocks(9, raw.ctypes.data_as(C.c_void_p), 1, out.ctypes.data_as(C.POINTER(C.c_uint16))) == -1
+
+
+@pytest.mark.parametrize("qtype", sorted(modelgen.KQUANT_TYPES))
+def test_kquant_expansion_vs_live_reference(qtype):
+    ref, _ = reflib.load()
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    raw, n_el = _random_blocks(qtype, n_blocks=1500)
+    y = np.empty(raw.shape[0] * n_el, np.float32)
+    getattr(ref, f"dequantize_row_{qtype}")(raw.ctypes.data_as(C.c_void_p), y.ctypes.data_as(FP), C.c_int64(y.size))
+    mine = modelgen.dequantize_kblocks(raw.tobytes(), qtype)
+    assert np.array_equal(mine.view(np.uint32), y.view(np.uint32))
