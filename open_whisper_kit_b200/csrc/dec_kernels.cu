@@ -883,6 +883,10 @@ void dec_cross_attn(DType dt, const void * q, const DecRow * d_rows, int R, int 
 void dec_sample_greedy(float * logits, int ld, const SampleRow * d_srows, int R, const uint32_t * d_static_mask,
                        const SampleParams & prm, SampleOut * d_out, cudaStream_t st) {
     if (R <= 0) return;
+    if (prm.n_vocab > SAMPLE_CTAS * SAMPLE_HALF) {       // model_load() rejects such files; never a silent truncation
+        cuda_fail(cudaErrorInvalidValue, "n_vocab <= 53248 (greedy selection kernel)", __FILE__, __LINE__);
+        return;
+    }
     static bool set = false;
     if (!set) {
         WB_CUDA(cudaFuncSetAttribute(sample_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SAMPLE_SMEM));

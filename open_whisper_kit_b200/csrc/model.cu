@@ -448,7 +448,8 @@ bool model_load(whisper_model_loader * loader, Model & m, DType dtype, int devic
         return false;
     }
     const int d = hp.n_audio_state;
-    if (hp.n_text_state != d || d <= 0 || d % 64 != 0 || d > 1280 || hp.n_audio_head * 64 != d ||
+    if (hp.n_vocab > 53248 /* greedy selection kernel: two CTAs x 26624 logits per row */ || hp.n_text_state != d || d <= 0 ||
+        d % 64 != 0 || d > 1280 || hp.n_audio_head * 64 != d ||
         hp.n_text_head * 64 != d || hp.n_audio_ctx != 1500 || hp.n_text_ctx <= 0 || hp.n_mels <= 0 || hp.n_vocab <= 0) {
         wlog(GGML_LOG_LEVEL_ERROR, "%s: unsupported geometry (d=%d, heads=%d/%d, audio_ctx=%d)\n", __func__, d,
              hp.n_audio_head, hp.n_text_head, hp.n_audio_ctx);
