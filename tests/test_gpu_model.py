@@ -241,6 +241,40 @@ def test_audio_ctx_vs_live_reference(lib, model_dir, audio_ctx, fa):
     assert n_cmp >= 20 and worst <= (2e-2 if not fa else 5e-2)     # measured: 1.2e-3 / 1.1e-3 / 8.6e-3
 
 
+def test_language_auto_detect_vs_live_reference(lib, model_dir):
+    """whisper_lang_auto_detect (encode the window at the offset, one decoder step on <|sot|>, softmax over the language
+    tokens; src/whisper.cpp:4021-4094) and whisper_full with language = "auto" against the reference run live on this CPU."""
+    ref, _ = reflib.load()
+    if ref is None:
+        pytest.skip("oracle/_ref was not built / did not travel")
+    path = model_path(model_dir, "tiny")            # multilingual vocabulary (99 languages)
+    pcm = pcm_for({"kind": "synth", "seed": 7, "windows": 2})
+    n_lang = lib.whisper_lang_max_id() + 1
+    out = {}
+    for name, lib_, kw in (("ours", lib, {}), ("ref", ref, {"use_gpu": False})):
+        with api.Whisper(lib_, path, flash_attn=False, **kw) as w:
+            assert w.pcm_to_mel(pcm, 8) == 0
+            per_offset = []
+            for offset_ms in (0, 12000):
+                probs = np.zeros(n_lang, np.float32)
+                lid = lib_.whisper_lang_auto_detect(w.ctx, offset_ms, 8, probs.ctypes.data_as(FP))
+                per_offset.append((lid, probs))
+            assert lib_.whisper_lang_auto_detect(w.ctx, 10 ** 7, 8, None) == -2          # past the end of the audio
+            p = w.greedy_params(no_timestamps=False, n_threads=8, language=b"auto")
+            rc, segs = w.full(p, pcm)
+            assert rc == 0
+            out[name] = (per_offset, lib_.whisper_full_lang_id(w.ctx), [t for s_ in segs for t in s_.tokens])
+    for (la, pa), (lb, pb) in zip(out["ours"][0], out["ref"][0]):
+        top2 = np.sort(pb)[-2:]
+        print(f"language id ours {la} reference {lb}; probs max|d| = {np.abs(pa - pb).max():.3e}; reference top-2 {top2[1]:.4f} / {top2[0]:.4f}")
+        assert abs(pa.sum() - 1.0) < 1e-4 and np.abs(pa - pb).max() <= 2e-3
+        if top2[1] - top2[0] > 4e-3:
+            assert la == lb
+    if out["ours"][1] == out["ref"][1]:
+        n = min(len(out["ours"][2]), len(out["ref"][2]), 12)
+        assert n >= 4 and out["ours"][2][:n] == out["ref"][2][:n]
+
+
 def test_low_level_api_vs_live_reference(lib, model_dir):
     """whisper_pcm_to_mel -> whisper_encode -> whisper_decode (bench.cpp's call sequence) against the live reference."""
     ref, _ = reflib.load()
