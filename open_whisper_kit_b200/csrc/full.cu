@@ -376,6 +376,8 @@ bool decode_single(whisper_context & ctx, whisper_state & st, const whisper_toke
     return ok;
 }
 
+static int lang_from_logits(const Vocab & vocab, const float * logits, float * lang_probs);
+
 // whisper_lang_auto_detect_with_state, src/whisper.cpp:4021-4094
 int lang_auto_detect(whisper_context & ctx, whisper_state & st, int offset_ms, float * lang_probs) {
     const int seek = offset_ms / 10;
@@ -392,9 +394,14 @@ int lang_auto_detect(whisper_context & ctx, whisper_state & st, int offset_ms, f
     const Vocab & vocab = ctx.eng.model.vocab;
     const whisper_token sot = vocab.token_sot;
     if (!decode_single(ctx, st, &sot, 1, 0)) return -7;
+    return lang_from_logits(vocab, st.logits.data(), lang_probs);
+}
+
+// softmax over the language tokens of one logits row -> most probable language id (src/whisper.cpp:4060-4091)
+static int lang_from_logits(const Vocab & vocab, const float * logits, float * lang_probs) {
     std::vector<std::pair<double, int>> li;
     const int n_lang = std::min(lang_max_id() + 1, std::max(0, vocab.n_vocab - (vocab.token_sot + 1)));
-    for (int i = 0; i < n_lang; ++i) li.emplace_back(st.logits[vocab.token_sot + 1 + i], i);
+    for (int i = 0; i < n_lang; ++i) li.emplace_back(logits[vocab.token_sot + 1 + i], i);
     std::sort(li.begin(), li.end(), [](const std::pair<double, int> & a, const std::pair<double, int> & b) { return a.first > b.first; });
     const double mx = li[0].first;
     double sum = 0.0;
@@ -426,6 +433,8 @@ struct Stream {
     const float * samples = nullptr;
     int n_samples = 0;
     bool samples_on_device = false;
+    int detected_lang = -1;      // >= 0: language found by the batched detection pass of run_streams
+    std::vector<float> detected_probs;
     int rc = 0;
     Phase phase = Phase::WINDOW;
 
@@ -459,7 +468,8 @@ static int stream_begin(whisper_context & ctx, Stream & s) {
     if (params.language == nullptr || strlen(params.language) == 0 || strcmp(params.language, "auto") == 0 ||
         params.detect_language) {
         std::vector<float> probs(lang_max_id() + 1, 0.0f);
-        const int id = lang_auto_detect(ctx, *state, 0, probs.data());
+        if (s.detected_lang >= 0) probs = s.detected_probs;
+        const int id = s.detected_lang >= 0 ? s.detected_lang : lang_auto_detect(ctx, *state, 0, probs.data());
         if (id < 0) {
             wlog(GGML_LOG_LEVEL_ERROR, "%s: failed to auto-detect language\n", __func__);
             return -3;
@@ -892,6 +902,52 @@ int run_streams(whisper_context & ctx, std::vector<StreamSpec> & specs) {
         const int64_t dt = time_us() - t0;
         dbg_mel += dt;
         for (int i = 0; i < n_streams; ++i) S[i].state->t_mel_us += dt / std::max(1, n_streams);
+    }
+    // Language detection for all the streams that ask for it ("auto" / detect_language) as ONE encoder batch and ONE decoder
+    // step on <|sot|> instead of a single-window pass per stream (what whisper_lang_auto_detect does; the arithmetic per stream
+    // is the same).  Streams this pass cannot take (no audio, a left-over audio_ctx override) fall back to the per-stream path.
+    {
+        std::vector<int> need;
+        for (int i = 0; i < n_streams; ++i) {
+            const auto & p = S[i].params;
+            const bool wants = p.language == nullptr || strlen(p.language) == 0 || strcmp(p.language, "auto") == 0 || p.detect_language;
+            if (wants && vocab.is_multilingual() && S[i].state->mel.valid && S[i].state->mel.n_len_org > 0 && S[i].state->exp_n_audio_ctx == 0)
+                need.push_back(i);
+        }
+        if (need.size() > 1 && e.size_cross(ctx.batch_cross, n_streams, 1500)) {
+            const int64_t t0 = time_us();
+            bool ok = true;
+            for (size_t k = 0; k < need.size() && ok; k += 32) {
+                std::vector<EncJob> jobs;
+                for (size_t q = k; q < std::min(need.size(), k + 32); ++q) jobs.push_back({&S[need[q]].state->mel, 0});
+                ok = e.encode(jobs, ctx.batch_cross, (int) k, false);
+            }
+            std::vector<DecRow> rows;
+            std::vector<int> lrows;
+            for (size_t q = 0; q < need.size() && ok; ++q) {
+                whisper_decoder & dec = S[need[q]].state->decoders[0];
+                ok = dec.kv.reserve(e.self_kv_bytes());
+                rows.push_back({vocab.token_sot, 0, dec.kv.p, ctx.batch_cross.window_base((int) q, hp.n_text_state)});
+                lrows.push_back((int) q);
+            }
+            e.cross_T = 1500;
+            ok = ok && e.decode(rows, lrows, ctx.batch_cross.layer_stride);
+            std::vector<float> lg;
+            if (ok) {
+                lg.resize(need.size() * (size_t) hp.n_vocab);
+                ok = e.fetch_logits_rows(0, (int) need.size(), lg.data());
+            }
+            const int64_t dt = time_us() - t0;
+            for (size_t q = 0; q < need.size() && ok; ++q) {
+                Stream & s = S[need[q]];
+                s.detected_probs.assign(lang_max_id() + 1, 0.0f);
+                s.detected_lang = lang_from_logits(vocab, lg.data() + q * (size_t) hp.n_vocab, s.detected_probs.data());
+                s.state->t_encode_us += dt / (int64_t) need.size();
+                s.state->n_encode++;
+                s.state->n_decode++;
+            }
+            if (!ok) cuda_clear_failure();        // the per-stream path reports the error with the reference's code
+        }
     }
     for (int i = 0; i < n_streams; ++i) {
         S[i].rc = stream_begin(ctx, S[i]);

@@ -275,6 +275,27 @@ def test_language_auto_detect_vs_live_reference(lib, model_dir):
         assert n >= 4 and out["ours"][2][:n] == out["ref"][2][:n]
 
 
+def test_batched_language_detection_matches_per_stream_and_reference(lib, model_dir):
+    """whisper_full_parallel with language = "auto": the chunks' languages are detected in one encoder batch + one decoder
+    step (csrc/full.cu) -- same ids and same transcription as the reference, whose worker states detect one by one."""
+    ref, _ = reflib.load()
+    if ref is None:
+        pytest.skip("oracle/_ref was not built / did not travel")
+    path = model_path(model_dir, "tiny")
+    pcm = pcm_for({"kind": "synth", "seed": 7, "windows": 3})
+    res = {}
+    for name, lib_, kw in (("ours", lib, {}), ("ref", ref, {"use_gpu": False})):
+        with api.Whisper(lib_, path, flash_attn=False, **kw) as w:
+            p = w.greedy_params(no_timestamps=False, n_threads=4, language=b"auto")
+            rc, segs = w.full(p, pcm, n_processors=3)
+            assert rc == 0
+            res[name] = (lib_.whisper_full_lang_id(w.ctx), [(s_.t0, s_.t1, s_.tokens) for s_ in segs])
+    print("language ids:", res["ours"][0], res["ref"][0], "segments:", len(res["ours"][1]), len(res["ref"][1]))
+    assert res["ours"][0] == res["ref"][0]
+    n = min(len(res["ours"][1]), len(res["ref"][1]), 4)
+    assert n >= 2 and res["ours"][1][:n] == res["ref"][1][:n]
+
+
 def test_low_level_api_vs_live_reference(lib, model_dir):
     """whisper_pcm_to_mel -> whisper_encode -> whisper_decode (bench.cpp's call sequence) against the live reference."""
     ref, _ = reflib.load()
