@@ -125,7 +125,7 @@ template <typename F> static void parallel_for(int n, F && fn) {
     for (auto & th : pool) th.join();
 }
 
-// whisper_process_logits, src/whisper.cpp:6177-6445 (grammar branch omitted: out of scope)
+// whisper_process_logits, src/whisper.cpp:6177-6445
 static void process_logits_host(whisper_context & ctx, whisper_state & state, whisper_decoder & dec,
                                 const whisper_full_params & params, const std::vector<uint32_t> & static_bits,
                                 const float * logits_row, float temperature) {
@@ -206,6 +206,10 @@ static void process_logits_host(whisper_context & ctx, whisper_state & state, wh
                 logits[i] = -INFINITY;
                 logprobs[i] = -INFINITY;
             }
+        } else if (params.n_grammar_rules > 0) {
+            // penalise the text tokens the grammar cannot continue with, then redo the log-softmax (src/whisper.cpp:6363-6385)
+            grammar_suppress_invalid(vocab.id_to_token, vocab.token_eot, params.grammar_penalty, logits, dec.grammar);
+            compute_logprobs(logits.data(), n, logprobs);
         }
     }
     for (int i = 0; i < n; ++i) probs[i] = logits[i] == -INFINITY ? 0.0f : expf(logprobs[i]);
@@ -423,6 +427,7 @@ struct beam_candidate {
     int seek_delta;
     bool has_ts;
     whisper_sequence sequence;
+    whisper_grammar grammar;
 };
 
 enum class Phase { WINDOW, PROMPT, STEPPING, RANK, DONE };
@@ -1076,7 +1081,7 @@ int run_streams(whisper_context & ctx, std::vector<StreamSpec> & specs) {
                         break;
                 }
                 s.n_decoders_cur = std::max(1, ndc);
-                s.device_path = p.strategy == WHISPER_SAMPLING_GREEDY && s.t_cur < 1e-6f && !p.logits_filter_callback;
+                s.device_path = p.strategy == WHISPER_SAMPLING_GREEDY && s.t_cur < 1e-6f && !p.logits_filter_callback && p.grammar_rules == nullptr;
                 for (int j = 0; j < s.n_decoders_cur; ++j) {
                     whisper_decoder & d = st->decoders[j];
                     d.sequence.tokens.clear();
@@ -1089,6 +1094,8 @@ int run_streams(whisper_context & ctx, std::vector<StreamSpec> & specs) {
                     d.seek_delta = 3000;
                     d.failed = d.completed = d.has_ts = false;
                     d.has_pending = false;
+                    if (p.grammar_rules != nullptr) d.grammar = grammar_init(p.grammar_rules, p.n_grammar_rules, p.i_start_rule);
+                    else d.grammar = {};
                     if (!d.kv.reserve(e.self_kv_bytes())) return -7;
                 }
                 s.prompt.clear();
@@ -1241,7 +1248,7 @@ int run_streams(whisper_context & ctx, std::vector<StreamSpec> & specs) {
                         } else {
                             const auto & toks = d.sampled;
                             for (const auto & t : toks) {
-                                bc_per_dec[j].push_back({j, d.seek_delta, d.has_ts, d.sequence});
+                                bc_per_dec[j].push_back({j, d.seek_delta, d.has_ts, d.sequence, d.grammar});
                                 bc_per_dec[j].back().sequence.tokens.push_back(t);
                                 bc_per_dec[j].back().sequence.sum_logprobs_all += t.plog;
                             }
@@ -1270,6 +1277,7 @@ int run_streams(whisper_context & ctx, std::vector<StreamSpec> & specs) {
                             d.seek_delta = cur.seek_delta;
                             d.has_ts = cur.has_ts;
                             d.sequence = cur.sequence;
+                            d.grammar = cur.grammar;
                             // KV history of the parent beam: copy into the alternate buffer, swap afterwards
                             if (cur.decoder_idx != j) {
                                 if (!d.kv_alt.reserve(e.self_kv_bytes())) return -7;
@@ -1297,6 +1305,7 @@ int run_streams(whisper_context & ctx, std::vector<StreamSpec> & specs) {
                             d.sequence.result_len = i + 1;
                             d.has_ts = true;
                         }
+                        grammar_accept_token(vocab.id_to_token, d.grammar, token.id);
                         if (token.id == vocab.token_eot || (p.max_tokens > 0 && i >= p.max_tokens) ||
                             (d.has_ts && s.seek + d.seek_delta + 10 >= s.seek_end)) {
                             if (d.sequence.result_len == 0 && !p.no_timestamps) {
