@@ -383,6 +383,60 @@ def test_grammar_constrained_sampling_vs_live_reference(lib, model_dir, strategy
         assert res["ours"][0][:n] == res["ref"][0][:n]
 
 
+def test_callbacks_vs_live_reference(lib, model_dir):
+    """new_segment / progress / encoder_begin / abort / logits_filter callbacks of whisper_full: same call sequence, same
+    arguments and same effect as in the reference (src/whisper.cpp:7035-7052, 7504-7538, 7685-7694)."""
+    ref, _ = reflib.load()
+    if ref is None:
+        pytest.skip("oracle/_ref was not built / did not travel")
+    path = model_path(model_dir, "tiny.en")
+    pcm = pcm_for({"kind": "synth", "seed": 7, "windows": 2})
+    NEW_SEG = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p)
+    PROGRESS = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p)
+    ENC_BEGIN = C.CFUNCTYPE(C.c_bool, C.c_void_p, C.c_void_p, C.c_void_p)
+    ABORT = C.CFUNCTYPE(C.c_bool, C.c_void_p)
+    FILTER = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_float), C.c_void_p)
+
+    def run(lib_, mode, **kw):
+        ev = []
+        with api.Whisper(lib_, path, flash_attn=False, **kw) as w:
+            n_vocab = lib_.whisper_n_vocab(w.ctx)
+            eot = lib_.whisper_token_eot(w.ctx)
+            p = w.greedy_params(no_timestamps=False, n_threads=8)
+            cbs = [NEW_SEG(lambda c, st, n_new, ud: ev.append(("seg", n_new, lib_.whisper_full_n_segments(w.ctx)))),
+                   PROGRESS(lambda c, st, prog, ud: ev.append(("progress", prog))),
+                   ENC_BEGIN(lambda c, st, ud: (ev.append(("enc",)), mode != "enc_false" or len([e for e in ev if e[0] == "enc"]) < 2)[1]),
+                   ABORT(lambda ud: mode == "abort")]            # always true: the first encoder pass is abandoned (-6)
+
+            def filt(c, st, toks, n_toks, logits, ud):
+                a = np.ctypeslib.as_array(logits, shape=(n_vocab,))
+                a[1:eot:2] = -np.inf                                   # odd text tokens are forbidden
+            cbs.append(FILTER(filt))
+            p.new_segment_callback = C.cast(cbs[0], C.c_void_p)
+            p.progress_callback = C.cast(cbs[1], C.c_void_p)
+            p.encoder_begin_callback = C.cast(cbs[2], C.c_void_p)
+            if mode == "abort":
+                p.abort_callback = C.cast(cbs[3], C.c_void_p)
+            if mode == "filter":
+                p.logits_filter_callback = C.cast(cbs[4], C.c_void_p)
+            rc, segs = w.full(p, pcm)
+            toks = [t for s_ in segs for t in s_.tokens]
+        return rc, [e for e in ev if e[0] != "abort?"], toks, eot
+
+    for mode in ("plain", "filter", "enc_false", "abort"):
+        rc_a, ev_a, tok_a, eot = run(lib, mode)
+        rc_b, ev_b, tok_b, _ = run(ref, mode, use_gpu=False)
+        print(f"{mode}: rc {rc_a}/{rc_b}, {len(ev_a)}/{len(ev_b)} callback events, {len(tok_a)}/{len(tok_b)} tokens")
+        assert rc_a == rc_b
+        if mode in ("plain", "filter", "enc_false"):
+            n = min(len(tok_a), len(tok_b), 16)
+            assert tok_a[:n] == tok_b[:n] and (mode == "enc_false" or n >= 8)
+            if tok_a == tok_b:
+                assert ev_a == ev_b
+        if mode == "filter":
+            assert all(t % 2 == 0 or t >= eot for t in tok_a)
+
+
 def test_low_level_api_vs_live_reference(lib, model_dir):
     """whisper_pcm_to_mel -> whisper_encode -> whisper_decode (bench.cpp's call sequence) against the live reference."""
     ref, _ = reflib.load()
