@@ -31,6 +31,9 @@ whisper_context * init_with_loader(whisper_model_loader * loader, whisper_contex
         if (loader->close) loader->close(loader->context);
         return nullptr;
     }
+    if (params.dtw_token_timestamps)
+        wlog(GGML_LOG_LEVEL_WARN, "%s: dtw_token_timestamps is not implemented on the B200 path: whisper_token_data::t_dtw stays -1\n",
+             __func__);
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0 || params.gpu_device < 0 || params.gpu_device >= n_dev) {
         cudaGetLastError();
