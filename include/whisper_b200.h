@@ -113,6 +113,12 @@ WB200_API int whisper_b200_chain_geometry(int grid, int rows, int N, int K, int 
  * half bit patterns.  Returns the number of elements written, or -1 for a type the loader does not take. */
 WB200_API long long whisper_b200_dequantize_blocks(int ggml_type, const void * raw, long long n_blocks, uint16_t * out16);
 
+/* The grammar automaton of the sampling path (csrc/grammar.cu, host logic only -- needs no device) run over a whole UTF-8 text
+ * as if it were one token: 0 = some character cannot continue the grammar, 1 = the text is a complete sentence of the
+ * grammar, 2 = a valid prefix that is not complete yet.  rules / n_rules / i_start_rule as in whisper_full_params. */
+WB200_API int whisper_b200_grammar_match(const struct whisper_grammar_element ** rules, size_t n_rules, size_t i_start_rule,
+                                         const char * text);
+
 #ifdef __cplusplus
 }
 #endif

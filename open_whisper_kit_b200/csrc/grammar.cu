@@ -248,3 +248,20 @@ void grammar_accept_token(const std::vector<std::string> & id_to_token, whisper_
 }
 
 }  // namespace wb
+
+#include "whisper_b200.h"
+
+extern "C" WB200_API int whisper_b200_grammar_match(const struct whisper_grammar_element ** rules, size_t n_rules, size_t i_start_rule,
+                                                    const char * text) {
+    if (!rules || !text || i_start_rule >= n_rules) return 0;
+    whisper_grammar g = wb::grammar_init(rules, n_rules, i_start_rule);
+    // the candidate check of the sampling path: is this text rejected at the current position?
+    std::vector<std::string> vocab(1, std::string(text));
+    std::vector<float> logits(1, 0.0f);
+    wb::grammar_suppress_invalid(vocab, 1, 1.0f, logits, g);
+    if (logits[0] != 0.0f) return 0;
+    wb::grammar_accept_token(vocab, g, 0);
+    for (const auto & stack : g.stacks)
+        if (stack.empty()) return 1;
+    return g.stacks.empty() ? 0 : 2;
+}
