@@ -116,6 +116,17 @@ WB200_API long long whisper_b200_dequantize_blocks(int ggml_type, const void * r
 /* The grammar automaton of the sampling path (csrc/grammar.cu, host logic only -- needs no device) run over a whole UTF-8 text
  * as if it were one token: 0 = some character cannot continue the grammar, 1 = the text is a complete sentence of the
  * grammar, 2 = a valid prefix that is not complete yet.  rules / n_rules / i_start_rule as in whisper_full_params. */
+/* The token-level timestamp heuristic and the max_len re-wrapping (csrc/full.cu, host logic only -- needs no device) applied
+ * to ONE segment whose inputs are all given explicitly; restates whisper_exp_compute_token_level_timestamps and
+ * whisper_wrap_segment (src/whisper.cpp:8455-8660, 6077-6130).  token_texts: the n_vocab token strings; tok_state =
+ * {t_beg, t_last, tid_last} in / out; tokens are updated in place; segment k after wrapping is seg_t[2k] .. seg_t[2k+1] with
+ * seg_ntok[k] tokens.  Returns the number of segments, or -1. */
+WB200_API int whisper_b200_token_timestamps(const char * const * token_texts, int n_vocab, int token_eot, int token_beg,
+                                            const float * pcm, int n_samples, long long seg_t0, long long seg_t1,
+                                            struct whisper_token_data * tokens, int n_tokens, float thold_pt, float thold_ptsum,
+                                            long long * tok_state, int max_len, int split_on_word, long long * seg_t, int * seg_ntok,
+                                            int seg_cap);
+
 WB200_API int whisper_b200_grammar_match(const struct whisper_grammar_element ** rules, size_t n_rules, size_t i_start_rule,
                                          const char * text);
 

@@ -14,6 +14,7 @@
 //                 draws per beam, src/whisper.cpp:6519-6592) or a user logits callback -> the logits row is copied to
 //                 the host and the restated reference rules/samplers below run there.
 #include "full.h"
+#include "whisper_b200.h"
 
 #include <math.h>
 #include <string.h>
@@ -1507,3 +1508,43 @@ int run_streams(whisper_context & ctx, std::vector<StreamSpec> & specs) {
 }
 
 }  // namespace wb
+
+// Host-only hook (needs no device): the token-level timestamp heuristic and the max_len re-wrapping of ONE segment, with every
+// input given explicitly.  tok_state = {t_beg, t_last, tid_last} in / out.  Returns the number of segments (>= 1) after
+// wrapping, or -1.  seg_t[2k], seg_t[2k+1], seg_ntok[k] describe segment k; tokens are updated in place, in order.
+extern "C" WB200_API int whisper_b200_token_timestamps(
+    const char * const * token_texts, int n_vocab, int token_eot, int token_beg, const float * pcm, int n_samples, long long seg_t0,
+    long long seg_t1, whisper_token_data * tokens, int n_tokens, float thold_pt, float thold_ptsum, long long * tok_state, int max_len,
+    int split_on_word, long long * seg_t, int * seg_ntok, int seg_cap) {
+    if (!token_texts || !tokens || !tok_state || n_tokens < 0 || n_vocab <= 0) return -1;
+    wb::Vocab vocab;
+    vocab.n_vocab = n_vocab;
+    vocab.token_eot = token_eot;
+    vocab.token_beg = token_beg;
+    vocab.id_to_token.assign(token_texts, token_texts + n_vocab);
+    whisper_state st;
+    wb::signal_energy(pcm, n_samples, 32, st.energy);
+    st.t_beg = tok_state[0];
+    st.t_last = tok_state[1];
+    st.tid_last = (whisper_token) tok_state[2];
+    st.result_all.push_back({(int64_t) seg_t0, (int64_t) seg_t1, "", 0.0f, {}, false});
+    st.result_all.back().tokens.assign(tokens, tokens + n_tokens);
+    wb::compute_token_level_timestamps(vocab, st, 0, thold_pt, thold_ptsum);
+    int n_seg = 1;
+    if (max_len > 0) n_seg = wb::wrap_segment(vocab, st, max_len, split_on_word != 0);
+    tok_state[0] = st.t_beg;
+    tok_state[1] = st.t_last;
+    tok_state[2] = st.tid_last;
+    int k = 0;
+    for (size_t i = 0; i < st.result_all.size(); ++i) {
+        const auto & seg = st.result_all[i];
+        if ((int) i < seg_cap && seg_t && seg_ntok) {
+            seg_t[2 * i] = seg.t0;
+            seg_t[2 * i + 1] = seg.t1;
+            seg_ntok[i] = (int) seg.tokens.size();
+        }
+        for (const auto & t : seg.tokens)
+            if (k < n_tokens) tokens[k++] = t;
+    }
+    return n_seg;
+}

@@ -89,6 +89,39 @@ int64_t ref_kv_cross_copy(struct whisper_context * ctx, int which /*0=k 1=v*/, f
     return n;
 }
 
+// The reference's token-level timestamp heuristic and max_len re-wrapping on ONE externally supplied segment
+// (whisper_exp_compute_token_level_timestamps / whisper_wrap_segment / get_signal_energy, src/whisper.cpp:8425-8660, 6077-6130).
+// tok_state = {t_beg, t_last, tid_last} in / out.  Same contract as whisper_b200_token_timestamps of the product.
+__attribute__((visibility("default")))
+int ref_token_timestamps(struct whisper_context * ctx, const float * pcm, int n_samples, long long seg_t0, long long seg_t1,
+                         whisper_token_data * tokens, int n_tokens, float thold_pt, float thold_ptsum, long long * tok_state,
+                         int max_len, int split_on_word, long long * seg_t, int * seg_ntok, int seg_cap) {
+    if (!ctx || !ctx->state || !tokens || !tok_state) return -1;
+    whisper_state & st = *ctx->state;
+    st.energy   = get_signal_energy(pcm, n_samples, 32);
+    st.t_beg    = tok_state[0];
+    st.t_last   = tok_state[1];
+    st.tid_last = (whisper_token) tok_state[2];
+    st.result_all.clear();
+    st.result_all.push_back({ (int64_t) seg_t0, (int64_t) seg_t1, "", 0.0f, {}, false });
+    st.result_all.back().tokens.assign(tokens, tokens + n_tokens);
+    whisper_exp_compute_token_level_timestamps(*ctx, st, 0, thold_pt, thold_ptsum);
+    int n_seg = 1;
+    if (max_len > 0) n_seg = whisper_wrap_segment(*ctx, st, max_len, split_on_word != 0);
+    tok_state[0] = st.t_beg;
+    tok_state[1] = st.t_last;
+    tok_state[2] = st.tid_last;
+    int k = 0;
+    for (size_t i = 0; i < st.result_all.size(); ++i) {
+        const auto & seg = st.result_all[i];
+        if ((int) i < seg_cap && seg_t && seg_ntok) {
+            seg_t[2*i] = seg.t0; seg_t[2*i + 1] = seg.t1; seg_ntok[i] = (int) seg.tokens.size();
+        }
+        for (const auto & t : seg.tokens) if (k < n_tokens) tokens[k++] = t;
+    }
+    return n_seg;
+}
+
 // Run the reference's own logit rules + greedy sampler on an externally supplied logits row.
 // Used to pin the oracle restatement of whisper_process_logits / whisper_sample_token
 // (src/whisper.cpp:6177-6445, 6460-6517).  `hist` are the tokens sampled so far.
