@@ -127,6 +127,15 @@ WB200_API int whisper_b200_token_timestamps(const char * const * token_texts, in
                                             long long * tok_state, int max_len, int split_on_word, long long * seg_t, int * seg_ntok,
                                             int seg_cap);
 
+/* The host sampling path's restatement of whisper_process_logits followed by the greedy whisper_sample_token
+ * (csrc/full.cu <- src/whisper.cpp:6177-6517; host logic only -- needs no device) on ONE explicit logits row and decoder
+ * state.  token_texts: the n_vocab token strings; special = {eot, sot, translate, transcribe, solm, prev, nosp, not, beg};
+ * hist: the tokens sampled so far.  Any of the outputs may be NULL.  Returns 0, or -1. */
+WB200_API int whisper_b200_process_logits(const char * const * token_texts, int n_vocab, const int * special, int n_audio_ctx,
+                                          struct whisper_full_params params, float temperature, const float * logits_row,
+                                          const whisper_token * hist, int n_hist, int has_ts, int seek_delta, float * logits_out,
+                                          float * logprobs_out, float * probs_out, struct whisper_token_data * tok_out);
+
 WB200_API int whisper_b200_grammar_match(const struct whisper_grammar_element ** rules, size_t n_rules, size_t i_start_rule,
                                          const char * text);
 

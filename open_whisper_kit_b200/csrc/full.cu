@@ -53,8 +53,7 @@ std::string to_timestamp(int64_t t, bool comma) {
 
 // ---- token ids that are suppressed at every step (everything in whisper_process_logits that does not depend on the
 // decoder state: src/whisper.cpp:6224-6292) ------------------------------------------------------------------------
-static void build_static_suppress(const whisper_context & ctx, const whisper_full_params & p, std::vector<uint32_t> & bits) {
-    const Vocab & v = ctx.eng.model.vocab;
+static void build_static_suppress(const Vocab & v, const whisper_full_params & p, std::vector<uint32_t> & bits) {
     const int V = v.n_vocab;
     bits.assign((V + 31) / 32, 0u);
     auto kill = [&](int id) {
@@ -127,10 +126,10 @@ template <typename F> static void parallel_for(int n, F && fn) {
 }
 
 // whisper_process_logits, src/whisper.cpp:6177-6445
-static void process_logits_host(whisper_context & ctx, whisper_state & state, whisper_decoder & dec,
+// cb_ctx: only handed to the user's logits_filter_callback; vocab / n_audio_ctx: the model's
+static void process_logits_host(whisper_context * cb_ctx, const Vocab & vocab, int n_audio_ctx, whisper_state & state, whisper_decoder & dec,
                                 const whisper_full_params & params, const std::vector<uint32_t> & static_bits,
                                 const float * logits_row, float temperature) {
-    const Vocab & vocab = ctx.eng.model.vocab;
     const int n = vocab.n_vocab;
     const auto & toks = dec.sequence.tokens;
     const bool is_initial = toks.empty();
@@ -162,7 +161,7 @@ static void process_logits_host(whisper_context & ctx, whisper_state & state, wh
         if (id < n) logits[id] = -INFINITY;
     }
     if (params.logits_filter_callback) {
-        params.logits_filter_callback(&ctx, &state, toks.data(), (int) toks.size(), logits.data(),
+        params.logits_filter_callback(cb_ctx, &state, toks.data(), (int) toks.size(), logits.data(),
                                       params.logits_filter_callback_user_data);
     }
     // regex / non-speech suppressions (after the callback, as in the reference)
@@ -181,7 +180,7 @@ static void process_logits_host(whisper_context & ctx, whisper_state & state, wh
         }
     }
     if (is_initial && params.max_initial_ts > 0.0f) {
-        const float precision = 30.0f / ctx.eng.model.hp.n_audio_ctx;
+        const float precision = 30.0f / n_audio_ctx;
         const int tid0 = (int) std::round(params.max_initial_ts / precision);
         for (int i = vocab.token_beg + tid0 + 1; i < n; ++i) logits[i] = -INFINITY;
     }
@@ -962,7 +961,7 @@ int run_streams(whisper_context & ctx, std::vector<StreamSpec> & specs) {
 
     // static suppression mask (state independent rules); identical params across streams of one call
     std::vector<uint32_t> static_bits;
-    build_static_suppress(ctx, S[0].params, static_bits);
+    build_static_suppress(vocab, S[0].params, static_bits);
     if (!ctx.static_mask.reserve(static_bits.size() * 4)) return -7;
     WB_CUDA(cudaMemcpy(ctx.static_mask.p, static_bits.data(), static_bits.size() * 4, cudaMemcpyHostToDevice));
     int space_id = -1;
@@ -1160,7 +1159,7 @@ int run_streams(whisper_context & ctx, std::vector<StreamSpec> & specs) {
                             fail_stream(s, -8);
                             continue;
                         }
-                        process_logits_host(ctx, *st, st->decoders[0], s.params, static_bits, logits_host.data(), s.t_cur);
+                        process_logits_host(&ctx, vocab, hp.n_audio_ctx, *st, st->decoders[0], s.params, static_bits, logits_host.data(), s.t_cur);
                         for (int j = 1; j < s.n_decoders_cur; ++j) {
                             whisper_decoder & d = st->decoders[j];
                             e.kv_copy_prefix(st->decoders[0].kv.p, d.kv.p, (int) s.prompt.size());
@@ -1418,7 +1417,7 @@ int run_streams(whisper_context & ctx, std::vector<StreamSpec> & specs) {
                                 const int r = host_rows[q];
                                 Stream & s = S[owner[r].first];
                                 whisper_decoder & d = s.state->decoders[owner[r].second];
-                                process_logits_host(ctx, *s.state, d, s.params, static_bits,
+                                process_logits_host(&ctx, vocab, hp.n_audio_ctx, *s.state, d, s.params, static_bits,
                                                     logits_rows_host.data() + (size_t) (r - r_lo) * hp.n_vocab, s.t_cur);
                             });
                     }
@@ -1547,4 +1546,39 @@ extern "C" WB200_API int whisper_b200_token_timestamps(
             if (k < n_tokens) tokens[k++] = t;
     }
     return n_seg;
+}
+
+// Host-only hook (needs no device): the host sampling path's restatement of whisper_process_logits + the greedy
+// whisper_sample_token on ONE explicit logits row and decoder state (token history, has_ts, seek_delta), for a vocabulary given
+// as its n_vocab token strings and special-token ids = {eot, sot, translate, transcribe, solm, prev, nosp, not, beg}.
+extern "C" WB200_API int whisper_b200_process_logits(const char * const * token_texts, int n_vocab, const int * special, int n_audio_ctx,
+                                                     struct whisper_full_params params, float temperature, const float * logits_row,
+                                                     const whisper_token * hist, int n_hist, int has_ts, int seek_delta, float * logits_out,
+                                                     float * logprobs_out, float * probs_out, struct whisper_token_data * tok_out) {
+    if (!token_texts || !special || !logits_row || n_vocab <= 0 || n_audio_ctx <= 0) return -1;
+    wb::Vocab vocab;
+    vocab.n_vocab = n_vocab;
+    vocab.id_to_token.assign(token_texts, token_texts + n_vocab);
+    for (int i = 0; i < n_vocab; ++i) vocab.token_to_id[vocab.id_to_token[i]] = i;
+    vocab.token_eot = special[0]; vocab.token_sot = special[1]; vocab.token_translate = special[2]; vocab.token_transcribe = special[3];
+    vocab.token_solm = special[4]; vocab.token_prev = special[5]; vocab.token_nosp = special[6]; vocab.token_not = special[7];
+    vocab.token_beg = special[8];
+    whisper_state st;
+    whisper_decoder & dec = st.decoders[0];
+    dec.has_ts = has_ts != 0;
+    dec.seek_delta = seek_delta;
+    for (int i = 0; i < n_hist; ++i) {
+        whisper_token_data td = {};
+        td.id = hist[i];
+        dec.sequence.tokens.push_back(td);
+    }
+    if (params.grammar_rules != nullptr) dec.grammar = wb::grammar_init(params.grammar_rules, params.n_grammar_rules, params.i_start_rule);
+    std::vector<uint32_t> static_bits;
+    wb::build_static_suppress(vocab, params, static_bits);
+    wb::process_logits_host(nullptr, vocab, n_audio_ctx, st, dec, params, static_bits, logits_row, temperature);
+    if (logits_out) memcpy(logits_out, dec.logits.data(), (size_t) n_vocab * sizeof(float));
+    if (logprobs_out) memcpy(logprobs_out, dec.logprobs.data(), (size_t) n_vocab * sizeof(float));
+    if (probs_out) memcpy(probs_out, dec.probs.data(), (size_t) n_vocab * sizeof(float));
+    if (tok_out) *tok_out = wb::sample_token_host(vocab, dec, true);
+    return 0;
 }
