@@ -136,6 +136,11 @@ WB200_API int whisper_b200_process_logits(const char * const * token_texts, int 
                                           const whisper_token * hist, int n_hist, int has_ts, int seek_delta, float * logits_out,
                                           float * logprobs_out, float * probs_out, struct whisper_token_data * tok_out);
 
+/* The tokenizer of whisper_tokenize (csrc/whisper_api.cu <- src/whisper.cpp:3272-3320; host logic only -- needs no device) on
+ * a vocabulary given as its n_vocab token strings.  Returns the token count, or -needed if n_max_tokens is too small. */
+WB200_API int whisper_b200_tokenize(const char * const * token_texts, int n_vocab, const char * text, whisper_token * tokens,
+                                    int n_max_tokens);
+
 WB200_API int whisper_b200_grammar_match(const struct whisper_grammar_element ** rules, size_t n_rules, size_t i_start_rule,
                                          const char * text);
 

@@ -822,3 +822,21 @@ WB200_API int whisper_b200_full_device(struct whisper_context * ctx, struct whis
 }
 
 }  // extern "C"
+
+// Host-only hook (needs no device): the tokenizer on a vocabulary given as its n_vocab token strings; same return convention
+// as whisper_tokenize (count, or -needed when n_max_tokens is too small).
+extern "C" WB200_API int whisper_b200_tokenize(const char * const * token_texts, int n_vocab, const char * text, whisper_token * tokens,
+                                               int n_max_tokens) {
+    if (!token_texts || !text || n_vocab <= 0) return -1;
+    try {
+        wb::Vocab vocab;
+        vocab.n_vocab = n_vocab;
+        for (int i = 0; i < n_vocab; ++i) vocab.token_to_id[token_texts[i]] = i;
+        const std::vector<int> res = tokenize(vocab, text);
+        if (n_max_tokens < (int) res.size()) return -(int) res.size();
+        for (size_t i = 0; i < res.size(); ++i) tokens[i] = res[i];
+        return (int) res.size();
+    } catch (const std::exception &) {
+        return -1;
+    }
+}
