@@ -130,11 +130,18 @@ WB200_API int whisper_b200_token_timestamps(const char * const * token_texts, in
 /* The host sampling path's restatement of whisper_process_logits followed by the greedy whisper_sample_token
  * (csrc/full.cu <- src/whisper.cpp:6177-6517; host logic only -- needs no device) on ONE explicit logits row and decoder
  * state.  token_texts: the n_vocab token strings; special = {eot, sot, translate, transcribe, solm, prev, nosp, not, beg};
- * hist: the tokens sampled so far.  Any of the outputs may be NULL.  Returns 0, or -1. */
+ * hist: the tokens sampled so far.  topk_out (optional): topk_k draws of the restated whisper_sample_token_topk (6519-6592)
+ * with the decoder's mt19937 seeded with topk_seed.  Any of the outputs may be NULL.  Returns 0, or -1. */
 WB200_API int whisper_b200_process_logits(const char * const * token_texts, int n_vocab, const int * special, int n_audio_ctx,
                                           struct whisper_full_params params, float temperature, const float * logits_row,
                                           const whisper_token * hist, int n_hist, int has_ts, int seek_delta, float * logits_out,
-                                          float * logprobs_out, float * probs_out, struct whisper_token_data * tok_out);
+                                          float * logprobs_out, float * probs_out, struct whisper_token_data * tok_out, int topk_k,
+                                          unsigned topk_seed, struct whisper_token_data * topk_out);
+
+/* whisper_sequence_score restated (src/whisper.cpp:6595-6641; host logic only): out = {sum_logprobs, avg_logprobs, entropy,
+ * score} of the first result_len of n tokens given by ids and log-probabilities. */
+WB200_API int whisper_b200_sequence_score(struct whisper_full_params params, const float * plog, const whisper_token * ids, int n,
+                                          int result_len, double * out);
 
 /* The tokenizer of whisper_tokenize (csrc/whisper_api.cu <- src/whisper.cpp:3272-3320; host logic only -- needs no device) on
  * a vocabulary given as its n_vocab token strings.  Returns the token count, or -needed if n_max_tokens is too small. */

@@ -1554,7 +1554,8 @@ extern "C" WB200_API int whisper_b200_token_timestamps(
 extern "C" WB200_API int whisper_b200_process_logits(const char * const * token_texts, int n_vocab, const int * special, int n_audio_ctx,
                                                      struct whisper_full_params params, float temperature, const float * logits_row,
                                                      const whisper_token * hist, int n_hist, int has_ts, int seek_delta, float * logits_out,
-                                                     float * logprobs_out, float * probs_out, struct whisper_token_data * tok_out) {
+                                                     float * logprobs_out, float * probs_out, struct whisper_token_data * tok_out,
+                                                     int topk_k, unsigned topk_seed, struct whisper_token_data * topk_out) {
     if (!token_texts || !special || !logits_row || n_vocab <= 0 || n_audio_ctx <= 0) return -1;
     wb::Vocab vocab;
     vocab.n_vocab = n_vocab;
@@ -1580,5 +1581,28 @@ extern "C" WB200_API int whisper_b200_process_logits(const char * const * token_
     if (logprobs_out) memcpy(logprobs_out, dec.logprobs.data(), (size_t) n_vocab * sizeof(float));
     if (probs_out) memcpy(probs_out, dec.probs.data(), (size_t) n_vocab * sizeof(float));
     if (tok_out) *tok_out = wb::sample_token_host(vocab, dec, true);
+    if (topk_out && topk_k > 0) {          // the sampled draws of the beam / best_of path, decoder RNG seeded as given
+        dec.rng = std::mt19937(topk_seed);
+        const auto toks = wb::sample_token_topk_host(vocab, dec, topk_k);
+        for (int i = 0; i < topk_k; ++i) topk_out[i] = toks[i];
+    }
+    return 0;
+}
+
+// Host-only hook: whisper_sequence_score restated (csrc/full.cu <- src/whisper.cpp:6595-6641) on a sequence given by its token
+// ids and log-probabilities; out = {sum_logprobs, avg_logprobs, entropy, score}.
+extern "C" WB200_API int whisper_b200_sequence_score(struct whisper_full_params params, const float * plog, const whisper_token * ids, int n,
+                                                     int result_len, double * out) {
+    if (!plog || !ids || !out || n < 0) return -1;
+    whisper_sequence seq = {};
+    for (int i = 0; i < n; ++i) {
+        whisper_token_data td = {};
+        td.id = ids[i];
+        td.plog = plog[i];
+        seq.tokens.push_back(td);
+    }
+    seq.result_len = result_len;
+    wb::sequence_score(params, seq);
+    out[0] = seq.sum_logprobs; out[1] = seq.avg_logprobs; out[2] = seq.entropy; out[3] = seq.score;
     return 0;
 }

@@ -152,6 +152,36 @@ int ref_process_logits(struct whisper_context * ctx, struct whisper_full_params 
     return 0;
 }
 
+// k draws of whisper_sample_token_topk ("beam search" / best_of sampling, src/whisper.cpp:6519-6592) from the distribution left
+// in decoder 0 by the last ref_process_logits call, with the decoder's mt19937 re-seeded first; and whisper_sequence_score
+// (6595-6641) of a sequence given by its token log-probabilities.
+__attribute__((visibility("default")))
+int ref_sample_topk(struct whisper_context * ctx, int k, unsigned seed, whisper_token_data * out) {
+    if (!ctx || !ctx->state || !out || k <= 0) return -1;
+    whisper_decoder & dec = ctx->state->decoders[0];
+    if ((int) dec.probs.size() != ctx->vocab.n_vocab) return -2;
+    dec.rng = std::mt19937(seed);
+    const auto toks = whisper_sample_token_topk(*ctx, dec, k);
+    for (int i = 0; i < k; ++i) out[i] = toks[i];
+    return 0;
+}
+
+__attribute__((visibility("default")))
+int ref_sequence_score(struct whisper_full_params params, const float * plog, const whisper_token * ids, int n, int result_len,
+                       double * out /* sum_logprobs, avg_logprobs, entropy, score */) {
+    whisper_sequence seq = {};
+    for (int i = 0; i < n; ++i) {
+        whisper_token_data td = {};
+        td.id = ids[i];
+        td.plog = plog[i];
+        seq.tokens.push_back(td);
+    }
+    seq.result_len = result_len;
+    whisper_sequence_score(params, seq);
+    out[0] = seq.sum_logprobs; out[1] = seq.avg_logprobs; out[2] = seq.entropy; out[3] = seq.score;
+    return 0;
+}
+
 __attribute__((visibility("default")))
 float ref_no_speech_prob(struct whisper_context * ctx) {
     return ctx && ctx->state ? ctx->state->no_speech_prob : -1.0f;

@@ -27,6 +27,7 @@ REF_PROTOTYPES = {
                                      C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_int, _FP, _FP, _FP,
                                      C.POINTER(capi.whisper_token_data)]),
     "ref_no_speech_prob": (C.c_float, [C.c_void_p]),
+    "ref_sample_topk": (C.c_int, [C.c_void_p, C.c_int, C.c_uint, C.POINTER(capi.whisper_token_data)]),
     "ref_token_timestamps": (C.c_int, [C.c_void_p, _FP, C.c_int, C.c_longlong, C.c_longlong, C.c_void_p, C.c_int, C.c_float,
                                        C.c_float, C.POINTER(C.c_longlong), C.c_int, C.c_int, C.POINTER(C.c_longlong),
                                        C.POINTER(C.c_int), C.c_int]),

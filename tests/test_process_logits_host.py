@@ -27,7 +27,8 @@ def ctxs(request, tmp_path_factory):
     lib = pkg.load()
     lib.whisper_b200_process_logits.restype = C.c_int
     lib.whisper_b200_process_logits.argtypes = [C.c_void_p, C.c_int, IP, C.c_int, capi.whisper_full_params, C.c_float, FP, IP, C.c_int,
-                                                C.c_int, C.c_int, FP, FP, FP, C.POINTER(capi.whisper_token_data)]
+                                                C.c_int, C.c_int, FP, FP, FP, C.POINTER(capi.whisper_token_data), C.c_int, C.c_uint,
+                                                C.POINTER(capi.whisper_token_data)]
     n_vocab = ref.whisper_n_vocab(w.ctx)
     texts = [ref.whisper_token_to_str(w.ctx, i) or b"" for i in range(n_vocab)]
     special = [ref.whisper_token_eot(w.ctx), ref.whisper_token_sot(w.ctx), ref.whisper_token_translate(w.ctx),
@@ -73,16 +74,19 @@ def test_process_logits_and_greedy_token_match_reference(ctxs, kind, variant):
     for side in ("ours", "ref"):
         lo, lp, pr = (np.empty(n_vocab, np.float32) for _ in range(3))
         tok = capi.whisper_token_data()
+        draws = (capi.whisper_token_data * 5)()
         if side == "ours":
             rc = lib.whisper_b200_process_logits(C.cast(text_arr, C.c_void_p), n_vocab, special_arr, 1500, p, temperature,
                                                  logits.ctypes.data_as(FP), h_arr, len(hist), has_ts, seek_delta, lo.ctypes.data_as(FP),
-                                                 lp.ctypes.data_as(FP), pr.ctypes.data_as(FP), C.byref(tok))
+                                                 lp.ctypes.data_as(FP), pr.ctypes.data_as(FP), C.byref(tok), 5, 1234 + len(hist), draws)
         else:
             rc = ref.ref_process_logits(w.ctx, p, temperature, logits.ctypes.data_as(FP), h_arr, len(hist), has_ts, seek_delta,
                                         lo.ctypes.data_as(FP), lp.ctypes.data_as(FP), pr.ctypes.data_as(FP), C.byref(tok))
+            assert ref.ref_sample_topk(w.ctx, 5, 1234 + len(hist), draws) == 0
         assert rc == 0
-        out.append((lo, lp, pr, (tok.id, tok.tid, tok.p, tok.plog, tok.pt, tok.ptsum)))
-    (la, pa, qa, ta), (lb, pb, qb, tb) = out
+        out.append((lo, lp, pr, (tok.id, tok.tid, tok.p, tok.plog, tok.pt, tok.ptsum), [(d.id, d.tid) for d in draws]))
+    (la, pa, qa, ta, da), (lb, pb, qb, tb, db) = out
+    assert da == db, "mt19937 / discrete_distribution draws differ"
     assert np.array_equal(np.isneginf(la), np.isneginf(lb)), "different tokens suppressed"
     fin = ~np.isneginf(lb)
     assert np.array_equal(la[fin], lb[fin])
@@ -90,3 +94,23 @@ def test_process_logits_and_greedy_token_match_reference(ctxs, kind, variant):
     fin = ~np.isneginf(pb)
     assert np.abs(pa[fin] - pb[fin]).max() <= 2e-6 and np.abs(qa - qb).max() <= 1e-7
     assert ta[:2] == tb[:2] and np.allclose(ta[2:], tb[2:], rtol=2e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("case", range(8))
+def test_sequence_score_matches_reference(ctxs, case):
+    ref, w, lib, n_vocab, _, _, special = ctxs
+    lib.whisper_b200_sequence_score.restype = C.c_int
+    lib.whisper_b200_sequence_score.argtypes = [capi.whisper_full_params, FP, IP, C.c_int, C.c_int, C.POINTER(C.c_double)]
+    ref.ref_sequence_score.restype = C.c_int
+    ref.ref_sequence_score.argtypes = [capi.whisper_full_params, FP, IP, C.c_int, C.c_int, C.POINTER(C.c_double)]
+    rng = np.random.default_rng(50 + case)
+    n = int(rng.integers(1, 80))
+    ids = rng.integers(0, 40 if case % 2 else special[0], n).astype(np.int32)          # few distinct ids: low entropy
+    plog = (-rng.exponential(1.0, n)).astype(np.float32)
+    p = w.greedy_params(no_timestamps=False, n_threads=1)
+    p.length_penalty = [-1.0, 0.0, 0.6, 1.0][case % 4]
+    result_len = int(rng.integers(0 if case == 0 else 1, n + 1))
+    a, b = (C.c_double * 4)(), (C.c_double * 4)()
+    assert lib.whisper_b200_sequence_score(p, plog.ctypes.data_as(FP), ids.ctypes.data_as(IP), n, result_len, a) == 0
+    assert ref.ref_sequence_score(p, plog.ctypes.data_as(FP), ids.ctypes.data_as(IP), n, result_len, b) == 0
+    assert np.allclose(list(a), list(b), rtol=1e-12, atol=0.0), (list(a), list(b))
