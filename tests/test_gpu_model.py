@@ -437,6 +437,35 @@ def test_callbacks_vs_live_reference(lib, model_dir):
             assert all(t % 2 == 0 or t >= eot for t in tok_a)
 
 
+@pytest.mark.parametrize("arch", ["tiny.en", "tiny", "large-v3-turbo"])
+def test_vocabulary_and_model_info_vs_live_reference(lib, model_dir, arch, tmp_path):
+    """whisper_model_load's header / vocabulary handling (src/whisper.cpp:1485-1672): every token string incl. the synthesised
+    specials ([_EOT_], [_TT_n], [_LANG_xx] ...), every special-token id and every model getter equal the reference's, for the
+    51864-, 51865- and 51866-entry vocabularies (header-only files: the reference's own "test model" convention)."""
+    ref, _ = reflib.load()
+    if ref is None:
+        pytest.skip("oracle/_ref was not built / did not travel")
+    path = os.path.join(str(tmp_path), f"{arch}-header.bin")
+    modelgen.write_model(path, arch, with_tensors=False)
+    getters = ["whisper_n_vocab", "whisper_n_text_ctx", "whisper_n_audio_ctx", "whisper_is_multilingual", "whisper_model_n_vocab",
+               "whisper_model_n_audio_ctx", "whisper_model_n_audio_state", "whisper_model_n_audio_head", "whisper_model_n_audio_layer",
+               "whisper_model_n_text_ctx", "whisper_model_n_text_state", "whisper_model_n_text_head", "whisper_model_n_text_layer",
+               "whisper_model_n_mels", "whisper_model_ftype", "whisper_model_type", "whisper_token_eot", "whisper_token_sot",
+               "whisper_token_solm", "whisper_token_prev", "whisper_token_nosp", "whisper_token_not", "whisper_token_beg",
+               "whisper_token_translate", "whisper_token_transcribe"]
+    info = {}
+    for name, lib_, kw in (("ours", lib, {}), ("ref", ref, {"use_gpu": False})):
+        with api.Whisper(lib_, path, flash_attn=False, **kw) as w:
+            vals = {g: getattr(lib_, g)(w.ctx) for g in getters}
+            n = vals["whisper_n_vocab"]
+            vals["strings"] = [lib_.whisper_token_to_str(w.ctx, i) for i in range(n)]
+            vals["lang_tokens"] = [lib_.whisper_token_lang(w.ctx, i) for i in range(lib_.whisper_lang_max_id() + 1)]
+            vals["model_type_str"] = lib_.whisper_model_type_readable(w.ctx)
+            info[name] = vals
+    for k in info["ref"]:
+        assert info["ours"][k] == info["ref"][k], k
+
+
 def test_low_level_api_vs_live_reference(lib, model_dir):
     """whisper_pcm_to_mel -> whisper_encode -> whisper_decode (bench.cpp's call sequence) against the live reference."""
     ref, _ = reflib.load()
