@@ -22,6 +22,17 @@ void cuda_clear_failure();
         if (e__ != cudaSuccess) ::wb::cuda_fail(e__, #expr, __FILE__, __LINE__); \
     } while (0)
 
+// Launch-site helper: true the first time a site runs on the CURRENT device (kernel function attributes such as the dynamic
+// shared-memory limit are per device, and one process may hold contexts on several GPUs).
+static inline bool first_use_on_device(unsigned long long & seen) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (seen & bit) return false;
+    seen |= bit;
+    return true;
+}
+
 template <typename T> static inline T ceil_div(T a, T b) { return (a + b - 1) / b; }
 template <typename T> static inline T round_up(T a, T b) { return ceil_div(a, b) * b; }
 

@@ -271,17 +271,15 @@ bool skinny_gemm(const GemmArgs & g, SkinnyWorkspace & wsp, cudaStream_t stream)
     cfg.attrs = attr;
     cfg.numAttrs = 2;
     if (g.dtype == DType::F16) {
-        static bool set = false;
-        if (!set) {
+        static unsigned long long set = 0;      // per device: function attributes are
+        if (first_use_on_device(set)) {
             WB_CUDA(cudaFuncSetAttribute(skinny_gemm_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, S_SMEM));
-            set = true;
         }
         WB_CUDA(cudaLaunchKernelEx(&cfg, skinny_gemm_kernel<__half>, p));
     } else {
-        static bool set = false;
-        if (!set) {
+        static unsigned long long set = 0;      // per device: function attributes are
+        if (first_use_on_device(set)) {
             WB_CUDA(cudaFuncSetAttribute(skinny_gemm_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, S_SMEM));
-            set = true;
         }
         WB_CUDA(cudaLaunchKernelEx(&cfg, skinny_gemm_kernel<__nv_bfloat16>, p));
     }
