@@ -113,9 +113,6 @@ WB200_API int whisper_b200_chain_geometry(int grid, int rows, int N, int K, int 
  * half bit patterns.  Returns the number of elements written, or -1 for a type the loader does not take. */
 WB200_API long long whisper_b200_dequantize_blocks(int ggml_type, const void * raw, long long n_blocks, uint16_t * out16);
 
-/* The grammar automaton of the sampling path (csrc/grammar.cu, host logic only -- needs no device) run over a whole UTF-8 text
- * as if it were one token: 0 = some character cannot continue the grammar, 1 = the text is a complete sentence of the
- * grammar, 2 = a valid prefix that is not complete yet.  rules / n_rules / i_start_rule as in whisper_full_params. */
 /* The token-level timestamp heuristic and the max_len re-wrapping (csrc/full.cu, host logic only -- needs no device) applied
  * to ONE segment whose inputs are all given explicitly; restates whisper_exp_compute_token_level_timestamps and
  * whisper_wrap_segment (src/whisper.cpp:8455-8660, 6077-6130).  token_texts: the n_vocab token strings; tok_state =
@@ -147,9 +144,6 @@ WB200_API int whisper_b200_sequence_score(struct whisper_full_params params, con
  * a vocabulary given as its n_vocab token strings.  Returns the token count, or -needed if n_max_tokens is too small. */
 WB200_API int whisper_b200_tokenize(const char * const * token_texts, int n_vocab, const char * text, whisper_token * tokens,
                                     int n_max_tokens);
-
-WB200_API int whisper_b200_grammar_match(const struct whisper_grammar_element ** rules, size_t n_rules, size_t i_start_rule,
-                                         const char * text);
 
 #ifdef __cplusplus
 }

@@ -7,13 +7,16 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+#include <mutex>
+
 namespace wb {
 
 // ---- error handling -------------------------------------------------------------------------------
 // No exception crosses the C ABI (reference contract, include/whisper.h: errors are return codes), so
 // CUDA failures are recorded, logged once and surfaced by the caller as the API's failure value.
 void cuda_fail(cudaError_t e, const char * expr, const char * file, int line);
-bool cuda_failed();            // sticky flag, per process
+bool cuda_failed();            // sticky flag of the calling thread (one API call = one thread = one context)
 void cuda_clear_failure();
 
 #define WB_CUDA(expr)                                                        \
@@ -22,15 +25,23 @@ void cuda_clear_failure();
         if (e__ != cudaSuccess) ::wb::cuda_fail(e__, #expr, __FILE__, __LINE__); \
     } while (0)
 
-// Launch-site helper: true the first time a site runs on the CURRENT device (kernel function attributes such as the dynamic
-// shared-memory limit are per device, and one process may hold contexts on several GPUs).
-static inline bool first_use_on_device(unsigned long long & seen) {
+// Launch-site helper: runs `configure` once per device, before the first launch of a kernel on that device (kernel function
+// attributes such as the dynamic shared-memory limit are per device, and one process may hold contexts on several GPUs that
+// are driven from several threads).  The done-bit is published only after `configure` returned, and late-comers wait on the
+// mutex, so no thread can launch ahead of the attribute.
+struct DeviceOnce {
+    std::atomic<unsigned long long> done{0};
+    std::mutex mu;
+};
+template <typename F> static inline void once_per_device(DeviceOnce & o, F && configure) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
     const unsigned long long bit = 1ull << (dev & 63);
-    if (seen & bit) return false;
-    seen |= bit;
-    return true;
+    if (o.done.load(std::memory_order_acquire) & bit) return;
+    std::lock_guard<std::mutex> lock(o.mu);
+    if (o.done.load(std::memory_order_relaxed) & bit) return;
+    configure();
+    o.done.fetch_or(bit, std::memory_order_release);
 }
 
 template <typename T> static inline T ceil_div(T a, T b) { return (a + b - 1) / b; }

@@ -830,13 +830,13 @@ void dec_cross_attn(DType dt, const void * q, const DecRow * d_rows, int R, int 
     if (bulk && !q_split) {
         const int nq = (d_groups && n_groups > 0) ? CBQ_MAX : 1;
         const size_t bsmem = (size_t) CB_STAGES * CB_CHUNK + (size_t) nq * ((T + 31) & ~31) * sizeof(float);
-        static unsigned long long set = 0;      // per device: function attributes are
-        if (first_use_on_device(set)) {
+        static DeviceOnce set;      // function attributes are per device
+        once_per_device(set, [&] {
             WB_CUDA(cudaFuncSetAttribute(cross_attn_bulk_kernel<__half, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
             WB_CUDA(cudaFuncSetAttribute(cross_attn_bulk_kernel<__nv_bfloat16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
             WB_CUDA(cudaFuncSetAttribute(cross_attn_bulk_kernel<__half, CBQ_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
             WB_CUDA(cudaFuncSetAttribute(cross_attn_bulk_kernel<__nv_bfloat16, CBQ_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        }
+        });
         if (bsmem <= 100 * 1024) {
             const dim3 g(nq > 1 ? n_groups : R, n_head);
             const __half * qh = reinterpret_cast<const __half *>(q);
@@ -886,10 +886,10 @@ void dec_sample_greedy(float * logits, int ld, const SampleRow * d_srows, int R,
         cuda_fail(cudaErrorInvalidValue, "n_vocab <= 53248 (greedy selection kernel)", __FILE__, __LINE__);
         return;
     }
-    static unsigned long long set = 0;      // per device: function attributes are
-    if (first_use_on_device(set)) {
+    static DeviceOnce set;      // function attributes are per device
+    once_per_device(set, [&] {
         WB_CUDA(cudaFuncSetAttribute(sample_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SAMPLE_SMEM));
-    }
+    });
     launch_pdl(sample_greedy_kernel, dim3(R * SAMPLE_CTAS), dim3(SAMPLE_THREADS), SAMPLE_SMEM, st, logits, ld, d_srows, d_static_mask, prm,
                d_out);
     WB_CUDA(cudaGetLastError());

@@ -328,17 +328,17 @@ bool enc_attention_tc(DType dt, const void * qkv, void * out, void * vt_scratch,
     const float scale_log2e = (1.0f / sqrtf((float) FA_DH)) * 1.4426950408889634f;
     dim3 tgrid(ceil_div(TP, 64), n_head, n_windows), grid(ceil_div(T, FA_BQ), n_head, n_windows);
     if (dt == DType::F16) {
-        static unsigned long long set = 0;      // per device: function attributes are
-        if (first_use_on_device(set)) {
+        static DeviceOnce set;      // function attributes are per device
+        once_per_device(set, [&] {
             WB_CUDA(cudaFuncSetAttribute(enc_attn_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
-        }
+        });
         v_transpose_kernel<__half><<<tgrid, 256, 0, st>>>(reinterpret_cast<const __half *>(qkv), reinterpret_cast<__half *>(vt_scratch), T, TP, d, n_head);
         enc_attn_tc_kernel<__half><<<grid, FA_THREADS, FA_SMEM, st>>>(tm_q, tm_k, tm_vt, reinterpret_cast<__half *>(out), T, d, n_head, scale_log2e, n_phantom);
     } else {
-        static unsigned long long set = 0;      // per device: function attributes are
-        if (first_use_on_device(set)) {
+        static DeviceOnce set;      // function attributes are per device
+        once_per_device(set, [&] {
             WB_CUDA(cudaFuncSetAttribute(enc_attn_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
-        }
+        });
         v_transpose_kernel<__nv_bfloat16><<<tgrid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16 *>(qkv), reinterpret_cast<__nv_bfloat16 *>(vt_scratch), T, TP, d, n_head);
         enc_attn_tc_kernel<__nv_bfloat16><<<grid, FA_THREADS, FA_SMEM, st>>>(tm_q, tm_k, tm_vt, reinterpret_cast<__nv_bfloat16 *>(out), T, d, n_head, scale_log2e, n_phantom);
     }

@@ -1,5 +1,5 @@
 // Batched device engine: mel -> encoder (+ cross K/V) -> decoder rows -> logits / on-device selection.
-// One Engine per whisper_context (one model replica on one GPU); calls are serialised by a mutex.
+// One Engine per whisper_context (one model replica on one GPU); calls are serialised by a (recursive) mutex.
 #pragma once
 
 #include <mutex>
@@ -78,7 +78,11 @@ struct Engine {
     int device = 0;
     cudaStream_t stream = nullptr;
     MelPlan mel_plan;
-    std::mutex mu;
+    // Serialises the API calls on this context (one GPU = one queue).  Recursive: the progress / encoder_begin / new_segment /
+    // abort callbacks of whisper_full run on the calling thread under the lock and may call the low-level entry points
+    // (whisper_pcm_to_mel, whisper_encode, whisper_decode, ... on ANOTHER state); a nested whisper_full* is refused.
+    std::recursive_mutex mu;
+    bool in_full = false;
 
     Arena ws;                  // activations
     DeviceBlock meta;          // small per-call device arrays

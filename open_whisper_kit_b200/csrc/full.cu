@@ -14,6 +14,7 @@
 //                 draws per beam, src/whisper.cpp:6519-6592) or a user logits callback -> the logits row is copied to
 //                 the host and the restated reference rules/samplers below run there.
 #include "full.h"
+#include "token_times.h"
 #include "whisper_b200.h"
 
 #include <math.h>
@@ -206,10 +207,6 @@ static void process_logits_host(whisper_context * cb_ctx, const Vocab & vocab, i
                 logits[i] = -INFINITY;
                 logprobs[i] = -INFINITY;
             }
-        } else if (params.n_grammar_rules > 0) {
-            // penalise the text tokens the grammar cannot continue with, then redo the log-softmax (src/whisper.cpp:6363-6385)
-            grammar_suppress_invalid(vocab.id_to_token, vocab.token_eot, params.grammar_penalty, logits, dec.grammar);
-            compute_logprobs(logits.data(), n, logprobs);
         }
     }
     for (int i = 0; i < n; ++i) probs[i] = logits[i] == -INFINITY ? 0.0f : expf(logprobs[i]);
@@ -361,9 +358,10 @@ bool decode_single(whisper_context & ctx, whisper_state & st, const whisper_toke
     }
     const int64_t t0 = time_us();
     std::vector<int> lrows(1, n_tokens - 1);
+    const int outer_T = e.cross_T;                   // a callback of a running whisper_full may call in here
     e.cross_T = st.cross_T;
     bool ok = e.decode(rows, lrows, st.cross_layer_stride);
-    e.cross_T = 1500;
+    e.cross_T = outer_T;
     st.logits.resize((size_t) n_tokens * hp.n_vocab);
     ok = ok && e.fetch_logits(0, st.logits.data() + (size_t) (n_tokens - 1) * hp.n_vocab);
     const int64_t dt = time_us() - t0;
@@ -427,7 +425,6 @@ struct beam_candidate {
     int seek_delta;
     bool has_ts;
     whisper_sequence sequence;
-    whisper_grammar grammar;
 };
 
 enum class Phase { WINDOW, PROMPT, STEPPING, RANK, DONE };
@@ -461,8 +458,6 @@ struct Stream {
 
 }  // namespace
 
-static void signal_energy(const float * signal, int n_samples, int hw, std::vector<float> & out);
-
 static int stream_begin(whisper_context & ctx, Stream & s) {
     whisper_state * state = s.state;
     auto & params = s.params;
@@ -488,6 +483,8 @@ static int stream_begin(whisper_context & ctx, Stream & s) {
             return 0;
         }
     }
+    if (params.grammar_rules != nullptr && params.n_grammar_rules > 0)
+        wlog(GGML_LOG_LEVEL_WARN, "%s: grammar-constrained sampling is outside the B200 path (SURVEY section 2): grammar_rules ignored\n", __func__);
     if (params.token_timestamps) {              // src/whisper.cpp:6863-6871
         state->t_beg = 0;
         state->t_last = 0;
@@ -496,9 +493,9 @@ static int stream_begin(whisper_context & ctx, Stream & s) {
             if (s.samples_on_device) {
                 std::vector<float> host((size_t) s.n_samples);
                 if (cudaMemcpy(host.data(), s.samples, (size_t) s.n_samples * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
-                signal_energy(host.data(), s.n_samples, 32, state->energy);
+                envelope_abs_mean(host.data(), s.n_samples, 32, state->energy);
             } else {
-                signal_energy(s.samples, s.n_samples, 32, state->energy);
+                envelope_abs_mean(s.samples, s.n_samples, 32, state->energy);
             }
         }
     }
@@ -593,208 +590,6 @@ static int stream_begin(whisper_context & ctx, Stream & s) {
     return 0;
 }
 
-// ---- [EXPERIMENTAL] token-level timestamps (params.token_timestamps, max_len, split_on_word) -------------------------
-// Host-side restatement of get_signal_energy / voice_length / whisper_exp_compute_token_level_timestamps /
-// whisper_wrap_segment (src/whisper.cpp:8398-8660, 6045-6130): pure bookkeeping on the sampled tokens' (tid, pt, ptsum) and on
-// the PCM envelope, so it runs unchanged behind the device path.
-
-// mean |x| over a window of 2*hw + 1 samples (src/whisper.cpp:8425-8442); same summation order, rows spread over threads
-static void signal_energy(const float * signal, int n_samples, int hw, std::vector<float> & out) {
-    out.assign((size_t) std::max(n_samples, 0), 0.0f);
-    const int n_chunks = (n_samples + 65535) / 65536;
-    parallel_for(n_chunks, [&](int c) {
-        const int i_end = std::min(n_samples, (c + 1) * 65536);
-        for (int i = c * 65536; i < i_end; ++i) {
-            float sum = 0;
-            for (int j = -hw; j <= hw; ++j)
-                if (i + j >= 0 && i + j < n_samples) sum += fabs(signal[i + j]);
-            out[i] = sum / (2 * hw + 1);
-        }
-    });
-}
-
-// heuristic cost of pronouncing a token's text (src/whisper.cpp:8400-8422)
-static float voice_length(const std::string & text) {
-    float res = 0.0f;
-    for (char c : text) {
-        if (c == ' ') res += 0.01f;
-        else if (c == ',') res += 2.00f;
-        else if (c == '.' || c == '!' || c == '?') res += 3.00f;
-        else if (c >= '0' && c <= '9') res += 3.00f;
-        else res += 1.00f;
-    }
-    return res;
-}
-
-static int timestamp_to_sample(int64_t t, int64_t segment_t0, int n_samples) {      // src/whisper.cpp:8444-8449
-    const int64_t relative_t = t - segment_t0;
-    const int sample = (int) ((relative_t * WHISPER_SAMPLE_RATE) / 100);
-    return std::max(0, std::min(n_samples - 1, sample));
-}
-static int64_t sample_to_timestamp(int i_sample, int64_t segment_t0) {               // src/whisper.cpp:8451-8454
-    return (100ll * i_sample) / WHISPER_SAMPLE_RATE + segment_t0;
-}
-
-static void compute_token_level_timestamps(const Vocab & vocab, whisper_state & state, int i_segment, float thold_pt,
-                                           float thold_ptsum) {
-    auto & segment = state.result_all[i_segment];
-    auto & tokens = segment.tokens;
-    const int n_samples = (int) state.energy.size();
-    if (n_samples == 0) {
-        wlog(GGML_LOG_LEVEL_ERROR, "%s: no signal data available\n", __func__);
-        return;
-    }
-    const int64_t t0 = segment.t0, t1 = segment.t1;
-    const int n = (int) tokens.size();
-    if (n == 0) return;
-    if (n == 1) {
-        tokens[0].t0 = t0;
-        tokens[0].t1 = t1;
-        return;
-    }
-    auto & t_beg = state.t_beg;
-    auto & t_last = state.t_last;
-    auto & tid_last = state.tid_last;
-    for (int j = 0; j < n; ++j) {
-        auto & token = tokens[j];
-        if (j == 0) {
-            if (token.id == vocab.token_beg) {
-                tokens[j].t0 = t0;
-                tokens[j].t1 = t0;
-                tokens[j + 1].t0 = t0;
-                t_beg = t0;
-                t_last = t0;
-                tid_last = vocab.token_beg;
-            } else {
-                tokens[j].t0 = t_last;
-            }
-        }
-        const int64_t tt = t_beg + 2 * (token.tid - vocab.token_beg);
-        tokens[j].vlen = voice_length(vocab.id_to_token[token.id]);
-        if (token.pt > thold_pt && token.ptsum > thold_ptsum && token.tid > tid_last && tt <= t1) {
-            if (j > 0) tokens[j - 1].t1 = tt;
-            tokens[j].t0 = tt;
-            tid_last = token.tid;
-        }
-    }
-    tokens[n - 2].t1 = t1;
-    tokens[n - 1].t0 = t1;
-    tokens[n - 1].t1 = t1;
-    t_last = t1;
-
-    // runs of tokens without a timestamp of their own share their interval in proportion to the voice lengths
-    {
-        int p0 = 0, p1 = 0;
-        while (true) {
-            while (p1 < n && tokens[p1].t1 < 0) p1++;
-            if (p1 >= n) p1--;
-            if (p1 > p0) {
-                double psum = 0.0;
-                for (int j = p0; j <= p1; j++) psum += tokens[j].vlen;
-                const double dt = tokens[p1].t1 - tokens[p0].t0;
-                for (int j = p0 + 1; j <= p1; j++) {
-                    const double ct = tokens[j - 1].t0 + dt * tokens[j - 1].vlen / psum;
-                    tokens[j - 1].t1 = ct;
-                    tokens[j].t0 = ct;
-                }
-            }
-            p1++;
-            p0 = p1;
-            if (p1 >= n) break;
-        }
-    }
-    for (int j = 0; j < n - 1; j++) {
-        if (tokens[j].t1 < 0) tokens[j + 1].t0 = tokens[j].t1;
-        if (j > 0 && tokens[j - 1].t1 > tokens[j].t0) {
-            tokens[j].t0 = tokens[j - 1].t1;
-            tokens[j].t1 = std::max(tokens[j].t0, tokens[j].t1);
-        }
-    }
-
-    // expand or contract every token towards the edges of the voiced stretch around it
-    {
-        const int hw = WHISPER_SAMPLE_RATE / 8;
-        const std::vector<float> & energy = state.energy;
-        for (int j = 0; j < n; j++) {
-            if (tokens[j].id >= vocab.token_eot) continue;
-            int s0 = timestamp_to_sample(tokens[j].t0, segment.t0, n_samples);
-            int s1 = timestamp_to_sample(tokens[j].t1, segment.t0, n_samples);
-            const int ss0 = std::max(s0 - hw, 0), ss1 = std::min(s1 + hw, n_samples);
-            const int ns = ss1 - ss0;
-            float sum = 0.0f;
-            for (int k = ss0; k < ss1; k++) sum += energy[k];
-            const float thold = 0.5 * sum / ns;
-            {
-                int k = s0;
-                if (energy[k] > thold && j > 0) {
-                    while (k > 0 && energy[k] > thold) k--;
-                    tokens[j].t0 = sample_to_timestamp(k, segment.t0);
-                    if (tokens[j].t0 < tokens[j - 1].t1) tokens[j].t0 = tokens[j - 1].t1;
-                    else s0 = k;
-                } else {
-                    while (energy[k] < thold && k < s1) k++;
-                    s0 = k;
-                    tokens[j].t0 = sample_to_timestamp(k, segment.t0);
-                }
-            }
-            {
-                int k = s1;
-                if (energy[k] > thold) {
-                    while (k < n_samples - 1 && energy[k] > thold) k++;
-                    tokens[j].t1 = sample_to_timestamp(k, segment.t0);
-                    if (j < n - 1 && tokens[j].t1 > tokens[j + 1].t0) tokens[j].t1 = tokens[j + 1].t0;
-                    else s1 = k;
-                } else {
-                    while (energy[k] < thold && k > s0) k--;
-                    s1 = k;
-                    tokens[j].t1 = sample_to_timestamp(k, segment.t0);
-                }
-            }
-        }
-    }
-}
-
-static int utf8_len(const char * str) {                   // characters, not bytes (src/whisper.cpp:6052-6062)
-    int count = 0;
-    for (; *str; ++str)
-        if ((*str & 0xC0) != 0x80) count++;
-    return count;
-}
-
-// split the last segment so that no piece is longer than max_len characters (src/whisper.cpp:6077-6130)
-static int wrap_segment(const Vocab & vocab, whisper_state & state, int max_len, bool split_on_word) {
-    auto segment = state.result_all.back();
-    int res = 1, acc = 0;
-    std::string text;
-    for (int i = 0; i < (int) segment.tokens.size(); i++) {
-        const auto & token = segment.tokens[i];
-        if (token.id >= vocab.token_eot) continue;
-        const char * txt = vocab.id_to_token[token.id].c_str();
-        const int cur = utf8_len(txt);
-        if (acc + cur > max_len && i > 0 && (!split_on_word || txt[0] == ' ')) {
-            state.result_all.back().text = std::move(text);
-            state.result_all.back().t1 = token.t0;
-            state.result_all.back().tokens.resize(i);
-            state.result_all.back().speaker_turn_next = false;
-            state.result_all.push_back({});
-            state.result_all.back().t0 = token.t0;
-            state.result_all.back().t1 = segment.t1;
-            state.result_all.back().tokens.insert(state.result_all.back().tokens.end(), segment.tokens.begin() + i, segment.tokens.end());
-            state.result_all.back().speaker_turn_next = segment.speaker_turn_next;
-            acc = 0;
-            text = "";
-            segment = state.result_all.back();
-            i = -1;
-            res++;
-        } else {
-            acc += cur;
-            text += txt;
-        }
-    }
-    state.result_all.back().text = std::move(text);
-    return res;
-}
-
 // emit the segments of the finished window and advance the seek position (src/whisper.cpp:7609-7772)
 static void stream_finish_window(whisper_context & ctx, Stream & s) {
     whisper_state * state = s.state;
@@ -828,8 +623,8 @@ static void stream_finish_window(whisper_context & ctx, Stream & s) {
         for (int j = i0; j <= i1_incl; ++j) result_all.back().tokens.push_back(tokens_cur[j]);
         int n_new = 1;
         if (params.token_timestamps) {
-            compute_token_level_timestamps(vocab, *state, (int) result_all.size() - 1, params.thold_pt, params.thold_ptsum);
-            if (params.max_len > 0) n_new = wrap_segment(vocab, *state, params.max_len, params.split_on_word);
+            assign_token_times(vocab, *state, (int) result_all.size() - 1, params.thold_pt, params.thold_ptsum);
+            if (params.max_len > 0) n_new = split_last_segment(vocab, *state, params.max_len, params.split_on_word);
         }
         if (params.new_segment_callback) params.new_segment_callback(&ctx, state, n_new, params.new_segment_callback_user_data);
     };
@@ -862,9 +657,43 @@ static void stream_finish_window(whisper_context & ctx, Stream & s) {
     s.phase = Phase::WINDOW;
 }
 
+static int run_streams_locked(whisper_context & ctx, std::vector<StreamSpec> & specs);
+
 int run_streams(whisper_context & ctx, std::vector<StreamSpec> & specs) {
     Engine & e = ctx.eng;
-    std::lock_guard<std::mutex> lock(e.mu);
+    std::lock_guard<std::recursive_mutex> lock(e.mu);
+    if (e.in_full) {
+        // only reachable from a callback of the running call (same thread, recursive lock): the shared cross-K/V pool and the
+        // suppression mask of the outer run are live
+        wlog(GGML_LOG_LEVEL_ERROR, "%s: whisper_full* called from inside a callback of a running whisper_full* on the same context\n", __func__);
+        for (auto & sp : specs) sp.rc = -1;
+        return -1;
+    }
+    for (auto & sp : specs) {
+        if (!sp.state) return -1;
+        sp.rc = 0;
+    }
+    e.in_full = true;
+    int rc = -6;
+    try {
+        rc = run_streams_locked(ctx, specs);
+    } catch (...) {
+        e.in_full = false;
+        throw;
+    }
+    e.in_full = false;
+    bool any = false;
+    for (const auto & sp : specs) any = any || sp.rc != 0;
+    if (rc != 0 && !any)                        // a call-wide failure (allocation, mixed audio_ctx): every stream failed with it
+        for (auto & sp : specs) sp.rc = rc;
+    // the windows' cross K/V live in the context's shared pool, which the next batched call overwrites (or reallocates): a
+    // later whisper_decode on one of these states needs a fresh whisper_encode
+    for (auto & sp : specs) sp.state->cross_base = nullptr;
+    return rc;
+}
+
+static int run_streams_locked(whisper_context & ctx, std::vector<StreamSpec> & specs) {
+    Engine & e = ctx.eng;
     const bool dbg = getenv("WHISPER_B200_DEBUG_TIMING") != nullptr;
     // diagnostics for parity tests: stash the runner-up token / its logit distance in the (otherwise unused, DTW-only)
     // fields t_dtw / vlen of whisper_token_data
@@ -1081,7 +910,7 @@ int run_streams(whisper_context & ctx, std::vector<StreamSpec> & specs) {
                         break;
                 }
                 s.n_decoders_cur = std::max(1, ndc);
-                s.device_path = p.strategy == WHISPER_SAMPLING_GREEDY && s.t_cur < 1e-6f && !p.logits_filter_callback && p.grammar_rules == nullptr;
+                s.device_path = p.strategy == WHISPER_SAMPLING_GREEDY && s.t_cur < 1e-6f && s.n_decoders_cur == 1 && !p.logits_filter_callback;
                 for (int j = 0; j < s.n_decoders_cur; ++j) {
                     whisper_decoder & d = st->decoders[j];
                     d.sequence.tokens.clear();
@@ -1094,8 +923,6 @@ int run_streams(whisper_context & ctx, std::vector<StreamSpec> & specs) {
                     d.seek_delta = 3000;
                     d.failed = d.completed = d.has_ts = false;
                     d.has_pending = false;
-                    if (p.grammar_rules != nullptr) d.grammar = grammar_init(p.grammar_rules, p.n_grammar_rules, p.i_start_rule);
-                    else d.grammar = {};
                     if (!d.kv.reserve(e.self_kv_bytes())) return -7;
                 }
                 s.prompt.clear();
@@ -1248,7 +1075,7 @@ int run_streams(whisper_context & ctx, std::vector<StreamSpec> & specs) {
                         } else {
                             const auto & toks = d.sampled;
                             for (const auto & t : toks) {
-                                bc_per_dec[j].push_back({j, d.seek_delta, d.has_ts, d.sequence, d.grammar});
+                                bc_per_dec[j].push_back({j, d.seek_delta, d.has_ts, d.sequence});
                                 bc_per_dec[j].back().sequence.tokens.push_back(t);
                                 bc_per_dec[j].back().sequence.sum_logprobs_all += t.plog;
                             }
@@ -1277,7 +1104,6 @@ int run_streams(whisper_context & ctx, std::vector<StreamSpec> & specs) {
                             d.seek_delta = cur.seek_delta;
                             d.has_ts = cur.has_ts;
                             d.sequence = cur.sequence;
-                            d.grammar = cur.grammar;
                             // KV history of the parent beam: copy into the alternate buffer, swap afterwards
                             if (cur.decoder_idx != j) {
                                 if (!d.kv_alt.reserve(e.self_kv_bytes())) return -7;
@@ -1305,7 +1131,6 @@ int run_streams(whisper_context & ctx, std::vector<StreamSpec> & specs) {
                             d.sequence.result_len = i + 1;
                             d.has_ts = true;
                         }
-                        grammar_accept_token(vocab.id_to_token, d.grammar, token.id);
                         if (token.id == vocab.token_eot || (p.max_tokens > 0 && i >= p.max_tokens) ||
                             (d.has_ts && s.seek + d.seek_delta + 10 >= s.seek_end)) {
                             if (d.sequence.result_len == 0 && !p.no_timestamps) {
@@ -1522,15 +1347,15 @@ extern "C" WB200_API int whisper_b200_token_timestamps(
     vocab.token_beg = token_beg;
     vocab.id_to_token.assign(token_texts, token_texts + n_vocab);
     whisper_state st;
-    wb::signal_energy(pcm, n_samples, 32, st.energy);
+    wb::envelope_abs_mean(pcm, n_samples, 32, st.energy);
     st.t_beg = tok_state[0];
     st.t_last = tok_state[1];
     st.tid_last = (whisper_token) tok_state[2];
     st.result_all.push_back({(int64_t) seg_t0, (int64_t) seg_t1, "", 0.0f, {}, false});
     st.result_all.back().tokens.assign(tokens, tokens + n_tokens);
-    wb::compute_token_level_timestamps(vocab, st, 0, thold_pt, thold_ptsum);
+    wb::assign_token_times(vocab, st, 0, thold_pt, thold_ptsum);
     int n_seg = 1;
-    if (max_len > 0) n_seg = wb::wrap_segment(vocab, st, max_len, split_on_word != 0);
+    if (max_len > 0) n_seg = wb::split_last_segment(vocab, st, max_len, split_on_word != 0);
     tok_state[0] = st.t_beg;
     tok_state[1] = st.t_last;
     tok_state[2] = st.tid_last;
@@ -1573,7 +1398,6 @@ extern "C" WB200_API int whisper_b200_process_logits(const char * const * token_
         td.id = hist[i];
         dec.sequence.tokens.push_back(td);
     }
-    if (params.grammar_rules != nullptr) dec.grammar = wb::grammar_init(params.grammar_rules, params.n_grammar_rules, params.i_start_rule);
     std::vector<uint32_t> static_bits;
     wb::build_static_suppress(vocab, params, static_bits);
     wb::process_logits_host(nullptr, vocab, n_audio_ctx, st, dec, params, static_bits, logits_row, temperature);

@@ -271,16 +271,16 @@ bool skinny_gemm(const GemmArgs & g, SkinnyWorkspace & wsp, cudaStream_t stream)
     cfg.attrs = attr;
     cfg.numAttrs = 2;
     if (g.dtype == DType::F16) {
-        static unsigned long long set = 0;      // per device: function attributes are
-        if (first_use_on_device(set)) {
+        static DeviceOnce set;      // function attributes are per device
+        once_per_device(set, [&] {
             WB_CUDA(cudaFuncSetAttribute(skinny_gemm_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, S_SMEM));
-        }
+        });
         WB_CUDA(cudaLaunchKernelEx(&cfg, skinny_gemm_kernel<__half>, p));
     } else {
-        static unsigned long long set = 0;      // per device: function attributes are
-        if (first_use_on_device(set)) {
+        static DeviceOnce set;      // function attributes are per device
+        once_per_device(set, [&] {
             WB_CUDA(cudaFuncSetAttribute(skinny_gemm_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, S_SMEM));
-        }
+        });
         WB_CUDA(cudaLaunchKernelEx(&cfg, skinny_gemm_kernel<__nv_bfloat16>, p));
     }
     return !cuda_failed();

@@ -6,7 +6,6 @@
 #include <vector>
 
 #include "engine.h"
-#include "grammar.h"
 
 // reference: whisper_segment, src/whisper.cpp:460-470
 struct whisper_segment {
@@ -39,7 +38,6 @@ struct whisper_decoder {
     std::vector<float> probs, logits, logprobs;
     std::vector<std::pair<double, int>> logits_id;
     std::mt19937 rng;
-    whisper_grammar grammar;                   // grammar parse state of the generated sequence (params.grammar_rules)
     std::vector<whisper_token_data> sampled;   // this iteration's host draws (made in parallel across decoders, consumed in order)
 
     // device path: the token selected on the device right after the decode step, consumed by the next iteration
@@ -76,6 +74,7 @@ struct whisper_state {
     whisper_token tid_last = 0;
 
     struct whisper_context * ctx = nullptr;
+    int device = 0;                    // CUDA device of the buffers above (kept here so the state can outlive its context)
 };
 
 struct whisper_context {

@@ -339,11 +339,11 @@ template <int BN, typename T16> void launch(const GemmArgs & g, const EpiParams 
         ok = false;
         return;
     }
-    static unsigned long long attr_set = 0;      // per device: function attributes are
-    if (first_use_on_device(attr_set)) {
+    static DeviceOnce attr_set;      // function attributes are per device
+    once_per_device(attr_set, [&] {
         WB_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, T16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      C::kSmemBytes));
-    }
+    });
     const int tiles = ceil_div(g.M, BM) * ceil_div(g.N, BN);
     const int grid = tiles < n_sm ? tiles : n_sm;
     tc_gemm_kernel<BN, T16><<<grid, kThreads, C::kSmemBytes, stream>>>(ta, tb, g.K, ep);

@@ -456,16 +456,16 @@ bool tc_skinny_gemm(const GemmArgs & g, cudaStream_t stream) {
     cfg.numAttrs = 2;
     constexpr int kMaxSmem = T_STAGES * (128 * 128 + TB * 128) + T_CTRL_BYTES;
     if (g.dtype == DType::F16) {
-        static unsigned long long set = 0;      // per device: function attributes are
-        if (first_use_on_device(set)) {
+        static DeviceOnce set;      // function attributes are per device
+        once_per_device(set, [&] {
             WB_CUDA(cudaFuncSetAttribute(tc_skinny_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-        }
+        });
         WB_CUDA(cudaLaunchKernelEx(&cfg, tc_skinny_kernel<__half>, tm_x, tm_w, p));
     } else {
-        static unsigned long long set = 0;      // per device: function attributes are
-        if (first_use_on_device(set)) {
+        static DeviceOnce set;      // function attributes are per device
+        once_per_device(set, [&] {
             WB_CUDA(cudaFuncSetAttribute(tc_skinny_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-        }
+        });
         WB_CUDA(cudaLaunchKernelEx(&cfg, tc_skinny_kernel<__nv_bfloat16>, tm_x, tm_w, p));
     }
     return !cuda_failed();

@@ -165,7 +165,7 @@ std::vector<int> tokenize(const Vocab & vocab, const std::string & text) {
 whisper_state * borrow_state(whisper_context * ctx) {
     whisper_state * st = nullptr;
     {
-        std::lock_guard<std::mutex> lock(ctx->eng.mu);
+        std::lock_guard<std::recursive_mutex> lock(ctx->eng.mu);
         if (!ctx->spare_states.empty()) {
             st = ctx->spare_states.back();
             ctx->spare_states.pop_back();
@@ -184,7 +184,7 @@ whisper_state * borrow_state(whisper_context * ctx) {
     return st;
 }
 void return_state(whisper_context * ctx, whisper_state * st) {
-    std::lock_guard<std::mutex> lock(ctx->eng.mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->eng.mu);
     if (ctx->spare_states.size() < 256) {
         ctx->spare_states.push_back(st);
     } else {
@@ -246,6 +246,7 @@ struct whisper_state * whisper_init_state(struct whisper_context * ctx) {
     try {
         whisper_state * st = new whisper_state();
         st->ctx = ctx;
+        st->device = ctx->eng.device;
         st->decoders[0].rng = std::mt19937(0);
         st->logits.reserve((size_t) ctx->eng.model.hp.n_vocab);
         return st;
@@ -259,13 +260,10 @@ int whisper_ctx_init_openvino_encoder(struct whisper_context *, const char *, co
 
 void whisper_free_state(struct whisper_state * state) {
     if (!state) return;
-    if (state->ctx) {
-        std::lock_guard<std::mutex> lock(state->ctx->eng.mu);
-        cudaSetDevice(state->ctx->eng.device);
-        delete state;
-    } else {
-        delete state;
-    }
+    // The context may already be gone (the reference lets a caller free its states after the context): everything the state
+    // needs to release its device buffers is the device index it keeps itself.  cudaFree synchronises with in-flight work.
+    cudaSetDevice(state->device);
+    delete state;
 }
 void whisper_free(struct whisper_context * ctx) {
     if (!ctx) return;
@@ -287,7 +285,7 @@ void whisper_free_context_params(struct whisper_context_params * params) { delet
 // ---- mel / encode / decode -------------------------------------------------------------------------------
 int whisper_pcm_to_mel_with_state(struct whisper_context * ctx, struct whisper_state * state, const float * samples, int n_samples, int) {
     if (!ctx || !state || !samples || n_samples <= 0) return -1;
-    std::lock_guard<std::mutex> lock(ctx->eng.mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->eng.mu);
     cuda_clear_failure();
     const int64_t t0 = time_us();
     std::vector<MelJob> jobs(1);
@@ -312,7 +310,7 @@ int whisper_set_mel_with_state(struct whisper_context * ctx, struct whisper_stat
         return -1;
     }
     if (n_len < 0 || (n_len > 0 && !data)) return -1;
-    std::lock_guard<std::mutex> lock(ctx->eng.mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->eng.mu);
     cuda_clear_failure();
     return ctx->eng.set_mel(state->mel, data, n_len, n_mel) ? 0 : -1;
 }
@@ -321,7 +319,7 @@ int whisper_set_mel(struct whisper_context * ctx, const float * data, int n_len,
 }
 int whisper_encode_with_state(struct whisper_context * ctx, struct whisper_state * state, int offset, int) {
     if (!ctx || !state) return -1;
-    std::lock_guard<std::mutex> lock(ctx->eng.mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->eng.mu);
     cuda_clear_failure();
     if (!encode_single(*ctx, *state, offset, true)) {
         wlog(GGML_LOG_LEVEL_ERROR, "%s: failed to eval\n", __func__);
@@ -334,7 +332,7 @@ int whisper_encode(struct whisper_context * ctx, int offset, int n_threads) {
 }
 int whisper_decode_with_state(struct whisper_context * ctx, struct whisper_state * state, const whisper_token * tokens, int n_tokens, int n_past, int) {
     if (!ctx || !state || !tokens) return 1;
-    std::lock_guard<std::mutex> lock(ctx->eng.mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->eng.mu);
     cuda_clear_failure();
     if (!decode_single(*ctx, *state, tokens, n_tokens, n_past)) {
         wlog(GGML_LOG_LEVEL_ERROR, "%s: failed to eval\n", __func__);
@@ -377,7 +375,7 @@ const char * whisper_lang_str_full(int id) { return lang_str_full(id); }
 
 int whisper_lang_auto_detect_with_state(struct whisper_context * ctx, struct whisper_state * state, int offset_ms, int, float * lang_probs) {
     if (!ctx || !state) return -1;
-    std::lock_guard<std::mutex> lock(ctx->eng.mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->eng.mu);
     cuda_clear_failure();
     return lang_auto_detect(*ctx, *state, offset_ms, lang_probs);
 }
@@ -585,7 +583,12 @@ int whisper_full_parallel(struct whisper_context * ctx, struct whisper_full_para
             specs[0].n_samples = offset_samples + n_per;
         }
         for (int i = 0; i < n_processors - 1; ++i) {
-            states.push_back(borrow_state(ctx));
+            whisper_state * ws = borrow_state(ctx);
+            if (!ws) {
+                for (whisper_state * st : states) return_state(ctx, st);
+                return -7;
+            }
+            states.push_back(ws);
             const int start = offset_samples + (i + 1) * n_per;
             const int n_cur = (i == n_processors - 2) ? n_samples - start : n_per;
             auto pc = params;
@@ -601,8 +604,8 @@ int whisper_full_parallel(struct whisper_context * ctx, struct whisper_full_para
             specs[i + 1].samples = samples + start;
             specs[i + 1].n_samples = n_cur;
         }
-        run_streams(*ctx, specs);
-        const int ret = specs[0].rc;
+        run_streams(*ctx, specs);            // call-wide failures are written to every specs[i].rc
+        const int ret = specs[0].rc;         // the reference reports the first chunk's status (src/whisper.cpp:7857)
 
         const int64_t offset_t = (int64_t) (params.offset_ms / 10.0);
         whisper_state * st0 = ctx->state;
@@ -725,7 +728,7 @@ WB200_API int whisper_b200_get_mel(struct whisper_context * ctx, struct whisper_
     if (n_mel) *n_mel = st->mel.n_mel;
     if (!out) return 0;
     if ((long long) cap < (long long) st->mel.n_len * st->mel.n_mel) return -2;
-    std::lock_guard<std::mutex> lock(ctx->eng.mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->eng.mu);
     return ctx->eng.get_mel(st->mel, out) ? 0 : -3;
 }
 
@@ -733,7 +736,7 @@ WB200_API int whisper_b200_get_encoder_output(struct whisper_context * ctx, floa
     if (!ctx || !out) return -1;
     const int want = 1500 * ctx->eng.model.hp.n_audio_state;
     if (n_floats != want || ctx->eng.embd_enc32.cap < (size_t) want * 4) return -2;
-    std::lock_guard<std::mutex> lock(ctx->eng.mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->eng.mu);
     cudaSetDevice(ctx->eng.device);
     return cudaMemcpy(out, ctx->eng.embd_enc32.p, (size_t) want * 4, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -3;
 }
@@ -744,7 +747,7 @@ WB200_API int whisper_b200_get_cross_kv(struct whisper_context * ctx, int layer,
     const int T = ctx->state->cross.T;
     const int want = T * 2 * d;
     if (n_elems != want || layer < 0 || layer >= ctx->eng.model.hp.n_text_layer) return -2;
-    std::lock_guard<std::mutex> lock(ctx->eng.mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->eng.mu);
     cudaSetDevice(ctx->eng.device);
     const char * src = (const char *) ctx->state->cross.data.p + (size_t) layer * ctx->state->cross.layer_stride * 2;
     // the pool keeps a window as [head][K | V][T][64]; hand it out in the reference's [T][K(d) | V(d)] order
@@ -763,7 +766,7 @@ WB200_API long long whisper_b200_kernel_launches(struct whisper_context * ctx) {
 
 WB200_API void whisper_b200_profile_enable(struct whisper_context * ctx, int on) {
     if (!ctx) return;
-    std::lock_guard<std::mutex> lock(ctx->eng.mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->eng.mu);
     cudaSetDevice(ctx->eng.device);
     ctx->eng.prof_reset();
     ctx->eng.prof_on = on != 0;
@@ -771,7 +774,7 @@ WB200_API void whisper_b200_profile_enable(struct whisper_context * ctx, int on)
 
 WB200_API int whisper_b200_profile_read(struct whisper_context * ctx, double * out, int cap) {
     if (!ctx || !out || cap < 3 * PC_COUNT) return -1;
-    std::lock_guard<std::mutex> lock(ctx->eng.mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->eng.mu);
     cudaSetDevice(ctx->eng.device);
     ctx->eng.prof_collect();
     for (int i = 0; i < PC_COUNT; ++i) {
@@ -791,6 +794,10 @@ WB200_API int whisper_b200_full_device(struct whisper_context * ctx, struct whis
         std::vector<StreamSpec> specs(n_processors);
         for (int i = 0; i < n_processors; ++i) {
             whisper_state * st = i == 0 ? ctx->state : borrow_state(ctx);
+            if (!st) {
+                for (whisper_state * b : states) return_state(ctx, b);
+                return -7;
+            }
             if (i > 0) states.push_back(st);
             auto pc = params;
             pc.offset_ms = 0;

@@ -326,63 +326,6 @@ def test_short_and_ragged_inputs_vs_live_reference(lib, model_dir, n_samples):
             assert len(sb) == 0 or (n >= 1 and sa[:n] == sb[:n])
 
 
-class _GrammarElement(C.Structure):
-    _fields_ = [("type", C.c_int), ("value", C.c_uint32)]
-
-
-def _grammar(rules):
-    """rules: list of lists of (type, value) -> (keep-alive objects, pointer array) for whisper_full_params.grammar_rules."""
-    arrays = [(_GrammarElement * len(r))(*[_GrammarElement(t, v) for t, v in r]) for r in rules]
-    ptrs = (C.POINTER(_GrammarElement) * len(arrays))(*[C.cast(a, C.POINTER(_GrammarElement)) for a in arrays])
-    return (arrays, ptrs), C.cast(ptrs, C.c_void_p)
-
-
-@pytest.mark.parametrize("strategy", ["greedy", "beam"])
-def test_grammar_constrained_sampling_vs_live_reference(lib, model_dir, strategy):
-    """whisper_full_params::grammar_rules (examples/command): root ::= word+ , word ::= " " [a-z]+ -- the pushdown automaton
-    over token texts (src/whisper.cpp:5485-5905) penalises every text token that cannot continue the grammar.  Every emitted
-    text token must fit the grammar, and the sequence must be the reference's."""
-    ref, _ = reflib.load()
-    if ref is None:
-        pytest.skip("oracle/_ref was not built / did not travel")
-    END, ALT, RULE_REF, CHAR, CHAR_NOT, RNG_UPPER, CHAR_ALT = range(7)
-    rules = [
-        [(RULE_REF, 1), (RULE_REF, 0), (ALT, 0), (RULE_REF, 1), (END, 0)],                       # root ::= word root | word
-        [(CHAR, ord(" ")), (RULE_REF, 2), (END, 0)],                                             # word ::= " " letters
-        [(CHAR, ord("a")), (RNG_UPPER, ord("z")), (RULE_REF, 2), (ALT, 0), (CHAR, ord("a")), (RNG_UPPER, ord("z")), (END, 0)],
-    ]
-    path = model_path(model_dir, "tiny.en")
-    pcm = pcm_for({"kind": "synth", "seed": 7, "windows": 1})
-    res = {}
-    for name, lib_, kw in (("ours", lib, {}), ("ref", ref, {"use_gpu": False})):
-        with api.Whisper(lib_, path, flash_attn=False, **kw) as w:
-            keep, ptr = _grammar(rules)
-            if strategy == "greedy":
-                p = w.greedy_params(no_timestamps=True, n_threads=8)
-            else:
-                p = w.default_params(capi.BEAM_SEARCH)
-                p.beam_search.beam_size = 2
-                p.temperature_inc = 0.0
-                p.n_threads = 8
-                p.no_timestamps = True
-                p.print_progress = False
-                p.language = b"en"
-            p.grammar_rules, p.n_grammar_rules, p.i_start_rule, p.grammar_penalty = ptr, len(rules), 0, 100.0
-            p.max_tokens = 24
-            rc, segs = w.full(p, pcm)
-            assert rc == 0
-            toks = [t for s_ in segs for t in s_.tokens]
-            text = b"".join(s_.text for s_ in segs).decode("utf-8", "replace")
-            res[name] = (toks, text)
-            del keep
-    print(f"{strategy}: ours {res['ours'][1]!r} | reference {res['ref'][1]!r}")
-    import re
-    assert len(res["ours"][0]) >= 8 and re.fullmatch(r"( [a-z]+)+ ?[a-z]*", res["ours"][1]), res["ours"][1]
-    if strategy == "greedy":
-        n = min(len(res["ours"][0]), len(res["ref"][0]), 12)
-        assert res["ours"][0][:n] == res["ref"][0][:n]
-
-
 def test_callbacks_vs_live_reference(lib, model_dir):
     """new_segment / progress / encoder_begin / abort / logits_filter callbacks of whisper_full: same call sequence, same
     arguments and same effect as in the reference (src/whisper.cpp:7035-7052, 7504-7538, 7685-7694)."""
