@@ -102,6 +102,55 @@ WB200_API double whisper_b200_kernel_gemm_bench(int dtype, int M, int N, int K, 
  * 2 self-attention at position aux, 3 KV append; R rows of width d. */
 WB200_API double whisper_b200_kernel_step_bench(int which, int dtype, int R, int d, int aux, int iters);
 
+/* ---- multi-GPU: a group of contexts, one model replica per GPU ------------------------------------------------------------
+ * whisper_full_parallel (reference src/whisper.cpp:7801-7929) splits the audio into n_processors chunks and decodes them
+ * independently; whisper_b200_group_full_parallel does the same split, deals the chunks out to the GPUs of the group in
+ * contiguous blocks (chunk i -> GPU floor(i * n_gpus / n_processors)), runs one batch per GPU on one worker thread each -- no
+ * collective on the path -- and gathers the segments on the host in chunk order with the reference's timestamp fix-up
+ * (7879-7889).  The result is read from context 0 with the whisper_full_get_* accessors and equals what whisper_full_parallel
+ * produces on one GPU.  devices == NULL: the first n_devices visible GPUs (n_devices <= 0: all of them). */
+struct whisper_b200_group;
+WB200_API struct whisper_b200_group * whisper_b200_group_init_from_file(const char * path_model, struct whisper_context_params params,
+                                                                        const int * devices, int n_devices);
+WB200_API void whisper_b200_group_free(struct whisper_b200_group * g);
+WB200_API int whisper_b200_group_size(struct whisper_b200_group * g);
+WB200_API struct whisper_context * whisper_b200_group_context(struct whisper_b200_group * g, int i);
+WB200_API int whisper_b200_group_full_parallel(struct whisper_b200_group * g, struct whisper_full_params params, const float * samples,
+                                               int n_samples, int n_processors);
+/* GPU index (0 .. n_gpus-1) that owns chunk `chunk` of n_chunks; host logic only -- needs no device. */
+WB200_API int whisper_b200_partition_owner(int chunk, int n_chunks, int n_gpus);
+
+/* The on-device logit rules + token selection kernel (csrc/dec_kernels.cu: whisper_process_logits + whisper_sample_token /
+ * whisper_sample_token_topk, src/whisper.cpp:6177-6592) on explicit logits rows and decoder states.
+ * logits: host [n_logit_rows][n_vocab] f32.  rows[r].logits_row picks the row; n_tokens / last / penult / has_ts / seek_delta are
+ * the decoder state the rules read; temperature > 0 divides the logits; n_draws == 0 -> arg-max into out[r], else n_draws
+ * categorical draws into draws[draw_off ..] from uniforms[draw_off ..] (u in [0,1), what std::discrete_distribution would take
+ * from the decoder's generator), out[r] then carries tid / pt / ptsum only.  static_mask: (n_vocab + 31) / 32 words, bit = token
+ * suppressed at every step (may be NULL).  Returns 0, or a negative error. */
+struct whisper_b200_sample_row {
+    int logits_row, n_tokens, last, penult, has_ts, seek_delta;
+    float temperature;
+    int n_draws, draw_off, tid_default;
+};
+struct whisper_b200_sample_params {
+    int n_vocab, token_eot, token_beg, token_space, suppress_blank, no_timestamps;
+    float max_initial_ts;
+    int tid0;
+};
+struct whisper_b200_sample_out {
+    int id, tid;
+    float p, plog, pt, ptsum;
+    int runner_up;
+    float gap;
+};
+struct whisper_b200_draw_out {
+    int id;
+    float p, plog;
+};
+WB200_API int whisper_b200_kernel_sample(const float * logits, int n_logit_rows, const struct whisper_b200_sample_row * rows, int n_rows,
+                                         const uint32_t * static_mask, struct whisper_b200_sample_params prm, const double * uniforms,
+                                         int n_uniforms, struct whisper_b200_sample_out * out, struct whisper_b200_draw_out * draws);
+
 /* Stream-K geometry of one GEMM phase of the persistent decoder-step kernel (csrc/dec_chain.h, host logic only -- needs
  * no device): out[0..4] = {tiles, k-blocks per tile, units, CTAs taking part, partial-tile slots per output tile}.
  * direct != 0: every CTA owns one whole 128-column tile.  Returns 0, or -1 for shapes the kernel does not take. */

@@ -39,6 +39,12 @@ EXT_PROTOTYPES = {
     "whisper_b200_profile_read": (_C.c_int, [_C.c_void_p, _C.POINTER(_C.c_double), _C.c_int]),
     "whisper_b200_chain_geometry": (_C.c_int, [_C.c_int] * 6 + [_IP]),
     "whisper_b200_dequantize_blocks": (_C.c_longlong, [_C.c_int, _C.c_void_p, _C.c_longlong, _U16P]),
+    "whisper_b200_partition_owner": (_C.c_int, [_C.c_int, _C.c_int, _C.c_int]),
+    "whisper_b200_group_init_from_file": (_C.c_void_p, [_C.c_char_p, capi.whisper_context_params, _IP, _C.c_int]),
+    "whisper_b200_group_free": (None, [_C.c_void_p]),
+    "whisper_b200_group_size": (_C.c_int, [_C.c_void_p]),
+    "whisper_b200_group_context": (_C.c_void_p, [_C.c_void_p, _C.c_int]),
+    "whisper_b200_group_full_parallel": (_C.c_int, [_C.c_void_p, capi.whisper_full_params, _FP, _C.c_int, _C.c_int]),
     "whisper_b200_token_timestamps": (_C.c_int, [_C.c_void_p, _C.c_int, _C.c_int, _C.c_int, _FP, _C.c_int, _C.c_longlong, _C.c_longlong,
                                                  _C.c_void_p, _C.c_int, _C.c_float, _C.c_float, _C.POINTER(_C.c_longlong), _C.c_int, _C.c_int,
                                                  _C.POINTER(_C.c_longlong), _IP, _C.c_int]),

@@ -522,7 +522,7 @@ constexpr int SAMPLE_SMEM = SAMPLE_HALF * 4;   // the CTA's half row after the r
 
 struct SampleXchg {                            // one slot per cluster-wide reduction: slots are never reused inside a launch
     float f[4];
-    double d;
+    double d, d2;
     ArgMax a[2];
 };
 
@@ -533,9 +533,18 @@ struct SampleXchg {                            // one slot per cluster-wide redu
 // Block-wide results are exchanged through DSMEM and combined in rank order by both CTAs.  The log-softmax, the
 // timestamp-mass rule and the probabilities follow the reference's own formulation step by step
 // (src/whisper.cpp:6137-6171, 6336-6361); arg-max / timestamp statistics are whisper_sample_token's (6460-6517).
+//
+// Rows with n_draws > 0 do not take the arg-max but draw from the categorical distribution of the processed row
+// (whisper_sample_token with best = false, whisper_sample_token_topk: src/whisper.cpp:6504-6511, 6519-6592).  The reference
+// draws through std::discrete_distribution, i.e. index = lower_bound(cp, u) with cp the running sum (in double, index order)
+// of probs / sum(probs) and u = generate_canonical<double, 53>(mt19937).  The host draws the u's from each decoder's own
+// mt19937 -- the only stateful part -- and the kernel does the rest: probabilities into shared memory, their sum, a block /
+// cluster-wide scan of the normalised per-thread sums in double (each thread owns 52 consecutive tokens), and for every u the
+// one thread whose scan interval contains it walks its tokens.  Logits never leave the device.
 __global__ void __cluster_dims__(SAMPLE_CTAS, 1, 1) __launch_bounds__(SAMPLE_THREADS)
-sample_greedy_kernel(float * __restrict__ logits, int ld, const SampleRow * __restrict__ srows,
-                     const uint32_t * __restrict__ static_mask, SampleParams prm, SampleOut * __restrict__ outs) {
+sample_kernel(const float * __restrict__ logits, int ld, const SampleRow * __restrict__ srows,
+              const uint32_t * __restrict__ static_mask, SampleParams prm, SampleOut * __restrict__ outs,
+              const double * __restrict__ uniforms, DrawOut * __restrict__ draws) {
     extern __shared__ __align__(16) float sh_v[];          // [SAMPLE_HALF]
     __shared__ float sh_f[SAMPLE_THREADS / 32];
     __shared__ double sh_d[SAMPLE_THREADS / 32];
@@ -565,8 +574,8 @@ sample_greedy_kernel(float * __restrict__ logits, int ld, const SampleRow * __re
     const bool pen_ts = sr.n_tokens < 2 || sr.penult >= beg;
     const int init_lim = (is_initial && prm.max_initial_ts > 0.0f) ? beg + prm.tid0 + 1 : V;
     const int mono_lim = sr.has_ts ? beg + sr.seek_delta / 2 : beg;
-    const bool use_temp = prm.temperature > 0.0f;
-    const float temp = use_temp ? prm.temperature : 1.0f;
+    const bool use_temp = sr.temperature > 0.0f;
+    const float temp = use_temp ? sr.temperature : 1.0f;
     auto allowed = [&](int i, uint32_t mask_word) {
         bool kill = (mask_word >> (i & 31)) & 1u;
         if (is_initial && prm.suppress_blank && (i == eot || i == prm.token_space)) kill = true;
@@ -677,6 +686,112 @@ sample_greedy_kernel(float * __restrict__ logits, int ld, const SampleRow * __re
         mask_text = timestamp_logprob > mx_text - logZ;
     }
 
+    if (sr.n_draws > 0) {
+        // ---- categorical draws ----
+        constexpr int PER = SAMPLE_HALF / SAMPLE_THREADS;         // 52 consecutive tokens per thread
+        static_assert(PER % 4 == 0 && PER * SAMPLE_THREADS == SAMPLE_HALF, "chunking of the half row");
+        const int e0 = tid * PER;
+        float4 * v4 = reinterpret_cast<float4 *>(sh_v) + e0 / 4;
+        // probabilities (0 for suppressed tokens) replace the logits in shared memory; their sum and the timestamp statistics
+        double loc = 0.0, sum_ts = 0.0;
+        ArgMax best_ts = {0.0f, 0x7fffffff};
+#pragma unroll 1
+        for (int j = 0; j < PER / 4; ++j) {
+            const float4 t = v4[j];
+            float x[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int i = lo + e0 + 4 * j + c;
+                float pr = 0.0f;
+                if (x[c] > -INFINITY && !(mask_text && i < beg)) pr = expf(x[c] - logZ);
+                x[c] = pr;
+                loc += (double) pr;
+                if (i >= beg && pr > 0.0f) {
+                    best_ts = amax(best_ts, ArgMax{pr, i});
+                    sum_ts += (double) pr;
+                }
+            }
+            v4[j] = make_float4(x[0], x[1], x[2], x[3]);
+        }
+        const double cta_total = block_sum_d<SAMPLE_THREADS>(loc, sh_d);
+        best_ts = block_amax<SAMPLE_THREADS>(best_ts, sh_a);
+        sum_ts = block_sum_d<SAMPLE_THREADS>(sum_ts, sh_d);
+        if (tid == 0) {
+            sh_x[3].d = cta_total; sh_x[3].d2 = sum_ts; sh_x[3].a[1] = best_ts;
+        }
+        cluster.sync();
+        const double total = rank == 0 ? cta_total + peer_x[3].d : peer_x[3].d + cta_total;
+        best_ts = amax(best_ts, peer_x[3].a[1]);
+        sum_ts = rank == 0 ? sum_ts + peer_x[3].d2 : peer_x[3].d2 + sum_ts;
+
+        // scan of the normalised per-thread sums.  excl of a thread IS the incl of its predecessor (same value, not a
+        // recomputation), across lanes, warps and the two CTAs, so every u has exactly one owner.
+        double locq = 0.0;
+#pragma unroll 1
+        for (int j = 0; j < PER / 4; ++j) {
+            const float4 t = v4[j];
+            locq += (double) t.x / total;
+            locq += (double) t.y / total;
+            locq += (double) t.z / total;
+            locq += (double) t.w / total;
+        }
+        const int lane = tid & 31, warp = tid >> 5;
+        double v = locq;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double t = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += t;
+        }
+        const double vprev = __shfl_up_sync(0xffffffffu, v, 1);
+        if (lane == 31) sh_d[warp] = v;
+        __syncthreads();
+        double wp = 0.0;
+        for (int w = 0; w < warp; ++w) wp += sh_d[w];
+        double cta_q = 0.0;
+        for (int w = 0; w < SAMPLE_THREADS / 32; ++w) cta_q += sh_d[w];
+        if (tid == 0) sh_x[4].d = cta_q;
+        cluster.sync();
+        const double base = rank == 0 ? 0.0 : peer_x[4].d;
+        const double excl = base + (lane == 0 ? wp : wp + vprev), incl = base + (wp + v);
+        const bool first_thread = rank == 0 && tid == 0, last_thread = rank == SAMPLE_CTAS - 1 && tid == SAMPLE_THREADS - 1;
+        for (int dr = 0; dr < sr.n_draws; ++dr) {
+            const double u = uniforms[sr.draw_off + dr];
+            const bool overflow = last_thread && u > incl;          // cp.back() is forced to 1 in the reference: the last token
+            if (!((u > excl && u <= incl) || (first_thread && u <= excl) || overflow)) continue;
+            int found = -1, last_nz = -1;
+            double c = excl;
+            for (int e = 0; e < PER; ++e) {
+                const float pr = sh_v[e0 + e];
+                if (pr > 0.0f) last_nz = e;
+                c += (double) pr / total;
+                if (found < 0 && c >= u) found = e;
+            }
+            int id;
+            if (found >= 0) id = lo + e0 + found;
+            else if (overflow) id = V - 1;
+            else id = lo + e0 + (last_nz >= 0 ? last_nz : PER - 1);      // walk and scan associate differently: last ulp
+            if (id >= V) id = V - 1;
+            DrawOut o;
+            o.id = id;
+            o.p = (id >= lo && id < lo + SAMPLE_HALF) ? sh_v[id - lo] : 0.0f;
+            float lx = l[id];
+            if (use_temp) lx = lx / temp;
+            o.plog = o.p > 0.0f ? lx - logZ : -INFINITY;
+            draws[sr.draw_off + dr] = o;
+        }
+        if (tid == 0 && rank == 0) {
+            SampleOut o;
+            o.id = 0; o.p = 0.0f; o.plog = 0.0f;
+            o.tid = best_ts.i == 0x7fffffff ? sr.tid_default : best_ts.i;
+            o.pt = (float) ((double) (best_ts.i == 0x7fffffff ? 0.0f : best_ts.v) / (sum_ts + 1e-10));
+            o.ptsum = (float) sum_ts;
+            o.runner_up = -1; o.gap = INFINITY;
+            outs[r] = o;
+        }
+        cluster.sync();       // the peer may still be reading this CTA's exchange slots
+        return;
+    }
+
     // Greedy arg-max = first index of the maximal PROBABILITY expf(logit - logZ) (src/whisper.cpp:6460-6517).  expf is
     // monotone, so the winner is within rounding distance of its thread's largest logit: each thread finds its two largest
     // logits (cheap compares), evaluates probabilities only for the elements that close to its maximum, and the block /
@@ -753,7 +868,7 @@ sample_greedy_kernel(float * __restrict__ logits, int ld, const SampleRow * __re
         o.id = best.i == 0x7fffffff ? 0 : best.i;
         o.p = best.i == 0x7fffffff ? 0.0f : best.v;
         o.plog = best.i == 0x7fffffff ? 0.0f : (value(o.id) - logZ);
-        o.tid = best_ts.i == 0x7fffffff ? 0 : best_ts.i;
+        o.tid = best_ts.i == 0x7fffffff ? sr.tid_default : best_ts.i;
         o.pt = (float) ((double) (best_ts.i == 0x7fffffff ? 0.0f : best_ts.v) / (sum_ts + 1e-10));
         o.ptsum = (float) sum_ts;
         if (o.id >= beg) {
@@ -879,8 +994,8 @@ void dec_cross_attn(DType dt, const void * q, const DecRow * d_rows, int R, int 
     WB_CUDA(cudaGetLastError());
 }
 
-void dec_sample_greedy(float * logits, int ld, const SampleRow * d_srows, int R, const uint32_t * d_static_mask,
-                       const SampleParams & prm, SampleOut * d_out, cudaStream_t st) {
+void dec_sample(const float * logits, int ld, const SampleRow * d_srows, int R, const uint32_t * d_static_mask,
+                const SampleParams & prm, SampleOut * d_out, const double * d_uniforms, DrawOut * d_draws, cudaStream_t st) {
     if (R <= 0) return;
     if (prm.n_vocab > SAMPLE_CTAS * SAMPLE_HALF) {       // model_load() rejects such files; never a silent truncation
         cuda_fail(cudaErrorInvalidValue, "n_vocab <= 53248 (greedy selection kernel)", __FILE__, __LINE__);
@@ -888,10 +1003,10 @@ void dec_sample_greedy(float * logits, int ld, const SampleRow * d_srows, int R,
     }
     static DeviceOnce set;      // function attributes are per device
     once_per_device(set, [&] {
-        WB_CUDA(cudaFuncSetAttribute(sample_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SAMPLE_SMEM));
+        WB_CUDA(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SAMPLE_SMEM));
     });
-    launch_pdl(sample_greedy_kernel, dim3(R * SAMPLE_CTAS), dim3(SAMPLE_THREADS), SAMPLE_SMEM, st, logits, ld, d_srows, d_static_mask, prm,
-               d_out);
+    launch_pdl(sample_kernel, dim3(R * SAMPLE_CTAS), dim3(SAMPLE_THREADS), SAMPLE_SMEM, st, logits, ld, d_srows, d_static_mask, prm,
+               d_out, d_uniforms, d_draws);
     WB_CUDA(cudaGetLastError());
 }
 

@@ -16,12 +16,17 @@ struct DecRow {
 
 // Per-row decoder state the logit rules depend on (reference whisper_decoder, src/whisper.cpp:797-820).
 struct SampleRow {
-    int logits_row;   // row of the logits buffer
+    int logits_row;   // row of the logits buffer (several decoders may share one: the fan-out after the prompt pass)
     int n_tokens;     // tokens sampled so far in this window (0 -> "initial")
     int last;         // last / penultimate sampled token ids (valid if n_tokens >= 1 / 2)
     int penult;
     int has_ts;
     int seek_delta;
+    float temperature;   // > 0: logits are divided by it first (whisper_process_logits, src/whisper.cpp:6199-6203)
+    int n_draws;         // 0: arg-max (whisper_sample_token, best); k > 0: k draws from the categorical distribution of the
+                         // processed row, one per uniform (whisper_sample_token best = false / whisper_sample_token_topk)
+    int draw_off;        // first of this row's n_draws entries in the uniforms / draws arrays
+    int tid_default;     // tid reported when no timestamp token has probability mass (0 for sample_token, token_beg for topk)
 };
 
 struct SampleParams {
@@ -30,7 +35,11 @@ struct SampleParams {
     int suppress_blank, no_timestamps;
     float max_initial_ts;
     int tid0;            // round(max_initial_ts / 0.02)
-    float temperature;
+};
+
+struct DrawOut {         // one categorical draw: token, its probability and log-probability
+    int id;
+    float p, plog;
 };
 
 struct SampleOut {       // the float fields of whisper_token_data (include/whisper.h)
@@ -53,8 +62,11 @@ constexpr int DEC_CROSS_GROUP_MAX = 4;
 void dec_cross_attn(DType dt, const void * q, const DecRow * d_rows, int R, int d, int n_head, size_t layer_off_elems,
                     int T, int n_phantom, void * out, cudaStream_t st, const SplitIn * q_split = nullptr,
                     const int2 * d_groups = nullptr, int n_groups = 0);
-void dec_sample_greedy(float * logits, int ld, const SampleRow * d_srows, int R, const uint32_t * d_static_mask,
-                       const SampleParams & prm, SampleOut * d_out, cudaStream_t st);
+// Logit rules + selection for R decoder rows: arg-max rows fill d_out[r] completely; rows with n_draws > 0 fill the timestamp
+// statistics of d_out[r] (tid, pt, ptsum) and d_draws[draw_off .. draw_off + n_draws) from d_uniforms[draw_off ..]
+// (uniforms in [0, 1) drawn by the host from each decoder's mt19937, exactly as std::discrete_distribution consumes them).
+void dec_sample(const float * logits, int ld, const SampleRow * d_srows, int R, const uint32_t * d_static_mask,
+                const SampleParams & prm, SampleOut * d_out, const double * d_uniforms, DrawOut * d_draws, cudaStream_t st);
 void dec_token_prob(const float * logits, int ld, const SampleRow * d_srows, int R, int n_vocab, int token, float * d_out,
                     cudaStream_t st);
 

@@ -801,25 +801,31 @@ bool Engine::fetch_logits_rows(int row0, int n_rows, float * out) {
     return !cuda_failed();
 }
 
-bool Engine::sample_greedy(const std::vector<SampleRow> & srows, const uint32_t * d_mask, const SampleParams & prm,
-                           std::vector<SampleOut> & out) {
+bool Engine::sample(const std::vector<SampleRow> & srows, const std::vector<double> & uniforms, const uint32_t * d_mask,
+                    const SampleParams & prm, std::vector<SampleOut> & out, std::vector<DrawOut> & draws) {
     const int R = (int) srows.size();
+    const size_t n_u = uniforms.size();
     out.resize(R);
+    draws.resize(n_u);
     if (R == 0) return true;
-    const size_t in_b = R * sizeof(SampleRow), out_b = R * sizeof(SampleOut);
-    if (!meta.reserve(round_up<size_t>(in_b, 256) + out_b)) return false;
-    SampleRow * d_in = (SampleRow *) meta.p;
-    SampleOut * d_out = (SampleOut *) ((char *) meta.p + round_up<size_t>(in_b, 256));
-    char * hb = (char *) pinned(1, in_b + out_b);
-    memcpy(hb, srows.data(), in_b);
-    WB_CUDA(cudaMemcpyAsync(d_in, hb, in_b, cudaMemcpyHostToDevice, stream));
+    // device / pinned layout: [rows | uniforms | outs | draws], each part 256-byte aligned
+    const size_t in_b = round_up<size_t>(R * sizeof(SampleRow), 256), u_b = round_up<size_t>(n_u * sizeof(double), 256);
+    const size_t out_b = round_up<size_t>(R * sizeof(SampleOut), 256), dr_b = round_up<size_t>(n_u * sizeof(DrawOut), 256);
+    if (!meta.reserve(in_b + u_b + out_b + dr_b)) return false;
+    char * dev = (char *) meta.p;
+    char * hb = (char *) pinned(1, in_b + u_b + out_b + dr_b);
+    memcpy(hb, srows.data(), R * sizeof(SampleRow));
+    if (n_u) memcpy(hb + in_b, uniforms.data(), n_u * sizeof(double));
+    WB_CUDA(cudaMemcpyAsync(dev, hb, in_b + (n_u ? u_b : 0), cudaMemcpyHostToDevice, stream));
     prof_begin(PC_SAMPLE, (double) R * model.hp.n_vocab * 4.0 * 5.0);
-    dec_sample_greedy((float *) logits.p, ld_logits, d_in, R, d_mask, prm, d_out, stream);
+    dec_sample((const float *) logits.p, ld_logits, (const SampleRow *) dev, R, d_mask, prm, (SampleOut *) (dev + in_b + u_b),
+               (const double *) (dev + in_b), (DrawOut *) (dev + in_b + u_b + out_b), stream);
     prof_end();
     n_kernel_launches += 1;
-    WB_CUDA(cudaMemcpyAsync(hb + in_b, d_out, out_b, cudaMemcpyDeviceToHost, stream));
+    WB_CUDA(cudaMemcpyAsync(hb + in_b + u_b, dev + in_b + u_b, out_b + (n_u ? dr_b : 0), cudaMemcpyDeviceToHost, stream));
     WB_CUDA(cudaStreamSynchronize(stream));
-    memcpy(out.data(), hb + in_b, out_b);
+    memcpy(out.data(), hb + in_b + u_b, R * sizeof(SampleOut));
+    if (n_u) memcpy(draws.data(), hb + in_b + u_b + out_b, n_u * sizeof(DrawOut));
     return !cuda_failed();
 }
 

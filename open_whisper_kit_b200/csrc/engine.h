@@ -142,8 +142,10 @@ struct Engine {
     bool chain_usable(int R);
     bool fetch_logits(int row, float * out);                         // D2H one row (n_vocab floats)
     bool fetch_logits_rows(int row0, int n_rows, float * out);       // D2H rows [row0, row0 + n_rows) packed [n_rows][n_vocab]
-    bool sample_greedy(const std::vector<SampleRow> & srows, const uint32_t * d_mask, const SampleParams & prm,
-                       std::vector<SampleOut> & out);
+    // logit rules + arg-max / categorical draws on the rows of the last decode(); uniforms: one per requested draw, indexed by
+    // SampleRow::draw_off (empty when every row is an arg-max row)
+    bool sample(const std::vector<SampleRow> & srows, const std::vector<double> & uniforms, const uint32_t * d_mask,
+                const SampleParams & prm, std::vector<SampleOut> & out, std::vector<DrawOut> & draws);
     bool token_prob(const std::vector<SampleRow> & srows, int token, std::vector<float> & out);
     bool kv_copy_prefix(const void * src, void * dst, int n_pos);    // self-KV: positions [0, n_pos) of every layer
 

@@ -108,9 +108,9 @@ static void compute_logprobs(const float * logits, int n, std::vector<float> & l
 // The host sampling path works per decoder on private state (its logits / probs copies, its mt19937), as the reference's
 // worker threads do (src/whisper.cpp:7504-7538): run fn(0..n-1) on up to 32 host threads.  Exactly the same arithmetic
 // per item as the serial loop, so results do not depend on the thread count.
-template <typename F> static void parallel_for(int n, F && fn) {
+template <typename F> static void parallel_for(int n, F && fn, int max_threads = 32) {
     const int hw = (int) std::thread::hardware_concurrency();
-    const int n_thr = std::max(1, std::min(n, std::min(hw > 0 ? hw : 4, 32)));
+    const int n_thr = std::max(1, std::min(n, std::min(hw > 0 ? hw : 4, std::max(1, max_threads))));
     if (n_thr <= 1) {
         for (int i = 0; i < n; ++i) fn(i);
         return;
@@ -451,6 +451,7 @@ struct Stream {
     float t_cur = 0.0f;
     int n_decoders_cur = 1;
     bool device_path = false;
+    int k_draws = 0;             // device path: categorical draws per live decoder and step (0 = arg-max)
     int best_decoder_id = 0;
     int window = 0;              // index into the shared cross pool
     bool no_timestamps = false;
@@ -813,10 +814,78 @@ static int run_streams_locked(whisper_context & ctx, std::vector<StreamSpec> & s
     struct CrossTReset { Engine & e; ~CrossTReset() { e.cross_T = 1500; } } cross_t_reset{e};
     const int n_max = hp.n_text_ctx / 2 - 4;
     std::vector<float> logits_host((size_t) hp.n_vocab), logits_rows_host;
+    const int host_threads = S[0].params.logits_filter_callback ? std::max(1, S[0].params.n_threads) : 32;
 
     auto fail_stream = [&](Stream & s, int rc) {
         s.rc = rc;
         s.phase = Phase::DONE;
+    };
+
+    // Device-side selection for a set of (stream, decoder, logits row) triples: builds the per-row decoder state the rules need,
+    // draws the uniforms of the sampling rows from the decoders' own mt19937 in row order (std::discrete_distribution consumes
+    // generate_canonical<double, 53> per draw, i.e. the reference's RNG streams stay in step), runs dec_kernels.cu's sampler and
+    // hands the result to the decoders: `pending` for arg-max rows, `sampled` for drawing rows.
+    struct SelItem { int si, j, logits_row; };
+    auto device_select = [&](const std::vector<SelItem> & items) -> bool {
+        if (items.empty()) return true;
+        std::vector<SampleRow> sr;
+        std::vector<double> uniforms;
+        sr.reserve(items.size());
+        for (const auto & it : items) {
+            Stream & s = S[it.si];
+            whisper_decoder & d = s.state->decoders[it.j];
+            const auto & tk = d.sequence.tokens;
+            const int n = (int) tk.size();
+            SampleRow r = {};
+            r.logits_row = it.logits_row;
+            r.n_tokens = n;
+            r.last = n > 0 ? tk[n - 1].id : 0;
+            r.penult = n > 1 ? tk[n - 2].id : 0;
+            r.has_ts = d.has_ts ? 1 : 0;
+            r.seek_delta = d.seek_delta;
+            r.temperature = s.t_cur;
+            r.n_draws = s.k_draws;
+            r.draw_off = (int) uniforms.size();
+            r.tid_default = s.params.strategy == WHISPER_SAMPLING_BEAM_SEARCH ? vocab.token_beg : 0;
+            for (int q = 0; q < s.k_draws; ++q) uniforms.push_back(std::generate_canonical<double, 53>(d.rng));
+            sr.push_back(r);
+        }
+        const auto & p = S[items[0].si].params;       // the streams of one call share the parameters that enter the kernel
+        SampleParams prm;
+        prm.n_vocab = hp.n_vocab;
+        prm.token_eot = vocab.token_eot;
+        prm.token_beg = vocab.token_beg;
+        prm.token_space = space_id;
+        prm.suppress_blank = p.suppress_blank;
+        prm.no_timestamps = p.no_timestamps;
+        prm.max_initial_ts = p.max_initial_ts;
+        prm.tid0 = (int) std::round(p.max_initial_ts / (30.0f / hp.n_audio_ctx));
+        std::vector<SampleOut> so;
+        std::vector<DrawOut> dr;
+        if (!e.sample(sr, uniforms, (const uint32_t *) ctx.static_mask.p, prm, so, dr)) return false;
+        for (size_t q = 0; q < items.size(); ++q) {
+            whisper_decoder & d = S[items[q].si].state->decoders[items[q].j];
+            if (sr[q].n_draws == 0) {
+                d.pending = {so[q].id, so[q].tid, so[q].p, so[q].plog, so[q].pt, so[q].ptsum, -1, -1, -1, 0.0f};
+                if (dbg_gaps) {
+                    d.pending.t_dtw = so[q].runner_up;
+                    d.pending.vlen = so[q].gap;
+                }
+                d.has_pending = true;
+            } else {
+                d.sampled.clear();
+                for (int k = 0; k < sr[q].n_draws; ++k) {
+                    const DrawOut & o = dr[sr[q].draw_off + k];
+                    whisper_token_data t = {o.id, so[q].tid, o.p, o.plog, so[q].pt, so[q].ptsum, -1, -1, -1, 0.0f};
+                    if (t.id >= vocab.token_beg) {
+                        t.tid = t.id;
+                        t.pt = t.p;
+                    }
+                    d.sampled.push_back(t);
+                }
+            }
+        }
+        return true;
     };
 
     while (true) {
@@ -910,7 +979,13 @@ static int run_streams_locked(whisper_context & ctx, std::vector<StreamSpec> & s
                         break;
                 }
                 s.n_decoders_cur = std::max(1, ndc);
-                s.device_path = p.strategy == WHISPER_SAMPLING_GREEDY && s.t_cur < 1e-6f && s.n_decoders_cur == 1 && !p.logits_filter_callback;
+                // Selection runs on the device unless the user wants to see (and edit) the logits.  Greedy strategy: arg-max below
+                // temperature 1e-6, else one categorical draw per decoder; beam-search strategy: beam_size draws per beam at any
+                // temperature (src/whisper.cpp:7247-7268).  (Several decoders that would all take the arg-max -- 0 < t < 1e-6 with
+                // best_of > 1 -- are left to the host path.)
+                const bool argmax = p.strategy == WHISPER_SAMPLING_GREEDY && s.t_cur < 1e-6f;
+                s.k_draws = argmax ? 0 : (p.strategy == WHISPER_SAMPLING_BEAM_SEARCH ? p.beam_search.beam_size : 1);
+                s.device_path = !p.logits_filter_callback && !(argmax && s.n_decoders_cur > 1) && s.k_draws <= WHISPER_MAX_DECODERS;
                 for (int j = 0; j < s.n_decoders_cur; ++j) {
                     whisper_decoder & d = st->decoders[j];
                     d.sequence.tokens.clear();
@@ -972,15 +1047,16 @@ static int run_streams_locked(whisper_context & ctx, std::vector<StreamSpec> & s
             // B2. process the prompt logits for decoder 0 and fan out to the other decoders
             {
                 const int64_t t0 = time_us();
-                std::vector<SampleRow> sr;
-                std::vector<int> sr_stream;
+                std::vector<SelItem> sel;
                 for (size_t a = 0; a < act.size(); ++a) {
                     Stream & s = S[act[a]];
                     if (s.phase != Phase::STEPPING) continue;
                     whisper_state * st = s.state;
+                    for (int j = 1; j < s.n_decoders_cur; ++j)
+                        e.kv_copy_prefix(st->decoders[0].kv.p, st->decoders[j].kv.p, (int) s.prompt.size());
                     if (s.device_path) {
-                        sr.push_back({(int) a, 0, 0, 0, 0, 3000});
-                        sr_stream.push_back(act[a]);
+                        // every decoder of the stream selects from the same processed prompt row (with its own RNG)
+                        for (int j = 0; j < s.n_decoders_cur; ++j) sel.push_back({act[a], j, (int) a});
                     } else {
                         if (!e.fetch_logits((int) a, logits_host.data())) {
                             fail_stream(s, -8);
@@ -989,41 +1065,14 @@ static int run_streams_locked(whisper_context & ctx, std::vector<StreamSpec> & s
                         process_logits_host(&ctx, vocab, hp.n_audio_ctx, *st, st->decoders[0], s.params, static_bits, logits_host.data(), s.t_cur);
                         for (int j = 1; j < s.n_decoders_cur; ++j) {
                             whisper_decoder & d = st->decoders[j];
-                            e.kv_copy_prefix(st->decoders[0].kv.p, d.kv.p, (int) s.prompt.size());
                             d.probs = st->decoders[0].probs;
                             d.logits = st->decoders[0].logits;
                             d.logprobs = st->decoders[0].logprobs;
                         }
                     }
                 }
-                if (!sr.empty()) {
-                    // all device-path streams of one call share the parameters that enter the kernel
-                    const auto & p = S[sr_stream[0]].params;
-                    SampleParams prm;
-                    prm.n_vocab = hp.n_vocab;
-                    prm.token_eot = vocab.token_eot;
-                    prm.token_beg = vocab.token_beg;
-                    prm.token_space = space_id;
-                    prm.suppress_blank = p.suppress_blank;
-                    prm.no_timestamps = p.no_timestamps;
-                    prm.max_initial_ts = p.max_initial_ts;
-                    prm.tid0 = (int) std::round(p.max_initial_ts / (30.0f / hp.n_audio_ctx));
-                    prm.temperature = 0.0f;
-                    std::vector<SampleOut> so;
-                    if (!e.sample_greedy(sr, (const uint32_t *) ctx.static_mask.p, prm, so)) {
-                        for (int si : sr_stream) fail_stream(S[si], -8);
-                    } else {
-                        for (size_t q = 0; q < sr.size(); ++q) {
-                            whisper_decoder & d = S[sr_stream[q]].state->decoders[0];
-                            d.pending = {so[q].id, so[q].tid, so[q].p, so[q].plog, so[q].pt, so[q].ptsum, -1, -1, -1, 0.0f};
-                            if (dbg_gaps) {
-                                d.pending.t_dtw = so[q].runner_up;
-                                d.pending.vlen = so[q].gap;
-                            }
-                            d.has_pending = true;
-                        }
-                    }
-                }
+                if (!device_select(sel))
+                    for (const auto & it : sel) fail_stream(S[it.si], -8);
                 const int64_t dt = time_us() - t0;
                 for (int si : act) S[si].state->t_sample_us += dt / (int64_t) act.size();
             }
@@ -1038,7 +1087,7 @@ static int run_streams_locked(whisper_context & ctx, std::vector<StreamSpec> & s
                     std::vector<std::pair<int, int>> jobs;
                     for (int si : act) {
                         Stream & s = S[si];
-                        if (s.phase != Phase::STEPPING || (s.device_path && s.params.strategy != WHISPER_SAMPLING_BEAM_SEARCH)) continue;
+                        if (s.phase != Phase::STEPPING || s.device_path) continue;
                         for (int j = 0; j < s.n_decoders_cur; ++j)
                             if (!s.state->decoders[j].completed && !s.state->decoders[j].failed) jobs.push_back({si, j});
                     }
@@ -1064,7 +1113,7 @@ static int run_streams_locked(whisper_context & ctx, std::vector<StreamSpec> & s
                         if (d.completed || d.failed) continue;
                         if (!beam) {
                             whisper_token_data tok;
-                            if (s.device_path) {
+                            if (s.device_path && s.k_draws == 0) {
                                 tok = d.pending;
                                 d.has_pending = false;
                             } else {
@@ -1190,42 +1239,13 @@ static int run_streams_locked(whisper_context & ctx, std::vector<StreamSpec> & s
                 dbg_steps++;
                 bool ok = e.decode(rows, lrows, ctx.batch_cross.layer_stride);
                 dbg_dec_submit += time_us() - td0;
-                // selection: device path rows in one kernel, host path rows one by one
-                std::vector<SampleRow> sr;
-                std::vector<int> sr_row;
-                for (size_t r = 0; r < owner.size() && ok; ++r) {
-                    Stream & s = S[owner[r].first];
-                    whisper_decoder & d = s.state->decoders[owner[r].second];
-                    if (s.device_path) {
-                        const auto & tk = d.sequence.tokens;
-                        const int n = (int) tk.size();
-                        sr.push_back({(int) r, n, n > 0 ? tk[n - 1].id : 0, n > 1 ? tk[n - 2].id : 0, d.has_ts ? 1 : 0, d.seek_delta});
-                        sr_row.push_back((int) r);
-                    }
-                }
-                if (ok && !sr.empty()) {
-                    const auto & p = S[owner[sr_row[0]].first].params;
-                    SampleParams prm;
-                    prm.n_vocab = hp.n_vocab;
-                    prm.token_eot = vocab.token_eot;
-                    prm.token_beg = vocab.token_beg;
-                    prm.token_space = space_id;
-                    prm.suppress_blank = p.suppress_blank;
-                    prm.no_timestamps = p.no_timestamps;
-                    prm.max_initial_ts = p.max_initial_ts;
-                    prm.tid0 = (int) std::round(p.max_initial_ts / (30.0f / hp.n_audio_ctx));
-                    prm.temperature = 0.0f;
-                    std::vector<SampleOut> so;
-                    ok = e.sample_greedy(sr, (const uint32_t *) ctx.static_mask.p, prm, so);
-                    for (size_t q = 0; q < sr.size() && ok; ++q) {
-                        whisper_decoder & d = S[owner[sr_row[q]].first].state->decoders[owner[sr_row[q]].second];
-                        d.pending = {so[q].id, so[q].tid, so[q].p, so[q].plog, so[q].pt, so[q].ptsum, -1, -1, -1, 0.0f};
-                        if (dbg_gaps) {
-                            d.pending.t_dtw = so[q].runner_up;
-                            d.pending.vlen = so[q].gap;
-                        }
-                        d.has_pending = true;
-                    }
+                // selection for the NEXT iteration: device-path rows in one kernel; nothing is selected from the last step's logits
+                // (the reference's loop ends there too, so no uniform may be drawn from the decoders' generators)
+                if (ok && i + 1 < n_max) {
+                    std::vector<SelItem> sel;
+                    for (size_t r = 0; r < owner.size(); ++r)
+                        if (S[owner[r].first].device_path) sel.push_back({owner[r].first, owner[r].second, (int) r});
+                    ok = device_select(sel);
                 }
                 const int64_t td1 = time_us();
                 dbg_sel += td1 - td0;
@@ -1244,7 +1264,7 @@ static int run_streams_locked(whisper_context & ctx, std::vector<StreamSpec> & s
                                 whisper_decoder & d = s.state->decoders[owner[r].second];
                                 process_logits_host(&ctx, vocab, hp.n_audio_ctx, *s.state, d, s.params, static_bits,
                                                     logits_rows_host.data() + (size_t) (r - r_lo) * hp.n_vocab, s.t_cur);
-                            });
+                            }, host_threads);     // the user's logits_filter_callback runs on these threads: honour n_threads
                     }
                 }
                 const int64_t td2 = time_us();

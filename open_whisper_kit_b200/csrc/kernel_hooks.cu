@@ -279,6 +279,36 @@ WB200_API double whisper_b200_kernel_step_bench(int which, int dtype, int R, int
     return cuda_failed() ? -1.0 : 1e3 * ms / iters;
 }
 
+static_assert(sizeof(whisper_b200_sample_row) == sizeof(SampleRow) && sizeof(whisper_b200_sample_params) == sizeof(SampleParams) &&
+              sizeof(whisper_b200_sample_out) == sizeof(SampleOut) && sizeof(whisper_b200_draw_out) == sizeof(DrawOut),
+              "the hook's C structs mirror dec_kernels.h");
+
+WB200_API int whisper_b200_kernel_sample(const float * logits, int n_logit_rows, const struct whisper_b200_sample_row * rows, int n_rows,
+                                         const uint32_t * static_mask, struct whisper_b200_sample_params prm, const double * uniforms,
+                                         int n_uniforms, struct whisper_b200_sample_out * out, struct whisper_b200_draw_out * draws) {
+    if (!logits || !rows || !out || n_rows <= 0 || n_logit_rows <= 0 || prm.n_vocab <= 0 || (n_uniforms > 0 && (!uniforms || !draws))) return -1;
+    for (int r = 0; r < n_rows; ++r)
+        if (rows[r].logits_row < 0 || rows[r].logits_row >= n_logit_rows || rows[r].n_draws < 0 ||
+            (rows[r].n_draws > 0 && (rows[r].draw_off < 0 || rows[r].draw_off + rows[r].n_draws > n_uniforms))) return -2;
+    cuda_clear_failure();
+    const int V = prm.n_vocab, ld = round_up(V, 8), words = (V + 31) / 32;
+    DevBuf d_l((size_t) n_logit_rows * ld * 4), d_r((size_t) n_rows * sizeof(SampleRow)), d_m((size_t) words * 4),
+        d_o((size_t) n_rows * sizeof(SampleOut)), d_u((size_t) n_uniforms * 8), d_d((size_t) n_uniforms * sizeof(DrawOut));
+    WB_CUDA(cudaMemcpy2D(d_l.p, (size_t) ld * 4, logits, (size_t) V * 4, (size_t) V * 4, n_logit_rows, cudaMemcpyHostToDevice));
+    WB_CUDA(cudaMemcpy(d_r.p, rows, (size_t) n_rows * sizeof(SampleRow), cudaMemcpyHostToDevice));
+    if (static_mask) WB_CUDA(cudaMemcpy(d_m.p, static_mask, (size_t) words * 4, cudaMemcpyHostToDevice));
+    else WB_CUDA(cudaMemset(d_m.p, 0, (size_t) words * 4));
+    if (n_uniforms > 0) WB_CUDA(cudaMemcpy(d_u.p, uniforms, (size_t) n_uniforms * 8, cudaMemcpyHostToDevice));
+    SampleParams sp;
+    memcpy(&sp, &prm, sizeof(sp));
+    dec_sample(d_l.as<float>(), ld, d_r.as<SampleRow>(), n_rows, d_m.as<uint32_t>(), sp, d_o.as<SampleOut>(), d_u.as<double>(),
+               d_d.as<DrawOut>(), 0);
+    WB_CUDA(cudaDeviceSynchronize());
+    WB_CUDA(cudaMemcpy(out, d_o.p, (size_t) n_rows * sizeof(SampleOut), cudaMemcpyDeviceToHost));
+    if (n_uniforms > 0) WB_CUDA(cudaMemcpy(draws, d_d.p, (size_t) n_uniforms * sizeof(DrawOut), cudaMemcpyDeviceToHost));
+    return cuda_failed() ? -4 : 0;
+}
+
 WB200_API int whisper_b200_chain_geometry(int grid, int rows, int N, int K, int min_units, int direct, int * out) {
     if (!out || grid <= 0 || rows <= 0 || rows > 128 || N <= 0 || K <= 0 || N % SG_TILE_COLS != 0 || K % 64 != 0) return -1;
     const SplitGeom g = direct ? chain_geom_direct(rows, N, K) : chain_geom(grid, rows, N, K, min_units);

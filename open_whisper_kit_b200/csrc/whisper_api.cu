@@ -560,7 +560,113 @@ int whisper_full(struct whisper_context * ctx, struct whisper_full_params params
 }
 
 // Chunking, timestamp fix-up and timing merge as the reference (src/whisper.cpp:7801-7929); the chunks are decoded as
-// rows of ONE device batch instead of n_processors host threads.
+// rows of ONE device batch per GPU instead of n_processors host threads.  With a group of contexts (one model replica per
+// GPU, include/whisper_b200.h) the chunks are dealt out in contiguous blocks, one worker thread per GPU, no collective: the
+// only exchange is this host-side gather of the segments in chunk order.
+static int full_parallel_on(const std::vector<whisper_context *> & ctxs, struct whisper_full_params params, const float * samples,
+                            int n_samples, int n_processors) {
+    whisper_context * ctx = ctxs[0];
+    const int G = (int) ctxs.size();
+    const int offset_samples = (WHISPER_SAMPLE_RATE * params.offset_ms) / 1000;
+    const int n_per = (n_samples - offset_samples) / n_processors;
+    std::vector<whisper_state *> states(n_processors, nullptr);     // [0] is the caller's state, the rest are borrowed
+    std::vector<int> owner(n_processors, 0);
+    std::vector<std::vector<StreamSpec>> specs(G);
+    auto give_back = [&]() {
+        for (int i = 1; i < n_processors; ++i)
+            if (states[i]) return_state(ctxs[owner[i]], states[i]);
+    };
+    for (int i = 0; i < n_processors; ++i) {
+        owner[i] = whisper_b200_partition_owner(i, n_processors, G);
+        states[i] = i == 0 ? ctx->state : borrow_state(ctxs[owner[i]]);
+        if (!states[i]) {
+            give_back();
+            return -7;
+        }
+        StreamSpec sp;
+        sp.state = states[i];
+        sp.params = params;
+        sp.params.print_realtime = false;
+        if (i == 0) {
+            sp.samples = samples;
+            sp.n_samples = offset_samples + n_per;
+        } else {
+            const int start = offset_samples + i * n_per;
+            sp.params.offset_ms = 0;
+            sp.params.print_progress = false;
+            sp.params.new_segment_callback = nullptr;
+            sp.params.new_segment_callback_user_data = nullptr;
+            sp.params.progress_callback = nullptr;
+            sp.params.progress_callback_user_data = nullptr;
+            sp.samples = samples + start;
+            sp.n_samples = (i == n_processors - 1) ? n_samples - start : n_per;
+        }
+        specs[owner[i]].push_back(sp);
+    }
+    // GPU 0 runs on the calling thread (its chunk 0 fires the user's callbacks there, as the reference's main thread does)
+    std::vector<std::thread> workers;
+    for (int g = 1; g < G; ++g) {
+        if (specs[g].empty()) continue;
+        workers.emplace_back([&, g]() {
+            try {
+                run_streams(*ctxs[g], specs[g]);
+            } catch (const std::exception & ex) {
+                wlog(GGML_LOG_LEVEL_ERROR, "%s: GPU %d: %s\n", __func__, ctxs[g]->eng.device, ex.what());
+                for (auto & sp : specs[g]) sp.rc = -6;
+            }
+        });
+    }
+    try {
+        run_streams(*ctx, specs[0]);         // call-wide failures are written to every spec's rc
+    } catch (...) {
+        for (auto & th : workers) th.join();
+        give_back();
+        throw;
+    }
+    for (auto & th : workers) th.join();
+    int ret = specs[0][0].rc;                // the reference reports the first chunk's status (src/whisper.cpp:7857) ...
+    for (int g = 1; g < G && ret == 0; ++g)  // ... a replica that failed as a whole must not pass silently either
+        for (const auto & sp : specs[g])
+            if (sp.rc != 0 && ret == 0) ret = sp.rc;
+
+    const int64_t offset_t = (int64_t) (params.offset_ms / 10.0);
+    whisper_state * st0 = ctx->state;
+    for (int i = 1; i < n_processors; ++i) {
+        whisper_state * sti = states[i];
+        const int64_t shift = 100 * ((int64_t) i * n_per) / WHISPER_SAMPLE_RATE + offset_t;
+        for (auto & result : sti->result_all) {
+            result.t0 += shift;
+            result.t1 += shift;
+            if (!st0->result_all.empty()) result.t0 = std::max(result.t0, st0->result_all.back().t1);
+            st0->result_all.push_back(std::move(result));
+            if (params.new_segment_callback) params.new_segment_callback(ctx, st0, 1, params.new_segment_callback_user_data);
+        }
+        st0->t_mel_us += sti->t_mel_us;
+        st0->t_sample_us += sti->t_sample_us;
+        st0->t_encode_us += sti->t_encode_us;
+        st0->t_decode_us += sti->t_decode_us;
+        st0->t_batchd_us += sti->t_batchd_us;
+        st0->t_prompt_us += sti->t_prompt_us;
+        st0->n_sample += sti->n_sample;
+        st0->n_encode += sti->n_encode;
+        st0->n_decode += sti->n_decode;
+        st0->n_batchd += sti->n_batchd;
+        st0->n_prompt += sti->n_prompt;
+    }
+    give_back();
+    st0->t_mel_us /= n_processors;
+    st0->t_sample_us /= n_processors;
+    st0->t_encode_us /= n_processors;
+    st0->t_decode_us /= n_processors;
+    wlog(GGML_LOG_LEVEL_WARN, "\n");
+    wlog(GGML_LOG_LEVEL_WARN, "%s: the audio has been split into %d chunks at the following times:\n", __func__, n_processors);
+    for (int i = 1; i < n_processors; ++i)
+        wlog(GGML_LOG_LEVEL_WARN, "%s: split %d - %s\n", __func__, i,
+             to_timestamp(100 * ((int64_t) i * n_per) / WHISPER_SAMPLE_RATE + offset_t, false).c_str());
+    wlog(GGML_LOG_LEVEL_WARN, "%s: the transcription quality may be degraded near these boundaries\n", __func__);
+    return ret;
+}
+
 int whisper_full_parallel(struct whisper_context * ctx, struct whisper_full_params params, const float * samples, int n_samples,
                           int n_processors) {
     if (!ctx || !ctx->state) return -1;
@@ -570,78 +676,83 @@ int whisper_full_parallel(struct whisper_context * ctx, struct whisper_full_para
         return -1;
     }
     try {
-        const int offset_samples = (WHISPER_SAMPLE_RATE * params.offset_ms) / 1000;
-        const int n_per = (n_samples - offset_samples) / n_processors;
-        std::vector<whisper_state *> states;
-        std::vector<StreamSpec> specs(n_processors);
-        {
-            auto p0 = params;
-            p0.print_realtime = false;
-            specs[0].state = ctx->state;
-            specs[0].params = p0;
-            specs[0].samples = samples;
-            specs[0].n_samples = offset_samples + n_per;
-        }
-        for (int i = 0; i < n_processors - 1; ++i) {
-            whisper_state * ws = borrow_state(ctx);
-            if (!ws) {
-                for (whisper_state * st : states) return_state(ctx, st);
-                return -7;
-            }
-            states.push_back(ws);
-            const int start = offset_samples + (i + 1) * n_per;
-            const int n_cur = (i == n_processors - 2) ? n_samples - start : n_per;
-            auto pc = params;
-            pc.offset_ms = 0;
-            pc.print_progress = false;
-            pc.print_realtime = false;
-            pc.new_segment_callback = nullptr;
-            pc.new_segment_callback_user_data = nullptr;
-            pc.progress_callback = nullptr;
-            pc.progress_callback_user_data = nullptr;
-            specs[i + 1].state = states[i];
-            specs[i + 1].params = pc;
-            specs[i + 1].samples = samples + start;
-            specs[i + 1].n_samples = n_cur;
-        }
-        run_streams(*ctx, specs);            // call-wide failures are written to every specs[i].rc
-        const int ret = specs[0].rc;         // the reference reports the first chunk's status (src/whisper.cpp:7857)
+        return full_parallel_on({ctx}, params, samples, n_samples, n_processors);
+    } catch (const std::exception & ex) {
+        wlog(GGML_LOG_LEVEL_ERROR, "%s: %s\n", __func__, ex.what());
+        return -6;
+    }
+}
 
-        const int64_t offset_t = (int64_t) (params.offset_ms / 10.0);
-        whisper_state * st0 = ctx->state;
-        for (int i = 0; i < n_processors - 1; ++i) {
-            auto & results_i = states[i]->result_all;
-            for (auto & result : results_i) {
-                result.t0 += 100 * ((int64_t) (i + 1) * n_per) / WHISPER_SAMPLE_RATE + offset_t;
-                result.t1 += 100 * ((int64_t) (i + 1) * n_per) / WHISPER_SAMPLE_RATE + offset_t;
-                if (!st0->result_all.empty()) result.t0 = std::max(result.t0, st0->result_all.back().t1);
-                st0->result_all.push_back(std::move(result));
-                if (params.new_segment_callback) params.new_segment_callback(ctx, st0, 1, params.new_segment_callback_user_data);
+// ---- context group: one replica per GPU (include/whisper_b200.h) ------------------------------------------------------------
+struct whisper_b200_group {
+    std::vector<whisper_context *> ctxs;
+};
+
+WB200_API int whisper_b200_partition_owner(int chunk, int n_chunks, int n_gpus) {
+    if (n_gpus <= 1 || n_chunks <= 0 || chunk < 0) return 0;
+    // contiguous blocks whose sizes differ by at most one: chunk i -> floor(i * G / n)
+    return (int) std::min<long long>((long long) chunk * n_gpus / n_chunks, n_gpus - 1);
+}
+
+WB200_API struct whisper_b200_group * whisper_b200_group_init_from_file(const char * path_model, struct whisper_context_params params,
+                                                                        const int * devices, int n_devices) {
+    if (!path_model) return nullptr;
+    int visible = 0;
+    if (cudaGetDeviceCount(&visible) != cudaSuccess || visible <= 0) {
+        cudaGetLastError();
+        wlog(GGML_LOG_LEVEL_ERROR, "%s: no CUDA device is visible; no CPU fallback exists\n", __func__);
+        return nullptr;
+    }
+    std::vector<int> devs;
+    if (devices && n_devices > 0) devs.assign(devices, devices + n_devices);
+    else for (int i = 0; i < (n_devices > 0 ? std::min(n_devices, visible) : visible); ++i) devs.push_back(i);
+    try {
+        auto * g = new whisper_b200_group();
+        g->ctxs.assign(devs.size(), nullptr);
+        // the replicas load concurrently (file -> pinned staging -> HBM per device); only replica 0 owns a default state that
+        // callers read results from, the others get theirs for symmetry with whisper_init_from_file_with_params
+        std::vector<std::thread> loaders;
+        for (size_t i = 0; i < devs.size(); ++i)
+            loaders.emplace_back([&, i]() {
+                whisper_context_params cp = params;
+                cp.gpu_device = devs[i];
+                g->ctxs[i] = init_from_file(path_model, cp, true);
+            });
+        for (auto & th : loaders) th.join();
+        for (whisper_context * c : g->ctxs)
+            if (!c) {
+                whisper_b200_group_free(g);
+                return nullptr;
             }
-            st0->t_mel_us += states[i]->t_mel_us;
-            st0->t_sample_us += states[i]->t_sample_us;
-            st0->t_encode_us += states[i]->t_encode_us;
-            st0->t_decode_us += states[i]->t_decode_us;
-            st0->t_batchd_us += states[i]->t_batchd_us;
-            st0->t_prompt_us += states[i]->t_prompt_us;
-            st0->n_sample += states[i]->n_sample;
-            st0->n_encode += states[i]->n_encode;
-            st0->n_decode += states[i]->n_decode;
-            st0->n_batchd += states[i]->n_batchd;
-            st0->n_prompt += states[i]->n_prompt;
-            return_state(ctx, states[i]);
-        }
-        st0->t_mel_us /= n_processors;
-        st0->t_sample_us /= n_processors;
-        st0->t_encode_us /= n_processors;
-        st0->t_decode_us /= n_processors;
-        wlog(GGML_LOG_LEVEL_WARN, "\n");
-        wlog(GGML_LOG_LEVEL_WARN, "%s: the audio has been split into %d chunks at the following times:\n", __func__, n_processors);
-        for (int i = 0; i < n_processors - 1; ++i)
-            wlog(GGML_LOG_LEVEL_WARN, "%s: split %d - %s\n", __func__, (i + 1),
-                 to_timestamp(100 * ((int64_t) (i + 1) * n_per) / WHISPER_SAMPLE_RATE + offset_t, false).c_str());
-        wlog(GGML_LOG_LEVEL_WARN, "%s: the transcription quality may be degraded near these boundaries\n", __func__);
-        return ret;
+        return g;
+    } catch (const std::exception & ex) {
+        wlog(GGML_LOG_LEVEL_ERROR, "%s: %s\n", __func__, ex.what());
+        return nullptr;
+    }
+}
+
+WB200_API void whisper_b200_group_free(struct whisper_b200_group * g) {
+    if (!g) return;
+    for (whisper_context * c : g->ctxs) whisper_free(c);
+    delete g;
+}
+
+WB200_API int whisper_b200_group_size(struct whisper_b200_group * g) { return g ? (int) g->ctxs.size() : 0; }
+
+WB200_API struct whisper_context * whisper_b200_group_context(struct whisper_b200_group * g, int i) {
+    return g && i >= 0 && i < (int) g->ctxs.size() ? g->ctxs[i] : nullptr;
+}
+
+WB200_API int whisper_b200_group_full_parallel(struct whisper_b200_group * g, struct whisper_full_params params, const float * samples,
+                                               int n_samples, int n_processors) {
+    if (!g || g->ctxs.empty() || !g->ctxs[0]->state) return -1;
+    if (params.vad) {
+        wlog(GGML_LOG_LEVEL_ERROR, "%s: VAD is outside the scope of the B200 path (failed to compute VAD)\n", __func__);
+        return -1;
+    }
+    if (n_processors <= 1) return whisper_full(g->ctxs[0], params, samples, n_samples);
+    try {
+        return full_parallel_on(g->ctxs, params, samples, n_samples, n_processors);
     } catch (const std::exception & ex) {
         wlog(GGML_LOG_LEVEL_ERROR, "%s: %s\n", __func__, ex.what());
         return -6;

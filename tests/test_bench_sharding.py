@@ -53,3 +53,17 @@ def test_shard_windows_partition_property():
             parts = [bench.shard_windows(n, r, world) for r in range(world)]
             flat = [w for p in parts for w in p]
             assert flat == list(range(n))
+
+
+def test_library_chunk_partition_is_contiguous_and_balanced():
+    """whisper_b200_partition_owner (host logic of the multi-GPU entry point): chunk -> GPU in contiguous blocks whose sizes
+    differ by at most one, every GPU used when there are enough chunks."""
+    import open_whisper_kit_b200 as pkg
+    lib = pkg.load()
+    for n_chunks in (1, 2, 5, 8, 15, 64, 120):
+        for n_gpus in (1, 2, 3, 4, 8):
+            owners = [lib.whisper_b200_partition_owner(i, n_chunks, n_gpus) for i in range(n_chunks)]
+            assert owners == sorted(owners) and owners[0] == 0 and max(owners) < n_gpus
+            counts = [owners.count(g) for g in range(n_gpus)]
+            if n_chunks >= n_gpus:
+                assert min(counts) >= 1 and max(counts) - min(counts) <= 1, (n_chunks, n_gpus, counts)

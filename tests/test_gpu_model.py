@@ -97,7 +97,7 @@ def run_case(lib, model_dir, case):
         return rc, [[int(s.t0), int(s.t1), [int(x) for x in s.tokens]] for s in segs], segs
 
 
-NEAR_TIE = 0.05      # logit distance below which a different greedy choice counts as a tie flip (2.5x the 2e-2 logit gate)
+MARGIN = 4e-2        # 2 x the spec's logits tolerance (2e-2 max-abs): below it two conforming implementations may pick differently
 
 
 def by_chunk(segments):
@@ -110,16 +110,33 @@ def by_chunk(segments):
     return out
 
 
+def _report(name, entry):
+    try:
+        out = os.path.join(os.path.dirname(HERE), "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        path = os.path.join(out, "parity_report.json")
+        data = json.load(open(path)) if os.path.exists(path) else {}
+        data[name] = entry
+        json.dump(data, open(path, "w"), indent=1, sort_keys=True)
+    except OSError:
+        pass
+
+
 @pytest.mark.parametrize("name", sorted(GOLD_TOK.keys()))
 def test_greedy_tokens_identical_to_reference_golden(lib, model_dir, name, monkeypatch):
     """Greedy tokens and segment times vs the reference CPU path (BASELINE.json configs 1 and 2).
 
-    Bar: identical.  With random-init weights the greedy arg-max is decided, a few times per thousand steps, by logit
-    distances of 1e-3..1e-4 -- below the difference between two builds of the reference itself (its AVX2 and AVX-512
-    builds diverge at token 1689 of 3520 on the base.en case).  So a chunk may differ from the golden
-    sequence only if, at its FIRST differing step, our two best candidates are within NEAR_TIE logits of each other and
-    the reference's token is our runner-up; everything before that step must be identical.  The number of such flips
-    is printed and bounded."""
+    Bar: identical.  north_star also allows the logits to differ by 2e-2, and on random-init weights (Gaussian logits) the
+    reference's own top-1 / top-2 margin is below 2 x 2e-2 at ~10 % of the steps, whatever the scale of the init -- margins and
+    rounding errors scale together; the reference's AVX2 and AVX-512 builds diverge from each other on the base.en case (see
+    DESIGN.md).  So identity is REQUIRED wherever the reference's recorded margin allows it and a difference is accepted only
+    where it does not:
+      * case with recorded per-step margins (golden "steps", from the reference alone): every token before a chunk's first
+        sub-margin step must be identical; the first mismatch of a chunk, if any, must sit ON a sub-margin step and be the
+        reference's recorded runner-up;
+      * other cases (no margins recorded -- timestamp mode): a chunk's first mismatch must be a near-tie of OUR two best
+        candidates (< MARGIN logits) with the reference's token as our runner-up; at most a quarter of the chunks may have one.
+    Every flip is written to gpurun_out/parity_report.json."""
     monkeypatch.setenv("WHISPER_B200_DEBUG_GAPS", "1")
     case = GOLD_TOK[name]
     rc, _, segs = run_case(lib, model_dir, case)
@@ -127,6 +144,7 @@ def test_greedy_tokens_identical_to_reference_golden(lib, model_dir, name, monke
     ours = by_chunk([(s.t0, s.t1, s.tokens, s.token_data) for s in segs])
     ref = by_chunk([(s[0], s[1], s[2], None) for s in case["segments"]])
     n_chunks = case["n_processors"]
+    steps = case.get("steps")
     n_ident, flips = 0, []
     for c in range(n_chunks):
         a = [t for t, _ in ours.get(c, [])]
@@ -137,15 +155,23 @@ def test_greedy_tokens_identical_to_reference_golden(lib, model_dir, name, monke
         k = next((i for i, (x, y) in enumerate(zip(a, b)) if x != y), None)
         assert k is not None, f"chunk {c}: one sequence is a strict prefix of the other ({len(a)} vs {len(b)} tokens)"
         td = ours[c][k][1]
-        flips.append((c, k, a[k], b[k], round(td.vlen, 5)))
-        assert td.vlen < NEAR_TIE and td.t_dtw == b[k], \
-            f"chunk {c} step {k}: ours {a[k]} vs reference {b[k]}, our runner-up {td.t_dtw} at distance {td.vlen}"
+        if steps:
+            gaps, runner = steps[c]["gaps"], steps[c]["runner_up"]
+            strict = next((i for i, g in enumerate(gaps) if g < MARGIN), len(gaps))
+            flips.append({"chunk": c, "step": k, "ours": a[k], "reference": b[k], "reference_margin": gaps[k], "strict_prefix": strict})
+            assert k >= strict and gaps[k] < MARGIN and a[k] == runner[k], \
+                f"chunk {c} step {k}: ours {a[k]} vs reference {b[k]}; reference margin {gaps[k]}, its runner-up {runner[k]}"
+        else:
+            flips.append({"chunk": c, "step": k, "ours": a[k], "reference": b[k], "our_margin": round(td.vlen, 5)})
+            assert td.vlen < MARGIN and td.t_dtw == b[k], \
+                f"chunk {c} step {k}: ours {a[k]} vs reference {b[k]}, our runner-up {td.t_dtw} at distance {td.vlen}"
     n_ref_tok = sum(len(v) for v in ref.values())
-    print(f"{name}: {n_ref_tok} reference tokens, {n_ident}/{n_chunks} chunks identical, near-tie flips (chunk, step, ours, ref, "
-          f"logit distance): {flips}")
+    _report("golden_tokens/" + name, {"reference_tokens": n_ref_tok, "chunks": n_chunks, "chunks_identical": n_ident, "flips": flips})
+    print(f"{name}: {n_ref_tok} reference tokens, {n_ident}/{n_chunks} chunks identical, flips: {flips}")
     if not flips:
         assert [(s.t0, s.t1) for s in segs] == [(s[0], s[1]) for s in case["segments"]]
-    assert len(flips) <= max(1, n_chunks // 2)
+    if not steps:
+        assert len(flips) <= n_chunks // 4
 
 
 def test_token_data_fields_match_live_reference(lib, model_dir):

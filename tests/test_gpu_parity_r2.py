@@ -1,0 +1,178 @@
+"""GPU parity on the BASELINE configurations and whisper_full features that round 1 left untested, against golden
+fixtures produced by the UNMODIFIED reference (tests/golden/make_golden_r2.py -> golden_r2.json):
+
+  * large-v3 (32 + 32 layers), greedy: two windows x 49 steps without timestamps, one window in timestamp mode   (config 3)
+  * large-v3-turbo and tiny, "beam search" 5 + timestamps -- selection entirely on the device                    (config 4)
+  * temperature fallback ladder (greedy best_of 3 at t > 0, forced by a logprob threshold)
+  * prompt carry-over across windows (no_context = false), initial_prompt, offset / duration, translate
+
+What "identical tokens" can mean on random-init weights.  north_star gives TWO bars: logits within 2e-2 max-abs, greedy tokens
+identical.  They are only compatible at steps where the reference's own top-1 / top-2 logit margin exceeds 2 x 2e-2: below
+that, two implementations that both meet the logits bar may legitimately pick different tokens (the reference's own AVX2 and
+AVX-512 builds do; entries "<case>@v3" of the fixture).  Random-init logits are Gaussian, so a margin below 4e-2 occurs at
+~10 % of the steps whatever the init scale (margins and errors scale together).  The rule here therefore uses ONLY numbers
+recorded from the reference, never our own margins:
+
+  strict   every token before a window's first sub-margin step must be identical;
+  beyond   the comparison goes on; the first mismatch of a window must sit ON a sub-margin step and our token must be the
+           reference's recorded runner-up; after a legitimate flip the two sequences are different texts and are not compared.
+
+Cases without recorded margins (timestamp mode, sampling) are compared token for token over the whole fixture.
+Every comparison is appended to gpurun_out/parity_report.json (copied to profiles/ by the builder).
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from open_whisper_kit_b200 import api
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import cases_r2  # noqa: E402
+
+GOLD = json.load(open(os.path.join(HERE, "golden", "golden_r2.json")))
+MARGIN = 4e-2          # 2 x the logits tolerance of the spec
+PLOG_TOL = 6e-2        # |plog - reference|: two logits at <= 2e-2 each plus the log-sum-exp
+
+
+def report(name, entry):
+    try:
+        out = os.path.join(os.path.dirname(HERE), "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        path = os.path.join(out, "parity_report.json")
+        data = json.load(open(path)) if os.path.exists(path) else {}
+        data[name] = entry
+        json.dump(data, open(path, "w"), indent=1, sort_keys=True)
+    except OSError:
+        pass
+
+
+def run_ours(lib, model_dir, case):
+    path = os.path.join(model_dir, f"{case['arch']}-1.bin")
+    if not os.path.exists(path):
+        cases_r2.modelgen.write_model(path, case["arch"], ftype=1)
+    with api.Whisper(lib, path, flash_attn=False) as w:
+        keep = []
+        p = cases_r2.params_for(w, case, keep)
+        rc, segs = w.full(p, cases_r2.pcm_for(case), n_processors=case["n_processors"])
+        return rc, [[int(s.t0), int(s.t1), [int(x) for x in s.tokens], [float(t.p) for t in s.token_data],
+                     [float(t.plog) for t in s.token_data]] for s in segs]
+
+
+def flat(segments):
+    return [t for s in segments for t in s[2]]
+
+
+def first_diff(a, b):
+    return next((i for i, (x, y) in enumerate(zip(a, b)) if x != y), None if len(a) == len(b) else min(len(a), len(b)))
+
+
+def test_large_v3_greedy_identity_where_the_reference_margin_allows(lib, model_dir):
+    """BASELINE config 3 geometry: large-v3, 32 encoder + 32 decoder layers, d = 1280, 128 mel bins."""
+    name = "large-v3/synth2/nots48"
+    gold = GOLD[name]
+    rc, segs = run_ours(lib, model_dir, gold)
+    assert rc == gold["rc"] == 0
+    assert len(segs) == len(gold["segments"]) == gold["windows"]
+    entry = {"windows": []}
+    for wi, (ours, ref) in enumerate(zip(segs, gold["segments"])):
+        assert (ours[0], ours[1]) == (ref[0], ref[1])
+        gaps, runner = gold["steps"][wi]["gaps"], gold["steps"][wi]["runner_up"]
+        strict = next((k for k, g in enumerate(gaps) if g < MARGIN), len(gaps))
+        assert ours[2][:strict] == ref[2][:strict], f"window {wi}: mismatch inside the strict prefix of {strict} tokens"
+        k = first_diff(ours[2], ref[2])
+        if k is not None:
+            assert k < len(gaps) and gaps[k] < MARGIN and k < len(ours[2]) and ours[2][k] == runner[k], \
+                f"window {wi} step {k}: ours {ours[2][k] if k < len(ours[2]) else None} vs reference {ref[2][k]} " \
+                f"(reference margin {gaps[k] if k < len(gaps) else None}, runner-up {runner[k] if k < len(runner) else None})"
+        n_cmp = len(ref[2]) if k is None else k
+        dpl = max(abs(a - b) for a, b in zip(ours[4][:n_cmp], ref[4][:n_cmp])) if n_cmp else 0.0
+        assert dpl <= PLOG_TOL, f"window {wi}: plog differs by {dpl}"
+        entry["windows"].append({"tokens": len(ref[2]), "strict_prefix": strict, "identical_until": n_cmp,
+                                 "flip_margin": None if k is None else gaps[k], "min_reference_margin": min(gaps),
+                                 "max_plog_diff": round(dpl, 5)})
+    report(name, entry)
+    print(name, entry)
+
+
+@pytest.mark.parametrize("name", ["large-v3/synth1/ts", "tiny/synth3/carry", "tiny/synth2/prompt_offset_translate"])
+def test_greedy_features_identical_to_reference(lib, model_dir, name):
+    """Timestamp-mode decoding of one large-v3 window over the full 220-token budget (segments cut at timestamp tokens,
+    seek advance inside the window), prompt carry-over across three windows of one stream (no_context = false,
+    src/whisper.cpp:7125-7144, 7625-7636), and initial_prompt + offset_ms + duration_ms + translate + language."""
+    gold = GOLD[name]
+    rc, segs = run_ours(lib, model_dir, gold)
+    assert rc == gold["rc"] == 0
+    k = first_diff(flat(segs), flat(gold["segments"]))
+    report(name, {"reference_tokens": len(flat(gold["segments"])), "first_difference": k, "segments": len(gold["segments"])})
+    assert [(s[0], s[1], s[2]) for s in segs] == [(s[0], s[1], s[2]) for s in gold["segments"]], f"first token difference at {k}"
+    dpl = max((abs(a - b) for s, r in zip(segs, gold["segments"]) for a, b in zip(s[4], r[4])), default=0.0)
+    assert dpl <= PLOG_TOL
+
+
+@pytest.mark.parametrize("name", ["tiny/synth2/beam5", "large-v3-turbo/synth2/beam5", "base.en/synth2/fallback"])
+def test_sampled_decoding_on_device_vs_reference(lib, model_dir, name):
+    """"Beam search" (k categorical draws per beam and step from each decoder's own mt19937, src/whisper.cpp:6519-6592,
+    7247-7341) and the temperature-fallback ladder (7069-7606) with the selection running on the device: same RNG streams, same
+    rules, same candidate ranking.
+
+    A categorical draw is a comparison of a uniform with a cumulative sum over ~50 000 probabilities, so it amplifies logit
+    differences far below the 2e-2 tolerance: the reference's OWN AVX2 and AVX-512 builds produce different tokens on two of
+    the three cases (fixture entries "<case>@v3").  The bar is therefore the reference's own reproducibility: our sequence must
+    be identical to the reference's (AVX-512 build) for as long as the reference's two builds agree with each other.  The
+    arithmetic-independent statement -- identical draws from identical logits -- is tests/test_gpu_sampler.py."""
+    gold = GOLD[name]
+    rc, segs = run_ours(lib, model_dir, gold)
+    assert rc == gold["rc"] == 0
+    a, b = flat(segs), flat(gold["segments"])
+    k = first_diff(a, b)
+    v3 = GOLD[name + "@v3"]
+    k_ref = first_diff(flat(v3["segments"]), b)
+    report(name, {"reference_tokens": len(b), "our_tokens": len(a), "first_difference": k,
+                  "first_difference_between_reference_builds": k_ref})
+    print(name, "tokens", len(a), len(b), "first difference", k, "| reference AVX2 vs AVX-512 builds:", k_ref)
+    need = len(b) if k_ref is None else k_ref
+    assert a[:need] == b[:need], f"first token difference at {k}, the reference's builds agree up to {need}"
+    if k is None:
+        assert [(s[0], s[1]) for s in segs] == [(s[0], s[1]) for s in gold["segments"]]
+        dpl = max((abs(x - y) for s, r in zip(segs, gold["segments"]) for x, y in zip(s[4], r[4])), default=0.0)
+        assert dpl <= PLOG_TOL
+
+
+@pytest.mark.parametrize("name", ["tiny/synth2/beam5", "base.en/synth2/fallback"])
+def test_device_selection_equals_host_selection(lib, model_dir, name, monkeypatch):
+    """The same call with a pass-through logits_filter_callback, which forces the host restatement of the reference's rules
+    and samplers (csrc/full.cu) on logits rows copied back from the device: identical tokens, times and probabilities."""
+    import ctypes as C
+    from open_whisper_kit_b200 import capi
+    gold = GOLD[name]
+    path = os.path.join(model_dir, f"{gold['arch']}-1.bin")
+    if not os.path.exists(path):
+        cases_r2.modelgen.write_model(path, gold["arch"], ftype=1)
+    res = []
+    calls = [0]
+
+    def passthrough(ctx, state, tokens, n_tokens, logits, user):
+        calls[0] += 1
+
+    cb = capi.LOGITS_FILTER_CB(passthrough) if hasattr(capi, "LOGITS_FILTER_CB") else None
+    if cb is None:
+        pytest.skip("capi has no LOGITS_FILTER_CB type")
+    for use_host in (False, True):
+        with api.Whisper(lib, path, flash_attn=False) as w:
+            keep = []
+            p = cases_r2.params_for(w, gold, keep)
+            if use_host:
+                p.logits_filter_callback = C.cast(cb, C.c_void_p)
+            rc, segs = w.full(p, cases_r2.pcm_for(gold), n_processors=gold["n_processors"])
+            assert rc == 0
+            res.append([(int(s.t0), int(s.t1), [int(x) for x in s.tokens], [float(t.plog) for t in s.token_data]) for s in segs])
+    assert calls[0] > 0
+    assert [(s[0], s[1], s[2]) for s in res[0]] == [(s[0], s[1], s[2]) for s in res[1]]
+    dpl = max((abs(x - y) for s, r in zip(res[0], res[1]) for x, y in zip(s[3], r[3])), default=0.0)
+    assert dpl <= 1e-5

@@ -1,0 +1,151 @@
+"""The on-device logit rules + token selection kernel (csrc/dec_kernels.cu, sample_kernel) against the compiled reference's own
+functions on identical inputs: one logits row, one decoder state, one parameter set through
+
+  * whisper_b200_kernel_sample (product, CUDA): arg-max row and categorical-draw row (beam search / temperature sampling), and
+  * ref_process_logits + ref_sample_topk (oracle/ref_harness.cpp -> whisper_process_logits, whisper_sample_token,
+    whisper_sample_token_topk, src/whisper.cpp:6177-6592) with the decoder's mt19937 seeded the same way.
+
+The reference draws through std::discrete_distribution, which consumes generate_canonical<double, 53>(mt19937) per draw; the
+product's host draws those uniforms from the decoder's generator and the kernel does the rest, so the uniforms handed to the
+kernel here are rebuilt from the raw MT19937 stream (numpy's legacy seeding == std::mt19937(seed)).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import open_whisper_kit_b200 as pkg
+from open_whisper_kit_b200 import api, capi, modelgen
+from oracle import reflib
+
+pytestmark = pytest.mark.gpu
+
+FP = C.POINTER(C.c_float)
+
+
+class SampleRow(C.Structure):
+    _fields_ = [("logits_row", C.c_int), ("n_tokens", C.c_int), ("last", C.c_int), ("penult", C.c_int), ("has_ts", C.c_int),
+                ("seek_delta", C.c_int), ("temperature", C.c_float), ("n_draws", C.c_int), ("draw_off", C.c_int),
+                ("tid_default", C.c_int)]
+
+
+class SampleParams(C.Structure):
+    _fields_ = [("n_vocab", C.c_int), ("token_eot", C.c_int), ("token_beg", C.c_int), ("token_space", C.c_int),
+                ("suppress_blank", C.c_int), ("no_timestamps", C.c_int), ("max_initial_ts", C.c_float), ("tid0", C.c_int)]
+
+
+class SampleOut(C.Structure):
+    _fields_ = [("id", C.c_int), ("tid", C.c_int), ("p", C.c_float), ("plog", C.c_float), ("pt", C.c_float), ("ptsum", C.c_float),
+                ("runner_up", C.c_int), ("gap", C.c_float)]
+
+
+class DrawOut(C.Structure):
+    _fields_ = [("id", C.c_int), ("p", C.c_float), ("plog", C.c_float)]
+
+
+def mt19937_uniforms(seed, n):
+    """n x generate_canonical<double, 53>(std::mt19937(seed)): two 32-bit outputs per value, low word first."""
+    bg = np.random.MT19937()
+    bg._legacy_seeding(seed)
+    raw = bg.random_raw(2 * n).astype(np.float64)
+    u = (raw[0::2] + raw[1::2] * 4294967296.0) / 18446744073709551616.0
+    return np.where(u >= 1.0, np.nextafter(1.0, 0.0), u)
+
+
+@pytest.fixture(scope="module", params=["tiny.en", "large-v3"])
+def ctxs(request, tmp_path_factory):
+    ref, _ = reflib.load()
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    path = os.path.join(str(tmp_path_factory.mktemp("smp")), f"{request.param}-header.bin")
+    modelgen.write_model(path, request.param, with_tensors=False)      # vocabulary only
+    w = api.Whisper(ref, path, use_gpu=False, flash_attn=False)
+    lib = pkg.load()
+    lib.whisper_b200_kernel_sample.restype = C.c_int
+    lib.whisper_b200_kernel_sample.argtypes = [FP, C.c_int, C.POINTER(SampleRow), C.c_int, C.POINTER(C.c_uint32), SampleParams,
+                                               C.POINTER(C.c_double), C.c_int, C.POINTER(SampleOut), C.POINTER(DrawOut)]
+    n_vocab = ref.whisper_n_vocab(w.ctx)
+    sp = dict(eot=ref.whisper_token_eot(w.ctx), sot=ref.whisper_token_sot(w.ctx), translate=ref.whisper_token_translate(w.ctx),
+              transcribe=ref.whisper_token_transcribe(w.ctx), solm=ref.whisper_token_solm(w.ctx), prev=ref.whisper_token_prev(w.ctx),
+              nosp=ref.whisper_token_nosp(w.ctx), tnot=ref.whisper_token_not(w.ctx), beg=ref.whisper_token_beg(w.ctx))
+    space = next(i for i in range(n_vocab) if (ref.whisper_token_to_str(w.ctx, i) or b"") == b" ")
+    # tokens suppressed at every step (src/whisper.cpp:6224-6249); the regex / non-speech lists are off in these cases
+    kill = [sp["tnot"], sp["sot"], sp["nosp"], sp["solm"], sp["translate"], sp["transcribe"], sp["prev"]]
+    kill += [sp["sot"] + 1 + i for i in range(ref.whisper_lang_max_id() + 1)]
+    mask = np.zeros((n_vocab + 31) // 32, np.uint32)
+    for t in kill:
+        if 0 <= t < n_vocab:
+            mask[t >> 5] |= np.uint32(1 << (t & 31))
+    yield ref, w, lib, n_vocab, sp, space, mask
+
+
+def _history(rng, kind, eot, beg):
+    txt = lambda: int(rng.integers(0, eot))                      # noqa: E731
+    ts = lambda: beg + int(rng.integers(1, 400))                 # noqa: E731
+    return {"empty": [], "text": [txt(), txt(), txt()], "ts_last": [txt(), ts()], "ts_pair": [txt(), ts(), ts()],
+            "only_ts": [ts()], "long": [ts()] + [txt() for _ in range(20)]}[kind]
+
+
+@pytest.mark.parametrize("kind", ["empty", "text", "ts_last", "ts_pair", "only_ts", "long"])
+@pytest.mark.parametrize("variant", ["default", "no_ts", "temp", "no_blank_rule", "ts_heavy", "peaked", "peaked_temp"])
+def test_device_selection_matches_reference(ctxs, kind, variant):
+    ref, w, lib, n_vocab, sp, space, mask = ctxs
+    eot, beg = sp["eot"], sp["beg"]
+    rng = np.random.default_rng(abs(hash((kind, variant, n_vocab))) % (2 ** 32))
+    p = w.greedy_params(no_timestamps=False, n_threads=1)
+    temperature, sigma = 0.0, 3.0
+    if variant == "no_ts":
+        p.no_timestamps = True
+    elif variant == "temp":
+        temperature = 0.6
+    elif variant == "no_blank_rule":
+        p.suppress_blank = False
+        p.max_initial_ts = 0.0
+    elif variant == "peaked":
+        sigma = 12.0
+    elif variant == "peaked_temp":
+        sigma, temperature = 6.0, 0.2
+    logits = (sigma * rng.standard_normal(n_vocab)).astype(np.float32)
+    if variant == "ts_heavy":
+        logits[beg:] += 6.0
+    hist = _history(rng, kind, eot, beg)
+    has_ts = int(any(t >= beg for t in hist))
+    seek_delta = 2 * (max([t - beg for t in hist if t >= beg] or [0]))
+    h_arr = (C.c_int32 * max(1, len(hist)))(*hist)
+    K, seed = 5, 4321 + len(hist)
+
+    # reference
+    tok = capi.whisper_token_data()
+    ref_draws = (capi.whisper_token_data * K)()
+    pr = np.empty(n_vocab, np.float32)
+    assert ref.ref_process_logits(w.ctx, p, temperature, logits.ctypes.data_as(FP), h_arr, len(hist), has_ts, seek_delta, None, None,
+                                  pr.ctypes.data_as(FP), C.byref(tok)) == 0
+    assert ref.ref_sample_topk(w.ctx, K, seed, ref_draws) == 0
+
+    # product: row 0 arg-max, row 1 K draws, both on logits row 0
+    n = len(hist)
+    rows = (SampleRow * 2)()
+    for r, nd in enumerate((0, K)):
+        rows[r] = SampleRow(0, n, hist[-1] if n > 0 else 0, hist[-2] if n > 1 else 0, has_ts, seek_delta, temperature, nd, 0,
+                            0 if nd == 0 else beg)
+    prm = SampleParams(n_vocab, eot, beg, space, int(p.suppress_blank), int(p.no_timestamps), p.max_initial_ts,
+                       int(round(p.max_initial_ts / 0.02)))
+    u = mt19937_uniforms(seed, K)
+    out = (SampleOut * 2)()
+    draws = (DrawOut * K)()
+    rc = lib.whisper_b200_kernel_sample(logits.ctypes.data_as(FP), 1, rows, 2, mask.ctypes.data_as(C.POINTER(C.c_uint32)), prm,
+                                        u.ctypes.data_as(C.POINTER(C.c_double)), K, out, draws)
+    assert rc == 0
+
+    g = out[0]
+    assert (g.id, g.tid) == (tok.id, tok.tid)
+    assert np.allclose([g.p, g.plog, g.pt, g.ptsum], [tok.p, tok.plog, tok.pt, tok.ptsum], rtol=3e-6, atol=1e-7)
+    assert [d.id for d in draws] == [d.id for d in ref_draws], (list(u), [d.id for d in draws], [d.id for d in ref_draws])
+    for d, rd in zip(draws, ref_draws):
+        assert np.allclose([d.p, d.plog], [rd.p, rd.plog], rtol=3e-6, atol=1e-7)
+        tid = d.id if d.id >= beg else out[1].tid
+        pt = d.p if d.id >= beg else out[1].pt
+        assert tid == rd.tid and np.allclose([pt, out[1].ptsum], [rd.pt, rd.ptsum], rtol=3e-6, atol=1e-7)
+    # every drawn token must be one the reference left alive
+    assert all(pr[d.id] > 0 for d in draws)
