@@ -262,7 +262,7 @@ def parity_check(lib, model_path, device):
         ours = segment_tokens(lib, ctx)
     finally:
         lib.whisper_free(ctx)
-    margin, res, ok = 4e-2, [], len(ours) == len(gold["segments"])
+    margin, res, ok = 5e-3, [], len(ours) == len(gold["segments"])
     for wi, ref in enumerate(gold["segments"]):
         if wi >= len(ours):
             break
@@ -275,7 +275,7 @@ def parity_check(lib, model_path, device):
         ok = ok and good
         res.append({"reference_tokens": len(ref[2]), "strict_prefix": strict, "identical_until": len(ref[2]) if k is None else k})
     return {"ok": bool(ok), "against": "tests/golden/golden_r2.json large-v3/synth2/nots48 (unmodified reference, AVX-512 build)",
-            "rule": "identical before the reference's first top-2 margin < 4e-2; a later first mismatch must be the reference's runner-up "
+            "rule": "identical before the reference's first top-2 margin < 5e-3; a later first mismatch must be the reference's runner-up "
                     "on such a step", "windows": res}
 
 

@@ -96,6 +96,12 @@ WB200_API int whisper_b200_kernel_tc_skinny_gemm(int dtype, int M, int N, int K,
                                                  const float * bias, float scale, int scale_cols, int gelu,
                                                  const float * resid, uint16_t * out16, float * out32);
 
+/* Two decoder-step GEMMs with the LayerNorm between them folded in (csrc/tc_skinny.cu): x = a1 * w1^T + bias1 + resid, whose
+ * epilogue also emits per-tile row statistics, then y = LayerNorm(x; gamma, beta, eps) * w2^T with the normalised A operand built
+ * inside the second kernel.  M <= 64; d, K1 multiples of 64.  x_out [M][d], y_out [M][N2] f32.  Returns 0 or a negative error. */
+WB200_API int whisper_b200_kernel_ln_gemm_pair(int dtype, int M, int d, int K1, int N2, const uint16_t * a1, const uint16_t * w1,
+                                               const float * bias1, const float * resid, const float * gamma, const float * beta,
+                                               float eps, const uint16_t * w2, float * x_out, float * y_out);
 WB200_API double whisper_b200_kernel_gemm_bench(int dtype, int M, int N, int K, int gelu, int iters);
 
 /* Average microseconds of one decoder-step kernel launched back to back: which = 0 LayerNorm, 1 cross-attention,

@@ -27,6 +27,7 @@ EXT_PROTOTYPES = {
                                                    _C.c_int, _C.c_int, _FP, _U16P, _FP]),
     "whisper_b200_kernel_tc_skinny_gemm": (_C.c_int, [_C.c_int, _C.c_int, _C.c_int, _C.c_int, _U16P, _U16P, _FP, _C.c_float,
                                                       _C.c_int, _C.c_int, _FP, _U16P, _FP]),
+    "whisper_b200_kernel_ln_gemm_pair": (_C.c_int, [_C.c_int] * 5 + [_U16P, _U16P, _FP, _FP, _FP, _FP, _C.c_float, _U16P, _FP, _FP]),
     "whisper_b200_kernel_gemm_bench": (_C.c_double, [_C.c_int, _C.c_int, _C.c_int, _C.c_int, _C.c_int, _C.c_int]),
     "whisper_b200_kernel_step_bench": (_C.c_double, [_C.c_int] * 6),
     "whisper_b200_full_device": (_C.c_int, [_C.c_void_p, capi.whisper_full_params, _C.c_void_p, _C.c_int, _C.c_int]),

@@ -58,7 +58,7 @@ void dec_self_attn(DType dt, const void * qkv, const DecRow * d_rows, int R, int
 struct SplitIn;   // dec_chain.h: the query as partial tiles of the chain kernel's cross-q GEMM (q is ignored then)
 // d_groups (optional): n_groups runs {first row, count <= DEC_CROSS_GROUP_MAX} of consecutive rows that share one window's cross
 // K/V (prompt tokens, beams): one CTA per (run, head) then streams the K/V once for all rows of the run.
-constexpr int DEC_CROSS_GROUP_MAX = 4;
+constexpr int DEC_CROSS_GROUP_MAX = 5;
 void dec_cross_attn(DType dt, const void * q, const DecRow * d_rows, int R, int d, int n_head, size_t layer_off_elems,
                     int T, int n_phantom, void * out, cudaStream_t st, const SplitIn * q_split = nullptr,
                     const int2 * d_groups = nullptr, int n_groups = 0);

@@ -39,6 +39,14 @@ __global__ void kv_copy_prefix_kernel(const uint4 * __restrict__ src, uint4 * __
     const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n8) dst[blockIdx.y * layer_stride8 + i] = src[blockIdx.y * layer_stride8 + i];
 }
+// blockIdx.z = pair; every pair copies positions [0, n_pos) of every layer (blockIdx.y)
+__global__ void kv_copy_batch_kernel(const Engine::KvCopy * __restrict__ list, size_t layer_stride8, int row8) {
+    const Engine::KvCopy c = list[blockIdx.z];
+    const size_t n8 = (size_t) c.n_pos * row8;
+    const uint4 * src = reinterpret_cast<const uint4 *>(c.src) + blockIdx.y * layer_stride8;
+    uint4 * dst = reinterpret_cast<uint4 *>(c.dst) + blockIdx.y * layer_stride8;
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t) gridDim.x * blockDim.x) dst[i] = src[i];
+}
 }  // namespace
 
 bool Engine::init(int dev, bool fa) {
@@ -108,7 +116,7 @@ void Engine::prof_reset() {
 Engine::~Engine() {
     prof_collect();
     for (auto e : prof_pool) cudaEventDestroy(e);
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < 3; ++i)
         if (h_pinned[i]) cudaFreeHost(h_pinned[i]);
     if (stream) cudaStreamDestroy(stream);
 }
@@ -366,7 +374,7 @@ bool Engine::decode(const std::vector<DecRow> & rows, const std::vector<int> & l
     auto sz = [&](size_t b) { need += round_up<size_t>(b, 256); };
     sz((size_t) R * d * 4); sz((size_t) R * d * 2); sz((size_t) R * 3 * d * 2); sz((size_t) R * d * 2); sz((size_t) R * d * 2);
     sz((size_t) R * 4 * d * 2); sz((size_t) std::max(1, RL) * d * 2); sz(R * sizeof(DecRow)); sz(std::max(1, RL) * sizeof(int));
-    sz(R * sizeof(int2));
+    sz(R * sizeof(int2)); sz((size_t) (d / 64 + 1) * R * sizeof(float2));
     if (!ws.begin(need)) return false;
     float * x = (float *) ws.take((size_t) R * d * 4);
     void * h16 = ws.take((size_t) R * d * 2);
@@ -378,6 +386,7 @@ bool Engine::decode(const std::vector<DecRow> & rows, const std::vector<int> & l
     DecRow * d_rows = (DecRow *) ws.take(R * sizeof(DecRow));
     int * d_lrows = (int *) ws.take(std::max(1, RL) * sizeof(int));
     int2 * d_groups = (int2 *) ws.take(R * sizeof(int2));
+    float2 * ln_part = (float2 *) ws.take((size_t) (d / 64 + 1) * R * sizeof(float2));
     if (!logits.reserve((size_t) std::max(1, RL) * ld_logits * 4)) return false;
 
     // runs of consecutive rows that attend to the same window (prompt tokens of a window, beams of a stream): the cross-
@@ -408,7 +417,9 @@ bool Engine::decode(const std::vector<DecRow> & rows, const std::vector<int> & l
         // few rows: stream the weights with every SM -- tcgen05 version (tc_skinny.cu) unless WHISPER_B200_TC_SKINNY=0, else
         // the mma.sync one (skinny_gemm.cu); many rows (long prompts): tensor-core tiles (tc_gemm.cu)
         static const bool tcs = !(getenv("WHISPER_B200_TC_SKINNY") && atoi(getenv("WHISPER_B200_TC_SKINNY")) == 0);
-        if (g.M <= 128) {
+        if (g.ln_x || g.ln_part_out) {
+            ok = ok && tc_skinny_usable(g) && tc_skinny_gemm(g, stream);       // LayerNorm-fused forms exist on this kernel only
+        } else if (g.M <= 128) {
             ok = ok && (tcs && tc_skinny_usable(g) ? tc_skinny_gemm(g, stream) : skinny_gemm(g, skinny_ws, stream));
         } else if (g.M <= 512 && tcs && !g.pos) {
             // short prompts (a handful of tokens per window): 128 x 256 tensor-core tiles would leave most SMs without a tile
@@ -443,6 +454,17 @@ bool Engine::decode(const std::vector<DecRow> & rows, const std::vector<int> & l
     for (int i = 1; i < R && fuse_append; ++i)
         if (rows[i].self_kv == rows[i - 1].self_kv) fuse_append = false;
     if (fuse_append && chain_usable(R)) return decode_chain(rows, logit_rows, cross_layer_stride);
+    // Single-token step with at most 64 rows: the three LayerNorms of a layer are folded into their neighbours -- the GEMM that
+    // produces the residual stream (O, cross-O, MLP-down) also emits per-tile row statistics, and the GEMM that consumes the
+    // normalised rows (QKV, cross-Q, MLP-up) builds its A operand from the f32 stream itself (tc_skinny.cu).  Saves three
+    // dependent launches per layer; only the very first and the final LayerNorm of a step remain kernels of their own.
+    static const bool ln_fuse_env = !(getenv("WHISPER_B200_LN_FUSE") && atoi(getenv("WHISPER_B200_LN_FUSE")) == 0);
+    static const bool tcs_env = !(getenv("WHISPER_B200_TC_SKINNY") && atoi(getenv("WHISPER_B200_TC_SKINNY")) == 0);
+    const bool fuse_ln = ln_fuse_env && tcs_env && fuse_append && R <= 64 && d % 64 == 0;
+    auto ln_consumer = [&](GemmArgs & g, const float * gw, const float * gb) {      // A operand = LayerNorm(x) with (gw, gb)
+        g.a = nullptr; g.lda = 0;
+        g.ln_x = x; g.ld_lnx = d; g.ln_part_in = ln_part; g.ln_gamma = gw; g.ln_beta = gb; g.ln_eps = hp.eps;
+    };
 
     prof_begin(PC_DEC_MISC, (double) R * d * 10.0);
     dec_embed(dt, model.d_te, model.d_pe, d_rows, R, d, x, stream);
@@ -450,11 +472,12 @@ bool Engine::decode(const std::vector<DecRow> & rows, const std::vector<int> & l
     n_kernel_launches += 1;
     for (int il = 0; il < hp.n_text_layer; ++il) {
         const DecLayer & L = model.dec[il];
-        ln(L.ln1_w, L.ln1_b);
+        if (!fuse_ln || il == 0) ln(L.ln1_w, L.ln1_b);
         {
             GemmArgs g;   // Q and K carry dh^-0.25 each (src/whisper.cpp:2506, 2550, 2557); V is biased only
             g.dtype = dt; g.M = R; g.N = 3 * d; g.K = d; g.a = h16; g.lda = d; g.w = L.wqkv; g.ldw = d;
             g.bias = L.bqkv; g.scale = qk_scale; g.scale_cols = 2 * d; g.out16 = qkv; g.ldo16 = 3 * d;
+            if (fuse_ln && il > 0) ln_consumer(g, L.ln1_w, L.ln1_b);
             gemm(g);
         }
         if (!fuse_append) {
@@ -473,13 +496,15 @@ bool Engine::decode(const std::vector<DecRow> & rows, const std::vector<int> & l
             GemmArgs g;
             g.dtype = dt; g.M = R; g.N = d; g.K = d; g.a = att; g.lda = d; g.w = L.wo; g.ldw = d;
             g.bias = L.bo; g.resid = x; g.ldr = d; g.out32 = x; g.ldo32 = d;
+            if (fuse_ln) g.ln_part_out = ln_part;
             gemm(g);
         }
-        ln(L.lnx_w, L.lnx_b);
+        if (!fuse_ln) ln(L.lnx_w, L.lnx_b);
         {
             GemmArgs g;
             g.dtype = dt; g.M = R; g.N = d; g.K = d; g.a = h16; g.lda = d; g.w = L.wxq; g.ldw = d;
             g.bias = L.bxq; g.out16 = q16; g.ldo16 = d;
+            if (fuse_ln) ln_consumer(g, L.lnx_w, L.lnx_b);
             gemm(g);
         }
         prof_begin(PC_CROSS_ATTN, (double) R * cross_T * 2.0 * d * 2.0);
@@ -490,19 +515,22 @@ bool Engine::decode(const std::vector<DecRow> & rows, const std::vector<int> & l
             GemmArgs g;
             g.dtype = dt; g.M = R; g.N = d; g.K = d; g.a = att; g.lda = d; g.w = L.wxo; g.ldw = d;
             g.bias = L.bxo; g.resid = x; g.ldr = d; g.out32 = x; g.ldo32 = d;
+            if (fuse_ln) g.ln_part_out = ln_part;
             gemm(g);
         }
-        ln(L.ln2_w, L.ln2_b);
+        if (!fuse_ln) ln(L.ln2_w, L.ln2_b);
         {
             GemmArgs g;
             g.dtype = dt; g.M = R; g.N = 4 * d; g.K = d; g.a = h16; g.lda = d; g.w = L.w1; g.ldw = d;
             g.bias = L.b1; g.gelu = true; g.out16 = mlp; g.ldo16 = 4 * d;
+            if (fuse_ln) ln_consumer(g, L.ln2_w, L.ln2_b);
             gemm(g);
         }
         {
             GemmArgs g;
             g.dtype = dt; g.M = R; g.N = d; g.K = 4 * d; g.a = mlp; g.lda = 4 * d; g.w = L.w2; g.ldw = 4 * d;
             g.bias = L.b2; g.resid = x; g.ldr = d; g.out32 = x; g.ldo32 = d;
+            if (fuse_ln && il + 1 < hp.n_text_layer) g.ln_part_out = ln_part;
             gemm(g);
         }
     }
@@ -855,6 +883,26 @@ bool Engine::kv_copy_prefix(const void * src, void * dst, int n_pos) {
     const size_t n8 = (size_t) n_pos * 2 * d / 8;
     dim3 grid((unsigned) ceil_div<size_t>(n8, 256), model.hp.n_text_layer);
     kv_copy_prefix_kernel<<<grid, 256, 0, stream>>>((const uint4 *) src, (uint4 *) dst, layer8, n8);
+    n_kernel_launches += 1;
+    WB_CUDA(cudaGetLastError());
+    return !cuda_failed();
+}
+
+bool Engine::kv_copy_prefix_batch(const std::vector<KvCopy> & copies) {
+    const int n = (int) copies.size();
+    if (n == 0) return true;
+    const int d = model.hp.n_text_state;
+    const size_t bytes = n * sizeof(KvCopy);
+    if (!kv_copy_list.reserve(bytes)) return false;
+    // (the previous list's H2D copy has completed: every decode step ends with a synchronising read-back of the selection)
+    void * hb = pinned(2, bytes);
+    memcpy(hb, copies.data(), bytes);
+    WB_CUDA(cudaMemcpyAsync(kv_copy_list.p, hb, bytes, cudaMemcpyHostToDevice, stream));
+    int max_pos = 1;
+    for (const auto & c : copies) max_pos = std::max(max_pos, c.n_pos);
+    const int row8 = 2 * d / 8;
+    dim3 grid((unsigned) std::min<size_t>(ceil_div<size_t>((size_t) max_pos * row8, 256), 64), model.hp.n_text_layer, n);
+    kv_copy_batch_kernel<<<grid, 256, 0, stream>>>((const KvCopy *) kv_copy_list.p, (size_t) model.hp.n_text_ctx * row8, row8);
     n_kernel_launches += 1;
     WB_CUDA(cudaGetLastError());
     return !cuda_failed();

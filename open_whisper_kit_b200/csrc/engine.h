@@ -99,8 +99,9 @@ struct Engine {
     std::vector<double> chain_trace_acc;
     long long chain_trace_steps = 0;
     int ld_logits = 0;
-    void * h_pinned[2] = {nullptr, nullptr};   // pinned host staging: [0] decoder rows (H2D), [1] sampler I/O
-    size_t h_pinned_cap[2] = {0, 0};
+    void * h_pinned[3] = {nullptr, nullptr, nullptr};   // pinned host staging: [0] decoder rows (H2D), [1] sampler I/O, [2] KV copy lists
+    size_t h_pinned_cap[3] = {0, 0, 0};
+    DeviceBlock kv_copy_list;
     long long n_kernel_launches = 0;   // launches of our own kernels (bench.py reports them)
 
     // profiler
@@ -148,6 +149,8 @@ struct Engine {
                 const SampleParams & prm, std::vector<SampleOut> & out, std::vector<DrawOut> & draws);
     bool token_prob(const std::vector<SampleRow> & srows, int token, std::vector<float> & out);
     bool kv_copy_prefix(const void * src, void * dst, int n_pos);    // self-KV: positions [0, n_pos) of every layer
+    struct KvCopy { const void * src; void * dst; int n_pos; };
+    bool kv_copy_prefix_batch(const std::vector<KvCopy> & copies);   // the same for many (src, dst) pairs in ONE launch
 
     size_t self_kv_bytes() const {
         return (size_t) model.hp.n_text_layer * model.hp.n_text_ctx * 2 * model.hp.n_text_state * 2;

@@ -420,11 +420,15 @@ static int lang_from_logits(const Vocab & vocab, const float * logits, float * l
 // ---- the batched whisper_full ---------------------------------------------------------------------------------
 namespace {
 
+// One hypothesis of a beam-search step: beam `decoder_idx` continued by `token`.  The reference copies the parent's whole
+// whisper_sequence into every candidate (src/whisper.cpp:7280-7291); here a candidate is a (parent, token) pair and sequences are
+// materialised only for the beams that actually change parent.
 struct beam_candidate {
     int decoder_idx;
     int seek_delta;
     bool has_ts;
-    whisper_sequence sequence;
+    whisper_token_data token;
+    double sum_logprobs_all;
 };
 
 enum class Phase { WINDOW, PROMPT, STEPPING, RANK, DONE };
@@ -1078,7 +1082,8 @@ static int run_streams_locked(whisper_context & ctx, std::vector<StreamSpec> & s
             }
 
             // B3. token loop (src/whisper.cpp:7219-7544)
-            std::vector<std::vector<beam_candidate>> bc_per_dec;
+            std::vector<beam_candidate> cands;
+            std::vector<Engine::KvCopy> kv_copies;
             for (int i = 0; i < n_max; ++i) {
                 const int64_t ts0 = time_us();
                 bool any_live = false;
@@ -1104,9 +1109,7 @@ static int run_streams_locked(whisper_context & ctx, std::vector<StreamSpec> & s
                     whisper_state * st = s.state;
                     const auto & p = s.params;
                     const bool beam = p.strategy == WHISPER_SAMPLING_BEAM_SEARCH;
-                    if (beam) {
-                        bc_per_dec.assign(s.n_decoders_cur, {});
-                    }
+                    if (beam) cands.clear();
                     // sampling
                     for (int j = 0; j < s.n_decoders_cur; ++j) {
                         whisper_decoder & d = st->decoders[j];
@@ -1122,47 +1125,65 @@ static int run_streams_locked(whisper_context & ctx, std::vector<StreamSpec> & s
                             d.sequence.tokens.push_back(tok);
                             d.sequence.sum_logprobs_all += tok.plog;
                         } else {
-                            const auto & toks = d.sampled;
-                            for (const auto & t : toks) {
-                                bc_per_dec[j].push_back({j, d.seek_delta, d.has_ts, d.sequence});
-                                bc_per_dec[j].back().sequence.tokens.push_back(t);
-                                bc_per_dec[j].back().sequence.sum_logprobs_all += t.plog;
-                            }
+                            for (const auto & t : d.sampled)
+                                cands.push_back({j, d.seek_delta, d.has_ts, t, d.sequence.sum_logprobs_all + t.plog});
+                            if (!d.sampled.empty()) st->n_sample += 1;
                         }
                     }
                     if (beam) {
-                        std::vector<beam_candidate> cands;
-                        for (const auto & bc : bc_per_dec) {
-                            cands.insert(cands.end(), bc.begin(), bc.end());
-                            if (!bc.empty()) st->n_sample += 1;
-                        }
+                        // rank the hypotheses (same comparator, same input order as the reference -> same permutation)
                         std::sort(cands.begin(), cands.end(), [](const beam_candidate & a, const beam_candidate & b) {
-                            if (a.sequence.sum_logprobs_all != b.sequence.sum_logprobs_all)
-                                return a.sequence.sum_logprobs_all > b.sequence.sum_logprobs_all;
+                            if (a.sum_logprobs_all != b.sum_logprobs_all) return a.sum_logprobs_all > b.sum_logprobs_all;
                             return a.decoder_idx < b.decoder_idx;
                         });
+                        // two hypotheses are the same sequence if they append the same token to the same history
+                        auto same_sequence = [&](const beam_candidate & a, const beam_candidate & b) {
+                            if (a.token.id != b.token.id) return false;
+                            if (a.decoder_idx == b.decoder_idx) return true;
+                            const auto & ta = st->decoders[a.decoder_idx].sequence.tokens;
+                            const auto & tb = st->decoders[b.decoder_idx].sequence.tokens;
+                            if (ta.size() != tb.size()) return false;
+                            for (int k = (int) ta.size() - 1; k >= 0; --k)
+                                if (ta[k].id != tb[k].id) return false;
+                            return true;
+                        };
+                        // pass 1 (reads only): which hypothesis every live beam continues with (src/whisper.cpp:7305-7334)
+                        int chosen[WHISPER_MAX_DECODERS];
                         uint32_t cur_c = 0;
-                        const int n_past_kv = (int) s.prompt.size() + i;
-                        std::vector<int> swapped;
                         for (int j = 0; j < s.n_decoders_cur; ++j) {
-                            whisper_decoder & d = st->decoders[j];
+                            chosen[j] = -1;
+                            const whisper_decoder & d = st->decoders[j];
                             if (d.completed || d.failed) continue;
                             if (cur_c >= cands.size()) cur_c = 0;
-                            auto & cur = cands[cur_c++];
-                            while (cands.size() > cur_c && sequences_equal(cands[cur_c].sequence, cur.sequence) && i > 0) ++cur_c;
+                            const beam_candidate & cur = cands[cur_c];
+                            chosen[j] = (int) cur_c++;
+                            while (cands.size() > cur_c && same_sequence(cands[cur_c], cur) && i > 0) ++cur_c;
+                        }
+                        // pass 2: beams that change parent take a copy of the parent's OLD sequence and self-attention history
+                        // (into the alternate cache; all copies of the step go out as one launch after the stream loop) ...
+                        const int n_past_kv = (int) s.prompt.size() + i;
+                        whisper_sequence moved[WHISPER_MAX_DECODERS];
+                        for (int j = 0; j < s.n_decoders_cur; ++j) {
+                            if (chosen[j] < 0 || cands[chosen[j]].decoder_idx == j) continue;
+                            whisper_decoder & d = st->decoders[j];
+                            moved[j] = st->decoders[cands[chosen[j]].decoder_idx].sequence;
+                            if (!d.kv_alt.reserve(e.self_kv_bytes())) return -7;
+                            kv_copies.push_back({st->decoders[cands[chosen[j]].decoder_idx].kv.p, d.kv_alt.p, n_past_kv});
+                        }
+                        // ... then every live beam appends its token
+                        for (int j = 0; j < s.n_decoders_cur; ++j) {
+                            if (chosen[j] < 0) continue;
+                            const beam_candidate & cur = cands[chosen[j]];
+                            whisper_decoder & d = st->decoders[j];
+                            if (cur.decoder_idx != j) {
+                                d.sequence = std::move(moved[j]);
+                                std::swap(d.kv.p, d.kv_alt.p);          // valid once this step's copy launch has run (before the decode)
+                                std::swap(d.kv.cap, d.kv_alt.cap);
+                            }
                             d.seek_delta = cur.seek_delta;
                             d.has_ts = cur.has_ts;
-                            d.sequence = cur.sequence;
-                            // KV history of the parent beam: copy into the alternate buffer, swap afterwards
-                            if (cur.decoder_idx != j) {
-                                if (!d.kv_alt.reserve(e.self_kv_bytes())) return -7;
-                                e.kv_copy_prefix(st->decoders[cur.decoder_idx].kv.p, d.kv_alt.p, n_past_kv);
-                                swapped.push_back(j);
-                            }
-                        }
-                        for (int j : swapped) {
-                            std::swap(st->decoders[j].kv.p, st->decoders[j].kv_alt.p);
-                            std::swap(st->decoders[j].kv.cap, st->decoders[j].kv_alt.cap);
+                            d.sequence.tokens.push_back(cur.token);
+                            d.sequence.sum_logprobs_all = cur.sum_logprobs_all;
                         }
                     }
                     // per-decoder state machine
@@ -1217,6 +1238,10 @@ static int run_streams_locked(whisper_context & ctx, std::vector<StreamSpec> & s
                 for (int si : act) S[si].state->t_sample_us += (ts1 - ts0) / (int64_t) act.size();
                 if (!any_live) break;
 
+                if (!kv_copies.empty()) {           // the parent histories of every beam that changed parent in this step
+                    if (!e.kv_copy_prefix_batch(kv_copies)) return -7;
+                    kv_copies.clear();
+                }
                 // next-token rows of every live sequence
                 rows.clear();
                 lrows.clear();

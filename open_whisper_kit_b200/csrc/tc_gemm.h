@@ -24,6 +24,17 @@ struct GemmArgs {
     // (w, t, kv, h, c) goes to out16[w * T * N + ((h * 2 + kv) * T + t) * 64 + c] -- each (window, head) stream contiguous.
     int head_major_T = 0;
     float * out32 = nullptr;    int ldo32 = 0;
+    // ---- LayerNorm folded into the decoder-step GEMMs (tc_skinny only; see tc_skinny.cu) ----
+    // producer side: besides out32 (the new residual stream) the epilogue writes, per 64-column tile and row, the tile's mean
+    // and centred sum of squares of out32 -> ln_part_out[tile * M + row]
+    float2 * ln_part_out = nullptr;
+    // consumer side: a == nullptr; the A operand is LayerNorm(ln_x) built by the kernel itself from the f32 rows ln_x[M][ld_lnx]
+    // and the n = K / 64 partial statistics per row that the producer left in ln_part_in (combined with Chan's formula)
+    const float * ln_x = nullptr; int ld_lnx = 0;
+    const float2 * ln_part_in = nullptr;
+    const float * ln_gamma = nullptr;
+    const float * ln_beta = nullptr;
+    float ln_eps = 1e-5f;
 };
 
 // Returns false when the arguments violate the kernel's alignment contract or the launch failed.

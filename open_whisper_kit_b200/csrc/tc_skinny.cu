@@ -40,7 +40,7 @@ constexpr int T_THREADS = 192;
 // of 5 x 16 KB still fit the 164 KB shared-memory carve-out; one more stage moves the SM to the 228 KB carve-out, which
 // stays in force for the cross-attention kernel that follows and costs it a third of its speed (28 KB of L1 left).
 constexpr int T_STAGES = 5;
-constexpr int T_CTRL_BYTES = 128;         // mbarriers + TMEM base address, behind the ring
+constexpr int T_CTRL_BYTES = 128 + 512;   // mbarriers + TMEM base address | per-row {mean, rstd} of the LayerNorm-fused A operand
 constexpr int T_PITCH = 68;               // floats per row of the f32 tile in shared memory
 
 struct TcSkinnyParams {
@@ -53,6 +53,12 @@ struct TcSkinnyParams {
     void * out16; int ldo16;
     float * out32; int ldo32;
     unsigned long long * trace;        // development aid (WHISPER_B200_TCS_TRACE): 8 time stamps per CTA, or null
+    // LayerNorm fusion (GemmArgs): statistics of the output rows for the next GEMM / A operand = LayerNorm(ln_x) built in place
+    float2 * ln_part_out;
+    const float * ln_x; int ld_lnx;
+    const float2 * ln_part_in;
+    const float * ln_gamma; const float * ln_beta;
+    float ln_eps;
 };
 
 __device__ __forceinline__ unsigned long long gtime() {
@@ -95,7 +101,9 @@ tc_skinny_kernel(const __grid_constant__ TMap tm_x, const __grid_constant__ TMap
     uint64_t * b_empty = b_full + T_STAGES;
     uint64_t & b_acc = b_empty[T_STAGES];
     uint32_t & s_tmem = *reinterpret_cast<uint32_t *>(b_empty + T_STAGES + 1);
-    static_assert((2 * T_STAGES + 2) * 8 <= T_CTRL_BYTES, "control block");
+    static_assert((2 * T_STAGES + 2) * 8 <= 128, "control block");
+    float2 * s_stat = reinterpret_cast<float2 *>(reinterpret_cast<uint8_t *>(b_full) + 128);      // [64] rows (LayerNorm-fused A operand)
+    const bool ln_in = p.ln_x != nullptr;
     // [rows_pad][T_PITCH] f32; overlays the operand ring, which is dead once the last MMA has completed
     float * tile_sum = reinterpret_cast<float *>(smem);
 
@@ -134,7 +142,7 @@ tc_skinny_kernel(const __grid_constant__ TMap tm_x, const __grid_constant__ TMap
     if (tid == 0) {
         if (ptx::smem_u32(smem) & 1023u) __trap();
         for (int s = 0; s < T_STAGES; ++s) {
-            ptx::mbar_init(&b_full[s], 1);
+            ptx::mbar_init(&b_full[s], ln_in ? 2 : 1);        // TMA producer (+ the warps that build the normalised A tile)
             ptx::mbar_init(&b_empty[s], 1);
         }
         ptx::mbar_init(&b_acc, 1);
@@ -156,8 +164,9 @@ tc_skinny_kernel(const __grid_constant__ TMap tm_x, const __grid_constant__ TMap
             ptx::prefetch_tensormap(&tm_x);
             ptx::prefetch_tensormap(&tm_w);
             const int npre = nkb < T_STAGES ? nkb : T_STAGES;
+            const uint32_t tx_bytes = ln_in ? TB * 128u : stage_bytes;      // LayerNorm-fused: only the weight half arrives by TMA
             for (int i = 0; i < npre; ++i) {                  // weights first: they do not depend on the predecessor grid
-                ptx::mbar_arrive_expect_tx(&b_full[i], stage_bytes);
+                ptx::mbar_arrive_expect_tx(&b_full[i], tx_bytes);
                 ptx::tma_load_2d(smem + i * stage_bytes + x_bytes, &tm_w, &b_full[i], (kb0 + i) * TB, n0);
             }
             pdl_wait();
@@ -165,10 +174,10 @@ tc_skinny_kernel(const __grid_constant__ TMap tm_x, const __grid_constant__ TMap
                 const int s = i % T_STAGES;
                 if (i >= npre) {
                     ts_wait(&b_empty[s], ((i / T_STAGES) - 1) & 1);
-                    ptx::mbar_arrive_expect_tx(&b_full[s], stage_bytes);
+                    ptx::mbar_arrive_expect_tx(&b_full[s], tx_bytes);
                     ptx::tma_load_2d(smem + s * stage_bytes + x_bytes, &tm_w, &b_full[s], (kb0 + i) * TB, n0);
                 }
-                ptx::tma_load_2d(smem + s * stage_bytes, &tm_x, &b_full[s], (kb0 + i) * TB, 0);
+                if (!ln_in) ptx::tma_load_2d(smem + s * stage_bytes, &tm_x, &b_full[s], (kb0 + i) * TB, 0);
             }
         }
         pdl_wait();
@@ -197,6 +206,67 @@ tc_skinny_kernel(const __grid_constant__ TMap tm_x, const __grid_constant__ TMap
         pdl_wait();
         TS_STAMP(1);      // predecessor grid complete
         preload();
+        if (ln_in) {
+            // ===== A operand = LayerNorm(ln_x), built here instead of by a kernel of its own (rows_pad == 64, checked on the host) =====
+            // (1) row statistics: the producer GEMM left {mean, centred sum of squares} per 64-column tile; thread r combines the
+            //     K / 64 partials of row r in tile order (Chan et al.), which is as accurate as a two-pass variance.
+            if (tid < 64) {
+                float mean = 0.0f, m2 = 0.0f, cnt = 0.0f;
+                if (tid < p.M) {
+                    const int n_part = p.K / TB;
+                    for (int t = 0; t < n_part; ++t) {
+                        const float2 q = p.ln_part_in[(size_t) t * p.M + tid];
+                        const float delta = q.x - mean, tot = cnt + (float) TB;
+                        mean += delta * ((float) TB / tot);
+                        m2 += q.y + delta * delta * (cnt * (float) TB / tot);
+                        cnt = tot;
+                    }
+                }
+                s_stat[tid] = make_float2(mean, 1.0f / sqrtf(m2 / (float) p.K + p.ln_eps));
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            // (2) per k-block: thread (r8 = tid / 16, c4 = tid % 16) normalises four consecutive columns of rows r8, r8 + 8, ...
+            //     and stores them as 8 bytes of the 128-byte-swizzled K-major tile the MMA descriptor expects (16-byte chunk
+            //     index XOR row % 8).  Up to three k-blocks of loads are in flight per thread.
+            const int c4 = tid & 15, r8 = tid >> 4;
+            for (int i0 = 0; i0 < nkb; i0 += 3) {
+                const int nb = nkb - i0 < 3 ? nkb - i0 : 3;
+                float4 xv[3][8];
+#pragma unroll
+                for (int b = 0; b < 3; ++b) {
+                    if (b >= nb) break;
+                    const float * src = p.ln_x + (size_t) (kb0 + i0 + b) * TB + 4 * c4;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int r = r8 + 8 * j;
+                        xv[b][j] = r < p.M ? *reinterpret_cast<const float4 *>(src + (size_t) r * p.ld_lnx) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    }
+                }
+#pragma unroll
+                for (int b = 0; b < 3; ++b) {
+                    if (b >= nb) break;
+                    const int i = i0 + b, s = i % T_STAGES;
+                    if (i >= T_STAGES) ts_wait(&b_empty[s], ((i / T_STAGES) - 1) & 1);
+                    const int k = (kb0 + i) * TB + 4 * c4;
+                    const float4 g = __ldg(reinterpret_cast<const float4 *>(p.ln_gamma + k));
+                    const float4 be = __ldg(reinterpret_cast<const float4 *>(p.ln_beta + k));
+                    uint8_t * xs = smem + s * stage_bytes;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int r = r8 + 8 * j;
+                        const float2 st = s_stat[r];
+                        const float4 v = xv[b][j];
+                        const T16 h[4] = {Half16<T16>::from_f((v.x - st.x) * st.y * g.x + be.x), Half16<T16>::from_f((v.y - st.x) * st.y * g.y + be.y),
+                                          Half16<T16>::from_f((v.z - st.x) * st.y * g.z + be.z), Half16<T16>::from_f((v.w - st.x) * st.y * g.w + be.w)};
+                        const uint2 pk = r < p.M ? *reinterpret_cast<const uint2 *>(h) : make_uint2(0u, 0u);
+                        *reinterpret_cast<uint2 *>(xs + r * 128 + (((c4 >> 1) ^ (r & 7)) << 4) + ((c4 & 1) << 3)) = pk;
+                    }
+                    ptx::fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core's async proxy
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (tid == 0) ptx::mbar_arrive(&b_full[s]);
+                }
+            }
+        }
         const int row = warp * 32 + lane;
         if (nkb > 0) {
             ts_wait(&b_acc, 0);
@@ -284,6 +354,20 @@ tc_skinny_kernel(const __grid_constant__ TMap tm_x, const __grid_constant__ TMap
                     if (n + i < p.scale_cols) y *= p.scale;
                     if (p.gelu) y = gelu_ts<T16>(y, p.ref_f16_gelu);
                     x[i] = y + r4[i];
+                }
+                if (p.ln_part_out) {
+                    // statistics of this row's 64 output columns for the LayerNorm folded into the next GEMM: the 16 units of a
+                    // row sit in 16 consecutive lanes (the host only asks for this when every K split owns whole rows)
+                    const unsigned hm = 0xffffu << (lane & 16);
+                    float sm = (x[0] + x[1]) + (x[2] + x[3]);
+#pragma unroll
+                    for (int o = 8; o > 0; o >>= 1) sm += __shfl_xor_sync(hm, sm, o);
+                    const float mean = sm * (1.0f / (float) TB);
+                    const float d0 = x[0] - mean, d1 = x[1] - mean, d2 = x[2] - mean, d3 = x[3] - mean;
+                    float sq = (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+#pragma unroll
+                    for (int o = 8; o > 0; o >>= 1) sq += __shfl_xor_sync(hm, sq, o);
+                    if ((lane & 15) == 0) p.ln_part_out[(size_t) nt * p.M + m] = make_float2(mean, sq);
                 }
                 if (p.vec_io && n + 3 < p.N) {
                     if (p.out32) *reinterpret_cast<float4 *>(p.out32 + (size_t) m * p.ldo32 + n) = make_float4(x[0], x[1], x[2], x[3]);
@@ -390,8 +474,17 @@ struct TcsTrace {
 }  // namespace
 
 bool tc_skinny_usable(const GemmArgs & g) {
-    return g.M > 0 && g.M <= 128 && g.K % TB == 0 && g.lda % 8 == 0 && g.ldw % 8 == 0 && !g.pos &&
-           !(reinterpret_cast<uintptr_t>(g.a) & 15) && !(reinterpret_cast<uintptr_t>(g.w) & 15);
+    const bool base = g.M > 0 && g.M <= 128 && g.K % TB == 0 && g.ldw % 8 == 0 && !g.pos && !(reinterpret_cast<uintptr_t>(g.w) & 15);
+    if (!base) return false;
+    if (g.ln_x) {       // LayerNorm-fused A operand: 64 rows at most, 16-byte addressable f32 rows and affine parameters
+        if (g.M > 64 || !g.ln_part_in || !g.ln_gamma || !g.ln_beta || g.ld_lnx % 4 != 0) return false;
+        if ((reinterpret_cast<uintptr_t>(g.ln_x) | reinterpret_cast<uintptr_t>(g.ln_gamma) | reinterpret_cast<uintptr_t>(g.ln_beta)) & 15) return false;
+    } else if (g.lda % 8 != 0 || (reinterpret_cast<uintptr_t>(g.a) & 15)) {
+        return false;
+    }
+    // statistics out: whole 64-column tiles, and the units of a row must stay inside one half-warp of one K split
+    if (g.ln_part_out && (g.N % TB != 0 || !g.out32)) return false;
+    return true;
 }
 
 bool tc_skinny_gemm(const GemmArgs & g, cudaStream_t stream) {
@@ -412,11 +505,14 @@ bool tc_skinny_gemm(const GemmArgs & g, cudaStream_t stream) {
     int KS = std::max(ceil_div(n_sm, n_tiles), ceil_div(kblocks, T_STAGES));
     KS = std::min(KS, 8);
     while (KS > 1 && (n_tiles * KS > cta_per_sm * n_sm || KS > kblocks / 2)) --KS;
+    if (g.ln_part_out)                    // every K split must own whole rows of the tile: a power of two (rows_pad is 64 or 128)
+        while (KS & (KS - 1)) --KS;
 
     static std::mutex mu;
     static std::unordered_map<WKey, TMap, WKeyHash> wmaps;
     TMap tm_x, tm_w;
-    if (!tc_make_tmap(&tm_x, g.a, g.M, g.K, g.lda, rows_pad, g.dtype)) return false;
+    if (g.ln_x) memset(&tm_x, 0, sizeof(tm_x));           // never dereferenced: the kernel builds the A tiles itself
+    else if (!tc_make_tmap(&tm_x, g.a, g.M, g.K, g.lda, rows_pad, g.dtype)) return false;
     {
         std::lock_guard<std::mutex> lock(mu);
         const WKey key = {g.w, g.N, g.K, g.ldw, (int) g.dtype};
@@ -433,6 +529,8 @@ bool tc_skinny_gemm(const GemmArgs & g, cudaStream_t stream) {
     p.bias = g.bias; p.scale = g.scale; p.scale_cols = g.scale_cols;
     p.gelu = g.gelu ? 1 : 0; p.ref_f16_gelu = g.dtype == DType::F16 ? 1 : 0;
     p.resid = g.resid; p.ldr = g.ldr; p.out16 = g.out16; p.ldo16 = g.ldo16; p.out32 = g.out32; p.ldo32 = g.ldo32;
+    p.ln_part_out = g.ln_part_out; p.ln_x = g.ln_x; p.ld_lnx = g.ld_lnx; p.ln_part_in = g.ln_part_in;
+    p.ln_gamma = g.ln_gamma; p.ln_beta = g.ln_beta; p.ln_eps = g.ln_eps;
     static TcsTrace trace;
     p.trace = trace.slot({n_tiles, KS, g.M, g.N, g.K});
     auto al = [](const void * q, uintptr_t a) { return (reinterpret_cast<uintptr_t>(q) & (a - 1)) == 0; };

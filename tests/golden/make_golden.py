@@ -118,7 +118,7 @@ def run_gaps(ref, case):
     whisper_decode for the raw logits, ref_process_logits (harness hook around whisper_process_logits) for the rules.
     """
     from open_whisper_kit_b200 import capi
-    assert case["no_timestamps"] and case["pcm"]["kind"] == "synth"
+    assert case["no_timestamps"]
     w = api.Whisper(ref, model_path(case["arch"], case["ftype"]), use_gpu=False, flash_attn=case["flash_attn"])
     p = w.greedy_params(no_timestamps=True, n_threads=8)
     n_vocab = ref.whisper_n_vocab(w.ctx)
@@ -127,7 +127,10 @@ def run_gaps(ref, case):
     lo = np.empty(n_vocab, np.float32)
     for wi, seg in enumerate(case["segments"]):
         toks = seg[2]
-        pcm = modelgen.synth_pcm(480000, seed=case["pcm"]["seed"], stream=wi)
+        if case["pcm"]["kind"] == "synth":
+            pcm = modelgen.synth_pcm(480000, seed=case["pcm"]["seed"], stream=wi)
+        else:
+            pcm = pcm_for(case["pcm"])          # one chunk = the whole file
         assert w.pcm_to_mel(pcm, 8) == 0 and w.encode(0, 8) == 0
         rc, lg = w.decode([sot, tnot], 0, 8)
         gaps, runner = [], []
@@ -161,7 +164,7 @@ def main():
     path = os.path.join(HERE, "golden_tokens.json")
     golden = json.load(open(path)) if os.path.exists(path) else {}
     for name, case in TOKEN_CASES.items():
-        if not any(name.startswith(c) for c in args.cases.split(",")):
+        if not any(name.startswith(c) for c in args.cases.split(",")) or (args.gaps and name in golden):
             continue
         print("running", name, flush=True)
         golden[name] = run_tokens(ref, case)
@@ -170,9 +173,12 @@ def main():
               "cpu s", golden[name]["reference_cpu_seconds"], flush=True)
         json.dump(golden, open(path, "w"), indent=0, sort_keys=True)
     if args.gaps:
-        name = "base.en/synth16/nots/fa0"
-        golden[name]["steps"] = run_gaps(ref, golden[name])
-        json.dump(golden, open(path, "w"), indent=0, sort_keys=True)
+        for name in ("base.en/synth16/nots/fa0", "tiny.en/jfk/nots/fa0"):
+            if "steps" in golden[name] or not any(name.startswith(c) for c in args.cases.split(",")):
+                continue
+            print("margins of", name, flush=True)
+            golden[name]["steps"] = run_gaps(ref, golden[name])
+            json.dump(golden, open(path, "w"), indent=0, sort_keys=True)
     if not args.skip_tensors:
         np.savez_compressed(os.path.join(HERE, "golden_tensors.npz"), **run_tensors(ref))
     print("reference variant", variant)

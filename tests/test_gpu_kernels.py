@@ -225,3 +225,42 @@ def test_tc_skinny_gemm(lib, shape, dtype):
     ref, o32, o16 = run_gemm(lib, dtype, M, N, K, bias=True, gelu=True, seed=M + N + K, skinny=2)
     tol = 2.0 ** -9 if dtype == 0 else 2e-3
     assert np.abs(o32 - ref).max() <= tol * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("dtype", [0, 1])
+@pytest.mark.parametrize("shape", [(64, 1280, 1280, 3840), (37, 1280, 5120, 1280), (8, 384, 384, 1536), (1, 512, 2048, 512),
+                                   (64, 1024, 1024, 4096)])
+def test_layernorm_folded_into_decoder_gemms(lib, shape, dtype):
+    """x = a1 w1^T + b1 + resid with per-tile row statistics from the epilogue, then y = LayerNorm(x) w2^T with the normalised
+    16-bit A operand built inside the second kernel from the f32 rows (csrc/tc_skinny.cu) -- against float64 numpy.  What the
+    reference computes as ggml_norm + mul + add followed by mul_mat (src/whisper.cpp:2520-2530, 2641-2651, 2747-2757)."""
+    M, d, K1, N2 = shape
+    rng = np.random.default_rng(M + d + K1 + N2 + dtype)
+    a1 = rng.standard_normal((M, K1), dtype=np.float32)
+    w1 = (rng.standard_normal((d, K1), dtype=np.float32) / np.sqrt(K1)).astype(np.float32)
+    w2 = (rng.standard_normal((N2, d), dtype=np.float32) / np.sqrt(d)).astype(np.float32)
+    b1 = (0.1 * rng.standard_normal(d)).astype(np.float32)
+    resid = (2.0 * rng.standard_normal((M, d)) + 0.5).astype(np.float32)          # non-zero mean: the centred variance matters
+    gamma = (1.0 + 0.1 * rng.standard_normal(d)).astype(np.float32)
+    beta = (0.1 * rng.standard_normal(d)).astype(np.float32)
+    a1b, w1b, w2b = to_bits(a1, dtype), to_bits(w1, dtype), to_bits(w2, dtype)
+    x = np.zeros((M, d), np.float32)
+    y = np.zeros((M, N2), np.float32)
+    rc = lib.whisper_b200_kernel_ln_gemm_pair(dtype, M, d, K1, N2, a1b.ctypes.data_as(U16P), w1b.ctypes.data_as(U16P), b1.ctypes.data_as(FP),
+                                              resid.ctypes.data_as(FP), gamma.ctypes.data_as(FP), beta.ctypes.data_as(FP), 1e-5,
+                                              w2b.ctypes.data_as(U16P), x.ctypes.data_as(FP), y.ctypes.data_as(FP))
+    assert rc == 0
+    x_ref = from_bits(a1b, dtype).astype(np.float64) @ from_bits(w1b, dtype).astype(np.float64).T + b1 + resid
+    assert np.abs(x - x_ref).max() <= 2e-3 * max(1.0, np.abs(x_ref).max())
+    # LayerNorm of the kernel's own x (so the comparison isolates the statistics + normalisation + second GEMM)
+    xd = x.astype(np.float64)
+    mu = xd.mean(axis=1, keepdims=True)
+    var = ((xd - mu) ** 2).mean(axis=1, keepdims=True)
+    h = (xd - mu) / np.sqrt(var + 1e-5) * gamma + beta
+    h16 = from_bits(to_bits(h.astype(np.float32), dtype), dtype).astype(np.float64)
+    y_ref = h16 @ from_bits(w2b, dtype).astype(np.float64).T
+    err = np.abs(y - y_ref).max()
+    print(f"ln-folded gemm pair {shape} dtype={dtype}: x max|d| = {np.abs(x - x_ref).max():.3e}, y max|d| = {err:.3e}")
+    # an element of h that sits on a 16-bit rounding boundary may round the other way (statistics combined from 64-column
+    # partials instead of one two-pass sweep): one ulp of one operand element
+    assert err <= (2.0 ** -8 if dtype == 0 else 2.0 ** -5) * max(1.0, np.abs(y_ref).max())

@@ -97,7 +97,8 @@ def run_case(lib, model_dir, case):
         return rc, [[int(s.t0), int(s.t1), [int(x) for x in s.tokens]] for s in segs], segs
 
 
-MARGIN = 4e-2        # 2 x the spec's logits tolerance (2e-2 max-abs): below it two conforming implementations may pick differently
+MARGIN = 5e-3        # flips are accepted only below this top-2 logit margin -- an eighth of 2 x the spec's logits tolerance (2e-2);
+                     # every flip measured so far sits below 1e-3 (profiles/r2_parity_report.json)
 
 
 def by_chunk(segments):
@@ -127,15 +128,15 @@ def test_greedy_tokens_identical_to_reference_golden(lib, model_dir, name, monke
     """Greedy tokens and segment times vs the reference CPU path (BASELINE.json configs 1 and 2).
 
     Bar: identical.  north_star also allows the logits to differ by 2e-2, and on random-init weights (Gaussian logits) the
-    reference's own top-1 / top-2 margin is below 2 x 2e-2 at ~10 % of the steps, whatever the scale of the init -- margins and
-    rounding errors scale together; the reference's AVX2 and AVX-512 builds diverge from each other on the base.en case (see
-    DESIGN.md).  So identity is REQUIRED wherever the reference's recorded margin allows it and a difference is accepted only
-    where it does not:
+    reference's own top-1 / top-2 margin is tiny at a fixed fraction of the steps, whatever the scale of the init -- margins and
+    rounding errors scale together (1.3 % of the steps are below MARGIN = 5e-3); the reference's AVX2 and AVX-512 builds diverge
+    from each other on the base.en case.  So identity is REQUIRED wherever the reference's recorded margin
+    allows it and a difference is accepted only where it does not:
       * case with recorded per-step margins (golden "steps", from the reference alone): every token before a chunk's first
         sub-margin step must be identical; the first mismatch of a chunk, if any, must sit ON a sub-margin step and be the
         reference's recorded runner-up;
       * other cases (no margins recorded -- timestamp mode): a chunk's first mismatch must be a near-tie of OUR two best
-        candidates (< MARGIN logits) with the reference's token as our runner-up; at most a quarter of the chunks may have one.
+        candidates (< MARGIN logits) with the reference's token as our runner-up; at most max(1, chunks / 4) chunks may have one.
     Every flip is written to gpurun_out/parity_report.json."""
     monkeypatch.setenv("WHISPER_B200_DEBUG_GAPS", "1")
     case = GOLD_TOK[name]
@@ -171,7 +172,7 @@ def test_greedy_tokens_identical_to_reference_golden(lib, model_dir, name, monke
     if not flips:
         assert [(s.t0, s.t1) for s in segs] == [(s[0], s[1]) for s in case["segments"]]
     if not steps:
-        assert len(flips) <= n_chunks // 4
+        assert len(flips) <= max(1, n_chunks // 4)
 
 
 def test_token_data_fields_match_live_reference(lib, model_dir):
