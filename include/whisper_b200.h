@@ -108,6 +108,14 @@ WB200_API double whisper_b200_kernel_gemm_bench(int dtype, int M, int N, int K, 
  * 2 self-attention at position aux, 3 KV append; R rows of width d. */
 WB200_API double whisper_b200_kernel_step_bench(int which, int dtype, int R, int d, int aux, int iters);
 
+/* ---- 16-bit PCM ingest -------------------------------------------------------------------------------------------------------
+ * whisper_pcm_to_mel / whisper_full_parallel for int16 mono 16 kHz samples: x = s / 32768 -- the conversion the reference's
+ * callers run on the host before the API (examples/common-whisper.cpp:42-134, miniaudio s16 -> f32) -- is applied inside the
+ * mel kernel's load stage, so half the bytes cross PCIe and HBM.  Results are bit-identical to passing the converted floats. */
+WB200_API int whisper_b200_pcm16_to_mel(struct whisper_context * ctx, const int16_t * samples, int n_samples);
+WB200_API int whisper_b200_full_parallel_i16(struct whisper_context * ctx, struct whisper_full_params params, const int16_t * samples,
+                                             int n_samples, int n_processors);
+
 /* ---- multi-GPU: a group of contexts, one model replica per GPU ------------------------------------------------------------
  * whisper_full_parallel (reference src/whisper.cpp:7801-7929) splits the audio into n_processors chunks and decodes them
  * independently; whisper_b200_group_full_parallel does the same split, deals the chunks out to the GPUs of the group in

@@ -138,7 +138,7 @@ bool Engine::run_mel(const std::vector<MelJob> & jobs) {
     const int n_mel = model.filt_n_mel;
     size_t stage_floats = 0;
     for (const auto & j : jobs)
-        if (j.pcm_host) stage_floats += round_up<size_t>(j.n_samples, 4);
+        if (j.pcm_host) stage_floats += round_up<size_t>(j.i16 ? (j.n_samples + 1) / 2 : j.n_samples, 4);
     if (!pcm_stage.reserve(stage_floats * 4)) return false;
     if (!meta.reserve(jobs.size() * sizeof(MelStream))) return false;
     std::vector<MelStream> sts(jobs.size());
@@ -160,16 +160,16 @@ bool Engine::run_mel(const std::vector<MelJob> & jobs) {
         const float * src = j.pcm_dev;
         if (j.pcm_host) {
             float * dst = (float *) pcm_stage.p + off;
-            WB_CUDA(cudaMemcpyAsync(dst, j.pcm_host, (size_t) j.n_samples * 4, cudaMemcpyHostToDevice, stream));
+            WB_CUDA(cudaMemcpyAsync(dst, j.pcm_host, (size_t) j.n_samples * (j.i16 ? 2 : 4), cudaMemcpyHostToDevice, stream));
             src = dst;
-            off += round_up<size_t>(j.n_samples, 4);
+            off += round_up<size_t>(j.i16 ? (j.n_samples + 1) / 2 : j.n_samples, 4);
         }
-        sts[i] = {src, j.n_samples, g.n_frames_fft, (float *) mb.data.p, g.stride, (unsigned *) mb.max_enc.p};
+        sts[i] = {src, j.n_samples, g.n_frames_fft, (float *) mb.data.p, g.stride, (unsigned *) mb.max_enc.p, j.i16 ? 1 : 0};
         max_frames = std::max(max_frames, g.n_frames_fft);
     }
     WB_CUDA(cudaMemcpyAsync(meta.p, sts.data(), sts.size() * sizeof(MelStream), cudaMemcpyHostToDevice, stream));
     double mel_bytes = 0.0;
-    for (const auto & j : jobs) mel_bytes += (double) j.n_samples * 4.0 + (double) (j.n_samples / 160) * n_mel * 4.0;
+    for (const auto & j : jobs) mel_bytes += (double) j.n_samples * (j.i16 ? 2.0 : 4.0) + (double) (j.n_samples / 160) * n_mel * 4.0;
     prof_begin(PC_MEL, mel_bytes);
     mel_launch(mel_plan, (const MelStream *) meta.p, (int) jobs.size(), max_frames, stream);
     prof_end();

@@ -57,6 +57,7 @@ struct CrossKV {
 struct MelJob {
     const float * pcm_host = nullptr;   // exactly one of pcm_host / pcm_dev
     const float * pcm_dev = nullptr;
+    bool i16 = false;                   // the pointer holds int16 samples (converted inside the mel kernel's load)
     int n_samples = 0;
     MelBuf * out = nullptr;
 };

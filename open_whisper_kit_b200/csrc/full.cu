@@ -439,6 +439,7 @@ struct Stream {
     const float * samples = nullptr;
     int n_samples = 0;
     bool samples_on_device = false;
+    bool samples_i16 = false;
     int detected_lang = -1;      // >= 0: language found by the batched detection pass of run_streams
     std::vector<float> detected_probs;
     int rc = 0;
@@ -495,13 +496,25 @@ static int stream_begin(whisper_context & ctx, Stream & s) {
         state->t_last = 0;
         state->tid_last = 0;
         if (s.n_samples > 0) {
-            if (s.samples_on_device) {
-                std::vector<float> host((size_t) s.n_samples);
-                if (cudaMemcpy(host.data(), s.samples, (size_t) s.n_samples * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
-                envelope_abs_mean(host.data(), s.n_samples, 32, state->energy);
-            } else {
-                envelope_abs_mean(s.samples, s.n_samples, 32, state->energy);
+            // the envelope is computed on the host from f32 samples: fetch / convert the stream when it is not that already
+            std::vector<float> host;
+            const float * pcm = s.samples;
+            if (s.samples_on_device || s.samples_i16) {
+                host.resize((size_t) s.n_samples);
+                std::vector<int16_t> h16;
+                const void * src = s.samples;
+                if (s.samples_on_device) {
+                    void * dst = s.samples_i16 ? (h16.resize((size_t) s.n_samples), (void *) h16.data()) : (void *) host.data();
+                    if (cudaMemcpy(dst, s.samples, (size_t) s.n_samples * (s.samples_i16 ? 2 : 4), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+                    src = dst;
+                }
+                if (s.samples_i16) {
+                    const int16_t * q = (const int16_t *) src;
+                    for (int k = 0; k < s.n_samples; ++k) host[k] = (float) q[k] * (1.0f / 32768.0f);
+                }
+                pcm = host.data();
             }
+            envelope_abs_mean(pcm, s.n_samples, 32, state->energy);
         }
     }
     s.seek_start = params.offset_ms / 10;
@@ -722,6 +735,7 @@ static int run_streams_locked(whisper_context & ctx, std::vector<StreamSpec> & s
             S[i].samples = specs[i].samples;
             S[i].n_samples = specs[i].n_samples;
             S[i].samples_on_device = specs[i].samples_on_device;
+            S[i].samples_i16 = specs[i].samples_i16;
             S[i].window = i;
             S[i].state->result_all.clear();
             if (specs[i].n_samples > 0) {
@@ -729,6 +743,7 @@ static int run_streams_locked(whisper_context & ctx, std::vector<StreamSpec> & s
                 if (specs[i].samples_on_device) j.pcm_dev = specs[i].samples;
                 else j.pcm_host = specs[i].samples;
                 j.n_samples = specs[i].n_samples;
+                j.i16 = specs[i].samples_i16;
                 j.out = &S[i].state->mel;
                 jobs.push_back(j);
             }

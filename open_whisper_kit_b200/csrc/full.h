@@ -14,6 +14,7 @@ struct StreamSpec {
     const float * samples = nullptr;
     int n_samples = 0;
     bool samples_on_device = false;
+    bool samples_i16 = false;          // `samples` points at int16 PCM (s / 32768 is applied by the mel kernel's load)
     int rc = 0;
 };
 

@@ -67,6 +67,7 @@ WB200_API int whisper_b200_kernel_log_mel(const float * pcm, int n_samples, cons
     st.out = d_raw.as<float>();
     st.out_stride = g.stride;
     st.max_enc = d_max.as<unsigned>();
+    st.pcm_i16 = 0;
     WB_CUDA(cudaMemcpy(d_st.p, &st, sizeof(st), cudaMemcpyHostToDevice));
     mel_launch(plan, d_st.as<MelStream>(), 1, g.n_frames_fft, 0);
     mel_finalize_launch(d_raw.as<float>(), g.stride, g.n_frames_fft, d_max.as<unsigned>(), d_fin.as<float>(), g.n_len,
@@ -95,7 +96,7 @@ WB200_API double whisper_b200_kernel_log_mel_bench(int n_streams, int n_samples,
         WB_CUDA(cudaMemcpy(d_pcm.as<float>() + (size_t) i * n_samples, h.data(), (size_t) n_samples * 4,
                            cudaMemcpyHostToDevice));
         sts[i] = {d_pcm.as<float>() + (size_t) i * n_samples, n_samples, g.n_frames_fft,
-                  d_raw.as<float>() + (size_t) i * n_mel * g.stride, g.stride, d_max.as<unsigned>() + i};
+                  d_raw.as<float>() + (size_t) i * n_mel * g.stride, g.stride, d_max.as<unsigned>() + i, 0};
     }
     WB_CUDA(cudaMemcpy(d_st.p, sts.data(), sizeof(MelStream) * n_streams, cudaMemcpyHostToDevice));
     WB_CUDA(cudaMemset(d_max.p, 0, (size_t) n_streams * 4));

@@ -118,27 +118,35 @@ mel_kernel(const MelStream * __restrict__ streams, const float * __restrict__ ta
     // ---- stage 1: PCM tile -> shared (padded[p] = p<200 ? x[200-p] : x[p-200], zero past the audio) ----
     {
         const float * __restrict__ x = st.pcm;
-        const bool vec_ok = ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+        const short * __restrict__ x16 = reinterpret_cast<const short *>(st.pcm);
+        const bool i16 = st.pcm_i16 != 0;
+        constexpr float kI16 = 1.0f / 32768.0f;                  // exact: a power of two
+        const bool vec_ok = ((reinterpret_cast<uintptr_t>(x) & (i16 ? 7 : 15)) == 0);
         for (int q4 = tid; q4 < kTileSamples / 4; q4 += kThreads) {
             const int q = q4 * 4;
             const long long p = p0 + q;
             float4 v;
             const long long s = p - kFrame / 2;
             if (vec_ok && s >= 0 && s + 3 < st.n_samples) {
-                v = __ldg(reinterpret_cast<const float4 *>(x + s));
+                if (i16) {
+                    const short4 h = __ldg(reinterpret_cast<const short4 *>(x16 + s));        // 8 bytes = four samples
+                    v = make_float4((float) h.x * kI16, (float) h.y * kI16, (float) h.z * kI16, (float) h.w * kI16);
+                } else {
+                    v = __ldg(reinterpret_cast<const float4 *>(x + s));
+                }
             } else {
                 float e[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const long long pp = p + i;
-                    float val = 0.0f;
+                    long long idx = -1;
                     if (pp < kFrame / 2) {
                         const long long r = kFrame / 2 - pp;          // reflect (start only, as the reference)
-                        if (r < st.n_samples) val = x[r];
+                        if (r < st.n_samples) idx = r;
                     } else if (pp < n_pad) {
-                        val = x[pp - kFrame / 2];
+                        idx = pp - kFrame / 2;
                     }
-                    e[i] = val;
+                    e[i] = idx < 0 ? 0.0f : (i16 ? (float) x16[idx] * kI16 : x[idx]);
                 }
                 v = make_float4(e[0], e[1], e[2], e[3]);
             }

@@ -7,12 +7,14 @@ namespace wb {
 
 // One audio stream of a batched launch (lives in device memory; blockIdx.y selects it).
 struct MelStream {
-    const float * pcm;        // device, mono 16 kHz f32
+    const float * pcm;        // device, mono 16 kHz: f32 in [-1, 1], or (pcm_i16 != 0) int16 behind the same pointer
     int           n_samples;
     int           n_frames_fft;  // frames that see audio (the rest of the reference's n_len frames are the constant -10)
     float *       out;        // device, raw log10 mel [n_mel][out_stride]
     int           out_stride;
     unsigned *    max_enc;    // device, ordered-uint encoding of the running max (init 0)
+    int           pcm_i16;    // 16-bit PCM ingest fused into the load: x = s / 32768 (what the reference's decoder front-end,
+                              // examples/common-whisper.cpp:42-134 via miniaudio's s16 -> f32, hands to whisper_pcm_to_mel)
 };
 
 struct MelGeometry {

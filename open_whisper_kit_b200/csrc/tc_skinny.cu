@@ -208,62 +208,81 @@ tc_skinny_kernel(const __grid_constant__ TMap tm_x, const __grid_constant__ TMap
         preload();
         if (ln_in) {
             // ===== A operand = LayerNorm(ln_x), built here instead of by a kernel of its own (rows_pad == 64, checked on the host) =====
-            // (1) row statistics: the producer GEMM left {mean, centred sum of squares} per 64-column tile; thread r combines the
-            //     K / 64 partials of row r in tile order (Chan et al.), which is as accurate as a two-pass variance.
-            if (tid < 64) {
+            // Everything this needs from the predecessor is requested at once -- the row statistics the producer GEMM left per
+            // 64-column tile AND the first k-block of f32 rows -- so the critical path stays ONE round trip to L2, like the TMA
+            // load it replaces.  Two threads per row combine the K / 64 partial {mean, centred sum of squares} pairs (Chan et
+            // al.; as accurate as a two-pass variance) and merge their halves through a shuffle.
+            // Per k-block thread (r8 = tid / 16, c4 = tid % 16) normalises four consecutive columns of rows r8, r8 + 8, ... and
+            // stores them as 8 bytes of the 128-byte-swizzled K-major tile the MMA descriptor expects (16-byte chunk index XOR
+            // row % 8); the next k-block's rows are in flight meanwhile.
+            const int c4 = tid & 15, r8 = tid >> 4;
+            const int srow = tid >> 1, shalf = tid & 1, n_part = p.K / TB;          // n_part <= 20 (host check)
+            float2 q[10];
+#pragma unroll
+            for (int t = 0; t < 10; ++t) {
+                const int tt = 2 * t + shalf;
+                q[t] = (srow < p.M && tt < n_part) ? p.ln_part_in[(size_t) tt * p.M + srow] : make_float2(0.0f, 0.0f);
+            }
+            struct Blk { float4 x[8]; float4 g, b; };
+            auto load_blk = [&](int i, Blk & v) {
+                const int k = (kb0 + i) * TB + 4 * c4;
+                const float * src = p.ln_x + k;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int r = r8 + 8 * j;
+                    v.x[j] = r < p.M ? *reinterpret_cast<const float4 *>(src + (size_t) r * p.ld_lnx) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                }
+                v.g = __ldg(reinterpret_cast<const float4 *>(p.ln_gamma + k));
+                v.b = __ldg(reinterpret_cast<const float4 *>(p.ln_beta + k));
+            };
+            auto do_blk = [&](int i, const Blk & v) {
+                const int s = i % T_STAGES;
+                if (i >= T_STAGES) ts_wait(&b_empty[s], ((i / T_STAGES) - 1) & 1);
+                uint8_t * xs = smem + s * stage_bytes;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int r = r8 + 8 * j;
+                    const float2 st = s_stat[r];
+                    const float4 x = v.x[j];
+                    const T16 h[4] = {Half16<T16>::from_f((x.x - st.x) * st.y * v.g.x + v.b.x), Half16<T16>::from_f((x.y - st.x) * st.y * v.g.y + v.b.y),
+                                      Half16<T16>::from_f((x.z - st.x) * st.y * v.g.z + v.b.z), Half16<T16>::from_f((x.w - st.x) * st.y * v.g.w + v.b.w)};
+                    const uint2 pk = r < p.M ? *reinterpret_cast<const uint2 *>(h) : make_uint2(0u, 0u);
+                    *reinterpret_cast<uint2 *>(xs + r * 128 + (((c4 >> 1) ^ (r & 7)) << 4) + ((c4 & 1) << 3)) = pk;
+                }
+                ptx::fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core's async proxy
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (tid == 0) ptx::mbar_arrive(&b_full[s]);
+            };
+            Blk va, vb;
+            if (nkb > 0) load_blk(0, va);
+            {
                 float mean = 0.0f, m2 = 0.0f, cnt = 0.0f;
-                if (tid < p.M) {
-                    const int n_part = p.K / TB;
-                    for (int t = 0; t < n_part; ++t) {
-                        const float2 q = p.ln_part_in[(size_t) t * p.M + tid];
-                        const float delta = q.x - mean, tot = cnt + (float) TB;
+#pragma unroll
+                for (int t = 0; t < 10; ++t) {
+                    if (2 * t + shalf < n_part) {
+                        const float delta = q[t].x - mean, tot = cnt + (float) TB;
                         mean += delta * ((float) TB / tot);
-                        m2 += q.y + delta * delta * (cnt * (float) TB / tot);
+                        m2 += q[t].y + delta * delta * (cnt * (float) TB / tot);
                         cnt = tot;
                     }
                 }
-                s_stat[tid] = make_float2(mean, 1.0f / sqrtf(m2 / (float) p.K + p.ln_eps));
+                // merge the two halves of the row in a fixed order (even tiles, then odd tiles)
+                const float mean_o = __shfl_xor_sync(0xffffffffu, mean, 1), m2_o = __shfl_xor_sync(0xffffffffu, m2, 1),
+                            cnt_o = __shfl_xor_sync(0xffffffffu, cnt, 1);
+                const float mA = shalf ? mean_o : mean, qA = shalf ? m2_o : m2, nA = shalf ? cnt_o : cnt;
+                const float mB = shalf ? mean : mean_o, qB = shalf ? m2 : m2_o, nB = shalf ? cnt : cnt_o;
+                const float tot = nA + nB, delta = mB - mA;
+                const float mu = tot > 0.0f ? mA + delta * (nB / tot) : 0.0f;
+                const float ss = tot > 0.0f ? qA + qB + delta * delta * (nA * nB / tot) : 0.0f;
+                if (shalf == 0) s_stat[srow] = make_float2(mu, tot > 0.0f ? 1.0f / sqrtf(ss / (float) p.K + p.ln_eps) : 0.0f);
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            // (2) per k-block: thread (r8 = tid / 16, c4 = tid % 16) normalises four consecutive columns of rows r8, r8 + 8, ...
-            //     and stores them as 8 bytes of the 128-byte-swizzled K-major tile the MMA descriptor expects (16-byte chunk
-            //     index XOR row % 8).  Up to three k-blocks of loads are in flight per thread.
-            const int c4 = tid & 15, r8 = tid >> 4;
-            for (int i0 = 0; i0 < nkb; i0 += 3) {
-                const int nb = nkb - i0 < 3 ? nkb - i0 : 3;
-                float4 xv[3][8];
-#pragma unroll
-                for (int b = 0; b < 3; ++b) {
-                    if (b >= nb) break;
-                    const float * src = p.ln_x + (size_t) (kb0 + i0 + b) * TB + 4 * c4;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int r = r8 + 8 * j;
-                        xv[b][j] = r < p.M ? *reinterpret_cast<const float4 *>(src + (size_t) r * p.ld_lnx) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                    }
-                }
-#pragma unroll
-                for (int b = 0; b < 3; ++b) {
-                    if (b >= nb) break;
-                    const int i = i0 + b, s = i % T_STAGES;
-                    if (i >= T_STAGES) ts_wait(&b_empty[s], ((i / T_STAGES) - 1) & 1);
-                    const int k = (kb0 + i) * TB + 4 * c4;
-                    const float4 g = __ldg(reinterpret_cast<const float4 *>(p.ln_gamma + k));
-                    const float4 be = __ldg(reinterpret_cast<const float4 *>(p.ln_beta + k));
-                    uint8_t * xs = smem + s * stage_bytes;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int r = r8 + 8 * j;
-                        const float2 st = s_stat[r];
-                        const float4 v = xv[b][j];
-                        const T16 h[4] = {Half16<T16>::from_f((v.x - st.x) * st.y * g.x + be.x), Half16<T16>::from_f((v.y - st.x) * st.y * g.y + be.y),
-                                          Half16<T16>::from_f((v.z - st.x) * st.y * g.z + be.z), Half16<T16>::from_f((v.w - st.x) * st.y * g.w + be.w)};
-                        const uint2 pk = r < p.M ? *reinterpret_cast<const uint2 *>(h) : make_uint2(0u, 0u);
-                        *reinterpret_cast<uint2 *>(xs + r * 128 + (((c4 >> 1) ^ (r & 7)) << 4) + ((c4 & 1) << 3)) = pk;
-                    }
-                    ptx::fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core's async proxy
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                    if (tid == 0) ptx::mbar_arrive(&b_full[s]);
+            for (int i = 0; i < nkb; i += 2) {
+                if (i + 1 < nkb) load_blk(i + 1, vb);
+                do_blk(i, va);
+                if (i + 1 < nkb) {
+                    if (i + 2 < nkb) load_blk(i + 2, va);
+                    do_blk(i + 1, vb);
                 }
             }
         }
@@ -477,7 +496,7 @@ bool tc_skinny_usable(const GemmArgs & g) {
     const bool base = g.M > 0 && g.M <= 128 && g.K % TB == 0 && g.ldw % 8 == 0 && !g.pos && !(reinterpret_cast<uintptr_t>(g.w) & 15);
     if (!base) return false;
     if (g.ln_x) {       // LayerNorm-fused A operand: 64 rows at most, 16-byte addressable f32 rows and affine parameters
-        if (g.M > 64 || !g.ln_part_in || !g.ln_gamma || !g.ln_beta || g.ld_lnx % 4 != 0) return false;
+        if (g.M > 64 || g.K > 20 * TB || !g.ln_part_in || !g.ln_gamma || !g.ln_beta || g.ld_lnx % 4 != 0) return false;
         if ((reinterpret_cast<uintptr_t>(g.ln_x) | reinterpret_cast<uintptr_t>(g.ln_gamma) | reinterpret_cast<uintptr_t>(g.ln_beta)) & 15) return false;
     } else if (g.lda % 8 != 0 || (reinterpret_cast<uintptr_t>(g.a) & 15)) {
         return false;

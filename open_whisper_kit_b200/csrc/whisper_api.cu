@@ -564,7 +564,11 @@ int whisper_full(struct whisper_context * ctx, struct whisper_full_params params
 // GPU, include/whisper_b200.h) the chunks are dealt out in contiguous blocks, one worker thread per GPU, no collective: the
 // only exchange is this host-side gather of the segments in chunk order.
 static int full_parallel_on(const std::vector<whisper_context *> & ctxs, struct whisper_full_params params, const float * samples,
-                            int n_samples, int n_processors) {
+                            int n_samples, int n_processors, bool i16 = false) {
+    // i16: `samples` really points at int16 PCM; offsets are in samples either way
+    auto at = [&](int start) {
+        return i16 ? reinterpret_cast<const float *>(reinterpret_cast<const int16_t *>(samples) + start) : samples + start;
+    };
     whisper_context * ctx = ctxs[0];
     const int G = (int) ctxs.size();
     const int offset_samples = (WHISPER_SAMPLE_RATE * params.offset_ms) / 1000;
@@ -587,6 +591,7 @@ static int full_parallel_on(const std::vector<whisper_context *> & ctxs, struct 
         sp.state = states[i];
         sp.params = params;
         sp.params.print_realtime = false;
+        sp.samples_i16 = i16;
         if (i == 0) {
             sp.samples = samples;
             sp.n_samples = offset_samples + n_per;
@@ -598,7 +603,7 @@ static int full_parallel_on(const std::vector<whisper_context *> & ctxs, struct 
             sp.params.new_segment_callback_user_data = nullptr;
             sp.params.progress_callback = nullptr;
             sp.params.progress_callback_user_data = nullptr;
-            sp.samples = samples + start;
+            sp.samples = at(start);
             sp.n_samples = (i == n_processors - 1) ? n_samples - start : n_per;
         }
         specs[owner[i]].push_back(sp);
@@ -753,6 +758,47 @@ WB200_API int whisper_b200_group_full_parallel(struct whisper_b200_group * g, st
     if (n_processors <= 1) return whisper_full(g->ctxs[0], params, samples, n_samples);
     try {
         return full_parallel_on(g->ctxs, params, samples, n_samples, n_processors);
+    } catch (const std::exception & ex) {
+        wlog(GGML_LOG_LEVEL_ERROR, "%s: %s\n", __func__, ex.what());
+        return -6;
+    }
+}
+
+// ---- 16-bit PCM ingest: the s16 -> f32 conversion of the reference's audio front-end is fused into the
+// mel kernel's load, so half the bytes cross PCIe and HBM ---------------------------------------------------------------------
+WB200_API int whisper_b200_pcm16_to_mel(struct whisper_context * ctx, const int16_t * samples, int n_samples) {
+    if (!ctx || !ctx->state || !samples || n_samples <= 0) return -1;
+    std::lock_guard<std::recursive_mutex> lock(ctx->eng.mu);
+    cuda_clear_failure();
+    const int64_t t0 = time_us();
+    std::vector<MelJob> jobs(1);
+    jobs[0].pcm_host = reinterpret_cast<const float *>(samples);
+    jobs[0].i16 = true;
+    jobs[0].n_samples = n_samples;
+    jobs[0].out = &ctx->state->mel;
+    const bool ok = ctx->eng.run_mel(jobs);
+    ctx->state->t_mel_us += time_us() - t0;
+    return ok ? 0 : -1;
+}
+
+WB200_API int whisper_b200_full_parallel_i16(struct whisper_context * ctx, struct whisper_full_params params, const int16_t * samples,
+                                             int n_samples, int n_processors) {
+    if (!ctx || !ctx->state || !samples) return -1;
+    if (params.vad) {
+        wlog(GGML_LOG_LEVEL_ERROR, "%s: VAD is outside the scope of the B200 path (failed to compute VAD)\n", __func__);
+        return -1;
+    }
+    try {
+        if (n_processors <= 1) {
+            std::vector<StreamSpec> specs(1);
+            specs[0].state = ctx->state;
+            specs[0].params = params;
+            specs[0].samples = reinterpret_cast<const float *>(samples);
+            specs[0].n_samples = n_samples;
+            specs[0].samples_i16 = true;
+            return run_streams(*ctx, specs);
+        }
+        return full_parallel_on({ctx}, params, reinterpret_cast<const float *>(samples), n_samples, n_processors, true);
     } catch (const std::exception & ex) {
         wlog(GGML_LOG_LEVEL_ERROR, "%s: %s\n", __func__, ex.what());
         return -6;

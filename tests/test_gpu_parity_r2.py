@@ -185,4 +185,6 @@ def test_device_selection_equals_host_selection(lib, model_dir, name, monkeypatc
     assert calls[0] > 0
     assert [(s[0], s[1], s[2]) for s in res[0]] == [(s[0], s[1], s[2]) for s in res[1]]
     dpl = max((abs(x - y) for s, r in zip(res[0], res[1]) for x, y in zip(s[3], r[3])), default=0.0)
-    assert dpl <= 5e-5      # sequential (host, as the reference) vs tree-ordered (device) f32 log-sum-exp over 52 000 terms
+    # sequential f32 log-sum-exp over 52 000 terms (host, as the reference: drops the terms below half an ulp of the running sum,
+    # ~1e-4 of the mass) vs the device's tree-ordered sum, see tests/test_gpu_sampler.py
+    assert dpl <= 3e-4

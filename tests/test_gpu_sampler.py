@@ -118,9 +118,9 @@ def test_device_selection_matches_reference(ctxs, kind, variant):
     # reference
     tok = capi.whisper_token_data()
     ref_draws = (capi.whisper_token_data * K)()
-    pr = np.empty(n_vocab, np.float32)
-    assert ref.ref_process_logits(w.ctx, p, temperature, logits.ctypes.data_as(FP), h_arr, len(hist), has_ts, seek_delta, None, None,
-                                  pr.ctypes.data_as(FP), C.byref(tok)) == 0
+    pr, lo = np.empty(n_vocab, np.float32), np.empty(n_vocab, np.float32)
+    assert ref.ref_process_logits(w.ctx, p, temperature, logits.ctypes.data_as(FP), h_arr, len(hist), has_ts, seek_delta,
+                                  lo.ctypes.data_as(FP), None, pr.ctypes.data_as(FP), C.byref(tok)) == 0
     assert ref.ref_sample_topk(w.ctx, K, seed, ref_draws) == 0
 
     # product: row 0 arg-max, row 1 K draws, both on logits row 0
@@ -138,11 +138,22 @@ def test_device_selection_matches_reference(ctxs, kind, variant):
                                         u.ctypes.data_as(C.POINTER(C.c_double)), K, out, draws)
     assert rc == 0
 
-    # Probabilities: the reference's log-sum-exp is a SEQUENTIAL f32 sum over ~52 000 terms (src/whisper.cpp:6137-6160), whose own
-    # rounding error is ~sqrt(n) * 2^-24 ~ 1e-5 relative; a tree-ordered sum cannot (and need not) reproduce its last bits, so
-    # p / plog are compared at 5e-5 relative / 2e-5 absolute.  Token ids -- arg-max and every draw -- must be identical.
+    # Probabilities.  The reference's log-sum-exp is a SEQUENTIAL f32 sum over ~52 000 terms (src/whisper.cpp:6137-6160): once
+    # the running sum is large, every term below half an ulp of it is rounded away, which for Gaussian logits loses ~1e-4 of
+    # the mass -- a systematic error of the reference, reproduced by the product's host restatement (tests/
+    # test_process_logits_host.py) but not by the device's tree-ordered sum, which keeps those terms.  So p / plog are compared
+    # with the reference at 3e-4, and with the exact (float64) log-softmax of the reference's processed logits at 3e-6: the
+    # device has to be the more accurate of the two.  Token ids -- arg-max and every draw -- must be identical.
     def close(a, b):
-        return np.allclose(a, b, rtol=5e-5, atol=2e-5)
+        return np.allclose(a, b, rtol=3e-4, atol=3e-4)
+
+    if not np.all(np.isneginf(lo[:beg])):          # (text tokens masked by the timestamp-mass rule: logZ predates the mask)
+        fin = ~np.isneginf(lo)
+        l64 = lo[fin].astype(np.float64)
+        logz = l64.max() + np.log(np.exp(l64 - l64.max()).sum())
+        plog_exact = float(lo[tok.id]) - logz
+        assert abs(out[0].plog - plog_exact) <= 3e-6 * max(1.0, abs(logz)), (out[0].plog, tok.plog, plog_exact)
+        assert abs(out[0].plog - plog_exact) <= abs(tok.plog - plog_exact) + 2e-6 * max(1.0, abs(logz))
 
     g = out[0]
     assert (g.id, g.tid) == (tok.id, tok.tid)
