@@ -93,7 +93,7 @@ struct whisper_context_params {
     bool use_gpu;      /* must stay true: this library has no CPU path */
     bool flash_attn;   /* true: attention sees the reference's 36 zero phantom keys of the 1536-padded K/V */
     int gpu_device;
-    bool dtw_token_timestamps; /* out of scope (DTW); ignored */
+    bool dtw_token_timestamps;
     enum whisper_alignment_heads_preset dtw_aheads_preset;
     int dtw_n_top;
     struct whisper_aheads dtw_aheads;

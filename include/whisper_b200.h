@@ -165,6 +165,14 @@ WB200_API int whisper_b200_kernel_sample(const float * logits, int n_logit_rows,
                                          const uint32_t * static_mask, struct whisper_b200_sample_params prm, const double * uniforms,
                                          int n_uniforms, struct whisper_b200_sample_out * out, struct whisper_b200_draw_out * draws);
 
+/* The alignment stage of the DTW token timestamps (csrc/dtw.cu, host logic only -- needs no device): probs [n_heads][n_tokens][T]
+ * cross-attention probabilities of the alignment heads -> standardise over the tokens per (head, audio position), median filter
+ * of medfilt_width along the first n_audio positions, mean over heads, negate, dynamic time warping over the tokens
+ * skip_front .. n_tokens - 2 (reference src/whisper.cpp:8712-8998).  first_out[k] = first audio position of token
+ * skip_front + k on the path.  Returns the number of aligned tokens, or -1. */
+WB200_API int whisper_b200_dtw_align(const float * probs, int n_heads, int n_tokens, int T, int n_audio, int skip_front,
+                                     int medfilt_width, int * first_out);
+
 /* Stream-K geometry of one GEMM phase of the persistent decoder-step kernel (csrc/dec_chain.h, host logic only -- needs
  * no device): out[0..4] = {tiles, k-blocks per tile, units, CTAs taking part, partial-tile slots per output tile}.
  * direct != 0: every CTA owns one whole 128-column tile.  Returns 0, or -1 for shapes the kernel does not take. */

@@ -31,12 +31,22 @@ class Segment:
 
 
 class Whisper:
-    def __init__(self, lib, model_path, use_gpu=True, flash_attn=True, gpu_device=0):
+    def __init__(self, lib, model_path, use_gpu=True, flash_attn=True, gpu_device=0, dtw_preset=None, dtw_heads=None, dtw_n_top=-1):
+        """dtw_preset: a whisper_alignment_heads_preset value (1 = N_TOP_MOST with dtw_n_top, 2 = CUSTOM with dtw_heads =
+        [(text layer, head), ...]) switches DTW token timestamps on (the reference refuses them with flash_attn)."""
         self.lib = lib
         cp = lib.whisper_context_default_params()
         cp.use_gpu = use_gpu
         cp.flash_attn = flash_attn
         cp.gpu_device = gpu_device
+        if dtw_preset is not None:
+            cp.dtw_token_timestamps = True
+            cp.dtw_aheads_preset = dtw_preset
+            cp.dtw_n_top = dtw_n_top
+            if dtw_heads:
+                self._heads = (capi.whisper_ahead * len(dtw_heads))(*[capi.whisper_ahead(l, h) for l, h in dtw_heads])
+                cp.dtw_aheads.n_heads = len(dtw_heads)
+                cp.dtw_aheads.heads = self._heads
         self.ctx = lib.whisper_init_from_file_with_params(model_path.encode(), cp)
         if not self.ctx:
             raise RuntimeError(f"whisper_init_from_file_with_params failed for {model_path}")

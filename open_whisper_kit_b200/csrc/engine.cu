@@ -453,7 +453,10 @@ bool Engine::decode(const std::vector<DecRow> & rows, const std::vector<int> & l
     bool fuse_append = true;
     for (int i = 1; i < R && fuse_append; ++i)
         if (rows[i].self_kv == rows[i - 1].self_kv) fuse_append = false;
-    if (fuse_append && chain_usable(R)) return decode_chain(rows, logit_rows, cross_layer_stride);
+    if (fuse_append && !align.on && chain_usable(R)) return decode_chain(rows, logit_rows, cross_layer_stride);
+    if (align.on) {
+        if (align.n_heads_total <= 0 || !align.probs.reserve((size_t) align.n_heads_total * R * cross_T * sizeof(float))) return false;
+    }
     // Single-token step with at most 64 rows: the three LayerNorms of a layer are folded into their neighbours -- the GEMM that
     // produces the residual stream (O, cross-O, MLP-down) also emits per-tile row statistics, and the GEMM that consumes the
     // normalised rows (QKV, cross-Q, MLP-up) builds its A operand from the f32 stream itself (tc_skinny.cu).  Saves three
@@ -506,6 +509,13 @@ bool Engine::decode(const std::vector<DecRow> & rows, const std::vector<int> & l
             g.bias = L.bxq; g.out16 = q16; g.ldo16 = d;
             if (fuse_ln) ln_consumer(g, L.lnx_w, L.lnx_b);
             gemm(g);
+        }
+        if (align.on && !align.heads_by_layer[il].empty()) {
+            int a0 = 0;
+            for (int k = 0; k < il; ++k) a0 += (int) align.heads_by_layer[k].size();
+            dtw_capture_layer(dt, q16, d_rows, R, d, (const int *) align.d_heads.p + a0, (int) align.heads_by_layer[il].size(),
+                              il * cross_layer_stride, cross_T, a0, (float *) align.probs.p, stream);
+            n_kernel_launches += 1;
         }
         prof_begin(PC_CROSS_ATTN, (double) R * cross_T * 2.0 * d * 2.0);
         dec_cross_attn(dt, q16, d_rows, R, d, H, il * cross_layer_stride, cross_T, n_phantom(cross_T), att, stream, nullptr, d_groups, n_groups);

@@ -7,6 +7,7 @@
 
 #include "dec_chain.h"
 #include "dec_kernels.h"
+#include "dtw.h"
 #include "enc_kernels.h"
 #include "mel.h"
 #include "model.h"
@@ -121,6 +122,16 @@ struct Engine {
     // (src/whisper.cpp:2055, 2481)
     int n_phantom(int T = 1500) const { return flash_attn ? (T + 255) / 256 * 256 - T : 0; }
     int cross_T = 1500;        // audio context of the cross K/V the next decode() call reads (set by the caller)
+
+    // DTW token timestamps: when `on`, the next decode() also writes the cross-attention probabilities of the alignment heads
+    // (heads_by_layer, capture order = layer, then list order) for every row to `probs` [n_heads_total][rows][cross_T]
+    struct AlignCapture {
+        bool on = false;
+        std::vector<std::vector<int>> heads_by_layer;
+        int n_heads_total = 0;
+        DeviceBlock d_heads;       // the head lists, flattened in capture order
+        DeviceBlock probs;
+    } align;
 
     bool init(int device, bool flash_attn);
     ~Engine();

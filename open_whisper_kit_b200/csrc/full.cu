@@ -608,12 +608,61 @@ static int stream_begin(whisper_context & ctx, Stream & s) {
     return 0;
 }
 
+// DTW token timestamps of the segments [i_segment, i_segment + n_segments) of the window that starts at `seek`: one more
+// prompt-style decoder pass over [sot, (lang), notimestamps, text tokens, eot] with the alignment heads' cross-attention
+// probabilities captured on the device, then the alignment on the host (dtw.cu; src/whisper.cpp:8850-8998).
+static void dtw_window(whisper_context & ctx, Stream & s, int i_segment, int n_segments, int seek, int n_frames) {
+    Engine & e = ctx.eng;
+    whisper_state * state = s.state;
+    const Vocab & vocab = e.model.vocab;
+    std::vector<whisper_token> tokens = {vocab.token_sot};
+    if (vocab.is_multilingual()) {
+        const int id = lang_id(s.params.language);
+        state->lang_id = id;
+        tokens.push_back(vocab.token_sot + 1 + std::max(0, id));
+    }
+    const int sot_len = (int) tokens.size();
+    tokens.push_back(vocab.token_not);
+    std::vector<whisper_token_data *> text;
+    for (int i = i_segment; i < i_segment + n_segments; ++i)
+        for (auto & t : state->result_all[i].tokens)
+            if (t.id < vocab.token_eot) {
+                tokens.push_back(t.id);
+                text.push_back(&t);
+            }
+    tokens.push_back(vocab.token_eot);
+    const int n_tokens = (int) tokens.size(), n_audio = n_frames / 2, T = e.cross_T;
+    if (text.empty() || n_tokens > e.model.hp.n_text_ctx || n_audio <= 7 || n_audio > T || !state->cross_base) return;
+    whisper_decoder & dec = state->decoders[0];
+    if (!dec.kv.reserve(e.self_kv_bytes())) return;
+    std::vector<DecRow> rows(n_tokens);
+    for (int i = 0; i < n_tokens; ++i) rows[i] = {tokens[i], i, dec.kv.p, state->cross_base};
+    e.align.on = true;
+    const bool ok = e.decode(rows, {}, ctx.batch_cross.layer_stride);
+    e.align.on = false;
+    if (!ok) {
+        wlog(GGML_LOG_LEVEL_ERROR, "%s: decoder pass for the alignment heads failed\n", __func__);
+        return;
+    }
+    const int A = e.align.n_heads_total;
+    std::vector<float> probs((size_t) A * n_tokens * T);
+    WB_CUDA(cudaMemcpyAsync(probs.data(), e.align.probs.p, probs.size() * sizeof(float), cudaMemcpyDeviceToHost, e.stream));
+    WB_CUDA(cudaStreamSynchronize(e.stream));
+    if (cuda_failed()) return;
+    const std::vector<int> first = dtw_align(probs.data(), A, n_tokens, T, n_audio, sot_len, 7);
+    // row 0 of the alignment is <|notimestamps|>; text token k owns row k + 1 (one audio position = 20 ms = 2 ticks)
+    for (size_t k = 0; k < text.size() && k + 1 < first.size(); ++k)
+        if (first[k + 1] >= 0) text[k]->t_dtw = (int64_t) first[k + 1] * 2 + seek;
+}
+
 // emit the segments of the finished window and advance the seek position (src/whisper.cpp:7609-7772)
 static void stream_finish_window(whisper_context & ctx, Stream & s) {
     whisper_state * state = s.state;
     const auto & params = s.params;
     const Vocab & vocab = ctx.eng.model.vocab;
     auto & result_all = state->result_all;
+    const size_t n_segments_before = result_all.size();
+    const bool dtw = ctx.eng.align.n_heads_total > 0;
     const whisper_decoder & best = state->decoders[s.best_decoder_id];
     int seek_delta = best.seek_delta;
     const int result_len = best.sequence.result_len;
@@ -644,7 +693,7 @@ static void stream_finish_window(whisper_context & ctx, Stream & s) {
             assign_token_times(vocab, *state, (int) result_all.size() - 1, params.thold_pt, params.thold_ptsum);
             if (params.max_len > 0) n_new = split_last_segment(vocab, *state, params.max_len, params.split_on_word);
         }
-        if (params.new_segment_callback) params.new_segment_callback(&ctx, state, n_new, params.new_segment_callback_user_data);
+        if (params.new_segment_callback && !dtw) params.new_segment_callback(&ctx, state, n_new, params.new_segment_callback_user_data);
     };
 
     if (!tokens_cur.empty() && ctx.eng.model.n_loaded > 0 && !is_no_speech) {
@@ -667,6 +716,16 @@ static void stream_finish_window(whisper_context & ctx, Stream & s) {
             }
         }
         if (!text.empty()) emit(t0, seek + seek_delta, text, i0, (int) tokens_cur.size() - 1, speaker_turn_next);
+    }
+    {   // [EXPERIMENTAL] token-level timestamps with DTW (src/whisper.cpp:7745-7760)
+        const int n_segments = (int) (result_all.size() - n_segments_before);
+        if (dtw && n_segments) {
+            const int n_frames = std::min(std::min(3000, seek_delta), s.seek_end - seek);
+            dtw_window(ctx, s, (int) n_segments_before, n_segments, seek, n_frames);
+            if (params.new_segment_callback)
+                for (int seg = (int) result_all.size() - n_segments; seg < n_segments; seg++)
+                    params.new_segment_callback(&ctx, state, seg, params.new_segment_callback_user_data);
+        }
     }
     const bool single_timestamp_ending = tokens_cur.size() > 1 && tokens_cur[tokens_cur.size() - 2].id < vocab.token_beg &&
                                          tokens_cur[tokens_cur.size() - 1].id > vocab.token_beg;

@@ -10,6 +10,7 @@
 #include "mel.h"
 #include "dec_chain.h"
 #include "dec_kernels.h"
+#include "dtw.h"
 #include "enc_kernels.h"
 #include "skinny_gemm.h"
 #include "tc_gemm.h"
@@ -341,6 +342,15 @@ WB200_API int whisper_b200_kernel_sample(const float * logits, int n_logit_rows,
     WB_CUDA(cudaMemcpy(out, d_o.p, (size_t) n_rows * sizeof(SampleOut), cudaMemcpyDeviceToHost));
     if (n_uniforms > 0) WB_CUDA(cudaMemcpy(draws, d_d.p, (size_t) n_uniforms * sizeof(DrawOut), cudaMemcpyDeviceToHost));
     return cuda_failed() ? -4 : 0;
+}
+
+// Host-only hook: the alignment stage of the DTW token timestamps (csrc/dtw.cu::dtw_align) on explicit head probabilities.
+WB200_API int whisper_b200_dtw_align(const float * probs, int n_heads, int n_tokens, int T, int n_audio, int skip_front, int medfilt_width,
+                                     int * first_out) {
+    if (!probs || !first_out || n_heads <= 0 || n_tokens <= skip_front + 1 || n_audio <= 0 || n_audio > T || medfilt_width % 2 == 0) return -1;
+    const std::vector<int> first = dtw_align(probs, n_heads, n_tokens, T, n_audio, skip_front, medfilt_width);
+    for (size_t i = 0; i < first.size(); ++i) first_out[i] = first[i];
+    return (int) first.size();
 }
 
 WB200_API int whisper_b200_chain_geometry(int grid, int rows, int N, int K, int min_units, int direct, int * out) {

@@ -223,38 +223,22 @@ tc_skinny_kernel(const __grid_constant__ TMap tm_x, const __grid_constant__ TMap
                 const int tt = 2 * t + shalf;
                 q[t] = (srow < p.M && tt < n_part) ? p.ln_part_in[(size_t) tt * p.M + srow] : make_float2(0.0f, 0.0f);
             }
-            struct Blk { float4 x[8]; float4 g, b; };
-            auto load_blk = [&](int i, Blk & v) {
-                const int k = (kb0 + i) * TB + 4 * c4;
-                const float * src = p.ln_x + k;
+            // the f32 rows of up to three k-blocks (a CTA's whole K slice in the step's shapes) are requested before anything is
+            // consumed: 24 x 16 bytes per thread in flight
+            float4 xv[3][8];
+            auto load_x = [&](int i0) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int r = r8 + 8 * j;
-                    v.x[j] = r < p.M ? *reinterpret_cast<const float4 *>(src + (size_t) r * p.ld_lnx) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                }
-                v.g = __ldg(reinterpret_cast<const float4 *>(p.ln_gamma + k));
-                v.b = __ldg(reinterpret_cast<const float4 *>(p.ln_beta + k));
-            };
-            auto do_blk = [&](int i, const Blk & v) {
-                const int s = i % T_STAGES;
-                if (i >= T_STAGES) ts_wait(&b_empty[s], ((i / T_STAGES) - 1) & 1);
-                uint8_t * xs = smem + s * stage_bytes;
+                for (int bb = 0; bb < 3; ++bb) {
+                    if (i0 + bb >= nkb) break;
+                    const float * src = p.ln_x + (size_t) (kb0 + i0 + bb) * TB + 4 * c4;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int r = r8 + 8 * j;
-                    const float2 st = s_stat[r];
-                    const float4 x = v.x[j];
-                    const T16 h[4] = {Half16<T16>::from_f((x.x - st.x) * st.y * v.g.x + v.b.x), Half16<T16>::from_f((x.y - st.x) * st.y * v.g.y + v.b.y),
-                                      Half16<T16>::from_f((x.z - st.x) * st.y * v.g.z + v.b.z), Half16<T16>::from_f((x.w - st.x) * st.y * v.g.w + v.b.w)};
-                    const uint2 pk = r < p.M ? *reinterpret_cast<const uint2 *>(h) : make_uint2(0u, 0u);
-                    *reinterpret_cast<uint2 *>(xs + r * 128 + (((c4 >> 1) ^ (r & 7)) << 4) + ((c4 & 1) << 3)) = pk;
+                    for (int j = 0; j < 8; ++j) {
+                        const int r = r8 + 8 * j;
+                        xv[bb][j] = r < p.M ? *reinterpret_cast<const float4 *>(src + (size_t) r * p.ld_lnx) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    }
                 }
-                ptx::fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core's async proxy
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (tid == 0) ptx::mbar_arrive(&b_full[s]);
             };
-            Blk va, vb;
-            if (nkb > 0) load_blk(0, va);
+            load_x(0);
             {
                 float mean = 0.0f, m2 = 0.0f, cnt = 0.0f;
 #pragma unroll
@@ -277,12 +261,36 @@ tc_skinny_kernel(const __grid_constant__ TMap tm_x, const __grid_constant__ TMap
                 if (shalf == 0) s_stat[srow] = make_float2(mu, tot > 0.0f ? 1.0f / sqrtf(ss / (float) p.K + p.ln_eps) : 0.0f);
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            for (int i = 0; i < nkb; i += 2) {
-                if (i + 1 < nkb) load_blk(i + 1, vb);
-                do_blk(i, va);
-                if (i + 1 < nkb) {
-                    if (i + 2 < nkb) load_blk(i + 2, va);
-                    do_blk(i + 1, vb);
+            for (int i0 = 0; i0 < nkb; i0 += 3) {
+                if (i0 > 0) load_x(i0);
+                float4 gv[3], bv[3];
+#pragma unroll
+                for (int bb = 0; bb < 3; ++bb) {
+                    if (i0 + bb >= nkb) break;
+                    const int k = (kb0 + i0 + bb) * TB + 4 * c4;
+                    gv[bb] = __ldg(reinterpret_cast<const float4 *>(p.ln_gamma + k));
+                    bv[bb] = __ldg(reinterpret_cast<const float4 *>(p.ln_beta + k));
+                }
+#pragma unroll
+                for (int bb = 0; bb < 3; ++bb) {
+                    if (i0 + bb >= nkb) break;
+                    const int i = i0 + bb, s = i % T_STAGES;
+                    if (i >= T_STAGES) ts_wait(&b_empty[s], ((i / T_STAGES) - 1) & 1);
+                    uint8_t * xs = smem + s * stage_bytes;
+                    const float4 g = gv[bb], be = bv[bb];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int r = r8 + 8 * j;
+                        const float2 st = s_stat[r];
+                        const float4 x = xv[bb][j];
+                        const T16 h[4] = {Half16<T16>::from_f((x.x - st.x) * st.y * g.x + be.x), Half16<T16>::from_f((x.y - st.x) * st.y * g.y + be.y),
+                                          Half16<T16>::from_f((x.z - st.x) * st.y * g.z + be.z), Half16<T16>::from_f((x.w - st.x) * st.y * g.w + be.w)};
+                        const uint2 pk = r < p.M ? *reinterpret_cast<const uint2 *>(h) : make_uint2(0u, 0u);
+                        *reinterpret_cast<uint2 *>(xs + r * 128 + (((c4 >> 1) ^ (r & 7)) << 4) + ((c4 & 1) << 3)) = pk;
+                    }
+                    ptx::fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core's async proxy
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (tid == 0) ptx::mbar_arrive(&b_full[s]);
                 }
             }
         }

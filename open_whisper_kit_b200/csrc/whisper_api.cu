@@ -31,9 +31,10 @@ whisper_context * init_with_loader(whisper_model_loader * loader, whisper_contex
         if (loader->close) loader->close(loader->context);
         return nullptr;
     }
-    if (params.dtw_token_timestamps)
-        wlog(GGML_LOG_LEVEL_WARN, "%s: dtw_token_timestamps is not implemented on the B200 path: whisper_token_data::t_dtw stays -1\n",
-             __func__);
+    if (params.flash_attn && params.dtw_token_timestamps) {       // as the reference (src/whisper.cpp:3708-3711)
+        wlog(GGML_LOG_LEVEL_WARN, "%s: dtw_token_timestamps is not supported with flash_attn - disabling\n", __func__);
+        params.dtw_token_timestamps = false;
+    }
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0 || params.gpu_device < 0 || params.gpu_device >= n_dev) {
         cudaGetLastError();
@@ -56,6 +57,24 @@ whisper_context * init_with_loader(whisper_model_loader * loader, whisper_contex
             return nullptr;
         }
         ctx->t_load_us = time_us() - t0;
+        if (params.dtw_token_timestamps) {
+            // alignment heads (src/whisper.cpp:1160-1272): an invalid selection fails the initialisation, as aheads_masks_init does
+            auto & al = ctx->eng.align;
+            const auto & hp = ctx->eng.model.hp;
+            if (!dtw_alignment_heads(params, hp.n_text_layer, hp.n_text_head, al.heads_by_layer)) {
+                delete ctx;
+                return nullptr;
+            }
+            std::vector<int> flat;
+            for (const auto & l : al.heads_by_layer) flat.insert(flat.end(), l.begin(), l.end());
+            al.n_heads_total = (int) flat.size();
+            if (flat.empty() || !al.d_heads.reserve(flat.size() * sizeof(int)) ||
+                cudaMemcpy(al.d_heads.p, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) {
+                wlog(GGML_LOG_LEVEL_ERROR, "%s: no usable alignment heads for dtw_token_timestamps\n", __func__);
+                delete ctx;
+                return nullptr;
+            }
+        }
         if (with_state) {
             ctx->state = whisper_init_state(ctx);
             if (!ctx->state) {
