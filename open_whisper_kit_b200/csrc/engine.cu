@@ -457,11 +457,14 @@ bool Engine::decode(const std::vector<DecRow> & rows, const std::vector<int> & l
     if (align.on) {
         if (align.n_heads_total <= 0 || !align.probs.reserve((size_t) align.n_heads_total * R * cross_T * sizeof(float))) return false;
     }
-    // Single-token step with at most 64 rows: the three LayerNorms of a layer are folded into their neighbours -- the GEMM that
-    // produces the residual stream (O, cross-O, MLP-down) also emits per-tile row statistics, and the GEMM that consumes the
-    // normalised rows (QKV, cross-Q, MLP-up) builds its A operand from the f32 stream itself (tc_skinny.cu).  Saves three
-    // dependent launches per layer; only the very first and the final LayerNorm of a step remain kernels of their own.
-    static const bool ln_fuse_env = !(getenv("WHISPER_B200_LN_FUSE") && atoi(getenv("WHISPER_B200_LN_FUSE")) == 0);
+    // Single-token step with at most 64 rows, OPT-IN (WHISPER_B200_LN_FUSE=1): the three LayerNorms of a layer folded into their
+    // neighbours -- the GEMM that produces the residual stream (O, cross-O, MLP-down) also emits per-tile row statistics, and the
+    // GEMM that consumes the normalised rows (QKV, cross-Q, MLP-up) builds its A operand from the f32 stream itself
+    // (tc_skinny.cu).  Removes three dependent launches per layer, but measured SLOWER than the separate kernels on B200
+    // (large-v3, 64 rows: 1255-1280 ms against 1225 ms per 64-window step): the LayerNorm kernel costs 1.65 us + a 1.3 us
+    // programmatic hand-over, while building the tile in the consumer puts ~3.5 us (L2 round trip for f32 rows instead of a TMA
+    // of 16-bit rows, statistics, normalise, two barriers) on ITS critical path.  Kept as a tested experiment, off by default.
+    static const bool ln_fuse_env = getenv("WHISPER_B200_LN_FUSE") && atoi(getenv("WHISPER_B200_LN_FUSE")) != 0;
     static const bool tcs_env = !(getenv("WHISPER_B200_TC_SKINNY") && atoi(getenv("WHISPER_B200_TC_SKINNY")) == 0);
     const bool fuse_ln = ln_fuse_env && tcs_env && fuse_append && R <= 64 && d % 64 == 0;
     auto ln_consumer = [&](GemmArgs & g, const float * gw, const float * gb) {      // A operand = LayerNorm(x) with (gw, gb)
