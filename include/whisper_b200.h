@@ -108,6 +108,12 @@ WB200_API double whisper_b200_kernel_gemm_bench(int dtype, int M, int N, int K, 
  * 2 self-attention at position aux, 3 KV append; R rows of width d. */
 WB200_API double whisper_b200_kernel_step_bench(int which, int dtype, int R, int d, int aux, int iters);
 
+/* Beam bookkeeping hook: copy positions [0, n_pos) of the self-attention history (decoder 0) of state `src` into state `dst`
+ * with the batched copy kernel the beam search uses when a beam changes parent (reference: whisper_kv_cache_seq_cp,
+ * src/whisper.cpp:1100-1137); `dst` then also points at `src`'s cross K/V, so whisper_decode_with_state(dst, ..., n_past = n_pos)
+ * continues `src`'s sequence. */
+WB200_API int whisper_b200_kv_copy(struct whisper_context * ctx, struct whisper_state * src, struct whisper_state * dst, int n_pos);
+
 /* ---- 16-bit PCM ingest -------------------------------------------------------------------------------------------------------
  * whisper_pcm_to_mel / whisper_full_parallel for int16 mono 16 kHz samples: x = s / 32768 -- the conversion the reference's
  * callers run on the host before the API (examples/common-whisper.cpp:42-134, miniaudio s16 -> f32) -- is applied inside the

@@ -43,6 +43,7 @@ EXT_PROTOTYPES = {
     "whisper_b200_pcm16_to_mel": (_C.c_int, [_C.c_void_p, _C.POINTER(_C.c_int16), _C.c_int]),
     "whisper_b200_full_parallel_i16": (_C.c_int, [_C.c_void_p, capi.whisper_full_params, _C.POINTER(_C.c_int16), _C.c_int, _C.c_int]),
     "whisper_b200_dtw_align": (_C.c_int, [_FP] + [_C.c_int] * 6 + [_IP]),
+    "whisper_b200_kv_copy": (_C.c_int, [_C.c_void_p, _C.c_void_p, _C.c_void_p, _C.c_int]),
     "whisper_b200_partition_owner": (_C.c_int, [_C.c_int, _C.c_int, _C.c_int]),
     "whisper_b200_group_init_from_file": (_C.c_void_p, [_C.c_char_p, capi.whisper_context_params, _IP, _C.c_int]),
     "whisper_b200_group_free": (None, [_C.c_void_p]),

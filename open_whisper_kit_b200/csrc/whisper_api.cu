@@ -936,6 +936,25 @@ WB200_API int whisper_b200_get_cross_kv(struct whisper_context * ctx, int layer,
     return 0;
 }
 
+// Copies positions [0, n_pos) of the self-attention history of decoder 0 of `src` into decoder 0 of `dst` with the batched
+// copy kernel the beam search uses when a beam changes parent (the role of whisper_kv_cache_seq_cp, src/whisper.cpp:1100-1137).
+WB200_API int whisper_b200_kv_copy(struct whisper_context * ctx, struct whisper_state * src, struct whisper_state * dst, int n_pos) {
+    if (!ctx || !src || !dst || n_pos < 0 || n_pos > ctx->eng.model.hp.n_text_ctx) return -1;
+    std::lock_guard<std::recursive_mutex> lock(ctx->eng.mu);
+    cuda_clear_failure();
+    cudaSetDevice(ctx->eng.device);
+    if (!src->decoders[0].kv.p || !dst->decoders[0].kv.reserve(ctx->eng.self_kv_bytes())) return -2;
+    std::vector<Engine::KvCopy> copies(1);
+    copies[0] = {src->decoders[0].kv.p, dst->decoders[0].kv.p, n_pos};
+    if (!ctx->eng.kv_copy_prefix_batch(copies)) return -3;
+    WB_CUDA(cudaStreamSynchronize(ctx->eng.stream));
+    // the copy shares the source window's cross K/V too (a beam inherits its stream's audio)
+    dst->cross_base = src->cross_base;
+    dst->cross_layer_stride = src->cross_layer_stride;
+    dst->cross_T = src->cross_T;
+    return cuda_failed() ? -4 : 0;
+}
+
 WB200_API int whisper_b200_dtype(struct whisper_context * ctx) { return ctx ? (int) ctx->eng.model.dtype : -1; }
 
 WB200_API long long whisper_b200_kernel_launches(struct whisper_context * ctx) { return ctx ? ctx->eng.n_kernel_launches : 0; }

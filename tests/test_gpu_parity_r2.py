@@ -188,3 +188,49 @@ def test_device_selection_equals_host_selection(lib, model_dir, name, monkeypatc
     # sequential f32 log-sum-exp over 52 000 terms (host, as the reference: drops the terms below half an ulp of the running sum,
     # ~1e-4 of the mass) vs the device's tree-ordered sum, see tests/test_gpu_sampler.py
     assert dpl <= 3e-4
+
+
+def test_self_attention_history_copy_continues_the_parent_sequence(lib, model_dir):
+    """Beam bookkeeping (reference whisper_kv_cache_seq_cp, src/whisper.cpp:1100-1137): a beam that changes parent
+    takes the parent's self-attention history through the batched copy kernel.  State B receives A's first n positions and
+    must then produce bit-identical logits to A for the same next token; the positions beyond n must not matter."""
+    import ctypes as C
+    path = os.path.join(model_dir, "tiny.en-1.bin")
+    if not os.path.exists(path):
+        cases_r2.modelgen.write_model(path, "tiny.en", ftype=1)
+    pcm = cases_r2.modelgen.synth_pcm(480000, seed=3)
+    with api.Whisper(lib, path, flash_attn=False) as w:
+        n_vocab = lib.whisper_n_vocab(w.ctx)
+        sa = lib.whisper_init_state(w.ctx)
+        sb = lib.whisper_init_state(w.ctx)
+        assert sa and sb
+        try:
+            FP = C.POINTER(C.c_float)
+            pcm_p = pcm.ctypes.data_as(FP)
+            assert lib.whisper_pcm_to_mel_with_state(w.ctx, sa, pcm_p, len(pcm), 1) == 0
+            assert lib.whisper_encode_with_state(w.ctx, sa, 0, 1) == 0
+            sot = lib.whisper_token_sot(w.ctx)
+            hist = [sot, 400, 1234, 50, 7, 30000, 812, 9]
+            arr = (C.c_int32 * len(hist))(*hist)
+            assert lib.whisper_decode_with_state(w.ctx, sa, arr, len(hist), 0, 1) == 0
+            # B: garbage history first (positions that the copy must overwrite / that lie beyond the copied prefix)
+            junk = (C.c_int32 * 12)(*([sot] + [77] * 11))
+            assert lib.whisper_pcm_to_mel_with_state(w.ctx, sb, pcm_p, len(pcm), 1) == 0
+            assert lib.whisper_encode_with_state(w.ctx, sb, 0, 1) == 0
+            assert lib.whisper_decode_with_state(w.ctx, sb, junk, 12, 0, 1) == 0
+            assert lib.whisper_b200_kv_copy(w.ctx, sa, sb, len(hist)) == 0
+            nxt = (C.c_int32 * 1)(4321)
+            assert lib.whisper_decode_with_state(w.ctx, sa, nxt, 1, len(hist), 1) == 0
+            la = np.ctypeslib.as_array(lib.whisper_get_logits_from_state(sa), shape=(n_vocab,)).copy()
+            assert lib.whisper_decode_with_state(w.ctx, sb, nxt, 1, len(hist), 1) == 0
+            lb = np.ctypeslib.as_array(lib.whisper_get_logits_from_state(sb), shape=(n_vocab,)).copy()
+            assert np.array_equal(la, lb)
+            # a shorter prefix is a different history: the logits must differ
+            assert lib.whisper_decode_with_state(w.ctx, sb, junk, 12, 0, 1) == 0
+            assert lib.whisper_b200_kv_copy(w.ctx, sa, sb, len(hist) - 3) == 0
+            assert lib.whisper_decode_with_state(w.ctx, sb, nxt, 1, len(hist), 1) == 0
+            lc = np.ctypeslib.as_array(lib.whisper_get_logits_from_state(sb), shape=(n_vocab,)).copy()
+            assert not np.array_equal(la, lc)
+        finally:
+            lib.whisper_free_state(sa)
+            lib.whisper_free_state(sb)
