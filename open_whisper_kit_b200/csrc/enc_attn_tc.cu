@@ -95,6 +95,17 @@ v_transpose_kernel(const T16 * __restrict__ qkv, T16 * __restrict__ vt, int T, i
     }
 }
 
+// rows 64..79 of every head's V^T block: row 64 = 1 (row sums through the PV MMA), rows 65..79 = 0.  Written once per encoder
+// call when the QKV GEMM's epilogue fills rows 0..63 itself.
+template <typename T16>
+__global__ void vt_tail_rows_kernel(T16 * __restrict__ vt, int TP, int n_blocks) {
+    const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t per = (size_t) 16 * TP;
+    if (i >= per * n_blocks) return;
+    const size_t b = i / per, r = (i % per) / TP, k = i % TP;
+    vt[(b * FA_VROWS + 64 + r) * TP + k] = T16(r == 0 ? 1.0f : 0.0f);
+}
+
 template <typename T16>
 __global__ void __launch_bounds__(FA_THREADS, 2)
 enc_attn_tc_kernel(const __grid_constant__ TMap tm_q, const __grid_constant__ TMap tm_k, const __grid_constant__ TMap tm_vt,
@@ -315,8 +326,16 @@ size_t enc_attention_tc_scratch_bytes(int n_windows, int T, int n_head) {
     return (size_t) n_windows * n_head * FA_VROWS * TP * 2;
 }
 
+void enc_attention_tc_init_vt(DType dt, void * vt_scratch, int n_windows, int T, int n_head, cudaStream_t st) {
+    const int TP = round_up(T, 8), n_blocks = n_windows * n_head;
+    const size_t n = (size_t) 16 * TP * n_blocks;
+    if (dt == DType::F16) vt_tail_rows_kernel<__half><<<(unsigned) ceil_div<size_t>(n, 256), 256, 0, st>>>(reinterpret_cast<__half *>(vt_scratch), TP, n_blocks);
+    else vt_tail_rows_kernel<__nv_bfloat16><<<(unsigned) ceil_div<size_t>(n, 256), 256, 0, st>>>(reinterpret_cast<__nv_bfloat16 *>(vt_scratch), TP, n_blocks);
+    WB_CUDA(cudaGetLastError());
+}
+
 bool enc_attention_tc(DType dt, const void * qkv, void * out, void * vt_scratch, int n_windows, int T, int d, int n_head,
-                      int n_phantom, cudaStream_t st) {
+                      int n_phantom, cudaStream_t st, bool vt_ready) {
     if (d != n_head * FA_DH || (d % 8) != 0) return false;
     const int TP = round_up(T, 8);
     TMap tm_q, tm_k, tm_vt;
@@ -332,14 +351,14 @@ bool enc_attention_tc(DType dt, const void * qkv, void * out, void * vt_scratch,
         once_per_device(set, [&] {
             WB_CUDA(cudaFuncSetAttribute(enc_attn_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
         });
-        v_transpose_kernel<__half><<<tgrid, 256, 0, st>>>(reinterpret_cast<const __half *>(qkv), reinterpret_cast<__half *>(vt_scratch), T, TP, d, n_head);
+        if (!vt_ready) v_transpose_kernel<__half><<<tgrid, 256, 0, st>>>(reinterpret_cast<const __half *>(qkv), reinterpret_cast<__half *>(vt_scratch), T, TP, d, n_head);
         enc_attn_tc_kernel<__half><<<grid, FA_THREADS, FA_SMEM, st>>>(tm_q, tm_k, tm_vt, reinterpret_cast<__half *>(out), T, d, n_head, scale_log2e, n_phantom);
     } else {
         static DeviceOnce set;      // function attributes are per device
         once_per_device(set, [&] {
             WB_CUDA(cudaFuncSetAttribute(enc_attn_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
         });
-        v_transpose_kernel<__nv_bfloat16><<<tgrid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16 *>(qkv), reinterpret_cast<__nv_bfloat16 *>(vt_scratch), T, TP, d, n_head);
+        if (!vt_ready) v_transpose_kernel<__nv_bfloat16><<<tgrid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16 *>(qkv), reinterpret_cast<__nv_bfloat16 *>(vt_scratch), T, TP, d, n_head);
         enc_attn_tc_kernel<__nv_bfloat16><<<grid, FA_THREADS, FA_SMEM, st>>>(tm_q, tm_k, tm_vt, reinterpret_cast<__nv_bfloat16 *>(out), T, d, n_head, scale_log2e, n_phantom);
     }
     WB_CUDA(cudaGetLastError());

@@ -30,7 +30,10 @@ void enc_attention(DType dt, const void * qkv, void * out, int n_windows, int T,
 
 // The same attention on tcgen05 / TMEM (enc_attn_tc.cu); vt_scratch holds V^T, enc_attention_tc_scratch_bytes() bytes.
 size_t enc_attention_tc_scratch_bytes(int n_windows, int T, int n_head);
+// vt_ready: rows 0..63 of the V^T blocks were written by the QKV GEMM's epilogue (GemmArgs::vt) and rows 64..79 by
+// enc_attention_tc_init_vt(); otherwise a transpose kernel fills the scratch from qkv first.
+void enc_attention_tc_init_vt(DType dt, void * vt_scratch, int n_windows, int T, int n_head, cudaStream_t st);
 bool enc_attention_tc(DType dt, const void * qkv, void * out, void * vt_scratch, int n_windows, int T, int d, int n_head,
-                      int n_phantom, cudaStream_t st);
+                      int n_phantom, cudaStream_t st, bool vt_ready = false);
 
 }  // namespace wb

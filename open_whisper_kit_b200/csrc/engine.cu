@@ -297,6 +297,14 @@ bool Engine::encode(const std::vector<EncJob> & jobs, CrossKV & kv, int win0, bo
     }
     n_kernel_launches += 2;
 
+    // V^T for the tcgen05 attention comes straight out of the QKV GEMM's epilogue (WHISPER_B200_VT_EPILOGUE=0: transpose kernel)
+    static const bool vt_epi_env = !(getenv("WHISPER_B200_VT_EPILOGUE") && atoi(getenv("WHISPER_B200_VT_EPILOGUE")) == 0);
+    const bool vt_epi = vt_epi_env && vt != nullptr && d == H * 64;
+    const int TP = round_up(T, 8);
+    if (vt_epi) {
+        enc_attention_tc_init_vt(dt, vt, W, T, H, stream);
+        n_kernel_launches += 1;
+    }
     gemm_cls = PC_GEMM_ENC;
     for (int il = 0; il < hp.n_audio_layer; ++il) {
         const EncLayer & L = model.enc[il];
@@ -305,6 +313,9 @@ bool Engine::encode(const std::vector<EncJob> & jobs, CrossKV & kv, int win0, bo
             GemmArgs g;
             g.dtype = dt; g.M = (int) M; g.N = 3 * d; g.K = d; g.a = h16; g.lda = d; g.w = L.wqkv; g.ldw = d;
             g.bias = L.bqkv; g.out16 = qkv; g.ldo16 = 3 * d;
+            if (vt_epi) {
+                g.vt = vt; g.vt_col0 = 2 * d; g.vt_T = T; g.vt_TP = TP; g.vt_H = H;
+            }
             gemm(g);
         }
         prof_begin(PC_ENC_ATTN, 4.0 * (double) W * T * (double) T * d);
@@ -312,8 +323,8 @@ bool Engine::encode(const std::vector<EncJob> & jobs, CrossKV & kv, int win0, bo
             enc_attention(dt, qkv, att, W, T, d, H, n_phantom(T), stream);
             n_kernel_launches += 1;
         } else {
-            ok = ok && enc_attention_tc(dt, qkv, att, vt, W, T, d, H, n_phantom(T), stream);
-            n_kernel_launches += 2;
+            ok = ok && enc_attention_tc(dt, qkv, att, vt, W, T, d, H, n_phantom(T), stream, vt_epi);
+            n_kernel_launches += vt_epi ? 1 : 2;
         }
         prof_end();
         {

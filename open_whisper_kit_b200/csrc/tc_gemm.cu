@@ -58,6 +58,8 @@ struct EpiParams {
     int hm_T;          // head-major remap of out16 (GemmArgs::head_major_T)
     float * out32;
     int ldo32;
+    void * vt;         // V^T scratch of the encoder attention (GemmArgs::vt), or null
+    int vt_col0, vt_T, vt_TP, vt_H;
 };
 
 template <typename T16> __device__ __forceinline__ float gelu_epi(float v, int ref_f16) {
@@ -256,7 +258,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                             if (col0 + j < ep.N) o[j] = v[j];
                     }
                 }
-                if (out16) {
+                if (ep.vt && col0 >= ep.vt_col0) {
+                    // V third of the encoder's QKV projection: straight into the attention kernel's V^T layout
+                    const int w = row / ep.vt_T, t = row - w * ep.vt_T, c0 = col0 - ep.vt_col0;
+                    T16 * o = reinterpret_cast<T16 *>(ep.vt) + ((size_t) (w * ep.vt_H + (c0 >> 6)) * 80 + (c0 & 63)) * ep.vt_TP + t;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (col0 + j < ep.N) o[(size_t) j * ep.vt_TP] = Half16<T16>::from_f(v[j]);
+                } else if (out16) {
                     T16 * o = out16 + (size_t) row * ep.ldo16 + col0;
                     if (ep.hm_T > 0) {          // cross-K/V pool: [window][head][K|V][T][64]; a 32-column chunk stays inside one head
                         const int w = row / ep.hm_T, t = row - w * ep.hm_T, half = ep.N >> 1;
@@ -395,6 +404,8 @@ bool tc_gemm(const GemmArgs & g, cudaStream_t stream) {
     ep.out16 = g.out16;
     ep.ldo16 = g.ldo16;
     ep.hm_T = g.head_major_T;
+    ep.vt = g.vt; ep.vt_col0 = g.vt_col0; ep.vt_T = g.vt_T; ep.vt_TP = g.vt_TP; ep.vt_H = g.vt_H;
+    if (g.vt && (g.vt_col0 % 64 || g.vt_T <= 0 || g.vt_TP < g.vt_T || g.vt_H <= 0 || g.M % g.vt_T || (g.N - g.vt_col0) != g.vt_H * 64)) return false;
     ep.out32 = g.out32;
     ep.ldo32 = g.ldo32;
     static int n_sm = 0;

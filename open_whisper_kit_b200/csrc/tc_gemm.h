@@ -24,6 +24,10 @@ struct GemmArgs {
     // (w, t, kv, h, c) goes to out16[w * T * N + ((h * 2 + kv) * T + t) * 64 + c] -- each (window, head) stream contiguous.
     int head_major_T = 0;
     float * out32 = nullptr;    int ldo32 = 0;
+    // > 0 (tc_gemm only, encoder QKV GEMM): columns >= vt_col0 (the V third) are NOT written to out16 but, transposed, to the
+    // attention kernel's V^T scratch vt[(w * vt_H + head) * 80 + c][vt_TP] at key position t (row = w * vt_T + t): the
+    // per-layer transpose kernel disappears.  The 32 rows of a warp are 32 consecutive keys = one 64-byte segment per column.
+    void * vt = nullptr; int vt_col0 = 0, vt_T = 0, vt_TP = 0, vt_H = 0;
     // ---- LayerNorm folded into the decoder-step GEMMs (tc_skinny only; see tc_skinny.cu) ----
     // producer side: besides out32 (the new residual stream) the epilogue writes, per 64-column tile and row, the tile's mean
     // and centred sum of squares of out32 -> ln_part_out[tile * M + row]
