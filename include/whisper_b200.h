@@ -179,6 +179,19 @@ WB200_API int whisper_b200_kernel_sample(const float * logits, int n_logit_rows,
 WB200_API int whisper_b200_dtw_align(const float * probs, int n_heads, int n_tokens, int T, int n_audio, int skip_front,
                                      int medfilt_width, int * first_out);
 
+/* Voice activity detection (reference src/whisper.cpp:4341-5496, 6643-6825, 7947-8033).  The whisper_vad_* functions of
+ * whisper.h run the Silero model on the GPU (csrc/vad.cu); these hooks expose the two host stages around it for parity tests.
+ *   _vad_segments_from_probs: the probability -> speech-segment state machine on explicit probabilities (host only; replaces
+ *     whisper_vad_segments_from_probs at 5209-5420).  seg_out[2i], [2i+1] = start, end in centiseconds; returns the count.
+ *   _vad_filter: the audio filter whisper_full applies when params.vad is set (whisper_vad, 6643-6825): filtered samples into
+ *     out[0..cap), the (processed, original) time pairs into table; returns the filtered length, -1/-2 on failure.
+ *   _vad_map_time: processed -> original time through such a table (map_processed_to_original_time, 7947-7989; host only). */
+WB200_API int whisper_b200_vad_segments_from_probs(const float * probs, int n_probs, int n_window, struct whisper_vad_params params,
+                                                   long long * seg_out, int cap);
+WB200_API int whisper_b200_vad_filter(struct whisper_context * ctx, struct whisper_full_params params, const float * samples,
+                                      int n_samples, float * out, int cap, long long * table, int cap_pairs, int * n_pairs);
+WB200_API long long whisper_b200_vad_map_time(const long long * table, int n_pairs, long long t);
+
 /* Stream-K geometry of one GEMM phase of the persistent decoder-step kernel (csrc/dec_chain.h, host logic only -- needs
  * no device): out[0..4] = {tiles, k-blocks per tile, units, CTAs taking part, partial-tile slots per output tile}.
  * direct != 0: every CTA owns one whole 128-column tile.  Returns 0, or -1 for shapes the kernel does not take. */

@@ -18,6 +18,11 @@ _IP = _C.POINTER(_C.c_int)
 
 # extension entry points of include/whisper_b200.h
 EXT_PROTOTYPES = {
+    "whisper_b200_vad_segments_from_probs": (_C.c_int, [_FP, _C.c_int, _C.c_int, capi.whisper_vad_params,
+                                                        _C.POINTER(_C.c_longlong), _C.c_int]),
+    "whisper_b200_vad_filter": (_C.c_int, [_C.c_void_p, capi.whisper_full_params, _FP, _C.c_int, _FP, _C.c_int,
+                                           _C.POINTER(_C.c_longlong), _C.c_int, _IP]),
+    "whisper_b200_vad_map_time": (_C.c_longlong, [_C.POINTER(_C.c_longlong), _C.c_int, _C.c_longlong]),
     "whisper_b200_device_count": (_C.c_int, []),
     "whisper_b200_kernel_log_mel": (_C.c_int, [_FP, _C.c_int, _FP, _C.c_int, _FP, _C.c_int, _IP, _IP]),
     "whisper_b200_kernel_log_mel_bench": (_C.c_double, [_C.c_int, _C.c_int, _FP, _C.c_int, _C.c_int, _C.c_int]),

@@ -123,3 +123,63 @@ class Whisper:
 
     def all_tokens(self):
         return [t for s in self.segments() for t in s.tokens]
+
+
+class Vad:
+    """whisper_vad_* of include/whisper.h: Silero voice activity detection (speech probability per 512-sample chunk, and the
+    speech segments derived from them).  Works on either library; the product runs the model on the GPU and has no CPU path."""
+
+    def __init__(self, lib, model_path, gpu_device=0):
+        self.lib = lib
+        cp = lib.whisper_vad_default_context_params()
+        cp.gpu_device = gpu_device
+        self.vctx = lib.whisper_vad_init_from_file_with_params(model_path.encode(), cp)
+        if not self.vctx:
+            raise RuntimeError(f"whisper_vad_init_from_file_with_params failed for {model_path}")
+
+    def close(self):
+        if self.vctx:
+            self.lib.whisper_vad_free(self.vctx)
+            self.vctx = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def default_params(self):
+        return self.lib.whisper_vad_default_params()
+
+    def probs(self):
+        n = self.lib.whisper_vad_n_probs(self.vctx)
+        if n == 0:
+            return np.zeros(0, np.float32)
+        return np.ctypeslib.as_array(self.lib.whisper_vad_probs(self.vctx), shape=(n,)).copy()
+
+    def detect(self, pcm, stateful=False):
+        pcm = np.ascontiguousarray(pcm, dtype=np.float32)
+        fn = self.lib.whisper_vad_detect_speech_stateful if stateful else self.lib.whisper_vad_detect_speech
+        if not fn(self.vctx, capi.as_float_ptr(pcm), len(pcm)):
+            raise RuntimeError("whisper_vad_detect_speech failed")
+        return self.probs()
+
+    def reset(self):
+        self.lib.whisper_vad_reset_state(self.vctx)
+
+    def _take(self, segs):
+        if not segs:
+            raise RuntimeError("whisper_vad_segments_* failed")
+        n = self.lib.whisper_vad_segments_n_segments(segs)
+        out = [(self.lib.whisper_vad_segments_get_segment_t0(segs, i), self.lib.whisper_vad_segments_get_segment_t1(segs, i))
+               for i in range(n)]
+        self.lib.whisper_vad_free_segments(segs)
+        return out
+
+    def segments_from_probs(self, params=None):
+        return self._take(self.lib.whisper_vad_segments_from_probs(self.vctx, params or self.default_params()))
+
+    def segments_from_samples(self, pcm, params=None):
+        pcm = np.ascontiguousarray(pcm, dtype=np.float32)
+        return self._take(self.lib.whisper_vad_segments_from_samples(self.vctx, params or self.default_params(),
+                                                                     capi.as_float_ptr(pcm), len(pcm)))

@@ -62,6 +62,10 @@ class whisper_vad_params(C.Structure):
     ]
 
 
+class whisper_vad_context_params(C.Structure):
+    _fields_ = [("n_threads", C.c_int), ("use_gpu", C.c_bool), ("gpu_device", C.c_int)]
+
+
 class _greedy(C.Structure):
     _fields_ = [("best_of", C.c_int)]
 
@@ -255,16 +259,16 @@ PROTOTYPES = {
     "whisper_full_get_token_p": (C.c_float, [_P, _I, _I]),
     "whisper_full_get_token_p_from_state": (C.c_float, [_P, _I, _I]),
     "whisper_vad_default_params": (whisper_vad_params, []),
-    "whisper_vad_default_context_params": (None, []),  # struct by value; only presence is checked
-    "whisper_vad_init_from_file_with_params": (_P, None),
-    "whisper_vad_init_with_params": (_P, None),
+    "whisper_vad_default_context_params": (whisper_vad_context_params, []),
+    "whisper_vad_init_from_file_with_params": (_P, [C.c_char_p, whisper_vad_context_params]),
+    "whisper_vad_init_with_params": (_P, [_P, whisper_vad_context_params]),
     "whisper_vad_detect_speech": (c_bool, [_P, _FP, _I]),
     "whisper_vad_detect_speech_stateful": (c_bool, [_P, _FP, _I]),
     "whisper_vad_reset_state": (None, [_P]),
     "whisper_vad_n_probs": (_I, [_P]),
     "whisper_vad_probs": (_FP, [_P]),
-    "whisper_vad_segments_from_probs": (_P, None),
-    "whisper_vad_segments_from_samples": (_P, None),
+    "whisper_vad_segments_from_probs": (_P, [_P, whisper_vad_params]),
+    "whisper_vad_segments_from_samples": (_P, [_P, whisper_vad_params, _FP, _I]),
     "whisper_vad_segments_n_segments": (_I, [_P]),
     "whisper_vad_segments_get_segment_t0": (C.c_float, [_P, _I]),
     "whisper_vad_segments_get_segment_t1": (C.c_float, [_P, _I]),

@@ -73,9 +73,18 @@ struct whisper_state {
     int64_t t_beg = 0, t_last = 0;
     whisper_token tid_last = 0;
 
+    // VAD pre-filter of whisper_full (reference whisper_state, src/whisper.cpp:923-934): the detector is created on first use;
+    // the table maps times of the filtered ("processed") audio back to the original recording
+    struct whisper_vad_context * vad_context = nullptr;
+    bool has_vad_segments = false;
+    struct vad_time_mapping { int64_t processed_time, original_time; };
+    std::vector<vad_time_mapping> vad_mapping_table;
+
     struct whisper_context * ctx = nullptr;
     int device = 0;                    // CUDA device of the buffers above (kept here so the state can outlive its context)
 };
+
+struct whisper_vad_context;
 
 struct whisper_context {
     int64_t t_load_us = 0;

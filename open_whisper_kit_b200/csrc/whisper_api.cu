@@ -11,6 +11,7 @@
 #include <thread>
 
 #include "full.h"
+#include "vad_api.h"
 #include "whisper_b200.h"
 
 using namespace wb;
@@ -282,6 +283,7 @@ void whisper_free_state(struct whisper_state * state) {
     // The context may already be gone (the reference lets a caller free its states after the context): everything the state
     // needs to release its device buffers is the device index it keeps itself.  cudaFree synchronises with in-flight work.
     cudaSetDevice(state->device);
+    vad_free_state_context(state);
     delete state;
 }
 void whisper_free(struct whisper_context * ctx) {
@@ -292,9 +294,13 @@ void whisper_free(struct whisper_context * ctx) {
         whisper_state * st = ctx->state;
         ctx->state = nullptr;
         st->ctx = nullptr;
+        vad_free_state_context(st);
         delete st;
     }
-    for (whisper_state * st : ctx->spare_states) delete st;
+    for (whisper_state * st : ctx->spare_states) {
+        vad_free_state_context(st);
+        delete st;
+    }
     ctx->spare_states.clear();
     delete ctx;
 }
@@ -571,9 +577,18 @@ int whisper_full_with_state(struct whisper_context * ctx, struct whisper_state *
 }
 int whisper_full(struct whisper_context * ctx, struct whisper_full_params params, const float * samples, int n_samples) {
     if (!ctx || !ctx->state) return -1;
-    if (params.vad) {
-        wlog(GGML_LOG_LEVEL_ERROR, "%s: VAD is outside the scope of the B200 path (failed to compute VAD)\n", __func__);
-        return -1;
+    std::vector<float> vad_samples;
+    if (params.vad) {                       // src/whisper.cpp:7784-7797
+        if (!vad_filter(*ctx, *ctx->state, params, samples, n_samples, vad_samples)) {
+            wlog(GGML_LOG_LEVEL_ERROR, "%s: failed to compute VAD\n", __func__);
+            return -1;
+        }
+        if (vad_samples.empty()) {
+            ctx->state->result_all.clear();
+            return 0;
+        }
+        samples = vad_samples.data();
+        n_samples = (int) vad_samples.size();
     }
     return whisper_full_with_state(ctx, ctx->state, params, samples, n_samples);
 }
@@ -695,9 +710,15 @@ int whisper_full_parallel(struct whisper_context * ctx, struct whisper_full_para
                           int n_processors) {
     if (!ctx || !ctx->state) return -1;
     if (n_processors <= 1) return whisper_full(ctx, params, samples, n_samples);
-    if (params.vad) {
-        wlog(GGML_LOG_LEVEL_ERROR, "%s: VAD is outside the scope of the B200 path (failed to compute VAD)\n", __func__);
-        return -1;
+    std::vector<float> vad_samples;
+    if (params.vad) {                       // src/whisper.cpp:7812-7824
+        if (!vad_filter(*ctx, *ctx->state, params, samples, n_samples, vad_samples)) {
+            wlog(GGML_LOG_LEVEL_ERROR, "%s: failed to compute VAD\n", __func__);
+            return -1;
+        }
+        if (vad_samples.empty()) return 0;
+        samples = vad_samples.data();
+        n_samples = (int) vad_samples.size();
     }
     try {
         return full_parallel_on({ctx}, params, samples, n_samples, n_processors);
@@ -770,11 +791,17 @@ WB200_API struct whisper_context * whisper_b200_group_context(struct whisper_b20
 WB200_API int whisper_b200_group_full_parallel(struct whisper_b200_group * g, struct whisper_full_params params, const float * samples,
                                                int n_samples, int n_processors) {
     if (!g || g->ctxs.empty() || !g->ctxs[0]->state) return -1;
-    if (params.vad) {
-        wlog(GGML_LOG_LEVEL_ERROR, "%s: VAD is outside the scope of the B200 path (failed to compute VAD)\n", __func__);
-        return -1;
-    }
     if (n_processors <= 1) return whisper_full(g->ctxs[0], params, samples, n_samples);
+    std::vector<float> vad_samples;
+    if (params.vad) {                       // the filter runs once, on the first GPU; results land in its state as always
+        if (!vad_filter(*g->ctxs[0], *g->ctxs[0]->state, params, samples, n_samples, vad_samples)) {
+            wlog(GGML_LOG_LEVEL_ERROR, "%s: failed to compute VAD\n", __func__);
+            return -1;
+        }
+        if (vad_samples.empty()) return 0;
+        samples = vad_samples.data();
+        n_samples = (int) vad_samples.size();
+    }
     try {
         return full_parallel_on(g->ctxs, params, samples, n_samples, n_processors);
     } catch (const std::exception & ex) {
@@ -803,9 +830,10 @@ WB200_API int whisper_b200_pcm16_to_mel(struct whisper_context * ctx, const int1
 WB200_API int whisper_b200_full_parallel_i16(struct whisper_context * ctx, struct whisper_full_params params, const int16_t * samples,
                                              int n_samples, int n_processors) {
     if (!ctx || !ctx->state || !samples) return -1;
-    if (params.vad) {
-        wlog(GGML_LOG_LEVEL_ERROR, "%s: VAD is outside the scope of the B200 path (failed to compute VAD)\n", __func__);
-        return -1;
+    if (params.vad) {                       // the detector takes f32 PCM: widen on the host, then the f32 entry point
+        std::vector<float> f((size_t) std::max(n_samples, 0));
+        for (int i = 0; i < n_samples; ++i) f[i] = samples[i] * (1.0f / 32768.0f);
+        return whisper_full_parallel(ctx, params, f.data(), n_samples, n_processors);
     }
     try {
         if (n_processors <= 1) {
@@ -829,10 +857,20 @@ int whisper_full_n_segments_from_state(struct whisper_state * state) { return (i
 int whisper_full_n_segments(struct whisper_context * ctx) { return (int) ctx->state->result_all.size(); }
 int whisper_full_lang_id_from_state(struct whisper_state * state) { return state->lang_id; }
 int whisper_full_lang_id(struct whisper_context * ctx) { return ctx->state->lang_id; }
-int64_t whisper_full_get_segment_t0_from_state(struct whisper_state * state, int i) { return state->result_all[i].t0; }
-int64_t whisper_full_get_segment_t0(struct whisper_context * ctx, int i) { return ctx->state->result_all[i].t0; }
-int64_t whisper_full_get_segment_t1_from_state(struct whisper_state * state, int i) { return state->result_all[i].t1; }
-int64_t whisper_full_get_segment_t1(struct whisper_context * ctx, int i) { return ctx->state->result_all[i].t1; }
+// with the VAD pre-filter the stored times are those of the filtered audio: map them back (src/whisper.cpp:7991-8033)
+int64_t whisper_full_get_segment_t0_from_state(struct whisper_state * state, int i) {
+    const int64_t t0 = state->result_all[i].t0;
+    if (!state->has_vad_segments || state->vad_mapping_table.empty()) return t0;
+    return vad_map_time(state->vad_mapping_table, t0);
+}
+int64_t whisper_full_get_segment_t1_from_state(struct whisper_state * state, int i) {
+    const int64_t t1 = state->result_all[i].t1;
+    if (!state->has_vad_segments || state->vad_mapping_table.empty()) return t1;
+    const int64_t o1 = vad_map_time(state->vad_mapping_table, t1), o0 = whisper_full_get_segment_t0_from_state(state, i);
+    return o1 - o0 < 10 ? o0 + 10 : o1;          // never a zero-length segment
+}
+int64_t whisper_full_get_segment_t0(struct whisper_context * ctx, int i) { return whisper_full_get_segment_t0_from_state(ctx->state, i); }
+int64_t whisper_full_get_segment_t1(struct whisper_context * ctx, int i) { return whisper_full_get_segment_t1_from_state(ctx->state, i); }
 bool whisper_full_get_segment_speaker_turn_next_from_state(struct whisper_state * state, int i) { return state->result_all[i].speaker_turn_next; }
 bool whisper_full_get_segment_speaker_turn_next(struct whisper_context * ctx, int i) { return ctx->state->result_all[i].speaker_turn_next; }
 const char * whisper_full_get_segment_text_from_state(struct whisper_state * state, int i) { return state->result_all[i].text.c_str(); }
@@ -853,33 +891,6 @@ float whisper_full_get_token_p_from_state(struct whisper_state * state, int i, i
 float whisper_full_get_token_p(struct whisper_context * ctx, int i, int j) { return ctx->state->result_all[i].tokens[j].p; }
 float whisper_full_get_segment_no_speech_prob_from_state(struct whisper_state * state, int i) { return state->result_all[i].no_speech_prob; }
 float whisper_full_get_segment_no_speech_prob(struct whisper_context * ctx, int i) { return ctx->state->result_all[i].no_speech_prob; }
-
-// ---- VAD: outside the scope of the path; init reports failure exactly like a missing model file ---------------------
-struct whisper_vad_context_params whisper_vad_default_context_params(void) {
-    whisper_vad_context_params r = {4, false, 0};
-    return r;
-}
-struct whisper_vad_context * whisper_vad_init_from_file_with_params(const char *, struct whisper_vad_context_params) {
-    wlog(GGML_LOG_LEVEL_ERROR, "%s: VAD is not part of the B200 transcription path\n", __func__);
-    return nullptr;
-}
-struct whisper_vad_context * whisper_vad_init_with_params(struct whisper_model_loader * loader, struct whisper_vad_context_params) {
-    if (loader && loader->close) loader->close(loader->context);
-    wlog(GGML_LOG_LEVEL_ERROR, "%s: VAD is not part of the B200 transcription path\n", __func__);
-    return nullptr;
-}
-bool whisper_vad_detect_speech(struct whisper_vad_context *, const float *, int) { return false; }
-bool whisper_vad_detect_speech_stateful(struct whisper_vad_context *, const float *, int) { return false; }
-void whisper_vad_reset_state(struct whisper_vad_context *) {}
-int whisper_vad_n_probs(struct whisper_vad_context *) { return 0; }
-float * whisper_vad_probs(struct whisper_vad_context *) { return nullptr; }
-struct whisper_vad_segments * whisper_vad_segments_from_probs(struct whisper_vad_context *, struct whisper_vad_params) { return nullptr; }
-struct whisper_vad_segments * whisper_vad_segments_from_samples(struct whisper_vad_context *, struct whisper_vad_params, const float *, int) { return nullptr; }
-int whisper_vad_segments_n_segments(struct whisper_vad_segments *) { return 0; }
-float whisper_vad_segments_get_segment_t0(struct whisper_vad_segments *, int) { return 0.0f; }
-float whisper_vad_segments_get_segment_t1(struct whisper_vad_segments *, int) { return 0.0f; }
-void whisper_vad_free_segments(struct whisper_vad_segments *) {}
-void whisper_vad_free(struct whisper_vad_context *) {}
 
 // ---- misc ---------------------------------------------------------------------------------------------------------
 int whisper_bench_memcpy(int n_threads) {

@@ -187,4 +187,49 @@ float ref_no_speech_prob(struct whisper_context * ctx) {
     return ctx && ctx->state ? ctx->state->no_speech_prob : -1.0f;
 }
 
+// ---- VAD ------------------------------------------------------------------------------------------------------------------
+// whisper_vad_segments_from_probs (src/whisper.cpp:5209-5420) on explicit probabilities: it reads only probs and n_window of
+// the context, so a bare context carries them.  seg_out[2i], [2i+1] = start, end (centiseconds).
+__attribute__((visibility("default")))
+int ref_vad_segments_from_probs(const float * probs, int n_probs, int n_window, struct whisper_vad_params params,
+                                long long * seg_out, int cap) {
+    whisper_vad_context v;
+    v.n_window = n_window;
+    v.probs.assign(probs, probs + n_probs);
+    whisper_vad_segments * s = whisper_vad_segments_from_probs(&v, params);
+    if (!s) return -1;
+    const int n = (int) s->data.size();
+    for (int i = 0; i < n && i < cap; ++i) {
+        seg_out[2*i]     = s->data[i].start;
+        seg_out[2*i + 1] = s->data[i].end;
+    }
+    whisper_vad_free_segments(s);
+    return n;
+}
+
+// the audio filter of whisper_full (whisper_vad, src/whisper.cpp:6643-6825): filtered samples and the time mapping table
+__attribute__((visibility("default")))
+int ref_vad_filter(struct whisper_context * ctx, struct whisper_full_params params, const float * samples, int n_samples,
+                   float * out, int cap, long long * table, int cap_pairs, int * n_pairs) {
+    if (!ctx || !ctx->state) return -1;
+    std::vector<float> filtered;
+    if (!whisper_vad(ctx, ctx->state, params, samples, n_samples, filtered)) return -2;
+    const auto & tab = ctx->state->vad_mapping_table;
+    *n_pairs = (int) tab.size();
+    for (int i = 0; i < (int) tab.size() && i < cap_pairs; ++i) {
+        table[2*i]     = tab[i].processed_time;
+        table[2*i + 1] = tab[i].original_time;
+    }
+    for (int i = 0; i < (int) filtered.size() && i < cap; ++i) out[i] = filtered[i];
+    return (int) filtered.size();
+}
+
+// map_processed_to_original_time (src/whisper.cpp:7947-7989) on an explicit table
+__attribute__((visibility("default")))
+long long ref_vad_map_time(const long long * table, int n_pairs, long long t) {
+    std::vector<vad_time_mapping> tab(n_pairs);
+    for (int i = 0; i < n_pairs; ++i) tab[i] = {table[2*i], table[2*i + 1]};
+    return map_processed_to_original_time(t, tab);
+}
+
 } // extern "C"

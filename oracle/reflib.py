@@ -17,6 +17,10 @@ from open_whisper_kit_b200 import capi  # noqa: E402
 _FP = C.POINTER(C.c_float)
 
 REF_PROTOTYPES = {
+    "ref_vad_segments_from_probs": (C.c_int, [_FP, C.c_int, C.c_int, capi.whisper_vad_params, C.POINTER(C.c_longlong), C.c_int]),
+    "ref_vad_filter": (C.c_int, [C.c_void_p, capi.whisper_full_params, _FP, C.c_int, _FP, C.c_int, C.POINTER(C.c_longlong),
+                                 C.c_int, C.POINTER(C.c_int)]),
+    "ref_vad_map_time": (C.c_longlong, [C.POINTER(C.c_longlong), C.c_int, C.c_longlong]),
     "ref_mel_dims": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "ref_mel_copy": (C.c_int, [C.c_void_p, _FP]),
     "ref_log_mel": (C.c_int, [_FP, C.c_int, C.c_int, _FP, C.c_int, _FP, C.c_int, C.POINTER(C.c_int),
