@@ -147,7 +147,11 @@ def test_full_with_vad_is_full_on_the_filtered_audio_with_mapped_times(lib, mode
         # parallel entry point, 2 processors: same filter in front
         rc, par = w.full(p, pcm, n_processors=2)
         assert rc == 0 and len(par) > 0
-        p.vad = False
+    # (a fresh context: like the reference, a state keeps its time table until the next VAD run, so a plain run on the same
+    # state would read its times through the stale table)
+    with api.Whisper(lib, path) as w:
+        p = w.greedy_params()
+        p.max_tokens = 24
         rc, plain = w.full(p, filtered)
         assert rc == 0
     assert [s.tokens for s in with_vad] == [s.tokens for s in plain]
@@ -171,6 +175,9 @@ def test_full_with_vad_on_silence_returns_no_segments(lib, model_dir):
         p.vad_model_path = VAD_MODEL.encode()
         rc, segs = w.full(p, np.zeros(16000 * 3, np.float32))
         assert rc == 0 and segs == []
+    with api.Whisper(lib, path) as w:               # (the detector is created once per state: a new state for the bad path)
+        p = w.greedy_params()
+        p.vad = True
         p.vad_model_path = b"/nonexistent/vad.bin"
         rc, _ = w.full(p, np.zeros(16000, np.float32))
         assert rc == -1
