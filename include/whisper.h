@@ -4,7 +4,7 @@
  * group below): same symbol names, argument meaning, by-value struct layouts and error conventions, so
  * whisper-cli, whisper-bench, the Go/Java/Ruby/JS bindings and the Swift SDK link against this library
  * unchanged.  Only the batched transcription path behind it is re-implemented (hand-written sm_100a CUDA);
- * entry points of subsystems that are out of scope for this path (VAD, OpenVINO, ggml micro-benches) are
+ * entry points of subsystems that are out of scope for this path (OpenVINO, ggml micro-benches) are
  * exported and return the reference's own "not available" value.
  *
  * The two ggml typedefs the reference header leaks (ggml_abort_callback, ggml_log_callback) come from the
@@ -340,7 +340,7 @@ struct whisper_full_params {
     size_t i_start_rule;
     float grammar_penalty;
 
-    bool vad;                     /* VAD pre-filter: out of scope; vad=true makes whisper_full return -1 */
+    bool vad;                     /* VAD pre-filter (GPU Silero detector, csrc/vad.cu); -1 if the detector cannot be set up */
     const char * vad_model_path;
     whisper_vad_params vad_params;
 };
@@ -380,7 +380,8 @@ WHISPER_API whisper_token_data whisper_full_get_token_data_from_state(struct whi
 WHISPER_API float whisper_full_get_token_p(struct whisper_context * ctx, int i_segment, int i_token);
 WHISPER_API float whisper_full_get_token_p_from_state(struct whisper_state * state, int i_segment, int i_token);
 
-/* ---- VAD (reference include/whisper.h:690-734): out of scope for the path; init returns NULL ---- */
+/* ---- VAD (reference include/whisper.h:690-734): the Silero detector on the GPU (csrc/vad.cu, csrc/vad_api.cu).
+ * use_gpu is accepted and ignored (there is no CPU path); gpu_device selects the device; init returns NULL without one. ---- */
 WHISPER_API struct whisper_vad_params whisper_vad_default_params(void);
 
 struct whisper_vad_context_params {
