@@ -238,7 +238,7 @@ def cpu_baseline_subprocess(args, extra=()):
 
 
 # ---------------------------------------------------------------------------------------------------------------
-def parity_check(lib, model_path, device):
+def parity_check(lib, model_path, device, cross_kv="f16"):
     """Decode the first two windows in the golden numeric mode and compare with the reference-generated fixture
     (tests/golden/golden_r2.json, case large-v3/synth2/nots48; rule of tests/test_gpu_parity_r2.py)."""
     from open_whisper_kit_b200 import modelgen
@@ -249,7 +249,10 @@ def parity_check(lib, model_path, device):
     cp = lib.whisper_context_default_params()
     cp.gpu_device = device
     cp.flash_attn = False
+    if cross_kv == "fp8":
+        os.environ["WHISPER_B200_CROSS_KV"] = "fp8"
     ctx = lib.whisper_init_from_file_with_params(model_path.encode(), cp)
+    os.environ.pop("WHISPER_B200_CROSS_KV", None)
     if not ctx:
         return {"ok": False, "why": "second context failed to load"}
     try:
@@ -345,7 +348,12 @@ def main_transcribe(args):
     cp = lib.whisper_context_default_params()
     cp.gpu_device = local_rank
     t0 = time.time()
+    if args.cross_kv == "fp8":
+        os.environ["WHISPER_B200_CROSS_KV"] = "fp8"        # read when a context is created
+    else:
+        os.environ.pop("WHISPER_B200_CROSS_KV", None)
     ctx = lib.whisper_init_from_file_with_params(path.encode(), cp)
+    os.environ.pop("WHISPER_B200_CROSS_KV", None)
     if not ctx:
         raise SystemExit("model load failed")
     load_s = time.time() - t0
@@ -411,10 +419,35 @@ def main_transcribe(args):
         ms_g = timed(lambda: step_device(p=pg), max(1, args.steps))
         greedy_ts = {"ms_per_step": ms_g / max(1, args.steps), "ratio_beam_over_greedy": (ms_dev / args.steps) / (ms_g / max(1, args.steps))}
 
+    # secondary line of the default single-GPU run: the same step with the opt-in e4m3 cross-K/V pool (reduced storage precision,
+    # tests/test_gpu_cross_fp8.py is its parity study) -- what halving the bytes of the roofline kernel buys
+    fp8_line = None
+    if world == 1 and not beam and args.cross_kv == "f16" and not args.no_fp8_line and wl.n_win:
+        try:
+            os.environ["WHISPER_B200_CROSS_KV"] = "fp8"
+            ctx8 = lib.whisper_init_from_file_with_params(path.encode(), cp)
+            os.environ.pop("WHISPER_B200_CROSS_KV", None)
+            if ctx8:
+                def step8():
+                    rc8 = lib.whisper_b200_full_device(ctx8, params, wl.dev_ptr, wl.n_samples, wl.n_win)
+                    assert rc8 == 0, rc8
+                for _ in range(2):
+                    step8()
+                ms8 = timed(step8, max(1, args.steps)) / max(1, args.steps)
+                same = segment_tokens(lib, ctx8) == segment_tokens(lib, ctx)
+                fp8_line = {"value": audio_s / (ms8 * 1e-3), "unit": "audio-s/s", "ms_per_step": ms8,
+                            "tokens_identical_to_f16_pool_run": bool(same),
+                            "note": "WHISPER_B200_CROSS_KV=fp8: cross K/V stored as e4m3 chunks with per-chunk scales; NOT the reference's "
+                                    "F16 cache, off by default; parity study: tests/test_gpu_cross_fp8.py"}
+                lib.whisper_free(ctx8)
+        except Exception as ex:            # never lets the opt-in line cost the headline
+            os.environ.pop("WHISPER_B200_CROSS_KV", None)
+            fp8_line = {"value": None, "note": f"failed: {ex}"}
+
     check = None
     cpu_baseline = None
     if rank == 0 and not beam:
-        check = parity_check(lib, path, local_rank)
+        check = parity_check(lib, path, local_rank, args.cross_kv)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_baseline = cpu_baseline_subprocess(args)
 
@@ -439,6 +472,11 @@ def main_transcribe(args):
             "cpu_baseline": cpu_baseline,
             "model_load_s": round(load_s, 1),
         }
+        if args.cross_kv == "fp8":
+            line["config"]["cross_kv"] = "e4m3 chunks, per-chunk f32 scale (opt-in; the reference's cache is F16)"
+            line["config"]["workload"] += ", cross K/V e4m3 (opt-in)"
+        if fp8_line is not None:
+            line["opt_in_fp8_cross_kv"] = fp8_line
         if weak is not None:
             line["weak"] = weak
         if greedy_ts is not None:
@@ -621,6 +659,9 @@ def main():
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--no-weak", action="store_true", help="skip the second (weak-scaling) measurement at N > 1")
     ap.add_argument("--timestamps", action="store_true", help="decode with timestamp tokens (variable work)")
+    ap.add_argument("--cross-kv", default="f16", choices=["f16", "fp8"],
+                    help="fp8: the whole run with the opt-in e4m3 cross-K/V pool (reduced precision; not the headline configuration)")
+    ap.add_argument("--no-fp8-line", action="store_true", help="skip the secondary e4m3 cross-K/V measurement of the default run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -458,6 +458,274 @@ cross_attn_bulk_kernel(const T16 * __restrict__ q, int ldq, const DecRow * __res
     }
 }
 
+// ---- cross-attention on an e4m3 K/V pool (opt-in, WHISPER_B200_CROSS_KV=fp8) ------------------------------------------------
+// The K/V stream is what bounds the decoder step (at the HBM roof in 16 bits), so this variant halves the bytes: the pool holds
+// e4m3 values in self-contained chunks of 128 keys -- [128 keys][64 dims] bytes followed by the chunk's f32 scale (16 bytes with
+// padding) -- written by cross_quant_kernel from the 16-bit GEMM output (scale = max |x| of the chunk / 448; a floating-point
+// format keeps its relative precision across binades, so a finer scale granularity would buy nothing).  Per (window, layer,
+// head): nck K chunks, then nck V chunks.  Same ring / producer / softmax structure and thread -> key / dimension mapping as
+// cross_attn_bulk_kernel; the dot products run as HFMA2 on e4m3 -> f16 converted pairs (exact conversion) with short f16
+// accumulation chains (4 products per lane for a score, 4 keys per flush for the output) that end in f32 -- far below the e4m3
+// quantisation step.  q is pre-multiplied by 2^-4 so that no f16 partial sum can overflow (|k| <= 448).
+// NOT the reference's arithmetic (its cross K/V is F16, src/whisper.cpp:942): a reduced-precision storage format, off by default.
+constexpr int C8_STAGES = 6, C8_KEYS = 128, C8_DATA = C8_KEYS * 64, C8_CHUNK = C8_DATA + 16;
+
+__device__ __forceinline__ __half2 e4m3x2_to_half2(unsigned short v) {
+    unsigned r;
+    asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(r) : "h"(v));
+    return *reinterpret_cast<__half2 *>(&r);
+}
+
+template <int NQ>
+__global__ void __launch_bounds__(CB_THREADS, 2)
+cross_attn_fp8_kernel(const __half * __restrict__ q, int ldq, const DecRow * __restrict__ rows, const int2 * __restrict__ groups, int d,
+                      size_t layer_off, int T, float kq_scale, int n_phantom, __half * __restrict__ out) {
+    extern __shared__ __align__(128) uint8_t cb_smem[];         // ring [C8_STAGES][C8_CHUNK] | scores [NQ][T_pad] f32
+    __shared__ __align__(8) uint64_t b_full[C8_STAGES], b_empty[C8_STAGES];
+    __shared__ float s_red[NQ][2 * CB_WARPS];
+    __shared__ float s_o[CB_WARPS][64];
+    const int T_pad = (T + 31) & ~31;
+    float * s_sc = reinterpret_cast<float *>(cb_smem + ((C8_STAGES * C8_CHUNK + 127) & ~127));
+    const int h = blockIdx.y;
+    const int r0 = NQ > 1 ? groups[blockIdx.x].x : (int) blockIdx.x;
+    const int nq = NQ > 1 ? groups[blockIdx.x].y : 1;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int sub = lane & 7, grp = lane >> 3;      // 8 lanes per key row (8 bytes each), 4 key rows per warp instruction
+    const int nck = (T + C8_KEYS - 1) / C8_KEYS;
+    if (tid == 0) {
+        for (int i = 0; i < C8_STAGES; ++i) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t) __cvta_generic_to_shared(&b_full[i])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t) __cvta_generic_to_shared(&b_empty[i])), "r"(CB_WARPS));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == CB_WARPS) {
+        if (lane == 0) {
+            const DecRow row = rows[r0];
+            const uint8_t * blk = reinterpret_cast<const uint8_t *>(row.cross_kv) + layer_off * 2 + (size_t) h * 2 * nck * C8_CHUNK;
+            for (int c = 0; c < 2 * nck; ++c) {
+                const int s = c % C8_STAGES;
+                if (c >= C8_STAGES) cb_wait(&b_empty[s], ((c / C8_STAGES) - 1) & 1);
+                const uint32_t bar = (uint32_t) __cvta_generic_to_shared(&b_full[s]);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(C8_CHUNK) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 (uint32_t) __cvta_generic_to_shared(cb_smem + s * C8_CHUNK)),
+                             "l"(blk + (size_t) c * C8_CHUNK), "r"(C8_CHUNK), "r"(bar)
+                             : "memory");
+                if (c == nck) pdl_trigger();
+            }
+        }
+        return;
+    }
+
+    pdl_wait();
+    __half2 q2[NQ][4];
+#pragma unroll
+    for (int qi = 0; qi < NQ; ++qi) {
+        const uint4 u = qi < nq ? *reinterpret_cast<const uint4 *>(q + (size_t) (r0 + qi) * ldq + h * 64 + sub * 8) : make_uint4(0, 0, 0, 0);
+        const __half2 * e = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) q2[qi][j] = __hmul2(e[j], __float2half2_rn(0.0625f));
+    }
+    auto sync_compute = [] { asm volatile("bar.sync 1, %0;" ::"n"(CB_WARPS * 32) : "memory"); };
+    float mx[NQ];
+#pragma unroll
+    for (int qi = 0; qi < NQ; ++qi) mx[qi] = -INFINITY;
+    for (int c = 0; c < nck; ++c) {
+        const int s = c % C8_STAGES;
+        cb_wait(&b_full[s], (c / C8_STAGES) & 1);
+        const uint8_t * stage = cb_smem + s * C8_CHUNK;
+        const float sc = *reinterpret_cast<const float *>(stage + C8_DATA) * kq_scale * 16.0f;
+#pragma unroll
+        for (int u = 0; u < C8_KEYS / (4 * CB_WARPS); ++u) {
+            const int kl = warp * 4 + grp + 4 * CB_WARPS * u, t = c * C8_KEYS + kl;
+            const uint2 kb = *reinterpret_cast<const uint2 *>(stage + kl * 64 + sub * 8);
+            __half2 k2[4];
+            k2[0] = e4m3x2_to_half2((unsigned short) (kb.x & 0xffffu));
+            k2[1] = e4m3x2_to_half2((unsigned short) (kb.x >> 16));
+            k2[2] = e4m3x2_to_half2((unsigned short) (kb.y & 0xffffu));
+            k2[3] = e4m3x2_to_half2((unsigned short) (kb.y >> 16));
+#pragma unroll
+            for (int qi = 0; qi < NQ; ++qi) {
+                if (NQ > 1 && qi >= nq) break;
+                __half2 a2 = __hmul2(q2[qi][0], k2[0]);
+#pragma unroll
+                for (int j = 1; j < 4; ++j) a2 = __hfma2(q2[qi][j], k2[j], a2);
+                float acc = __low2float(a2) + __high2float(a2);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+                acc *= sc;
+                if (t < T) {
+                    if (sub == 0) s_sc[qi * T_pad + t] = acc;
+                    mx[qi] = fmaxf(mx[qi], acc);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t) __cvta_generic_to_shared(&b_empty[s])) : "memory");
+    }
+    pdl_trigger();
+#pragma unroll
+    for (int qi = 0; qi < NQ; ++qi) {
+        const float m = warp_max(mx[qi]);
+        if (lane == 0) s_red[qi][warp] = m;
+    }
+    sync_compute();
+    float inv[NQ];
+#pragma unroll
+    for (int qi = 0; qi < NQ; ++qi) {
+        float m = s_red[qi][0];
+#pragma unroll
+        for (int i = 1; i < CB_WARPS; ++i) m = fmaxf(m, s_red[qi][i]);
+        if (n_phantom > 0) m = fmaxf(m, 0.0f);
+        mx[qi] = m;
+        float sum = 0.0f;
+        if (qi < nq)
+            for (int t = tid; t < T; t += CB_WARPS * 32) {
+                const float e = expf(s_sc[qi * T_pad + t] - m);
+                s_sc[qi * T_pad + t] = e;
+                sum += e;
+            }
+        sum = warp_sum(sum);
+        if (lane == 0) s_red[qi][CB_WARPS + warp] = sum;
+    }
+    sync_compute();
+#pragma unroll
+    for (int qi = 0; qi < NQ; ++qi) {
+        float sum = s_red[qi][CB_WARPS];
+#pragma unroll
+        for (int i = 1; i < CB_WARPS; ++i) sum += s_red[qi][CB_WARPS + i];
+        if (n_phantom > 0) sum += (float) n_phantom * expf(-mx[qi]);
+        inv[qi] = 1.0f / sum;
+    }
+
+    float o[NQ][8];
+#pragma unroll
+    for (int qi = 0; qi < NQ; ++qi)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[qi][j] = 0.0f;
+    for (int c = nck; c < 2 * nck; ++c) {
+        const int s = c % C8_STAGES, c0 = (c - nck) * C8_KEYS;
+        cb_wait(&b_full[s], (c / C8_STAGES) & 1);
+        const uint8_t * stage = cb_smem + s * C8_CHUNK;
+        const float sv = *reinterpret_cast<const float *>(stage + C8_DATA);
+        __half2 a2[NQ][4];
+#pragma unroll
+        for (int qi = 0; qi < NQ; ++qi)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) a2[qi][j] = __float2half2_rn(0.0f);
+#pragma unroll
+        for (int u = 0; u < C8_KEYS / (4 * CB_WARPS); ++u) {
+            const int kl = warp * 4 + grp + 4 * CB_WARPS * u, t = c0 + kl;
+            const bool ok = t < T;
+            const uint2 vb = *reinterpret_cast<const uint2 *>(stage + kl * 64 + sub * 8);
+            __half2 v2[4];
+            v2[0] = e4m3x2_to_half2((unsigned short) (vb.x & 0xffffu));
+            v2[1] = e4m3x2_to_half2((unsigned short) (vb.x >> 16));
+            v2[2] = e4m3x2_to_half2((unsigned short) (vb.y & 0xffffu));
+            v2[3] = e4m3x2_to_half2((unsigned short) (vb.y >> 16));
+#pragma unroll
+            for (int qi = 0; qi < NQ; ++qi) {
+                if (NQ > 1 && qi >= nq) break;
+                const __half2 pr = __float2half2_rn(ok ? s_sc[qi * T_pad + t] * inv[qi] : 0.0f);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) a2[qi][j] = __hfma2(pr, v2[j], a2[qi][j]);
+            }
+        }
+#pragma unroll
+        for (int qi = 0; qi < NQ; ++qi) {
+            if (NQ > 1 && qi >= nq) break;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = __half22float2(a2[qi][j]);
+                o[qi][2 * j] = fmaf(f.x, sv, o[qi][2 * j]);
+                o[qi][2 * j + 1] = fmaf(f.y, sv, o[qi][2 * j + 1]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t) __cvta_generic_to_shared(&b_empty[s])) : "memory");
+    }
+#pragma unroll
+    for (int qi = 0; qi < NQ; ++qi) {
+        if (NQ > 1 && qi >= nq) break;          // CTA-uniform
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            o[qi][j] += __shfl_xor_sync(0xffffffffu, o[qi][j], 8);
+            o[qi][j] += __shfl_xor_sync(0xffffffffu, o[qi][j], 16);
+        }
+        if (qi > 0) sync_compute();
+        if (grp == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s_o[warp][sub * 8 + j] = o[qi][j];
+        }
+        sync_compute();
+        if (tid < 64) {
+            float v = s_o[0][tid];
+#pragma unroll
+            for (int i = 1; i < CB_WARPS; ++i) v += s_o[i][tid];
+            out[(size_t) (r0 + qi) * d + h * 64 + tid] = __float2half(v);
+        }
+    }
+}
+
+// 16-bit head-major K/V of one text layer ([window][head][K | V][T][64], the cross-K/V GEMM's output) -> the e4m3 chunk pool.
+// One CTA per chunk of 128 keys: thread = (key, half of the 64 dims); keys past T are written as zeros.
+__global__ void __launch_bounds__(256)
+cross_quant_kernel(const __half * __restrict__ src, uint8_t * __restrict__ dst, int T, int nck, size_t dst_window_bytes) {
+    __shared__ float s_max[8];
+    const int c = blockIdx.x, hk = blockIdx.y, w = blockIdx.z, n_hk = gridDim.y;
+    const int key = threadIdx.x >> 1, half = threadIdx.x & 1, t = c * C8_KEYS + key;
+    float v[32];
+    if (t < T) {
+        const uint4 * p = reinterpret_cast<const uint4 *>(src + (((size_t) w * n_hk + hk) * T + t) * 64 + half * 32);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint4 u = p[i];
+            const __half2 * e = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = __half22float2(e[j]);
+                v[i * 8 + 2 * j] = f.x;
+                v[i * 8 + 2 * j + 1] = f.y;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0.0f;
+    }
+    float m = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) m = fmaxf(m, fabsf(v[i]));
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = m;
+    __syncthreads();
+    m = s_max[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, s_max[i]);
+    const float scale = m > 0.0f ? m * (1.0f / 448.0f) : 1.0f, inv = 1.0f / scale;
+    uint8_t * chunk = dst + (size_t) w * dst_window_bytes + ((size_t) hk * nck + c) * C8_CHUNK;
+    unsigned pk[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        unsigned r = 0;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            unsigned short h2;
+            const float a = v[i * 4 + 2 * j] * inv, b = v[i * 4 + 2 * j + 1] * inv;
+            asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(h2) : "f"(b), "f"(a));      // first source -> upper byte
+            r |= (unsigned) h2 << (16 * j);
+        }
+        pk[i] = r;
+    }
+    uint4 * o = reinterpret_cast<uint4 *>(chunk + key * 64 + half * 32);
+    o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    if (threadIdx.x == 0) *reinterpret_cast<float4 *>(chunk + C8_DATA) = make_float4(scale, 0.0f, 0.0f, 0.0f);
+}
+
 // ---- logit rules + greedy selection ------------------------------------------------------------------------
 struct ArgMax {
     float v;
@@ -991,6 +1259,43 @@ void dec_cross_attn(DType dt, const void * q, const DecRow * d_rows, int R, int 
             launch_pdl(cross_attn_kernel<__nv_bfloat16, false, false>, grid, dim3(128), smem, st,
                        reinterpret_cast<const __nv_bfloat16 *>(q), d, d_rows, d, layer_off_elems, T, kq_scale, n_phantom, 0,
                        reinterpret_cast<__nv_bfloat16 *>(out), qs);
+    WB_CUDA(cudaGetLastError());
+}
+
+size_t cross_fp8_window_bytes(int n_head, int T) { return (size_t) n_head * 2 * ((T + C8_KEYS - 1) / C8_KEYS) * C8_CHUNK; }
+
+void cross_fp8_quantize(const void * kv16, void * dst_layer_win0, int W, int n_head, int T, cudaStream_t st) {
+    if (W <= 0) return;
+    const int nck = (T + C8_KEYS - 1) / C8_KEYS;
+    cross_quant_kernel<<<dim3(nck, 2 * n_head, W), 256, 0, st>>>(reinterpret_cast<const __half *>(kv16), reinterpret_cast<uint8_t *>(dst_layer_win0),
+                                                                 T, nck, cross_fp8_window_bytes(n_head, T));
+    WB_CUDA(cudaGetLastError());
+}
+
+void dec_cross_attn_fp8(const void * q, const DecRow * d_rows, int R, int d, int n_head, size_t layer_off_elems, int T, int n_phantom,
+                        void * out, cudaStream_t st, const int2 * d_groups, int n_groups) {
+    if (R <= 0) return;
+    const float kq_scale = powf(64.0f, -0.25f);
+    const int nq = (d_groups && n_groups > 0) ? CBQ_MAX : 1;
+    const size_t bsmem = (size_t) ((C8_STAGES * C8_CHUNK + 127) & ~127) + (size_t) nq * ((T + 31) & ~31) * sizeof(float);
+    static DeviceOnce set;
+    once_per_device(set, [&] {
+        WB_CUDA(cudaFuncSetAttribute(cross_attn_fp8_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        WB_CUDA(cudaFuncSetAttribute(cross_attn_fp8_kernel<CBQ_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    });
+    if (bsmem > 100 * 1024) {
+        fprintf(stderr, "%s: audio context %d does not fit the e4m3 cross-attention kernel\n", __func__, T);
+        cuda_fail(cudaErrorInvalidValue, "cross_attn_fp8 shared memory", __FILE__, __LINE__);
+        return;
+    }
+    const dim3 g(nq > 1 ? n_groups : R, n_head);
+    const __half * qh = reinterpret_cast<const __half *>(q);
+    if (nq > 1)
+        launch_pdl(cross_attn_fp8_kernel<CBQ_MAX>, g, dim3(CB_THREADS), bsmem, st, qh, d, d_rows, d_groups, d, layer_off_elems, T, kq_scale,
+                   n_phantom, reinterpret_cast<__half *>(out));
+    else
+        launch_pdl(cross_attn_fp8_kernel<1>, g, dim3(CB_THREADS), bsmem, st, qh, d, d_rows, d_groups, d, layer_off_elems, T, kq_scale,
+                   n_phantom, reinterpret_cast<__half *>(out));
     WB_CUDA(cudaGetLastError());
 }
 

@@ -62,6 +62,13 @@ constexpr int DEC_CROSS_GROUP_MAX = 5;
 void dec_cross_attn(DType dt, const void * q, const DecRow * d_rows, int R, int d, int n_head, size_t layer_off_elems,
                     int T, int n_phantom, void * out, cudaStream_t st, const SplitIn * q_split = nullptr,
                     const int2 * d_groups = nullptr, int n_groups = 0);
+// Opt-in e4m3 cross-K/V pool (WHISPER_B200_CROSS_KV=fp8, f16 models only): bytes of one window in one text layer; the 16-bit
+// head-major K/V of W windows of one layer -> the pool (dst = that layer's first window of the batch); the attention over it
+// (layer_off_elems in 2-byte units like everywhere else).
+size_t cross_fp8_window_bytes(int n_head, int T);
+void cross_fp8_quantize(const void * kv16, void * dst_layer_win0, int W, int n_head, int T, cudaStream_t st);
+void dec_cross_attn_fp8(const void * q, const DecRow * d_rows, int R, int d, int n_head, size_t layer_off_elems, int T, int n_phantom,
+                        void * out, cudaStream_t st, const int2 * d_groups, int n_groups);
 // Logit rules + selection for R decoder rows: arg-max rows fill d_out[r] completely; rows with n_draws > 0 fill the timestamp
 // statistics of d_out[r] (tid, pt, ptsum) and d_draws[draw_off .. draw_off + n_draws) from d_uniforms[draw_off ..]
 // (uniforms in [0, 1) drawn by the host from each decoder's mt19937, exactly as std::discrete_distribution consumes them).

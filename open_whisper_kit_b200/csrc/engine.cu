@@ -62,6 +62,16 @@ bool Engine::init(int dev, bool fa) {
         return false;
     }
     ld_logits = round_up(model.hp.n_vocab, 8);
+    if (const char * e = getenv("WHISPER_B200_CROSS_KV")) {
+        if (!strcmp(e, "fp8")) {
+            if (model.dtype == DType::F16) {
+                cross_fp8 = true;
+                wlog(GGML_LOG_LEVEL_WARN, "%s: cross K/V stored as e4m3 (WHISPER_B200_CROSS_KV=fp8): reduced precision, not the reference's F16 cache\n", __func__);
+            } else {
+                wlog(GGML_LOG_LEVEL_WARN, "%s: WHISPER_B200_CROSS_KV=fp8 needs f16 operands; ignored\n", __func__);
+            }
+        }
+    }
     return true;
 }
 
@@ -214,7 +224,9 @@ bool Engine::size_cross(CrossKV & kv, int n_windows, int T) {
     const int d = model.hp.n_audio_state;
     kv.n_windows = n_windows;
     kv.T = T;
-    kv.layer_stride = (size_t) n_windows * T * 2 * d;
+    kv.fp8 = cross_fp8;
+    kv.window_bytes = cross_fp8 ? cross_fp8_window_bytes(model.hp.n_audio_head, T) : (size_t) T * 2 * d * 2;
+    kv.layer_stride = (size_t) n_windows * kv.window_bytes / 2;
     return kv.data.reserve(kv.layer_stride * model.hp.n_text_layer * 2);
 }
 
@@ -356,16 +368,19 @@ bool Engine::encode(const std::vector<EncJob> & jobs, CrossKV & kv, int win0, bo
     gemm_cls = PC_GEMM_CROSS;
 
     // cross K/V for every text layer straight into the pool: K scaled by dh^-0.25 (no bias), V + bias
+    if (kv.fp8 != cross_fp8 || (kv.fp8 && !kv16_tmp.reserve(M * 2 * d * 2))) return false;
     const float kscale = powf(64.0f, -0.25f);
     for (int il = 0; il < hp.n_text_layer; ++il) {
         const DecLayer & L = model.dec[il];
         GemmArgs g;
         g.dtype = dt; g.M = (int) M; g.N = 2 * d; g.K = d; g.a = enc16; g.lda = d; g.w = L.wxkv; g.ldw = d;
         g.bias = L.bxkv; g.scale = kscale; g.scale_cols = d;
-        g.out16 = (char *) kv.data.p + (il * kv.layer_stride + (size_t) win0 * T * 2 * d) * 2;
+        char * pool = (char *) kv.data.p + il * kv.layer_stride * 2 + (size_t) win0 * kv.window_bytes;
+        g.out16 = kv.fp8 ? kv16_tmp.p : pool;
         g.ldo16 = 2 * d;
         g.head_major_T = T;       // [window][head][K|V][T][64]: the decoder streams one (window, head) block per CTA
         gemm(g);
+        if (kv.fp8) cross_fp8_quantize(kv16_tmp.p, pool, W, H, T, stream);
     }
     WB_CUDA(cudaStreamSynchronize(stream));
     if (!ok) wlog(GGML_LOG_LEVEL_ERROR, "%s: GEMM launch rejected its arguments\n", __func__);
@@ -464,7 +479,7 @@ bool Engine::decode(const std::vector<DecRow> & rows, const std::vector<int> & l
     bool fuse_append = true;
     for (int i = 1; i < R && fuse_append; ++i)
         if (rows[i].self_kv == rows[i - 1].self_kv) fuse_append = false;
-    if (fuse_append && !align.on && chain_usable(R)) return decode_chain(rows, logit_rows, cross_layer_stride);
+    if (fuse_append && !align.on && !cross_fp8 && chain_usable(R)) return decode_chain(rows, logit_rows, cross_layer_stride);
     if (align.on) {
         if (align.n_heads_total <= 0 || !align.probs.reserve((size_t) align.n_heads_total * R * cross_T * sizeof(float))) return false;
     }
@@ -531,8 +546,11 @@ bool Engine::decode(const std::vector<DecRow> & rows, const std::vector<int> & l
                               il * cross_layer_stride, cross_T, a0, (float *) align.probs.p, stream);
             n_kernel_launches += 1;
         }
-        prof_begin(PC_CROSS_ATTN, (double) R * cross_T * 2.0 * d * 2.0);
-        dec_cross_attn(dt, q16, d_rows, R, d, H, il * cross_layer_stride, cross_T, n_phantom(cross_T), att, stream, nullptr, d_groups, n_groups);
+        prof_begin(PC_CROSS_ATTN, cross_fp8 ? (double) R * cross_fp8_window_bytes(H, cross_T) : (double) R * cross_T * 2.0 * d * 2.0);
+        if (cross_fp8)
+            dec_cross_attn_fp8(q16, d_rows, R, d, H, il * cross_layer_stride, cross_T, n_phantom(cross_T), att, stream, d_groups, n_groups);
+        else
+            dec_cross_attn(dt, q16, d_rows, R, d, H, il * cross_layer_stride, cross_T, n_phantom(cross_T), att, stream, nullptr, d_groups, n_groups);
         prof_end();
         n_kernel_launches += 1;
         {

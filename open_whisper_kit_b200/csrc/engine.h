@@ -47,12 +47,18 @@ struct MelBuf {
 
 // Cross-attention K/V of a set of windows: [n_text_layer][n_windows][n_head][K | V][T][64], 16-bit.
 // T = audio context of the encoder run that filled it (1500, or whisper_full_params::audio_ctx).
+// With Engine::cross_fp8 the pool holds e4m3 chunks instead (dec_kernels.cu, cross_attn_fp8_kernel): same nesting, window_bytes
+// per (layer, window); layer_stride stays in 2-byte units either way.
 struct CrossKV {
     DeviceBlock data;
     int n_windows = 0;
     int T = 1500;
-    size_t layer_stride = 0;   // elements
-    const void * window_base(int w, int d) const { return (const char *) data.p + (size_t) w * T * 2 * d * 2; }
+    size_t layer_stride = 0;   // elements (2-byte units)
+    size_t window_bytes = 0;   // one window in one text layer
+    bool fp8 = false;
+    const void * window_base(int w, int d) const {
+        return (const char *) data.p + (size_t) w * (window_bytes ? window_bytes : (size_t) T * 2 * d * 2);
+    }
 };
 
 struct MelJob {
@@ -122,6 +128,10 @@ struct Engine {
     // (src/whisper.cpp:2055, 2481)
     int n_phantom(int T = 1500) const { return flash_attn ? (T + 255) / 256 * 256 - T : 0; }
     int cross_T = 1500;        // audio context of the cross K/V the next decode() call reads (set by the caller)
+    // WHISPER_B200_CROSS_KV=fp8 (f16 models, no DTW): cross K/V stored as e4m3 chunks -- half the bytes of the stream that bounds
+    // the decoder step, at reduced precision (NOT the reference's arithmetic; off by default)
+    bool cross_fp8 = false;
+    DeviceBlock kv16_tmp;      // 16-bit K/V of one text layer of an encoder chunk, the quantiser's input
 
     // DTW token timestamps: when `on`, the next decode() also writes the cross-attention probabilities of the alignment heads
     // (heads_by_layer, capture order = layer, then list order) for every row to `probs` [n_heads_total][rows][cross_T]

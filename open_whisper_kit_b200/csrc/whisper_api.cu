@@ -58,6 +58,10 @@ whisper_context * init_with_loader(whisper_model_loader * loader, whisper_contex
             return nullptr;
         }
         ctx->t_load_us = time_us() - t0;
+        if (params.dtw_token_timestamps && ctx->eng.cross_fp8) {
+            wlog(GGML_LOG_LEVEL_WARN, "%s: dtw_token_timestamps reads the 16-bit cross K/V - WHISPER_B200_CROSS_KV=fp8 ignored for this context\n", __func__);
+            ctx->eng.cross_fp8 = false;
+        }
         if (params.dtw_token_timestamps) {
             // alignment heads (src/whisper.cpp:1160-1272): an invalid selection fails the initialisation, as aheads_masks_init does
             auto & al = ctx->eng.align;
@@ -937,6 +941,31 @@ WB200_API int whisper_b200_get_cross_kv(struct whisper_context * ctx, int layer,
     std::lock_guard<std::recursive_mutex> lock(ctx->eng.mu);
     cudaSetDevice(ctx->eng.device);
     const char * src = (const char *) ctx->state->cross.data.p + (size_t) layer * ctx->state->cross.layer_stride * 2;
+    if (ctx->state->cross.fp8) {
+        // e4m3 pool (opt-in): expand the chunks [128 keys][64] + f32 scale back to 16 bits in the same [T][K | V] order
+        const size_t bytes = ctx->state->cross.window_bytes;
+        std::vector<uint8_t> raw(bytes);
+        if (cudaMemcpy(raw.data(), src, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return -3;
+        const int nck = (T + 127) / 128;
+        const size_t chunk = 128 * 64 + 16;
+        auto e4m3 = [](uint8_t b) {
+            const int e = (b >> 3) & 15, m = b & 7;
+            const float v = e == 0 ? ldexpf((float) m, -9) : ldexpf(1.0f + m / 8.0f, e - 7);
+            return (b & 0x80) ? -v : v;
+        };
+        for (int h = 0; h < d / 64; ++h)
+            for (int kv = 0; kv < 2; ++kv)
+                for (int t = 0; t < T; ++t) {
+                    const uint8_t * ck = raw.data() + ((size_t) (h * 2 + kv) * nck + t / 128) * chunk;
+                    float sc;
+                    memcpy(&sc, ck + 128 * 64, 4);
+                    for (int j = 0; j < 64; ++j) {
+                        const __half hv = __float2half(e4m3(ck[(t % 128) * 64 + j]) * sc);
+                        memcpy(out + (size_t) t * 2 * d + kv * d + h * 64 + j, &hv, 2);
+                    }
+                }
+        return 0;
+    }
     // the pool keeps a window as [head][K | V][T][64]; hand it out in the reference's [T][K(d) | V(d)] order
     std::vector<uint16_t> hm((size_t) want);
     if (cudaMemcpy(hm.data(), src, (size_t) want * 2, cudaMemcpyDeviceToHost) != cudaSuccess) return -3;
