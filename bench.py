@@ -434,9 +434,10 @@ def main_transcribe(args):
                 for _ in range(2):
                     step8()
                 ms8 = timed(step8, max(1, args.steps)) / max(1, args.steps)
-                same = segment_tokens(lib, ctx8) == segment_tokens(lib, ctx)
+                t8, t16 = segment_tokens(lib, ctx8), segment_tokens(lib, ctx)
                 fp8_line = {"value": audio_s / (ms8 * 1e-3), "unit": "audio-s/s", "ms_per_step": ms8,
-                            "tokens_identical_to_f16_pool_run": bool(same),
+                            "segments_identical_to_f16_pool_run": f"{sum(a == b for a, b in zip(t8, t16))} of {len(t16)} "
+                                                                  "(220 tokens each; a near-tie flip changes the rest of a window)",
                             "note": "WHISPER_B200_CROSS_KV=fp8: cross K/V stored as e4m3 chunks with per-chunk scales; NOT the reference's "
                                     "F16 cache, off by default; parity study: tests/test_gpu_cross_fp8.py"}
                 lib.whisper_free(ctx8)
