@@ -280,7 +280,7 @@ __device__ __forceinline__ void cb_wait(uint64_t * bar, uint32_t parity) {      
 template <typename T16, int NQ>
 __global__ void __launch_bounds__(CB_THREADS, 2)
 cross_attn_bulk_kernel(const T16 * __restrict__ q, int ldq, const DecRow * __restrict__ rows, const int2 * __restrict__ groups, int d,
-                       size_t layer_off, int T, float kq_scale, int n_phantom, T16 * __restrict__ out) {
+                       size_t layer_off, int T, float kq_scale, int n_phantom, T16 * __restrict__ out, int evict_first) {
     extern __shared__ __align__(128) uint8_t cb_smem[];         // ring [CB_STAGES][CB_CHUNK] | scores [NQ][T_pad] f32
     __shared__ __align__(8) uint64_t b_full[CB_STAGES], b_empty[CB_STAGES];
     __shared__ float s_red[NQ][2 * CB_WARPS];
@@ -308,16 +308,26 @@ cross_attn_bulk_kernel(const T16 * __restrict__ q, int ldq, const DecRow * __res
             const DecRow row = rows[r0];
             const uint8_t * blk = reinterpret_cast<const uint8_t *>(reinterpret_cast<const T16 *>(row.cross_kv) + layer_off +
                                                                     (size_t) h * 2 * T * 64);
+            // the stream is read once: evict-first, so that it displaces neither itself nor the K prefixes of the CTAs that have
+            // not started yet (requested into L2 by the GEMMs before this launch, tc_skinny.cu)
+            uint64_t pol;
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
             for (int c = 0; c < 2 * nck; ++c) {
                 const int s = c % CB_STAGES, sweep = c / nck, j = c - sweep * nck;
                 if (c >= CB_STAGES) cb_wait(&b_empty[s], ((c / CB_STAGES) - 1) & 1);
                 const uint32_t bytes = (uint32_t) (min(CB_KEYS, T - j * CB_KEYS) * 128);
                 const uint32_t bar = (uint32_t) __cvta_generic_to_shared(&b_full[s]);
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                                 (uint32_t) __cvta_generic_to_shared(cb_smem + s * CB_CHUNK)),
-                             "l"(blk + (size_t) sweep * T * 128 + (size_t) j * CB_CHUNK), "r"(bytes), "r"(bar)
-                             : "memory");
+                if (evict_first)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                                     (uint32_t) __cvta_generic_to_shared(cb_smem + s * CB_CHUNK)),
+                                 "l"(blk + (size_t) sweep * T * 128 + (size_t) j * CB_CHUNK), "r"(bytes), "r"(bar), "l"(pol)
+                                 : "memory");
+                else
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                     (uint32_t) __cvta_generic_to_shared(cb_smem + s * CB_CHUNK)),
+                                 "l"(blk + (size_t) sweep * T * 128 + (size_t) j * CB_CHUNK), "r"(bytes), "r"(bar)
+                                 : "memory");
                 if (c == nck) pdl_trigger();        // with the compute warps' trigger after the K sweep: let the successor in
             }
         }
@@ -1221,23 +1231,24 @@ void dec_cross_attn(DType dt, const void * q, const DecRow * d_rows, int R, int 
             WB_CUDA(cudaFuncSetAttribute(cross_attn_bulk_kernel<__nv_bfloat16, CBQ_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         });
         if (bsmem <= 100 * 1024) {
+            static const int evict_first = !(getenv("WHISPER_B200_CROSS_EVICT") && atoi(getenv("WHISPER_B200_CROSS_EVICT")) == 0);
             const dim3 g(nq > 1 ? n_groups : R, n_head);
             const __half * qh = reinterpret_cast<const __half *>(q);
             const __nv_bfloat16 * qb = reinterpret_cast<const __nv_bfloat16 *>(q);
             if (dt == DType::F16) {
                 if (nq > 1)
                     launch_pdl(cross_attn_bulk_kernel<__half, CBQ_MAX>, g, dim3(CB_THREADS), bsmem, st, qh, d, d_rows, d_groups, d, layer_off_elems,
-                               T, kq_scale, n_phantom, reinterpret_cast<__half *>(out));
+                               T, kq_scale, n_phantom, reinterpret_cast<__half *>(out), evict_first);
                 else
                     launch_pdl(cross_attn_bulk_kernel<__half, 1>, g, dim3(CB_THREADS), bsmem, st, qh, d, d_rows, d_groups, d, layer_off_elems, T,
-                               kq_scale, n_phantom, reinterpret_cast<__half *>(out));
+                               kq_scale, n_phantom, reinterpret_cast<__half *>(out), evict_first);
             } else {
                 if (nq > 1)
                     launch_pdl(cross_attn_bulk_kernel<__nv_bfloat16, CBQ_MAX>, g, dim3(CB_THREADS), bsmem, st, qb, d, d_rows, d_groups, d,
-                               layer_off_elems, T, kq_scale, n_phantom, reinterpret_cast<__nv_bfloat16 *>(out));
+                               layer_off_elems, T, kq_scale, n_phantom, reinterpret_cast<__nv_bfloat16 *>(out), evict_first);
                 else
                     launch_pdl(cross_attn_bulk_kernel<__nv_bfloat16, 1>, g, dim3(CB_THREADS), bsmem, st, qb, d, d_rows, d_groups, d, layer_off_elems,
-                               T, kq_scale, n_phantom, reinterpret_cast<__nv_bfloat16 *>(out));
+                               T, kq_scale, n_phantom, reinterpret_cast<__nv_bfloat16 *>(out), evict_first);
             }
             WB_CUDA(cudaGetLastError());
             return;

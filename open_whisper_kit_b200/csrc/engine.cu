@@ -443,8 +443,8 @@ bool Engine::decode(const std::vector<DecRow> & rows, const std::vector<int> & l
         // few rows: stream the weights with every SM -- tcgen05 version (tc_skinny.cu) unless WHISPER_B200_TC_SKINNY=0, else
         // the mma.sync one (skinny_gemm.cu); many rows (long prompts): tensor-core tiles (tc_gemm.cu)
         static const bool tcs = !(getenv("WHISPER_B200_TC_SKINNY") && atoi(getenv("WHISPER_B200_TC_SKINNY")) == 0);
-        if (g.ln_x || g.ln_part_out) {
-            ok = ok && tc_skinny_usable(g) && tc_skinny_gemm(g, stream);       // LayerNorm-fused forms exist on this kernel only
+        if (g.ln_part_in || g.ln_part_out) {
+            ok = ok && tc_skinny_usable(g) && tc_skinny_gemm(g, stream);       // LayerNorm-folded forms exist on this kernel only
         } else if (g.M <= 128) {
             ok = ok && (tcs && tc_skinny_usable(g) ? tc_skinny_gemm(g, stream) : skinny_gemm(g, skinny_ws, stream));
         } else if (g.M <= 512 && tcs && !g.pos) {
@@ -483,19 +483,29 @@ bool Engine::decode(const std::vector<DecRow> & rows, const std::vector<int> & l
     if (align.on) {
         if (align.n_heads_total <= 0 || !align.probs.reserve((size_t) align.n_heads_total * R * cross_T * sizeof(float))) return false;
     }
-    // Single-token step with at most 64 rows, OPT-IN (WHISPER_B200_LN_FUSE=1): the three LayerNorms of a layer folded into their
-    // neighbours -- the GEMM that produces the residual stream (O, cross-O, MLP-down) also emits per-tile row statistics, and the
-    // GEMM that consumes the normalised rows (QKV, cross-Q, MLP-up) builds its A operand from the f32 stream itself
-    // (tc_skinny.cu).  Removes three dependent launches per layer, but measured SLOWER than the separate kernels on B200
-    // (large-v3, 64 rows: 1255-1280 ms against 1225 ms per 64-window step): the LayerNorm kernel costs 1.65 us + a 1.3 us
-    // programmatic hand-over, while building the tile in the consumer puts ~3.5 us (L2 round trip for f32 rows instead of a TMA
-    // of 16-bit rows, statistics, normalise, two barriers) on ITS critical path.  Kept as a tested experiment, off by default.
-    static const bool ln_fuse_env = getenv("WHISPER_B200_LN_FUSE") && atoi(getenv("WHISPER_B200_LN_FUSE")) != 0;
+    // At most 128 rows (every GEMM of the step runs on the weight-streaming kernel): the three LayerNorms of a layer are folded
+    // algebraically into their neighbours (tc_skinny.cu) -- the GEMM that produces the residual stream (O, cross-O, MLP-down) also
+    // writes the 16-bit rows x * gamma of the NEXT LayerNorm and per-tile row statistics; the GEMM that consumes the normalised
+    // rows (QKV, cross-Q, MLP-up) streams those rows as an ordinary A operand and applies mean / rstd in its epilogue with the
+    // per-column sums prepared at model load (model.cu: ln_fold).  Removes three dependent launches per layer with nothing added
+    // to a critical path.  WHISPER_B200_LN_FOLD=0 keeps the separate LayerNorm kernels (the rounding points of the reference).
+    static const bool ln_fold_env = !(getenv("WHISPER_B200_LN_FOLD") && atoi(getenv("WHISPER_B200_LN_FOLD")) == 0);
     static const bool tcs_env = !(getenv("WHISPER_B200_TC_SKINNY") && atoi(getenv("WHISPER_B200_TC_SKINNY")) == 0);
-    const bool fuse_ln = ln_fuse_env && tcs_env && fuse_append && R <= 64 && d % 64 == 0;
-    auto ln_consumer = [&](GemmArgs & g, const float * gw, const float * gb) {      // A operand = LayerNorm(x) with (gw, gb)
-        g.a = nullptr; g.lda = 0;
-        g.ln_x = x; g.ld_lnx = d; g.ln_part_in = ln_part; g.ln_gamma = gw; g.ln_beta = gb; g.ln_eps = hp.eps;
+    const bool fold = ln_fold_env && tcs_env && !exact_ln && R <= 128 && d % 64 == 0;
+    auto ln_consumer = [&](GemmArgs & g, const float * colsum, const float * bias_folded) {      // A operand = x * gamma rows in h16
+        g.ln_part_in = ln_part; g.ln_parts = d / 64; g.ln_colsum = colsum; g.bias = bias_folded; g.ln_eps = hp.eps;
+    };
+    auto ln_producer = [&](GemmArgs & g, const float * gamma_next) {
+        g.ln_part_out = ln_part; g.out16 = h16; g.ldo16 = d; g.out16_gamma = gamma_next;
+    };
+    // L2 prefetch of the coming cross-attention's K prefix by the six GEMMs that run between two cross-attention launches
+    // (tc_skinny.cu): slots 0-2 = cross-O, MLP up, MLP down of the previous layer, 3-5 = QKV, O, cross-Q of the layer itself
+    static const int pf_chunks_env = getenv("WHISPER_B200_CROSS_PF_CHUNKS") ? atoi(getenv("WHISPER_B200_CROSS_PF_CHUNKS")) : 4;
+    const int pf_chunks = (tcs_env && !cross_fp8 && R <= 64 && !align.on) ? std::min(pf_chunks_env, cross_T * 128 / 16384) : 0;
+    auto prefetch = [&](GemmArgs & g, int layer, int slot) {
+        if (pf_chunks <= 0 || layer >= hp.n_text_layer) return;
+        g.pf_rows = d_rows; g.pf_R = R; g.pf_H = H; g.pf_chunks = pf_chunks; g.pf_slot = slot; g.pf_slots = 6;
+        g.pf_layer_off_bytes = (size_t) layer * cross_layer_stride * 2; g.pf_head_bytes = 2 * cross_T * 64 * 2;
     };
 
     prof_begin(PC_DEC_MISC, (double) R * d * 10.0);
@@ -504,12 +514,13 @@ bool Engine::decode(const std::vector<DecRow> & rows, const std::vector<int> & l
     n_kernel_launches += 1;
     for (int il = 0; il < hp.n_text_layer; ++il) {
         const DecLayer & L = model.dec[il];
-        if (!fuse_ln || il == 0) ln(L.ln1_w, L.ln1_b);
+        if (!fold || il == 0) ln(L.ln1_w, L.ln1_b);
         {
             GemmArgs g;   // Q and K carry dh^-0.25 each (src/whisper.cpp:2506, 2550, 2557); V is biased only
             g.dtype = dt; g.M = R; g.N = 3 * d; g.K = d; g.a = h16; g.lda = d; g.w = L.wqkv; g.ldw = d;
             g.bias = L.bqkv; g.scale = qk_scale; g.scale_cols = 2 * d; g.out16 = qkv; g.ldo16 = 3 * d;
-            if (fuse_ln && il > 0) ln_consumer(g, L.ln1_w, L.ln1_b);
+            if (fold && il > 0) ln_consumer(g, L.qkv_c, L.qkv_b);
+            prefetch(g, il, 3);
             gemm(g);
         }
         if (!fuse_append) {
@@ -528,15 +539,17 @@ bool Engine::decode(const std::vector<DecRow> & rows, const std::vector<int> & l
             GemmArgs g;
             g.dtype = dt; g.M = R; g.N = d; g.K = d; g.a = att; g.lda = d; g.w = L.wo; g.ldw = d;
             g.bias = L.bo; g.resid = x; g.ldr = d; g.out32 = x; g.ldo32 = d;
-            if (fuse_ln) g.ln_part_out = ln_part;
+            if (fold) ln_producer(g, L.lnx_w);
+            prefetch(g, il, 4);
             gemm(g);
         }
-        if (!fuse_ln) ln(L.lnx_w, L.lnx_b);
+        if (!fold) ln(L.lnx_w, L.lnx_b);
         {
             GemmArgs g;
             g.dtype = dt; g.M = R; g.N = d; g.K = d; g.a = h16; g.lda = d; g.w = L.wxq; g.ldw = d;
             g.bias = L.bxq; g.out16 = q16; g.ldo16 = d;
-            if (fuse_ln) ln_consumer(g, L.lnx_w, L.lnx_b);
+            if (fold) ln_consumer(g, L.xq_c, L.xq_b);
+            prefetch(g, il, 5);
             gemm(g);
         }
         if (align.on && !align.heads_by_layer[il].empty()) {
@@ -557,22 +570,25 @@ bool Engine::decode(const std::vector<DecRow> & rows, const std::vector<int> & l
             GemmArgs g;
             g.dtype = dt; g.M = R; g.N = d; g.K = d; g.a = att; g.lda = d; g.w = L.wxo; g.ldw = d;
             g.bias = L.bxo; g.resid = x; g.ldr = d; g.out32 = x; g.ldo32 = d;
-            if (fuse_ln) g.ln_part_out = ln_part;
+            if (fold) ln_producer(g, L.ln2_w);
+            prefetch(g, il + 1, 0);
             gemm(g);
         }
-        if (!fuse_ln) ln(L.ln2_w, L.ln2_b);
+        if (!fold) ln(L.ln2_w, L.ln2_b);
         {
             GemmArgs g;
             g.dtype = dt; g.M = R; g.N = 4 * d; g.K = d; g.a = h16; g.lda = d; g.w = L.w1; g.ldw = d;
             g.bias = L.b1; g.gelu = true; g.out16 = mlp; g.ldo16 = 4 * d;
-            if (fuse_ln) ln_consumer(g, L.ln2_w, L.ln2_b);
+            if (fold) ln_consumer(g, L.m1_c, L.m1_b);
+            prefetch(g, il + 1, 1);
             gemm(g);
         }
         {
             GemmArgs g;
             g.dtype = dt; g.M = R; g.N = d; g.K = 4 * d; g.a = mlp; g.lda = 4 * d; g.w = L.w2; g.ldw = 4 * d;
             g.bias = L.b2; g.resid = x; g.ldr = d; g.out32 = x; g.ldo32 = d;
-            if (fuse_ln && il + 1 < hp.n_text_layer) g.ln_part_out = ln_part;
+            if (fold && il + 1 < hp.n_text_layer) ln_producer(g, model.dec[il + 1].ln1_w);
+            prefetch(g, il + 1, 2);
             gemm(g);
         }
     }

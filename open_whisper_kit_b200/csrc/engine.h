@@ -135,6 +135,9 @@ struct Engine {
 
     // DTW token timestamps: when `on`, the next decode() also writes the cross-attention probabilities of the alignment heads
     // (heads_by_layer, capture order = layer, then list order) for every row to `probs` [n_heads_total][rows][cross_T]
+    // set for the duration of a whisper_full* call that asks for token-level timestamps: decode() keeps the separate LayerNorm
+    // kernels (the reference's rounding points) instead of the algebraic fold
+    bool exact_ln = false;
     struct AlignCapture {
         bool on = false;
         std::vector<std::vector<int>> heads_by_layer;

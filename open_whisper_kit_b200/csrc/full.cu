@@ -751,14 +751,20 @@ int run_streams(whisper_context & ctx, std::vector<StreamSpec> & specs) {
         sp.rc = 0;
     }
     e.in_full = true;
+    // Token-level timestamps threshold the token probabilities (src/whisper.cpp:8455-8660): a call that asks for them keeps the
+    // reference's rounding points (separate LayerNorm kernels) instead of the algebraic LayerNorm fold of the decoder step
+    e.exact_ln = false;
+    for (const auto & sp : specs) e.exact_ln = e.exact_ln || sp.params.token_timestamps;
     int rc = -6;
     try {
         rc = run_streams_locked(ctx, specs);
     } catch (...) {
         e.in_full = false;
+        e.exact_ln = false;
         throw;
     }
     e.in_full = false;
+    e.exact_ln = false;
     bool any = false;
     for (const auto & sp : specs) any = any || sp.rc != 0;
     if (rc != 0 && !any)                        // a call-wide failure (allocation, mixed audio_ctx): every stream failed with it

@@ -183,31 +183,53 @@ WB200_API int whisper_b200_kernel_tc_skinny_gemm(int dtype, int M, int N, int K,
     return gemm_hook(2, dtype, M, N, K, a, w, bias, scale, scale_cols, gelu, nullptr, 0, resid, out16, out32);
 }
 
-// Two decoder-step GEMMs with the LayerNorm between them folded in (tc_skinny.cu): x = a1 * w1^T + bias1 + resid (also emits the
-// per-tile row statistics), y = LayerNorm(x; gamma, beta) * w2^T.  M <= 64, d and K1 multiples of 64.
+// Two decoder-step GEMMs with the LayerNorm between them folded in algebraically (tc_skinny.cu): x = a1 * w1^T + bias1 + resid
+// (also emits the 16-bit rows x * gamma and the per-tile row statistics), y = LayerNorm(x; gamma, beta) * w2^T + bias2 computed as
+// rstd * ((x * gamma) w2^T - mean * c) + b'.  M <= 128, d and K1 multiples of 64.
 WB200_API int whisper_b200_kernel_ln_gemm_pair(int dtype, int M, int d, int K1, int N2, const uint16_t * a1, const uint16_t * w1,
                                                const float * bias1, const float * resid, const float * gamma, const float * beta,
                                                float eps, const uint16_t * w2, float * x_out, float * y_out) {
     if (!a1 || !w1 || !resid || !gamma || !beta || !w2 || !x_out || !y_out) return -1;
     cuda_clear_failure();
     const int ld2 = round_up(N2, 8);
+    // the fold vectors, as model.cu prepares them at load (double accumulation over the 16-bit weights)
+    std::vector<float> c(N2), bf(N2);
+    for (int n = 0; n < N2; ++n) {
+        double cs = 0.0, bs = 0.0;
+        for (int k = 0; k < d; ++k) {
+            float wv;
+            if (dtype == 1) {
+                const unsigned u = (unsigned) w2[(size_t) n * d + k] << 16;
+                memcpy(&wv, &u, 4);
+            } else {
+                __half hh;
+                memcpy(&hh, &w2[(size_t) n * d + k], 2);
+                wv = __half2float(hh);
+            }
+            cs += (double) wv * gamma[k];
+            bs += (double) wv * beta[k];
+        }
+        c[n] = (float) cs;
+        bf[n] = (float) bs;
+    }
     DevBuf d_a((size_t) M * K1 * 2), d_w1((size_t) d * K1 * 2), d_b((size_t) d * 4), d_x((size_t) M * d * 4), d_g((size_t) d * 4),
-        d_be((size_t) d * 4), d_w2((size_t) N2 * d * 2), d_y((size_t) M * ld2 * 4), d_part((size_t) (d / 64 + 1) * M * sizeof(float2));
+        d_h((size_t) M * d * 2), d_w2((size_t) N2 * d * 2), d_y((size_t) M * ld2 * 4), d_part((size_t) (d / 64 + 1) * M * sizeof(float2)),
+        d_c((size_t) ld2 * 4), d_bf((size_t) ld2 * 4);
     WB_CUDA(cudaMemcpy(d_a.p, a1, (size_t) M * K1 * 2, cudaMemcpyHostToDevice));
     WB_CUDA(cudaMemcpy(d_w1.p, w1, (size_t) d * K1 * 2, cudaMemcpyHostToDevice));
     if (bias1) WB_CUDA(cudaMemcpy(d_b.p, bias1, (size_t) d * 4, cudaMemcpyHostToDevice));
     WB_CUDA(cudaMemcpy(d_x.p, resid, (size_t) M * d * 4, cudaMemcpyHostToDevice));
     WB_CUDA(cudaMemcpy(d_g.p, gamma, (size_t) d * 4, cudaMemcpyHostToDevice));
-    WB_CUDA(cudaMemcpy(d_be.p, beta, (size_t) d * 4, cudaMemcpyHostToDevice));
     WB_CUDA(cudaMemcpy(d_w2.p, w2, (size_t) N2 * d * 2, cudaMemcpyHostToDevice));
+    WB_CUDA(cudaMemcpy(d_c.p, c.data(), (size_t) N2 * 4, cudaMemcpyHostToDevice));
+    WB_CUDA(cudaMemcpy(d_bf.p, bf.data(), (size_t) N2 * 4, cudaMemcpyHostToDevice));
     GemmArgs g1;
     g1.dtype = dtype == 1 ? DType::BF16 : DType::F16; g1.M = M; g1.N = d; g1.K = K1; g1.a = d_a.p; g1.lda = K1; g1.w = d_w1.p; g1.ldw = K1;
     g1.bias = bias1 ? d_b.as<float>() : nullptr; g1.resid = d_x.as<float>(); g1.ldr = d; g1.out32 = d_x.as<float>(); g1.ldo32 = d;
-    g1.ln_part_out = d_part.as<float2>();
+    g1.ln_part_out = d_part.as<float2>(); g1.out16 = d_h.p; g1.ldo16 = d; g1.out16_gamma = d_g.as<float>();
     GemmArgs g2;
-    g2.dtype = g1.dtype; g2.M = M; g2.N = N2; g2.K = d; g2.w = d_w2.p; g2.ldw = d; g2.out32 = d_y.as<float>(); g2.ldo32 = ld2;
-    g2.ln_x = d_x.as<float>(); g2.ld_lnx = d; g2.ln_part_in = d_part.as<float2>(); g2.ln_gamma = d_g.as<float>(); g2.ln_beta = d_be.as<float>();
-    g2.ln_eps = eps;
+    g2.dtype = g1.dtype; g2.M = M; g2.N = N2; g2.K = d; g2.a = d_h.p; g2.lda = d; g2.w = d_w2.p; g2.ldw = d; g2.out32 = d_y.as<float>(); g2.ldo32 = ld2;
+    g2.ln_part_in = d_part.as<float2>(); g2.ln_parts = d / 64; g2.ln_colsum = d_c.as<float>(); g2.bias = d_bf.as<float>(); g2.ln_eps = eps;
     if (!tc_skinny_usable(g1) || !tc_skinny_usable(g2)) return -2;
     if (!tc_skinny_gemm(g1, 0) || !tc_skinny_gemm(g2, 0)) return -3;
     WB_CUDA(cudaDeviceSynchronize());

@@ -138,6 +138,29 @@ struct HostTensor {
     size_t nelem() const { return (size_t) ne[0] * ne[1] * ne[2] * ne[3]; }
 };
 
+// c[n] = sum_k gamma[k] W[n][k], b'[n] = bias[n] + sum_k beta[k] W[n][k] from the 16-bit weights as the GEMM sees them: one warp
+// per output column, double accumulation (runs once per model load).
+template <typename T16>
+__global__ void ln_fold_kernel(const T16 * __restrict__ w, const float * __restrict__ gamma, const float * __restrict__ beta,
+                               const float * __restrict__ bias, int N, int K, float * __restrict__ c_out, float * __restrict__ b_out) {
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (n >= N) return;
+    double c = 0.0, b = 0.0;
+    for (int k = lane; k < K; k += 32) {
+        const double wv = (double) Half16<T16>::to_f(w[(size_t) n * K + k]);
+        c += wv * (double) gamma[k];
+        b += wv * (double) beta[k];
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (lane == 0) {
+        c_out[n] = (float) c;
+        b_out[n] = (float) (b + (bias ? (double) bias[n] : 0.0));
+    }
+}
+
 struct Uploader {
     Model & m;
     void * d_tmp = nullptr;
@@ -188,6 +211,15 @@ struct Uploader {
         }
         WB_CUDA(cudaGetLastError());
         WB_CUDA(cudaDeviceSynchronize());
+    }
+    void ln_fold(const void * w, const float * gamma, const float * beta, const float * bias, int N, int K, float *& c, float *& b) {
+        c = (float *) dalloc((size_t) N * 4);
+        b = (float *) dalloc((size_t) N * 4);
+        if (!w || !gamma || !beta || !c || !b) return;
+        const unsigned bl = (unsigned) ceil_div(N, 8);
+        if (m.dtype == DType::F16) ln_fold_kernel<__half><<<bl, 256>>>((const __half *) w, gamma, beta, bias, N, K, c, b);
+        else ln_fold_kernel<__nv_bfloat16><<<bl, 256>>>((const __nv_bfloat16 *) w, gamma, beta, bias, N, K, c, b);
+        WB_CUDA(cudaGetLastError());
     }
     void put_conv(const HostTensor * t, void * dst, int n_out, int n_in, int kpad) {
         if (!t) return;
@@ -732,6 +764,9 @@ bool model_load(whisper_model_loader * loader, Model & m, DType dtype, int devic
         L.b1 = f32(p + ".mlp.0.bias", 4 * (size_t) d);
         L.w2 = w16(p + ".mlp.2.weight", d, 4 * d);
         L.b2 = f32(p + ".mlp.2.bias", d);
+        up.ln_fold(L.wqkv, L.ln1_w, L.ln1_b, L.bqkv, 3 * d, d, L.qkv_c, L.qkv_b);
+        up.ln_fold(L.wxq, L.lnx_w, L.lnx_b, L.bxq, d, d, L.xq_c, L.xq_b);
+        up.ln_fold(L.w1, L.ln2_w, L.ln2_b, L.b1, 4 * d, d, L.m1_c, L.m1_b);
     }
     WB_CUDA(cudaDeviceSynchronize());
     if (!up.ok || cuda_failed()) {

@@ -51,6 +51,10 @@ struct DecLayer {
     float *ln2_w, *ln2_b;
     void * w1;    float * b1;
     void * w2;    float * b2;
+    // LayerNorm folded into the GEMM that consumes it (tc_skinny.cu): c[n] = sum_k gamma[k] W[n][k], b'[n] = b[n] + sum_k beta[k] W[n][k]
+    float *qkv_c, *qkv_b;           // ln1 into wqkv
+    float *xq_c, *xq_b;             // lnx into wxq
+    float *m1_c, *m1_b;             // ln2 into w1
 };
 
 struct Model {

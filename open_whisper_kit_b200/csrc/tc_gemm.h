@@ -28,17 +28,25 @@ struct GemmArgs {
     // attention kernel's V^T scratch vt[(w * vt_H + head) * 80 + c][vt_TP] at key position t (row = w * vt_T + t): the
     // per-layer transpose kernel disappears.  The 32 rows of a warp are 32 consecutive keys = one 64-byte segment per column.
     void * vt = nullptr; int vt_col0 = 0, vt_T = 0, vt_TP = 0, vt_H = 0;
-    // ---- LayerNorm folded into the decoder-step GEMMs (tc_skinny only; see tc_skinny.cu) ----
-    // producer side: besides out32 (the new residual stream) the epilogue writes, per 64-column tile and row, the tile's mean
-    // and centred sum of squares of out32 -> ln_part_out[tile * M + row]
+    // ---- LayerNorm folded algebraically into the decoder-step GEMMs (tc_skinny only; see tc_skinny.cu) ----
+    //   LN(x) W^T + b = rstd * ((x * gamma) W^T - mean * c) + b',  c[n] = sum_k gamma[k] W[n][k],  b'[n] = b[n] + sum_k beta[k] W[n][k]
+    // producer side (the GEMM that writes the residual stream out32): per 64-column tile and row, the tile's mean and centred sum
+    // of squares of out32 -> ln_part_out[tile * M + row]; out16 = 16-bit(out32 * out16_gamma[n]) (the next LayerNorm's gamma)
     float2 * ln_part_out = nullptr;
-    // consumer side: a == nullptr; the A operand is LayerNorm(ln_x) built by the kernel itself from the f32 rows ln_x[M][ld_lnx]
-    // and the n = K / 64 partial statistics per row that the producer left in ln_part_in (combined with Chan's formula)
-    const float * ln_x = nullptr; int ld_lnx = 0;
-    const float2 * ln_part_in = nullptr;
-    const float * ln_gamma = nullptr;
-    const float * ln_beta = nullptr;
+    const float * out16_gamma = nullptr;
+    // consumer side: a = the producer's out16 rows; ln_part_in = its ln_part_out with ln_parts = K / 64 tiles per row;
+    // ln_colsum = c; bias must be b'
+    const float2 * ln_part_in = nullptr; int ln_parts = 0;
+    const float * ln_colsum = nullptr;
     float ln_eps = 1e-5f;
+    // ---- L2 prefetch of the NEXT cross-attention's K stream, carried by the decoder-step GEMMs that run before it (tc_skinny only) ----
+    // Between two cross-attention launches HBM is ~85 % idle (the GEMM chain is latency-bound), so an idle lane of every GEMM CTA
+    // asks L2 (cp.async.bulk.prefetch.L2, evict-last) for the first pf_chunks x 16 KB of each (row, head) K block of the coming
+    // launch; the cross-attention kernel streams with evict-first so that its own 490 MB do not push them out before use.
+    // Chunk ids [0, pf_R * pf_H * pf_chunks) are dealt to pf_slots launches; this one is pf_slot.  pf_rows: the step's device rows.
+    const void * pf_rows = nullptr;          // const DecRow *
+    int pf_R = 0, pf_H = 0, pf_chunks = 0, pf_slot = 0, pf_slots = 1;
+    size_t pf_layer_off_bytes = 0; int pf_head_bytes = 0;
 };
 
 // Returns false when the arguments violate the kernel's alignment contract or the launch failed.
