@@ -18,6 +18,9 @@
 #include "tc_gemm.h"
 
 #include <cuda.h>
+
+#include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 #include "ptx.cuh"
@@ -308,6 +311,288 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
 }
 
+// ---- 2-CTA variant: one 256 x 256 output tile per pair of SMs (tcgen05 cta_group::2) -------------------------------------------
+// The 1-CTA kernel above loads 48 KB of operands per 128 x 256 x 64 block of MMAs (87 FLOP per byte): at K = 1280 it is bound by the
+// L2 -> SM path (~950 TFLOP/s).  Here the two CTAs of a cluster own one 256 x 256 tile: each stages ITS 128 rows of A and ITS 128
+// rows of the weight tile (32 KB per k-block and CTA, 131 FLOP per byte), the leader CTA (cluster rank 0) issues
+// tcgen05.mma.cta_group::2 (M = 256: the tensor cores of both SMs run, reading A from their own SM and the two halves of B from
+// both), and each CTA's TMEM receives the accumulator rows of its own 128 A rows.
+//   both CTAs, warp 0 : TMA producer; every load reports its bytes to the LEADER's full barrier (which expects 64 KB per stage)
+//   leader,    warp 1 : MMA issuer; tcgen05.commit multicast to both CTAs frees the stage / publishes the accumulator in both
+//   both CTAs, warps 4-11: epilogue on the own 128 rows, then an arrive on the leader's "accumulator drained" barrier
+struct Cfg2 {
+    static constexpr int BN = 256;
+    static constexpr int kStages = 6;
+    static constexpr int kABytes = BM * BK * 2;              // this CTA's 128 rows of A
+    static constexpr int kBBytes = (BN / 2) * BK * 2;        // this CTA's 128 rows of the 256-row weight tile
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kTmemCols = 2 * BN;                 // two accumulator stages: all 512 columns
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+__device__ __forceinline__ void g2_wait(uint64_t * bar, uint32_t parity) {       // bounded: a protocol error must trap, not hang
+    for (unsigned spins = 0; !ptx::mbar_try_wait(bar, parity); ++spins)
+        if (spins > (1u << 28)) __trap();
+}
+__device__ __forceinline__ void g2_wait_cluster(uint64_t * bar, uint32_t parity) {      // arrivals come from the other CTA too
+    for (unsigned spins = 0;; ++spins) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(ok)
+            : "r"(ptx::smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if (spins > (1u << 28)) __trap();
+    }
+}
+__device__ __forceinline__ uint32_t g2_map_to_cta(uint32_t smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+// 2-D tiled load into THIS CTA's shared memory; completion bytes go to the mbarrier at cluster address `bar` (the leader's)
+__device__ __forceinline__ void g2_tma_load_2d(void * smem_dst, const void * tmap, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(ptx::smem_u32(smem_dst)), "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void g2_umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on the mbarrier at this offset in BOTH CTAs of the pair once all MMAs issued so far have completed
+__device__ __forceinline__ void g2_commit_both(uint64_t * bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(ptx::smem_u32(bar)),
+                 "h"((uint16_t) 3)
+                 : "memory");
+}
+
+template <typename T16>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int K, const EpiParams ep) {
+    using C = Cfg2;
+    constexpr int BN = C::BN;
+    extern __shared__ uint8_t smem_raw[];
+    // both CTAs of the pair must see identical offsets (the leader's descriptors address the peer's memory too): the dynamic
+    // window starts at the same shared-memory address in every CTA of a launch, so the same round-up applies
+    uint8_t * smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t * smem_a = smem;
+    uint8_t * smem_b = smem + C::kStages * C::kABytes;
+    uint64_t * bars = reinterpret_cast<uint64_t *>(smem + C::kStages * C::kStageBytes);
+    uint64_t * full_bar = bars;                       // [kStages]   both producers -> leader's MMA issuer   (leader's copy is used)
+    uint64_t * empty_bar = bars + C::kStages;         // [kStages]   leader's MMA issuer -> producer of each CTA
+    uint64_t * tfull_bar = bars + 2 * C::kStages;     // [2]         leader's MMA issuer -> epilogue of each CTA
+    uint64_t * tempty_bar = tfull_bar + 2;            // [2]         epilogues of both CTAs -> leader's MMA issuer (leader's copy)
+    uint32_t * tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+    const int tiles_m = (ep.M + 2 * BM - 1) / (2 * BM);
+    const int tiles_n = ep.N / BN;
+    const int n_tiles = tiles_m * tiles_n;
+    const int k_blocks = (K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tmap_a);
+        ptx::prefetch_tensormap(&tmap_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < C::kStages; ++i) {
+            ptx::mbar_init(&full_bar[i], 1);
+            ptx::mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&tfull_bar[i], 1);
+            ptx::mbar_init(&tempty_bar[i], 2 * kEpiWarps);   // one arrive per epilogue warp of both CTAs
+        }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ptx::smem_u32(tmem_slot)), "r"(C::kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    // the peer's barriers must exist before a load or a commit signals them
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs) =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = pair; tile < n_tiles; tile += n_pairs) {
+                const int m0 = (tile / tiles_n) * 2 * BM + (int) rank * BM;
+                const int n0 = (tile % tiles_n) * BN + (int) rank * (BN / 2);
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    g2_wait(&empty_bar[stage], phase ^ 1);
+                    if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
+                    const uint32_t bar = g2_map_to_cta(ptx::smem_u32(&full_bar[stage]), 0);
+                    g2_tma_load_2d(smem_a + stage * C::kABytes, &tmap_a, bar, kb * BK, m0);
+                    g2_tma_load_2d(smem_b + stage * C::kBBytes, &tmap_b, bar, kb * BK, n0);
+                    if (++stage == C::kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (leader CTA only) =====
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_f16(Half16<T16>::kind, 2 * BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = pair; tile < n_tiles; tile += n_pairs) {
+                g2_wait_cluster(&tempty_bar[acc], acc_phase ^ 1);       // both epilogues drained this accumulator
+                ptx::tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t) (acc * BN);
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    g2_wait_cluster(&full_bar[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint64_t da = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem_a + stage * C::kABytes));
+                    const uint64_t db = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem_b + stage * C::kBBytes));
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                        g2_umma_f16(tmem_d, da + (uint64_t) (2 * k), db + (uint64_t) (2 * k), idesc, (uint32_t) ((kb | k) != 0));
+                    g2_commit_both(&empty_bar[stage]);                  // the stage is free in both CTAs once these MMAs retire
+                    if (++stage == C::kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                g2_commit_both(&tfull_bar[acc]);                         // accumulator complete in both CTAs
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+            }
+        }
+    } else if (warp >= kEpiWarp0) {
+        // ===== epilogue (both CTAs, own 128 rows) =====
+        const int ew = warp & 3;                       // TMEM lane quarter this warp may read (warp % 4)
+        const int chalf = (warp - kEpiWarp0) >> 2;     // which half of the tile's columns
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        T16 * out16 = reinterpret_cast<T16 *>(ep.out16);
+        const uint32_t tempty_leader = g2_map_to_cta(ptx::smem_u32(&tempty_bar[0]), 0);
+        for (int tile = pair; tile < n_tiles; tile += n_pairs) {
+            const int m0 = (tile / tiles_n) * 2 * BM + (int) rank * BM;
+            const int n0 = (tile % tiles_n) * BN;
+            g2_wait(&tfull_bar[acc], acc_phase);
+            ptx::tc_fence_after();
+            const int row = m0 + ew * 32 + lane;
+            const bool row_ok = row < ep.M;
+            const float * pos_row = ep.pos ? ep.pos + (size_t) (row % ep.pos_rows) * ep.N : nullptr;
+            const float * res_row = ep.resid ? ep.resid + (size_t) row * ep.ldr : nullptr;
+#pragma unroll 1
+            for (int c = chalf * (BN / 64); c < (chalf + 1) * (BN / 64); ++c) {
+                const int col0 = n0 + c * 32;
+                uint32_t r[32];
+                ptx::tmem_ld_32x32(tmem_base + ((uint32_t) (ew * 32) << 16) + (uint32_t) (acc * BN + c * 32), r);
+                ptx::tmem_ld_wait();
+                if (!row_ok) continue;
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                if (ep.bias) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b = __ldg(reinterpret_cast<const float4 *>(ep.bias + col0 + j));
+                        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+                    }
+                }
+                if (col0 < ep.scale_cols) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (col0 + j < ep.scale_cols) v[j] *= ep.scale;
+                }
+                if (ep.gelu) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = gelu_epi<T16>(v[j], ep.ref_f16_gelu);
+                }
+                if (pos_row) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] += __ldg(pos_row + col0 + j);
+                }
+                if (res_row) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b = *reinterpret_cast<const float4 *>(res_row + col0 + j);
+                        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+                    }
+                }
+                if (ep.out32) {
+                    float * o = ep.out32 + (size_t) row * ep.ldo32 + col0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4 *>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                }
+                if (ep.vt && col0 >= ep.vt_col0) {
+                    // V third of the encoder's QKV projection: straight into the attention kernel's V^T layout
+                    const int w = row / ep.vt_T, t = row - w * ep.vt_T, c0 = col0 - ep.vt_col0;
+                    T16 * o = reinterpret_cast<T16 *>(ep.vt) + ((size_t) (w * ep.vt_H + (c0 >> 6)) * 80 + (c0 & 63)) * ep.vt_TP + t;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) o[(size_t) j * ep.vt_TP] = Half16<T16>::from_f(v[j]);
+                } else if (out16) {
+                    T16 * o = out16 + (size_t) row * ep.ldo16 + col0;
+                    if (ep.hm_T > 0) {          // cross-K/V pool: [window][head][K|V][T][64]; a 32-column chunk stays inside one head
+                        const int w = row / ep.hm_T, t = row - w * ep.hm_T, half = ep.N >> 1;
+                        const int kv = col0 >= half ? 1 : 0, hc = col0 - kv * half;
+                        o = out16 + (size_t) w * ep.hm_T * ep.N + ((size_t) ((hc >> 6) * 2 + kv) * ep.hm_T + t) * 64 + (hc & 63);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        union {
+                            uint4 u;
+                            T16 h[8];
+                        } pk;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) pk.h[q] = Half16<T16>::from_f(v[j + q]);
+                        *reinterpret_cast<uint4 *>(o + j) = pk.u;
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0)
+                asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(tempty_leader + (uint32_t) (acc * 8)) : "memory");
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    // neither CTA may leave while the other still signals its barriers or (the leader's MMAs) reads its shared memory
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (warp == 2) {
+        ptx::tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::kTmemCols) : "memory");
+    }
+}
+
 // ---- host: tensor maps ---------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -356,6 +641,23 @@ template <int BN, typename T16> void launch(const GemmArgs & g, const EpiParams 
     const int tiles = ceil_div(g.M, BM) * ceil_div(g.N, BN);
     const int grid = tiles < n_sm ? tiles : n_sm;
     tc_gemm_kernel<BN, T16><<<grid, kThreads, C::kSmemBytes, stream>>>(ta, tb, g.K, ep);
+    WB_CUDA(cudaGetLastError());
+}
+
+template <typename T16> void launch2(const GemmArgs & g, const EpiParams & ep, int n_sm, cudaStream_t stream, bool & ok) {
+    using C = Cfg2;
+    CUtensorMap ta, tb;
+    if (!make_tmap(&ta, g.a, g.M, g.K, g.lda, BM, g.dtype) || !make_tmap(&tb, g.w, g.N, g.K, g.ldw, C::BN / 2, g.dtype)) {
+        ok = false;
+        return;
+    }
+    static DeviceOnce attr_set;      // function attributes are per device
+    once_per_device(attr_set, [&] {
+        WB_CUDA(cudaFuncSetAttribute(tc_gemm2_kernel<T16>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    });
+    const int tiles = ceil_div(g.M, 2 * BM) * (g.N / C::BN);
+    const int pairs = std::min(tiles, n_sm / 2);
+    tc_gemm2_kernel<T16><<<2 * pairs, kThreads, C::kSmemBytes, stream>>>(ta, tb, g.K, ep);
     WB_CUDA(cudaGetLastError());
 }
 
@@ -417,6 +719,16 @@ bool tc_gemm(const GemmArgs & g, cudaStream_t stream) {
     }
     bool ok = true;
     const bool wide = (g.N % 256 == 0) || g.N > 1024;
+    // 2-CTA tiles (256 x 256 per SM pair): whole 256-column tiles, vector epilogue, enough tiles to give every pair several
+    static const bool two_cta_env = !(getenv("WHISPER_B200_GEMM_2CTA") && atoi(getenv("WHISPER_B200_GEMM_2CTA")) == 0);
+    const bool vec_ok = !(reinterpret_cast<uintptr_t>(g.bias) & 15) && !(reinterpret_cast<uintptr_t>(g.resid) & 15) &&
+                        !(reinterpret_cast<uintptr_t>(g.out32) & 15) && !(reinterpret_cast<uintptr_t>(g.out16) & 15) &&
+                        !(reinterpret_cast<uintptr_t>(g.pos) & 15);
+    if (two_cta_env && g.N % 256 == 0 && g.M >= 2048 && vec_ok && (!g.pos || g.N % 4 == 0)) {
+        if (g.dtype == DType::F16) launch2<__half>(g, ep, n_sm, stream, ok);
+        else launch2<__nv_bfloat16>(g, ep, n_sm, stream, ok);
+        return ok && !cuda_failed();
+    }
     if (g.dtype == DType::F16) {
         if (wide) launch<256, __half>(g, ep, n_sm, stream, ok);
         else launch<128, __half>(g, ep, n_sm, stream, ok);

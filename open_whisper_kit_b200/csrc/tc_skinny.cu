@@ -331,7 +331,8 @@ tc_skinny_kernel(const __grid_constant__ TMap tm_x, const __grid_constant__ TMap
                 const int r = blk / p.pf_H, h = blk - r * p.pf_H;
                 const uint8_t * src = reinterpret_cast<const uint8_t *>(p.pf_rows[r].cross_kv) + p.pf_layer_off_bytes +
                                       (size_t) h * p.pf_head_bytes + (size_t) j * 16384;
-                asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(src), "r"(16384u), "l"(pol) : "memory");
+                const uint32_t bytes = (uint32_t) min(16384, p.pf_head_bytes - j * 16384);      // the block's last request is short
+                asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(src), "r"(bytes), "l"(pol) : "memory");
             }
         }
         if (warp * 32 < p.rows_pad) {

@@ -190,6 +190,27 @@ def test_tc_gemm_epilogues(lib, dtype):
     assert np.abs(o32 - ref).max() <= 2e-3 * max(1.0, np.abs(ref).max())
 
 
+@pytest.mark.parametrize("dtype", [0, 1])
+@pytest.mark.parametrize("shape", [(2048, 256, 64), (2100, 768, 1280), (4500, 1280, 3840), (2304, 512, 320), (6000, 2560, 1280)])
+def test_tc_gemm_two_cta_tiles(lib, shape, dtype):
+    """M >= 2048 and N % 256 == 0 run on the cta_group::2 kernel (256 x 256 tiles per SM pair, csrc/tc_gemm.cu): plain product, a
+    row count that leaves the second CTA of the last pair without rows, and every epilogue the encoder uses on that path."""
+    M, N, K = shape
+    ref, o32, o16 = run_gemm(lib, dtype, M, N, K, seed=M + N + K)
+    err = np.abs(o32 - ref).max()
+    print(f"2-CTA gemm {shape} dtype={dtype}: max|d| f32 out = {err:.3e}")
+    assert err <= 2e-3 * max(1.0, np.abs(ref).max())
+    tol16 = (2.0 ** -10 if dtype == 0 else 2.0 ** -7) * np.maximum(np.abs(ref), 1e-2)
+    assert (np.abs(o16 - ref) <= tol16 + 1e-3).all()
+    tol = 2.0 ** -9 if dtype == 0 else 2e-3
+    ref, o32, _ = run_gemm(lib, dtype, M, N, K, bias=True, gelu=True, seed=1)
+    assert np.abs(o32 - ref).max() <= tol * max(1.0, np.abs(ref).max())
+    ref, o32, _ = run_gemm(lib, dtype, M, N, K, bias=True, gelu=True, pos_rows=1500, seed=2)
+    assert np.abs(o32 - ref).max() <= tol * max(1.0, np.abs(ref).max())
+    ref, o32, _ = run_gemm(lib, dtype, M, N, K, bias=True, resid=True, scale_cols=N // 2, scale=64.0 ** -0.25, seed=3)
+    assert np.abs(o32 - ref).max() <= 2e-3 * max(1.0, np.abs(ref).max())
+
+
 SKINNY_SHAPES = [(64, 1280, 1280), (64, 3840, 1280), (64, 1280, 5120), (64, 5120, 1280), (1, 384, 384), (5, 1152, 384),
                  (16, 512, 2048), (100, 1536, 512), (128, 51864, 384), (33, 51866, 128), (7, 200, 64)]
 
