@@ -29,7 +29,8 @@ namespace wb {
 
 namespace {
 
-constexpr int FA_THREADS = 192;     // 4 softmax warps (thread = query row) + TMA producer + MMA issuer
+// softmax warps per CTA: 4 (thread = query row) or 8 (two threads per row, 32 of the tile's 64 keys each) + TMA producer + MMA issuer
+constexpr int fa_threads(int sw) { return (sw + 2) * 32; }
 constexpr int FA_BQ = 128, FA_BK = 64, FA_DH = 64;
 constexpr int FA_Q_BYTES = 128 * 128;                   // 128 queries x 64 x 16-bit
 constexpr int FA_K_BYTES = FA_BK * 128;                 // 64 keys x 64 x 16-bit
@@ -106,13 +107,14 @@ __global__ void vt_tail_rows_kernel(T16 * __restrict__ vt, int TP, int n_blocks)
     vt[(b * FA_VROWS + 64 + r) * TP + k] = T16(r == 0 ? 1.0f : 0.0f);
 }
 
-template <typename T16>
-__global__ void __launch_bounds__(FA_THREADS, 2)
+template <typename T16, int SW>
+__global__ void __launch_bounds__(fa_threads(SW), 2)
 enc_attn_tc_kernel(const __grid_constant__ TMap tm_q, const __grid_constant__ TMap tm_k, const __grid_constant__ TMap tm_vt,
                    T16 * __restrict__ out, int T, int d, int H, float scale_log2e, int n_phantom) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t b_q, b_kfull[2], b_kempty[2], b_vfull[2], b_vempty[2], b_s[2], b_p[2], b_pv[2];
     __shared__ uint32_t s_tmem;
+    __shared__ float s_hmax[SW == 8 ? 2 : 1][2][128];       // SW == 8: the two threads of a row exchange their half-tile maxima here
     uint8_t * smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * FA_BQ, head = blockIdx.y, win = blockIdx.z;
@@ -126,7 +128,7 @@ enc_attn_tc_kernel(const __grid_constant__ TMap tm_q, const __grid_constant__ TM
             ptx::mbar_init(&b_vfull[i], 1);
             ptx::mbar_init(&b_vempty[i], 1);
             ptx::mbar_init(&b_s[i], 1);
-            ptx::mbar_init(&b_p[i], 128);
+            ptx::mbar_init(&b_p[i], SW * 32);
             ptx::mbar_init(&b_pv[i], 1);
         }
         ptx::fence_mbar_init();
@@ -140,7 +142,7 @@ enc_attn_tc_kernel(const __grid_constant__ TMap tm_q, const __grid_constant__ TM
     ptx::tc_fence_after();
     const uint32_t tmem = s_tmem;
     // tile j uses buffer j & 1 of every ring; its k-th use of that buffer (k = j >> 1) completes phase k of the buffer's barriers
-    if (warp == 4) {
+    if (warp == SW) {
         // ===== TMA producer =====
         if (lane == 0) {
             ptx::prefetch_tensormap(&tm_q);
@@ -158,7 +160,7 @@ enc_attn_tc_kernel(const __grid_constant__ TMap tm_q, const __grid_constant__ TM
                 ptx::tma_load_3d(smem + FA_OFF_V + s * FA_V_BYTES, &tm_vt, &b_vfull[s], j * FA_BK, 0, win * H + head);
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == SW + 1) {
         // ===== MMA issuer =====
         // S is double-buffered in TMEM and P in shared memory: S_{j+1} is already computed while the softmax warps work on
         // S_j, and PV_j reads P_j while they write P_{j+1}, so the two hand-offs per tile (commit -> mbarrier -> wake-up, ~1 us
@@ -196,6 +198,117 @@ enc_attn_tc_kernel(const __grid_constant__ TMap tm_q, const __grid_constant__ TM
                 if (j + 2 < n_tiles) issue_s(j + 2);     // S buffer s is free: the softmax warps published P_j after reading it
             }
         }
+    } else if constexpr (SW == 8) {
+        // ===== softmax, two threads per query row =====
+        // Same scheme as the four-warp variant below (one pass over S per key tile against the row maximum of the EARLIER tiles,
+        // O and the row sum in TMEM), but a row's 64 scores of a tile are split between warp w (keys 0..31) and warp w + 4 (keys
+        // 32..63) -- both may read TMEM lanes 32 (w % 4) .. -- so that every SM sub-partition has four softmax warps to hide the
+        // tcgen05.ld / MUFU / convert latencies behind (the phase is bound by instruction latency, not by a pipe: 21 % tensor,
+        // 48 % XU with two warps per sub-partition).  The two threads of a row exchange their half-tile maxima through shared
+        // memory once per tile (double-buffered, one 256-thread named barrier), so both take identical rescaling decisions.
+        constexpr float kGrow = 12.0f;
+        const int half = warp >> 2, row = (warp & 3) * 32 + lane;
+        const uint32_t t_lane = tmem + ((uint32_t) ((warp & 3) * 32) << 16);
+        auto sync_softmax = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+        float m_run = -INFINITY;
+#pragma unroll 1
+        for (int j = 0; j < n_tiles; ++j) {
+            const int s = j & 1;
+            fa_wait(&b_s[s], (j >> 1) & 1);
+            ptx::tc_fence_after();
+            const int key0 = j * FA_BK + half * 32;
+            const bool edge = key0 + 32 > T;
+            uint32_t r[32];
+            ptx::tmem_ld_32x32(t_lane + (uint32_t) (s * FA_BK + half * 32), r);
+            ptx::tmem_ld_wait();
+            if (edge) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (key0 + i >= T) r[i] = __float_as_uint(-INFINITY);
+            }
+            // this half's maximum: four independent chains
+            float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                m4[0] = fmaxf(m4[0], __uint_as_float(r[i]));
+                m4[1] = fmaxf(m4[1], __uint_as_float(r[i + 1]));
+                m4[2] = fmaxf(m4[2], __uint_as_float(r[i + 2]));
+                m4[3] = fmaxf(m4[3], __uint_as_float(r[i + 3]));
+            }
+            float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+            uint32_t pk[16];
+            auto exp_half = [&](float mb) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 2)
+                    pk[i >> 1] = ex2_pack<T16>(fmaf(__uint_as_float(r[i]), scale_log2e, -mb), fmaf(__uint_as_float(r[i + 1]), scale_log2e, -mb));
+            };
+            // the exponentials against the stale maximum do not wait for the exchange (tile 0 has no maximum yet: after it)
+            if (j > 0) exp_half(m_run * scale_log2e);
+            s_hmax[s][half][row] = mx;
+            sync_softmax();
+            mx = fmaxf(mx, s_hmax[s][half ^ 1][row]);
+            const bool grow = j == 0 || (mx - m_run) * scale_log2e > kGrow;
+            if (__any_sync(0xffffffffu, grow)) {            // identical in the partner warp (same rows, same maxima)
+                const float m_new = grow ? mx : m_run;
+                const float f = j == 0 ? 1.0f : ex2((m_run - m_new) * scale_log2e);      // 1 for the rows that keep their maximum
+                m_run = m_new;
+                exp_half(m_run * scale_log2e);
+                if (j > 0) {              // rescale this thread's half of the row's accumulator (+ the row sum); PV_{j-1} must have landed
+                    fa_wait(&b_pv[(j - 1) & 1], ((j - 1) >> 1) & 1);
+                    ptx::tc_fence_after();
+                    uint32_t o[32];
+                    ptx::tmem_ld_32x32(t_lane + 128u + (uint32_t) (half * 32), o);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+                    ptx::tmem_st_32x32(t_lane + 128u + (uint32_t) (half * 32), o);
+                    if (half == 0) {
+                        const uint32_t l = ptx::tmem_ld_32x1(t_lane + 128u + 64u);
+                        ptx::tmem_ld_wait();
+                        ptx::tmem_st_32x1(t_lane + 128u + 64u, __float_as_uint(__uint_as_float(l) * f));
+                    }
+                    ptx::tmem_st_wait();
+                }
+            }
+            // P buffer s is free once PV_{j-2} has read it
+            if (j >= 2) fa_wait(&b_pv[s], ((j >> 1) - 1) & 1);
+            uint8_t * prow = smem + FA_OFF_P + s * FA_P_BYTES + row * 128;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<uint4 *>(prow + (((half * 4 + q) ^ (row & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+            ptx::fence_proxy_async_smem();           // P was written through the generic proxy; the tensor core reads it through the async one
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&b_p[s]);
+        }
+        // O and the row sum l (column 64: the ones row of V^T) sit in TMEM, both relative to m_run
+        fa_wait(&b_pv[(n_tiles - 1) & 1], ((n_tiles - 1) >> 1) & 1);
+        ptx::tc_fence_after();
+        float l = __uint_as_float(ptx::tmem_ld_32x1(t_lane + 128u + 64u)), f = 1.0f;
+        ptx::tmem_ld_wait();
+        if (n_phantom > 0) {              // phantom keys: score 0, value 0
+            const float m_new = fmaxf(m_run, 0.0f);
+            f = ex2((m_run - m_new) * scale_log2e);
+            l = l * f + (float) n_phantom * ex2(-m_new * scale_log2e);
+        }
+        const float inv = f / l;
+        const int q = q0 + row;
+        T16 * orow = out + ((size_t) win * T + (q < T ? q : 0)) * (size_t) d + head * FA_DH + half * 32;
+        {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32(t_lane + 128u + (uint32_t) (half * 32), r);
+            ptx::tmem_ld_wait();
+            if (q < T) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    *reinterpret_cast<uint4 *>(orow + i) =
+                        make_uint4(pack2<T16>(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv),
+                                   pack2<T16>(__uint_as_float(r[i + 2]) * inv, __uint_as_float(r[i + 3]) * inv),
+                                   pack2<T16>(__uint_as_float(r[i + 4]) * inv, __uint_as_float(r[i + 5]) * inv),
+                                   pack2<T16>(__uint_as_float(r[i + 6]) * inv, __uint_as_float(r[i + 7]) * inv));
+                }
+            }
+        }
+        ptx::tc_fence_before();
     } else {
         // ===== softmax: thread = query row =====
         // P = exp2((s - m) * scale) against the row maximum m of the tiles seen BEFORE this one: P may then exceed 1, which a
@@ -345,21 +458,26 @@ bool enc_attention_tc(DType dt, const void * qkv, void * out, void * vt_scratch,
     // V^T (+ ones row) as {T, 80, W*H} with row pitch TP
     if (!tc_make_tmap3d(&tm_vt, vt_scratch, T, FA_VROWS, n_windows * n_head, (size_t) TP * 2, (size_t) FA_VROWS * TP * 2, 64, FA_VROWS, dt)) return false;
     const float scale_log2e = (1.0f / sqrtf((float) FA_DH)) * 1.4426950408889634f;
+    static const bool sw8 = !(getenv("WHISPER_B200_FA_WARPS") && atoi(getenv("WHISPER_B200_FA_WARPS")) == 4);
     dim3 tgrid(ceil_div(TP, 64), n_head, n_windows), grid(ceil_div(T, FA_BQ), n_head, n_windows);
     if (dt == DType::F16) {
         static DeviceOnce set;      // function attributes are per device
         once_per_device(set, [&] {
-            WB_CUDA(cudaFuncSetAttribute(enc_attn_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+            WB_CUDA(cudaFuncSetAttribute(enc_attn_tc_kernel<__half, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+            WB_CUDA(cudaFuncSetAttribute(enc_attn_tc_kernel<__half, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
         });
         if (!vt_ready) v_transpose_kernel<__half><<<tgrid, 256, 0, st>>>(reinterpret_cast<const __half *>(qkv), reinterpret_cast<__half *>(vt_scratch), T, TP, d, n_head);
-        enc_attn_tc_kernel<__half><<<grid, FA_THREADS, FA_SMEM, st>>>(tm_q, tm_k, tm_vt, reinterpret_cast<__half *>(out), T, d, n_head, scale_log2e, n_phantom);
+        if (sw8) enc_attn_tc_kernel<__half, 8><<<grid, fa_threads(8), FA_SMEM, st>>>(tm_q, tm_k, tm_vt, reinterpret_cast<__half *>(out), T, d, n_head, scale_log2e, n_phantom);
+        else enc_attn_tc_kernel<__half, 4><<<grid, fa_threads(4), FA_SMEM, st>>>(tm_q, tm_k, tm_vt, reinterpret_cast<__half *>(out), T, d, n_head, scale_log2e, n_phantom);
     } else {
         static DeviceOnce set;      // function attributes are per device
         once_per_device(set, [&] {
-            WB_CUDA(cudaFuncSetAttribute(enc_attn_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+            WB_CUDA(cudaFuncSetAttribute(enc_attn_tc_kernel<__nv_bfloat16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+            WB_CUDA(cudaFuncSetAttribute(enc_attn_tc_kernel<__nv_bfloat16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
         });
         if (!vt_ready) v_transpose_kernel<__nv_bfloat16><<<tgrid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16 *>(qkv), reinterpret_cast<__nv_bfloat16 *>(vt_scratch), T, TP, d, n_head);
-        enc_attn_tc_kernel<__nv_bfloat16><<<grid, FA_THREADS, FA_SMEM, st>>>(tm_q, tm_k, tm_vt, reinterpret_cast<__nv_bfloat16 *>(out), T, d, n_head, scale_log2e, n_phantom);
+        if (sw8) enc_attn_tc_kernel<__nv_bfloat16, 8><<<grid, fa_threads(8), FA_SMEM, st>>>(tm_q, tm_k, tm_vt, reinterpret_cast<__nv_bfloat16 *>(out), T, d, n_head, scale_log2e, n_phantom);
+        else enc_attn_tc_kernel<__nv_bfloat16, 4><<<grid, fa_threads(4), FA_SMEM, st>>>(tm_q, tm_k, tm_vt, reinterpret_cast<__nv_bfloat16 *>(out), T, d, n_head, scale_log2e, n_phantom);
     }
     WB_CUDA(cudaGetLastError());
     return !cuda_failed();

@@ -502,7 +502,8 @@ bool Engine::decode(const std::vector<DecRow> & rows, const std::vector<int> & l
     // (tc_skinny.cu): slots 0-2 = cross-O, MLP up, MLP down of the previous layer, 3-5 = QKV, O, cross-Q of the layer itself
     // How much: the first four 16 KB chunks of every (row, head) K block, ~84 MB per launch at 64 rows (measured at 64 windows:
     // 2 / 4 / 6 / 8 chunks give 242 / 243 / 241 / 242 ms per 60 steps against 248 without -- L2 keeps ~35-40 MB of it next to the
-    // GEMMs' own traffic).  Only for large batches: the requests compete with the latency-bound GEMM chain that carries them, and
+    // GEMMs' own traffic; an L2 persisting set-aside (cudaLimitPersistingL2CacheSize) does not change that and costs the encoder
+    // 18 % of its speed, so none is configured).  Only for large batches: the requests compete with the latency-bound GEMM chain that carries them, and
     // with few rows the cross-attention is too short to pay that back (8 windows: 516 ms per 220-token step with, 500 without).
     static const int pf_chunks_env = getenv("WHISPER_B200_CROSS_PF_CHUNKS") ? atoi(getenv("WHISPER_B200_CROSS_PF_CHUNKS")) : -1;
     const int pf_block_chunks = (2 * cross_T * 128 + 16383) / 16384;         // 16 KB requests that cover one K | V block

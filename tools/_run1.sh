@@ -1,6 +1,17 @@
 set -u
 O=gpurun_out
-timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-fp8-line > $O/r3_t9_bench.log 2> $O/r3_t9_bench.err; echo "bench rc=$?"
-WHISPER_B200_GEMM_2CTA=0 timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-fp8-line > $O/r3_t9_bench_1cta.log 2> $O/r3_t9_bench_1cta.err; echo "bench rc=$?"
-timeout 600 python bench.py --steps 3 --warmup 3 --windows 8 --no-cpu-baseline --no-fp8-line > $O/r3_t9_bench_w8.log 2> $O/r3_t9_bench_w8.err; echo "bench rc=$?"
-WHISPER_B200_CROSS_PF_CHUNKS=0 timeout 600 python bench.py --steps 3 --warmup 3 --windows 8 --no-cpu-baseline --no-fp8-line > $O/r3_t9_bench_w8_nopf.log 2> $O/r3_t9_bench_w8_nopf.err; echo "bench rc=$?"
+run() { # name env...
+  local n=$1; shift
+  env "$@" timeout 300 python tools/gpu_decode_probe.py large-v3 64 3 60 > $O/r3_t11_$n.log 2>&1; echo "$n rc=$?"; grep "run_streams" $O/r3_t11_$n.log | tail -2
+}
+python - <<'PY'
+import torch
+p=torch.cuda.get_device_properties(0)
+print("L2", p.L2_cache_size)
+PY
+run persist0_pf4 WHISPER_B200_L2_PERSIST_MB=0 WHISPER_B200_CROSS_PF_CHUNKS=4
+run persistmax_pf4 WHISPER_B200_CROSS_PF_CHUNKS=4
+run persistmax_pf6 WHISPER_B200_CROSS_PF_CHUNKS=6
+run persist48_pf4 WHISPER_B200_L2_PERSIST_MB=48 WHISPER_B200_CROSS_PF_CHUNKS=4
+run persist64_pf3 WHISPER_B200_L2_PERSIST_MB=64 WHISPER_B200_CROSS_PF_CHUNKS=3
+run persistmax_pf0 WHISPER_B200_CROSS_PF_CHUNKS=0
