@@ -108,6 +108,13 @@ WB200_API double whisper_b200_kernel_gemm_bench(int dtype, int M, int N, int K, 
  * 2 self-attention at position aux, 3 KV append; R rows of width d. */
 WB200_API double whisper_b200_kernel_step_bench(int which, int dtype, int R, int d, int aux, int iters);
 
+/* Masked self-attention of the decoder step (reference: KQ / soft_max_ext / KQV of whisper_build_graph_decoder,
+ * src/whisper.cpp:2594-2632) on explicit inputs: row r attends to positions 0..pos[r] of its own cache [n_ctx][2d] (K | V);
+ * qkv [R][3d]; with fused_append the K / V of position pos[r] come from qkv and are stored into the cache.  variant: -1 the
+ * default kernel, 0 the CUDA-core kernel, 1 the mma.sync-fragment kernel.  out [R][d]; cache_out (optional) receives the caches. */
+WB200_API int whisper_b200_kernel_self_attn(int dtype, int R, int d, int n_ctx, const int * pos, const uint16_t * qkv, const uint16_t * cache,
+                                            int fused_append, int variant, uint16_t * out, uint16_t * cache_out);
+
 /* Beam bookkeeping hook: copy positions [0, n_pos) of the self-attention history (decoder 0) of state `src` into state `dst`
  * with the batched copy kernel the beam search uses when a beam changes parent (reference: whisper_kv_cache_seq_cp,
  * src/whisper.cpp:1100-1137); `dst` then also points at `src`'s cross K/V, so whisper_decode_with_state(dst, ..., n_past = n_pos)

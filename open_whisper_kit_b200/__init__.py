@@ -35,6 +35,7 @@ EXT_PROTOTYPES = {
     "whisper_b200_kernel_ln_gemm_pair": (_C.c_int, [_C.c_int] * 5 + [_U16P, _U16P, _FP, _FP, _FP, _FP, _C.c_float, _U16P, _FP, _FP]),
     "whisper_b200_kernel_gemm_bench": (_C.c_double, [_C.c_int, _C.c_int, _C.c_int, _C.c_int, _C.c_int, _C.c_int]),
     "whisper_b200_kernel_step_bench": (_C.c_double, [_C.c_int] * 6),
+    "whisper_b200_kernel_self_attn": (_C.c_int, [_C.c_int] * 4 + [_IP, _U16P, _U16P, _C.c_int, _C.c_int, _U16P, _U16P]),
     "whisper_b200_full_device": (_C.c_int, [_C.c_void_p, capi.whisper_full_params, _C.c_void_p, _C.c_int, _C.c_int]),
     "whisper_b200_get_mel": (_C.c_int, [_C.c_void_p, _C.c_void_p, _FP, _C.c_int, _IP, _IP]),
     "whisper_b200_get_encoder_output": (_C.c_int, [_C.c_void_p, _FP, _C.c_int]),

@@ -251,6 +251,164 @@ cross_attn_kernel(const T16 * __restrict__ q, int ldq, const DecRow * __restrict
     }
 }
 
+// ---- masked self-attention of the decoder step with the dot products on mma.sync fragments -------------------------------------
+// cross_attn_kernel<SELF = true> spends ~46 instructions per (4 keys x 8 lanes) on f16 -> f32 conversions, FFMAs and shuffle
+// reductions: 6.2 M warp instructions per launch at 113 positions, issue slots 57 % busy, 14.3 us (profiles/r4_ncu_summary.txt).
+// The tensor cores are used here as a convert-and-accumulate engine (the problem stays a matrix-vector product: one query per
+// sequence and head, 1/8 of each MMA is useful work) -- what counts is that a 16-byte load feeds an MMA operand register as it is:
+//   scores: A = 16 keys x 16 dims straight from the cache rows (a lane's two 16-byte loads per key row ARE its A registers; the
+//           assignment of dims to the k index is a permutation applied to K and q alike, so the dot product does not care),
+//           B = q in all eight columns -> every lane of a quad receives the scores of key rows lane/4 and lane/4 + 8;
+//   P V   : A = V^T (16 dims x 16 keys): the two keys of a register pair come from two cache rows, one PRMT each,
+//           B = the 16-bit probabilities in all eight columns -> a lane receives 8 output dims.
+// Same rounding points as before (f32 scores, expf, probabilities rounded to 16 bits, f32 accumulation); only the order of the
+// f32 additions differs.  One CTA per (row, head), warp w owns the 16-key groups w, w + 4, ...
+template <typename T16> __device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1);
+template <> __device__ __forceinline__ void mma_16816<__half>(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+template <> __device__ __forceinline__ void mma_16816<__nv_bfloat16>(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+template <typename T16> __device__ __forceinline__ uint32_t pack16x2(float lo, float hi) {
+    const T16 a = Half16<T16>::from_f(lo), b = Half16<T16>::from_f(hi);
+    return (uint32_t) *reinterpret_cast<const unsigned short *>(&a) | ((uint32_t) *reinterpret_cast<const unsigned short *>(&b) << 16);
+}
+
+template <typename T16>
+__global__ void __launch_bounds__(128, 9)
+self_attn_mma_kernel(const T16 * __restrict__ qkv, int ldq, const DecRow * __restrict__ rows, int d, size_t layer_off,
+                     int fused_append, T16 * __restrict__ out) {
+    extern __shared__ float s_sc[];          // [n_ctx]
+    __shared__ float s_red[8];
+    __shared__ float s_o[4][64];
+    const int r = blockIdx.x, h = blockIdx.y;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g8 = lane >> 2, t4 = lane & 3;
+    // the successor is a GEMM that only needs its weights until this grid completes: let it in at once
+    pdl_trigger();
+    // row descriptors and the self K/V of earlier positions were written before this launch's predecessor began: pull the cache
+    // rows into L2 while the QKV projection is still running
+    const DecRow row = rows[r];
+    const int ld = 2 * d;
+    const T16 * kbase = reinterpret_cast<const T16 *>(row.self_kv) + layer_off + h * 64;
+    for (int t = tid; t < row.pos; t += 128) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(kbase + (size_t) t * ld));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(kbase + (size_t) t * ld + d));
+    }
+    pdl_wait();
+    const int T = row.pos + 1;
+    // this step's own key / value (position row.pos) come straight from the projection output; their copy into the cache is for
+    // later steps, nothing in this launch reads it back
+    const T16 * qrow = qkv + (size_t) r * ldq + h * 64;
+    const T16 * knew = fused_append ? qrow + d : nullptr;
+    if (fused_append && tid < 16) {
+        const int which = tid >> 3, c = tid & 7;       // 0: K slice, 1: V slice; 8 x 16 bytes each
+        const uint4 u = *reinterpret_cast<const uint4 *>(qrow + (1 + which) * d + c * 8);
+        T16 * dst = reinterpret_cast<T16 *>(row.self_kv) + layer_off + (size_t) row.pos * ld + which * d + h * 64 + c * 8;
+        *reinterpret_cast<uint4 *>(dst) = u;
+    }
+    const uint4 zero4 = make_uint4(0, 0, 0, 0);
+    const int n_groups = (T + 15) >> 4;
+
+    // ---- scores ----
+    float mx = -INFINITY;
+    {
+        const uint4 qx = *reinterpret_cast<const uint4 *>(qrow + t4 * 8), qy = *reinterpret_cast<const uint4 *>(qrow + 32 + t4 * 8);
+        const uint32_t Q[8] = {qx.x, qx.y, qx.z, qx.w, qy.x, qy.y, qy.z, qy.w};
+        auto krow = [&](int t) { return (knew && t == row.pos) ? knew : kbase + (size_t) t * ld; };
+        // two groups per trip: eight independent 16-byte loads per lane in flight
+        for (int g = warp; g < n_groups; g += 8) {
+            const int ta0 = g * 16 + g8, tb0 = ta0 + 8, ta1 = ta0 + 64, tb1 = tb0 + 64;      // group g and group g + 4
+            uint4 k[8];
+            const int tt[4] = {ta0, tb0, ta1, tb1};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const bool ok = tt[i] < T;
+                const T16 * p = krow(ok ? tt[i] : 0);
+                k[2 * i] = ok ? *reinterpret_cast<const uint4 *>(p + t4 * 8) : zero4;
+                k[2 * i + 1] = ok ? *reinterpret_cast<const uint4 *>(p + 32 + t4 * 8) : zero4;
+            }
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const uint4 xa = k[4 * half], ya = k[4 * half + 1], xb = k[4 * half + 2], yb = k[4 * half + 3];
+                const uint32_t Ra[8] = {xa.x, xa.y, xa.z, xa.w, ya.x, ya.y, ya.z, ya.w};
+                const uint32_t Rb[8] = {xb.x, xb.y, xb.z, xb.w, yb.x, yb.y, yb.z, yb.w};
+                float c[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+                for (int s = 0; s < 4; ++s) mma_16816<T16>(c, Ra[2 * s], Rb[2 * s], Ra[2 * s + 1], Rb[2 * s + 1], Q[2 * s], Q[2 * s + 1]);
+                const int ta = tt[2 * half], tb = tt[2 * half + 1];
+                if (ta < T) { mx = fmaxf(mx, c[0]); if (t4 == 0) s_sc[ta] = c[0]; }
+                if (tb < T) { mx = fmaxf(mx, c[2]); if (t4 == 0) s_sc[tb] = c[2]; }
+            }
+        }
+    }
+    mx = warp_max(mx);
+    if (lane == 0) s_red[warp] = mx;
+    __syncthreads();
+    mx = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
+    float sum = 0.0f;
+    for (int t = tid; t < T; t += 128) {
+        const float e = expf(s_sc[t] - mx);
+        s_sc[t] = e;
+        sum += e;
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) s_red[4 + warp] = sum;
+    __syncthreads();
+    sum = s_red[4] + s_red[5] + s_red[6] + s_red[7];
+    const float inv = 1.0f / sum;
+
+    // ---- P V ----
+    const T16 * vbase = kbase + d;
+    const T16 * vnew = knew ? knew + d : nullptr;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+    for (int g = warp; g < n_groups; g += 4) {
+        // this lane's four keys of the group: k = 2 t4, 2 t4 + 1, 2 t4 + 8, 2 t4 + 9 (the B fragment's k indices)
+        const int k0 = g * 16 + 2 * t4;
+        const int kk[4] = {k0, k0 + 1, k0 + 8, k0 + 9};
+        uint4 v[4];
+        float p[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const bool ok = kk[i] < T;
+            const T16 * src = (vnew && kk[i] == row.pos) ? vnew : vbase + (size_t) (ok ? kk[i] : 0) * ld;
+            v[i] = ok ? *reinterpret_cast<const uint4 *>(src + g8 * 8) : zero4;
+            p[i] = ok ? s_sc[kk[i]] * inv : 0.0f;
+        }
+        const uint32_t pab = pack16x2<T16>(p[0], p[1]), pcd = pack16x2<T16>(p[2], p[3]);
+        const uint32_t va[4] = {v[0].x, v[0].y, v[0].z, v[0].w}, vb[4] = {v[1].x, v[1].y, v[1].z, v[1].w};
+        const uint32_t vc[4] = {v[2].x, v[2].y, v[2].z, v[2].w}, vd[4] = {v[3].x, v[3].y, v[3].z, v[3].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            // rows lane/4 and lane/4 + 8 of A = dims 8 g8 + 2 i and 8 g8 + 2 i + 1; columns = this lane's key pairs
+            const uint32_t a0 = __byte_perm(va[i], vb[i], 0x5410), a1 = __byte_perm(va[i], vb[i], 0x7632);
+            const uint32_t a2 = __byte_perm(vc[i], vd[i], 0x5410), a3 = __byte_perm(vc[i], vd[i], 0x7632);
+            mma_16816<T16>(acc[i], a0, a1, a2, a3, pab, pcd);
+        }
+    }
+    if (t4 == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            s_o[warp][g8 * 8 + 2 * i] = acc[i][0];
+            s_o[warp][g8 * 8 + 2 * i + 1] = acc[i][2];
+        }
+    }
+    __syncthreads();
+    if (tid < 64) {
+        const float v = s_o[0][tid] + s_o[1][tid] + s_o[2][tid] + s_o[3][tid];
+        out[(size_t) r * d + h * 64 + tid] = Half16<T16>::from_f(v);
+    }
+}
+
 // ---- cross-attention on a bulk-copy ring --------------------------------------------------------------------------------
 // Same arithmetic as cross_attn_kernel<SELF = false> (same thread -> key / dimension mapping, same reduction orders), but the
 // contiguous 2 x 187.5 KB K / V blocks of one (window, head) arrive through cp.async.bulk in 16 KB chunks (128 keys) into a
@@ -1198,10 +1356,23 @@ void dec_kv_append(const void * qkv, const DecRow * d_rows, int R, int d, size_t
 }
 
 void dec_self_attn(DType dt, const void * qkv, const DecRow * d_rows, int R, int d, int n_head, size_t layer_off_elems,
-                   int n_ctx, bool fused_append, void * out, cudaStream_t st) {
+                   int n_ctx, bool fused_append, void * out, cudaStream_t st, int variant) {
     if (R <= 0) return;
     dim3 grid(R, n_head);
     const size_t smem = (size_t) n_ctx * sizeof(float);
+    // dot products on mma.sync fragments (self_attn_mma_kernel) unless WHISPER_B200_SELF_MMA=0 (the CUDA-core kernel it replaced)
+    static const bool mma_env = !(getenv("WHISPER_B200_SELF_MMA") && atoi(getenv("WHISPER_B200_SELF_MMA")) == 0);
+    const bool use_mma = variant < 0 ? mma_env : variant == 1;
+    if (use_mma && d == n_head * 64) {
+        if (dt == DType::F16)
+            launch_pdl(self_attn_mma_kernel<__half>, grid, dim3(128), smem, st, reinterpret_cast<const __half *>(qkv), 3 * d, d_rows, d,
+                       layer_off_elems, fused_append ? 1 : 0, reinterpret_cast<__half *>(out));
+        else
+            launch_pdl(self_attn_mma_kernel<__nv_bfloat16>, grid, dim3(128), smem, st, reinterpret_cast<const __nv_bfloat16 *>(qkv), 3 * d,
+                       d_rows, d, layer_off_elems, fused_append ? 1 : 0, reinterpret_cast<__nv_bfloat16 *>(out));
+        WB_CUDA(cudaGetLastError());
+        return;
+    }
     if (dt == DType::F16)
         launch_pdl(cross_attn_kernel<__half, true, false>, grid, dim3(128), smem, st, reinterpret_cast<const __half *>(qkv), 3 * d,
                    d_rows, d, layer_off_elems, 0, 1.0f, 0, fused_append ? 1 : 0, reinterpret_cast<__half *>(out), SplitIn{});

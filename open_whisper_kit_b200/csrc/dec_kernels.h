@@ -53,8 +53,9 @@ void dec_embed(DType dt, const void * te, const float * pe, const DecRow * d_row
                cudaStream_t st);
 void dec_kv_append(const void * qkv, const DecRow * d_rows, int R, int d, size_t layer_off_elems, cudaStream_t st);
 // fused_append: also store this token's K/V into the cache (only valid when every sequence has exactly one row).
+// variant: -1 default (mma.sync fragments unless WHISPER_B200_SELF_MMA=0), 0 CUDA-core kernel, 1 mma.sync kernel (tests compare them).
 void dec_self_attn(DType dt, const void * qkv, const DecRow * d_rows, int R, int d, int n_head, size_t layer_off_elems,
-                   int n_ctx, bool fused_append, void * out, cudaStream_t st);
+                   int n_ctx, bool fused_append, void * out, cudaStream_t st, int variant = -1);
 struct SplitIn;   // dec_chain.h: the query as partial tiles of the chain kernel's cross-q GEMM (q is ignored then)
 // d_groups (optional): n_groups runs {first row, count <= DEC_CROSS_GROUP_MAX} of consecutive rows that share one window's cross
 // K/V (prompt tokens, beams): one CTA per (run, head) then streams the K/V once for all rows of the run.

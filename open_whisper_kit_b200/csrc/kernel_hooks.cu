@@ -336,6 +336,30 @@ WB200_API double whisper_b200_kernel_step_bench(int which, int dtype, int R, int
     return cuda_failed() ? -1.0 : 1e3 * ms / iters;
 }
 
+// Masked self-attention of R decoder rows over explicit caches: row r sits at position pos[r] of its own cache [n_ctx][2d] (K | V);
+// qkv [R][3d] carries the step's projections (K / V of position pos[r] are taken from it and appended when fused_append is set,
+// otherwise the cache must already hold them).  variant: 0 CUDA-core kernel, 1 mma.sync kernel, -1 the default.
+WB200_API int whisper_b200_kernel_self_attn(int dtype, int R, int d, int n_ctx, const int * pos, const uint16_t * qkv, const uint16_t * cache,
+                                            int fused_append, int variant, uint16_t * out, uint16_t * cache_out) {
+    if (R <= 0 || d <= 0 || d % 64 != 0 || n_ctx <= 0 || !pos || !qkv || !cache || !out) return -1;
+    for (int r = 0; r < R; ++r)
+        if (pos[r] < 0 || pos[r] >= n_ctx) return -2;
+    cuda_clear_failure();
+    const DType dt = dtype == 1 ? DType::BF16 : DType::F16;
+    const size_t cache_row = (size_t) n_ctx * 2 * d * 2;
+    DevBuf d_qkv((size_t) R * 3 * d * 2), d_cache((size_t) R * cache_row), d_out((size_t) R * d * 2), d_rows((size_t) R * sizeof(DecRow));
+    WB_CUDA(cudaMemcpy(d_qkv.p, qkv, (size_t) R * 3 * d * 2, cudaMemcpyHostToDevice));
+    WB_CUDA(cudaMemcpy(d_cache.p, cache, (size_t) R * cache_row, cudaMemcpyHostToDevice));
+    std::vector<DecRow> hr(R);
+    for (int r = 0; r < R; ++r) hr[r] = {0, pos[r], (char *) d_cache.p + (size_t) r * cache_row, nullptr};
+    WB_CUDA(cudaMemcpy(d_rows.p, hr.data(), R * sizeof(DecRow), cudaMemcpyHostToDevice));
+    dec_self_attn(dt, d_qkv.p, d_rows.as<DecRow>(), R, d, d / 64, 0, n_ctx, fused_append != 0, d_out.p, 0, variant);
+    WB_CUDA(cudaDeviceSynchronize());
+    WB_CUDA(cudaMemcpy(out, d_out.p, (size_t) R * d * 2, cudaMemcpyDeviceToHost));
+    if (cache_out) WB_CUDA(cudaMemcpy(cache_out, d_cache.p, (size_t) R * cache_row, cudaMemcpyDeviceToHost));
+    return cuda_failed() ? -4 : 0;
+}
+
 static_assert(sizeof(whisper_b200_sample_row) == sizeof(SampleRow) && sizeof(whisper_b200_sample_params) == sizeof(SampleParams) &&
               sizeof(whisper_b200_sample_out) == sizeof(SampleOut) && sizeof(whisper_b200_draw_out) == sizeof(DrawOut),
               "the hook's C structs mirror dec_kernels.h");

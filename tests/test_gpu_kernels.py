@@ -290,3 +290,68 @@ def test_layernorm_folded_into_decoder_gemms(lib, shape, dtype):
     # stay within a small multiple of the reference rounding's own distance
     assert err <= 2.5 * ref_err + 1e-5
     assert np.abs(y - y_ref).max() <= (2.0 ** -8 if dtype == 0 else 2.0 ** -5) * max(1.0, np.abs(y_ref).max())
+
+
+# ---------------------------------------------------------------------------------------------------------
+def self_attn_ref(qkv, cache, pos, d, dtype, fused):
+    """Float64 restatement of the decoder's masked self-attention for one token per row (reference: KQ, soft_max_ext with the
+    causal mask, KQV of whisper_build_graph_decoder, src/whisper.cpp:2594-2632): q and K already carry dh^-0.25 each, the
+    probabilities are rounded to 16 bits before the product with V (the reference's F16 KQV operand)."""
+    R, H = qkv.shape[0], d // 64
+    out = np.zeros((R, d))
+    for r in range(R):
+        kv = cache[r].copy()
+        if fused:
+            kv[pos[r], :] = qkv[r, d:]
+        T = pos[r] + 1
+        for h in range(H):
+            q = qkv[r, h * 64:(h + 1) * 64].astype(np.float64)
+            k = kv[:T, h * 64:(h + 1) * 64].astype(np.float64)
+            v = kv[:T, d + h * 64:d + (h + 1) * 64].astype(np.float64)
+            s = k @ q
+            e = np.exp(s - s.max())
+            p = from_bits(to_bits((e / e.sum()).astype(np.float32), dtype), dtype).astype(np.float64)
+            out[r, h * 64:(h + 1) * 64] = p @ v
+    return out
+
+
+@pytest.mark.parametrize("dtype", [0, 1])
+@pytest.mark.parametrize("fused", [1, 0])
+def test_decoder_self_attention_kernels(lib, dtype, fused):
+    """Both self-attention kernels of the decoder step (mma.sync fragments = default, CUDA cores = WHISPER_B200_SELF_MMA=0) against
+    the float64 restatement at every kind of position: first token, group edges (15 / 16 / 17, 63 / 64 / 65), mid sequence, the last
+    slot of the text context; with the step's K / V taken from the projection output (fused append) or already in the cache."""
+    d, n_ctx = 384, 448
+    pos = np.array([0, 1, 2, 15, 16, 17, 31, 63, 64, 65, 100, 127, 128, 129, 200, 300, 446, 447], dtype=np.int32)
+    R = len(pos)
+    rng = np.random.default_rng(11 + dtype)
+    qkv = from_bits(to_bits(rng.standard_normal((R, 3 * d), dtype=np.float32) * 0.6, dtype), dtype)
+    cache = from_bits(to_bits(rng.standard_normal((R, n_ctx, 2 * d), dtype=np.float32) * 0.6, dtype), dtype)
+    # rows past a sequence's position hold garbage in a live cache (older windows): the kernels must not read them
+    for r in range(R):
+        cache[r, pos[r] + 1:, :] = 7.0e4 if dtype == 0 else 1.0e30
+        if fused:
+            cache[r, pos[r], :] = 7.0e4 if dtype == 0 else 1.0e30       # this slot is filled by the kernel itself
+        else:
+            cache[r, pos[r], :] = qkv[r, d:]
+    ref = self_attn_ref(qkv, cache, pos, d, dtype, fused)
+    outs = {}
+    for variant in (0, 1, -1):
+        o = np.zeros((R, d), dtype=np.uint16)
+        c_out = np.zeros((R, n_ctx, 2 * d), dtype=np.uint16)
+        rc = lib.whisper_b200_kernel_self_attn(dtype, R, d, n_ctx, pos.ctypes.data_as(C.POINTER(C.c_int)),
+                                               to_bits(qkv, dtype).ctypes.data_as(U16P), to_bits(cache, dtype).ctypes.data_as(U16P),
+                                               fused, variant, o.ctypes.data_as(U16P), c_out.ctypes.data_as(U16P))
+        assert rc == 0
+        got = from_bits(o, dtype)
+        err = np.abs(got - ref).max()
+        print(f"self-attention variant {variant} dtype={dtype} fused={fused}: max|d| = {err:.3e}")
+        assert np.isfinite(got).all()
+        assert err <= (2.0 ** -9 if dtype == 0 else 2.0 ** -6) * max(1.0, np.abs(ref).max())
+        if fused:       # the step's K | V row landed in the cache, bit for bit
+            kv_new = from_bits(c_out, dtype)[np.arange(R), pos, :]
+            assert np.array_equal(kv_new, qkv[:, d:])
+        outs[variant] = got
+    # the two kernels differ only in the order of their f32 additions: at most one 16-bit rounding step apart
+    assert np.abs(outs[0] - outs[1]).max() <= (2.0 ** -10 if dtype == 0 else 2.0 ** -7) * max(1.0, np.abs(ref).max())
+    assert np.array_equal(outs[1], outs[-1])
