@@ -21,6 +21,8 @@
 #include "enc_kernels.h"
 
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "ptx.cuh"
 #include "tc_gemm.h"
@@ -53,6 +55,18 @@ __device__ __forceinline__ float ex2(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// three-input maximum and two-wide f32 FMA (sm_100): half the issue slots of the softmax warps' max / scale passes
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+__device__ __forceinline__ void fma2(float & y0, float & y1, float a0, float a1, float s, float c) {      // (y0, y1) = (a0, a1) * s + c
+    asm("{\n\t.reg .b64 ra, rs, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rs, {%4, %4};\n\tmov.b64 rc, {%5, %5};\n\t"
+        "fma.rn.f32x2 rd, ra, rs, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(y0), "=f"(y1)
+        : "f"(a0), "f"(a1), "f"(s), "f"(c));
+}
 // two exponentials per MUFU instruction, straight into the 16-bit pair the P tile wants (f16 keeps subnormals)
 template <typename T16> __device__ __forceinline__ uint32_t ex2_pack(float a, float b);
 template <> __device__ __forceinline__ uint32_t ex2_pack<__half>(float a, float b) {
@@ -66,6 +80,7 @@ template <> __device__ __forceinline__ uint32_t ex2_pack<__nv_bfloat16>(float a,
     return y;
 }
 template <typename T16> __device__ __forceinline__ uint32_t pack2(float a, float b);
+
 template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
     __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t *>(&h);
@@ -110,8 +125,12 @@ __global__ void vt_tail_rows_kernel(T16 * __restrict__ vt, int TP, int n_blocks)
 template <typename T16, int SW>
 __global__ void __launch_bounds__(fa_threads(SW), 2)
 enc_attn_tc_kernel(const __grid_constant__ TMap tm_q, const __grid_constant__ TMap tm_k, const __grid_constant__ TMap tm_vt,
-                   T16 * __restrict__ out, int T, int d, int H, float scale_log2e, int n_phantom) {
+                   T16 * __restrict__ out, int T, int d, int H, float scale_log2e, int n_phantom, long long * __restrict__ trace) {
     extern __shared__ uint8_t smem_raw[];
+    // development aid (WHISPER_B200_FA_TRACE): clock64 stamps of CTA (0, 0, 0) -- [who][tile][8], who 0 / 1 = lane 0 of softmax warps
+    // 0 / 4, 2 = the MMA issuer
+    const bool tr = trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+#define FA_STAMP(who, j, i) do { if (tr && (j) < 32) trace[((who) * 32 + (j)) * 8 + (i)] = clock64(); } while (0)
     __shared__ __align__(8) uint64_t b_q, b_kfull[2], b_kempty[2], b_vfull[2], b_vempty[2], b_s[2], b_p[2], b_pv[2];
     __shared__ uint32_t s_tmem;
     __shared__ float s_hmax[SW == 8 ? 2 : 1][2][128];       // SW == 8: the two threads of a row exchange their half-tile maxima here
@@ -128,7 +147,7 @@ enc_attn_tc_kernel(const __grid_constant__ TMap tm_q, const __grid_constant__ TM
             ptx::mbar_init(&b_vfull[i], 1);
             ptx::mbar_init(&b_vempty[i], 1);
             ptx::mbar_init(&b_s[i], 1);
-            ptx::mbar_init(&b_p[i], SW * 32);
+            ptx::mbar_init(&b_p[i], SW == 8 ? 8 : SW * 32);      // SW == 8: one arrival per warp
             ptx::mbar_init(&b_pv[i], 1);
         }
         ptx::fence_mbar_init();
@@ -172,6 +191,7 @@ enc_attn_tc_kernel(const __grid_constant__ TMap tm_q, const __grid_constant__ TM
             auto issue_s = [&](int j) {
                 const int s = j & 1;
                 fa_wait(&b_kfull[s], (j >> 1) & 1);
+                FA_STAMP(2, j, 4);
                 ptx::tc_fence_after();
                 const uint64_t dk = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + FA_OFF_K + s * FA_K_BYTES));
 #pragma unroll
@@ -179,14 +199,18 @@ enc_attn_tc_kernel(const __grid_constant__ TMap tm_q, const __grid_constant__ TM
                     ptx::umma_f16(tmem + (uint32_t) (s * FA_BK), dq + (uint64_t) (2 * k), dk + (uint64_t) (2 * k), idesc_s, (uint32_t) (k != 0));
                 ptx::umma_commit(&b_kempty[s]);
                 ptx::umma_commit(&b_s[s]);
+                FA_STAMP(2, j, 5);
             };
             fa_wait(&b_q, 0);
             issue_s(0);
             if (n_tiles > 1) issue_s(1);
             for (int j = 0; j < n_tiles; ++j) {
                 const int s = j & 1;
+                FA_STAMP(2, j, 0);
                 fa_wait(&b_p[s], (j >> 1) & 1);      // P_j is in shared memory, S_j has been read, the accumulator is consistent
+                FA_STAMP(2, j, 1);
                 fa_wait(&b_vfull[s], (j >> 1) & 1);
+                FA_STAMP(2, j, 2);
                 ptx::tc_fence_after();
                 const uint64_t dp = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + FA_OFF_P + s * FA_P_BYTES));
                 const uint64_t dv = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + FA_OFF_V + s * FA_V_BYTES));
@@ -195,6 +219,7 @@ enc_attn_tc_kernel(const __grid_constant__ TMap tm_q, const __grid_constant__ TM
                     ptx::umma_f16(tmem + 128u, dp + (uint64_t) (2 * k), dv + (uint64_t) (2 * k), idesc_pv, (uint32_t) (j != 0 || k != 0));
                 ptx::umma_commit(&b_vempty[s]);
                 ptx::umma_commit(&b_pv[s]);
+                FA_STAMP(2, j, 3);
                 if (j + 2 < n_tiles) issue_s(j + 2);     // S buffer s is free: the softmax warps published P_j after reading it
             }
         }
@@ -211,16 +236,21 @@ enc_attn_tc_kernel(const __grid_constant__ TMap tm_q, const __grid_constant__ TM
         const uint32_t t_lane = tmem + ((uint32_t) ((warp & 3) * 32) << 16);
         auto sync_softmax = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
         float m_run = -INFINITY;
+        const bool trl = tr && lane == 0 && (warp & 3) == 0;
+#define FA_SSTAMP(j, i) do { if (trl && (j) < 32) trace[((half) * 32 + (j)) * 8 + (i)] = clock64(); } while (0)
 #pragma unroll 1
         for (int j = 0; j < n_tiles; ++j) {
             const int s = j & 1;
+            FA_SSTAMP(j, 0);
             fa_wait(&b_s[s], (j >> 1) & 1);
+            FA_SSTAMP(j, 1);
             ptx::tc_fence_after();
             const int key0 = j * FA_BK + half * 32;
             const bool edge = key0 + 32 > T;
             uint32_t r[32];
             ptx::tmem_ld_32x32(t_lane + (uint32_t) (s * FA_BK + half * 32), r);
             ptx::tmem_ld_wait();
+            FA_SSTAMP(j, 2);
             if (edge) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i)
@@ -229,23 +259,28 @@ enc_attn_tc_kernel(const __grid_constant__ TMap tm_q, const __grid_constant__ TM
             // this half's maximum: four independent chains
             float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-                m4[0] = fmaxf(m4[0], __uint_as_float(r[i]));
-                m4[1] = fmaxf(m4[1], __uint_as_float(r[i + 1]));
-                m4[2] = fmaxf(m4[2], __uint_as_float(r[i + 2]));
-                m4[3] = fmaxf(m4[3], __uint_as_float(r[i + 3]));
+            for (int i = 0; i < 32; i += 8) {
+                m4[0] = max3(m4[0], __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+                m4[1] = max3(m4[1], __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+                m4[2] = max3(m4[2], __uint_as_float(r[i + 4]), __uint_as_float(r[i + 5]));
+                m4[3] = max3(m4[3], __uint_as_float(r[i + 6]), __uint_as_float(r[i + 7]));
             }
-            float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+            float mx = fmaxf(max3(m4[0], m4[1], m4[2]), m4[3]);
             uint32_t pk[16];
             auto exp_half = [&](float mb) {
 #pragma unroll
-                for (int i = 0; i < 32; i += 2)
-                    pk[i >> 1] = ex2_pack<T16>(fmaf(__uint_as_float(r[i]), scale_log2e, -mb), fmaf(__uint_as_float(r[i + 1]), scale_log2e, -mb));
+                for (int i = 0; i < 32; i += 2) {
+                    float y0, y1;
+                    fma2(y0, y1, __uint_as_float(r[i]), __uint_as_float(r[i + 1]), scale_log2e, -mb);
+                    pk[i >> 1] = ex2_pack<T16>(y0, y1);
+                }
             };
             // the exponentials against the stale maximum do not wait for the exchange (tile 0 has no maximum yet: after it)
             if (j > 0) exp_half(m_run * scale_log2e);
             s_hmax[s][half][row] = mx;
+            FA_SSTAMP(j, 3);
             sync_softmax();
+            FA_SSTAMP(j, 4);
             mx = fmaxf(mx, s_hmax[s][half ^ 1][row]);
             const bool grow = j == 0 || (mx - m_run) * scale_log2e > kGrow;
             if (__any_sync(0xffffffffu, grow)) {            // identical in the partner warp (same rows, same maxima)
@@ -270,15 +305,19 @@ enc_attn_tc_kernel(const __grid_constant__ TMap tm_q, const __grid_constant__ TM
                     ptx::tmem_st_wait();
                 }
             }
-            // P buffer s is free once PV_{j-2} has read it
-            if (j >= 2) fa_wait(&b_pv[s], ((j >> 1) - 1) & 1);
+            // P buffer s is free once PV_{j-2} has read it -- which this thread already knows: the issuer queued S_j behind PV_{j-2},
+            // tcgen05 operations of one thread complete in order, and S_j's commit (b_s) was observed at the top of this iteration
+            FA_SSTAMP(j, 5);
             uint8_t * prow = smem + FA_OFF_P + s * FA_P_BYTES + row * 128;
 #pragma unroll
             for (int q = 0; q < 4; ++q)
                 *reinterpret_cast<uint4 *>(prow + (((half * 4 + q) ^ (row & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+            FA_SSTAMP(j, 6);
             ptx::fence_proxy_async_smem();           // P was written through the generic proxy; the tensor core reads it through the async one
             ptx::tc_fence_before();
-            ptx::mbar_arrive(&b_p[s]);
+            __syncwarp();                            // one arrival per warp (32 arrivals on one word serialise)
+            if (lane == 0) ptx::mbar_arrive(&b_p[s]);
+            FA_SSTAMP(j, 7);
         }
         // O and the row sum l (column 64: the ones row of V^T) sit in TMEM, both relative to m_run
         fa_wait(&b_pv[(n_tiles - 1) & 1], ((n_tiles - 1) >> 1) & 1);
@@ -432,6 +471,43 @@ enc_attn_tc_kernel(const __grid_constant__ TMap tm_q, const __grid_constant__ TM
     }
 }
 
+// ---- development trace: WHISPER_B200_FA_TRACE=<launch index> records the stamps of that launch, printed at exit ----
+struct FaTrace {
+    long want = -1, seen = 0;
+    long long * dev = nullptr;
+    FaTrace() {
+        const char * e = getenv("WHISPER_B200_FA_TRACE");
+        if (!e) return;
+        want = atol(e);
+        if (cudaMalloc(&dev, 3 * 32 * 8 * 8) != cudaSuccess) { want = -1; return; }
+        cudaMemset(dev, 0, 3 * 32 * 8 * 8);
+    }
+    ~FaTrace() {
+        if (want < 0 || !dev) return;
+        cudaDeviceSynchronize();
+        long long h[3 * 32 * 8];
+        if (cudaMemcpy(h, dev, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) return;
+        const long long t0 = h[(0 * 32 + 4) * 8 + 0];
+        fprintf(stderr, "fa_trace: cycles relative to softmax warp 0's loop top of tile 4\n");
+        fprintf(stderr, "fa_trace: softmax stamps = 0 top, 1 S ready, 2 S in regs, 3 exp done, 4 partner max, 5 P buffer free, 6 P stored, 7 arrived\n");
+        fprintf(stderr, "fa_trace: mma stamps     = 0 top, 1 P ready, 2 V ready, 3 PV issued, 4 K(j) ready, 5 S(j) issued\n");
+        for (int j = 4; j < 14; ++j)
+            for (int who = 0; who < 3; ++who) {
+                fprintf(stderr, "fa_trace tile %2d %s |", j, who == 0 ? "softmax w0" : who == 1 ? "softmax w4" : "mma       ");
+                for (int i = 0; i < (who == 2 ? 6 : 8); ++i) fprintf(stderr, " %6lld", h[(who * 32 + j) * 8 + i] ? h[(who * 32 + j) * 8 + i] - t0 : -1ll);
+                fprintf(stderr, "\n");
+            }
+    }
+    long long * slot() {
+        if (want < 0) return nullptr;
+        return seen++ == want ? dev : nullptr;
+    }
+};
+long long * fa_trace_slot() {
+    static FaTrace t;
+    return t.slot();
+}
+
 }  // namespace
 
 size_t enc_attention_tc_scratch_bytes(int n_windows, int T, int n_head) {
@@ -458,27 +534,23 @@ bool enc_attention_tc(DType dt, const void * qkv, void * out, void * vt_scratch,
     // V^T (+ ones row) as {T, 80, W*H} with row pitch TP
     if (!tc_make_tmap3d(&tm_vt, vt_scratch, T, FA_VROWS, n_windows * n_head, (size_t) TP * 2, (size_t) FA_VROWS * TP * 2, 64, FA_VROWS, dt)) return false;
     const float scale_log2e = (1.0f / sqrtf((float) FA_DH)) * 1.4426950408889634f;
+    long long * trace = fa_trace_slot();
     static const bool sw8 = !(getenv("WHISPER_B200_FA_WARPS") && atoi(getenv("WHISPER_B200_FA_WARPS")) == 4);
     dim3 tgrid(ceil_div(TP, 64), n_head, n_windows), grid(ceil_div(T, FA_BQ), n_head, n_windows);
-    if (dt == DType::F16) {
-        static DeviceOnce set;      // function attributes are per device
+    auto launch = [&](auto tag) {
+        using T16 = decltype(tag);
+        T16 * o = reinterpret_cast<T16 *>(out);
+        static DeviceOnce set;      // function attributes are per device (one guard per instantiation of this lambda = per T16)
         once_per_device(set, [&] {
-            WB_CUDA(cudaFuncSetAttribute(enc_attn_tc_kernel<__half, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
-            WB_CUDA(cudaFuncSetAttribute(enc_attn_tc_kernel<__half, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+            WB_CUDA(cudaFuncSetAttribute(enc_attn_tc_kernel<T16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+            WB_CUDA(cudaFuncSetAttribute(enc_attn_tc_kernel<T16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
         });
-        if (!vt_ready) v_transpose_kernel<__half><<<tgrid, 256, 0, st>>>(reinterpret_cast<const __half *>(qkv), reinterpret_cast<__half *>(vt_scratch), T, TP, d, n_head);
-        if (sw8) enc_attn_tc_kernel<__half, 8><<<grid, fa_threads(8), FA_SMEM, st>>>(tm_q, tm_k, tm_vt, reinterpret_cast<__half *>(out), T, d, n_head, scale_log2e, n_phantom);
-        else enc_attn_tc_kernel<__half, 4><<<grid, fa_threads(4), FA_SMEM, st>>>(tm_q, tm_k, tm_vt, reinterpret_cast<__half *>(out), T, d, n_head, scale_log2e, n_phantom);
-    } else {
-        static DeviceOnce set;      // function attributes are per device
-        once_per_device(set, [&] {
-            WB_CUDA(cudaFuncSetAttribute(enc_attn_tc_kernel<__nv_bfloat16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
-            WB_CUDA(cudaFuncSetAttribute(enc_attn_tc_kernel<__nv_bfloat16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
-        });
-        if (!vt_ready) v_transpose_kernel<__nv_bfloat16><<<tgrid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16 *>(qkv), reinterpret_cast<__nv_bfloat16 *>(vt_scratch), T, TP, d, n_head);
-        if (sw8) enc_attn_tc_kernel<__nv_bfloat16, 8><<<grid, fa_threads(8), FA_SMEM, st>>>(tm_q, tm_k, tm_vt, reinterpret_cast<__nv_bfloat16 *>(out), T, d, n_head, scale_log2e, n_phantom);
-        else enc_attn_tc_kernel<__nv_bfloat16, 4><<<grid, fa_threads(4), FA_SMEM, st>>>(tm_q, tm_k, tm_vt, reinterpret_cast<__nv_bfloat16 *>(out), T, d, n_head, scale_log2e, n_phantom);
-    }
+        if (!vt_ready) v_transpose_kernel<T16><<<tgrid, 256, 0, st>>>(reinterpret_cast<const T16 *>(qkv), reinterpret_cast<T16 *>(vt_scratch), T, TP, d, n_head);
+        if (!sw8) enc_attn_tc_kernel<T16, 4><<<grid, fa_threads(4), FA_SMEM, st>>>(tm_q, tm_k, tm_vt, o, T, d, n_head, scale_log2e, n_phantom, trace);
+        else enc_attn_tc_kernel<T16, 8><<<grid, fa_threads(8), FA_SMEM, st>>>(tm_q, tm_k, tm_vt, o, T, d, n_head, scale_log2e, n_phantom, trace);
+    };
+    if (dt == DType::F16) launch(__half{});
+    else launch(__nv_bfloat16{});
     WB_CUDA(cudaGetLastError());
     return !cuda_failed();
 }
