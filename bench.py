@@ -613,7 +613,8 @@ def main_mel_sweep(args):
             audio_s = 3600.0 * hours
             algo = audio_s * (64000 + 100 * n_mel * 4)
             rows.append({"hours": hours, "n_mel": n_mel, "kernel_ms": round(k_ms, 4), "kernel_GBs": round(algo / (k_ms * 1e-3) / 1e9, 1),
-                         "kernel_frac_of_hbm_peak": round(algo / (k_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 3),
+                         # aggregate GB/s over all ranks against the aggregate peak (= the per-GPU fraction of the slowest rank)
+                         "kernel_frac_of_hbm_peak": round(algo / (k_ms * 1e-3) / 1e9 / (peaks["hbm_gbs"] * world), 3),
                          "e2e_ms": round(e_ms, 3), "e2e_GBs": round(algo / (e_ms * 1e-3) / 1e9, 1),
                          "h2d_bytes": n_samples * 4 * world, "audio_s_per_s": round(audio_s / (e_ms * 1e-3), 0)})
             del host

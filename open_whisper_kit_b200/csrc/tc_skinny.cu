@@ -59,6 +59,7 @@ struct TcSkinnyParams {
     const float * bias;
     float scale; int scale_cols;
     int gelu, ref_f16_gelu;
+    int w_l2_prefetch;                 // ask L2 for the weight tiles beyond the ring depth before the dependency resolves
     int vec_io;                        // bias / residual / outputs are 16-byte (8-byte for 16-bit) addressable per 4 columns
     const float * resid; int ldr;
     void * out16; int ldo16;
@@ -274,6 +275,11 @@ tc_skinny_kernel(const __grid_constant__ TMap tm_x, const __grid_constant__ TMap
                 ptx::mbar_arrive_expect_tx(&b_full[i], stage_bytes);
                 ptx::tma_load_2d(smem + i * stage_bytes + x_bytes, &tm_w, &b_full[i], (kb0 + i) * TB, n0);
             }
+            // the weight tiles that have to wait for a free stage (MLP down: ten k-blocks per CTA, MLP up: seven): into L2 meanwhile,
+            // so that the second round through the ring is an L2 round trip, not a DRAM one
+            if (p.w_l2_prefetch)
+                for (int i = npre; i < nkb; ++i)
+                    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(&tm_w), "r"((kb0 + i) * TB), "r"(n0) : "memory");
             pdl_wait();
             for (int i = 0; i < nkb; ++i) {
                 const int s = i % T_STAGES;
@@ -543,6 +549,10 @@ bool tc_skinny_gemm(const GemmArgs & g, cudaStream_t stream) {
     const int cta_per_sm = rows_pad == 64 ? 2 : 1;          // by shared memory: 81 KB / 121 KB per CTA
     int KS = std::max(ceil_div(n_sm, n_tiles), ceil_div(kblocks, T_STAGES));
     KS = std::min(KS, 8);
+    {   // experiment: fewer, longer K slices for the small GEMMs (fewer senders per owner in the split-K exchange)
+        static const int ks_small = getenv("WHISPER_B200_TCS_KS_SMALL") ? atoi(getenv("WHISPER_B200_TCS_KS_SMALL")) : 0;
+        if (ks_small > 0 && kblocks <= 4 * T_STAGES && n_tiles <= 32) KS = std::min(KS, std::max(ks_small, ceil_div(kblocks, T_STAGES)));
+    }
     while (KS > 1 && (n_tiles * KS > cta_per_sm * n_sm || KS > kblocks / 2)) --KS;
 
     static std::mutex mu;
@@ -582,6 +592,8 @@ bool tc_skinny_gemm(const GemmArgs & g, cudaStream_t stream) {
         p.pf_lo = (int) (tot * g.pf_slot / g.pf_slots); p.pf_hi = (int) (tot * (g.pf_slot + 1) / g.pf_slots);
         p.pf_layer_off_bytes = g.pf_layer_off_bytes; p.pf_head_bytes = g.pf_head_bytes;
     }
+    static const bool w_pf = !(getenv("WHISPER_B200_TCS_WPF") && atoi(getenv("WHISPER_B200_TCS_WPF")) == 0);
+    p.w_l2_prefetch = w_pf ? 1 : 0;
     static TcsTrace trace;
     p.trace = trace.slot({n_tiles, KS, g.M, g.N, g.K});
     auto al = [](const void * q, uintptr_t a) { return (reinterpret_cast<uintptr_t>(q) & (a - 1)) == 0; };
