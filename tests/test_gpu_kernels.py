@@ -117,13 +117,13 @@ def gelu_ref(v, dtype):
 
 
 def run_gemm(lib, dtype, M, N, K, bias=False, scale_cols=0, scale=1.0, gelu=False, pos_rows=0, resid=False, seed=0,
-             skinny=False):
+             skinny=False, bias_scale=0.1, only16=False):
     # skinny: False = tiled tcgen05 GEMM, True/1 = HMMA weight-streaming GEMM, 2 = tcgen05 weight-streaming GEMM
     rng = np.random.default_rng(seed)
     a = rng.standard_normal((M, K), dtype=np.float32)
     w = (rng.standard_normal((N, K), dtype=np.float32) / np.sqrt(K)).astype(np.float32)
     ab, wb = to_bits(a, dtype), to_bits(w, dtype)
-    b = (0.1 * rng.standard_normal(N)).astype(np.float32) if bias else None
+    b = (bias_scale * rng.standard_normal(N)).astype(np.float32) if bias else None
     p = rng.standard_normal((pos_rows, N)).astype(np.float32) if pos_rows else None
     r = rng.standard_normal((M, N)).astype(np.float32) if resid else None
     o16 = np.zeros((M, N), dtype=np.uint16)
@@ -139,7 +139,7 @@ def run_gemm(lib, dtype, M, N, K, bias=False, scale_cols=0, scale=1.0, gelu=Fals
                                           b.ctypes.data_as(FP) if bias else None, scale, scale_cols, int(gelu),
                                           p.ctypes.data_as(FP) if pos_rows else None, pos_rows,
                                           r.ctypes.data_as(FP) if resid else None, o16.ctypes.data_as(U16P),
-                                          o32.ctypes.data_as(FP))
+                                          None if only16 else o32.ctypes.data_as(FP))
     assert rc == 0
     ref = from_bits(ab, dtype).astype(np.float64) @ from_bits(wb, dtype).astype(np.float64).T
     if bias:
@@ -209,6 +209,22 @@ def test_tc_gemm_two_cta_tiles(lib, shape, dtype):
     assert np.abs(o32 - ref).max() <= tol * max(1.0, np.abs(ref).max())
     ref, o32, _ = run_gemm(lib, dtype, M, N, K, bias=True, resid=True, scale_cols=N // 2, scale=64.0 ** -0.25, seed=3)
     assert np.abs(o32 - ref).max() <= 2e-3 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("dtype", [0, 1])
+@pytest.mark.parametrize("shape", [(2304, 512, 320), (4500, 1280, 1280)])
+def test_tc_gemm_gelu_16bit_output_path(lib, shape, dtype):
+    """MLP up / conv 1 write a 16-bit result only: the 2-CTA kernel then evaluates GELU two values at a time without the range
+    clauses of ggml's table (0 below -10, identity above 10: reference ggml/src/ggml-cpu/vec.h:996-1009).  Must give the SAME 16-bit
+    numbers as the general path (same accumulators, f32 output requested as well), with a bias wide enough that a tenth of the
+    values fall outside (-10, 10)."""
+    M, N, K = shape
+    ref, _, o16_general = run_gemm(lib, dtype, M, N, K, bias=True, gelu=True, seed=5, bias_scale=6.0)
+    _, _, o16_only = run_gemm(lib, dtype, M, N, K, bias=True, gelu=True, seed=5, bias_scale=6.0, only16=True)
+    assert (np.abs(ref) >= 10.0).mean() > 0.02
+    assert np.array_equal(o16_only, o16_general)          # -0.0 == 0.0
+    tol16 = (2.0 ** -9 if dtype == 0 else 2.0 ** -6) * np.maximum(np.abs(ref), 1e-2)
+    assert (np.abs(o16_only - ref) <= tol16 + 1e-3).all()
 
 
 SKINNY_SHAPES = [(64, 1280, 1280), (64, 3840, 1280), (64, 1280, 5120), (64, 5120, 1280), (1, 384, 384), (5, 1152, 384),
