@@ -13,7 +13,9 @@
 //              tile -- exp2 against the row maximum of the earlier tiles ("stale" maximum, two exponentials per MUFU op
 //              straight into the 128-byte-swizzled 16-bit A-operand layout), O and the row sum accumulate in TMEM across all
 //              key tiles; a row whose scores outgrow its maximum by 2^12 takes the new one and rescales its TMEM lane.
-// V is consumed as V^T (K-major B operand), produced by a small transpose kernel per layer.
+//   Eight-softmax-warp variant (default): two threads per query row, and P_j is written back into TENSOR memory over the scores it
+//   came from (tcgen05.st) and consumed by the PV MMA as its A operand -- no shared-memory round trip, no proxy fence.
+// V is consumed as V^T (K-major B operand), written by the QKV GEMM's epilogue (or a small transpose kernel per layer).
 // Measured (B200, large-v3, 64 windows, in the bench step): ~335 TFLOP/s against 245 for the mma.sync kernel it replaces.
 // Per 64-key tile the MMA issuer spends ~430 cycles issuing S, ~430 issuing PV and ~900 waiting for P; a softmax thread
 // spends ~1200 of its ~1950 cycles in tcgen05.ld + FFMA / cvt / MUFU for its 64 scores: with one softmax warp per SM
@@ -122,7 +124,7 @@ __global__ void vt_tail_rows_kernel(T16 * __restrict__ vt, int TP, int n_blocks)
     vt[(b * FA_VROWS + 64 + r) * TP + k] = T16(r == 0 ? 1.0f : 0.0f);
 }
 
-template <typename T16, int SW>
+template <typename T16, int SW, bool PT>
 __global__ void __launch_bounds__(fa_threads(SW), 2)
 enc_attn_tc_kernel(const __grid_constant__ TMap tm_q, const __grid_constant__ TMap tm_k, const __grid_constant__ TMap tm_vt,
                    T16 * __restrict__ out, int T, int d, int H, float scale_log2e, int n_phantom, long long * __restrict__ trace) {
@@ -215,8 +217,12 @@ enc_attn_tc_kernel(const __grid_constant__ TMap tm_q, const __grid_constant__ TM
                 const uint64_t dp = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + FA_OFF_P + s * FA_P_BYTES));
                 const uint64_t dv = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + FA_OFF_V + s * FA_V_BYTES));
 #pragma unroll
-                for (int k = 0; k < 4; ++k)          // 64 keys = four 16-key steps
-                    ptx::umma_f16(tmem + 128u, dp + (uint64_t) (2 * k), dv + (uint64_t) (2 * k), idesc_pv, (uint32_t) (j != 0 || k != 0));
+                for (int k = 0; k < 4; ++k) {        // 64 keys = four 16-key steps
+                    if constexpr (PT)                // P_j sits in tensor memory, in the first 32 columns of S buffer s (8 columns per step)
+                        ptx::umma_f16_ts(tmem + 128u, tmem + (uint32_t) (s * FA_BK + 8 * k), dv + (uint64_t) (2 * k), idesc_pv, (uint32_t) (j != 0 || k != 0));
+                    else
+                        ptx::umma_f16(tmem + 128u, dp + (uint64_t) (2 * k), dv + (uint64_t) (2 * k), idesc_pv, (uint32_t) (j != 0 || k != 0));
+                }
                 ptx::umma_commit(&b_vempty[s]);
                 ptx::umma_commit(&b_pv[s]);
                 FA_STAMP(2, j, 3);
@@ -308,12 +314,22 @@ enc_attn_tc_kernel(const __grid_constant__ TMap tm_q, const __grid_constant__ TM
             // P buffer s is free once PV_{j-2} has read it -- which this thread already knows: the issuer queued S_j behind PV_{j-2},
             // tcgen05 operations of one thread complete in order, and S_j's commit (b_s) was observed at the top of this iteration
             FA_SSTAMP(j, 5);
-            uint8_t * prow = smem + FA_OFF_P + s * FA_P_BYTES + row * 128;
+            if constexpr (PT) {
+                // P_j goes back into tensor memory, over the scores it was computed from: 16-bit pairs, this thread's 32 keys = 16
+                // columns of its lane, keys 0..31 of the tile in columns 0..15 of S buffer s (warp w), keys 32..63 in columns 16..31
+                // (warp w + 4) -- columns the partner warp has finished reading before the exchange barrier above.  The PV MMA takes
+                // it from there as its A operand: no shared-memory round trip, no generic -> async proxy fence.
+                ptx::tmem_st_32x16(t_lane + (uint32_t) (s * FA_BK + half * 16), pk);
+                FA_SSTAMP(j, 6);
+                ptx::tmem_st_wait();
+            } else {
+                uint8_t * prow = smem + FA_OFF_P + s * FA_P_BYTES + row * 128;
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                *reinterpret_cast<uint4 *>(prow + (((half * 4 + q) ^ (row & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-            FA_SSTAMP(j, 6);
-            ptx::fence_proxy_async_smem();           // P was written through the generic proxy; the tensor core reads it through the async one
+                for (int q = 0; q < 4; ++q)
+                    *reinterpret_cast<uint4 *>(prow + (((half * 4 + q) ^ (row & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                FA_SSTAMP(j, 6);
+                ptx::fence_proxy_async_smem();       // P was written through the generic proxy; the tensor core reads it through the async one
+            }
             ptx::tc_fence_before();
             __syncwarp();                            // one arrival per warp (32 arrivals on one word serialise)
             if (lane == 0) ptx::mbar_arrive(&b_p[s]);
@@ -537,17 +553,21 @@ bool enc_attention_tc(DType dt, const void * qkv, void * out, void * vt_scratch,
     long long * trace = fa_trace_slot();
     static const bool sw8 = !(getenv("WHISPER_B200_FA_WARPS") && atoi(getenv("WHISPER_B200_FA_WARPS")) == 4);
     dim3 tgrid(ceil_div(TP, 64), n_head, n_windows), grid(ceil_div(T, FA_BQ), n_head, n_windows);
+    // P is handed to the PV MMA through tensor memory (eight-warp kernel); WHISPER_B200_FA_PTMEM=0: through shared memory
+    static const bool p_tmem = !(getenv("WHISPER_B200_FA_PTMEM") && atoi(getenv("WHISPER_B200_FA_PTMEM")) == 0);
     auto launch = [&](auto tag) {
         using T16 = decltype(tag);
         T16 * o = reinterpret_cast<T16 *>(out);
         static DeviceOnce set;      // function attributes are per device (one guard per instantiation of this lambda = per T16)
         once_per_device(set, [&] {
-            WB_CUDA(cudaFuncSetAttribute(enc_attn_tc_kernel<T16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
-            WB_CUDA(cudaFuncSetAttribute(enc_attn_tc_kernel<T16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+            WB_CUDA(cudaFuncSetAttribute(enc_attn_tc_kernel<T16, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+            WB_CUDA(cudaFuncSetAttribute(enc_attn_tc_kernel<T16, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+            WB_CUDA(cudaFuncSetAttribute(enc_attn_tc_kernel<T16, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
         });
         if (!vt_ready) v_transpose_kernel<T16><<<tgrid, 256, 0, st>>>(reinterpret_cast<const T16 *>(qkv), reinterpret_cast<T16 *>(vt_scratch), T, TP, d, n_head);
-        if (!sw8) enc_attn_tc_kernel<T16, 4><<<grid, fa_threads(4), FA_SMEM, st>>>(tm_q, tm_k, tm_vt, o, T, d, n_head, scale_log2e, n_phantom, trace);
-        else enc_attn_tc_kernel<T16, 8><<<grid, fa_threads(8), FA_SMEM, st>>>(tm_q, tm_k, tm_vt, o, T, d, n_head, scale_log2e, n_phantom, trace);
+        if (!sw8) enc_attn_tc_kernel<T16, 4, false><<<grid, fa_threads(4), FA_SMEM, st>>>(tm_q, tm_k, tm_vt, o, T, d, n_head, scale_log2e, n_phantom, trace);
+        else if (p_tmem) enc_attn_tc_kernel<T16, 8, true><<<grid, fa_threads(8), FA_SMEM, st>>>(tm_q, tm_k, tm_vt, o, T, d, n_head, scale_log2e, n_phantom, trace);
+        else enc_attn_tc_kernel<T16, 8, false><<<grid, fa_threads(8), FA_SMEM, st>>>(tm_q, tm_k, tm_vt, o, T, d, n_head, scale_log2e, n_phantom, trace);
     };
     if (dt == DType::F16) launch(__half{});
     else launch(__nv_bfloat16{});
