@@ -1,6 +1,7 @@
 """Small end-to-end pass over every kernel added in round 2, meant to run under `compute-sanitizer --tool memcheck`:
 tiny model, 3 windows -- greedy + timestamps (float and int16 PCM), "beam search" 5 (device draws, batched history copies,
-grouped cross-attention), temperature fallback, DTW token timestamps, the LayerNorm-folded decoder GEMMs."""
+grouped cross-attention), temperature fallback, DTW token timestamps, the LayerNorm-folded decoder GEMMs; base model, 3 windows --
+the 2-CTA encoder GEMM with its epilogues."""
 import ctypes as C
 import os
 import sys
@@ -53,4 +54,14 @@ with api.Whisper(lib, path, flash_attn=True) as w:
     p.logprob_thold = -0.5
     p.max_tokens = 12
     run("temperature ladder", w, p)
+# base geometry (d = 512): three windows = 4 500 rows, so the encoder GEMMs run on the 2-CTA kernel (cta_group::2 tiles, the two-wide
+# GELU epilogue, the V^T epilogue); the eight-warp attention kernel with P in tensor memory and the mma.sync self-attention run in
+# every pass above as well
+path_b = "/tmp/models/base-1.bin"
+if not os.path.exists(path_b):
+    modelgen.write_model(path_b, "base")
+with api.Whisper(lib, path_b, flash_attn=True) as w:
+    p = w.greedy_params(no_timestamps=True)
+    p.max_tokens = 8
+    run("base greedy", w, p)
 print("sanitize probe done")
