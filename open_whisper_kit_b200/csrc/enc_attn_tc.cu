@@ -43,10 +43,18 @@ constexpr int FA_K_BYTES = FA_BK * 128;                 // 64 keys x 64 x 16-bit
 constexpr int FA_VROWS = FA_DH + 16;
 constexpr int FA_V_BYTES = FA_VROWS * 128;              // [80 rows][64 keys]
 constexpr int FA_P_BYTES = 128 * 128;                   // [128 queries][64 keys]
-constexpr int FA_OFF_Q = 0, FA_OFF_K = FA_Q_BYTES, FA_OFF_V = FA_OFF_K + 2 * FA_K_BYTES, FA_OFF_P = FA_OFF_V + 2 * FA_V_BYTES;
-constexpr int FA_SMEM = FA_OFF_P + 2 * FA_P_BYTES + 1024;   // Q + 2 K + 2 V^T + 2 P + alignment slack = 85 KB: two CTAs per SM
+// K / V^T ring depth: two stages next to the two P buffers; FOUR when P lives in tensor memory (the 32 KB of P buffers become ring
+// stages: a K or V tile comes from DRAM, ~1 400 cycles = one whole tile period away, so with two stages the TMA producer -- which
+// can only ask for K_{j+2} once PV_{j-1} has released its V stage -- delivered just in time at best)
+constexpr int fa_ns(bool pt) { return pt ? 4 : 2; }
+constexpr int FA_OFF_Q = 0, FA_OFF_K = FA_Q_BYTES;
+constexpr int fa_off_v(bool pt) { return FA_OFF_K + fa_ns(pt) * FA_K_BYTES; }
+constexpr int fa_off_p(bool pt) { return fa_off_v(pt) + fa_ns(pt) * FA_V_BYTES; }       // P buffers exist only when !pt
+constexpr int fa_smem(bool pt) { return fa_off_p(pt) + (pt ? 0 : 2 * FA_P_BYTES) + 1024; }
+constexpr int FA_SMEM = fa_smem(true) > fa_smem(false) ? fa_smem(true) : fa_smem(false);   // 85 / 89 KB: two CTAs per SM
 constexpr int FA_TMEM_COLS = 256;                       // S (two buffers): columns 0..63, 64..127; PV: columns 128..207
-static_assert(FA_OFF_P % 1024 == 0 && FA_OFF_V % 1024 == 0, "128-byte swizzle atoms are 1024 bytes");
+static_assert(fa_off_p(false) % 1024 == 0 && fa_off_v(false) % 1024 == 0 && fa_off_v(true) % 1024 == 0 && FA_V_BYTES % 1024 == 0,
+              "128-byte swizzle atoms are 1024 bytes");
 
 __device__ __forceinline__ void fa_wait(uint64_t * bar, uint32_t parity) {       // bounded: a protocol error must trap, not hang
     for (unsigned spins = 0; !ptx::mbar_try_wait(bar, parity); ++spins)
@@ -133,7 +141,10 @@ enc_attn_tc_kernel(const __grid_constant__ TMap tm_q, const __grid_constant__ TM
     // 0 / 4, 2 = the MMA issuer
     const bool tr = trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
 #define FA_STAMP(who, j, i) do { if (tr && (j) < 32) trace[((who) * 32 + (j)) * 8 + (i)] = clock64(); } while (0)
-    __shared__ __align__(8) uint64_t b_q, b_kfull[2], b_kempty[2], b_vfull[2], b_vempty[2], b_s[2], b_p[2], b_pv[2];
+    // Ring stage of tile j: j % NS.  b_s[st] / b_pv[st]: "S_j / PV_j complete" (one tcgen05.commit each), waited for by the softmax
+    // warps (S_j ready, PV_{j-1} landed) AND by the TMA producer (the K / V stage is free again); b_p[j & 1]: P_j published.
+    constexpr int NS = fa_ns(PT), FA_OFF_V = fa_off_v(PT), FA_OFF_P = fa_off_p(PT);
+    __shared__ __align__(8) uint64_t b_q, b_kfull[NS], b_vfull[NS], b_s[NS], b_pv[NS], b_p[2];
     __shared__ uint32_t s_tmem;
     __shared__ float s_hmax[SW == 8 ? 2 : 1][2][128];       // SW == 8: the two threads of a row exchange their half-tile maxima here
     uint8_t * smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -143,14 +154,14 @@ enc_attn_tc_kernel(const __grid_constant__ TMap tm_q, const __grid_constant__ TM
 
     if (threadIdx.x == 0) {
         ptx::mbar_init(&b_q, 1);
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < NS; ++i) {
             ptx::mbar_init(&b_kfull[i], 1);
-            ptx::mbar_init(&b_kempty[i], 1);
             ptx::mbar_init(&b_vfull[i], 1);
-            ptx::mbar_init(&b_vempty[i], 1);
             ptx::mbar_init(&b_s[i], 1);
-            ptx::mbar_init(&b_p[i], SW == 8 ? 8 : SW * 32);      // SW == 8: one arrival per warp
             ptx::mbar_init(&b_pv[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&b_p[i], SW == 8 ? 8 : SW * 32);      // SW == 8: one arrival per warp
         }
         ptx::fence_mbar_init();
     }
@@ -172,13 +183,14 @@ enc_attn_tc_kernel(const __grid_constant__ TMap tm_q, const __grid_constant__ TM
             ptx::mbar_arrive_expect_tx(&b_q, FA_Q_BYTES);
             ptx::tma_load_3d(smem + FA_OFF_Q, &tm_q, &b_q, head * FA_DH, q0, win);
             for (int j = 0; j < n_tiles; ++j) {
-                const int s = j & 1;
-                if (j >= 2) fa_wait(&b_kempty[s], ((j >> 1) - 1) & 1);
-                ptx::mbar_arrive_expect_tx(&b_kfull[s], FA_K_BYTES);
-                ptx::tma_load_3d(smem + FA_OFF_K + s * FA_K_BYTES, &tm_k, &b_kfull[s], d + head * FA_DH, j * FA_BK, win);
-                if (j >= 2) fa_wait(&b_vempty[s], ((j >> 1) - 1) & 1);
-                ptx::mbar_arrive_expect_tx(&b_vfull[s], FA_V_BYTES);
-                ptx::tma_load_3d(smem + FA_OFF_V + s * FA_V_BYTES, &tm_vt, &b_vfull[s], j * FA_BK, 0, win * H + head);
+                const int st = j % NS;
+                const uint32_t prev = (uint32_t) ((j / NS) - 1) & 1u;     // phase of the stage's previous tenant, tile j - NS
+                if (j >= NS) fa_wait(&b_s[st], prev);            // S_{j-NS} complete = K stage st has been read (one commit serves both)
+                ptx::mbar_arrive_expect_tx(&b_kfull[st], FA_K_BYTES);
+                ptx::tma_load_3d(smem + FA_OFF_K + st * FA_K_BYTES, &tm_k, &b_kfull[st], d + head * FA_DH, j * FA_BK, win);
+                if (j >= NS) fa_wait(&b_pv[st], prev);           // PV_{j-NS} complete = V stage st has been read
+                ptx::mbar_arrive_expect_tx(&b_vfull[st], FA_V_BYTES);
+                ptx::tma_load_3d(smem + FA_OFF_V + st * FA_V_BYTES, &tm_vt, &b_vfull[st], j * FA_BK, 0, win * H + head);
             }
         }
     } else if (warp == SW + 1) {
@@ -190,32 +202,40 @@ enc_attn_tc_kernel(const __grid_constant__ TMap tm_q, const __grid_constant__ TM
             const uint32_t idesc_s = ptx::make_idesc_f16(Half16<T16>::kind, 128, FA_BK);
             const uint32_t idesc_pv = ptx::make_idesc_f16(Half16<T16>::kind, 128, FA_VROWS);
             const uint64_t dq = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + FA_OFF_Q));
-            auto issue_s = [&](int j) {
-                const int s = j & 1;
-                fa_wait(&b_kfull[s], (j >> 1) & 1);
+            auto wait_k = [&](int j) {
+                fa_wait(&b_kfull[j % NS], (uint32_t) (j / NS) & 1u);
                 FA_STAMP(2, j, 4);
+            };
+            auto issue_s = [&](int j) {          // K_j has arrived (wait_k)
+                const int s = j & 1, st = j % NS;
                 ptx::tc_fence_after();
-                const uint64_t dk = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + FA_OFF_K + s * FA_K_BYTES));
+                const uint64_t dk = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + FA_OFF_K + st * FA_K_BYTES));
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     ptx::umma_f16(tmem + (uint32_t) (s * FA_BK), dq + (uint64_t) (2 * k), dk + (uint64_t) (2 * k), idesc_s, (uint32_t) (k != 0));
-                ptx::umma_commit(&b_kempty[s]);
-                ptx::umma_commit(&b_s[s]);
+                ptx::umma_commit(&b_s[st]);
                 FA_STAMP(2, j, 5);
             };
             fa_wait(&b_q, 0);
+            wait_k(0);
             issue_s(0);
-            if (n_tiles > 1) issue_s(1);
+            if (n_tiles > 1) {
+                wait_k(1);
+                issue_s(1);
+            }
+            // Per tile this lane issues eight MMAs and two commits, ~65 cycles each as measured (profiles/r4_fa_trace.txt): with the
+            // P hand-off through tensor memory it is this issue sequence, not the softmax warps, that sets the tile period.  So
+            // what does not depend on the softmax warps -- V_j having arrived -- is waited for BEFORE P_j.
             for (int j = 0; j < n_tiles; ++j) {
-                const int s = j & 1;
+                const int s = j & 1, st = j % NS;
                 FA_STAMP(2, j, 0);
-                fa_wait(&b_p[s], (j >> 1) & 1);      // P_j is in shared memory, S_j has been read, the accumulator is consistent
-                FA_STAMP(2, j, 1);
-                fa_wait(&b_vfull[s], (j >> 1) & 1);
+                fa_wait(&b_vfull[st], (uint32_t) (j / NS) & 1u);
                 FA_STAMP(2, j, 2);
+                fa_wait(&b_p[s], (j >> 1) & 1);      // P_j is published, S_j has been read, the accumulator is consistent
+                FA_STAMP(2, j, 1);
                 ptx::tc_fence_after();
                 const uint64_t dp = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + FA_OFF_P + s * FA_P_BYTES));
-                const uint64_t dv = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + FA_OFF_V + s * FA_V_BYTES));
+                const uint64_t dv = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + FA_OFF_V + st * FA_V_BYTES));
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {        // 64 keys = four 16-key steps
                     if constexpr (PT)                // P_j sits in tensor memory, in the first 32 columns of S buffer s (8 columns per step)
@@ -223,10 +243,12 @@ enc_attn_tc_kernel(const __grid_constant__ TMap tm_q, const __grid_constant__ TM
                     else
                         ptx::umma_f16(tmem + 128u, dp + (uint64_t) (2 * k), dv + (uint64_t) (2 * k), idesc_pv, (uint32_t) (j != 0 || k != 0));
                 }
-                ptx::umma_commit(&b_vempty[s]);
-                ptx::umma_commit(&b_pv[s]);
+                ptx::umma_commit(&b_pv[st]);
                 FA_STAMP(2, j, 3);
-                if (j + 2 < n_tiles) issue_s(j + 2);     // S buffer s is free: the softmax warps published P_j after reading it
+                if (j + 2 < n_tiles) {               // S buffer s is free: the softmax warps published P_j after reading it
+                    wait_k(j + 2);
+                    issue_s(j + 2);
+                }
             }
         }
     } else if constexpr (SW == 8) {
@@ -248,7 +270,7 @@ enc_attn_tc_kernel(const __grid_constant__ TMap tm_q, const __grid_constant__ TM
         for (int j = 0; j < n_tiles; ++j) {
             const int s = j & 1;
             FA_SSTAMP(j, 0);
-            fa_wait(&b_s[s], (j >> 1) & 1);
+            fa_wait(&b_s[j % NS], (uint32_t) (j / NS) & 1u);
             FA_SSTAMP(j, 1);
             ptx::tc_fence_after();
             const int key0 = j * FA_BK + half * 32;
@@ -295,7 +317,7 @@ enc_attn_tc_kernel(const __grid_constant__ TMap tm_q, const __grid_constant__ TM
                 m_run = m_new;
                 exp_half(m_run * scale_log2e);
                 if (j > 0) {              // rescale this thread's half of the row's accumulator (+ the row sum); PV_{j-1} must have landed
-                    fa_wait(&b_pv[(j - 1) & 1], ((j - 1) >> 1) & 1);
+                    fa_wait(&b_pv[(j - 1) % NS], (uint32_t) ((j - 1) / NS) & 1u);
                     ptx::tc_fence_after();
                     uint32_t o[32];
                     ptx::tmem_ld_32x32(t_lane + 128u + (uint32_t) (half * 32), o);
@@ -336,7 +358,7 @@ enc_attn_tc_kernel(const __grid_constant__ TMap tm_q, const __grid_constant__ TM
             FA_SSTAMP(j, 7);
         }
         // O and the row sum l (column 64: the ones row of V^T) sit in TMEM, both relative to m_run
-        fa_wait(&b_pv[(n_tiles - 1) & 1], ((n_tiles - 1) >> 1) & 1);
+        fa_wait(&b_pv[(n_tiles - 1) % NS], (uint32_t) ((n_tiles - 1) / NS) & 1u);
         ptx::tc_fence_after();
         float l = __uint_as_float(ptx::tmem_ld_32x1(t_lane + 128u + 64u)), f = 1.0f;
         ptx::tmem_ld_wait();
@@ -377,7 +399,7 @@ enc_attn_tc_kernel(const __grid_constant__ TMap tm_q, const __grid_constant__ TM
 #pragma unroll 1
         for (int j = 0; j < n_tiles; ++j) {
             const int s = j & 1;
-            fa_wait(&b_s[s], (j >> 1) & 1);
+            fa_wait(&b_s[j % NS], (uint32_t) (j / NS) & 1u);
             ptx::tc_fence_after();
             const int key0 = j * FA_BK;
             const bool edge = key0 + FA_BK > T;
@@ -421,7 +443,7 @@ enc_attn_tc_kernel(const __grid_constant__ TMap tm_q, const __grid_constant__ TM
                 m_run = m_new;
                 exp_tile(m_run * scale_log2e, false);
                 if (j > 0) {              // rescale this row's accumulator (64 values + the row sum); PV_{j-1} must have landed
-                    fa_wait(&b_pv[(j - 1) & 1], ((j - 1) >> 1) & 1);
+                    fa_wait(&b_pv[(j - 1) % NS], (uint32_t) ((j - 1) / NS) & 1u);
                     ptx::tc_fence_after();
 #pragma unroll 1
                     for (int c = 0; c < 2; ++c) {
@@ -439,7 +461,7 @@ enc_attn_tc_kernel(const __grid_constant__ TMap tm_q, const __grid_constant__ TM
                 }
             }
             // P buffer s is free once PV_{j-2} has read it
-            if (j >= 2) fa_wait(&b_pv[s], ((j >> 1) - 1) & 1);
+            if (j >= 2) fa_wait(&b_pv[(j - 2) % NS], (uint32_t) ((j - 2) / NS) & 1u);
             uint8_t * prow = smem + FA_OFF_P + s * FA_P_BYTES + row * 128;
 #pragma unroll
             for (int q = 0; q < 8; ++q)
@@ -449,7 +471,7 @@ enc_attn_tc_kernel(const __grid_constant__ TMap tm_q, const __grid_constant__ TM
             ptx::mbar_arrive(&b_p[s]);
         }
         // O and the row sum l (column 64: the ones row of V^T) sit in TMEM, both relative to m_run
-        fa_wait(&b_pv[(n_tiles - 1) & 1], ((n_tiles - 1) >> 1) & 1);
+        fa_wait(&b_pv[(n_tiles - 1) % NS], (uint32_t) ((n_tiles - 1) / NS) & 1u);
         ptx::tc_fence_after();
         float l = __uint_as_float(ptx::tmem_ld_32x1(t_lane + 128u + 64u)), f = 1.0f;
         ptx::tmem_ld_wait();
