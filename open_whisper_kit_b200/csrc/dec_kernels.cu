@@ -15,6 +15,8 @@
 
 #include <stdlib.h>
 
+#include <type_traits>
+
 namespace cg = cooperative_groups;
 
 namespace wb {
@@ -435,7 +437,12 @@ __device__ __forceinline__ void cb_wait(uint64_t * bar, uint32_t parity) {      
 
 // NQ > 1: one CTA serves up to NQ consecutive decoder rows that attend to the SAME window (the tokens of a prompt, the beams of
 // a beam search): the K / V stream is read once for all of them.  Per row the arithmetic is exactly the NQ = 1 arithmetic.
-template <typename T16, int NQ>
+// KM: the scores of the K sweep on mma.sync fragments (as self_attn_mma_kernel): a warp takes 16 consecutive keys of a chunk, its
+// lanes' 16-byte shared-memory loads of two key rows are the A registers, the (up to eight) queries of the CTA are the columns of B
+// -- one MMA chain per 16 keys whatever NQ is.  The V sweep stays on CUDA cores (a transposing read of the unswizzled [key][64]
+// chunk would be four-way bank-conflicted).  With one CTA per SM (8 sequences per GPU) the kernel is bound by its own instruction
+// stream, not by the K/V bytes: ~46 instructions per (4 keys x 8 lanes) in the K sweep become ~6.
+template <typename T16, int NQ, bool KM>
 __global__ void __launch_bounds__(CB_THREADS, 2)
 cross_attn_bulk_kernel(const T16 * __restrict__ q, int ldq, const DecRow * __restrict__ rows, const int2 * __restrict__ groups, int d,
                        size_t layer_off, int T, float kq_scale, int n_phantom, T16 * __restrict__ out, int evict_first) {
@@ -494,6 +501,52 @@ cross_attn_bulk_kernel(const T16 * __restrict__ q, int ldq, const DecRow * __res
 
     // ===== compute warps =====
     pdl_wait();
+    auto sync_compute = [] { asm volatile("bar.sync 1, %0;" ::"n"(CB_WARPS * 32) : "memory"); };
+    float mx[NQ];
+#pragma unroll
+    for (int qi = 0; qi < NQ; ++qi) mx[qi] = -INFINITY;
+    if constexpr (KM) {
+        static_assert(NQ <= 8, "the queries of a CTA are the eight columns of the B fragment");
+        const int g8 = lane >> 2, t4 = lane & 3;
+        // B: query g8 of the CTA (zeros beyond nq), dims 8 t4 .. and 32 + 8 t4 .. -- the same dims -> k assignment as the A loads below
+        uint32_t Q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (g8 < nq) {
+            const T16 * qrow = q + (size_t) (r0 + g8) * ldq + h * 64;
+            const uint4 qx = *reinterpret_cast<const uint4 *>(qrow + t4 * 8), qy = *reinterpret_cast<const uint4 *>(qrow + 32 + t4 * 8);
+            Q[0] = qx.x; Q[1] = qx.y; Q[2] = qx.z; Q[3] = qx.w; Q[4] = qy.x; Q[5] = qy.y; Q[6] = qy.z; Q[7] = qy.w;
+        }
+        float m0 = -INFINITY, m1 = -INFINITY;          // running maxima of queries 2 t4 and 2 t4 + 1 over this lane's key rows
+        const int qa = 2 * t4, qb = 2 * t4 + 1;
+        for (int c = 0; c < nck; ++c) {
+            const int s = c % CB_STAGES;
+            cb_wait(&b_full[s], (c / CB_STAGES) & 1);
+            const uint8_t * stage = cb_smem + s * CB_CHUNK;
+            const int kl = warp * 16 + g8, ta = c * CB_KEYS + kl, tb = ta + 8;
+            const uint4 z = make_uint4(0, 0, 0, 0);
+            const uint4 xa = ta < T ? *reinterpret_cast<const uint4 *>(stage + kl * 128 + t4 * 16) : z;
+            const uint4 ya = ta < T ? *reinterpret_cast<const uint4 *>(stage + kl * 128 + 64 + t4 * 16) : z;
+            const uint4 xb = tb < T ? *reinterpret_cast<const uint4 *>(stage + (kl + 8) * 128 + t4 * 16) : z;
+            const uint4 yb = tb < T ? *reinterpret_cast<const uint4 *>(stage + (kl + 8) * 128 + 64 + t4 * 16) : z;
+            const uint32_t Ra[8] = {xa.x, xa.y, xa.z, xa.w, ya.x, ya.y, ya.z, ya.w};
+            const uint32_t Rb[8] = {xb.x, xb.y, xb.z, xb.w, yb.x, yb.y, yb.z, yb.w};
+            float cc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mma_16816<T16>(cc, Ra[2 * k], Rb[2 * k], Ra[2 * k + 1], Rb[2 * k + 1], Q[2 * k], Q[2 * k + 1]);
+            // cc[0] / cc[1]: key ta x queries qa / qb; cc[2] / cc[3]: key tb
+            if (qa < nq) {
+                if (ta < T) { const float v = cc[0] * kq_scale; s_sc[qa * T_pad + ta] = v; m0 = fmaxf(m0, v); }
+                if (tb < T) { const float v = cc[2] * kq_scale; s_sc[qa * T_pad + tb] = v; m0 = fmaxf(m0, v); }
+            }
+            if (NQ > 1 && qb < nq) {
+                if (ta < T) { const float v = cc[1] * kq_scale; s_sc[qb * T_pad + ta] = v; m1 = fmaxf(m1, v); }
+                if (tb < T) { const float v = cc[3] * kq_scale; s_sc[qb * T_pad + tb] = v; m1 = fmaxf(m1, v); }
+            }
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t) __cvta_generic_to_shared(&b_empty[s])) : "memory");
+        }
+#pragma unroll
+        for (int qi = 0; qi < NQ; ++qi) mx[qi] = qi == qa ? m0 : (qi == qb ? m1 : -INFINITY);
+    } else {
     float qv[NQ][8];
 #pragma unroll
     for (int qi = 0; qi < NQ; ++qi) {
@@ -502,10 +555,6 @@ cross_attn_bulk_kernel(const T16 * __restrict__ q, int ldq, const DecRow * __res
 #pragma unroll
         for (int j = 0; j < 8; ++j) qv[qi][j] = Half16<T16>::to_f(e[j]);
     }
-    auto sync_compute = [] { asm volatile("bar.sync 1, %0;" ::"n"(CB_WARPS * 32) : "memory"); };
-    float mx[NQ];
-#pragma unroll
-    for (int qi = 0; qi < NQ; ++qi) mx[qi] = -INFINITY;
     for (int c = 0; c < nck; ++c) {
         const int s = c % CB_STAGES;
         cb_wait(&b_full[s], (c / CB_STAGES) & 1);
@@ -537,6 +586,7 @@ cross_attn_bulk_kernel(const T16 * __restrict__ q, int ldq, const DecRow * __res
         }
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t) __cvta_generic_to_shared(&b_empty[s])) : "memory");
+    }
     }
     pdl_trigger();
 #pragma unroll
@@ -1394,33 +1444,32 @@ void dec_cross_attn(DType dt, const void * q, const DecRow * d_rows, int R, int 
     if (bulk && !q_split) {
         const int nq = (d_groups && n_groups > 0) ? CBQ_MAX : 1;
         const size_t bsmem = (size_t) CB_STAGES * CB_CHUNK + (size_t) nq * ((T + 31) & ~31) * sizeof(float);
-        static DeviceOnce set;      // function attributes are per device
-        once_per_device(set, [&] {
-            WB_CUDA(cudaFuncSetAttribute(cross_attn_bulk_kernel<__half, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            WB_CUDA(cudaFuncSetAttribute(cross_attn_bulk_kernel<__nv_bfloat16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            WB_CUDA(cudaFuncSetAttribute(cross_attn_bulk_kernel<__half, CBQ_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            WB_CUDA(cudaFuncSetAttribute(cross_attn_bulk_kernel<__nv_bfloat16, CBQ_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        });
+        // the K sweep's scores run on mma.sync fragments (template parameter KM); WHISPER_B200_CROSS_MMA=0: on CUDA cores
+        static const bool k_mma = !(getenv("WHISPER_B200_CROSS_MMA") && atoi(getenv("WHISPER_B200_CROSS_MMA")) == 0);
         if (bsmem <= 100 * 1024) {
             static const int evict_first = !(getenv("WHISPER_B200_CROSS_EVICT") && atoi(getenv("WHISPER_B200_CROSS_EVICT")) == 0);
             const dim3 g(nq > 1 ? n_groups : R, n_head);
-            const __half * qh = reinterpret_cast<const __half *>(q);
-            const __nv_bfloat16 * qb = reinterpret_cast<const __nv_bfloat16 *>(q);
-            if (dt == DType::F16) {
-                if (nq > 1)
-                    launch_pdl(cross_attn_bulk_kernel<__half, CBQ_MAX>, g, dim3(CB_THREADS), bsmem, st, qh, d, d_rows, d_groups, d, layer_off_elems,
-                               T, kq_scale, n_phantom, reinterpret_cast<__half *>(out), evict_first);
-                else
-                    launch_pdl(cross_attn_bulk_kernel<__half, 1>, g, dim3(CB_THREADS), bsmem, st, qh, d, d_rows, d_groups, d, layer_off_elems, T,
-                               kq_scale, n_phantom, reinterpret_cast<__half *>(out), evict_first);
-            } else {
-                if (nq > 1)
-                    launch_pdl(cross_attn_bulk_kernel<__nv_bfloat16, CBQ_MAX>, g, dim3(CB_THREADS), bsmem, st, qb, d, d_rows, d_groups, d,
-                               layer_off_elems, T, kq_scale, n_phantom, reinterpret_cast<__nv_bfloat16 *>(out), evict_first);
-                else
-                    launch_pdl(cross_attn_bulk_kernel<__nv_bfloat16, 1>, g, dim3(CB_THREADS), bsmem, st, qb, d, d_rows, d_groups, d, layer_off_elems,
-                               T, kq_scale, n_phantom, reinterpret_cast<__nv_bfloat16 *>(out), evict_first);
-            }
+            auto launch = [&](auto tag, auto nq_tag, auto km_tag) {
+                using T16 = decltype(tag);
+                constexpr int NQ_ = decltype(nq_tag)::value;
+                constexpr bool KM_ = decltype(km_tag)::value;
+                static DeviceOnce set;      // function attributes are per device (one guard per instantiation)
+                once_per_device(set, [&] {
+                    WB_CUDA(cudaFuncSetAttribute(cross_attn_bulk_kernel<T16, NQ_, KM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                });
+                launch_pdl(cross_attn_bulk_kernel<T16, NQ_, KM_>, g, dim3(CB_THREADS), bsmem, st, reinterpret_cast<const T16 *>(q), d, d_rows, d_groups, d,
+                           layer_off_elems, T, kq_scale, n_phantom, reinterpret_cast<T16 *>(out), evict_first);
+            };
+            auto by_nq = [&](auto tag, auto km_tag) {
+                if (nq > 1) launch(tag, std::integral_constant<int, CBQ_MAX>{}, km_tag);
+                else launch(tag, std::integral_constant<int, 1>{}, km_tag);
+            };
+            auto by_km = [&](auto tag) {
+                if (k_mma) by_nq(tag, std::true_type{});
+                else by_nq(tag, std::false_type{});
+            };
+            if (dt == DType::F16) by_km(__half{});
+            else by_km(__nv_bfloat16{});
             WB_CUDA(cudaGetLastError());
             return;
         }
